@@ -1,0 +1,173 @@
+/* signerf_b200 — C ABI of the B200-native SIGNeRF reference-sheet hot path.
+ *
+ * The reference (cgtuebingen/SIGNeRF) has NO FFI: its hot path is Python calling nerfstudio
+ * (SURVEY.md §8b).  Every entry point below therefore cites the reference *Python* interface
+ * it replaces; the binding a maintainer adds on the reference side is the ctypes stub shown
+ * in INTEGRATION.md (mirrored by signerf_b200/_lib.py).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross the boundary;
+ *   - every `d_` pointer is DEVICE memory owned by the caller, every `h_` pointer HOST memory;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - return value: SGN_OK (0) or a negative SgnStatus; sgn_last_error() gives the message of
+ *     the last failure on the calling thread.  Nothing throws across the ABI;
+ *   - the library allocates only inside opaque handles (sgn_*_create / sgn_*_destroy);
+ *   - re-entrant per handle; safe to call from a non-main Python thread.
+ */
+#ifndef SIGNERF_B200_H
+#define SIGNERF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum SgnStatus {
+  SGN_OK = 0,
+  SGN_ERR_INVALID_ARG = -1,
+  SGN_ERR_UNSUPPORTED = -2, /* architecture/shape the sm_100a kernels are not specialised for */
+  SGN_ERR_CUDA = -3,
+  SGN_ERR_NO_DEVICE = -4
+} SgnStatus;
+
+const char* sgn_last_error(void);
+/* ABI version; bumped on any signature change. */
+int sgn_abi_version(void);
+/* Number of kernel launches issued by this library on the calling process so far
+ * (bench.py reports the delta over the timed region as `gpu_launches`). */
+uint64_t sgn_launch_count(void);
+
+/* ------------------------------------------------------------------ field (A4/A5) */
+/* One multiresolution hash grid = nerfstudio HashEncoding, torch-fallback semantics
+ * (always hashed, floor/ceil corners, primes {1, 2654435761, 805459861}).               */
+typedef struct SgnHashGrid {
+  const float* d_table;    /* [num_levels * 2^log2_size, 2] fp32, caller-owned, kept by reference */
+  const float* h_scalings; /* [num_levels] per-level resolution, EXACTLY the fp32 values of
+                              HashEncoding.scalings (never recomputed here)      */
+  int num_levels;          /* <= 16 */
+  int log2_size;           /* table rows per level = 2^log2_size */
+} SgnHashGrid;
+
+/* nn.Linear: y = W x + b, W row-major [out_dim, in_dim], host fp32. */
+typedef struct SgnLinear {
+  const float* h_weight;
+  const float* h_bias;
+  int in_dim, out_dim;
+} SgnLinear;
+
+/* nerfacto field + proposal networks (nerfstudio fields/nerfacto_field.py, density_fields.py)
+ * as SIGNeRFModel(NerfactoModel) holds them (reference signerf/signerf.py:27-39).            */
+typedef struct SgnFieldDesc {
+  SgnHashGrid grid;           /* main: 16 levels, 2^19, F=2 */
+  SgnLinear base[2];          /* 32->64->16 (ReLU between, no out activation) */
+  SgnLinear head[3];          /* 63->64->64->3 (ReLU, Sigmoid); input = [SH16, geo15, app32] */
+  const float* h_appearance;  /* [32] mean appearance embedding used in eval */
+  float average_init_density; /* SIGNeRF: 0.01 (signerf_config.py:35) */
+  int num_proposals;          /* 0 (flat mode only) or 2 */
+  SgnHashGrid prop_grid[2];
+  SgnLinear prop_mlp[2][2];   /* 10->16->1 each */
+} SgnFieldDesc;
+
+typedef struct SgnField SgnField;
+int sgn_field_create(const SgnFieldDesc* desc, SgnField** out);
+void sgn_field_destroy(SgnField* f);
+
+/* ------------------------------------------------------------------ K1: render (A1-A6) */
+#define SGN_MLP_FP16_MMA 0 /* fp16 mma.sync tensor-core MLP, fp32 accumulate (fast path)  */
+#define SGN_MLP_FP32 1     /* fp32 CUDA-core MLP (parity / debugging path)                  */
+
+typedef struct SgnRenderOpts {
+  float near_plane, far_plane; /* NearFarCollider(0.05, 1000) */
+  int mode;                    /* 0 = flat: S piecewise-lin-disp bins straight into the main field;
+                                  1 = cascade: ProposalNetworkSampler 256 -> 96 -> 48            */
+  int num_samples;             /* flat: S;  cascade: samples into the main field (48)            */
+  int num_prop_samples[2];     /* cascade only: {256, 96}                                        */
+  int mlp_mode;                /* SGN_MLP_* */
+  const float* h_bins;         /* optional [S+1] (flat) / [num_prop_samples[0]+1] (cascade) EUCLIDEAN
+                                  bin edges shared by all rays, computed by the host with the same
+                                  torch expression the reference uses; NULL = computed in-library */
+} SgnRenderOpts;
+
+/* Replaces, for V views at once, reference `DatasetGenerator.render_camera`'s
+ *   camera.generate_rays(camera_indices=0, ...)            datasetgenerator.py:691
+ *   graph.get_outputs_for_camera_ray_bundle(bundle)        datasetgenerator.py:694
+ * and returns the two outputs it consumes (:700-701) plus accumulation.
+ *   d_c2w  [V,3,4] camera-to-world, d_intr [V,4] = fx,fy,cx,cy   (device)
+ *   d_rgb  [V,H,W,3], d_depth [V,H,W,1], d_acc [V,H,W,1] or NULL (device)
+ * Ray id inside a view is y*W + x (row-major), pixel centres at +0.5.                        */
+int sgn_render_views(const SgnField* f, const float* d_c2w, const float* d_intr, int V, int H, int W,
+                     const SgnRenderOpts* opts, float* d_rgb, float* d_depth, float* d_acc, void* stream);
+
+/* Same call with HOST buffers: H2D of the cameras and D2H of the images happen inside
+ * (this is the end-to-end entry bench.py times as `e2e`).                                    */
+int sgn_render_views_host(const SgnField* f, const float* h_c2w, const float* h_intr, int V, int H, int W,
+                          const SgnRenderOpts* opts, float* h_rgb, float* h_depth, float* h_acc);
+
+/* Ray generation only (A2): nerfstudio Cameras.generate_rays semantics.
+ *   d_origins/d_directions [V,H,W,3]; d_pixel_area/d_dir_norm [V,H,W,1] or NULL.             */
+int sgn_generate_rays(const float* d_c2w, const float* d_intr, int V, int H, int W, float* d_origins,
+                      float* d_directions, float* d_pixel_area, float* d_dir_norm, void* stream);
+
+/* Hash-grid probe (A4) for parity tests: positions already in [0,1]^3.
+ *   which: 0 = main grid, 1/2 = proposal grid 0/1
+ *   d_indices [N, L, 8] int64 table rows (corner order of HashEncoding.pytorch_fwd), or NULL
+ *   d_features [N, 2L] fp32 trilinear features, or NULL                                       */
+int sgn_hash_encode(const SgnField* f, int which, const float* d_positions01, int64_t N,
+                    int64_t* d_indices, float* d_features, void* stream);
+
+/* Field probe (A5) for parity tests: world-space positions + unit directions ->
+ * d_density [N], d_rgb [N,3] with the selected MLP mode.                                      */
+int sgn_field_eval(const SgnField* f, const float* d_positions, const float* d_directions, int64_t N,
+                   int mlp_mode, float* d_density, float* d_rgb, void* stream);
+
+/* ------------------------------------------------------------------ K2/K3: mask + condition (A7-A9) */
+typedef struct SgnMaskOpts {
+  float aabb[6];           /* min xyz, max xyz (DatasetGenerator.aabb) */
+  int inverse_mask;        /* DatasetGeneratorConfig.inverse_mask */
+  int dilate_w, dilate_h;  /* mask_dialation (50,50); 0,0 = none. cv2 MORPH_ELLIPSE semantics */
+  float depth_radius;      /* additional_depth_radius (0.1) */
+  int use_manual_depth;    /* manual_depth is not None */
+  float manual_min, manual_max;
+} SgnMaskOpts;
+
+/* Replaces reference render_camera's masking_mode == "aabb" branch, datasetgenerator.py:758-818
+ * (intersect_with_aabb utils/intersection.py:5-56, cv2.dilate :775-778, min/max :786-792,
+ * condition :809-810, not-visible zeros :813-818) for V views without any host round trip.
+ *   d_depth [V,H,W,1] in; d_mask [V,H,W,1] uint8 0/1 out; d_cond [V,H,W,1] fp32 out
+ *   d_stats [V,4] fp32 out or NULL: {is_visible, min_depth, max_depth, visible_count}         */
+int sgn_mask_condition(const float* d_c2w, const float* d_intr, int V, int H, int W, const float* d_depth,
+                       const SgnMaskOpts* opts, uint8_t* d_mask, float* d_cond, float* d_stats,
+                       void* stream);
+
+/* cv2.dilate(mask, getStructuringElement(MORPH_ELLIPSE, (kw, kh))) > 0 on V binary images.    */
+int sgn_dilate_ellipse(const uint8_t* d_in, int V, int H, int W, int kw, int kh, uint8_t* d_out,
+                       void* stream);
+
+/* ------------------------------------------------------------------ K4: sheet (A10, A14) */
+/* F.interpolate(bilinear, align_corners=False) of V tiles [V,H,W,C] to (h,w) and paste of tile v
+ * at grid cell (v0+v) of a rows x cols sheet with `border` px between tiles
+ * (datasetgenerator.py:526-539, :633-646).  threshold >= 0: write (value > threshold) as 0/1
+ * (the mask path, `> 0.5`).  src_u8: source is uint8 0/1 (mask) instead of fp32.               */
+int sgn_sheet_paste(const void* d_src, int src_u8, int V, int H, int W, int C, float* d_sheet,
+                    int sheet_h, int sheet_w, int rows, int cols, int border, int tile_h, int tile_w,
+                    int first_cell, float threshold, void* stream);
+
+/* Inverse: cut tile `cell` out of the sheet and bilinear-resize to (H,W) (datasetgenerator.py:570-585,
+ * :652-659), optionally blending `edited*mask + base*(1-mask)` first (:562, :656).             */
+int sgn_sheet_cut(const float* d_sheet, int sheet_h, int sheet_w, int C, int rows, int cols, int border,
+                  int tile_h, int tile_w, int cell, float* d_out, int H, int W, void* stream);
+
+/* out = edited*mask + base*(1-mask), mask [npix] broadcast over C channels
+ * (datasetgenerator.py:562 sheet blend, :656 tile blend).                                     */
+int sgn_blend_masked(const float* d_edited, const float* d_base, const float* d_mask, int64_t npix, int C,
+                     float* d_out, void* stream);
+
+/* tensor_to_image quantisation (utils/image_tensor_converter.py:22-23,29-30):
+ * uint8(x*255) by truncation with wrap-around, exactly numpy's float32 -> uint8 cast.          */
+int sgn_quantize_u8(const float* d_in, int64_t n, uint8_t* d_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIGNERF_B200_H */

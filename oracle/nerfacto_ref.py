@@ -1,0 +1,473 @@
+"""ORACLE (test infrastructure, NOT product code) — CPU/PyTorch fp32 restatement of the
+nerfstudio==1.0.2 `implementation="torch"` nerfacto eval path that SIGNeRF's
+`DatasetGenerator.render_camera` drives (reference call sites:
+signerf/datasetgenerator/datasetgenerator.py:691 `camera.generate_rays(...)` and :694
+`graph.get_outputs_for_camera_ray_bundle(...)`; only outputs["rgb"] / outputs["depth"] are
+consumed, :700-701).
+
+PARITY UNPINNED for this file: nerfstudio 1.0.2 (pyproject.toml:6 of the reference) is a
+third-party dependency whose source is absent from /root/reference and is not installable
+here (no wheel, no network), and the reference ships no tests / golden vectors for this
+path.  The algorithm below restates the published nerfstudio 1.0.x
+code (cameras/cameras.py, cameras/rays.py, model_components/{scene_colliders,ray_samplers,
+renderers}.py, field_components/{spatial_distortions,encodings,mlp,activations}.py,
+fields/{nerfacto_field,density_fields}.py, models/nerfacto.py) op-for-op in fp32 so that
+torch's own rounding order is preserved.  Pieces of the path that DO live in
+/root/reference (AABB slab test, pose generator, uint8 quantisation, cv2 dilation) are
+pinned separately in oracle/sheet_ref.py against fixtures generated from the reference.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
+import this module.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+from torch import Tensor, nn
+
+HASH_PRIMES = (1, 2654435761, 805459861)  # nerfstudio encodings.py HashEncoding.hash_fn
+
+
+# --------------------------------------------------------------------------- field params
+def hash_scalings(num_levels: int, min_res: int, max_res: int) -> Tensor:
+    """HashEncoding.__init__: `torch.floor(min_res * growth_factor ** levels)`.
+
+    growth_factor is a numpy float64 scalar and `levels` an int64 tensor, so the power is
+    evaluated in torch's default dtype (float32) — 16 levels 16→2048 end at 2047, not 2048
+    (SURVEY.md §7 "fp32 scalings quirk").  Never recompute this elsewhere: pass this table.
+    """
+    levels = torch.arange(num_levels)
+    growth = np.exp((np.log(max_res) - np.log(min_res)) / (num_levels - 1)) if num_levels > 1 else 1
+    return torch.floor(min_res * growth**levels)
+
+
+class HashEncodingRef(nn.Module):
+    """nerfstudio HashEncoding, torch fallback (`pytorch_fwd`)."""
+
+    def __init__(self, num_levels=16, min_res=16, max_res=2048, log2_hashmap_size=19,
+                 features_per_level=2, hash_init_scale=1e-3):
+        super().__init__()
+        self.num_levels = num_levels
+        self.features_per_level = features_per_level
+        self.hash_table_size = 2**log2_hashmap_size
+        self.register_buffer("scalings", hash_scalings(num_levels, min_res, max_res))
+        self.hash_offset = torch.arange(num_levels) * self.hash_table_size
+        table = torch.rand(size=(self.hash_table_size * num_levels, features_per_level)) * 2 - 1
+        table *= hash_init_scale
+        self.hash_table = nn.Parameter(table)
+
+    def get_out_dim(self) -> int:
+        return self.num_levels * self.features_per_level
+
+    def hash_fn(self, in_tensor: Tensor) -> Tensor:
+        # int32 * int64 tensor -> int64 (type promotion); xor; python-style modulo; level offset
+        in_tensor = in_tensor * torch.tensor(HASH_PRIMES).to(in_tensor.device)
+        x = torch.bitwise_xor(in_tensor[..., 0], in_tensor[..., 1])
+        x = torch.bitwise_xor(x, in_tensor[..., 2])
+        x %= self.hash_table_size
+        x += self.hash_offset.to(x.device)
+        return x
+
+    def corner_indices(self, in_tensor: Tensor) -> Tuple[Tensor, Tensor]:
+        """Return ([...,L,8] int64 table rows, [...,L,3] trilinear offsets) for positions in [0,1]."""
+        in_tensor = in_tensor[..., None, :]
+        scaled = in_tensor * self.scalings.view(-1, 1).to(in_tensor.device)
+        scaled_c = torch.ceil(scaled).type(torch.int32)
+        scaled_f = torch.floor(scaled).type(torch.int32)
+        offset = scaled - scaled_f
+        c, f = scaled_c, scaled_f
+
+        def pick(a, b, d):
+            return torch.cat([a[..., 0:1], b[..., 1:2], d[..., 2:3]], dim=-1)
+
+        hashed = [
+            self.hash_fn(c),               # 0: c c c
+            self.hash_fn(pick(c, f, c)),   # 1: c f c
+            self.hash_fn(pick(f, f, c)),   # 2: f f c
+            self.hash_fn(pick(f, c, c)),   # 3: f c c
+            self.hash_fn(pick(c, c, f)),   # 4: c c f
+            self.hash_fn(pick(c, f, f)),   # 5: c f f
+            self.hash_fn(f),               # 6: f f f
+            self.hash_fn(pick(f, c, f)),   # 7: f c f
+        ]
+        return torch.stack(hashed, dim=-1), offset
+
+    def forward(self, in_tensor: Tensor) -> Tensor:
+        assert in_tensor.shape[-1] == 3
+        hashed, offset = self.corner_indices(in_tensor)
+        f = [self.hash_table[hashed[..., i]] for i in range(8)]  # each [..., L, F]
+        ox, oy, oz = offset[..., 0:1], offset[..., 1:2], offset[..., 2:3]
+        f_03 = f[0] * ox + f[3] * (1 - ox)
+        f_12 = f[1] * ox + f[2] * (1 - ox)
+        f_56 = f[5] * ox + f[6] * (1 - ox)
+        f_47 = f[4] * ox + f[7] * (1 - ox)
+        f0312 = f_03 * oy + f_12 * (1 - oy)
+        f4756 = f_47 * oy + f_56 * (1 - oy)
+        encoded = f0312 * oz + f4756 * (1 - oz)
+        return torch.flatten(encoded, start_dim=-2, end_dim=-1)
+
+
+class MLPRef(nn.Module):
+    """nerfstudio field_components/mlp.py MLP, torch path: biased nn.Linear, ReLU between."""
+
+    def __init__(self, in_dim: int, num_layers: int, layer_width: int, out_dim: int,
+                 out_activation: Optional[nn.Module] = None):
+        super().__init__()
+        dims = [in_dim] + [layer_width] * (num_layers - 1) + [out_dim]
+        self.layers = nn.ModuleList(nn.Linear(dims[i], dims[i + 1]) for i in range(num_layers))
+        self.out_activation = out_activation
+
+    def forward(self, x: Tensor) -> Tensor:
+        for i, layer in enumerate(self.layers):
+            x = layer(x)
+            if i < len(self.layers) - 1:
+                x = torch.relu(x)
+        if self.out_activation is not None:
+            x = self.out_activation(x)
+        return x
+
+
+def contract_linf(x: Tensor) -> Tensor:
+    """SceneContraction(order=inf).forward."""
+    mag = torch.linalg.norm(x, ord=float("inf"), dim=-1)[..., None]
+    return torch.where(mag < 1, x, (2 - (1 / mag)) * (x / mag))
+
+
+def sh_components_deg4(directions: Tensor) -> Tensor:
+    """nerfstudio utils/math.py components_from_spherical_harmonics(levels=4)."""
+    components = torch.zeros((*directions.shape[:-1], 16), device=directions.device)
+    x, y, z = directions[..., 0], directions[..., 1], directions[..., 2]
+    xx, yy, zz = x**2, y**2, z**2
+    components[..., 0] = 0.28209479177387814
+    components[..., 1] = 0.4886025119029199 * y
+    components[..., 2] = 0.4886025119029199 * z
+    components[..., 3] = 0.4886025119029199 * x
+    components[..., 4] = 1.0925484305920792 * x * y
+    components[..., 5] = 1.0925484305920792 * y * z
+    components[..., 6] = 0.9461746957575601 * zz - 0.31539156525251999
+    components[..., 7] = 1.0925484305920792 * x * z
+    components[..., 8] = 0.5462742152960396 * (xx - yy)
+    components[..., 9] = 0.5900435899266435 * y * (3 * xx - yy)
+    components[..., 10] = 2.890611442640554 * x * y * z
+    components[..., 11] = 0.4570457994644658 * y * (5 * zz - 1)
+    components[..., 12] = 0.3731763325901154 * z * (5 * zz - 3)
+    components[..., 13] = 0.4570457994644658 * x * (5 * zz - 1)
+    components[..., 14] = 1.445305721320277 * z * (xx - yy)
+    components[..., 15] = 0.5900435899266435 * x * (xx - 3 * yy)
+    return components
+
+
+class DensityFieldRef(nn.Module):
+    """fields/density_fields.py HashMLPDensityField (use_linear=False): proposal network."""
+
+    def __init__(self, num_levels=5, max_res=128, base_res=16, log2_hashmap_size=17,
+                 features_per_level=2, hidden_dim=16, num_layers=2, average_init_density=1.0):
+        super().__init__()
+        self.average_init_density = average_init_density
+        self.encoding = HashEncodingRef(num_levels, base_res, max_res, log2_hashmap_size, features_per_level)
+        self.mlp = MLPRef(self.encoding.get_out_dim(), num_layers, hidden_dim, 1)
+
+    def density(self, positions: Tensor) -> Tensor:
+        positions = contract_linf(positions)
+        positions = (positions + 2.0) / 4.0
+        selector = ((positions > 0.0) & (positions < 1.0)).all(dim=-1)
+        positions = positions * selector[..., None]
+        h = self.mlp(self.encoding(positions.view(-1, 3))).view(*positions.shape[:-1], -1)
+        density = self.average_init_density * torch.exp(h)  # trunc_exp forward == exp
+        return density * selector[..., None]
+
+
+class NerfactoFieldRef(nn.Module):
+    """fields/nerfacto_field.py NerfactoField, eval, no normals / transients / semantics."""
+
+    def __init__(self, num_images=30, num_levels=16, base_res=16, max_res=2048, log2_hashmap_size=19,
+                 features_per_level=2, hidden_dim=64, geo_feat_dim=15, hidden_dim_color=64,
+                 appearance_embedding_dim=32, average_init_density=0.01):
+        super().__init__()
+        self.geo_feat_dim = geo_feat_dim
+        self.average_init_density = average_init_density
+        self.appearance_embedding_dim = appearance_embedding_dim
+        self.encoding = HashEncodingRef(num_levels, base_res, max_res, log2_hashmap_size, features_per_level)
+        self.mlp_base = MLPRef(self.encoding.get_out_dim(), 2, hidden_dim, 1 + geo_feat_dim)
+        self.embedding_appearance = nn.Embedding(num_images, appearance_embedding_dim)
+        self.mlp_head = MLPRef(16 + geo_feat_dim + appearance_embedding_dim, 3, hidden_dim_color, 3,
+                               out_activation=nn.Sigmoid())
+
+    def contracted_positions(self, positions: Tensor) -> Tuple[Tensor, Tensor]:
+        positions = contract_linf(positions)
+        positions = (positions + 2.0) / 4.0
+        selector = ((positions > 0.0) & (positions < 1.0)).all(dim=-1)
+        return positions * selector[..., None], selector
+
+    def get_density(self, positions: Tensor) -> Tuple[Tensor, Tensor]:
+        p, selector = self.contracted_positions(positions)
+        h = self.mlp_base(self.encoding(p.view(-1, 3))).view(*p.shape[:-1], -1)
+        density_before_activation, base_mlp_out = torch.split(h, [1, self.geo_feat_dim], dim=-1)
+        density = self.average_init_density * torch.exp(density_before_activation)
+        return density * selector[..., None], base_mlp_out
+
+    def get_rgb(self, directions: Tensor, density_embedding: Tensor) -> Tensor:
+        """directions [..., S, 3] already broadcast per sample (frustums.directions)."""
+        d = (directions + 1.0) / 2.0  # get_normalized_directions
+        d = sh_components_deg4(d.view(-1, 3))  # torch-path SHEncoding is fed the [0,1] tensor as-is
+        app = torch.ones((*directions.shape[:-1], self.appearance_embedding_dim)) * self.embedding_appearance.weight.mean(dim=0)
+        h = torch.cat([d, density_embedding.reshape(-1, self.geo_feat_dim),
+                       app.view(-1, self.appearance_embedding_dim)], dim=-1)
+        return self.mlp_head(h).view(*directions.shape[:-1], -1)
+
+
+class NerfactoRef(nn.Module):
+    """models/nerfacto.py populate_modules with SIGNeRF's overrides (signerf_config.py:32-35)."""
+
+    def __init__(self, num_images=30, average_init_density=0.01, near=0.05, far=1000.0,
+                 num_proposal_samples=(256, 96), num_nerf_samples=48,
+                 proposal_net_args=({"hidden_dim": 16, "log2_hashmap_size": 17, "num_levels": 5, "max_res": 128},
+                                    {"hidden_dim": 16, "log2_hashmap_size": 17, "num_levels": 5, "max_res": 256}),
+                 log2_hashmap_size=19, num_levels=16, max_res=2048):
+        super().__init__()
+        self.near, self.far = near, far
+        self.num_proposal_samples = tuple(num_proposal_samples)
+        self.num_nerf_samples = num_nerf_samples
+        self.field = NerfactoFieldRef(num_images=num_images, average_init_density=average_init_density,
+                                      log2_hashmap_size=log2_hashmap_size, num_levels=num_levels, max_res=max_res)
+        self.proposal_networks = nn.ModuleList(
+            DensityFieldRef(**a, average_init_density=average_init_density) for a in proposal_net_args)
+
+
+# --------------------------------------------------------------------------- rays
+@dataclass
+class RaysRef:
+    origins: Tensor      # [N,3]
+    directions: Tensor   # [N,3] unit
+    pixel_area: Tensor   # [N,1]
+    directions_norm: Tensor  # [N,1]
+
+
+def generate_rays(c2w: Tensor, fx: float, fy: float, cx: float, cy: float, width: int, height: int) -> RaysRef:
+    """Cameras.generate_rays(camera_indices=0) for a perspective camera without distortion.
+
+    Ray id = y*W + x (row-major, `indexing="ij"`), pixel centre offset 0.5.
+    """
+    c2w = c2w[:3, :4].to(torch.float32)
+    ys, xs = torch.meshgrid(torch.arange(height), torch.arange(width), indexing="ij")
+    y = ys.to(torch.float32) + 0.5
+    x = xs.to(torch.float32) + 0.5
+    fx_t, fy_t, cx_t, cy_t = (torch.tensor(v, dtype=torch.float32) for v in (fx, fy, cx, cy))
+    coord = torch.stack([(x - cx_t) / fx_t, -(y - cy_t) / fy_t], -1)
+    coord_x = torch.stack([(x - cx_t + 1) / fx_t, -(y - cy_t) / fy_t], -1)
+    coord_y = torch.stack([(x - cx_t) / fx_t, -(y - cy_t + 1) / fy_t], -1)
+    coord_stack = torch.stack([coord, coord_x, coord_y], dim=0)  # [3,H,W,2]
+    directions_stack = torch.empty((3, height, width, 3), dtype=torch.float32)
+    directions_stack[..., 0] = coord_stack[..., 0]
+    directions_stack[..., 1] = coord_stack[..., 1]
+    directions_stack[..., 2] = -1.0
+    rotation = c2w[:3, :3]
+    directions_stack = torch.sum(directions_stack[..., None, :] * rotation, dim=-1)
+    norm = torch.maximum(torch.linalg.vector_norm(directions_stack, dim=-1, keepdim=True),
+                         torch.tensor([1e-6]))  # camera_utils.normalize_with_norm
+    directions_stack = directions_stack / norm
+    origins = c2w[:3, 3].expand(height, width, 3)
+    directions = directions_stack[0]
+    dx = torch.sqrt(torch.sum((directions - directions_stack[1]) ** 2, dim=-1))
+    dy = torch.sqrt(torch.sum((directions - directions_stack[2]) ** 2, dim=-1))
+    return RaysRef(origins.reshape(-1, 3).contiguous(), directions.reshape(-1, 3).contiguous(),
+                   (dx * dy).reshape(-1, 1), norm[0].reshape(-1, 1))
+
+
+# --------------------------------------------------------------------------- samplers
+def spacing_fn(x: Tensor) -> Tensor:  # UniformLinDispPiecewiseSampler
+    return torch.where(x < 1, x / 2, 1 - 1 / (2 * x))
+
+
+def spacing_fn_inv(x: Tensor) -> Tensor:
+    return torch.where(x < 0.5, 2 * x, 1 / (2 - 2 * x))
+
+
+@dataclass
+class SamplesRef:
+    starts: Tensor          # [N,S,1] euclid
+    ends: Tensor
+    spacing_starts: Tensor  # [N,S,1]
+    spacing_ends: Tensor
+
+
+def make_to_euclid(nears: Tensor, fars: Tensor):
+    s_near, s_far = spacing_fn(nears), spacing_fn(fars)
+    return lambda x: spacing_fn_inv(x * s_far + (1 - x) * s_near)
+
+
+def initial_samples(num_rays: int, num_samples: int, to_euclid) -> SamplesRef:
+    """SpacedSampler.generate_ray_samples, eval (no stratification)."""
+    bins = torch.linspace(0.0, 1.0, num_samples + 1)[None, ...]
+    euclid = to_euclid(bins)  # nears/fars are [N,1] -> [N,S+1]
+    bins = bins.expand(num_rays, -1)
+    return SamplesRef(euclid[..., :-1, None], euclid[..., 1:, None], bins[..., :-1, None], bins[..., 1:, None])
+
+
+def flat_bin_edges(num_samples: int, near: float, far: float) -> Tensor:
+    """Euclidean bin edges [S+1] shared by every ray when near/far are the collider constants."""
+    nears = torch.full((1, 1), near, dtype=torch.float32)
+    fars = torch.full((1, 1), far, dtype=torch.float32)
+    bins = torch.linspace(0.0, 1.0, num_samples + 1)[None, ...]
+    return make_to_euclid(nears, fars)(bins)[0]
+
+
+def pdf_resample(samples: SamplesRef, weights: Tensor, num_samples: int, to_euclid,
+                 histogram_padding: float = 0.01, eps: float = 1e-5) -> SamplesRef:
+    """PDFSampler.generate_ray_samples, eval branch, include_original=False."""
+    num_bins = num_samples + 1
+    weights = weights[..., 0] + histogram_padding
+    weights_sum = torch.sum(weights, dim=-1, keepdim=True)
+    padding = torch.relu(eps - weights_sum)
+    weights = weights + padding / weights.shape[-1]
+    weights_sum += padding
+    pdf = weights / weights_sum
+    cdf = torch.min(torch.ones_like(pdf), torch.cumsum(pdf, dim=-1))
+    cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], dim=-1)
+    u = torch.linspace(0.0, 1.0 - (1.0 / num_bins), steps=num_bins)
+    u = u + 1.0 / (2 * num_bins)
+    u = u.expand(size=(*cdf.shape[:-1], num_bins)).contiguous()
+    existing_bins = torch.cat([samples.spacing_starts[..., 0], samples.spacing_ends[..., -1:, 0]], dim=-1)
+    inds = torch.searchsorted(cdf, u, side="right")
+    below = torch.clamp(inds - 1, 0, existing_bins.shape[-1] - 1)
+    above = torch.clamp(inds, 0, existing_bins.shape[-1] - 1)
+    cdf_g0 = torch.gather(cdf, -1, below)
+    bins_g0 = torch.gather(existing_bins, -1, below)
+    cdf_g1 = torch.gather(cdf, -1, above)
+    bins_g1 = torch.gather(existing_bins, -1, above)
+    t = torch.clip(torch.nan_to_num((u - cdf_g0) / (cdf_g1 - cdf_g0), 0), 0, 1)
+    bins = bins_g0 + t * (bins_g1 - bins_g0)
+    euclid = to_euclid(bins)
+    return SamplesRef(euclid[..., :-1, None], euclid[..., 1:, None], bins[..., :-1, None], bins[..., 1:, None])
+
+
+def positions_of(rays_o: Tensor, rays_d: Tensor, s: SamplesRef) -> Tensor:
+    """Frustums.get_positions: origins + directions * (starts + ends) / 2."""
+    return rays_o[:, None, :] + rays_d[:, None, :] * (s.starts + s.ends) / 2
+
+
+def get_weights(s: SamplesRef, densities: Tensor) -> Tensor:
+    """RaySamples.get_weights."""
+    deltas = s.ends - s.starts
+    delta_density = deltas * densities
+    alphas = 1 - torch.exp(-delta_density)
+    transmittance = torch.cumsum(delta_density[..., :-1, :], dim=-2)
+    transmittance = torch.cat([torch.zeros((*transmittance.shape[:1], 1, 1)), transmittance], dim=-2)
+    transmittance = torch.exp(-transmittance)
+    weights = alphas * transmittance
+    return torch.nan_to_num(weights)
+
+
+# --------------------------------------------------------------------------- renderers
+def render_rgb_last_sample(rgb: Tensor, weights: Tensor) -> Tensor:
+    """RGBRenderer(background_color="last_sample"), eval: nan_to_num in, clamp out."""
+    rgb = torch.nan_to_num(rgb)
+    comp_rgb = torch.sum(weights * rgb, dim=-2)
+    accumulated_weight = torch.sum(weights, dim=-2)
+    comp_rgb = comp_rgb + rgb[..., -1, :] * (1.0 - accumulated_weight)
+    return torch.clamp(comp_rgb, min=0.0, max=1.0)
+
+
+def render_depth_median(weights: Tensor, s: SamplesRef) -> Tensor:
+    """DepthRenderer(method="median")."""
+    steps = (s.starts + s.ends) / 2
+    cumulative_weights = torch.cumsum(weights[..., 0], dim=-1)
+    split = torch.ones((*weights.shape[:-2], 1)) * 0.5
+    median_index = torch.searchsorted(cumulative_weights, split, side="left")
+    median_index = torch.clamp(median_index, 0, steps.shape[-2] - 1)
+    return torch.gather(steps[..., 0], dim=-1, index=median_index)
+
+
+# --------------------------------------------------------------------------- model forward
+@torch.no_grad()
+def render_rays(model: NerfactoRef, rays_o: Tensor, rays_d: Tensor, mode: str = "flat",
+                num_samples: Optional[int] = None, return_aux: bool = False) -> Dict[str, Tensor]:
+    """NerfactoModel.get_outputs in eval for one chunk of rays.
+
+    mode="flat":    BASELINE flat mode: the initial piecewise sampler with S bins feeds
+                    the main field directly, no proposal networks.
+    mode="cascade": the faithful 256 -> 96 -> 48 ProposalNetworkSampler (anneal = 1).
+    """
+    n = rays_o.shape[0]
+    nears = torch.ones_like(rays_o[..., 0:1]) * model.near  # NearFarCollider
+    fars = torch.ones_like(rays_o[..., 0:1]) * model.far
+    to_euclid = make_to_euclid(nears, fars)
+    aux = {}
+    if mode == "flat":
+        S = num_samples if num_samples is not None else model.num_nerf_samples
+        samples = initial_samples(n, S, to_euclid)
+    elif mode == "cascade":
+        counts = list(model.num_proposal_samples) + [model.num_nerf_samples]
+        samples = initial_samples(n, counts[0], to_euclid)
+        for i, net in enumerate(model.proposal_networks):
+            density = net.density(positions_of(rays_o, rays_d, samples))
+            w = get_weights(samples, density)
+            annealed = torch.pow(w, 1.0)
+            samples = pdf_resample(samples, annealed, counts[i + 1], to_euclid)
+            if return_aux:
+                aux[f"prop_weights_{i}"] = w
+    else:
+        raise ValueError(mode)
+    positions = positions_of(rays_o, rays_d, samples)
+    density, geo = model.field.get_density(positions)
+    dirs = rays_d[:, None, :].expand(-1, positions.shape[1], -1)
+    rgb = model.field.get_rgb(dirs, geo)
+    weights = get_weights(samples, density)
+    out = {
+        "rgb": render_rgb_last_sample(rgb, weights),
+        "depth": render_depth_median(weights, samples),
+        "accumulation": torch.sum(weights, dim=-2),
+    }
+    if return_aux:
+        aux.update(positions=positions, density=density, rgb_samples=rgb, weights=weights,
+                   starts=samples.starts, ends=samples.ends)
+        out["aux"] = aux
+    return out
+
+
+@torch.no_grad()
+def render_view(model: NerfactoRef, c2w: Tensor, fx: float, fy: float, cx: float, cy: float,
+                width: int, height: int, mode: str = "flat", num_samples: Optional[int] = None,
+                chunk: int = 1 << 15) -> Dict[str, Tensor]:
+    """Model.get_outputs_for_camera_ray_bundle: row-major chunks of `eval_num_rays_per_chunk`
+    (signerf_config.py:32 sets 1<<15), concatenated and viewed as (H, W, C)."""
+    rays = generate_rays(c2w, fx, fy, cx, cy, width, height)
+    outs: Dict[str, List[Tensor]] = {}
+    for i in range(0, rays.origins.shape[0], chunk):
+        o = render_rays(model, rays.origins[i:i + chunk], rays.directions[i:i + chunk], mode, num_samples)
+        for k, v in o.items():
+            outs.setdefault(k, []).append(v)
+    res = {k: torch.cat(v).view(height, width, -1) for k, v in outs.items()}
+    res["origins"] = rays.origins.view(height, width, 3)
+    res["directions"] = rays.directions.view(height, width, 3)
+    return res
+
+
+def make_model(seed: int = 0, dense: bool = False, table_scale: Optional[float] = None,
+               density_gain: Optional[float] = None, **kw) -> NerfactoRef:
+    """Benchmark field: seeded random init; `dense` raises the density logit bias to +6
+    (sigma ~ 4) so compositing is not degenerate; `table_scale` rescales the hash tables from the
+    1e-3 init to a trained-like magnitude so density/colour vary in space (parity tests)."""
+    gen_state = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    model = NerfactoRef(**kw)
+    torch.random.set_rng_state(gen_state)
+    if table_scale is not None:
+        with torch.no_grad():
+            for enc in [model.field.encoding] + [p.encoding for p in model.proposal_networks]:
+                enc.hash_table.mul_(table_scale / 1e-3)
+    if density_gain is not None:  # spatially varying density logit (test fields only)
+        with torch.no_grad():
+            model.field.mlp_base.layers[-1].weight[0].mul_(density_gain)
+            for p in model.proposal_networks:
+                p.mlp.layers[-1].weight.mul_(density_gain)
+    if dense:
+        with torch.no_grad():
+            model.field.mlp_base.layers[-1].bias[0] = 6.0
+            for p in model.proposal_networks:
+                p.mlp.layers[-1].bias[0] = 6.0
+    return model.eval()

@@ -1,0 +1,108 @@
+"""ctypes binding of the C ABI in include/signerf_b200.h.
+
+This is the stub a SIGNeRF maintainer would add on the reference side: the
+reference has no FFI of its own, its hot path is Python calling nerfstudio.  The library is
+built in-tree by `__graft_entry__.build()` / `make -C signerf_b200/csrc`; there is NO CPU
+fallback — a missing library or a missing GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsignerf_b200.so")
+
+SGN_OK = 0
+SGN_MLP_FP16_MMA = 0
+SGN_MLP_FP32 = 1
+
+
+class SgnError(RuntimeError):
+    """A C-ABI call returned a negative SgnStatus."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"signerf_b200 error {code}: {msg}")
+        self.code = code
+
+
+class SgnHashGrid(C.Structure):
+    _fields_ = [("d_table", C.c_void_p), ("h_scalings", C.POINTER(C.c_float)),
+                ("num_levels", C.c_int), ("log2_size", C.c_int)]
+
+
+class SgnLinear(C.Structure):
+    _fields_ = [("h_weight", C.POINTER(C.c_float)), ("h_bias", C.POINTER(C.c_float)),
+                ("in_dim", C.c_int), ("out_dim", C.c_int)]
+
+
+class SgnFieldDesc(C.Structure):
+    _fields_ = [("grid", SgnHashGrid), ("base", SgnLinear * 2), ("head", SgnLinear * 3),
+                ("h_appearance", C.POINTER(C.c_float)), ("average_init_density", C.c_float),
+                ("num_proposals", C.c_int), ("prop_grid", SgnHashGrid * 2),
+                ("prop_mlp", (SgnLinear * 2) * 2)]
+
+
+class SgnRenderOpts(C.Structure):
+    _fields_ = [("near_plane", C.c_float), ("far_plane", C.c_float), ("mode", C.c_int),
+                ("num_samples", C.c_int), ("num_prop_samples", C.c_int * 2), ("mlp_mode", C.c_int),
+                ("h_bins", C.POINTER(C.c_float))]
+
+
+class SgnMaskOpts(C.Structure):
+    _fields_ = [("aabb", C.c_float * 6), ("inverse_mask", C.c_int), ("dilate_w", C.c_int),
+                ("dilate_h", C.c_int), ("depth_radius", C.c_float), ("use_manual_depth", C.c_int),
+                ("manual_min", C.c_float), ("manual_max", C.c_float)]
+
+
+_vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+
+# name -> (restype, argtypes); every symbol include/signerf_b200.h declares.
+SIGNATURES = {
+    "sgn_last_error": (C.c_char_p, []),
+    "sgn_abi_version": (_i, []),
+    "sgn_launch_count": (C.c_uint64, []),
+    "sgn_field_create": (_i, [C.POINTER(SgnFieldDesc), C.POINTER(_vp)]),
+    "sgn_field_destroy": (None, [_vp]),
+    "sgn_render_views": (_i, [_vp, _vp, _vp, _i, _i, _i, C.POINTER(SgnRenderOpts), _vp, _vp, _vp, _vp]),
+    "sgn_render_views_host": (_i, [_vp, _vp, _vp, _i, _i, _i, C.POINTER(SgnRenderOpts), _vp, _vp, _vp]),
+    "sgn_generate_rays": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "sgn_hash_encode": (_i, [_vp, _i, _vp, _i64, _vp, _vp, _vp]),
+    "sgn_field_eval": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp]),
+    "sgn_mask_condition": (_i, [_vp, _vp, _i, _i, _i, _vp, C.POINTER(SgnMaskOpts), _vp, _vp, _vp, _vp]),
+    "sgn_dilate_ellipse": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "sgn_sheet_paste": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
+    "sgn_sheet_cut": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
+    "sgn_blend_masked": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp]),
+    "sgn_quantize_u8": (_i, [_vp, _i64, _vp, _vp]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once) and attach the prototypes.  Fails loudly when absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C signerf_b200/csrc`. signerf_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(code: int) -> None:
+    if code != SGN_OK:
+        raise SgnError(code, load().sgn_last_error().decode("utf-8", "replace"))
+
+
+def launch_count() -> int:
+    return int(load().sgn_launch_count())

@@ -1,0 +1,260 @@
+// Nerfacto-faithful sampling cascade (A3): ProposalNetworkSampler in eval
+//   initial piecewise-lin-disp bins (256) -> proposal net 0 -> PDF resample (96) -> proposal net 1
+//   -> PDF resample (48) -> main field (k_render_* with per-ray bins).
+// Restates nerfstudio 1.0.x model_components/ray_samplers.py (SpacedSampler, PDFSampler,
+// ProposalNetworkSampler) and fields/density_fields.py HashMLPDensityField for the call at
+// reference signerf/datasetgenerator/datasetgenerator.py:694.  Eval is deterministic (no RNG), _anneal = 1.
+#include <algorithm>
+#include <vector>
+
+#include "sgn_device.cuh"
+
+namespace sgn {
+
+int launch_render(const SgnField* f, const float* d_c2w, const float* d_intr, int V, int H, int W, int S,
+                  const float* d_bins, const float* d_ray_bins, int mlp_mode, float* d_rgb, float* d_depth,
+                  float* d_acc, cudaStream_t st);
+void host_flat_bins(int S, float near_p, float far_p, std::vector<float>& out);
+
+constexpr int kPWarps = 4;
+constexpr int kPThreads = kPWarps * 32;
+
+struct PropParams {
+  const PropDev* net;
+  const float* c2w;
+  const float* intr;
+  const float* bins;      // shared euclid edges [S+1] or null
+  const float* ray_bins;  // per-ray euclid edges [rays][S+1] or null
+  float* weights;         // out [rays][S]
+  int V, H, W, S;
+  int tiles_x, tiles_y, num_tiles;
+};
+
+// Proposal density + RaySamples.get_weights for every sample of every ray of the chunk.
+template <bool kPerRayBins>
+__global__ void __launch_bounds__(kPThreads) k_prop_weights(const __grid_constant__ PropParams p) {
+  __shared__ PropDev net;
+  extern __shared__ float sbins[];
+  for (int i = threadIdx.x; i < (int)(sizeof(PropDev) / 4); i += kPThreads)
+    reinterpret_cast<uint32_t*>(&net)[i] = reinterpret_cast<const uint32_t*>(p.net)[i];
+  if (!kPerRayBins)
+    for (int i = threadIdx.x; i <= p.S; i += kPThreads) sbins[i] = p.bins[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int per_view = p.tiles_x * p.tiles_y;
+  for (int tile = blockIdx.x * kPWarps + warp; tile < p.num_tiles; tile += gridDim.x * kPWarps) {
+    int v = tile / per_view, r = tile - v * per_view;
+    int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+    int x = tx * 8 + (lane & 7), y = ty * 4 + (lane >> 3);
+    bool valid = x < p.W && y < p.H;
+    x = min(x, p.W - 1);
+    y = min(y, p.H - 1);
+    const Camera cam = load_camera(p.c2w, p.intr, v);
+    float d[3];
+    ray_direction(cam, (float)x + 0.5f, (float)y + 0.5f, 0.f, 0.f, d);
+    size_t ray = ((size_t)v * p.H + y) * p.W + x;
+    const float* rb = kPerRayBins ? p.ray_bins + ray * (size_t)(p.S + 1) : nullptr;
+    float* wout = p.weights + ray * (size_t)p.S;
+    float cum = 0.f;
+    float t0 = kPerRayBins ? __ldg(rb) : sbins[0];
+    for (int i = 0; i < p.S; ++i) {
+      const float t1 = kPerRayBins ? __ldg(rb + i + 1) : sbins[i + 1];
+      const float mid = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+      float px, py, pz;
+      const bool sel = contract_to_unit(__fadd_rn(cam.o[0], __fmul_rn(d[0], mid)),
+                                        __fadd_rn(cam.o[1], __fmul_rn(d[1], mid)),
+                                        __fadd_rn(cam.o[2], __fmul_rn(d[2], mid)), px, py, pz);
+      float feat[10];
+#pragma unroll
+      for (int l = 0; l < 5; ++l) {
+        float2 f = encode_level(net.grid.table + (size_t)l * net.grid.size, net.grid.mask, net.grid.res[l], px, py, pz);
+        feat[2 * l] = f.x;
+        feat[2 * l + 1] = f.y;
+      }
+      float out = net.b1;
+#pragma unroll
+      for (int n = 0; n < 16; ++n) {
+        float a = net.b0[n];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) a = fmaf(net.w0[n * 10 + k], feat[k], a);
+        out = fmaf(net.w1[n], fmaxf(a, 0.f), out);
+      }
+      const float sigma = sel ? net.avg_density * expf(out) : 0.f;
+      const float dd = __fsub_rn(t1, t0) * sigma;
+      float w = (1.f - expf(-dd)) * expf(-cum);
+      cum += dd;
+      if (w != w) w = 0.f;
+      if (valid) wout[i] = w;
+      t0 = t1;
+    }
+  }
+}
+
+struct PdfParams {
+  const float* weights;       // [rays][S]
+  const float* spacing_in;    // shared [S+1] or per-ray [rays][S+1] spacing-domain bins
+  int spacing_per_ray;
+  const float* u;             // [nb] sample positions in cdf space
+  float* cdf_scratch;         // [rays][S+1]
+  float* spacing_out;         // [rays][nb]
+  float* euclid_out;          // [rays][nb]
+  float s_near, s_far;
+  int64_t rays;
+  int S, nb;
+};
+
+// PDFSampler.generate_ray_samples (eval, include_original=False): one thread per ray.
+__global__ void k_pdf_resample(const __grid_constant__ PdfParams p) {
+  const float pad_hist = 0.01f, eps = 1e-5f;
+  for (int64_t ray = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; ray < p.rays;
+       ray += (int64_t)gridDim.x * blockDim.x) {
+    const float* w = p.weights + ray * p.S;
+    const float* sb = p.spacing_in + (p.spacing_per_ray ? ray * (int64_t)(p.S + 1) : 0);
+    float* cdf = p.cdf_scratch + ray * (int64_t)(p.S + 1);
+    float sum = 0.f;
+    for (int i = 0; i < p.S; ++i) sum += __fadd_rn(w[i], pad_hist);
+    const float padding = fmaxf(eps - sum, 0.f);
+    const float padw = __fdiv_rn(padding, (float)p.S);
+    sum += padding;
+    float run = 0.f;
+    cdf[0] = 0.f;
+    for (int i = 0; i < p.S; ++i) {
+      float pdf = __fdiv_rn(__fadd_rn(__fadd_rn(w[i], pad_hist), padw), sum);
+      run = __fadd_rn(run, pdf);
+      cdf[i + 1] = fminf(1.f, run);
+    }
+    // searchsorted(cdf, u, side="right") by a forward merge: both sequences ascend.
+    int idx = 0;
+    for (int j = 0; j < p.nb; ++j) {
+      const float u = __ldg(p.u + j);
+      while (idx <= p.S && !(cdf[idx] > u)) ++idx;  // first idx with cdf[idx] > u, or S+1
+      const int below = min(max(idx - 1, 0), p.S), above = min(idx, p.S);
+      const float c0 = cdf[below], c1 = cdf[above];
+      const float b0 = __ldg(sb + below), b1 = __ldg(sb + above);
+      float t = __fdiv_rn(__fsub_rn(u, c0), __fsub_rn(c1, c0));
+      if (t != t) t = 0.f;                  // nan_to_num(nan=0); +-inf fall to the clip below
+      t = fminf(fmaxf(t, 0.f), 1.f);
+      const float nbv = __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));
+      p.spacing_out[ray * p.nb + j] = nbv;
+      p.euclid_out[ray * p.nb + j] = to_euclid(nbv, p.s_near, p.s_far);
+    }
+  }
+}
+
+static float h_spacing(float x) { return x < 1.f ? x / 2.f : 1.f - 1.f / (2.f * x); }
+
+// u = linspace(0, 1 - 1/nb, nb) + 1/(2 nb), evaluated like torch (fp32 symmetric linspace).
+static void host_pdf_u(int nb, std::vector<float>& u) {
+  u.resize(nb);
+  const float end = (float)(1.0 - 1.0 / (double)nb);
+  const float step = nb > 1 ? (end - 0.f) / (float)(nb - 1) : 0.f;
+  const float add = (float)(1.0 / (2.0 * (double)nb));
+  for (int i = 0; i < nb; ++i) {
+    volatile float base = i < nb / 2 ? 0.f + step * (float)i : end - step * (float)(nb - i - 1);
+    u[i] = base + add;
+  }
+}
+static void host_linspace01(int n, std::vector<float>& out) {
+  out.resize(n);
+  float step = 1.f / (float)(n - 1);
+  for (int i = 0; i < n; ++i) out[i] = i < n / 2 ? step * (float)i : 1.f - step * (float)(n - i - 1);
+}
+
+struct AsyncBuf {
+  void* p = nullptr;
+  cudaStream_t st;
+  explicit AsyncBuf(cudaStream_t s) : st(s) {}
+  cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes, st); }
+  ~AsyncBuf() {
+    if (p) cudaFreeAsync(p, st);
+  }
+  template <class T>
+  T* as() { return reinterpret_cast<T*>(p); }
+};
+
+int render_cascade(const SgnField* f, const float* d_c2w, const float* d_intr, int V, int H, int W,
+                   const SgnRenderOpts* o, float* d_rgb, float* d_depth, float* d_acc, cudaStream_t st) {
+  if (f->num_proposals != 2) {
+    set_error("cascade mode needs a field created with 2 proposal networks");
+    return SGN_ERR_INVALID_ARG;
+  }
+  const int S0 = o->num_prop_samples[0], S1 = o->num_prop_samples[1], S2 = o->num_samples;
+  SGN_CHECK_ARG(S0 >= 1 && S0 <= 1024 && S1 >= 1 && S1 <= 1024, "num_prop_samples must be 1..1024");
+  int nsm = 148;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+  }
+  std::vector<float> e0, sp0, u1, u2;
+  if (o->h_bins) e0.assign(o->h_bins, o->h_bins + S0 + 1);
+  else host_flat_bins(S0, o->near_plane, o->far_plane, e0);
+  host_linspace01(S0 + 1, sp0);
+  host_pdf_u(S1 + 1, u1);
+  host_pdf_u(S2 + 1, u2);
+  const float s_near = h_spacing(o->near_plane), s_far = h_spacing(o->far_plane);
+
+  const size_t rays_per_view = (size_t)H * W;
+  const int views_per_chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)V, ((size_t)1 << 20) / rays_per_view));
+  const size_t max_rays = rays_per_view * views_per_chunk;
+  const int Smax = std::max(S0, S1);
+
+  AsyncBuf small(st), wbuf(st), cdfbuf(st), sp1(st), eu1(st), sp2(st), eu2(st);
+  const size_t small_floats = (size_t)(S0 + 1) * 2 + (S1 + 1) + (S2 + 1);
+  SGN_CUDA(small.alloc(small_floats * 4));
+  SGN_CUDA(wbuf.alloc(max_rays * Smax * 4));
+  SGN_CUDA(cdfbuf.alloc(max_rays * (Smax + 1) * 4));
+  SGN_CUDA(sp1.alloc(max_rays * (S1 + 1) * 4));
+  SGN_CUDA(eu1.alloc(max_rays * (S1 + 1) * 4));
+  SGN_CUDA(sp2.alloc(max_rays * (S2 + 1) * 4));
+  SGN_CUDA(eu2.alloc(max_rays * (S2 + 1) * 4));
+  float* d_e0 = small.as<float>();
+  float* d_sp0 = d_e0 + (S0 + 1);
+  float* d_u1 = d_sp0 + (S0 + 1);
+  float* d_u2 = d_u1 + (S1 + 1);
+  SGN_CUDA(cudaMemcpyAsync(d_e0, e0.data(), (S0 + 1) * 4, cudaMemcpyHostToDevice, st));
+  SGN_CUDA(cudaMemcpyAsync(d_sp0, sp0.data(), (S0 + 1) * 4, cudaMemcpyHostToDevice, st));
+  SGN_CUDA(cudaMemcpyAsync(d_u1, u1.data(), (S1 + 1) * 4, cudaMemcpyHostToDevice, st));
+  SGN_CUDA(cudaMemcpyAsync(d_u2, u2.data(), (S2 + 1) * 4, cudaMemcpyHostToDevice, st));
+
+  for (int v0 = 0; v0 < V; v0 += views_per_chunk) {
+    const int nv = std::min(views_per_chunk, V - v0);
+    const int64_t rays = (int64_t)rays_per_view * nv;
+    PropParams pp;
+    pp.c2w = d_c2w + (size_t)v0 * 12;
+    pp.intr = d_intr + (size_t)v0 * 4;
+    pp.weights = wbuf.as<float>();
+    pp.V = nv; pp.H = H; pp.W = W;
+    pp.tiles_x = (W + 7) / 8;
+    pp.tiles_y = (H + 3) / 4;
+    pp.num_tiles = nv * pp.tiles_x * pp.tiles_y;
+    const int pblocks = std::min((pp.num_tiles + kPWarps - 1) / kPWarps, nsm * 8);
+    const int rblocks = (int)std::min<int64_t>((rays + 127) / 128, (int64_t)nsm * 16);
+    // stage 0: shared bins
+    pp.net = f->d_prop[0]; pp.bins = d_e0; pp.ray_bins = nullptr; pp.S = S0;
+    k_prop_weights<false><<<pblocks, kPThreads, (S0 + 1) * 4, st>>>(pp);
+    SGN_LAUNCH_CHECK();
+    PdfParams q;
+    q.weights = wbuf.as<float>(); q.spacing_in = d_sp0; q.spacing_per_ray = 0; q.u = d_u1;
+    q.cdf_scratch = cdfbuf.as<float>(); q.spacing_out = sp1.as<float>(); q.euclid_out = eu1.as<float>();
+    q.s_near = s_near; q.s_far = s_far; q.rays = rays; q.S = S0; q.nb = S1 + 1;
+    k_pdf_resample<<<rblocks, 128, 0, st>>>(q);
+    SGN_LAUNCH_CHECK();
+    // stage 1: per-ray bins
+    pp.net = f->d_prop[1]; pp.bins = nullptr; pp.ray_bins = eu1.as<float>(); pp.S = S1;
+    k_prop_weights<true><<<pblocks, kPThreads, 0, st>>>(pp);
+    SGN_LAUNCH_CHECK();
+    q.spacing_in = sp1.as<float>(); q.spacing_per_ray = 1; q.u = d_u2;
+    q.spacing_out = sp2.as<float>(); q.euclid_out = eu2.as<float>(); q.S = S1; q.nb = S2 + 1;
+    k_pdf_resample<<<rblocks, 128, 0, st>>>(q);
+    SGN_LAUNCH_CHECK();
+    // main field on the final per-ray bins
+    const size_t off = (size_t)v0 * rays_per_view;
+    int rc = launch_render(f, pp.c2w, pp.intr, nv, H, W, S2, nullptr, eu2.as<float>(), o->mlp_mode, d_rgb + off * 3,
+                           d_depth + off, d_acc ? d_acc + off : nullptr, st);
+    if (rc) return rc;
+  }
+  return SGN_OK;
+}
+
+}  // namespace sgn

@@ -1,0 +1,70 @@
+"""Synthetic nerfacto parameters and camera rings for benchmarks / smoke runs: random hash tables
+U(-1,1)*1e-3, nn.Linear default init, N(0,1) appearance embedding, piecewise scalings.  No datasets or
+checkpoints are available offline, so this is what "random hash-grid + MLP" in BASELINE.json's configs means."""
+from __future__ import annotations
+
+import math
+from typing import Dict, Tuple
+
+import numpy as np
+import torch
+from torch import Tensor, nn
+
+from .field import HashGridParams, LinearParams, NerfactoFieldB200
+
+
+def hash_scalings(num_levels: int, min_res: int, max_res: int) -> Tensor:
+    """HashEncoding.scalings with nerfstudio's own expression (float32 power: 16 -> 2047 at level 15)."""
+    levels = torch.arange(num_levels)
+    growth = np.exp((np.log(max_res) - np.log(min_res)) / (num_levels - 1)) if num_levels > 1 else 1
+    return torch.floor(min_res * growth**levels)
+
+
+def _linear(i: int, o: int, gen: torch.Generator) -> LinearParams:
+    bound = 1.0 / math.sqrt(i)  # kaiming_uniform(a=sqrt(5)) on weight and the default bias init share this bound
+    w = (torch.rand(o, i, generator=gen) * 2 - 1) * bound
+    b = (torch.rand(o, generator=gen) * 2 - 1) * bound
+    return LinearParams(w, b)
+
+
+def _grid(levels: int, max_res: int, log2: int, gen: torch.Generator, device, scale: float) -> HashGridParams:
+    table = ((torch.rand(levels * (1 << log2), 2, generator=gen) * 2 - 1) * scale).to(device)
+    return HashGridParams(table.contiguous(), hash_scalings(levels, 16, max_res), log2)
+
+
+def random_field(seed: int = 0, device="cuda", dense: bool = False, with_proposals: bool = True,
+                 table_scale: float = 1e-3, average_init_density: float = 0.01) -> NerfactoFieldB200:
+    gen = torch.Generator().manual_seed(seed)
+    grid = _grid(16, 2048, 19, gen, device, table_scale)
+    base = [_linear(32, 64, gen), _linear(64, 16, gen)]
+    head = [_linear(63, 64, gen), _linear(64, 64, gen), _linear(64, 3, gen)]
+    app = torch.randn(30, 32, generator=gen).mean(dim=0)
+    pg, pm = [], []
+    if with_proposals:
+        for max_res in (128, 256):
+            pg.append(_grid(5, max_res, 17, gen, device, table_scale))
+            pm.append([_linear(10, 16, gen), _linear(16, 1, gen)])
+    if dense:  # sigma ~ 0.01 * e^6 ~ 4: compositing saturates inside the scene instead of at the far plane
+        base[1].bias[0] = 6.0
+        for m in pm:
+            m[1].bias[0] = 6.0
+    return NerfactoFieldB200(grid, base, head, app, average_init_density, pg, pm)
+
+
+def camera_ring(n: int, width: int, height: int, radius: float = 0.5, theta_deg: float = 90.0,
+                phi_deg: Tuple[float, float] = (0.0, 300.0)) -> Tuple[Tensor, Tensor]:
+    """Look-at ring equivalent to the GUI default `circle_poses(size=n, radius=0.5, theta=90, phi=(0,300))`
+    (reference signerf/utils/poses_generation.py:22-73, interface.py:62-71); fx = fy = W, principal point centred."""
+    phis = torch.linspace(math.radians(phi_deg[0]), math.radians(phi_deg[1]), n)
+    theta = torch.tensor(math.radians(theta_deg))
+    pos = torch.stack([radius * torch.sin(theta) * torch.cos(phis), radius * torch.sin(theta) * torch.sin(phis),
+                       radius * torch.cos(theta) * torch.ones_like(phis)], -1)
+    z = pos / pos.norm(dim=-1, keepdim=True).clamp_min(1e-10)
+    up = torch.tensor([0.0, 0.0, 1.0]).expand(n, 3)
+    x = torch.linalg.cross(up, z)
+    x = x / x.norm(dim=-1, keepdim=True).clamp_min(1e-10)
+    y = torch.linalg.cross(z, x)
+    c2w = torch.zeros(n, 3, 4)
+    c2w[:, :, 0], c2w[:, :, 1], c2w[:, :, 2], c2w[:, :, 3] = x, y, z, pos
+    intr = torch.tensor([[float(width), float(width), width / 2.0, height / 2.0]]).repeat(n, 1)
+    return c2w, intr

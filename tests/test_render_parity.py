@@ -1,0 +1,193 @@
+"""GPU parity of K1 (fused renderer) against the oracle, through the C ABI.
+
+Tolerances (BASELINE.json north_star): bit-exact ray / hash indices, <= 1e-3 relative L2 on rgb / depth.
+The fp32 CUDA-core path is additionally held to 2e-5 so that geometry / hashing / compositing bugs cannot
+hide behind the fp16 tensor-core MLP's rounding."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nerfacto_ref as R
+from signerf_b200 import ops
+from tests.helpers import field_from_oracle, rel_l2, ring_cameras
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3          # north_star tolerance
+TOL_FP32 = 2e-5     # parity path
+
+
+@pytest.fixture(scope="module")
+def fields():
+    out = {}
+    for name, kw in {
+        "init": dict(),                                                        # benchmark field: 1e-3 tables
+        "dense": dict(dense=True),                                             # benchmark "dense" variant
+        "varied": dict(dense=True, table_scale=0.5, density_gain=20.0),        # spatially varying density
+        "sparse": dict(table_scale=0.5, density_gain=40.0),                    # partial accumulation
+    }.items():
+        m = R.make_model(0, **kw)
+        out[name] = (m, field_from_oracle(m))
+    yield out
+    for _, f in out.values():
+        f.close()
+
+
+def test_ray_generation_matches_and_ray_ids_are_row_major(fields):
+    c2w, intr = ring_cameras(3, 40, 24)
+    o, d, area, nrm = ops.generate_rays(c2w.cuda(), intr.cuda(), 24, 40)
+    for v in range(3):
+        ref = R.generate_rays(c2w[v], *intr[v].tolist(), 40, 24)
+        assert torch.equal(o[v].cpu().reshape(-1, 3), ref.origins)
+        assert torch.allclose(d[v].cpu().reshape(-1, 3), ref.directions, atol=2e-7, rtol=0)
+        assert torch.allclose(nrm[v].cpu().reshape(-1, 1), ref.directions_norm, rtol=1e-6)
+        assert torch.allclose(area[v].cpu().reshape(-1, 1), ref.pixel_area, rtol=2e-3)
+    # ray id = y*W + x: the direction of pixel (y, x) must be the oracle's row y*W+x, bit for bit in index order
+    ref = R.generate_rays(c2w[0], *intr[0].tolist(), 40, 24).directions.view(24, 40, 3)
+    diff = (d[0].cpu() - ref).abs().amax(-1)
+    assert float(diff.max()) <= 2e-7
+
+
+@pytest.mark.parametrize("which", [0, 1, 2])
+def test_hash_indices_bit_exact(fields, which):
+    m, f = fields["varied"]
+    enc = m.field.encoding if which == 0 else m.proposal_networks[which - 1].encoding
+    g = torch.Generator().manual_seed(7)
+    p = torch.rand(20000, 3, generator=g)
+    p[:64] = torch.tensor([0.0, 0.0, 0.0])          # selector-masked samples land on row 0
+    p[64:128] = (torch.arange(64).float() / 64)[:, None]  # exact lattice points: ceil == floor
+    p[128:192] = torch.rand(64, 3, generator=g) * 1e-4
+    p[192:256] = 1.0 - torch.rand(64, 3, generator=g) * 1e-4
+    idx, feat = ops.hash_encode(f, p.cuda(), which)
+    ref_idx, _ = enc.corner_indices(p)
+    assert torch.equal(idx.cpu(), ref_idx), "hash rows differ from HashEncoding.hash_fn"
+    ref_feat = enc(p)
+    assert rel_l2(feat, ref_feat) < 1e-6
+
+
+def test_hash_encode_empty_input(fields):
+    _, f = fields["init"]
+    idx, feat = ops.hash_encode(f, torch.zeros(0, 3).cuda())
+    assert idx.shape == (0, 16, 8) and feat.shape == (0, 32)
+
+
+@pytest.mark.parametrize("name", ["init", "varied"])
+def test_field_eval_both_mlp_paths(fields, name):
+    m, f = fields[name]
+    g = torch.Generator().manual_seed(3)
+    pos = torch.cat([(torch.rand(5000, 3, generator=g) - 0.5) * 2, (torch.rand(5003, 3, generator=g) - 0.5) * 40])
+    d = torch.nn.functional.normalize(torch.randn(pos.shape[0], 3, generator=g), dim=-1)
+    den_ref, geo = m.field.get_density(pos[:, None, :])
+    rgb_ref = m.field.get_rgb(d[:, None, :], geo)
+    den_ref, rgb_ref = den_ref.reshape(-1), rgb_ref.reshape(-1, 3)
+    den32, rgb32 = ops.field_eval(f, pos.cuda(), d.cuda(), ops.MLP_FP32)
+    assert rel_l2(den32, den_ref) < TOL_FP32 and rel_l2(rgb32, rgb_ref) < TOL_FP32
+    den16, rgb16 = ops.field_eval(f, pos.cuda(), d.cuda(), ops.MLP_FP16_MMA)
+    assert rel_l2(den16, den_ref) < TOL and rel_l2(rgb16, rgb_ref) < TOL
+
+
+@pytest.mark.parametrize("name", ["init", "dense", "varied", "sparse"])
+@pytest.mark.parametrize("mlp_mode", [ops.MLP_FP32, ops.MLP_FP16_MMA])
+def test_c1_flat_render_matches_oracle(fields, name, mlp_mode):
+    """BASELINE config 1: single 64x64 view, 32 samples/ray, flat sampling."""
+    m, f = fields[name]
+    c2w, intr = ring_cameras(16, 64, 64)
+    ref = R.render_view(m, c2w[0], *intr[0].tolist(), 64, 64, "flat", 32)
+    rgb, depth, acc = ops.render_views(f, c2w[:1].cuda(), intr[:1].cuda(), 64, 64,
+                                       ops.RenderOptions(mode="flat", num_samples=32, mlp_mode=mlp_mode), want_acc=True)
+    tol = TOL_FP32 if mlp_mode == ops.MLP_FP32 else TOL
+    assert rel_l2(rgb[0], ref["rgb"]) < tol
+    assert rel_l2(acc[0], ref["accumulation"]) < max(tol, 1e-5)
+    # median depth picks a bin mid-point: compare values, and count rays whose pick moved by a bin
+    flips = float(((depth[0].cpu() - ref["depth"]).abs() > 1e-6 * ref["depth"].abs()).float().mean())
+    assert flips <= (0.0 if mlp_mode == ops.MLP_FP32 else 2e-3), f"{flips:.2%} of rays picked another median bin"
+    assert rel_l2(depth[0], ref["depth"]) < tol
+
+
+def test_multi_view_ragged_size_and_in_library_bins(fields):
+    """Non tile-aligned image (W % 8 != 0, H % 4 != 0), several views, bins computed inside the library."""
+    m, f = fields["varied"]
+    H, W, V = 22, 37, 3
+    c2w, intr = ring_cameras(V, W, H)
+    rgb, depth = ops.render_views(f, c2w.cuda(), intr.cuda(), H, W, ops.RenderOptions(mode="flat", num_samples=24))
+    for v in range(V):
+        ref = R.render_view(m, c2w[v], *intr[v].tolist(), W, H, "flat", 24)
+        assert rel_l2(rgb[v], ref["rgb"]) < TOL and rel_l2(depth[v], ref["depth"]) < TOL
+    # library-side bin computation equals the torch expression
+    from signerf_b200 import _lib
+    import ctypes as C
+    o = ops.RenderOptions(mode="flat", num_samples=24).to_c([])
+    o.h_bins = None
+    rgb2 = torch.empty_like(rgb)
+    depth2 = torch.empty_like(depth)
+    _lib.check(_lib.load().sgn_render_views(f.handle, C.c_void_p(c2w.cuda().contiguous().data_ptr()),
+                                            C.c_void_p(intr.cuda().contiguous().data_ptr()), V, H, W, C.byref(o),
+                                            C.c_void_p(rgb2.data_ptr()), C.c_void_p(depth2.data_ptr()), None, None))
+    torch.cuda.synchronize()
+    assert torch.equal(rgb, rgb2) and torch.equal(depth, depth2)
+
+
+def test_host_entry_point_equals_device_entry_point(fields):
+    _, f = fields["varied"]
+    c2w, intr = ring_cameras(2, 32, 16)
+    opts = ops.RenderOptions(mode="flat", num_samples=16)
+    rgb, depth = ops.render_views(f, c2w.cuda(), intr.cuda(), 16, 32, opts)
+    h_rgb = np.empty((2, 16, 32, 3), np.float32)
+    h_depth = np.empty((2, 16, 32, 1), np.float32)
+    ops.render_views_host(f, c2w.numpy(), intr.numpy(), 16, 32, opts, h_rgb, h_depth)
+    assert np.array_equal(h_rgb, rgb.cpu().numpy()) and np.array_equal(h_depth, depth.cpu().numpy())
+
+
+@pytest.mark.parametrize("name", ["varied", "sparse"])
+@pytest.mark.parametrize("mlp_mode", [ops.MLP_FP32, ops.MLP_FP16_MMA])
+def test_cascade_render_matches_oracle(fields, name, mlp_mode):
+    """Nerfacto-faithful sampling: 256 -> 96 -> 48 with both proposal networks (C2' at test size)."""
+    m, f = fields[name]
+    c2w, intr = ring_cameras(2, 48, 32)
+    opts = ops.RenderOptions(mode="cascade", num_samples=48, num_prop_samples=(256, 96), mlp_mode=mlp_mode)
+    rgb, depth, acc = ops.render_views(f, c2w.cuda(), intr.cuda(), 32, 48, opts, want_acc=True)
+    for v in range(2):
+        ref = R.render_view(m, c2w[v], *intr[v].tolist(), 48, 32, "cascade")
+        assert rel_l2(rgb[v], ref["rgb"]) < TOL
+        assert rel_l2(acc[v], ref["accumulation"]) < TOL
+        # resampled bins move with 1-ulp changes in the proposal weights: depth is compared in L2 only
+        assert rel_l2(depth[v], ref["depth"]) < (5e-3 if name == "sparse" else TOL)
+
+
+def test_argument_errors_are_reported_not_crashed(fields):
+    _, f = fields["init"]
+    c2w, intr = ring_cameras(1, 8, 8)
+    from signerf_b200._lib import SgnError
+    with pytest.raises(SgnError):
+        ops.render_views(f, c2w.cuda(), intr.cuda(), 8, 8, ops.RenderOptions(mode="flat", num_samples=0))
+    with pytest.raises(SgnError):
+        ops.render_views(f, c2w.cuda(), intr.cuda(), 8, 8, ops.RenderOptions(mode="flat", num_samples=8, near_plane=5.0, far_plane=1.0))
+    with pytest.raises(ValueError):
+        ops.render_views(f, c2w.cuda(), intr.cuda(), 8, 8, ops.RenderOptions(mode="nope"))
+
+
+def test_full_size_properties_c2(fields):
+    """BASELINE config 2 size (512x512, 128 samples) on 2 views: size-independent properties.
+    (1) a view rendered alone equals the same view rendered inside a batch (pure partition, no cross-view state);
+    (2) rgb in [0,1], depth is one of the 128 bin mid-points, accumulation in [0,1];
+    (3) a 64x64 crop-equivalent camera (cx,cy shifted) reproduces the corresponding pixels."""
+    m, f = fields["varied"]
+    c2w, intr = ring_cameras(16, 512, 512)
+    opts = ops.RenderOptions(mode="flat", num_samples=128)
+    rgb, depth, acc = ops.render_views(f, c2w[:2].cuda(), intr[:2].cuda(), 512, 512, opts, want_acc=True)
+    rgb1, depth1 = ops.render_views(f, c2w[1:2].cuda(), intr[1:2].cuda(), 512, 512, opts)
+    assert torch.equal(rgb[1], rgb1[0]) and torch.equal(depth[1], depth1[0])
+    assert float(rgb.min()) >= 0 and float(rgb.max()) <= 1 and float(acc.min()) >= 0 and float(acc.max()) <= 1 + 1e-5
+    edges = ops.piecewise_bin_edges(128, 0.05, 1000.0)
+    mids = ((edges[:-1] + edges[1:]) / 2).cuda()
+    assert float((depth.reshape(-1, 1) - mids[None]).abs().amin(dim=1).max()) == 0.0
+    # crop: pixel (y0+j, x0+i) of the full view == pixel (j, i) of a camera with the principal point shifted
+    x0, y0 = 200, 136
+    intr_c = intr[:1].clone()
+    intr_c[0, 2] -= x0
+    intr_c[0, 3] -= y0
+    rgb_c, depth_c = ops.render_views(f, c2w[:1].cuda(), intr_c.cuda(), 64, 64, opts)
+    assert torch.equal(rgb_c[0], rgb[0, y0:y0 + 64, x0:x0 + 64]) and torch.equal(depth_c[0], depth[0, y0:y0 + 64, x0:x0 + 64])
+    # and the oracle on that crop (64x64x128 finishes in seconds on CPU)
+    ref = R.render_view(m, c2w[0], float(intr_c[0, 0]), float(intr_c[0, 1]), float(intr_c[0, 2]), float(intr_c[0, 3]), 64, 64, "flat", 128)
+    assert rel_l2(rgb_c[0], ref["rgb"]) < TOL and rel_l2(depth_c[0], ref["depth"]) < TOL
