@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py — reference-grid views/sec on B200 (BASELINE.json metric).
+
+One "step" = one pass of the hot path over one synthetic reference grid (BASELINE config C2/C3):
+    K1  render 16 views 512x512, flat 128 samples/ray through the nerfacto field   (sgn_render_views)
+    K2/K3  AABB mask + elliptical dilation + depth condition                         (sgn_mask_condition)
+    K4  paste the tiles into the 2048x2048 image / mask / condition sheets           (sgn_sheet_paste)
+    K5-K9 one ControlNet-depth SDXL UNet step (CFG batch 2) on the sheet latent      (sgn_unet_*; when built)
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference's Python path (oracle port) on host cores
+
+Multi-GPU (launched by torchrun, one rank per GPU): weak scaling.  A step produces N grids; every rank renders
+a per-view shard (views v with v % N == rank) of EVERY grid, one NCCL all-gather assembles the tiles, and rank r
+pastes / denoises grid r.  Per-rank work is exactly one metric unit for every N.
+
+Timing: per-step CUDA events on the launching stream, L2 flushed (256 MiB memset) between steps outside the
+events, barrier + synchronize on both sides of the K timed steps, max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+# ---------------------------------------------------------------------------------------------- workload
+ROWS = COLS = 4
+VIEWS = ROWS * COLS
+H = W = 512
+SAMPLES = 128
+LEVELS, CORNERS, FEATS = 16, 8, 2
+RENDER_BYTES_PER_SAMPLE = LEVELS * CORNERS * FEATS * 4      # 1024 B of hash-table gathers
+RENDER_BYTES_PER_RAY = 52                                   # o, d, near, far in; rgb, depth, acc out
+UNET_TFLOP_PER_STEP = 103.96                                # UNet 35.91 + ControlNet 16.08 per sample, x2 CFG
+
+METRIC = "reference-grid views/sec (render+1 UNet step) @4x4x512^2"
+UNIT = "grids/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=float(d["hbm_gbs"]), tensor=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    source="measured")
+    return dict(hbm=6650.0, tensor=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi sampler running DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                                  ("sw_power_cap", 8)):
+                    if r[col].lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- reference arm
+def cpu_oracle_sample(rays_per_sample: int = 8192):
+    """Time the oracle (literal torch restatement of nerfstudio's torch nerfacto eval = the reference's Python
+    path) on a bounded sample of the C2 workload: `rays_per_sample` rays of view 0 x 128 samples."""
+    from oracle import nerfacto_ref as R
+    from tests.helpers import ring_cameras
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    m = R.make_model(0)
+    c2w, intr = ring_cameras(VIEWS, W, H)
+    rays = R.generate_rays(c2w[0], *intr[0].tolist(), W, H)
+    o, d = rays.origins[:rays_per_sample], rays.directions[:rays_per_sample]
+
+    def run():
+        t = time.perf_counter()
+        R.render_rays(m, o, d, "flat", SAMPLES)
+        return time.perf_counter() - t
+
+    return run, cores, rays_per_sample
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    run, cores, n = cpu_oracle_sample()
+    for _ in range(args.warmup):
+        run()
+    ts = [run() for _ in range(args.steps)]
+    per_grid = float(np.mean(ts)) / n * VIEWS * H * W          # render only: the UNet half is not in the sample
+    val = 1.0 / per_grid
+    sample = f"{n} rays x {SAMPLES} samples of view 0 (flat), oracle/nerfacto_ref.py, scaled to 16x512^2 rays; UNet step not included"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": per_grid * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C2 4x4 grid 512x512, flat 128 samples/ray (bounded CPU sample)"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------- CUDA arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-unet", action="store_true", help="time the render half only (profiling)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    from signerf_b200 import _lib, ops, synthetic
+    from signerf_b200.sheet import ReferenceSheetRenderer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: signerf_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N = world
+
+    fld = synthetic.random_field(seed=0, device=dev, dense=True, with_proposals=False)
+    layout = ops.SheetLayout(ROWS, COLS, H, W, 0)
+    ropts = ops.RenderOptions(mode="flat", num_samples=SAMPLES)
+    mopts = ops.MaskOptions()
+    sheet = ReferenceSheetRenderer(fld, layout, H, W, ropts, mopts)
+
+    # cameras of the N grids of one step: grid g is the benchmark ring rotated by g * 7 degrees
+    c2w_all, intr_all = [], []
+    for g in range(N):
+        c, i = synthetic.camera_ring(VIEWS, W, H, phi_deg=(7.0 * g, 300.0 + 7.0 * g))
+        c2w_all.append(c)
+        intr_all.append(i)
+    c2w_all = torch.stack(c2w_all)      # [N,16,3,4]
+    intr_all = torch.stack(intr_all)    # [N,16,4]
+    # per-view shard of every grid for this rank
+    mine = [v for v in range(VIEWS) if v % N == rank]
+    c2w_h = c2w_all[:, mine].reshape(-1, 3, 4).contiguous().pin_memory()
+    intr_h = intr_all[:, mine].reshape(-1, 4).contiguous().pin_memory()
+    c2w_d, intr_d = c2w_h.to(dev), intr_h.to(dev)
+    nv = c2w_d.shape[0]                 # == 16 for every N
+    assert nv == VIEWS
+
+    unet = None
+    if not args.no_unet:
+        try:
+            from signerf_b200 import unet as unet_mod
+            unet = unet_mod.BenchUNet(dev, sheet_hw=(layout.height, layout.width), seed=0)
+        except ImportError:
+            unet = None
+
+    tiles = torch.empty((N, VIEWS, H, W, 6), dtype=torch.float32, device=dev) if N > 1 else None
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    k1_events = []
+
+    def step(c2w, intr, time_k1=False):
+        if time_k1:
+            a, b = ev(), ev()
+            a.record()
+        rgb, depth = ops.render_views(fld, c2w, intr, H, W, ropts)
+        if time_k1:
+            b.record()
+            k1_events.append((a, b))
+        mask, cond, _ = ops.mask_condition(c2w, intr, depth, mopts)
+        if N > 1:
+            # pack [rgb3 | depth | cond | mask] per pixel and all-gather the per-view shards of all N grids
+            packed = torch.cat([rgb, depth, cond, mask.float()], dim=-1).view(N, len(mine), H, W, 6)
+            gathered = [torch.empty_like(packed) for _ in range(N)]
+            dist.all_gather(gathered, packed)
+            for r in range(N):
+                tiles[:, r::N] = gathered[r]
+            t = tiles[rank]
+            rgb, cond, mask = t[..., 0:3].contiguous(), t[..., 4:5].contiguous(), t[..., 5:6].contiguous()
+        b_ = sheet.paste(rgb, mask, cond, 0)
+        out = b_.image
+        if unet is not None:
+            out = unet.step(b_.image, b_.mask, b_.condition)
+        return out
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(c2w_d, intr_d)
+        flush.zero_()
+    sync_all()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    evs = []
+    sync_all()
+    for _ in range(args.steps):
+        a, b = ev(), ev()
+        a.record()
+        step(c2w_d, intr_d, time_k1=True)
+        b.record()
+        evs.append((a, b))
+        flush.zero_()
+    sync_all()
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    k1_ms = sum(a.elapsed_time(b) for a, b in k1_events) / len(k1_events)
+
+    # e2e: host cameras (pinned) -> device, full step, result read back to the host, every step
+    res_h = None
+    e2e_evs = []
+    sync_all()
+    for i in range(args.warmup + args.steps):
+        a, b = ev(), ev()
+        a.record()
+        c = c2w_h.to(dev, non_blocking=True)
+        it = intr_h.to(dev, non_blocking=True)
+        out = step(c, it)
+        if res_h is None:
+            res_h = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+        res_h.copy_(out, non_blocking=True)
+        b.record()
+        b.synchronize()
+        if i >= args.warmup:
+            e2e_evs.append((a, b))
+        flush.zero_()
+    sync_all()
+    e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_evs)
+
+    t = torch.tensor([total_ms, e2e_ms, k1_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms, k1_ms = t.tolist()
+
+    if rank == 0:
+        pk = peaks()
+        ms_per_step = total_ms / args.steps
+        value = N * args.steps / (total_ms / 1e3)
+        e2e_value = N * args.steps / (e2e_ms / 1e3)
+        k1_bytes = VIEWS * H * W * (SAMPLES * RENDER_BYTES_PER_SAMPLE + RENDER_BYTES_PER_RAY)
+        k1_gbs = k1_bytes / (k1_ms / 1e3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 gather/composite + f16 mma MLP (f32 accumulate)", "data": "synthetic",
+            "config": {"workload": "C3 4x4 grid of 512x512 views, flat 128 samples/ray, nerfacto field (16-level 2^19 hash + MLPs), "
+                                   "AABB mask + 50x50 dilation + depth condition, 2048x2048 sheet" +
+                                   (", + 1 SDXL+ControlNet UNet step (CFG 2)" if unet is not None else "; UNet step NOT YET BUILT (render half only)"),
+                       "views": VIEWS, "height": H, "width": W, "samples_per_ray": SAMPLES, "sheet": [layout.height, layout.width],
+                       "unet": unet is not None, "sharding": f"per-view x{N} + all-gather" if N > 1 else "single GPU",
+                       "l2": "256 MiB memset between steps, outside the timed events"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(c2w_h.numel() * 4 + intr_h.numel() * 4),
+                    "d2h_bytes_per_step": int(res_h.numel() * res_h.element_size())},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"kernel": "k_render_mma", "bound": "hbm", "achieved": k1_gbs, "peak": pk["hbm"], "unit": "GB/s",
+                         "frac": k1_gbs / pk["hbm"], "traffic": None, "peak_source": pk["source"],
+                         "ms_per_launch": k1_ms, "algorithmic_bytes_per_launch": k1_bytes},
+        }
+        if N == 1 and not args.no_cpu_baseline:
+            run, cores, n = cpu_oracle_sample()
+            run()
+            ts = [run() for _ in range(2)]
+            per_grid = float(np.mean(ts)) / n * VIEWS * H * W
+            line["cpu_baseline"] = {"value": 1.0 / per_grid, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{n} rays x {SAMPLES} samples of view 0 through oracle/nerfacto_ref.py, "
+                                              "scaled to 16x512^2 rays; render half only"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -415,8 +415,9 @@ using namespace sgn;
 
 extern "C" int sgn_render_views(const SgnField* f, const float* d_c2w, const float* d_intr, int V, int H, int W,
                                 const SgnRenderOpts* o, float* d_rgb, float* d_depth, float* d_acc, void* stream) {
-  SGN_CHECK_ARG(f && d_c2w && d_intr && o && d_rgb && d_depth, "null pointer");
+  SGN_CHECK_ARG(f && o, "null field/opts");
   SGN_CHECK_ARG(V >= 0 && H > 0 && W > 0, "bad image shape");
+  SGN_CHECK_ARG(V == 0 || (d_c2w && d_intr && d_rgb && d_depth), "null pointer");
   SGN_CHECK_ARG(o->mlp_mode == SGN_MLP_FP16_MMA || o->mlp_mode == SGN_MLP_FP32, "bad mlp_mode");
   SGN_CHECK_ARG(o->num_samples >= 1 && o->num_samples < kMaxBins, "num_samples must be 1..1024");
   SGN_CHECK_ARG(o->far_plane > o->near_plane && o->near_plane >= 0.f, "need 0 <= near < far");
@@ -485,9 +486,9 @@ extern "C" int sgn_render_views_host(const SgnField* f, const float* h_c2w, cons
 
 extern "C" int sgn_generate_rays(const float* d_c2w, const float* d_intr, int V, int H, int W, float* d_origins,
                                  float* d_directions, float* d_pixel_area, float* d_dir_norm, void* stream) {
-  SGN_CHECK_ARG(d_c2w && d_intr && d_origins && d_directions, "null pointer");
   SGN_CHECK_ARG(V >= 0 && H > 0 && W > 0, "bad image shape");
   if (V == 0) return SGN_OK;
+  SGN_CHECK_ARG(d_c2w && d_intr && d_origins && d_directions, "null pointer");
   size_t n = (size_t)V * H * W;
   int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)sm_count() * 8);
   k_generate_rays<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_c2w, d_intr, V, H, W, d_origins,
@@ -498,10 +499,11 @@ extern "C" int sgn_generate_rays(const float* d_c2w, const float* d_intr, int V,
 
 extern "C" int sgn_hash_encode(const SgnField* f, int which, const float* d_pos, int64_t N, int64_t* d_indices,
                                float* d_features, void* stream) {
-  SGN_CHECK_ARG(f && d_pos, "null pointer");
+  SGN_CHECK_ARG(f != nullptr, "null field");
   SGN_CHECK_ARG(which >= 0 && which <= f->num_proposals, "grid index out of range");
   SGN_CHECK_ARG(N >= 0, "negative N");
-  if (N == 0) return SGN_OK;
+  if (N == 0) return SGN_OK;  // empty input: pointers may be null
+  SGN_CHECK_ARG(d_pos != nullptr, "null pointer");
   const GridDev& g = which == 0 ? f->grid : f->h_prop[which - 1].grid;
   int64_t work = N * g.num_levels;
   int blocks = (int)std::min<int64_t>((work + 255) / 256, (int64_t)sm_count() * 8);
@@ -513,10 +515,11 @@ extern "C" int sgn_hash_encode(const SgnField* f, int which, const float* d_pos,
 
 extern "C" int sgn_field_eval(const SgnField* f, const float* d_pos, const float* d_dir, int64_t N, int mlp_mode,
                               float* d_density, float* d_rgb, void* stream) {
-  SGN_CHECK_ARG(f && d_pos && d_dir && d_density && d_rgb, "null pointer");
+  SGN_CHECK_ARG(f != nullptr, "null field");
   SGN_CHECK_ARG(N >= 0, "negative N");
   SGN_CHECK_ARG(mlp_mode == SGN_MLP_FP16_MMA || mlp_mode == SGN_MLP_FP32, "bad mlp_mode");
-  if (N == 0) return SGN_OK;
+  if (N == 0) return SGN_OK;  // empty input: pointers may be null
+  SGN_CHECK_ARG(d_pos && d_dir && d_density && d_rgb, "null pointer");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (mlp_mode == SGN_MLP_FP16_MMA) {
     size_t smem = mma_smem_bytes(0, true);

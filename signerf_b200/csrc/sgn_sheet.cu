@@ -283,17 +283,18 @@ using namespace sgn;
 
 extern "C" int sgn_dilate_ellipse(const uint8_t* d_in, int V, int H, int W, int kw, int kh, uint8_t* d_out,
                                   void* stream) {
-  SGN_CHECK_ARG(d_in && d_out, "null pointer");
   SGN_CHECK_ARG(V >= 0 && H > 0 && W > 0, "bad image shape");
   SGN_CHECK_ARG(kw >= 1 && kh >= 1, "kernel size must be >= 1");
   if (V == 0) return SGN_OK;
+  SGN_CHECK_ARG(d_in && d_out, "null pointer");
   return dilate_impl(d_in, V, H, W, kw, kh, d_out, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int sgn_mask_condition(const float* d_c2w, const float* d_intr, int V, int H, int W, const float* d_depth,
                                   const SgnMaskOpts* o, uint8_t* d_mask, float* d_cond, float* d_stats, void* stream) {
-  SGN_CHECK_ARG(d_c2w && d_intr && d_depth && o && d_mask && d_cond, "null pointer");
+  SGN_CHECK_ARG(o != nullptr, "null opts");
   SGN_CHECK_ARG(V >= 0 && H > 0 && W > 0, "bad image shape");
+  SGN_CHECK_ARG(V == 0 || (d_c2w && d_intr && d_depth && d_mask && d_cond), "null pointer");
   SGN_CHECK_ARG((o->dilate_w == 0) == (o->dilate_h == 0), "dilate_w/h must both be zero or both positive");
   if (V == 0) return SGN_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -326,7 +327,7 @@ extern "C" int sgn_mask_condition(const float* d_c2w, const float* d_intr, int V
 extern "C" int sgn_sheet_paste(const void* d_src, int src_u8, int V, int H, int W, int C, float* d_sheet, int sheet_h,
                                int sheet_w, int rows, int cols, int border, int tile_h, int tile_w, int first_cell,
                                float threshold, void* stream) {
-  SGN_CHECK_ARG(d_src && d_sheet, "null pointer");
+  SGN_CHECK_ARG(V == 0 || (d_src && d_sheet), "null pointer");
   SGN_CHECK_ARG(V >= 0 && H > 0 && W > 0 && C > 0 && tile_h > 0 && tile_w > 0, "bad shape");
   SGN_CHECK_ARG(rows > 0 && cols > 0 && border >= 0 && first_cell >= 0 && first_cell + V <= rows * cols,
                 "tiles do not fit the grid");
@@ -360,9 +361,9 @@ extern "C" int sgn_sheet_cut(const float* d_sheet, int sheet_h, int sheet_w, int
 
 extern "C" int sgn_blend_masked(const float* d_edited, const float* d_base, const float* d_mask, int64_t npix, int C,
                                 float* d_out, void* stream) {
-  SGN_CHECK_ARG(d_edited && d_base && d_mask && d_out, "null pointer");
   SGN_CHECK_ARG(npix >= 0 && C > 0, "bad shape");
   if (npix == 0) return SGN_OK;
+  SGN_CHECK_ARG(d_edited && d_base && d_mask && d_out, "null pointer");
   k_blend<<<grid_for((size_t)npix * C, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_edited, d_base, d_mask,
                                                                                               (size_t)npix, C, d_out);
   SGN_LAUNCH_CHECK();
@@ -370,9 +371,9 @@ extern "C" int sgn_blend_masked(const float* d_edited, const float* d_base, cons
 }
 
 extern "C" int sgn_quantize_u8(const float* d_in, int64_t n, uint8_t* d_out, void* stream) {
-  SGN_CHECK_ARG(d_in && d_out, "null pointer");
   SGN_CHECK_ARG(n >= 0, "negative n");
   if (n == 0) return SGN_OK;
+  SGN_CHECK_ARG(d_in && d_out, "null pointer");
   k_quantize<<<grid_for((size_t)n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_in, (size_t)n, d_out);
   SGN_LAUNCH_CHECK();
   return SGN_OK;

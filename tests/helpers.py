@@ -47,3 +47,15 @@ def ring_cameras(n, width, height, radius=0.5):
     c2w[:, :, 0], c2w[:, :, 1], c2w[:, :, 2], c2w[:, :, 3] = x, y, z, pos
     intr = torch.tensor([[float(width), float(width), width / 2.0, height / 2.0]]).repeat(n, 1)
     return c2w, intr
+
+
+def depth_agreement(depth: torch.Tensor, ref: torch.Tensor):
+    """Median depth is a discrete pick (the mid-point of the first bin whose cumulative weight reaches 0.5), so a
+    1-ulp change of a weight can move a ray by a whole bin.  Returns (fraction of rays that picked another bin,
+    relative L2 over the rays that picked the same bin)."""
+    d = depth.detach().double().cpu().flatten()
+    r = ref.detach().double().cpu().flatten()
+    moved = (d - r).abs() > 1e-6 * r.abs()
+    same = ~moved
+    err = float((d[same] - r[same]).norm() / r[same].norm().clamp_min(1e-30)) if bool(same.any()) else 0.0
+    return float(moved.double().mean()), err
