@@ -49,13 +49,14 @@ def ring_cameras(n, width, height, radius=0.5):
     return c2w, intr
 
 
-def depth_agreement(depth: torch.Tensor, ref: torch.Tensor):
+def depth_agreement(depth: torch.Tensor, ref: torch.Tensor, same_bin_rtol: float = 1e-6):
     """Median depth is a discrete pick (the mid-point of the first bin whose cumulative weight reaches 0.5), so a
-    1-ulp change of a weight can move a ray by a whole bin.  Returns (fraction of rays that picked another bin,
+    1-ulp change of a weight can move a ray by a whole bin.  `same_bin_rtol` separates "same bin" from "another bin":
+    1e-6 for the shared flat bins (identical edges), 1e-3 for PDF-resampled edges (they carry fp32 rounding).  Returns (fraction of rays that picked another bin,
     relative L2 over the rays that picked the same bin)."""
     d = depth.detach().double().cpu().flatten()
     r = ref.detach().double().cpu().flatten()
-    moved = (d - r).abs() > 1e-6 * r.abs()
+    moved = (d - r).abs() > same_bin_rtol * r.abs()
     same = ~moved
     err = float((d[same] - r[same]).norm() / r[same].norm().clamp_min(1e-30)) if bool(same.any()) else 0.0
     return float(moved.double().mean()), err
