@@ -167,6 +167,36 @@ int sgn_blend_masked(const float* d_edited, const float* d_base, const float* d_
  * uint8(x*255) by truncation with wrap-around, exactly numpy's float32 -> uint8 cast.          */
 int sgn_quantize_u8(const float* d_in, int64_t n, uint8_t* d_out, void* stream);
 
+/* ------------------------------------------------------------------ K5-K9: SDXL / ControlNet UNet step (A11-A13) */
+/* The reference reaches this arithmetic over HTTP: Diffuser._diffuse_remote_sdwebui_controlnet POSTs the sheet to an
+ * A1111 SD-WebUI server (signerf/diffuser/diffuser.py:116-195) which runs sgm's UNetModel + the ControlNet extension.
+ * The in-process replacement plugs into the hook the reference leaves open, Diffuser._custom (diffuser.py:102-113);
+ * signerf_b200/unet.py walks the UNet graph and calls the operators below.
+ * Activations are NHWC ("tokens x channels"): the fp32 residual stream [B*H*W, C] and fp16 GEMM operands. */
+
+/* Epilogue of the tensor-core contractions:  y = acc + bias[n] + rowbias[m / rows_per_batch][n] + residual[m][n]. */
+typedef struct SgnEpilogue {
+  const float* d_bias;     /* [N] or NULL */
+  const float* d_rowbias;  /* [M / rows_per_batch, N] or NULL: ResBlock's per-image emb_layers output */
+  int rows_per_batch;
+  const float* d_residual; /* [M, ldo] fp32 or NULL; may alias the output (in-place residual add) */
+  int64_t ldo;             /* output (and residual) row stride in elements; 0 = dense */
+  int out_f16;             /* 0: fp32 output, 1: fp16 output */
+  int geglu;               /* 1: weight rows interleaved (value_j, gate_j): out[m][j] = value * gelu(gate), fp16 [M, N/2]
+                              (sgm GEGLU: `x, gate = proj(x).chunk(2); x * F.gelu(gate)`) */
+  int nchw;                /* conv only: store fp32 NCHW [B, N, H, W] (the UNet's 4-channel output conv) */
+} SgnEpilogue;
+
+/* nn.Linear / 1x1 conv on tcgen05: out[M,N] = A[M,K] . W[N,K]^T (+ epilogue).  A, W fp16 row-major with row strides
+ * lda / ldw (elements, multiples of 8); fp32 accumulation in TMEM. */
+int sgn_gemm_f16(const void* d_a, int64_t lda, const void* d_w, int64_t ldw, int M, int N, int K,
+                 const SgnEpilogue* ep, void* d_out, void* stream);
+
+/* 3x3 / stride 1 / pad 1 convolution as an implicit GEMM on tcgen05.  d_x fp16 NHWC [B,H,W,C] (C % 64 == 0),
+ * d_w fp16 [N, 9*C] with k = (ky*3 + kx)*C + c  (torch weight.permute(0,2,3,1)); out [B*H*W, N]. */
+int sgn_conv3x3_f16(const void* d_x, const void* d_w, int B, int H, int W, int C, int N, const SgnEpilogue* ep,
+                    void* d_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

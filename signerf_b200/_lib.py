@@ -56,6 +56,12 @@ class SgnMaskOpts(C.Structure):
                 ("manual_min", C.c_float), ("manual_max", C.c_float)]
 
 
+class SgnEpilogue(C.Structure):
+    _fields_ = [("d_bias", C.c_void_p), ("d_rowbias", C.c_void_p), ("rows_per_batch", C.c_int),
+                ("d_residual", C.c_void_p), ("ldo", C.c_int64), ("out_f16", C.c_int), ("geglu", C.c_int),
+                ("nchw", C.c_int)]
+
+
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
 # name -> (restype, argtypes); every symbol include/signerf_b200.h declares.
@@ -76,6 +82,8 @@ SIGNATURES = {
     "sgn_sheet_cut": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "sgn_blend_masked": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp]),
     "sgn_quantize_u8": (_i, [_vp, _i64, _vp, _vp]),
+    "sgn_gemm_f16": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, C.POINTER(SgnEpilogue), _vp, _vp]),
+    "sgn_conv3x3_f16": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.POINTER(SgnEpilogue), _vp, _vp]),
 }
 
 _lib: Optional[C.CDLL] = None

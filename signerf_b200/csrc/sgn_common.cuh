@@ -14,6 +14,7 @@ namespace sgn {
 
 void set_error(const std::string& msg);
 extern std::atomic<uint64_t> g_launches;
+int sm_count();  // SMs of the current device (sgn_render.cu)
 inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
 #define SGN_CHECK_ARG(cond, msg)                                   \

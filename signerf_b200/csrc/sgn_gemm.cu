@@ -1,0 +1,428 @@
+// K5: the dense contractions of the SDXL / ControlNet UNet on the 5th-generation tensor cores.
+//
+//   C[M,N] = A[M,K] . W[N,K]^T  (+ bias, + per-image row bias, + residual, GEGLU)      fp16 x fp16 -> fp32 (TMEM)
+//
+// One persistent warp-specialised kernel serves both operand shapes:
+//   linear : A is a row-major [M,K] fp16 matrix (tokens x channels)              -> 2-D TMA tiles
+//   conv3x3: A is an NHWC fp16 image, M = B*H*W output pixels, K = 9*Cin; the im2col is IMPLICIT: for tap (dy,dx)
+//            and channel block c0 the producer issues one 4-D TMA box {64 ch, 16 px, 8 rows, 1 image} at
+//            (c0, x0+dx-1, y0+dy-1, b); out-of-bounds rows/columns are zero-filled by TMA = the conv's zero padding.
+// Roles: warp 0 = TMA producer (1 lane), warp 1 = tcgen05.mma issuer (1 lane) + TMEM allocator, warps 2-5 = epilogue
+// (TMEM -> registers -> global).  4-stage smem ring (full/empty mbarriers), 2 accumulator buffers in TMEM
+// (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <algorithm>
+#include <vector>
+
+#include "sgn_common.cuh"
+#include "sgn_tc.cuh"
+
+namespace sgn {
+
+// ------------------------------------------------------------------ tensor maps (host)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+int encode_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                const uint32_t* box, const uint32_t* elem_strides) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+    return SGN_ERR_NO_DEVICE;
+  }
+  cuuint64_t d[5], s[5];
+  cuuint32_t b[5], e[5];
+  for (int i = 0; i < rank; ++i) {
+    d[i] = dims[i];
+    b[i] = box[i];
+    e[i] = elem_strides ? elem_strides[i] : 1;
+    if (i + 1 < rank) s[i] = strides_bytes[i];
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, e,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return SGN_ERR_CUDA;
+  }
+  return SGN_OK;
+}
+
+// ------------------------------------------------------------------ kernel
+constexpr int kGemmThreads = 192;
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kStages = 4;
+constexpr int kStageA = kBM * kBK * 2;    // 16 KB
+constexpr int kStageB = 256 * kBK * 2;    // 32 KB (block_n <= 256)
+constexpr int kAccStride = 256;           // TMEM columns between the two accumulator buffers
+constexpr int kConvTileW = 16, kConvTileH = 8;
+constexpr size_t kGemmSmem = 1024 + (size_t)kStages * (kStageA + kStageB) + 256;
+
+struct GemmParams {
+  int M, N, K;  // N = weight rows covered by tiles (multiple of block_n); n_valid <= N columns are stored
+  int n_valid;
+  int block_n, num_m_tiles, num_n_tiles, num_k_blocks;
+  int conv, H, W, cin_blocks, tiles_x, tiles_y;
+  const float* bias;
+  const float* rowbias;
+  int rows_per_batch;
+  const float* residual;
+  void* out;
+  long long ldo;
+  int out_f16, geglu, nchw;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+
+// One 16-column group of one output row.
+__device__ __forceinline__ void epilogue16(const GemmParams& p, const uint32_t* acc, long long m, int b, int n0) {
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
+  if (n0 + 16 <= p.n_valid && !p.nchw) {
+    if (p.bias) {
+      const float4* bp = reinterpret_cast<const float4*>(p.bias + n0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float4 t = __ldg(bp + q);
+        v[4 * q] += t.x, v[4 * q + 1] += t.y, v[4 * q + 2] += t.z, v[4 * q + 3] += t.w;
+      }
+    }
+    if (p.rowbias) {
+      const float4* bp = reinterpret_cast<const float4*>(p.rowbias + (size_t)b * p.n_valid + n0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float4 t = __ldg(bp + q);
+        v[4 * q] += t.x, v[4 * q + 1] += t.y, v[4 * q + 2] += t.z, v[4 * q + 3] += t.w;
+      }
+    }
+    if (p.geglu) {  // weight rows interleaved (value, gate): out[n/2] = value * gelu(gate)
+      __half2 h[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        h[q] = __floats2half2_rn(v[4 * q] * gelu_erf(v[4 * q + 1]), v[4 * q + 2] * gelu_erf(v[4 * q + 3]));
+      *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + m * p.ldo + (n0 >> 1)) =
+          *reinterpret_cast<uint4*>(h);
+      return;
+    }
+    if (p.residual) {
+      const float4* rp = reinterpret_cast<const float4*>(p.residual + m * p.ldo + n0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float4 t = rp[q];
+        v[4 * q] += t.x, v[4 * q + 1] += t.y, v[4 * q + 2] += t.z, v[4 * q + 3] += t.w;
+      }
+    }
+    if (p.out_f16) {
+      __half2 h[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) h[q] = __floats2half2_rn(v[2 * q], v[2 * q + 1]);
+      uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + m * p.ldo + n0);
+      op[0] = reinterpret_cast<uint4*>(h)[0];
+      op[1] = reinterpret_cast<uint4*>(h)[1];
+    } else {
+      float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + m * p.ldo + n0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) op[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+    return;
+  }
+  // ragged / NCHW tail (the UNet's 4-channel output conv): scalar, bounds-checked, fp32 only
+  for (int j = 0; j < 16; ++j) {
+    int n = n0 + j;
+    if (n >= p.n_valid) break;
+    float x = v[j];
+    if (p.bias) x += __ldg(p.bias + n);
+    if (p.rowbias) x += __ldg(p.rowbias + (size_t)b * p.n_valid + n);
+    if (p.nchw) {
+      long long hw = (long long)p.H * p.W;
+      long long pix = m - (long long)b * hw;
+      long long o = ((long long)b * p.n_valid + n) * hw + pix;
+      if (p.residual) x += p.residual[o];
+      reinterpret_cast<float*>(p.out)[o] = x;
+    } else {
+      if (p.residual) x += p.residual[m * p.ldo + n];
+      if (p.out_f16) reinterpret_cast<__half*>(p.out)[m * p.ldo + n] = __float2half_rn(x);
+      else reinterpret_cast<float*>(p.out)[m * p.ldo + n] = x;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStages * kStageA;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + kStages * kStageB);
+  uint64_t* empty = full + kStages;
+  uint64_t* tfull = empty + kStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tc::tma_prefetch_desc(&tmA);
+    tc::tma_prefetch_desc(&tmB);
+    for (int s = 0; s < kStages; ++s) {
+      tc::mbar_init(&full[s], 1);
+      tc::mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(&tfull[s], 1);
+      tc::mbar_init(&tempty[s], 4);
+    }
+    tc::mbar_fence_init();
+  }
+  if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---------------- TMA producer
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = kStageA + (uint32_t)p.block_n * (kBK * 2);
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int m_tile = t / p.num_n_tiles, n_tile = t - m_tile * p.num_n_tiles;
+        int b = 0, x0 = 0, y0 = 0;
+        if (p.conv) {
+          b = m_tile / tiles_per_img;
+          int r = m_tile - b * tiles_per_img;
+          int ty = r / p.tiles_x;
+          y0 = ty * kConvTileH;
+          x0 = (r - ty * p.tiles_x) * kConvTileW;
+        }
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          tc::mbar_wait(&empty[stage], phase ^ 1);
+          tc::mbar_expect_tx(&full[stage], tx_bytes);
+          if (p.conv) {
+            int tap = kb / p.cin_blocks, cb = kb - tap * p.cin_blocks;
+            int dy = tap / 3, dx = tap - dy * 3;
+            tc::tma_load_4d(sA + stage * kStageA, &tmA, &full[stage], cb * kBK, x0 + dx - 1, y0 + dy - 1, b);
+          } else {
+            tc::tma_load_2d(sA + stage * kStageA, &tmA, &full[stage], kb * kBK, m_tile * kBM);
+          }
+          tc::tma_load_2d(sB + stage * kStageB, &tmB, &full[stage], kb * kBK, n_tile * p.block_n);
+          if (++stage == kStages) stage = 0, phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---------------- MMA issuer
+      const uint32_t idesc = tc::umma_idesc_f16(kBM, p.block_n, false, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int i = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+        const int buf = i & 1;
+        const uint32_t ph = (i >> 1) & 1;
+        tc::mbar_wait(&tempty[buf], ph ^ 1);
+        tc::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * kAccStride;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          tc::mbar_wait(&full[stage], phase);
+          tc::tc_fence_after();
+          const uint64_t da = tc::umma_desc_sw128(tc::smem_u32(sA + stage * kStageA));
+          const uint64_t db = tc::umma_desc_sw128(tc::smem_u32(sB + stage * kStageB));
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k)  // +32 B per K=16 step inside the 128-B swizzled row
+            tc::umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          tc::umma_commit(&empty[stage]);
+          if (++stage == kStages) stage = 0, phase ^= 1;
+        }
+        tc::umma_commit(&tfull[buf]);
+      }
+    }
+  } else {  // ---------------- epilogue warps 2..5: TMEM lane quarter = warp % 4
+    const int lane_base = (warp & 3) * 32;
+    const int row = lane_base + lane;
+    int i = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+      const int buf = i & 1;
+      const uint32_t ph = (i >> 1) & 1;
+      const int m_tile = t / p.num_n_tiles, n_tile = t - m_tile * p.num_n_tiles;
+      long long m;
+      int b;
+      bool valid;
+      if (p.conv) {
+        b = m_tile / tiles_per_img;
+        int r = m_tile - b * tiles_per_img;
+        int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+        int y = ty * kConvTileH + row / kConvTileW, x = tx * kConvTileW + row % kConvTileW;
+        valid = y < p.H && x < p.W;
+        m = ((long long)b * p.H + y) * p.W + x;
+      } else {
+        m = (long long)m_tile * kBM + row;
+        valid = m < p.M;
+        b = p.rows_per_batch > 0 ? (int)(m / p.rows_per_batch) : 0;
+      }
+      tc::mbar_wait(&tfull[buf], ph);
+      tc::tc_fence_after();
+      const uint32_t taddr = tmem_base + buf * kAccStride + ((uint32_t)lane_base << 16);
+      const int n_base = n_tile * p.block_n;
+      int c0 = 0;
+      for (; c0 + 32 <= p.block_n; c0 += 32) {
+        uint32_t acc[32];
+        tc::tmem_ld32(taddr + c0, acc);
+        tc::tmem_ld_wait();
+        if (valid) {
+          epilogue16(p, acc, m, b, n_base + c0);
+          epilogue16(p, acc + 16, m, b, n_base + c0 + 16);
+        }
+      }
+      if (c0 < p.block_n) {
+        uint32_t acc[16];
+        tc::tmem_ld16(taddr + c0, acc);
+        tc::tmem_ld_wait();
+        if (valid) epilogue16(p, acc, m, b, n_base + c0);
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&tempty[buf]);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// block_n: a divisor of N (multiple of 16, <= 256) minimising waves x per-tile cost.
+static int pick_block_n(long long m_tiles, int N) {
+  int best = 0;
+  double best_cost = 1e30;
+  const int sms = sm_count();
+  for (int bn = 256; bn >= 16; bn -= 16) {
+    if (N % bn) continue;
+    long long tiles = m_tiles * (N / bn);
+    long long waves = (tiles + sms - 1) / sms;
+    double cost = (double)waves * (bn + 48.0);  // ~48 columns' worth of fixed per-tile overhead
+    if (cost < best_cost) best_cost = cost, best = bn;
+  }
+  return best;
+}
+
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SGN_CUDA(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+    attr_set = true;
+  }
+  int total = p.num_m_tiles * p.num_n_tiles;
+  int grid = std::min(total, sm_count());
+  k_gemm_tc<<<grid, kGemmThreads, kGemmSmem, st>>>(tmA, tmB, p);
+  SGN_LAUNCH_CHECK();
+  return SGN_OK;
+}
+
+static int fill_epilogue(GemmParams& p, const SgnEpilogue* ep, int n_valid, void* d_out) {
+  p.bias = ep ? ep->d_bias : nullptr;
+  p.rowbias = ep ? ep->d_rowbias : nullptr;
+  p.rows_per_batch = ep ? ep->rows_per_batch : 0;
+  p.residual = ep ? ep->d_residual : nullptr;
+  p.out_f16 = ep ? ep->out_f16 : 0;
+  p.geglu = ep ? ep->geglu : 0;
+  p.nchw = ep ? ep->nchw : 0;
+  p.out = d_out;
+  long long ld = ep ? ep->ldo : 0;
+  p.ldo = ld > 0 ? ld : (p.geglu ? n_valid / 2 : n_valid);
+  SGN_CHECK_ARG(!p.rowbias || p.rows_per_batch > 0, "rowbias needs rows_per_batch");
+  SGN_CHECK_ARG(!p.geglu || (n_valid % 16 == 0 && !p.residual && !p.nchw), "geglu needs N % 16 == 0 and no residual");
+  SGN_CHECK_ARG(!p.nchw || !p.out_f16, "nchw output is fp32 only");
+  SGN_CHECK_ARG((reinterpret_cast<uintptr_t>(d_out) & 15) == 0, "output must be 16-byte aligned");
+  SGN_CHECK_ARG(p.nchw || n_valid % 16 != 0 || (p.ldo % (p.out_f16 || p.geglu ? 8 : 4)) == 0, "ldo breaks 16-byte rows");
+  return SGN_OK;
+}
+
+}  // namespace sgn
+
+using namespace sgn;
+
+extern "C" int sgn_gemm_f16(const void* d_a, int64_t lda, const void* d_w, int64_t ldw, int M, int N, int K,
+                            const SgnEpilogue* ep, void* d_out, void* stream) {
+  SGN_CHECK_ARG(M >= 0 && N > 0 && K > 0, "bad GEMM shape");
+  if (M == 0) return SGN_OK;
+  SGN_CHECK_ARG(d_a && d_w && d_out, "null pointer");
+  SGN_CHECK_ARG(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0 && lda >= K && ldw >= K, "K and strides must be multiples of 8");
+  SGN_CHECK_ARG((reinterpret_cast<uintptr_t>(d_a) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_w) & 15) == 0,
+                "operands must be 16-byte aligned");
+  GemmParams p{};
+  p.M = M, p.K = K, p.n_valid = N;
+  int n_rows = (N + 15) / 16 * 16;  // weight rows past N are zero-filled by TMA
+  p.N = n_rows;
+  p.num_m_tiles = (M + kBM - 1) / kBM;
+  p.block_n = pick_block_n(p.num_m_tiles, n_rows);
+  p.num_n_tiles = n_rows / p.block_n;
+  p.num_k_blocks = (K + kBK - 1) / kBK;
+  p.conv = 0, p.tiles_x = p.tiles_y = 1;
+  int rc = fill_epilogue(p, ep, N, d_out);
+  if (rc) return rc;
+  CUtensorMap tmA, tmB;
+  uint64_t da[2] = {(uint64_t)K, (uint64_t)M}, sa[1] = {(uint64_t)lda * 2};
+  uint32_t ba[2] = {kBK, kBM};
+  rc = encode_tmap(&tmA, d_a, 2, da, sa, ba, nullptr);
+  if (rc) return rc;
+  uint64_t dw[2] = {(uint64_t)K, (uint64_t)N}, sw[1] = {(uint64_t)ldw * 2};
+  uint32_t bw[2] = {kBK, (uint32_t)p.block_n};
+  rc = encode_tmap(&tmB, d_w, 2, dw, sw, bw, nullptr);
+  if (rc) return rc;
+  return launch_gemm(tmA, tmB, p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int sgn_conv3x3_f16(const void* d_x, const void* d_w, int B, int H, int W, int C, int N,
+                               const SgnEpilogue* ep, void* d_out, void* stream) {
+  SGN_CHECK_ARG(B >= 0 && H > 0 && W > 0 && C > 0 && N > 0, "bad conv shape");
+  if (B == 0) return SGN_OK;
+  SGN_CHECK_ARG(d_x && d_w && d_out, "null pointer");
+  SGN_CHECK_ARG(C % kBK == 0, "tensor-core conv needs Cin % 64 == 0 (use sgn_conv2d_direct otherwise)");
+  SGN_CHECK_ARG((reinterpret_cast<uintptr_t>(d_x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_w) & 15) == 0,
+                "operands must be 16-byte aligned");
+  GemmParams p{};
+  p.M = B * H * W, p.K = 9 * C, p.n_valid = N;
+  int n_rows = (N + 15) / 16 * 16;
+  p.N = n_rows;
+  p.conv = 1, p.H = H, p.W = W, p.cin_blocks = C / kBK;
+  p.tiles_x = (W + kConvTileW - 1) / kConvTileW;
+  p.tiles_y = (H + kConvTileH - 1) / kConvTileH;
+  p.num_m_tiles = B * p.tiles_x * p.tiles_y;
+  p.block_n = pick_block_n(p.num_m_tiles, n_rows);
+  p.num_n_tiles = n_rows / p.block_n;
+  p.num_k_blocks = 9 * p.cin_blocks;
+  int rc = fill_epilogue(p, ep, N, d_out);
+  if (rc) return rc;
+  if (p.rowbias && p.rows_per_batch != H * W) {
+    set_error("invalid argument: conv rowbias is per image (rows_per_batch must be H*W)");
+    return SGN_ERR_INVALID_ARG;
+  }
+  CUtensorMap tmA, tmB;
+  uint64_t da[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  uint64_t sa[3] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+  uint32_t ba[4] = {kBK, kConvTileW, kConvTileH, 1};
+  rc = encode_tmap(&tmA, d_x, 4, da, sa, ba, nullptr);
+  if (rc) return rc;
+  uint64_t dw[2] = {(uint64_t)9 * C, (uint64_t)N}, sw[1] = {(uint64_t)9 * C * 2};
+  uint32_t bw[2] = {kBK, (uint32_t)p.block_n};
+  rc = encode_tmap(&tmB, d_w, 2, dw, sw, bw, nullptr);
+  if (rc) return rc;
+  return launch_gemm(tmA, tmB, p, reinterpret_cast<cudaStream_t>(stream));
+}

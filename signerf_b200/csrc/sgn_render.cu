@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(kThreads) k_field_eval_f32(const GridDev grid,
 
 // ------------------------------------------------------------------------------------------------
 // host helpers
-static int sm_count() {
+int sm_count() {
   static int n = 0;
   if (!n) {
     int dev = 0;
