@@ -197,6 +197,12 @@ int sgn_gemm_f16(const void* d_a, int64_t lda, const void* d_w, int64_t ldw, int
 int sgn_conv3x3_f16(const void* d_x, const void* d_w, int B, int H, int W, int C, int N, const SgnEpilogue* ep,
                     void* d_out, void* stream);
 
+/* sgm CrossAttention core (head_dim 64): out = softmax(Q K^T * scale) V per (image, head), on tcgen05.
+ * Q [B*T_q, ldq], K / V [B*T_kv, ldk / ldv], out [B*T_q, ldo], all fp16; head h uses columns [64h, 64h+64) of each
+ * (so Q/K/V may be column slices of one fused projection output).  Any T_q, T_kv >= 1 (77-token context included). */
+int sgn_attention_f16(const void* d_q, int64_t ldq, const void* d_k, int64_t ldk, const void* d_v, int64_t ldv,
+                      int B, int heads, int T_q, int T_kv, float scale, void* d_out, int64_t ldo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

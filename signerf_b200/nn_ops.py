@@ -81,3 +81,19 @@ def conv3x3_f16(x: Tensor, w: Tensor, bias: Optional[Tensor] = None, *, rowbias:
         _lib.check(_lib.load().sgn_conv3x3_f16(_ptr(x), _ptr(w), B, H, W, Cin, N, C.byref(e), _ptr(out),
                                                _stream(x.device)))
     return out
+
+
+def attention_f16(q: Tensor, k: Tensor, v: Tensor, batch: int, heads: int, out: Optional[Tensor] = None) -> Tensor:
+    """softmax(q k^T / 8) v per (image, head); q [B*Tq, >=64*heads], k / v [B*Tkv, ...] fp16 (column-slice views of a
+    fused projection are fine: only the last dimension must be contiguous) -> [B*Tq, 64*heads] fp16."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        if not t.is_cuda or t.dtype != torch.float16 or t.stride(1) != 1:
+            raise ValueError(f"{n} must be a CUDA fp16 matrix with unit column stride")
+    Tq, Tkv = q.shape[0] // batch, k.shape[0] // batch
+    if out is None:
+        out = torch.empty((q.shape[0], heads * 64), dtype=torch.float16, device=q.device)
+    with torch.cuda.device(q.device):
+        _lib.check(_lib.load().sgn_attention_f16(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0),
+                                                 batch, heads, Tq, Tkv, 0.125, _ptr(out), out.stride(0),
+                                                 _stream(q.device)))
+    return out
