@@ -203,6 +203,55 @@ int sgn_conv3x3_f16(const void* d_x, const void* d_w, int B, int H, int W, int C
 int sgn_attention_f16(const void* d_q, int64_t ldq, const void* d_k, int64_t ldk, const void* d_v, int64_t ldv,
                       int B, int heads, int T_q, int T_kv, float scale, void* d_out, int64_t ldo, void* stream);
 
+/* GroupNorm (sgm `normalization` = GroupNorm32(32, C), eps 1e-5; SpatialTransformer.norm eps 1e-6) + optional SiLU.
+ * d_x fp32 [B, HW, C] -> d_out fp16 [B, HW, C].  d_ws: scratch of sgn_group_norm_ws_doubles(B, HW, groups) doubles
+ * (per-chunk partial sums, reduced in a fixed order: results are run-to-run bit-identical). */
+int64_t sgn_group_norm_ws_doubles(int B, int HW, int groups);
+int sgn_group_norm_f16(const float* d_x, int B, int HW, int C, int groups, float eps, const float* d_gamma,
+                       const float* d_beta, int act_silu, double* d_ws, void* d_out, void* stream);
+/* nn.LayerNorm(C) over the last dimension: fp32 [M, C] -> fp16 [M, C]. */
+int sgn_layer_norm_f16(const float* d_x, int64_t M, int C, float eps, const float* d_gamma, const float* d_beta,
+                       void* d_out, void* stream);
+/* fp32 -> fp16 cast of n elements (n % 4 == 0). */
+int sgn_cast_f16(const float* d_x, int64_t n, void* d_out, void* stream);
+/* sgm Upsample: F.interpolate(scale_factor=2, mode="nearest"); fp32 NHWC [B,H,W,C] -> fp16 NHWC [B,2H,2W,C]. */
+int sgn_upsample2x_f16(const float* d_x, int B, int H, int W, int C, void* d_out, void* stream);
+/* torch.cat([a, b + scale*b2], dim=channel) on NHWC fp32: the UNet decoder's skip concat with the ControlNet residual
+ * folded in (sd-webui-controlnet hook: `h = cat([h, hs.pop() + control.pop()])`).  d_b2 may be NULL. */
+int sgn_concat_f32(const float* d_a, int Ca, const float* d_b, const float* d_b2, float scale, int Cb, int64_t P,
+                   float* d_out, void* stream);
+/* y += a * x (ControlNet middle-block residual). */
+int sgn_axpy_f32(const float* d_x, float a, int64_t n, float* d_y, void* stream);
+/* im2col of sgm Downsample (3x3 / stride 2 / pad 1): fp32 NHWC [B,H,W,C] -> fp16 [B*Ho*Wo, 9*C], feeding sgn_gemm_f16. */
+int sgn_im2col3x3_s2_f16(const float* d_x, int B, int H, int W, int C, void* d_out, void* stream);
+/* Direct fp32 3x3 / pad 1 conv for channel counts the tensor-core path does not take (UNet conv_in 4->320, ControlNet
+ * input_hint_block 3->16->...->256).  d_x fp32 NHWC or NCHW (in_nchw), d_w fp32 [Cout,3,3,Cin]; out NHWC fp32 / fp16
+ * = act(conv + bias + residual[b % res_batch]) (ControlNet: `h = conv_in(x) + guided_hint`, one hint per CFG pair;
+ * res_batch 0 = B). */
+int sgn_conv3x3_direct(const float* d_x, int in_nchw, const float* d_w, const float* d_bias, const float* d_residual,
+                       int res_batch, int B, int H, int W, int Cin, int Cout, int stride, int act_silu, int out_f16,
+                       void* d_out, void* stream);
+/* out[b] = act_out(W act_in(x[b]) + bias (+ residual[b])) for B <= 8 rows, fp32 (time_embed, label_emb, emb_layers). */
+int sgn_linear_small(const float* d_x, const float* d_w, const float* d_bias, const float* d_residual, int B, int N,
+                     int K, int silu_in, int silu_out, float* d_out, void* stream);
+/* sgm timestep_embedding(t, dim, max_period=10000): [cos | sin]. */
+int sgn_timestep_embedding(const float* d_t, int B, int dim, float* d_out, void* stream);
+
+/* K9 (A13): one sampler update on latents [B,C,H,W] fp32, fused: classifier-free guidance over d_eps = [cond | uncond]
+ * (2*B*C*H*W), k-diffusion eps -> denoised, A1111 inpaint blend `denoised = init*mask + (1-mask)*denoised`
+ * (d_mask [B,1,H,W], NULL = no blend) and the Euler-ancestral step x' = x + d*(sigma_down - sigma) + noise*sigma_up
+ * (d_noise NULL = no noise). d_denoised may be NULL. */
+int sgn_cfg_euler_step(const float* d_x, const float* d_eps, const float* d_init, const float* d_mask,
+                       const float* d_noise, int B, int C, int H, int W, float cfg_scale, float sigma, float sigma_down,
+                       float sigma_up, float* d_x_out, float* d_denoised, void* stream);
+
+/* out[r*n + i] = scale * x[i], r < repeats: A1111 CFGDenoiser's x_in = cat([x, x]) * c_in. */
+int sgn_scale_repeat_f32(const float* d_x, int64_t n, float scale, int repeats, float* d_out, void* stream);
+/* Sheet -> denoiser conditioning (diffuser.py:121-130, :146-166): d_hint [3,Hs,Ws] = uint8(cond*255)/255 replicated
+ * (tensor_to_image truncation, preprocessor "none"); d_lat_mask [Hs/8,Ws/8] = 1 - round(8x8 box mean of the mask). */
+int sgn_sheet_to_conditioning(const float* d_cond, const float* d_mask, int Hs, int Ws, float* d_hint,
+                              float* d_lat_mask, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -85,6 +85,20 @@ SIGNATURES = {
     "sgn_gemm_f16": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, C.POINTER(SgnEpilogue), _vp, _vp]),
     "sgn_conv3x3_f16": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.POINTER(SgnEpilogue), _vp, _vp]),
     "sgn_attention_f16": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _f, _vp, _i64, _vp]),
+    "sgn_group_norm_ws_doubles": (_i64, [_i, _i, _i]),
+    "sgn_group_norm_f16": (_i, [_vp, _i, _i, _i, _i, _f, _vp, _vp, _i, _vp, _vp, _vp]),
+    "sgn_layer_norm_f16": (_i, [_vp, _i64, _i, _f, _vp, _vp, _vp, _vp]),
+    "sgn_cast_f16": (_i, [_vp, _i64, _vp, _vp]),
+    "sgn_upsample2x_f16": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "sgn_concat_f32": (_i, [_vp, _i, _vp, _vp, _f, _i, _i64, _vp, _vp]),
+    "sgn_axpy_f32": (_i, [_vp, _f, _i64, _vp, _vp]),
+    "sgn_im2col3x3_s2_f16": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "sgn_conv3x3_direct": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "sgn_linear_small": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "sgn_timestep_embedding": (_i, [_vp, _i, _i, _vp, _vp]),
+    "sgn_scale_repeat_f32": (_i, [_vp, _i64, _f, _i, _vp, _vp]),
+    "sgn_sheet_to_conditioning": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "sgn_cfg_euler_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _f, _vp, _vp, _vp]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -1,0 +1,571 @@
+// K7-K9: the bandwidth-bound operators around the tensor-core contractions of the SDXL / ControlNet UNet
+// (SURVEY §8a rows A12/A13): GroupNorm(+SiLU), LayerNorm, casts / nearest upsample / concat / stride-2 im2col feeding
+// the fp16 GEMM operands, the small-channel direct convolutions (conv_in, ControlNet hint stack), the [B x K] embedding
+// linears, the sinusoidal timestep embedding and the fused CFG + inpaint-blend + Euler-ancestral sampler update.
+// Layout: NHWC.  The residual stream is fp32, everything handed to a tensor-core kernel is fp16.
+#include <algorithm>
+
+#include "sgn_common.cuh"
+
+namespace sgn {
+
+static inline int grid_1d(size_t n, int block, int per_sm = 8) {
+  size_t want = (n + block - 1) / block;
+  return (int)std::max<size_t>(1, std::min<size_t>(want, (size_t)sm_count() * per_sm));
+}
+
+__device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); }
+
+// ------------------------------------------------------------------ GroupNorm
+// x [B, HW, C] fp32.  Deterministic three-step reduction (no atomics, so CUDA-graph replays are bit-identical):
+//   1. per 256-pixel chunk: (sum, sum of squares) per group          -> ws[b][chunk][g] (double2)
+//   2. per image: chunks summed in order -> mean, rstd               -> ws tail [b][g] (float2 stored in a double)
+//   3. normalise + affine (+ SiLU) -> fp16
+constexpr int kGnPix = 256;  // pixels per block
+__global__ void __launch_bounds__(256) k_gn_stats(const float* __restrict__ x, int HW, int C, int G, double2* part) {
+  extern __shared__ float2 s_part[];  // [4][C/2]
+  const int b = blockIdx.y, chunks = gridDim.x;
+  const int p0 = blockIdx.x * kGnPix, p1 = min(HW, p0 + kGnPix);
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  const int half_c = C >> 1, cpg2 = (C / G) >> 1;
+  const float2* xb = reinterpret_cast<const float2*>(x + ((size_t)b * HW) * C);
+  for (int cp = tx; cp < half_c; cp += 64) {
+    float s = 0.f, q = 0.f;
+    for (int pix = p0 + ty; pix < p1; pix += 4) {
+      float2 v = __ldg(xb + (size_t)pix * half_c + cp);
+      s += v.x + v.y;
+      q = fmaf(v.x, v.x, fmaf(v.y, v.y, q));
+    }
+    s_part[ty * half_c + cp] = make_float2(s, q);
+  }
+  __syncthreads();
+  if (threadIdx.x < G) {
+    double s = 0.0, q = 0.0;
+    for (int t = 0; t < 4; ++t)
+      for (int cp = threadIdx.x * cpg2; cp < (threadIdx.x + 1) * cpg2; ++cp) {
+        float2 v = s_part[t * half_c + cp];
+        s += (double)v.x, q += (double)v.y;
+      }
+    part[((size_t)b * chunks + blockIdx.x) * G + threadIdx.x] = make_double2(s, q);
+  }
+}
+
+__global__ void k_gn_finalize(const double2* __restrict__ part, int chunks, int G, double n, float eps, float2* stats) {
+  const int b = blockIdx.x, g = threadIdx.x;
+  if (g >= G) return;
+  double s = 0.0, q = 0.0;
+  for (int c = 0; c < chunks; ++c) {
+    double2 v = part[((size_t)b * chunks + c) * G + g];
+    s += v.x, q += v.y;
+  }
+  const double mean = s / n, var = q / n - mean * mean;
+  stats[b * G + g] = make_float2((float)mean, (float)(1.0 / sqrt(fmax(var, 0.0) + (double)eps)));
+}
+
+// Pass 2: y = (x - mean) * rstd * gamma + beta, optional SiLU, fp16 out.
+__global__ void __launch_bounds__(256) k_gn_apply(const float* __restrict__ x, int HW, int C, int G, float eps,
+                                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                  const float2* __restrict__ stats, int act_silu, __half* out) {
+  __shared__ float s_mean[64], s_rstd[64];
+  const int b = blockIdx.y;
+  if (threadIdx.x < G) {
+    float2 st = stats[b * G + threadIdx.x];
+    s_mean[threadIdx.x] = st.x, s_rstd[threadIdx.x] = st.y;
+  }
+  __syncthreads();
+  const int half_c = C >> 1, cpg = C / G;
+  const size_t n2 = (size_t)HW * half_c;
+  const float2* xb = reinterpret_cast<const float2*>(x + ((size_t)b * HW) * C);
+  __half2* ob = reinterpret_cast<__half2*>(out + ((size_t)b * HW) * C);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
+    const int cp = (int)(i % half_c), c = 2 * cp, g = c / cpg;
+    float2 v = __ldg(xb + i);
+    float a = (v.x - s_mean[g]) * s_rstd[g] * __ldg(gamma + c) + __ldg(beta + c);
+    float d = (v.y - s_mean[g]) * s_rstd[g] * __ldg(gamma + c + 1) + __ldg(beta + c + 1);
+    if (act_silu) a = silu(a), d = silu(d);
+    ob[i] = __floats2half2_rn(a, d);
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm: one warp per token
+__global__ void __launch_bounds__(256) k_layer_norm(const float* __restrict__ x, long long M, int C, float eps,
+                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                    __half* out) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int c4 = C >> 2;
+  for (long long m = warp0; m < M; m += nwarps) {
+    const float4* xr = reinterpret_cast<const float4*>(x + m * C);
+    float s = 0.f;
+    for (int i = lane; i < c4; i += 32) {
+      float4 v = xr[i];
+      s += (v.x + v.y) + (v.z + v.w);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / C;
+    float q = 0.f;
+    for (int i = lane; i < c4; i += 32) {
+      float4 v = xr[i];
+      float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / C + eps);
+    uint2* orow = reinterpret_cast<uint2*>(out + m * C);
+    for (int i = lane; i < c4; i += 32) {
+      float4 v = xr[i];
+      float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i), bb = __ldg(reinterpret_cast<const float4*>(beta) + i);
+      __half2 h0 = __floats2half2_rn((v.x - mean) * rstd * g.x + bb.x, (v.y - mean) * rstd * g.y + bb.y);
+      __half2 h1 = __floats2half2_rn((v.z - mean) * rstd * g.z + bb.z, (v.w - mean) * rstd * g.w + bb.w);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&h0);
+      u.y = *reinterpret_cast<uint32_t*>(&h1);
+      orow[i] = u;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ data movement feeding the GEMM operands
+__global__ void k_cast_f16(const float* __restrict__ x, size_t n4, __half* out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&h0);
+    u.y = *reinterpret_cast<uint32_t*>(&h1);
+    reinterpret_cast<uint2*>(out)[i] = u;
+  }
+}
+
+// F.interpolate(scale_factor=2, mode="nearest") + fp16 cast: x [B,H,W,C] fp32 -> out [B,2H,2W,C] fp16
+__global__ void k_upsample2x_f16(const float* __restrict__ x, int B, int H, int W, int c4, __half* out) {
+  const size_t n = (size_t)B * 2 * H * 2 * W * c4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % c4);
+    size_t r = i / c4;
+    int ox = (int)(r % (2 * W));
+    r /= 2 * W;
+    int oy = (int)(r % (2 * H));
+    int b = (int)(r / (2 * H));
+    float4 v = __ldg(reinterpret_cast<const float4*>(x) + (((size_t)b * H + (oy >> 1)) * W + (ox >> 1)) * c4 + c);
+    __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&h0);
+    u.y = *reinterpret_cast<uint32_t*>(&h1);
+    reinterpret_cast<uint2*>(out)[i] = u;
+  }
+}
+
+// torch.cat([a, b + scale * b2], dim=channels): a [P,Ca], b / b2 [P,Cb] -> out [P, Ca+Cb]   (fp32)
+__global__ void k_concat(const float* __restrict__ a, int ca4, const float* __restrict__ b, const float* __restrict__ b2,
+                         float scale, int cb4, size_t P, float* out) {
+  const int c4 = ca4 + cb4;
+  const size_t n = P * c4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % c4);
+    size_t pix = i / c4;
+    float4 v;
+    if (c < ca4) {
+      v = __ldg(reinterpret_cast<const float4*>(a) + pix * ca4 + c);
+    } else {
+      v = __ldg(reinterpret_cast<const float4*>(b) + pix * cb4 + (c - ca4));
+      if (b2) {
+        float4 w = __ldg(reinterpret_cast<const float4*>(b2) + pix * cb4 + (c - ca4));
+        v.x = fmaf(scale, w.x, v.x), v.y = fmaf(scale, w.y, v.y), v.z = fmaf(scale, w.z, v.z), v.w = fmaf(scale, w.w, v.w);
+      }
+    }
+    reinterpret_cast<float4*>(out)[i] = v;
+  }
+}
+
+__global__ void k_axpy(const float* __restrict__ x, float a, size_t n4, float* y) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    float4 w = reinterpret_cast<float4*>(y)[i];
+    w.x = fmaf(a, v.x, w.x), w.y = fmaf(a, v.y, w.y), w.z = fmaf(a, v.z, w.z), w.w = fmaf(a, v.w, w.w);
+    reinterpret_cast<float4*>(y)[i] = w;
+  }
+}
+
+// im2col of a 3x3 / stride 2 / pad 1 conv: x [B,H,W,C] fp32 -> out [B*Ho*Wo, 9*C] fp16, k = (ky*3+kx)*C + c
+__global__ void k_im2col_s2(const float* __restrict__ x, int B, int H, int W, int c4, int Ho, int Wo, __half* out) {
+  const size_t n = (size_t)B * Ho * Wo * 9 * c4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % c4);
+    size_t r = i / c4;
+    int tap = (int)(r % 9);
+    r /= 9;
+    int ox = (int)(r % Wo);
+    r /= Wo;
+    int oy = (int)(r % Ho);
+    int b = (int)(r / Ho);
+    int iy = 2 * oy + tap / 3 - 1, ix = 2 * ox + tap % 3 - 1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+      v = __ldg(reinterpret_cast<const float4*>(x) + (((size_t)b * H + iy) * W + ix) * c4 + c);
+    __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&h0);
+    u.y = *reinterpret_cast<uint32_t*>(&h1);
+    reinterpret_cast<uint2*>(out)[i] = u;
+  }
+}
+
+// ------------------------------------------------------------------ direct 3x3 conv for small channel counts (fp32)
+// 16x16 output pixels per block, kCoT output channels per block (grid.z), input channels staged through shared
+// memory in chunks of kCiT.  w [Cout, 3, 3, Cin] fp32.
+constexpr int kDcTile = 16, kCoT = 16, kCiT = 8;
+struct DirectConvParams {
+  const float* x;
+  const float* w;
+  const float* bias;
+  const float* residual;  // NHWC [B,Ho,Wo,Cout] or null
+  void* out;
+  int B, H, W, Cin, Cout, stride, Ho, Wo;
+  int in_nchw, act_silu, out_f16;
+  int res_batch;  // residual holds res_batch images: output image b adds residual image b % res_batch
+};
+
+__global__ void __launch_bounds__(256) k_conv3x3_direct(const DirectConvParams p) {
+  extern __shared__ float smem_f[];
+  const int in_t = (kDcTile - 1) * p.stride + 3;  // input tile edge: 18 (stride 1) or 33 (stride 2)
+  float* s_in = smem_f;                             // [in_t][in_t][kCiT]
+  float* s_w = smem_f + in_t * in_t * kCiT;         // [9][kCiT][kCoT]
+  const int tiles_x = (p.Wo + kDcTile - 1) / kDcTile;
+  const int tx0 = (blockIdx.x % tiles_x) * kDcTile, ty0 = (blockIdx.x / tiles_x) * kDcTile;
+  const int b = blockIdx.y, co0 = blockIdx.z * kCoT;
+  const int lx = threadIdx.x % kDcTile, ly = threadIdx.x / kDcTile;
+  const int ox = tx0 + lx, oy = ty0 + ly;
+  float acc[kCoT];
+#pragma unroll
+  for (int i = 0; i < kCoT; ++i) acc[i] = 0.f;
+  const int ix0 = tx0 * p.stride - 1, iy0 = ty0 * p.stride - 1;
+  for (int ci0 = 0; ci0 < p.Cin; ci0 += kCiT) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < in_t * in_t * kCiT; i += 256) {
+      int ci, px, py;
+      if (p.in_nchw) {  // x fastest for coalescing
+        px = i % in_t;
+        py = (i / in_t) % in_t;
+        ci = i / (in_t * in_t);
+      } else {
+        ci = i % kCiT;
+        px = (i / kCiT) % in_t;
+        py = i / (kCiT * in_t);
+      }
+      int iy = iy0 + py, ix = ix0 + px, c = ci0 + ci;
+      float v = 0.f;
+      if (c < p.Cin && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
+        v = p.in_nchw ? __ldg(p.x + (((size_t)b * p.Cin + c) * p.H + iy) * p.W + ix)
+                      : __ldg(p.x + (((size_t)b * p.H + iy) * p.W + ix) * p.Cin + c);
+      s_in[(py * in_t + px) * kCiT + ci] = v;
+    }
+    for (int i = threadIdx.x; i < 9 * kCiT * kCoT; i += 256) {
+      int co = i % kCoT, ci = (i / kCoT) % kCiT, tap = i / (kCoT * kCiT);
+      float v = 0.f;
+      if (co0 + co < p.Cout && ci0 + ci < p.Cin) v = __ldg(p.w + ((size_t)(co0 + co) * 9 + tap) * p.Cin + ci0 + ci);
+      s_w[i] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const float* ip = s_in + ((ly * p.stride + tap / 3) * in_t + lx * p.stride + tap % 3) * kCiT;
+      const float* wp = s_w + tap * kCiT * kCoT;
+#pragma unroll
+      for (int ci = 0; ci < kCiT; ++ci) {
+        const float xv = ip[ci];
+#pragma unroll
+        for (int q = 0; q < kCoT / 4; ++q) {
+          float4 w4 = *reinterpret_cast<const float4*>(wp + ci * kCoT + 4 * q);
+          acc[4 * q] = fmaf(xv, w4.x, acc[4 * q]);
+          acc[4 * q + 1] = fmaf(xv, w4.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(xv, w4.z, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(xv, w4.w, acc[4 * q + 3]);
+        }
+      }
+    }
+  }
+  if (ox >= p.Wo || oy >= p.Ho) return;
+  const size_t o = (((size_t)b * p.Ho + oy) * p.Wo + ox) * p.Cout + co0;
+#pragma unroll
+  for (int i = 0; i < kCoT; ++i) {
+    if (co0 + i >= p.Cout) break;
+    float v = acc[i] + (p.bias ? __ldg(p.bias + co0 + i) : 0.f);
+    if (p.residual) v += p.residual[(((size_t)(b % p.res_batch) * p.Ho + oy) * p.Wo + ox) * p.Cout + co0 + i];
+    if (p.act_silu) v = silu(v);
+    if (p.out_f16) reinterpret_cast<__half*>(p.out)[o + i] = __float2half_rn(v);
+    else reinterpret_cast<float*>(p.out)[o + i] = v;
+  }
+}
+
+// ------------------------------------------------------------------ embedding path (M = batch rows)
+// out[b][n] = sum_k act(x[b][k]) * W[n][k] + bias[n] (+ residual[b][n]); one warp per output feature, B <= 8.
+__global__ void __launch_bounds__(256) k_linear_small(const float* __restrict__ x, const float* __restrict__ w,
+                                                      const float* __restrict__ bias, const float* __restrict__ residual,
+                                                      int B, int N, int K, int silu_in, int silu_out, float* out) {
+  const int lane = threadIdx.x & 31;
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (n >= N) return;
+  float acc[8];
+#pragma unroll
+  for (int b = 0; b < 8; ++b) acc[b] = 0.f;
+  const float* wr = w + (size_t)n * K;
+  for (int k = lane; k < K; k += 32) {
+    const float wv = __ldg(wr + k);
+#pragma unroll
+    for (int b = 0; b < 8; ++b)
+      if (b < B) {
+        float xv = __ldg(x + (size_t)b * K + k);
+        if (silu_in) xv = silu(xv);
+        acc[b] = fmaf(xv, wv, acc[b]);
+      }
+  }
+#pragma unroll
+  for (int b = 0; b < 8; ++b)
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], o);
+  if (lane == 0)
+    for (int b = 0; b < B; ++b) {
+      float v = acc[b] + (bias ? __ldg(bias + n) : 0.f);
+      if (residual) v += residual[(size_t)b * N + n];
+      if (silu_out) v = silu(v);
+      out[(size_t)b * N + n] = v;
+    }
+}
+
+// sgm timestep_embedding(t, dim): [cos(t f_i) | sin(t f_i)], f_i = exp(-ln(10000) i / half), fp32 like torch
+__global__ void k_timestep_embedding(const float* __restrict__ t, int B, int dim, float* out) {
+  const int half_d = dim / 2;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * half_d) return;
+  int b = i / half_d, j = i % half_d;
+  float f = expf(-9.210340371976184f * (float)j / (float)half_d);
+  float a = __ldg(t + b) * f;
+  out[(size_t)b * dim + j] = cosf(a);
+  out[(size_t)b * dim + half_d + j] = sinf(a);
+}
+
+// ------------------------------------------------------------------ K9: CFG + inpaint blend + Euler-ancestral update
+// eps [2, n] = UNet output for (cond, uncond) on input x * c_in.  k-diffusion CompVisDenoiser: denoised = x - sigma*eps.
+//   e      = eps_u + cfg * (eps_c - eps_u)
+//   den    = x - sigma * e ;  den = init * mask + nmask * den            (A1111 CFGDenoiser inpaint blend)
+//   d      = (x - den) / sigma ;  x' = x + d * (sigma_down - sigma) + noise * sigma_up
+__global__ void k_cfg_euler_step(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ init,
+                                 const float* __restrict__ mask, const float* __restrict__ noise, size_t n, size_t hw,
+                                 int channels, float cfg, float sigma, float sigma_down, float sigma_up, float* x_out,
+                                 float* denoised_out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float xv = x[i];
+    const float ec = __ldg(eps + i), eu = __ldg(eps + n + i);
+    const float e = eu + cfg * (ec - eu);
+    float den = xv - sigma * e;
+    if (mask) {
+      // latent mask [1,1,h,w] broadcast over channels: mask = 1 keeps the original latent (A1111: mask = 1 - latmask)
+      const size_t pix = i % hw + (i / (hw * channels)) * hw;
+      const float mk = __ldg(mask + pix);
+      den = __ldg(init + i) * mk + (1.f - mk) * den;
+    }
+    if (denoised_out) denoised_out[i] = den;
+    const float d = (xv - den) / sigma;
+    float xn = xv + d * (sigma_down - sigma);
+    if (noise) xn = fmaf(__ldg(noise + i), sigma_up, xn);
+    x_out[i] = xn;
+  }
+}
+
+// out[r] = scale * x for r in [0, repeats): the CFG pair (cond, uncond) shares one scaled latent x * c_in
+__global__ void k_scale_repeat(const float* __restrict__ x, size_t n, float scale, int repeats, float* out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = __ldg(x + i) * scale;
+    for (int r = 0; r < repeats; ++r) out[(size_t)r * n + i] = v;
+  }
+}
+
+// Sheet -> denoiser conditioning.  hint [3,Hs,Ws] = uint8-truncated condition / 255 on three channels (the reference
+// sends the condition sheet through tensor_to_image -> PNG; ControlNet preprocessor "none" divides by 255);
+// lat_mask [Hs/8, Ws/8] = 1 - round(mean of the 8x8 mask block): 1 where the ORIGINAL latent is kept.
+__global__ void k_hint_latmask(const float* __restrict__ cond, const float* __restrict__ mask, int Hs, int Ws, float* hint,
+                               float* lat_mask) {
+  const size_t n = (size_t)Hs * Ws;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float q = (float)(unsigned char)(int)(__ldg(cond + i) * 255.f) * (1.f / 255.f);
+    hint[i] = q, hint[n + i] = q, hint[2 * n + i] = q;
+    const int h8 = Hs >> 3, w8 = Ws >> 3;
+    if (i < (size_t)h8 * w8) {
+      const int ly = (int)(i / w8), lx = (int)(i % w8);
+      float s = 0.f;
+      for (int dy = 0; dy < 8; ++dy)
+        for (int dx = 0; dx < 8; ++dx) s += __ldg(mask + (size_t)(ly * 8 + dy) * Ws + lx * 8 + dx);
+      lat_mask[i] = 1.f - rintf(s * (1.f / 64.f));
+    }
+  }
+}
+
+}  // namespace sgn
+
+using namespace sgn;
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int64_t sgn_group_norm_ws_doubles(int B, int HW, int groups) {
+  const int64_t chunks = (HW + kGnPix - 1) / kGnPix;
+  return (int64_t)B * groups * (2 * chunks + 1);
+}
+
+extern "C" int sgn_group_norm_f16(const float* d_x, int B, int HW, int C, int groups, float eps, const float* d_gamma,
+                                  const float* d_beta, int act_silu, double* d_ws, void* d_out, void* stream) {
+  SGN_CHECK_ARG(B >= 0 && HW > 0 && C > 0 && groups > 0, "bad shape");
+  if (B == 0) return SGN_OK;
+  SGN_CHECK_ARG(d_x && d_gamma && d_beta && d_ws && d_out, "null pointer");
+  SGN_CHECK_ARG(groups <= 64 && C % groups == 0 && (C / groups) % 2 == 0, "need groups <= 64 and an even number of channels per group");
+  SGN_CHECK_ARG(C <= 2560, "GroupNorm kernel stages 4 x C/2 partials in 40 KB of shared memory (C <= 2560)");
+  const int chunks = (HW + kGnPix - 1) / kGnPix;
+  double2* part = reinterpret_cast<double2*>(d_ws);
+  float2* stats = reinterpret_cast<float2*>(part + (size_t)B * chunks * groups);
+  dim3 g1(chunks, B);
+  k_gn_stats<<<g1, 256, (size_t)4 * (C / 2) * sizeof(float2), ST(stream)>>>(d_x, HW, C, groups, part);
+  SGN_LAUNCH_CHECK();
+  k_gn_finalize<<<B, 64, 0, ST(stream)>>>(part, chunks, groups, (double)HW * (C / groups), eps, stats);
+  SGN_LAUNCH_CHECK();
+  size_t n2 = (size_t)HW * (C / 2);
+  dim3 g2((unsigned)std::max<size_t>(1, std::min<size_t>((n2 + 255) / 256, (size_t)sm_count() * 8 / std::max(1, B) + 1)), B);
+  k_gn_apply<<<g2, 256, 0, ST(stream)>>>(d_x, HW, C, groups, eps, d_gamma, d_beta, stats, act_silu,
+                                         reinterpret_cast<__half*>(d_out));
+  SGN_LAUNCH_CHECK();
+  return SGN_OK;
+}
+
+extern "C" int sgn_layer_norm_f16(const float* d_x, int64_t M, int C, float eps, const float* d_gamma,
+                                  const float* d_beta, void* d_out, void* stream) {
+  SGN_CHECK_ARG(M >= 0 && C > 0 && C % 4 == 0, "C must be a multiple of 4");
+  if (M == 0) return SGN_OK;
+  SGN_CHECK_ARG(d_x && d_gamma && d_beta && d_out, "null pointer");
+  k_layer_norm<<<grid_1d((size_t)M * 32, 256), 256, 0, ST(stream)>>>(d_x, M, C, eps, d_gamma, d_beta,
+                                                                      reinterpret_cast<__half*>(d_out));
+  SGN_LAUNCH_CHECK();
+  return SGN_OK;
+}
+
+extern "C" int sgn_cast_f16(const float* d_x, int64_t n, void* d_out, void* stream) {
+  SGN_CHECK_ARG(n >= 0 && n % 4 == 0, "n must be a multiple of 4");
+  if (n == 0) return SGN_OK;
+  SGN_CHECK_ARG(d_x && d_out, "null pointer");
+  k_cast_f16<<<grid_1d((size_t)n / 4, 256), 256, 0, ST(stream)>>>(d_x, (size_t)n / 4, reinterpret_cast<__half*>(d_out));
+  SGN_LAUNCH_CHECK();
+  return SGN_OK;
+}
+
+extern "C" int sgn_upsample2x_f16(const float* d_x, int B, int H, int W, int C, void* d_out, void* stream) {
+  SGN_CHECK_ARG(B >= 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "bad shape (C % 4)");
+  if (B == 0) return SGN_OK;
+  SGN_CHECK_ARG(d_x && d_out, "null pointer");
+  size_t n = (size_t)B * 4 * H * W * (C / 4);
+  k_upsample2x_f16<<<grid_1d(n, 256), 256, 0, ST(stream)>>>(d_x, B, H, W, C / 4, reinterpret_cast<__half*>(d_out));
+  SGN_LAUNCH_CHECK();
+  return SGN_OK;
+}
+
+extern "C" int sgn_concat_f32(const float* d_a, int Ca, const float* d_b, const float* d_b2, float scale, int Cb,
+                              int64_t P, float* d_out, void* stream) {
+  SGN_CHECK_ARG(P >= 0 && Ca >= 0 && Cb > 0 && Ca % 4 == 0 && Cb % 4 == 0, "channel counts must be multiples of 4");
+  if (P == 0) return SGN_OK;
+  SGN_CHECK_ARG((Ca == 0 || d_a) && d_b && d_out, "null pointer");
+  size_t n = (size_t)P * ((Ca + Cb) / 4);
+  k_concat<<<grid_1d(n, 256), 256, 0, ST(stream)>>>(d_a, Ca / 4, d_b, d_b2, scale, Cb / 4, (size_t)P, d_out);
+  SGN_LAUNCH_CHECK();
+  return SGN_OK;
+}
+
+extern "C" int sgn_axpy_f32(const float* d_x, float a, int64_t n, float* d_y, void* stream) {
+  SGN_CHECK_ARG(n >= 0 && n % 4 == 0, "n must be a multiple of 4");
+  if (n == 0) return SGN_OK;
+  SGN_CHECK_ARG(d_x && d_y, "null pointer");
+  k_axpy<<<grid_1d((size_t)n / 4, 256), 256, 0, ST(stream)>>>(d_x, a, (size_t)n / 4, d_y);
+  SGN_LAUNCH_CHECK();
+  return SGN_OK;
+}
+
+extern "C" int sgn_im2col3x3_s2_f16(const float* d_x, int B, int H, int W, int C, void* d_out, void* stream) {
+  SGN_CHECK_ARG(B >= 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "bad shape (C % 4)");
+  if (B == 0) return SGN_OK;
+  SGN_CHECK_ARG(d_x && d_out, "null pointer");
+  int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  size_t n = (size_t)B * Ho * Wo * 9 * (C / 4);
+  k_im2col_s2<<<grid_1d(n, 256), 256, 0, ST(stream)>>>(d_x, B, H, W, C / 4, Ho, Wo, reinterpret_cast<__half*>(d_out));
+  SGN_LAUNCH_CHECK();
+  return SGN_OK;
+}
+
+extern "C" int sgn_conv3x3_direct(const float* d_x, int in_nchw, const float* d_w, const float* d_bias,
+                                  const float* d_residual, int res_batch, int B, int H, int W, int Cin, int Cout,
+                                  int stride, int act_silu, int out_f16, void* d_out, void* stream) {
+  SGN_CHECK_ARG(B >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && (stride == 1 || stride == 2), "bad conv shape");
+  if (B == 0) return SGN_OK;
+  SGN_CHECK_ARG(d_x && d_w && d_out, "null pointer");
+  DirectConvParams p;
+  p.x = d_x, p.w = d_w, p.bias = d_bias, p.residual = d_residual, p.out = d_out;
+  p.B = B, p.H = H, p.W = W, p.Cin = Cin, p.Cout = Cout, p.stride = stride;
+  p.Ho = (H - 1) / stride + 1, p.Wo = (W - 1) / stride + 1;
+  p.in_nchw = in_nchw, p.act_silu = act_silu, p.out_f16 = out_f16;
+  p.res_batch = res_batch > 0 ? res_batch : B;
+  const int in_t = (kDcTile - 1) * stride + 3;
+  size_t smem = ((size_t)in_t * in_t * kCiT + 9 * kCiT * kCoT) * sizeof(float);
+  dim3 grid(((p.Wo + kDcTile - 1) / kDcTile) * ((p.Ho + kDcTile - 1) / kDcTile), B, (Cout + kCoT - 1) / kCoT);
+  k_conv3x3_direct<<<grid, 256, smem, ST(stream)>>>(p);
+  SGN_LAUNCH_CHECK();
+  return SGN_OK;
+}
+
+extern "C" int sgn_linear_small(const float* d_x, const float* d_w, const float* d_bias, const float* d_residual, int B,
+                                int N, int K, int silu_in, int silu_out, float* d_out, void* stream) {
+  SGN_CHECK_ARG(B >= 1 && B <= 8 && N > 0 && K > 0, "sgn_linear_small handles 1..8 rows");
+  SGN_CHECK_ARG(d_x && d_w && d_out, "null pointer");
+  k_linear_small<<<(N * 32 + 255) / 256, 256, 0, ST(stream)>>>(d_x, d_w, d_bias, d_residual, B, N, K, silu_in, silu_out,
+                                                               d_out);
+  SGN_LAUNCH_CHECK();
+  return SGN_OK;
+}
+
+extern "C" int sgn_timestep_embedding(const float* d_t, int B, int dim, float* d_out, void* stream) {
+  SGN_CHECK_ARG(B > 0 && dim > 0 && dim % 2 == 0, "dim must be even");
+  SGN_CHECK_ARG(d_t && d_out, "null pointer");
+  int n = B * (dim / 2);
+  k_timestep_embedding<<<(n + 127) / 128, 128, 0, ST(stream)>>>(d_t, B, dim, d_out);
+  SGN_LAUNCH_CHECK();
+  return SGN_OK;
+}
+
+extern "C" int sgn_cfg_euler_step(const float* d_x, const float* d_eps, const float* d_init, const float* d_mask,
+                                  const float* d_noise, int B, int C, int H, int W, float cfg_scale, float sigma,
+                                  float sigma_down, float sigma_up, float* d_x_out, float* d_denoised, void* stream) {
+  SGN_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0, "bad latent shape");
+  SGN_CHECK_ARG(d_x && d_eps && d_x_out, "null pointer");
+  SGN_CHECK_ARG((d_mask == nullptr) == (d_init == nullptr), "mask and init latent go together");
+  SGN_CHECK_ARG(sigma > 0.f, "sigma must be positive");
+  size_t n = (size_t)B * C * H * W;
+  k_cfg_euler_step<<<grid_1d(n, 256), 256, 0, ST(stream)>>>(d_x, d_eps, d_init, d_mask, d_noise, n, (size_t)H * W, C,
+                                                            cfg_scale, sigma, sigma_down, sigma_up, d_x_out, d_denoised);
+  SGN_LAUNCH_CHECK();
+  return SGN_OK;
+}
+
+extern "C" int sgn_scale_repeat_f32(const float* d_x, int64_t n, float scale, int repeats, float* d_out, void* stream) {
+  SGN_CHECK_ARG(n >= 0 && repeats >= 1, "bad shape");
+  if (n == 0) return SGN_OK;
+  SGN_CHECK_ARG(d_x && d_out, "null pointer");
+  k_scale_repeat<<<grid_1d((size_t)n, 256), 256, 0, ST(stream)>>>(d_x, (size_t)n, scale, repeats, d_out);
+  SGN_LAUNCH_CHECK();
+  return SGN_OK;
+}
+
+extern "C" int sgn_sheet_to_conditioning(const float* d_cond, const float* d_mask, int Hs, int Ws, float* d_hint,
+                                         float* d_lat_mask, void* stream) {
+  SGN_CHECK_ARG(Hs > 0 && Ws > 0 && Hs % 8 == 0 && Ws % 8 == 0, "sheet size must be a multiple of 8");
+  SGN_CHECK_ARG(d_cond && d_mask && d_hint && d_lat_mask, "null pointer");
+  k_hint_latmask<<<grid_1d((size_t)Hs * Ws, 256), 256, 0, ST(stream)>>>(d_cond, d_mask, Hs, Ws, d_hint, d_lat_mask);
+  SGN_LAUNCH_CHECK();
+  return SGN_OK;
+}

@@ -97,3 +97,142 @@ def attention_f16(q: Tensor, k: Tensor, v: Tensor, batch: int, heads: int, out: 
                                                  batch, heads, Tq, Tkv, 0.125, _ptr(out), out.stride(0),
                                                  _stream(q.device)))
     return out
+
+
+def _call(dev, fn, *args) -> None:
+    with torch.cuda.device(dev):
+        _lib.check(fn(*args, _stream(dev)))
+
+
+def group_norm_f16(x: Tensor, B: int, HW: int, groups: int, eps: float, gamma: Tensor, beta: Tensor, act_silu: bool,
+                   ws: Optional[Tensor] = None) -> Tensor:
+    """GroupNorm(groups) (+SiLU) of fp32 [B*HW, C] -> fp16 [B*HW, C]; ws: float64 scratch (allocated when None)."""
+    _chk(x, torch.float32, "x")
+    need = int(_lib.load().sgn_group_norm_ws_doubles(B, HW, groups))
+    if ws is None:
+        ws = torch.empty(need, dtype=torch.float64, device=x.device)
+    _chk(ws, torch.float64, "ws")
+    if ws.numel() < need:
+        raise ValueError(f"GroupNorm scratch needs {need} doubles, got {ws.numel()}")
+    out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    _call(x.device, _lib.load().sgn_group_norm_f16, _ptr(x), B, HW, x.shape[1], groups, eps, _ptr(gamma), _ptr(beta),
+          int(act_silu), _ptr(ws), _ptr(out))
+    return out
+
+
+def layer_norm_f16(x: Tensor, gamma: Tensor, beta: Tensor, eps: float = 1e-5) -> Tensor:
+    _chk(x, torch.float32, "x")
+    out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    _call(x.device, _lib.load().sgn_layer_norm_f16, _ptr(x), x.shape[0], x.shape[1], eps, _ptr(gamma), _ptr(beta), _ptr(out))
+    return out
+
+
+def cast_f16(x: Tensor) -> Tensor:
+    _chk(x, torch.float32, "x")
+    out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    _call(x.device, _lib.load().sgn_cast_f16, _ptr(x), x.numel(), _ptr(out))
+    return out
+
+
+def upsample2x_f16(x: Tensor, B: int, H: int, W: int) -> Tensor:
+    """fp32 [B*H*W, C] -> fp16 NHWC [B, 2H, 2W, C] (nearest)."""
+    _chk(x, torch.float32, "x")
+    Cc = x.shape[-1]
+    out = torch.empty((B, 2 * H, 2 * W, Cc), dtype=torch.float16, device=x.device)
+    _call(x.device, _lib.load().sgn_upsample2x_f16, _ptr(x), B, H, W, Cc, _ptr(out))
+    return out
+
+
+def concat_f32(a: Tensor, b: Tensor, b2: Optional[Tensor] = None, scale: float = 1.0) -> Tensor:
+    """cat([a, b + scale*b2], dim=1) of fp32 [P, C] matrices."""
+    _chk(a, torch.float32, "a")
+    _chk(b, torch.float32, "b")
+    _chk(b2, torch.float32, "b2")
+    P = a.shape[0]
+    out = torch.empty((P, a.shape[1] + b.shape[1]), dtype=torch.float32, device=a.device)
+    _call(a.device, _lib.load().sgn_concat_f32, _ptr(a), a.shape[1], _ptr(b), _ptr(b2), float(scale), b.shape[1], P, _ptr(out))
+    return out
+
+
+def axpy_f32(x: Tensor, a: float, y: Tensor) -> None:
+    _chk(x, torch.float32, "x")
+    _chk(y, torch.float32, "y")
+    _call(y.device, _lib.load().sgn_axpy_f32, _ptr(x), float(a), y.numel(), _ptr(y))
+
+
+def im2col3x3_s2_f16(x: Tensor, B: int, H: int, W: int):
+    """fp32 [B*H*W, C] -> (fp16 [B*Ho*Wo, 9C], Ho, Wo) for a 3x3 / stride 2 / pad 1 conv."""
+    _chk(x, torch.float32, "x")
+    Cc = x.shape[-1]
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = torch.empty((B * Ho * Wo, 9 * Cc), dtype=torch.float16, device=x.device)
+    _call(x.device, _lib.load().sgn_im2col3x3_s2_f16, _ptr(x), B, H, W, Cc, _ptr(out))
+    return out, Ho, Wo
+
+
+def conv3x3_direct(x: Tensor, in_nchw: bool, w: Tensor, bias: Optional[Tensor], residual: Optional[Tensor] = None,
+                   stride: int = 1, act_silu: bool = False, out_f16: bool = False) -> Tensor:
+    """fp32 direct conv; x NCHW [B,C,H,W] or NHWC [B,H,W,C]; w fp32 [Cout,3,3,Cin] -> NHWC [B,Ho,Wo,Cout]."""
+    _chk(x, torch.float32, "x")
+    _chk(w, torch.float32, "w")
+    _chk(residual, torch.float32, "residual")
+    if in_nchw:
+        B, Cin, H, W = x.shape
+    else:
+        B, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    out = torch.empty((B, Ho, Wo, Cout), dtype=torch.float16 if out_f16 else torch.float32, device=x.device)
+    res_batch = residual.shape[0] if residual is not None else 0
+    _call(x.device, _lib.load().sgn_conv3x3_direct, _ptr(x), int(in_nchw), _ptr(w), _ptr(bias), _ptr(residual), res_batch,
+          B, H, W, Cin, Cout, stride, int(act_silu), int(out_f16), _ptr(out))
+    return out
+
+
+def linear_small(x: Tensor, w: Tensor, bias: Optional[Tensor], residual: Optional[Tensor] = None, silu_in: bool = False,
+                 silu_out: bool = False) -> Tensor:
+    _chk(x, torch.float32, "x")
+    _chk(w, torch.float32, "w")
+    B, Kd = x.shape
+    N = w.shape[0]
+    out = torch.empty((B, N), dtype=torch.float32, device=x.device)
+    _call(x.device, _lib.load().sgn_linear_small, _ptr(x), _ptr(w), _ptr(bias), _ptr(residual), B, N, Kd, int(silu_in),
+          int(silu_out), _ptr(out))
+    return out
+
+
+def timestep_embedding(t: Tensor, dim: int) -> Tensor:
+    _chk(t, torch.float32, "t")
+    out = torch.empty((t.shape[0], dim), dtype=torch.float32, device=t.device)
+    _call(t.device, _lib.load().sgn_timestep_embedding, _ptr(t), t.shape[0], dim, _ptr(out))
+    return out
+
+
+def scale_cat2(x: Tensor, scale: float) -> Tensor:
+    """cat([x, x]) * scale along the batch dimension."""
+    _chk(x, torch.float32, "x")
+    out = torch.empty((2 * x.shape[0],) + tuple(x.shape[1:]), dtype=torch.float32, device=x.device)
+    _call(x.device, _lib.load().sgn_scale_repeat_f32, _ptr(x), x.numel(), float(scale), 2, _ptr(out))
+    return out
+
+
+def make_hint_and_latent_mask(cond_sheet: Tensor, mask_sheet: Tensor, hint: Tensor, lat_mask: Tensor) -> None:
+    _chk(cond_sheet, torch.float32, "cond_sheet")
+    _chk(mask_sheet, torch.float32, "mask_sheet")
+    Hs, Ws = cond_sheet.shape[0], cond_sheet.shape[1]
+    if hint.numel() != 3 * Hs * Ws or lat_mask.numel() != (Hs // 8) * (Ws // 8):
+        raise ValueError("hint / lat_mask do not match the sheet size")
+    _call(hint.device, _lib.load().sgn_sheet_to_conditioning, _ptr(cond_sheet), _ptr(mask_sheet), Hs, Ws, _ptr(hint),
+          _ptr(lat_mask))
+
+
+def cfg_euler_step(x: Tensor, eps: Tensor, init: Optional[Tensor], mask: Optional[Tensor], noise: Optional[Tensor],
+                   cfg_scale: float, sigma: float, sigma_down: float, sigma_up: float):
+    """Fused CFG + inpaint blend + Euler-ancestral update on latents [B,C,H,W]; eps [2B,C,H,W] = (cond, uncond)."""
+    for t, n in ((x, "x"), (eps, "eps"), (init, "init"), (mask, "mask"), (noise, "noise")):
+        _chk(t, torch.float32, n)
+    B, Cc, H, W = x.shape
+    x_out, den = torch.empty_like(x), torch.empty_like(x)
+    _call(x.device, _lib.load().sgn_cfg_euler_step, _ptr(x), _ptr(eps), _ptr(init), _ptr(mask), _ptr(noise), B, Cc, H, W,
+          float(cfg_scale), float(sigma), float(sigma_down), float(sigma_up), _ptr(x_out), _ptr(den))
+    return x_out, den
