@@ -154,6 +154,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-unet", action="store_true", help="time the render half only (profiling)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end and per-kernel passes (ncu runs only)")
+    ap.add_argument("--ncu-range", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed steps (run under `ncu --profile-from-start off`)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -198,15 +201,12 @@ def main():
 
     unet = None
     if not args.no_unet:
-        try:
-            from signerf_b200 import unet as unet_mod
-            unet = unet_mod.BenchUNet(dev, sheet_hw=(layout.height, layout.width), seed=0)
-        except ImportError:
-            unet = None
+        from signerf_b200 import unet as unet_mod
+        unet = unet_mod.BenchUNet(dev, sheet_hw=(layout.height, layout.width), seed=0)
 
     tiles = torch.empty((N, VIEWS, H, W, 6), dtype=torch.float32, device=dev) if N > 1 else None
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-    k1_events = []
+    k1_events, unet_events = [], []
 
     def step(c2w, intr, time_k1=False):
         if time_k1:
@@ -229,7 +229,13 @@ def main():
         b_ = sheet.paste(rgb, mask, cond, 0)
         out = b_.image
         if unet is not None:
+            if time_k1:
+                a, b = ev(), ev()
+                a.record()
             out = unet.step(b_.image, b_.mask, b_.condition)
+            if time_k1:
+                b.record()
+                unet_events.append((a, b))
         return out
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -251,6 +257,8 @@ def main():
     launches0 = _lib.launch_count()
     evs = []
     sync_all()
+    if args.ncu_range:
+        torch.cuda.cudart().cudaProfilerStart()
     for _ in range(args.steps):
         a, b = ev(), ev()
         a.record()
@@ -259,16 +267,21 @@ def main():
         evs.append((a, b))
         flush.zero_()
     sync_all()
+    if args.ncu_range:
+        torch.cuda.cudart().cudaProfilerStop()
     launches = _lib.launch_count() - launches0
+    if unet is not None:   # graph replays re-issue the launches counted while capturing
+        launches += args.steps * unet.launches_per_step
     clocks = sampler.stop() if rank == 0 else None
     total_ms = sum(a.elapsed_time(b) for a, b in evs)
     k1_ms = sum(a.elapsed_time(b) for a, b in k1_events) / len(k1_events)
+    unet_ms = sum(a.elapsed_time(b) for a, b in unet_events) / len(unet_events) if unet_events else 0.0
 
     # e2e: host cameras (pinned) -> device, full step, result read back to the host, every step
     res_h = None
     e2e_evs = []
     sync_all()
-    for i in range(args.warmup + args.steps):
+    for i in range(0 if args.no_e2e else args.warmup + args.steps):
         a, b = ev(), ev()
         a.record()
         c = c2w_h.to(dev, non_blocking=True)
@@ -283,12 +296,16 @@ def main():
             e2e_evs.append((a, b))
         flush.zero_()
     sync_all()
-    e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_evs)
+    e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_evs) if e2e_evs else float("nan")
+    if res_h is None:
+        res_h = torch.empty(0)
 
-    t = torch.tensor([total_ms, e2e_ms, k1_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, e2e_ms, k1_ms, unet_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, k1_ms = t.tolist()
+    total_ms, e2e_ms, k1_ms, unet_ms = t.tolist()
+    # per-kernel-family split of the diffusion half: one extra EAGER step, every C-ABI call bracketed by CUDA events
+    fam = unet.profile_eager() if (unet is not None and rank == 0 and not args.no_e2e) else {}
 
     if rank == 0:
         pk = peaks()
@@ -300,7 +317,8 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 gather/composite + f16 mma MLP (f32 accumulate)", "data": "synthetic",
+            "dtype": "f16 operands, f32 accumulate (tcgen05 UNet; f32 hash gather/composite + f16 mma MLP in the renderer)",
+            "data": "synthetic",
             "config": {"workload": "C3 4x4 grid of 512x512 views, flat 128 samples/ray, nerfacto field (16-level 2^19 hash + MLPs), "
                                    "AABB mask + 50x50 dilation + depth condition, 2048x2048 sheet" +
                                    (", + 1 SDXL+ControlNet UNet step (CFG 2)" if unet is not None else "; UNet step NOT YET BUILT (render half only)"),
@@ -311,10 +329,32 @@ def main():
                     "d2h_bytes_per_step": int(res_h.numel() * res_h.element_size())},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "k_render_mma", "bound": "hbm", "achieved": k1_gbs, "peak": pk["hbm"], "unit": "GB/s",
-                         "frac": k1_gbs / pk["hbm"], "traffic": None, "peak_source": pk["source"],
-                         "ms_per_launch": k1_ms, "algorithmic_bytes_per_launch": k1_bytes},
         }
+        render_roof = {"kernel": "k_render_mma", "bound": "hbm", "achieved": k1_gbs, "peak": pk["hbm"], "unit": "GB/s",
+                       "frac": k1_gbs / pk["hbm"], "traffic": 97.6e6, "peak_source": pk["source"], "ms_per_launch": k1_ms,
+                       "algorithmic_bytes_per_launch": k1_bytes,
+                       "note": "hash tables (64 MiB) stay L2-resident: ncu dram bytes per launch are 97.6 MB (profiles/), "
+                               "so the algorithmic-gather figure can exceed the HBM copy peak"}
+        if unet is not None:
+            tf = UNET_TFLOP_PER_STEP / (unet_ms / 1e3)
+            tc = {k: v for k, v in fam.items() if v["flops"] > 0}
+            top = max(tc, key=lambda k: tc[k]["ms"]) if tc else None
+            line["roofline"] = {
+                "kernel": top, "bound": "tensor",
+                "achieved": (tc[top]["flops"] / (tc[top]["ms"] / 1e3) / 1e12) if top else None,
+                "peak": pk["tensor"], "unit": "TFLOP/s",
+                "frac": (tc[top]["flops"] / (tc[top]["ms"] / 1e3) / 1e12 / pk["tensor"]) if top else None,
+                "traffic": None, "peak_source": pk["source"] + " (sustained bf16 cuBLAS)",
+                "ms_per_step_in_kernel": tc[top]["ms"] if top else None, "launches_per_step": tc[top]["calls"] if top else None,
+                "algorithmic_flops_per_step": tc[top]["flops"] if top else None,
+                "unet_step": {"ms": unet_ms, "algorithmic_tflop": UNET_TFLOP_PER_STEP, "achieved": tf,
+                              "frac": tf / pk["tensor"], "timed": "CUDA-graph replay inside the timed region"},
+                "by_kernel": {k: {"ms": round(v["ms"], 3), "calls": v["calls"],
+                                  "tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1) if v["flops"] else None}
+                              for k, v in sorted(fam.items(), key=lambda kv: -kv[1]["ms"])},
+                "render": render_roof}
+        else:
+            line["roofline"] = render_roof
         if N == 1 and not args.no_cpu_baseline:
             run, cores, n = cpu_oracle_sample()
             run()

@@ -1,0 +1,25 @@
+"""Single-kernel drivers for `ncu --set full` captures (one GPU, a handful of launches).
+    python profiles/run_kernel.py attention | gemm | conv | render"""
+import sys
+import torch
+sys.path.insert(0, "/root/repo")
+from signerf_b200 import nn_ops
+
+which = sys.argv[1]
+if which == "attention":      # self-attention of the 640-channel level at the 2048^2 sheet
+    B, heads, T = 2, 10, 16384
+    qkv = torch.randn(B * T, 3 * heads * 64, device="cuda").half()
+    c = heads * 64
+    for _ in range(3):
+        nn_ops.attention_f16(qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:], B, heads)
+elif which == "gemm":         # GEGLU projection of the 1280-channel level
+    a = torch.randn(8192, 1280, device="cuda").half()
+    w = torch.randn(10240, 1280, device="cuda").half()
+    for _ in range(3):
+        nn_ops.gemm_f16(a, w, None, out_f16=True)
+elif which == "conv":
+    x = torch.randn(2, 128, 128, 640, device="cuda").half()
+    w = torch.randn(640, 9 * 640, device="cuda").half()
+    for _ in range(3):
+        nn_ops.conv3x3_f16(x, w, None)
+torch.cuda.synchronize()

@@ -1,25 +1,37 @@
 // K6: softmax(Q K^T / sqrt(d)) V for the SpatialTransformer blocks of the SDXL / ControlNet UNet (SURVEY §8a row A12:
 // sgm CrossAttention, head_dim 64), both the self-attention over all sheet tokens (16 384 @640 ch, 4 096 @1280 ch at
-// the 2048^2 sheet) and the cross-attention over the 77 prompt tokens, on tcgen05 with the score tile in TMEM.
+// the 2048^2 sheet) and the cross-attention over the 77 prompt tokens, on tcgen05 with the score tiles in TMEM.
 //
-// One CTA = one 128-query tile of one (image, head).  Roles: warp 0 TMA producer, warp 1 tcgen05.mma issuer,
-// warps 2-5 softmax (thread i owns query row i = TMEM lane i).  Per 128-key tile j:
-//     S_j  = Q K_j^T                 4 x UMMA 128x128x16 into TMEM S[j%2]            (issued one tile ahead)
-//     P_j  = exp2(c S_j - c m_j)     TMEM -> registers (two passes: max, exp) -> fp16 -> swizzled smem P[j%2]
-//     O_j  = P_j V_j                 8 x UMMA 128x64x16 (V is the MN-major B operand) into TMEM O[j%2]
-//     acc  = acc * alpha_j + O_j     in registers of the softmax threads (the online-softmax rescale never touches TMEM)
+// One CTA = TWO 128-query tiles (A, B) of one (image, head) sharing every K/V tile.  Roles: warp 0 TMA producer,
+// warp 1 tcgen05.mma issuer, warps 2-5 softmax of tile A, warps 6-9 softmax of tile B (thread i owns query row i =
+// TMEM lane i).  The two softmax warpgroups ping-pong: while one exponentiates, the tensor core runs the other
+// tile's P.V and next Q.K^T.  Per 128-key tile j and query tile X:
+//     S_X  = Q_X K_j^T               4 x UMMA 128x128x16 into TMEM S_X
+//     P_X  = exp2(c S_X - c m)       ONE TMEM read of the row (128 registers) -> max -> exp -> fp16 -> TMEM P_X
+//     O_X += P_X V_j                 8 x UMMA 128x64x16, A = P_X from TMEM, B = V (MN-major smem), accumulating in TMEM
+// Shared-memory bandwidth (128 B/clk/SM) is what the tensor core competes for at these small N: keeping P in tensor
+// memory (tcgen05.st, A-from-TMEM MMA) halves the smem traffic per key tile (256 KB -> 128 KB per CTA).
+// The row of S is pulled into registers in one go and S_X is handed straight back to the issuer (s_free), so
+// Q_X K_{j+1}^T runs on the tensor core while the row is still being exponentiated.  The MUFU pipe is the next
+// limit at head_dim 64 (16 ex2/clk/SM = 1024 cycles per 128x128 tile against 512 tensor cycles); the two warpgroups
+// put two warps on every SM sub-partition so that one warp's FFMA / pack work fills the other's MUFU stalls.
+// S is read once and O stays in TMEM: the
+// online-softmax reference m is only advanced ("lazy rescale") when the row maximum grew by more than 2^8, in which
+// case the warp multiplies its O rows by exp2(c (m_old - m_new)) through tcgen05.ld / tcgen05.st; otherwise P is taken
+// against the stale m (P <= 2^8, harmless in fp16 / fp32 accumulation).  O is read once, at the end.
 // Keys beyond T_kv (ragged last tile, 77-token context) are masked to -inf before the max.
 #include "sgn_common.cuh"
 #include "sgn_tc.cuh"
 
 namespace sgn {
 
-constexpr int kAttnThreads = 192;
+constexpr int kAttnThreads = 320;
 constexpr int kHeadDim = 64;
 constexpr int kQTile = 128, kKvTile = 128;
-constexpr int kKvStages = 3;
+constexpr int kQPerCta = 2 * kQTile;
+constexpr int kKvStages = 4;
 constexpr int kTileBytes = 128 * 64 * 2;  // one [128 x 64] fp16 tile, 128-B rows, SWIZZLE_128B
-constexpr size_t kAttnSmem = 1024 + kTileBytes * (1 + 2 * kKvStages + 4) + 256;
+constexpr size_t kAttnSmem = 1024 + kTileBytes * (2 + 2 * kKvStages) + 256;
 
 struct AttnParams {
   int T_q, T_kv, n_kv_tiles;
@@ -27,6 +39,10 @@ struct AttnParams {
   __half* out;
   long long ldo;
 };
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -39,17 +55,17 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + kTileBytes;
+  uint8_t* sQ = smem;                          // Q_A, Q_B
+  uint8_t* sK = sQ + 2 * kTileBytes;
   uint8_t* sV = sK + kKvStages * kTileBytes;
-  uint8_t* sP = sV + kKvStages * kTileBytes;  // 2 buffers x 2 K-blocks x 16 KB
-  uint64_t* bar_q = reinterpret_cast<uint64_t*>(sP + 4 * kTileBytes);
+  uint64_t* bar_q = reinterpret_cast<uint64_t*>(sV + kKvStages * kTileBytes);
   uint64_t* kv_full = bar_q + 1;
   uint64_t* kv_empty = kv_full + kKvStages;
-  uint64_t* s_full = kv_empty + kKvStages;
+  uint64_t* s_full = kv_empty + kKvStages;     // [2] per query tile
   uint64_t* p_full = s_full + 2;
-  uint64_t* o_full = p_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+  uint64_t* o_full = p_full + 2;               // P_x(j) V(j) complete (one phase per key tile)
+  uint64_t* s_free = o_full + 2;               // S_x(j) is in registers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, head = blockIdx.y, img = blockIdx.z;
@@ -68,6 +84,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tc::mbar_init(&s_full[s], 1);
       tc::mbar_init(&p_full[s], 128);
       tc::mbar_init(&o_full[s], 1);
+      tc::mbar_init(&s_free[s], 128);
     }
     tc::mbar_fence_init();
   }
@@ -76,13 +93,15 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base;         // S[0] cols 0..127, S[1] cols 128..255
-  const uint32_t tO = tmem_base + 256;   // O[0] cols 256..319, O[1] cols 320..383
+  const uint32_t tS = tmem_base;         // S_A cols 0..127, S_B cols 128..255
+  const uint32_t tO = tmem_base + 256;   // O_A cols 256..319, O_B cols 320..383
+  const uint32_t tP = tmem_base + 384;   // P_A cols 384..447, P_B cols 448..511 (fp16 pairs: 128 keys = 64 columns)
 
   if (warp == 0) {
     if (lane == 0) {  // ---------------- TMA producer
-      tc::mbar_expect_tx(bar_q, kTileBytes);
-      tc::tma_load_2d(sQ, &tmQ, bar_q, head * kHeadDim, img * p.T_q + qt * kQTile);
+      tc::mbar_expect_tx(bar_q, 2 * kTileBytes);
+      tc::tma_load_2d(sQ, &tmQ, bar_q, head * kHeadDim, img * p.T_q + qt * kQPerCta);
+      tc::tma_load_2d(sQ + kTileBytes, &tmQ, bar_q, head * kHeadDim, img * p.T_q + qt * kQPerCta + kQTile);
       for (int j = 0; j < n_kv; ++j) {
         const int s = j % kKvStages;
         const uint32_t ph = (j / kKvStages) & 1;
@@ -97,126 +116,149 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (lane == 0) {  // ---------------- MMA issuer
       const uint32_t idesc_qk = tc::umma_idesc_f16(128, kKvTile, false, false);
       const uint32_t idesc_pv = tc::umma_idesc_f16(128, kHeadDim, false, true);  // B = V, MN-major
-      const uint64_t dq = tc::umma_desc_sw128(tc::smem_u32(sQ));
-      auto issue_pv = [&](int i) {
-        const int b = i & 1, s = i % kKvStages;
-        tc::mbar_wait(&p_full[b], (i >> 1) & 1);
-        tc::tc_fence_after();
-        const uint64_t dv = tc::umma_desc_sw128(tc::smem_u32(sV + s * kTileBytes));
-#pragma unroll
-        for (int kk = 0; kk < kKvTile / 16; ++kk) {
-          // A = P[b]: two 64-key K-blocks of 16 KB, +32 B per 16 keys inside a block;  B = V: 16 keys = 16 rows = 2 KB
-          const uint64_t dp = tc::umma_desc_sw128(tc::smem_u32(sP + (2 * b + (kk >> 2)) * kTileBytes)) + 2 * (kk & 3);
-          tc::umma_f16_ss(tO + b * kHeadDim, dp, dv + kk * (2048 >> 4), idesc_pv, kk != 0);
-        }
-        tc::umma_commit(&o_full[b]);
-        tc::umma_commit(&kv_empty[s]);
-      };
-      tc::mbar_wait(bar_q, 0);
-      for (int j = 0; j < n_kv; ++j) {
-        const int s = j % kKvStages;
-        tc::mbar_wait(&kv_full[s], (j / kKvStages) & 1);
-        tc::tc_fence_after();
-        const uint64_t dk = tc::umma_desc_sw128(tc::smem_u32(sK + s * kTileBytes));
+      auto issue_qk = [&](int x, int j) {
+        const uint64_t dq = tc::umma_desc_sw128(tc::smem_u32(sQ + x * kTileBytes));
+        const uint64_t dk = tc::umma_desc_sw128(tc::smem_u32(sK + (j % kKvStages) * kTileBytes));
 #pragma unroll
         for (int k = 0; k < kHeadDim / 16; ++k)
-          tc::umma_f16_ss(tS + (j & 1) * kKvTile, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
-        tc::umma_commit(&s_full[j & 1]);
-        if (j > 0) issue_pv(j - 1);
+          tc::umma_f16_ss(tS + x * kKvTile, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
+        tc::umma_commit(&s_full[x]);
+      };
+      auto issue_pv = [&](int x, int j) {
+        const uint64_t dv = tc::umma_desc_sw128(tc::smem_u32(sV + (j % kKvStages) * kTileBytes));
+#pragma unroll
+        for (int kk = 0; kk < kKvTile / 16; ++kk) {
+          // A = P_x in TMEM: 16 keys = 8 columns;  B = V: 16 keys = 16 rows = 2 KB
+          tc::umma_f16_ts(tO + x * kHeadDim, tP + x * 64 + kk * 8, dv + kk * (2048 >> 4), idesc_pv, (j | kk) != 0);
+        }
+        tc::umma_commit(&o_full[x]);
+      };
+      tc::mbar_wait(bar_q, 0);
+      tc::mbar_wait(&kv_full[0], 0);
+      tc::tc_fence_after();
+      issue_qk(0, 0);
+      issue_qk(1, 0);
+      // Event loop: serve whichever of {S_x free -> next Q K^T, P_x ready -> P V} is ready, per query tile.
+      int qk_next[2] = {1, 1}, pv_next[2] = {0, 0};
+      while (pv_next[0] < n_kv || pv_next[1] < n_kv) {
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+          const int jq = qk_next[x];
+          if (jq < n_kv && tc::mbar_test(&s_free[x], (jq - 1) & 1) &&
+              tc::mbar_test(&kv_full[jq % kKvStages], (jq / kKvStages) & 1)) {
+            tc::tc_fence_after();
+            issue_qk(x, jq);
+            qk_next[x] = jq + 1;
+          }
+          const int jp = pv_next[x];
+          if (jp < n_kv && tc::mbar_test(&p_full[x], jp & 1)) {
+            tc::tc_fence_after();
+            issue_pv(x, jp);
+            pv_next[x] = jp + 1;
+            if (pv_next[x ^ 1] > jp) tc::umma_commit(&kv_empty[jp % kKvStages]);  // both tiles are through K/V(jp)
+          }
+        }
       }
-      issue_pv(n_kv - 1);
     }
-  } else {  // ---------------- softmax warps: thread = query row = TMEM lane
+  } else {  // ---------------- softmax warpgroups: x = 0 (warps 2-5) / 1 (warps 6-9); thread = query row = TMEM lane
+    const int x = (warp - 2) >> 2;
     const int lane_base = (warp & 3) * 32;
     const int row = lane_base + lane;
     const uint32_t lane_addr = (uint32_t)lane_base << 16;
     const float sc = p.scale_log2e;
-    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
-    float acc[kHeadDim];
-#pragma unroll
-    for (int i = 0; i < kHeadDim; ++i) acc[i] = 0.f;
-    uint8_t* p_row = sP + (row >> 3) * 1024 + (row & 7) * 128;
-    const int sw = row & 7;
-
-    auto accumulate_o = [&](int i, float alpha) {
-      const int b = i & 1;
-      tc::mbar_wait(&o_full[b], (i >> 1) & 1);
-      tc::tc_fence_after();
-      uint32_t o[32];
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        tc::tmem_ld32(tO + b * kHeadDim + c * 32 + lane_addr, o);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int q = 0; q < 32; ++q) acc[c * 32 + q] = fmaf(acc[c * 32 + q], alpha, __uint_as_float(o[q]));
-      }
-    };
+    float m_run = -INFINITY, l_run = 0.f;
+    const uint32_t tp = tP + x * 64 + lane_addr;
+    const uint32_t ts = tS + x * kKvTile + lane_addr;
+    const uint32_t to = tO + x * kHeadDim + lane_addr;
 
     for (int j = 0; j < n_kv; ++j) {
-      const int b = j & 1;
       const int kv_rem = p.T_kv - j * kKvTile;  // >= 1
-      tc::mbar_wait(&s_full[b], (j >> 1) & 1);
+      tc::mbar_wait(&s_full[x], j & 1);
       tc::tc_fence_after();
-      const uint32_t ts = tS + b * kKvTile + lane_addr;
-      uint32_t s[32];
-      float mx = -INFINITY;
+      uint32_t s[128];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        tc::tmem_ld32(ts + c * 32, s);
-        tc::tmem_ld_wait();
-        if (kv_rem >= (c + 1) * 32) {
+      for (int c = 0; c < 4; ++c) tc::tmem_ld32(ts + c * 32, s + c * 32);
+      tc::tmem_ld_wait();
+      tc::tc_fence_before();
+      tc::mbar_arrive(&s_free[x]);     // the issuer may overwrite S_x with Q_x K_{j+1}^T now
+      if (kv_rem < kKvTile) {
 #pragma unroll
-          for (int q = 0; q < 32; ++q) mx = fmaxf(mx, __uint_as_float(s[q]));
-        } else {
-#pragma unroll
-          for (int q = 0; q < 32; ++q)
-            if (c * 32 + q < kv_rem) mx = fmaxf(mx, __uint_as_float(s[q]));
-        }
+        for (int q = 0; q < 128; ++q)
+          if (q >= kv_rem) s[q] = 0xff800000u;  // -inf
       }
-      const float m_new = fmaxf(m_run, mx);
-      const float alpha = ex2((m_run - m_new) * sc);  // first tile: exp2(-inf) = 0
-      const float neg_m = -m_new * sc;
-      float psum = 0.f;
+      float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        tc::tmem_ld32(ts + c * 32, s);
-        tc::tmem_ld_wait();
-        uint8_t* blk = p_row + (2 * b + (c >> 1)) * kTileBytes;
+      for (int q = 2; q < 128; q += 2) {
+        mx0 = fmaxf(mx0, __uint_as_float(s[q]));
+        mx1 = fmaxf(mx1, __uint_as_float(s[q + 1]));
+      }
+      const float mx = fmaxf(mx0, mx1);
+      // P_x(j-1) V(j-1) must be complete before P_x is rewritten or O_x rescaled; P_x(j) V(j) is not issued before
+      // this thread arrives on p_full, so O_x is quiescent in between.
+      if (j > 0) {
+        tc::mbar_wait(&o_full[x], (j - 1) & 1);
+        tc::tc_fence_after();
+      }
+      const bool grow = (mx - m_run) * sc > 8.f;   // also true on the first tile (m_run = -inf)
+      if (__any_sync(0xffffffffu, grow) && j > 0) {
+        const float alpha = grow ? ex2((m_run - mx) * sc) : 1.f;
+        uint32_t o[16];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {  // 8 keys = one 16-byte chunk
+        for (int c = 0; c < 4; ++c) {
+          tc::tmem_ld16(to + c * 16, o);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 16; ++q) o[q] = __float_as_uint(__uint_as_float(o[q]) * alpha);
+          tc::tmem_st16(to + c * 16, o);
+        }
+        tc::tmem_st_wait();
+        l_run *= alpha;
+      }
+      if (grow) m_run = mx;
+      const float neg_m = -m_run * sc;
+      float psum0 = 0.f, psum1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {      // 64 keys -> 32 packed columns per tcgen05.st
+        uint32_t pk[32];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
           float e[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int col = c * 32 + g * 8 + q;
-            e[q] = col < kv_rem ? ex2(fmaf(__uint_as_float(s[g * 8 + q]), sc, neg_m)) : 0.f;
-            psum += e[q];
+          for (int q = 0; q < 8; ++q) e[q] = ex2(fmaf(__uint_as_float(s[c * 64 + g * 8 + q]), sc, neg_m));
+          psum0 += (e[0] + e[1]) + (e[2] + e[3]);
+          psum1 += (e[4] + e[5]) + (e[6] + e[7]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            __half2 h = __floats2half2_rn(e[2 * q], e[2 * q + 1]);
+            pk[g * 4 + q] = *reinterpret_cast<uint32_t*>(&h);
           }
-          __half2 h[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) h[q] = __floats2half2_rn(e[2 * q], e[2 * q + 1]);
-          const int chunk = (c & 1) * 4 + g;
-          *reinterpret_cast<uint4*>(blk + ((chunk ^ sw) << 4)) = *reinterpret_cast<uint4*>(h);
         }
+        tc::tmem_st32(tp + c * 32, pk);
       }
-      l_run = fmaf(l_run, alpha, psum);
-      m_run = m_new;
-      tc::tc_fence_before();          // S[b] reads done before the issuer overwrites it (tile j+2)
-      tc::fence_proxy_async_smem();   // P[b] visible to the tensor core
-      tc::mbar_arrive(&p_full[b]);
-      if (j > 0) accumulate_o(j - 1, alpha_prev);
-      alpha_prev = alpha;
+      tc::tmem_st_wait();
+      l_run += psum0 + psum1;
+      tc::tc_fence_before();          // P_x written, O_x accesses done before the issuer touches them
+      tc::mbar_arrive(&p_full[x]);
     }
-    accumulate_o(n_kv - 1, alpha_prev);
-
-    const int q_row = qt * kQTile + row;
-    if (q_row < p.T_q) {
-      const float inv = 1.f / l_run;
-      __half2 h[kHeadDim / 2];
+    // O_x complete after the last P.V
+    tc::mbar_wait(&o_full[x], (n_kv - 1) & 1);
+    tc::tc_fence_after();
+    const int q_row = qt * kQPerCta + x * kQTile + row;
+    const float inv = 1.f / l_run;
+    __half* orow = p.out + ((long long)img * p.T_q + q_row) * p.ldo + head * kHeadDim;
 #pragma unroll
-      for (int i = 0; i < kHeadDim / 2; ++i) h[i] = __floats2half2_rn(acc[2 * i] * inv, acc[2 * i + 1] * inv);
-      uint4* op = reinterpret_cast<uint4*>(p.out + ((long long)img * p.T_q + q_row) * p.ldo + head * kHeadDim);
+    for (int c = 0; c < 2; ++c) {
+      uint32_t o[32];
+      tc::tmem_ld32(to + c * 32, o);
+      tc::tmem_ld_wait();
+      if (q_row < p.T_q) {
+        __half2 h[16];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) op[i] = reinterpret_cast<uint4*>(h)[i];
+        for (int i = 0; i < 16; ++i)
+          h[i] = __floats2half2_rn(__uint_as_float(o[2 * i]) * inv, __uint_as_float(o[2 * i + 1]) * inv);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(orow + c * 32)[i] = reinterpret_cast<uint4*>(h)[i];
+      }
     }
   }
   tc::tc_fence_before();
@@ -264,7 +306,7 @@ extern "C" int sgn_attention_f16(const void* d_q, int64_t ldq, const void* d_k, 
   p.scale_log2e = scale * 1.4426950408889634f;
   p.out = reinterpret_cast<__half*>(d_out);
   p.ldo = ldo;
-  dim3 grid((T_q + kQTile - 1) / kQTile, heads, B);
+  dim3 grid((T_q + kQPerCta - 1) / kQPerCta, heads, B);
   k_attention_tc<<<grid, kAttnThreads, kAttnSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
   SGN_LAUNCH_CHECK();
   return SGN_OK;

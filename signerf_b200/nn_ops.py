@@ -13,6 +13,47 @@ from . import _lib
 from .ops import _ptr, _stream
 
 
+# ---------------------------------------------------------------------------------------------- per-family profiling
+# bench.py brackets every C-ABI call with CUDA events (eager pass, outside the timed region) to split a step's device
+# time and algorithmic FLOPs by kernel family: the roofline numerators of the JSON line come from here.
+_PROFILE: Optional[dict] = None
+
+
+def start_profile() -> None:
+    global _PROFILE
+    _PROFILE = {}
+
+
+def stop_profile() -> dict:
+    """-> {family: {"ms": device time, "flops": algorithmic FLOPs, "calls": n}}"""
+    global _PROFILE
+    prof, _PROFILE = _PROFILE or {}, None
+    torch.cuda.synchronize()
+    out = {}
+    for name, spans in prof.items():
+        out[name] = {"ms": sum(a.elapsed_time(b) for a, b, _ in spans), "flops": float(sum(f for _, _, f in spans)),
+                     "calls": len(spans)}
+    return out
+
+
+class _span:
+    def __init__(self, name: str, flops: float = 0.0):
+        self.name, self.flops = name, flops
+
+    def __enter__(self):
+        if _PROFILE is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _PROFILE is not None:
+            self.b.record()
+            _PROFILE.setdefault(self.name, []).append((self.a, self.b, self.flops))
+        return False
+
+
 def _chk(t: Optional[Tensor], dtype: torch.dtype, name: str) -> None:
     if t is None:
         return
@@ -55,7 +96,7 @@ def gemm_f16(a: Tensor, w: Tensor, bias: Optional[Tensor] = None, *, rowbias: Op
     elif out.dtype != odt or tuple(out.shape) != oshape or not out.is_contiguous():
         raise ValueError("bad `out` tensor")
     e = _epilogue(bias, rowbias, rows_per_batch, residual, out_f16, geglu, False)
-    with torch.cuda.device(a.device):
+    with torch.cuda.device(a.device), _span("k_gemm_tc (linear)", 2.0 * M * N * K):
         _lib.check(_lib.load().sgn_gemm_f16(_ptr(a), K, _ptr(w), K, M, N, K, C.byref(e), _ptr(out), _stream(a.device)))
     return out
 
@@ -77,7 +118,7 @@ def conv3x3_f16(x: Tensor, w: Tensor, bias: Optional[Tensor] = None, *, rowbias:
     elif out.dtype != odt or tuple(out.shape) != oshape or not out.is_contiguous():
         raise ValueError("bad `out` tensor")
     e = _epilogue(bias, rowbias, H * W if rowbias is not None else 0, residual, out_f16, False, nchw)
-    with torch.cuda.device(x.device):
+    with torch.cuda.device(x.device), _span("k_gemm_tc (conv3x3)", 2.0 * B * H * W * N * 9 * Cin):
         _lib.check(_lib.load().sgn_conv3x3_f16(_ptr(x), _ptr(w), B, H, W, Cin, N, C.byref(e), _ptr(out),
                                                _stream(x.device)))
     return out
@@ -92,7 +133,7 @@ def attention_f16(q: Tensor, k: Tensor, v: Tensor, batch: int, heads: int, out: 
     Tq, Tkv = q.shape[0] // batch, k.shape[0] // batch
     if out is None:
         out = torch.empty((q.shape[0], heads * 64), dtype=torch.float16, device=q.device)
-    with torch.cuda.device(q.device):
+    with torch.cuda.device(q.device), _span("k_attention_tc", 4.0 * batch * heads * Tq * Tkv * 64):
         _lib.check(_lib.load().sgn_attention_f16(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0),
                                                  batch, heads, Tq, Tkv, 0.125, _ptr(out), out.stride(0),
                                                  _stream(q.device)))
@@ -100,7 +141,7 @@ def attention_f16(q: Tensor, k: Tensor, v: Tensor, batch: int, heads: int, out: 
 
 
 def _call(dev, fn, *args) -> None:
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _span(fn.__name__):
         _lib.check(fn(*args, _stream(dev)))
 
 

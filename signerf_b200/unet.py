@@ -597,6 +597,7 @@ class BenchUNet:
         sig = img2img_sigmas()
         self.sigma, self.sigma_next = sig[0], sig[1]
         self.use_graph, self.graph, self.out = use_graph, None, None
+        self.launches_per_step = 0   # kernel launches one step issues (counted while capturing; replays issue the same)
 
     def _run(self):
         return self.net.step(self.x, self.sigma, self.sigma_next, self.context, self.y, self.hint, self.noise, self.init,
@@ -614,8 +615,16 @@ class BenchUNet:
         if self.graph is None:
             self._run()  # warm-up outside capture (function attributes, lazy module load)
             torch.cuda.synchronize()
+            n0 = _lib.launch_count()
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self.out = self._run()
+            self.launches_per_step = _lib.launch_count() - n0
         self.graph.replay()
         return self.out
+
+    def profile_eager(self) -> dict:
+        """One eager step with every C-ABI call bracketed by CUDA events -> per-kernel-family time / FLOPs."""
+        K.start_profile()
+        self._run()
+        return K.stop_profile()
