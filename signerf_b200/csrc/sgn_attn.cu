@@ -40,6 +40,10 @@ struct AttnParams {
   long long ldo;
 };
 
+// named barriers 1 / 2: the exp2 sections of the two softmax warpgroups take turns on the MUFU pipe, which staggers
+// them by half a period: while one exponentiates, the other loads its next S row and finds the row maximum.
+__device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -171,6 +175,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t ts = tS + x * kKvTile + lane_addr;
     const uint32_t to = tO + x * kHeadDim + lane_addr;
 
+    if (x == 1) named_arrive(1, 256);  // group A takes the first turn
     for (int j = 0; j < n_kv; ++j) {
       const int kv_rem = p.T_kv - j * kKvTile;  // >= 1
       tc::mbar_wait(&s_full[x], j & 1);
@@ -217,6 +222,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       if (grow) m_run = mx;
       const float neg_m = -m_run * sc;
       float psum0 = 0.f, psum1 = 0.f;
+      named_sync(1 + x, 256);            // my turn on the MUFU pipe
 #pragma unroll
       for (int c = 0; c < 2; ++c) {      // 64 keys -> 32 packed columns per tcgen05.st
         uint32_t pk[32];
@@ -235,11 +241,13 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
         tc::tmem_st32(tp + c * 32, pk);
       }
+      named_arrive(2 - x, 256);          // hand the turn to the other warpgroup
       tc::tmem_st_wait();
       l_run += psum0 + psum1;
       tc::tc_fence_before();          // P_x written, O_x accesses done before the issuer touches them
       tc::mbar_arrive(&p_full[x]);
     }
+    if (x == 0) named_sync(1, 256);      // absorb group B's last hand-over
     // O_x complete after the last P.V
     tc::mbar_wait(&o_full[x], (n_kv - 1) & 1);
     tc::tc_fence_after();
