@@ -163,7 +163,7 @@ def main():
     args.warmup = max(args.warmup, 3)
 
     import torch.distributed as dist
-    from signerf_b200 import _lib, ops, synthetic
+    from signerf_b200 import _lib, ops, sharding, synthetic
     from signerf_b200.sheet import ReferenceSheetRenderer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -192,7 +192,7 @@ def main():
     c2w_all = torch.stack(c2w_all)      # [N,16,3,4]
     intr_all = torch.stack(intr_all)    # [N,16,4]
     # per-view shard of every grid for this rank
-    mine = [v for v in range(VIEWS) if v % N == rank]
+    mine = sharding.views_of_rank(VIEWS, N, rank)
     c2w_h = c2w_all[:, mine].reshape(-1, 3, 4).contiguous().pin_memory()
     intr_h = intr_all[:, mine].reshape(-1, 4).contiguous().pin_memory()
     c2w_d, intr_d = c2w_h.to(dev), intr_h.to(dev)
@@ -219,13 +219,9 @@ def main():
         mask, cond, _ = ops.mask_condition(c2w, intr, depth, mopts)
         if N > 1:
             # pack [rgb3 | depth | cond | mask] per pixel and all-gather the per-view shards of all N grids
-            packed = torch.cat([rgb, depth, cond, mask.float()], dim=-1).view(N, len(mine), H, W, 6)
-            gathered = [torch.empty_like(packed) for _ in range(N)]
-            dist.all_gather(gathered, packed)
-            for r in range(N):
-                tiles[:, r::N] = gathered[r]
-            t = tiles[rank]
-            rgb, cond, mask = t[..., 0:3].contiguous(), t[..., 4:5].contiguous(), t[..., 5:6].contiguous()
+            packed = sharding.pack_tiles(rgb, depth, cond, mask).view(N, len(mine), H, W, sharding.PACK_CHANNELS)
+            sharding.gather_grids(packed, VIEWS, N, rank, out=tiles)
+            rgb, _, cond, mask = sharding.unpack_tiles(tiles[rank])
         b_ = sheet.paste(rgb, mask, cond, 0)
         out = b_.image
         if unet is not None:

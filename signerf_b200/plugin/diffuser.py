@@ -1,0 +1,117 @@
+"""Mirror of reference signerf/diffuser/diffuser.py.  `DiffuserConfig` keeps every field (incl. the unused ones);
+`Diffuser.diffuse` keeps the signature and the `_custom(original, condition, rendered, mask)` argument order
+(diffuser.py:92-113).  mode="custom" — the hook the reference leaves unimplemented — runs the in-process
+SDXL + ControlNet-depth denoiser (signerf_b200/unet.py) instead of POSTing PNGs to an A1111 server."""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Callable, List, Literal, Optional, Type
+
+import torch
+from torch import Tensor
+
+from .. import nn_ops as K
+from .. import ops
+from ..unet import SDXLDenoiserB200, img2img_sigmas
+from .base import InstantiateConfig
+
+
+@dataclass
+class DiffuserConfig(InstantiateConfig):
+    """diffuser.py:19-60"""
+    _target: Type = field(default_factory=lambda: Diffuser)
+    mode: Literal["custom", "remoteSDWebUIControlNet"] = "remoteSDWebUIControlNet"
+    url: str = "http://127.0.0.1"
+    port: int = 5000
+    prompt: str = "don't change the image"
+    guidance_scale: float = 7
+    image_guidance_scale: float = 1.5
+    denoising_strength: float = 0.9
+    num_inference_steps: int = 20
+    lower_bound: float = 0.02
+    upper_bound: float = 0.98
+    seed: int = 1
+    stable_diffusion_model: str = "sd_xl_base_1.0.safetensors [31e35c80fc]"
+    controlnet_model: str = "diffusers_xl_depth_full [2f51180b]"
+    controlnet_lowvram: bool = False
+    controlnet_conditioning_scale: float = 0.8
+    controlnet_conditioning_scale_start: float = 0.0
+    controlnet_conditioning_scale_end: float = 1.0
+    controlnet_control_mode: Literal["Balanced", "My prompt is more important", "ControlNet is more important"] = "Balanced"
+
+
+class InProcessSDXL:
+    """The A1111 img2img request of diffuser.py:132-169 executed in-process on latents:
+    t_enc = int(min(strength, 0.999) * steps) Euler-ancestral steps with CFG, ControlNet (weight, Balanced,
+    guidance 0..1) and the inpaint blend.  Prompt conditioning (context [2,77,2048], y [2,2816]: cond then uncond) comes
+    from the caller — the CLIP text encoders and the VAE are §8(f) row 1; `codec` plugs a VAE in when there is one."""
+
+    def __init__(self, denoiser: SDXLDenoiserB200, context: Tensor, y: Tensor,
+                 codec: Optional[object] = None):
+        self.net, self.context, self.y, self.codec = denoiser, context, y, codec
+
+    def denoise_latents(self, init_latent: Tensor, hint: Tensor, latent_mask: Tensor, steps: int, strength: float,
+                        cfg_scale: float, control_weight: float, seed: int) -> Tensor:
+        """init_latent [1,4,h,w]; hint [1,3,8h,8w] in [0,1]; latent_mask [1,1,h,w] = 1 where the original is kept."""
+        sig = img2img_sigmas(steps, strength)
+        g = torch.Generator(device=init_latent.device).manual_seed(int(seed))
+        x = init_latent + torch.randn(init_latent.shape, generator=g, device=init_latent.device) * sig[0]
+        for i in range(len(sig) - 1):
+            noise = torch.randn(init_latent.shape, generator=g, device=init_latent.device) if sig[i + 1] > 0 else None
+            x, _, _ = self.net.step(x, sig[i], sig[i + 1], self.context, self.y, hint, noise, init_latent, latent_mask,
+                                    cfg_scale, control_weight)
+        return x
+
+
+class Diffuser:
+    """diffuser.py:62-195"""
+
+    def __init__(self, config: DiffuserConfig, device: str) -> None:
+        self.config, self.device = config, device
+        self.prompt = config.prompt
+        self.guidance_scale = config.guidance_scale
+        self.image_guidance_scale = config.image_guidance_scale
+        self.denoising_strength = config.denoising_strength
+        self.num_inference_steps = config.num_inference_steps
+        self.seed = config.seed
+        self.stable_diffusion_model = config.stable_diffusion_model
+        self.controlnet_conditioning_scale = config.controlnet_conditioning_scale
+        self.controlnet_model = config.controlnet_model
+        self.controlnet_lowvram = config.controlnet_lowvram
+        self.controlnet_conditioning_scale_start = config.controlnet_conditioning_scale_start
+        self.controlnet_conditioning_scale_end = config.controlnet_conditioning_scale_end
+        self.controlnet_control_mode = config.controlnet_control_mode
+        self.url = f"{self.config.url}:{self.config.port}"
+        self.backend: Optional[InProcessSDXL] = None   # attached by the host application (weights are not ours to ship)
+
+    def attach(self, backend: InProcessSDXL) -> None:
+        self.backend = backend
+
+    def diffuse(self, original_image: Tensor, rendered_image: Tensor, mask_image: Tensor = None,
+                condition_image: Tensor = None) -> Tensor:
+        if self.config.mode == "custom":
+            return self._custom(original_image, condition_image, rendered_image, mask_image)
+        if self.config.mode == "remoteSDWebUIControlNet":
+            raise NotImplementedError("the HTTP client of diffuser.py:116-195 is out of scope (SURVEY §2 row 2): keep the "
+                                      "reference's own Diffuser for mode='remoteSDWebUIControlNet', or use mode='custom'")
+        raise ValueError(f"unknown diffuser mode {self.config.mode}")
+
+    def _custom(self, original_image: Tensor, condition_image: Tensor, rendered_image: Tensor, mask_image: Tensor) -> Tensor:
+        """Sheet RGB [H,W,3] + mask [H,W,1] + condition [H,W,1] -> edited sheet [H,W,3] in [0,1]."""
+        if self.backend is None:
+            raise RuntimeError("Diffuser(mode='custom') needs an InProcessSDXL backend: call diffuser.attach(...)")
+        if self.backend.codec is None:
+            raise RuntimeError("no latent codec attached: the SDXL VAE is a §8(f) 'next' row — attach a codec object with "
+                               "encode(image[H,W,3]) -> latent[1,4,H/8,W/8] and decode(latent) -> image[H,W,3]")
+        H, W = original_image.shape[0], original_image.shape[1]
+        dev = self.backend.net.dev
+        img = ops.quantize_u8(original_image.to(dev)).float() / 255.0          # tensor_to_image truncation (diffuser.py:121)
+        mask = mask_image.to(dev).float() if mask_image is not None else torch.ones((H, W, 1), device=dev)
+        cond = condition_image.to(dev).float() if condition_image is not None else torch.zeros((H, W, 1), device=dev)
+        hint = torch.empty((1, 3, H, W), dtype=torch.float32, device=dev)
+        lat_mask = torch.empty((1, 1, H // 8, W // 8), dtype=torch.float32, device=dev)
+        K.make_hint_and_latent_mask(cond.contiguous(), mask.contiguous(), hint, lat_mask)
+        init = self.backend.codec.encode(img)
+        x = self.backend.denoise_latents(init, hint, lat_mask, self.num_inference_steps, self.denoising_strength,
+                                         self.guidance_scale, self.controlnet_conditioning_scale, self.seed)
+        return self.backend.codec.decode(x)

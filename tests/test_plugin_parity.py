@@ -1,0 +1,91 @@
+"""GPU: the plugin-level entry points (plugin.DatasetGenerator.generate_reference_sheet / generate_with_reference_sheet
+over the fused kernels) against the oracle's restatement of the reference's per-view Python loops
+(oracle/nerfacto_ref.py + oracle/sheet_ref.py), with a deterministic stand-in for the diffuser so that the sheet
+assembly, blending and tile cut-out are compared exactly."""
+import pytest
+import torch
+
+import signerf_b200.plugin as P
+from oracle import nerfacto_ref as R
+from oracle import sheet_ref as S
+from signerf_b200 import ops
+from tests.helpers import field_from_oracle, rel_l2, ring_cameras
+
+pytestmark = pytest.mark.gpu
+
+
+class _StubDiffuser(P.Diffuser):
+    """edited = 1 - 0.5 * image where masked; returned on the CPU like the reference's HTTP client does."""
+
+    def diffuse(self, original_image, rendered_image, mask_image=None, condition_image=None):
+        return (1.0 - 0.5 * original_image).cpu()
+
+
+def _generator(rows, cols, H, W, ds):
+    cfg = P.DatasetGeneratorConfig(rows=rows, cols=cols, width=W, height=H, downscale_factor=ds, mask_dialation=(7, 7),
+                                   fx=float(W), fy=float(W), cx=W / 2, cy=H / 2)
+    gen = cfg.setup(original_transform_matrix=torch.eye(4)[:3], original_scale_factor=1.0,
+                    transform_poses_to_original_space=lambda x: x, device="cuda")
+    gen.diffuser = _StubDiffuser(cfg.diffuser, "cuda")
+    return gen
+
+
+def _oracle_views(m, c2w, intr, H, W, gen, S_samples):
+    renders, masks, conds = [], [], []
+    for v in range(c2w.shape[0]):
+        ref = R.render_view(m, c2w[v], *intr[v].tolist(), W, H, "flat", S_samples)
+        rays = R.generate_rays(c2w[v], *intr[v].tolist(), W, H)
+        mk, cd, _ = S.render_camera_aabb(rays.origins.view(H, W, 3), rays.directions.view(H, W, 3), ref["depth"],
+                                         gen.aabb.cpu(), False, (7, 7), 0.1, None)
+        renders.append(ref["rgb"]), masks.append(mk), conds.append(cd)
+    return renders, masks, conds
+
+
+def test_generate_reference_sheet_and_with_reference_sheet():
+    rows, cols, H, W, ds, Ssamp = 2, 2, 48, 40, 2, 24
+    th, tw = H // ds, W // ds
+    m = R.make_model(0, dense=True, table_scale=0.5, density_gain=20.0)
+    graph = P.FusedNerfactoGraph(field_from_oracle(m), ops.RenderOptions(mode="flat", num_samples=Ssamp, mlp_mode=ops.MLP_FP32))
+    gen = _generator(rows, cols, H, W, ds)
+    c2w, intr = ring_cameras(rows * cols, W, H)
+    cams = P.CameraBatch(c2w[:-1], float(W), float(W), W / 2, H / 2, W, H)
+    img, msk, cnd, edited, refs = gen.generate_reference_sheet(graph, cams, tw, th)
+    renders, masks, conds = _oracle_views(m, c2w[:-1], intr[:-1], H, W, gen, Ssamp)
+    img_r, msk_r, cnd_r = S.reference_sheet(renders, masks, conds, rows, cols, th, tw, 0)
+    assert img.shape == img_r.shape == (2 * th, 2 * tw, 3)
+    assert rel_l2(img, img_r) < 2e-5 and rel_l2(cnd, cnd_r) < 1e-3
+    assert float((msk.cpu() != msk_r).float().mean()) < 2e-3            # median-depth bin flips at the box boundary
+    edited_r = S.blend(1.0 - 0.5 * img_r, img_r, msk_r)
+    same = (msk.cpu() == msk_r).expand_as(edited_r)
+    assert torch.allclose(edited.cpu()[same], edited_r[same], atol=1e-4)
+    assert len(refs) == 3 and set(refs[0]) == {"render", "mask", "condition", "render_scaled", "mask_scaled",
+                                               "condition_scaled", "edited", "edited_scaled"}
+    for i in range(3):
+        assert rel_l2(refs[i]["render"], renders[i]) < 2e-5
+        assert refs[i]["edited"].shape == (H, W, 3) and refs[i]["edited_scaled"].shape == (th, tw, 3)
+        assert torch.equal(refs[i]["edited"].cpu(), S.cut_tile(edited.cpu(), i, cols, th, tw, 0, H, W))
+    # per-dataset-camera pass: the last tile is overwritten IN PLACE in both sheet arguments (Appendix A.2)
+    cam_last = P.CameraBatch(c2w[-1:], float(W), float(W), W / 2, H / 2, W, H)
+    img_arg, cnd_arg = edited.clone(), cnd.clone()
+    out = gen.generate_with_reference_sheet(graph, cam_last, None, tw, th, img_arg, cnd_arg)
+    r_l, m_l, c_l = _oracle_views(m, c2w[-1:], intr[-1:], H, W, gen, Ssamp)
+    rs = S._interp(r_l[0], th, tw)
+    assert rel_l2(img_arg[th:, tw:], rs) < 2e-5 and torch.equal(img_arg[:th], edited[:th])
+    assert rel_l2(out["render_scaled"], rs) < 2e-5 and out["edited"].shape == (H, W, 3)
+    ms = S._interp(m_l[0].float(), th, tw) > 0.5
+    exp = (1.0 - 0.5 * rs) * ms + rs * (~ms)
+    ok = (out["mask_scaled"].cpu() == ms).expand_as(exp)
+    assert float(ok.float().mean()) > 0.995 and torch.allclose(out["edited_scaled"].cpu()[ok], exp[ok], atol=1e-4)
+
+
+def test_render_camera_return_arity_quirk():
+    m = R.make_model(0, dense=True)
+    graph = P.FusedNerfactoGraph(field_from_oracle(m), ops.RenderOptions(mode="flat", num_samples=8))
+    gen = _generator(2, 2, 16, 16, 1)
+    c2w, _ = ring_cameras(1, 16, 16)
+    cam = P.CameraBatch(c2w, 16.0, 16.0, 8.0, 8.0, 16, 16)
+    assert len(gen.render_camera(graph, cam)) == 3
+    assert len(gen.render_camera(graph, cam, with_mask=False)) == 4          # datasetgenerator.py:708
+    assert len(gen.render_camera(graph, cam, with_condition=False)) == 4     # :783
+    rgb, mask, cond = gen.render_camera(graph, cam)
+    assert rgb.shape == (16, 16, 3) and mask.dtype == torch.bool and cond.shape == (16, 16, 1)
