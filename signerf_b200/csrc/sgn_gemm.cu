@@ -7,10 +7,14 @@
 //   conv3x3: A is an NHWC fp16 image, M = B*H*W output pixels, K = 9*Cin; the im2col is IMPLICIT: for tap (dy,dx)
 //            and channel block c0 the producer issues one 4-D TMA box {64 ch, 16 px, 8 rows, 1 image} at
 //            (c0, x0+dx-1, y0+dy-1, b); out-of-bounds rows/columns are zero-filled by TMA = the conv's zero padding.
+// Two launch shapes: single CTAs, or clusters of 2 CTAs that work on vertically adjacent M tiles of the same N tile and
+// share every weight (B) tile: each CTA loads one half of it and multicasts that half into both shared memories, so
+// the L2 -> SM traffic per CTA drops from A+B to A+B/2 (L2 bandwidth, not the tensor pipe, bounds a 128x256 tile).
 // Roles: warp 0 = TMA producer (1 lane), warp 1 = tcgen05.mma issuer (1 lane) + TMEM allocator, warps 2-5 = epilogue
 // (TMEM -> registers -> global).  4-stage smem ring (full/empty mbarriers), 2 accumulator buffers in TMEM
 // (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "sgn_common.cuh"
@@ -161,6 +165,7 @@ __device__ __forceinline__ void epilogue16(const GemmParams& p, const uint32_t* 
   }
 }
 
+template <int kCluster>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -179,7 +184,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     tc::tma_prefetch_desc(&tmB);
     for (int s = 0; s < kStages; ++s) {
       tc::mbar_init(&full[s], 1);
-      tc::mbar_init(&empty[s], 1);
+      tc::mbar_init(&empty[s], kCluster);  // every CTA of the cluster must be through with the stage
     }
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&tfull[s], 1);
@@ -190,9 +195,16 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
   tc::tc_fence_before();
   __syncthreads();
+  if (kCluster > 1) tc::cluster_sync_all();  // peer barriers initialised before any multicast / remote arrive
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int total_tiles = p.num_m_tiles * p.num_n_tiles;
+  const uint32_t cta_rank = kCluster > 1 ? tc::cluster_ctarank() : 0;
+  const uint16_t mc_mask = (uint16_t)((1u << kCluster) - 1);
+  // work unit = kCluster vertically adjacent M tiles x one N tile; M tiles past the end are computed on zero-filled
+  // rows and never stored
+  const int m_groups = (p.num_m_tiles + kCluster - 1) / kCluster;
+  const int total_tiles = m_groups * p.num_n_tiles;
+  const int first_tile = blockIdx.x / kCluster, tile_step = gridDim.x / kCluster;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
 
   if (warp == 0) {
@@ -200,8 +212,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = kStageA + (uint32_t)p.block_n * (kBK * 2);
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int m_tile = t / p.num_n_tiles, n_tile = t - m_tile * p.num_n_tiles;
+      for (int t = first_tile; t < total_tiles; t += tile_step) {
+        const int m_group = t / p.num_n_tiles, n_tile = t - m_group * p.num_n_tiles;
+        const int m_tile = m_group * kCluster + (int)cta_rank;
         int b = 0, x0 = 0, y0 = 0;
         if (p.conv) {
           b = m_tile / tiles_per_img;
@@ -220,7 +233,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           } else {
             tc::tma_load_2d(sA + stage * kStageA, &tmA, &full[stage], kb * kBK, m_tile * kBM);
           }
-          tc::tma_load_2d(sB + stage * kStageB, &tmB, &full[stage], kb * kBK, n_tile * p.block_n);
+          if (kCluster == 1) {
+            tc::tma_load_2d(sB + stage * kStageB, &tmB, &full[stage], kb * kBK, n_tile * p.block_n);
+          } else {  // my half of the weight tile, into both CTAs
+            const int half_rows = p.block_n / kCluster;
+            tc::tma_load_2d_mc(sB + stage * kStageB + cta_rank * half_rows * (kBK * 2), &tmB, &full[stage], kb * kBK,
+                               n_tile * p.block_n + (int)cta_rank * half_rows, mc_mask);
+          }
           if (++stage == kStages) stage = 0, phase ^= 1;
         }
       }
@@ -231,7 +250,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       int stage = 0;
       uint32_t phase = 0;
       int i = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+      for (int t = first_tile; t < total_tiles; t += tile_step, ++i) {
         const int buf = i & 1;
         const uint32_t ph = (i >> 1) & 1;
         tc::mbar_wait(&tempty[buf], ph ^ 1);
@@ -245,7 +264,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k)  // +32 B per K=16 step inside the 128-B swizzled row
             tc::umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-          tc::umma_commit(&empty[stage]);
+          if (kCluster == 1) tc::umma_commit(&empty[stage]);
+          else tc::umma_commit_mc(&empty[stage], mc_mask);
           if (++stage == kStages) stage = 0, phase ^= 1;
         }
         tc::umma_commit(&tfull[buf]);
@@ -255,10 +275,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int lane_base = (warp & 3) * 32;
     const int row = lane_base + lane;
     int i = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++i) {
+    for (int t = first_tile; t < total_tiles; t += tile_step, ++i) {
       const int buf = i & 1;
       const uint32_t ph = (i >> 1) & 1;
-      const int m_tile = t / p.num_n_tiles, n_tile = t - m_tile * p.num_n_tiles;
+      const int m_group = t / p.num_n_tiles, n_tile = t - m_group * p.num_n_tiles;
+      const int m_tile = m_group * kCluster + (int)cta_rank;
       long long m;
       int b;
       bool valid;
@@ -267,7 +288,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         int r = m_tile - b * tiles_per_img;
         int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
         int y = ty * kConvTileH + row / kConvTileW, x = tx * kConvTileW + row % kConvTileW;
-        valid = y < p.H && x < p.W;
+        valid = y < p.H && x < p.W && m_tile < p.num_m_tiles;
         m = ((long long)b * p.H + y) * p.W + x;
       } else {
         m = (long long)m_tile * kBM + row;
@@ -322,17 +343,39 @@ static int pick_block_n(long long m_tiles, int N) {
   return best;
 }
 
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, cudaStream_t st) {
+// Cluster of 2 (multicast weight tiles) whenever there are at least two M tiles to pair; SGN_GEMM_CLUSTER=1 forces the
+// single-CTA shape (A/B comparison, debugging).
+static int pick_cluster(const GemmParams& p) {
+  static const int forced = [] {
+    const char* e = getenv("SGN_GEMM_CLUSTER");
+    return e ? atoi(e) : 0;
+  }();
+  if (forced == 1 || forced == 2) return p.num_m_tiles >= 2 ? forced : 1;
+  return p.num_m_tiles >= 2 ? 2 : 1;
+}
+
+template <int kCluster>
+static int launch_gemm_c(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    SGN_CUDA(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+    SGN_CUDA(cudaFuncSetAttribute(k_gemm_tc<kCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
     attr_set = true;
   }
-  int total = p.num_m_tiles * p.num_n_tiles;
-  int grid = std::min(total, sm_count());
-  k_gemm_tc<<<grid, kGemmThreads, kGemmSmem, st>>>(tmA, tmB, p);
+  const int groups = (p.num_m_tiles + kCluster - 1) / kCluster * p.num_n_tiles;
+  const int grid = std::min(groups, sm_count() / kCluster) * kCluster;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kGemmThreads), cfg.dynamicSmemBytes = kGemmSmem, cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCluster, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  SGN_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tc<kCluster>, tmA, tmB, p));
   SGN_LAUNCH_CHECK();
   return SGN_OK;
+}
+
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, int cluster, cudaStream_t st) {
+  return cluster == 2 ? launch_gemm_c<2>(tmA, tmB, p, st) : launch_gemm_c<1>(tmA, tmB, p, st);
 }
 
 static int fill_epilogue(GemmParams& p, const SgnEpilogue* ep, int n_valid, void* d_out) {
@@ -382,11 +425,12 @@ extern "C" int sgn_gemm_f16(const void* d_a, int64_t lda, const void* d_w, int64
   uint32_t ba[2] = {kBK, kBM};
   rc = encode_tmap(&tmA, d_a, 2, da, sa, ba, nullptr);
   if (rc) return rc;
+  const int cluster = pick_cluster(p);
   uint64_t dw[2] = {(uint64_t)K, (uint64_t)N}, sw[1] = {(uint64_t)ldw * 2};
-  uint32_t bw[2] = {kBK, (uint32_t)p.block_n};
+  uint32_t bw[2] = {kBK, (uint32_t)(p.block_n / cluster)};
   rc = encode_tmap(&tmB, d_w, 2, dw, sw, bw, nullptr);
   if (rc) return rc;
-  return launch_gemm(tmA, tmB, p, reinterpret_cast<cudaStream_t>(stream));
+  return launch_gemm(tmA, tmB, p, cluster, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int sgn_conv3x3_f16(const void* d_x, const void* d_w, int B, int H, int W, int C, int N,
@@ -420,9 +464,10 @@ extern "C" int sgn_conv3x3_f16(const void* d_x, const void* d_w, int B, int H, i
   uint32_t ba[4] = {kBK, kConvTileW, kConvTileH, 1};
   rc = encode_tmap(&tmA, d_x, 4, da, sa, ba, nullptr);
   if (rc) return rc;
+  const int cluster = pick_cluster(p);
   uint64_t dw[2] = {(uint64_t)9 * C, (uint64_t)N}, sw[1] = {(uint64_t)9 * C * 2};
-  uint32_t bw[2] = {kBK, (uint32_t)p.block_n};
+  uint32_t bw[2] = {kBK, (uint32_t)(p.block_n / cluster)};
   rc = encode_tmap(&tmB, d_w, 2, dw, sw, bw, nullptr);
   if (rc) return rc;
-  return launch_gemm(tmA, tmB, p, reinterpret_cast<cudaStream_t>(stream));
+  return launch_gemm(tmA, tmB, p, cluster, reinterpret_cast<cudaStream_t>(stream));
 }
