@@ -125,23 +125,73 @@ def cpu_oracle_sample(rays_per_sample: int = 8192):
     return run, cores, rays_per_sample
 
 
+UNET_CPU_SHEET = 512   # the CPU sample of the diffusion half runs the full-width networks on a 512^2 sheet (latent 64^2)
+
+
+def unet_tflop(sheet: int) -> float:
+    """Algorithmic TFLOP of one UNet + ControlNet step with CFG (batch 2) on a sheet x sheet image: everything but
+    self-attention scales with the pixel count, self-attention with its square (34.7 of 103.96 TFLOP at
+    2048^2 are QK^T / PV)."""
+    r = (sheet / 2048.0) ** 2
+    return (UNET_TFLOP_PER_STEP - 34.7) * r + 34.7 * r * r
+
+
+def cpu_unet_sample():
+    """The reference's diffusion arithmetic (fp32 torch, `--no-half`) = oracle/sdxl_ref.py at full SDXL width on the host
+    cores, one CFG step incl. ControlNet on a 512^2 sheet; scaled to the 2048^2 sheet by algorithmic FLOPs."""
+    from oracle import sdxl_ref as X
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = X.UNetConfig()
+    unet, ctrl = X.make_models(cfg, fast_init=True)
+    h = UNET_CPU_SHEET // 8
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1, 4, h, h, generator=g)
+    ctx, y = torch.randn(2, 77, cfg.context_dim, generator=g), torch.randn(2, cfg.adm_in_channels, generator=g)
+    hint, noise = torch.rand(1, 3, 8 * h, 8 * h, generator=g), torch.randn(1, 4, h, h, generator=g)
+
+    def run():
+        t = time.perf_counter()
+        X.denoise_step(unet, ctrl, x, 13.0, 10.0, ctx, y, hint, noise)
+        return time.perf_counter() - t
+
+    return run, cores, unet_tflop(2048) / unet_tflop(UNET_CPU_SHEET)
+
+
+def cpu_baseline(render_runs: int, unet_runs: int, with_unet: bool = True):
+    """-> (grids/s, cores, sample description) of the CPU path on bounded samples of the benchmark workload."""
+    run, cores, n = cpu_oracle_sample()
+    run()
+    per_grid = float(np.mean([run() for _ in range(render_runs)])) / n * VIEWS * H * W
+    sample = (f"render: {n} rays x {SAMPLES} samples of view 0 through oracle/nerfacto_ref.py, scaled to 16x512^2 rays "
+              f"({per_grid:.1f} s/grid)")
+    if with_unet:
+        urun, _, scale = cpu_unet_sample()
+        t = float(np.mean([urun() for _ in range(unet_runs)]))
+        per_grid += t * scale
+        sample += (f"; diffusion: one fp32 UNet+ControlNet CFG step of oracle/sdxl_ref.py (full SDXL width) on a "
+                   f"{UNET_CPU_SHEET}^2 sheet = {t:.1f} s, scaled x{scale:.1f} by algorithmic FLOPs to the 2048^2 sheet")
+    return 1.0 / per_grid, cores, sample
+
+
 def reference_arm(args):
+    """The reference's own CPU implementation of the path = the oracle ports (nothing of the reference is installable
+    here: SURVEY §0), on all host cores, bounded samples; rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    run, cores, n = cpu_oracle_sample()
-    for _ in range(args.warmup):
-        run()
-    ts = [run() for _ in range(args.steps)]
-    per_grid = float(np.mean(ts)) / n * VIEWS * H * W          # render only: the UNet half is not in the sample
-    val = 1.0 / per_grid
-    sample = f"{n} rays x {SAMPLES} samples of view 0 (flat), oracle/nerfacto_ref.py, scaled to 16x512^2 rays; UNet step not included"
+    t0 = time.perf_counter()
+    val, cores, sample = cpu_baseline(render_runs=max(1, min(args.steps, 3)), unet_runs=max(1, min(args.steps, 2)),
+                                      with_unet=not args.no_unet)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": per_grid * 1e3, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": 1e3 / val, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C2 4x4 grid 512x512, flat 128 samples/ray (bounded CPU sample)"},
+            "config": {"workload": "C3 4x4 grid 512x512, flat 128 samples/ray + 1 SDXL+ControlNet UNet step (CFG 2) on the "
+                                   "2048^2 sheet; CPU arm measured on bounded samples and scaled (see cpu_baseline.sample)",
+                       "wall_s": None},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    line["config"]["wall_s"] = round(time.perf_counter() - t0, 1)
     print(json.dumps(line))
 
 
@@ -352,13 +402,8 @@ def main():
         else:
             line["roofline"] = render_roof
         if N == 1 and not args.no_cpu_baseline:
-            run, cores, n = cpu_oracle_sample()
-            run()
-            ts = [run() for _ in range(2)]
-            per_grid = float(np.mean(ts)) / n * VIEWS * H * W
-            line["cpu_baseline"] = {"value": 1.0 / per_grid, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{n} rays x {SAMPLES} samples of view 0 through oracle/nerfacto_ref.py, "
-                                              "scaled to 16x512^2 rays; render half only"}
+            val, cores, sample = cpu_baseline(render_runs=2, unet_runs=1, with_unet=unet is not None)
+            line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -310,7 +310,8 @@ class ControlNet(nn.Module):
         return outs
 
 
-def make_models(cfg: UNetConfig, seed: int = 0, device="cpu", fp16_weights: bool = True) -> Tuple[UNetModel, ControlNet]:
+def make_models(cfg: UNetConfig, seed: int = 0, device="cpu", fp16_weights: bool = True,
+                fast_init: bool = False) -> Tuple[UNetModel, ControlNet]:
     """Random-init denoiser.  sgm / cldm zero-initialise (`zero_module`) the ResBlock output convs, proj_out, the UNet
     output conv and every ControlNet zero conv, which would make the random-weight network trivial; like every other
     layer they keep torch's default init here so that each branch is exercised.
@@ -319,6 +320,25 @@ def make_models(cfg: UNetConfig, seed: int = 0, device="cpu", fp16_weights: bool
     names (`sd_xl_base_1.0.safetensors`, `diffusers_xl_depth_full`, diffuser.py:47-49) are stored in fp16 and A1111's
     `--no-half` only up-casts them, so the reference's fp32 arithmetic runs on fp16-representable weights."""
     torch.manual_seed(seed)
+    if fast_init:
+        # full-width models for CPU timing only: skip torch's per-parameter init (minutes for 3.8 B parameters) and tile
+        # one block of random values over every tensor, scaled like the default init (values do not affect timing)
+        with torch.device("meta"):
+            unet, ctrl = UNetModel(cfg), ControlNet(cfg)
+        block = torch.rand(1 << 20) * 2 - 1
+        for m in (unet, ctrl):
+            m.to_empty(device="cpu")
+            with torch.no_grad():
+                for name, prm in m.named_parameters():
+                    if prm.dim() == 1:
+                        prm.fill_(1.0 if name.endswith("weight") and ("norm" in name or "layers.0" in name or name.startswith("out.0")) else 0.0)
+                        continue
+                    flat = prm.view(-1)
+                    bound = 1.0 / math.sqrt(prm[0].numel())
+                    for i in range(0, flat.numel(), block.numel()):
+                        n = min(block.numel(), flat.numel() - i)
+                        torch.mul(block[:n], bound, out=flat[i:i + n])
+        return unet.eval(), ctrl.eval()
     unet, ctrl = UNetModel(cfg), ControlNet(cfg)
     if fp16_weights:
         with torch.no_grad():

@@ -65,7 +65,7 @@ int encode_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* di
 }
 
 // ------------------------------------------------------------------ kernel
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two warps per TMEM lane quarter)
 constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kStages = 4;
@@ -188,7 +188,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     }
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&tfull[s], 1);
-      tc::mbar_init(&tempty[s], 4);
+      tc::mbar_init(&tempty[s], 8);
     }
     tc::mbar_fence_init();
   }
@@ -271,9 +271,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         tc::umma_commit(&tfull[buf]);
       }
     }
-  } else {  // ---------------- epilogue warps 2..5: TMEM lane quarter = warp % 4
+  } else {  // ---------------- epilogue warps 2..9: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4
     const int lane_base = (warp & 3) * 32;
     const int row = lane_base + lane;
+    const int col_half = (warp - 2) >> 2;
     int i = 0;
     for (int t = first_tile; t < total_tiles; t += tile_step, ++i) {
       const int buf = i & 1;
@@ -299,8 +300,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       tc::tc_fence_after();
       const uint32_t taddr = tmem_base + buf * kAccStride + ((uint32_t)lane_base << 16);
       const int n_base = n_tile * p.block_n;
-      int c0 = 0;
-      for (; c0 + 32 <= p.block_n; c0 += 32) {
+      // the two warps of a lane quarter split the tile's columns in 32-wide chunks: even chunks / odd chunks
+      int c0 = col_half * 32;
+      for (; c0 + 32 <= p.block_n; c0 += 64) {
         uint32_t acc[32];
         tc::tmem_ld32(taddr + c0, acc);
         tc::tmem_ld_wait();
@@ -309,7 +311,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           epilogue16(p, acc + 16, m, b, n_base + c0 + 16);
         }
       }
-      if (c0 < p.block_n) {
+      if (c0 < p.block_n && c0 + 16 == p.block_n) {  // 16-column tail (block_n % 32 == 16) belongs to whoever reaches it
         uint32_t acc[16];
         tc::tmem_ld16(taddr + c0, acc);
         tc::tmem_ld_wait();
@@ -322,6 +324,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   }
   tc::tc_fence_before();
   __syncthreads();
+  if (kCluster > 1) tc::cluster_sync_all();  // no CTA leaves while its peer can still multicast into it / arrive on it
   if (warp == 1) {
     __syncwarp();
     tc::tmem_dealloc(tmem_base, 512);

@@ -21,17 +21,34 @@ __device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); 
 //   1. per 256-pixel chunk: (sum, sum of squares) per group          -> ws[b][chunk][g] (double2)
 //   2. per image: chunks summed in order -> mean, rstd               -> ws tail [b][g] (float2 stored in a double)
 //   3. normalise + affine (+ SiLU) -> fp16
-constexpr int kGnPix = 256;  // pixels per block
-__global__ void __launch_bounds__(256) k_gn_stats(const float* __restrict__ x, int HW, int C, int G, double2* part) {
+constexpr int kGnPix = 256;  // max pixels per block (fewer on small images so that the grid still fills the GPU)
+static inline int gn_pix_per_block(int B, int HW) {
+  long long want = ((long long)B * HW + 148 * 4 - 1) / (148 * 4);      // ~4 blocks per SM
+  int pix = (int)std::min<long long>(kGnPix, std::max<long long>(8, (want + 3) / 4 * 4));
+  return pix;
+}
+__global__ void __launch_bounds__(256) k_gn_stats(const float* __restrict__ x, int HW, int C, int G, int pix_per_block,
+                                                  double2* part) {
   extern __shared__ float2 s_part[];  // [4][C/2]
   const int b = blockIdx.y, chunks = gridDim.x;
-  const int p0 = blockIdx.x * kGnPix, p1 = min(HW, p0 + kGnPix);
+  const int p0 = blockIdx.x * pix_per_block, p1 = min(HW, p0 + pix_per_block);
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
   const int half_c = C >> 1, cpg2 = (C / G) >> 1;
   const float2* xb = reinterpret_cast<const float2*>(x + ((size_t)b * HW) * C);
   for (int cp = tx; cp < half_c; cp += 64) {
     float s = 0.f, q = 0.f;
-    for (int pix = p0 + ty; pix < p1; pix += 4) {
+    int pix = p0 + ty;
+    for (; pix + 28 < p1; pix += 32) {  // 8 independent loads in flight per thread
+      float2 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(xb + (size_t)(pix + 4 * u) * half_c + cp);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        s += v[u].x + v[u].y;
+        q = fmaf(v[u].x, v[u].x, fmaf(v[u].y, v[u].y, q));
+      }
+    }
+    for (; pix < p1; pix += 4) {
       float2 v = __ldg(xb + (size_t)pix * half_c + cp);
       s += v.x + v.y;
       q = fmaf(v.x, v.x, fmaf(v.y, v.y, q));
@@ -73,18 +90,30 @@ __global__ void __launch_bounds__(256) k_gn_apply(const float* __restrict__ x, i
     s_mean[threadIdx.x] = st.x, s_rstd[threadIdx.x] = st.y;
   }
   __syncthreads();
-  const int half_c = C >> 1, cpg = C / G;
-  const size_t n2 = (size_t)HW * half_c;
-  const float2* xb = reinterpret_cast<const float2*>(x + ((size_t)b * HW) * C);
-  __half2* ob = reinterpret_cast<__half2*>(out + ((size_t)b * HW) * C);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (size_t)gridDim.x * blockDim.x) {
-    const int cp = (int)(i % half_c), c = 2 * cp, g = c / cpg;
-    float2 v = __ldg(xb + i);
-    float a = (v.x - s_mean[g]) * s_rstd[g] * __ldg(gamma + c) + __ldg(beta + c);
-    float d = (v.y - s_mean[g]) * s_rstd[g] * __ldg(gamma + c + 1) + __ldg(beta + c + 1);
-    if (act_silu) a = silu(a), d = silu(d);
-    ob[i] = __floats2half2_rn(a, d);
+  const int c4n = C >> 2, cpg = C / G;
+  const size_t n4 = (size_t)HW * c4n;
+  const float4* xb = reinterpret_cast<const float4*>(x + ((size_t)b * HW) * C);
+  uint2* ob = reinterpret_cast<uint2*>(out + ((size_t)b * HW) * C);
+  auto norm4 = [&](size_t i, float4 v) {
+    const int c = 4 * (int)(i % c4n), g0 = c / cpg, g1 = (c + 2) / cpg;  // cpg is even: a pair never straddles groups
+    const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c)), bt = __ldg(reinterpret_cast<const float4*>(beta + c));
+    float a = (v.x - s_mean[g0]) * s_rstd[g0] * gm.x + bt.x, d = (v.y - s_mean[g0]) * s_rstd[g0] * gm.y + bt.y;
+    float e = (v.z - s_mean[g1]) * s_rstd[g1] * gm.z + bt.z, f = (v.w - s_mean[g1]) * s_rstd[g1] * gm.w + bt.w;
+    if (act_silu) a = silu(a), d = silu(d), e = silu(e), f = silu(f);
+    __half2 h0 = __floats2half2_rn(a, d), h1 = __floats2half2_rn(e, f);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&h0);
+    u.y = *reinterpret_cast<uint32_t*>(&h1);
+    ob[i] = u;
+  };
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + stride < n4; i += 2 * stride) {  // two independent 16-byte loads in flight per thread
+    float4 v0 = __ldg(xb + i), v1 = __ldg(xb + i + stride);
+    norm4(i, v0);
+    norm4(i + stride, v1);
   }
+  if (i < n4) norm4(i, __ldg(xb + i));
 }
 
 // ------------------------------------------------------------------ LayerNorm: one warp per token
@@ -124,6 +153,50 @@ __global__ void __launch_bounds__(256) k_layer_norm(const float* __restrict__ x,
       u.x = *reinterpret_cast<uint32_t*>(&h0);
       u.y = *reinterpret_cast<uint32_t*>(&h1);
       orow[i] = u;
+    }
+  }
+}
+
+// Row held in registers (C = 128 * NV): one global read, two warp reductions.
+template <int NV>
+__global__ void __launch_bounds__(256) k_layer_norm_reg(const float* __restrict__ x, long long M, float eps,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        __half* out) {
+  constexpr int C = NV * 128;
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long m = warp0; m < M; m += nwarps) {
+    const float4* xr = reinterpret_cast<const float4*>(x + m * C);
+    float4 v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = xr[lane + 32 * i];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / C + eps);
+    uint2* orow = reinterpret_cast<uint2*>(out + m * C);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int j = lane + 32 * i;
+      float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + j), bb = __ldg(reinterpret_cast<const float4*>(beta) + j);
+      __half2 h0 = __floats2half2_rn((v[i].x - mean) * rstd * g.x + bb.x, (v[i].y - mean) * rstd * g.y + bb.y);
+      __half2 h1 = __floats2half2_rn((v[i].z - mean) * rstd * g.z + bb.z, (v[i].w - mean) * rstd * g.w + bb.w);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&h0);
+      u.y = *reinterpret_cast<uint32_t*>(&h1);
+      orow[j] = u;
     }
   }
 }
@@ -232,7 +305,7 @@ struct DirectConvParams {
 __global__ void __launch_bounds__(256) k_conv3x3_direct(const DirectConvParams p) {
   extern __shared__ float smem_f[];
   const int in_t = (kDcTile - 1) * p.stride + 3;  // input tile edge: 18 (stride 1) or 33 (stride 2)
-  float* s_in = smem_f;                             // [in_t][in_t][kCiT]
+  float* s_in = smem_f;                             // [kCiT][in_t][in_t]: lanes (adjacent pixels) hit adjacent banks
   float* s_w = smem_f + in_t * in_t * kCiT;         // [9][kCiT][kCoT]
   const int tiles_x = (p.Wo + kDcTile - 1) / kDcTile;
   const int tx0 = (blockIdx.x % tiles_x) * kDcTile, ty0 = (blockIdx.x / tiles_x) * kDcTile;
@@ -261,7 +334,7 @@ __global__ void __launch_bounds__(256) k_conv3x3_direct(const DirectConvParams p
       if (c < p.Cin && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
         v = p.in_nchw ? __ldg(p.x + (((size_t)b * p.Cin + c) * p.H + iy) * p.W + ix)
                       : __ldg(p.x + (((size_t)b * p.H + iy) * p.W + ix) * p.Cin + c);
-      s_in[(py * in_t + px) * kCiT + ci] = v;
+      s_in[(ci * in_t + py) * in_t + px] = v;
     }
     for (int i = threadIdx.x; i < 9 * kCiT * kCoT; i += 256) {
       int co = i % kCoT, ci = (i / kCoT) % kCiT, tap = i / (kCoT * kCiT);
@@ -272,11 +345,11 @@ __global__ void __launch_bounds__(256) k_conv3x3_direct(const DirectConvParams p
     __syncthreads();
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
-      const float* ip = s_in + ((ly * p.stride + tap / 3) * in_t + lx * p.stride + tap % 3) * kCiT;
+      const float* ip = s_in + (ly * p.stride + tap / 3) * in_t + lx * p.stride + tap % 3;
       const float* wp = s_w + tap * kCiT * kCoT;
 #pragma unroll
       for (int ci = 0; ci < kCiT; ++ci) {
-        const float xv = ip[ci];
+        const float xv = ip[ci * in_t * in_t];
 #pragma unroll
         for (int q = 0; q < kCoT / 4; ++q) {
           float4 w4 = *reinterpret_cast<const float4*>(wp + ci * kCoT + 4 * q);
@@ -411,7 +484,8 @@ using namespace sgn;
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
 extern "C" int64_t sgn_group_norm_ws_doubles(int B, int HW, int groups) {
-  const int64_t chunks = (HW + kGnPix - 1) / kGnPix;
+  const int pix = gn_pix_per_block(B, HW);
+  const int64_t chunks = (HW + pix - 1) / pix;
   return (int64_t)B * groups * (2 * chunks + 1);
 }
 
@@ -420,18 +494,20 @@ extern "C" int sgn_group_norm_f16(const float* d_x, int B, int HW, int C, int gr
   SGN_CHECK_ARG(B >= 0 && HW > 0 && C > 0 && groups > 0, "bad shape");
   if (B == 0) return SGN_OK;
   SGN_CHECK_ARG(d_x && d_gamma && d_beta && d_ws && d_out, "null pointer");
-  SGN_CHECK_ARG(groups <= 64 && C % groups == 0 && (C / groups) % 2 == 0, "need groups <= 64 and an even number of channels per group");
+  SGN_CHECK_ARG(groups <= 64 && C % groups == 0 && (C / groups) % 2 == 0 && C % 4 == 0,
+                "need groups <= 64, an even number of channels per group and C % 4 == 0");
   SGN_CHECK_ARG(C <= 2560, "GroupNorm kernel stages 4 x C/2 partials in 40 KB of shared memory (C <= 2560)");
-  const int chunks = (HW + kGnPix - 1) / kGnPix;
+  const int pix = gn_pix_per_block(B, HW);
+  const int chunks = (HW + pix - 1) / pix;
   double2* part = reinterpret_cast<double2*>(d_ws);
   float2* stats = reinterpret_cast<float2*>(part + (size_t)B * chunks * groups);
   dim3 g1(chunks, B);
-  k_gn_stats<<<g1, 256, (size_t)4 * (C / 2) * sizeof(float2), ST(stream)>>>(d_x, HW, C, groups, part);
+  k_gn_stats<<<g1, 256, (size_t)4 * (C / 2) * sizeof(float2), ST(stream)>>>(d_x, HW, C, groups, pix, part);
   SGN_LAUNCH_CHECK();
   k_gn_finalize<<<B, 64, 0, ST(stream)>>>(part, chunks, groups, (double)HW * (C / groups), eps, stats);
   SGN_LAUNCH_CHECK();
-  size_t n2 = (size_t)HW * (C / 2);
-  dim3 g2((unsigned)std::max<size_t>(1, std::min<size_t>((n2 + 255) / 256, (size_t)sm_count() * 8 / std::max(1, B) + 1)), B);
+  size_t n4 = (size_t)HW * (C / 4);
+  dim3 g2((unsigned)std::max<size_t>(1, std::min<size_t>((n4 + 511) / 512, (size_t)sm_count() * 8 / std::max(1, B) + 1)), B);
   k_gn_apply<<<g2, 256, 0, ST(stream)>>>(d_x, HW, C, groups, eps, d_gamma, d_beta, stats, act_silu,
                                          reinterpret_cast<__half*>(d_out));
   SGN_LAUNCH_CHECK();
@@ -443,8 +519,15 @@ extern "C" int sgn_layer_norm_f16(const float* d_x, int64_t M, int C, float eps,
   SGN_CHECK_ARG(M >= 0 && C > 0 && C % 4 == 0, "C must be a multiple of 4");
   if (M == 0) return SGN_OK;
   SGN_CHECK_ARG(d_x && d_gamma && d_beta && d_out, "null pointer");
-  k_layer_norm<<<grid_1d((size_t)M * 32, 256), 256, 0, ST(stream)>>>(d_x, M, C, eps, d_gamma, d_beta,
-                                                                      reinterpret_cast<__half*>(d_out));
+  const int grid = grid_1d((size_t)M * 32, 256);
+  __half* o = reinterpret_cast<__half*>(d_out);
+  switch (C % 128 == 0 ? C / 128 : 0) {
+    case 1: k_layer_norm_reg<1><<<grid, 256, 0, ST(stream)>>>(d_x, M, eps, d_gamma, d_beta, o); break;
+    case 2: k_layer_norm_reg<2><<<grid, 256, 0, ST(stream)>>>(d_x, M, eps, d_gamma, d_beta, o); break;
+    case 5: k_layer_norm_reg<5><<<grid, 256, 0, ST(stream)>>>(d_x, M, eps, d_gamma, d_beta, o); break;
+    case 10: k_layer_norm_reg<10><<<grid, 256, 0, ST(stream)>>>(d_x, M, eps, d_gamma, d_beta, o); break;
+    default: k_layer_norm<<<grid, 256, 0, ST(stream)>>>(d_x, M, C, eps, d_gamma, d_beta, o);
+  }
   SGN_LAUNCH_CHECK();
   return SGN_OK;
 }

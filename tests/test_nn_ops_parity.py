@@ -31,7 +31,7 @@ def test_group_norm(B, H, W, C, silu, eps):
     assert rel_l2(out.view(B, H, W, C).permute(0, 3, 1, 2), ref) < 1e-3
 
 
-@pytest.mark.parametrize("M,C", [(100, 128), (4096, 640), (333, 1280)])
+@pytest.mark.parametrize("M,C", [(100, 128), (4096, 640), (333, 1280), (50, 192)])
 def test_layer_norm(M, C):
     x = _r((M, C), 1, 3.0, -0.5)
     g, b = _r((C,), 2, 0.5, 1.0), _r((C,), 3)
