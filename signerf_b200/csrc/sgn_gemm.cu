@@ -7,9 +7,11 @@
 //   conv3x3: A is an NHWC fp16 image, M = B*H*W output pixels, K = 9*Cin; the im2col is IMPLICIT: for tap (dy,dx)
 //            and channel block c0 the producer issues one 4-D TMA box {64 ch, 16 px, 8 rows, 1 image} at
 //            (c0, x0+dx-1, y0+dy-1, b); out-of-bounds rows/columns are zero-filled by TMA = the conv's zero padding.
-// Two launch shapes: single CTAs, or clusters of 2 CTAs that work on vertically adjacent M tiles of the same N tile and
-// share every weight (B) tile: each CTA loads one half of it and multicasts that half into both shared memories, so
-// the L2 -> SM traffic per CTA drops from A+B to A+B/2 (L2 bandwidth, not the tensor pipe, bounds a 128x256 tile).
+// Two launch shapes: single CTAs (128 x N tiles), or CTA PAIRS (tcgen05 cta_group::2, 256 x N tiles): the two CTAs of a
+// cluster own vertically adjacent M tiles of the same N tile, each loads its 128 rows of A and only HALF of the weight
+// (B) tile, and the leader CTA issues one 256-row MMA that reads both halves.  Per-SM ingest drops from A+B to A+B/2
+// per k-block (measured: the TMA -> shared-memory ingest rate of an SM, ~70 B/clk, bounds the single-CTA 128x256 tile
+// at ~55 % of the tensor pipe) and the stage shrinks to 32 KB, which buys 6 pipeline stages instead of 4.
 // Roles: warp 0 = TMA producer (1 lane), warp 1 = tcgen05.mma issuer (1 lane) + TMEM allocator, warps 2-5 = epilogue
 // (TMEM -> registers -> global).  4-stage smem ring (full/empty mbarriers), 2 accumulator buffers in TMEM
 // (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
@@ -68,12 +70,14 @@ int encode_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* di
 constexpr int kGemmThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two warps per TMEM lane quarter)
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kStages = 4;
 constexpr int kStageA = kBM * kBK * 2;    // 16 KB
-constexpr int kStageB = 256 * kBK * 2;    // 32 KB (block_n <= 256)
+template <int kCluster> struct GemmCfg {
+  static constexpr int kStageB = (256 / kCluster) * kBK * 2;  // 32 KB (single CTA) / 16 KB (half of B per pair CTA)
+  static constexpr int kStages = kCluster == 2 ? 6 : 4;
+};
 constexpr int kAccStride = 256;           // TMEM columns between the two accumulator buffers
 constexpr int kConvTileW = 16, kConvTileH = 8;
-constexpr size_t kGemmSmem = 1024 + (size_t)kStages * (kStageA + kStageB) + 256;
+constexpr size_t kGemmSmem = 1024 + (size_t)4 * (kStageA + 32768) + 256;  // = 6 * (16 KB + 16 KB) for the pair shape
 
 struct GemmParams {
   int M, N, K;  // N = weight rows covered by tiles (multiple of block_n); n_valid <= N columns are stored
@@ -168,6 +172,7 @@ __device__ __forceinline__ void epilogue16(const GemmParams& p, const uint32_t* 
 template <int kCluster>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  constexpr int kStages = GemmCfg<kCluster>::kStages, kStageB = GemmCfg<kCluster>::kStageB;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
@@ -183,23 +188,25 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     tc::tma_prefetch_desc(&tmA);
     tc::tma_prefetch_desc(&tmB);
     for (int s = 0; s < kStages; ++s) {
-      tc::mbar_init(&full[s], 1);
-      tc::mbar_init(&empty[s], kCluster);  // every CTA of the cluster must be through with the stage
+      tc::mbar_init(&full[s], 1);          // pair: the leader's expect_tx covers the bytes both CTAs load
+      tc::mbar_init(&empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&tfull[s], 1);
-      tc::mbar_init(&tempty[s], 8);
+      tc::mbar_init(&tempty[s], 8 * kCluster);  // pair: the epilogue warps of both CTAs release the leader's buffer
     }
     tc::mbar_fence_init();
   }
-  if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
+  if (warp == 1) {
+    if (kCluster == 2) tc::tmem_alloc_pair(tmem_slot, 512);
+    else tc::tmem_alloc(tmem_slot, 512);
+  }
   tc::tc_fence_before();
   __syncthreads();
-  if (kCluster > 1) tc::cluster_sync_all();  // peer barriers initialised before any multicast / remote arrive
+  if (kCluster > 1) tc::cluster_sync_all();  // peer barriers initialised before any remote arrive / completion
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t cta_rank = kCluster > 1 ? tc::cluster_ctarank() : 0;
-  const uint16_t mc_mask = (uint16_t)((1u << kCluster) - 1);
   // work unit = kCluster vertically adjacent M tiles x one N tile; M tiles past the end are computed on zero-filled
   // rows and never stored
   const int m_groups = (p.num_m_tiles + kCluster - 1) / kCluster;
@@ -211,7 +218,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     if (lane == 0) {  // ---------------- TMA producer
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = kStageA + (uint32_t)p.block_n * (kBK * 2);
+      const int b_rows = p.block_n / kCluster;  // weight rows this CTA loads per k-block
+      const uint32_t tx_bytes = kCluster * (kStageA + (uint32_t)b_rows * (kBK * 2));  // both CTAs complete on the leader
       for (int t = first_tile; t < total_tiles; t += tile_step) {
         const int m_group = t / p.num_n_tiles, n_tile = t - m_group * p.num_n_tiles;
         const int m_tile = m_group * kCluster + (int)cta_rank;
@@ -225,28 +233,30 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           tc::mbar_wait(&empty[stage], phase ^ 1);
-          tc::mbar_expect_tx(&full[stage], tx_bytes);
+          int tap = 0, cb = kb, dy = 0, dx = 0;
           if (p.conv) {
-            int tap = kb / p.cin_blocks, cb = kb - tap * p.cin_blocks;
-            int dy = tap / 3, dx = tap - dy * 3;
-            tc::tma_load_4d(sA + stage * kStageA, &tmA, &full[stage], cb * kBK, x0 + dx - 1, y0 + dy - 1, b);
-          } else {
-            tc::tma_load_2d(sA + stage * kStageA, &tmA, &full[stage], kb * kBK, m_tile * kBM);
+            tap = kb / p.cin_blocks, cb = kb - tap * p.cin_blocks;
+            dy = tap / 3, dx = tap - dy * 3;
           }
           if (kCluster == 1) {
+            tc::mbar_expect_tx(&full[stage], tx_bytes);
+            if (p.conv) tc::tma_load_4d(sA + stage * kStageA, &tmA, &full[stage], cb * kBK, x0 + dx - 1, y0 + dy - 1, b);
+            else tc::tma_load_2d(sA + stage * kStageA, &tmA, &full[stage], kb * kBK, m_tile * kBM);
             tc::tma_load_2d(sB + stage * kStageB, &tmB, &full[stage], kb * kBK, n_tile * p.block_n);
-          } else {  // my half of the weight tile, into both CTAs
-            const int half_rows = p.block_n / kCluster;
-            tc::tma_load_2d_mc(sB + stage * kStageB + cta_rank * half_rows * (kBK * 2), &tmB, &full[stage], kb * kBK,
-                               n_tile * p.block_n + (int)cta_rank * half_rows, mc_mask);
+          } else {
+            const uint32_t lead_full = tc::mapa_u32(&full[stage], 0);
+            if (cta_rank == 0) tc::mbar_expect_tx(&full[stage], tx_bytes);
+            if (p.conv) tc::tma_load_4d_pair(sA + stage * kStageA, &tmA, lead_full, cb * kBK, x0 + dx - 1, y0 + dy - 1, b);
+            else tc::tma_load_2d_pair(sA + stage * kStageA, &tmA, lead_full, kb * kBK, m_tile * kBM);
+            tc::tma_load_2d_pair(sB + stage * kStageB, &tmB, lead_full, kb * kBK, n_tile * p.block_n + (int)cta_rank * b_rows);
           }
           if (++stage == kStages) stage = 0, phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ---------------- MMA issuer
-      const uint32_t idesc = tc::umma_idesc_f16(kBM, p.block_n, false, false);
+    if (lane == 0 && cta_rank == 0) {  // ---------------- MMA issuer (pair: the leader issues for both SMs)
+      const uint32_t idesc = tc::umma_idesc_f16(kBM * kCluster, p.block_n, false, false);
       int stage = 0;
       uint32_t phase = 0;
       int i = 0;
@@ -262,13 +272,16 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           const uint64_t da = tc::umma_desc_sw128(tc::smem_u32(sA + stage * kStageA));
           const uint64_t db = tc::umma_desc_sw128(tc::smem_u32(sB + stage * kStageB));
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k)  // +32 B per K=16 step inside the 128-B swizzled row
-            tc::umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          for (int k = 0; k < kBK / 16; ++k) {  // +32 B per K=16 step inside the 128-B swizzled row
+            if (kCluster == 1) tc::umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            else tc::umma_f16_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          }
           if (kCluster == 1) tc::umma_commit(&empty[stage]);
-          else tc::umma_commit_mc(&empty[stage], mc_mask);
+          else tc::umma_commit_pair(&empty[stage]);
           if (++stage == kStages) stage = 0, phase ^= 1;
         }
-        tc::umma_commit(&tfull[buf]);
+        if (kCluster == 1) tc::umma_commit(&tfull[buf]);
+        else tc::umma_commit_pair(&tfull[buf]);
       }
     }
   } else {  // ---------------- epilogue warps 2..9: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4
@@ -319,7 +332,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       }
       tc::tc_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&tempty[buf]);
+      if (lane == 0) {
+        if (kCluster == 1) tc::mbar_arrive(&tempty[buf]);
+        else tc::mbar_arrive_cluster(tc::mapa_u32(&tempty[buf], 0));
+      }
     }
   }
   tc::tc_fence_before();
@@ -327,7 +343,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   if (kCluster > 1) tc::cluster_sync_all();  // no CTA leaves while its peer can still multicast into it / arrive on it
   if (warp == 1) {
     __syncwarp();
-    tc::tmem_dealloc(tmem_base, 512);
+    if (kCluster == 2) tc::tmem_dealloc_pair(tmem_base, 512);
+    else tc::tmem_dealloc(tmem_base, 512);
   }
 }
 
