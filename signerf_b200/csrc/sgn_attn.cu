@@ -30,6 +30,7 @@ constexpr int kHeadDim = 64;
 constexpr int kQTile = 128, kKvTile = 128;
 constexpr int kQPerCta = 2 * kQTile;
 constexpr int kKvStages = 4;
+constexpr int kPolyEvery = 4;  // every 4th exponential on the FMA pipe (0 = all on MUFU)
 constexpr int kTileBytes = 128 * 64 * 2;  // one [128 x 64] fp16 tile, 128-B rows, SWIZZLE_128B
 constexpr size_t kAttnSmem = 1024 + kTileBytes * (2 + 2 * kKvStages) + 256;
 
@@ -46,6 +47,19 @@ __device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sy
 __device__ __forceinline__ void named_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// exp2 on the FMA / ALU pipes (Cody-Waite + degree-4 polynomial, rel. error < 5e-5, far below the fp16 rounding of P):
+// a quarter of the row goes this way so that the MUFU pipe (16 ex2/clk/SM) stops being the binding unit.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -120.f);
+  const float t = x + 12582912.f;            // 1.5 * 2^23: the low mantissa bits of t hold round(x)
+  const float f = x - (t - 12582912.f);      // f in [-0.5, 0.5]
+  float p = fmaf(f, 0.0096181291f, 0.0555041087f);
+  p = fmaf(p, f, 0.2402265070f);
+  p = fmaf(p, f, 0.6931471806f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));   // * 2^round(x)
 }
 
 __device__ __forceinline__ float ex2(float x) {
@@ -230,7 +244,10 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         for (int g = 0; g < 8; ++g) {
           float e[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) e[q] = ex2(fmaf(__uint_as_float(s[c * 64 + g * 8 + q]), sc, neg_m));
+          for (int q = 0; q < 8; ++q) {
+            const float t = fmaf(__uint_as_float(s[c * 64 + g * 8 + q]), sc, neg_m);
+            e[q] = (kPolyEvery > 0 && (q % kPolyEvery) == kPolyEvery - 1) ? ex2_poly(t) : ex2(t);
+          }
           psum0 += (e[0] + e[1]) + (e[2] + e[3]);
           psum1 += (e[4] + e[5]) + (e[6] + e[7]);
 #pragma unroll

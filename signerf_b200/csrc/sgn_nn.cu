@@ -67,16 +67,25 @@ __global__ void __launch_bounds__(256) k_gn_stats(const float* __restrict__ x, i
   }
 }
 
-__global__ void k_gn_finalize(const double2* __restrict__ part, int chunks, int G, double n, float eps, float2* stats) {
-  const int b = blockIdx.x, g = threadIdx.x;
-  if (g >= G) return;
+// 8 threads per group, each sums every 8th chunk; combined in a fixed shuffle order (deterministic)
+__global__ void __launch_bounds__(512) k_gn_finalize(const double2* __restrict__ part, int chunks, int G, double n, float eps,
+                                                     float2* stats) {
+  const int b = blockIdx.x, g = threadIdx.x >> 3, sub = threadIdx.x & 7;
   double s = 0.0, q = 0.0;
-  for (int c = 0; c < chunks; ++c) {
-    double2 v = part[((size_t)b * chunks + c) * G + g];
-    s += v.x, q += v.y;
+  if (g < G)
+    for (int c = sub; c < chunks; c += 8) {
+      double2 v = part[((size_t)b * chunks + c) * G + g];
+      s += v.x, q += v.y;
+    }
+#pragma unroll
+  for (int o = 4; o; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
   }
-  const double mean = s / n, var = q / n - mean * mean;
-  stats[b * G + g] = make_float2((float)mean, (float)(1.0 / sqrt(fmax(var, 0.0) + (double)eps)));
+  if (g < G && sub == 0) {
+    const double mean = s / n, var = q / n - mean * mean;
+    stats[b * G + g] = make_float2((float)mean, (float)(1.0 / sqrt(fmax(var, 0.0) + (double)eps)));
+  }
 }
 
 // Pass 2: y = (x - mean) * rstd * gamma + beta, optional SiLU, fp16 out.
@@ -504,7 +513,7 @@ extern "C" int sgn_group_norm_f16(const float* d_x, int B, int HW, int C, int gr
   dim3 g1(chunks, B);
   k_gn_stats<<<g1, 256, (size_t)4 * (C / 2) * sizeof(float2), ST(stream)>>>(d_x, HW, C, groups, pix, part);
   SGN_LAUNCH_CHECK();
-  k_gn_finalize<<<B, 64, 0, ST(stream)>>>(part, chunks, groups, (double)HW * (C / groups), eps, stats);
+  k_gn_finalize<<<B, 512, 0, ST(stream)>>>(part, chunks, groups, (double)HW * (C / groups), eps, stats);
   SGN_LAUNCH_CHECK();
   size_t n4 = (size_t)HW * (C / 4);
   dim3 g2((unsigned)std::max<size_t>(1, std::min<size_t>((n4 + 511) / 512, (size_t)sm_count() * 8 / std::max(1, B) + 1)), B);
