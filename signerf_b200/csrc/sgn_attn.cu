@@ -30,7 +30,7 @@ constexpr int kHeadDim = 64;
 constexpr int kQTile = 128, kKvTile = 128;
 constexpr int kQPerCta = 2 * kQTile;
 constexpr int kKvStages = 4;
-constexpr int kPolyEvery = 4;  // every 4th exponential on the FMA pipe (0 = all on MUFU)
+constexpr int kPolyEvery = 0;  // N > 0: every Nth exponential on the FMA pipe (measured slower on B200: issue-bound)
 constexpr int kTileBytes = 128 * 64 * 2;  // one [128 x 64] fp16 tile, 128-B rows, SWIZZLE_128B
 constexpr size_t kAttnSmem = 1024 + kTileBytes * (2 + 2 * kKvStages) + 256;
 

@@ -348,17 +348,26 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   }
 }
 
-// block_n: a divisor of N (multiple of 16, <= 256) minimising waves x per-tile cost.
+// block_n (multiple of 16, <= 256; the last N tile may be ragged: TMA zero-fills the missing weight rows and the
+// epilogue skips their columns).  Cost model fitted on B200: a k-block costs max(tensor time 2*bn cycles, load time
+// (16 KB + 64 B * bn) / 58 B/clk) -- the load side is latency x in-flight-bytes bound (192 KB of stages per SM against
+// ~1.7 us of loaded L2 latency), so wide tiles win even when they leave a partially filled last wave.
 static int pick_block_n(long long m_tiles, int N) {
-  int best = 0;
+  if (const char* e = getenv("SGN_GEMM_BN")) {  // tuning / debugging override
+    int bn = atoi(e);
+    if (bn >= 16 && bn <= 256 && bn % 16 == 0) return std::min(bn, (N + 15) / 16 * 16);
+  }
+  const int n16 = (N + 15) / 16 * 16;
+  const long long units = std::max(1, sm_count() / 2);        // CTA pairs
+  const long long m_groups = (m_tiles + 1) / 2;
+  int best = 16;
   double best_cost = 1e30;
-  const int sms = sm_count();
-  for (int bn = 256; bn >= 16; bn -= 16) {
-    if (N % bn) continue;
-    long long tiles = m_tiles * (N / bn);
-    long long waves = (tiles + sms - 1) / sms;
-    double cost = (double)waves * (bn + 48.0);  // ~48 columns' worth of fixed per-tile overhead
-    if (cost < best_cost) best_cost = cost, best = bn;
+  for (int bn = std::min(256, n16); bn >= 16; bn -= 16) {
+    long long tiles = m_groups * ((n16 + bn - 1) / bn);
+    long long rounds = (tiles + units - 1) / units;
+    double t = std::max(2.0 * bn, 282.0 + 1.1 * bn);
+    double cost = (double)rounds * (t + 40.0);                 // + per-tile epilogue hand-over
+    if (cost < best_cost - 1e-9) best_cost = cost, best = bn;
   }
   return best;
 }
@@ -435,7 +444,7 @@ extern "C" int sgn_gemm_f16(const void* d_a, int64_t lda, const void* d_w, int64
   p.N = n_rows;
   p.num_m_tiles = (M + kBM - 1) / kBM;
   p.block_n = pick_block_n(p.num_m_tiles, n_rows);
-  p.num_n_tiles = n_rows / p.block_n;
+  p.num_n_tiles = (n_rows + p.block_n - 1) / p.block_n;
   p.num_k_blocks = (K + kBK - 1) / kBK;
   p.conv = 0, p.tiles_x = p.tiles_y = 1;
   int rc = fill_epilogue(p, ep, N, d_out);
@@ -470,7 +479,7 @@ extern "C" int sgn_conv3x3_f16(const void* d_x, const void* d_w, int B, int H, i
   p.tiles_y = (H + kConvTileH - 1) / kConvTileH;
   p.num_m_tiles = B * p.tiles_x * p.tiles_y;
   p.block_n = pick_block_n(p.num_m_tiles, n_rows);
-  p.num_n_tiles = n_rows / p.block_n;
+  p.num_n_tiles = (n_rows + p.block_n - 1) / p.block_n;
   p.num_k_blocks = 9 * p.cin_blocks;
   int rc = fill_epilogue(p, ep, N, d_out);
   if (rc) return rc;

@@ -17,7 +17,8 @@ def _rand(shape, seed, scale=1.0):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 320, 320), (1000, 1920, 640), (77 * 2, 2560, 2048),
-                                   (4096, 640, 2560), (129, 16, 72), (2, 1280, 320)])
+                                   (4096, 640, 2560), (129, 16, 72), (2, 1280, 320), (512, 640, 128), (2048, 1280, 256),
+                                   (8192, 640, 64), (300, 1008, 64)])
 def test_gemm_matches_fp32_reference(M, N, K):
     a = _rand((M, K), 1).half().cuda()
     w = _rand((N, K), 2, K ** -0.5).half().cuda()
