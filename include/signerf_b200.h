@@ -185,6 +185,7 @@ typedef struct SgnEpilogue {
   int geglu;               /* 1: weight rows interleaved (value_j, gate_j): out[m][j] = value * gelu(gate), fp16 [M, N/2]
                               (sgm GEGLU: `x, gate = proj(x).chunk(2); x * F.gelu(gate)`) */
   int nchw;                /* conv only: store fp32 NCHW [B, N, H, W] (the UNet's 4-channel output conv) */
+  int act_silu;            /* 1: y = silu(y) before the store (ControlNet input_hint_block) */
 } SgnEpilogue;
 
 /* nn.Linear / 1x1 conv on tcgen05: out[M,N] = A[M,K] . W[N,K]^T (+ epilogue).  A, W fp16 row-major with row strides
@@ -251,6 +252,14 @@ int sgn_scale_repeat_f32(const float* d_x, int64_t n, float scale, int repeats, 
  * (tensor_to_image truncation, preprocessor "none"); d_lat_mask [Hs/8,Ws/8] = 1 - round(8x8 box mean of the mask). */
 int sgn_sheet_to_conditioning(const float* d_cond, const float* d_mask, int Hs, int Ws, float* d_hint,
                               float* d_lat_mask, void* stream);
+
+/* im2col of a 3x3 / pad 1 / stride 1|2 conv with the fp32 input split into two fp16 halves (x = hi + lo exactly to
+ * 2^-22): d_out fp16 [B*Ho*Wo, 2*Kp], Kp = round_up(9*C, 8), row = [hi(k) for k < Kp | lo(k) for k < Kp],
+ * k = (ky*3+kx)*C + c.  A GEMM against [W | W] then reproduces the fp32 convolution to fp32 rounding on the tensor
+ * cores (weights fp16-representable).  Used for the small-channel convs of ControlNet's input_hint_block.
+ * d_x fp32 NCHW (in_nchw) or NHWC. */
+int sgn_im2col3x3_split_f16(const float* d_x, int in_nchw, int B, int H, int W, int C, int stride, void* d_out,
+                            void* stream);
 
 #ifdef __cplusplus
 }

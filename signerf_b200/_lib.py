@@ -59,7 +59,7 @@ class SgnMaskOpts(C.Structure):
 class SgnEpilogue(C.Structure):
     _fields_ = [("d_bias", C.c_void_p), ("d_rowbias", C.c_void_p), ("rows_per_batch", C.c_int),
                 ("d_residual", C.c_void_p), ("ldo", C.c_int64), ("out_f16", C.c_int), ("geglu", C.c_int),
-                ("nchw", C.c_int)]
+                ("nchw", C.c_int), ("act_silu", C.c_int)]
 
 
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
@@ -93,6 +93,7 @@ SIGNATURES = {
     "sgn_concat_f32": (_i, [_vp, _i, _vp, _vp, _f, _i, _i64, _vp, _vp]),
     "sgn_axpy_f32": (_i, [_vp, _f, _i64, _vp, _vp]),
     "sgn_im2col3x3_s2_f16": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "sgn_im2col3x3_split_f16": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "sgn_conv3x3_direct": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "sgn_linear_small": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "sgn_timestep_embedding": (_i, [_vp, _i, _i, _vp, _vp]),

@@ -90,7 +90,7 @@ struct GemmParams {
   const float* residual;
   void* out;
   long long ldo;
-  int out_f16, geglu, nchw;
+  int out_f16, geglu, nchw, act_silu;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
@@ -134,6 +134,10 @@ __device__ __forceinline__ void epilogue16(const GemmParams& p, const uint32_t* 
         v[4 * q] += t.x, v[4 * q + 1] += t.y, v[4 * q + 2] += t.z, v[4 * q + 3] += t.w;
       }
     }
+    if (p.act_silu) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = v[j] / (1.f + __expf(-v[j]));
+    }
     if (p.out_f16) {
       __half2 h[8];
 #pragma unroll
@@ -163,6 +167,7 @@ __device__ __forceinline__ void epilogue16(const GemmParams& p, const uint32_t* 
       reinterpret_cast<float*>(p.out)[o] = x;
     } else {
       if (p.residual) x += p.residual[m * p.ldo + n];
+      if (p.act_silu) x = x / (1.f + __expf(-x));
       if (p.out_f16) reinterpret_cast<__half*>(p.out)[m * p.ldo + n] = __float2half_rn(x);
       else reinterpret_cast<float*>(p.out)[m * p.ldo + n] = x;
     }
@@ -415,12 +420,14 @@ static int fill_epilogue(GemmParams& p, const SgnEpilogue* ep, int n_valid, void
   p.out_f16 = ep ? ep->out_f16 : 0;
   p.geglu = ep ? ep->geglu : 0;
   p.nchw = ep ? ep->nchw : 0;
+  p.act_silu = ep ? ep->act_silu : 0;
   p.out = d_out;
   long long ld = ep ? ep->ldo : 0;
   p.ldo = ld > 0 ? ld : (p.geglu ? n_valid / 2 : n_valid);
   SGN_CHECK_ARG(!p.rowbias || p.rows_per_batch > 0, "rowbias needs rows_per_batch");
   SGN_CHECK_ARG(!p.geglu || (n_valid % 16 == 0 && !p.residual && !p.nchw), "geglu needs N % 16 == 0 and no residual");
   SGN_CHECK_ARG(!p.nchw || !p.out_f16, "nchw output is fp32 only");
+  SGN_CHECK_ARG(!p.act_silu || (!p.geglu && !p.nchw), "act_silu does not combine with geglu / nchw");
   SGN_CHECK_ARG((reinterpret_cast<uintptr_t>(d_out) & 15) == 0, "output must be 16-byte aligned");
   SGN_CHECK_ARG(p.nchw || n_valid % 16 != 0 || (p.ldo % (p.out_f16 || p.geglu ? 8 : 4)) == 0, "ldo breaks 16-byte rows");
   return SGN_OK;

@@ -296,6 +296,39 @@ __global__ void k_im2col_s2(const float* __restrict__ x, int B, int H, int W, in
   }
 }
 
+// im2col of a 3x3 / pad 1 conv with hi/lo fp16 split of the fp32 input: out [M, 2*Kp]; one thread per (pixel, 8 k's)
+// -> two 16-byte stores
+__global__ void k_im2col_split(const float* __restrict__ x, int in_nchw, int B, int H, int W, int C, int stride, int Ho,
+                               int Wo, int Kp, __half* out) {
+  const int k8n = Kp >> 3;
+  const size_t n = (size_t)B * Ho * Wo * k8n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int k0 = (int)(i % k8n) * 8;
+    size_t r = i / k8n;
+    const int ox = (int)(r % Wo);
+    r /= Wo;
+    const int oy = (int)(r % Ho), b = (int)(r / Ho);
+    __half hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = k0 + j;
+      float v = 0.f;
+      if (k < 9 * C) {
+        const int tap = k / C, c = k - tap * C;
+        const int iy = stride * oy + tap / 3 - 1, ix = stride * ox + tap % 3 - 1;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+          v = in_nchw ? __ldg(x + (((size_t)b * C + c) * H + iy) * W + ix)
+                      : __ldg(x + (((size_t)b * H + iy) * W + ix) * C + c);
+      }
+      hi[j] = __float2half_rn(v);
+      lo[j] = __float2half_rn(v - __half2float(hi[j]));
+    }
+    __half* row = out + (i / k8n) * (size_t)(2 * Kp);
+    *reinterpret_cast<uint4*>(row + k0) = *reinterpret_cast<uint4*>(hi);
+    *reinterpret_cast<uint4*>(row + Kp + k0) = *reinterpret_cast<uint4*>(lo);
+  }
+}
+
 // ------------------------------------------------------------------ direct 3x3 conv for small channel counts (fp32)
 // 16x16 output pixels per block, kCoT output channels per block (grid.z), input channels staged through shared
 // memory in chunks of kCiT.  w [Cout, 3, 3, Cin] fp32.
@@ -658,6 +691,19 @@ extern "C" int sgn_sheet_to_conditioning(const float* d_cond, const float* d_mas
   SGN_CHECK_ARG(Hs > 0 && Ws > 0 && Hs % 8 == 0 && Ws % 8 == 0, "sheet size must be a multiple of 8");
   SGN_CHECK_ARG(d_cond && d_mask && d_hint && d_lat_mask, "null pointer");
   k_hint_latmask<<<grid_1d((size_t)Hs * Ws, 256), 256, 0, ST(stream)>>>(d_cond, d_mask, Hs, Ws, d_hint, d_lat_mask);
+  SGN_LAUNCH_CHECK();
+  return SGN_OK;
+}
+
+extern "C" int sgn_im2col3x3_split_f16(const float* d_x, int in_nchw, int B, int H, int W, int C, int stride, void* d_out,
+                                       void* stream) {
+  SGN_CHECK_ARG(B >= 0 && H > 0 && W > 0 && C > 0 && (stride == 1 || stride == 2), "bad shape");
+  if (B == 0) return SGN_OK;
+  SGN_CHECK_ARG(d_x && d_out, "null pointer");
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1, Kp = (9 * C + 7) / 8 * 8;
+  const size_t n = (size_t)B * Ho * Wo * (Kp / 8);
+  k_im2col_split<<<grid_1d(n, 256, 16), 256, 0, ST(stream)>>>(d_x, in_nchw, B, H, W, C, stride, Ho, Wo, Kp,
+                                                              reinterpret_cast<__half*>(d_out));
   SGN_LAUNCH_CHECK();
   return SGN_OK;
 }

@@ -65,7 +65,7 @@ def _chk(t: Optional[Tensor], dtype: torch.dtype, name: str) -> None:
         raise ValueError(f"{name} must be contiguous")
 
 
-def _epilogue(bias, rowbias, rows_per_batch, residual, out_f16, geglu, nchw, ldo=0) -> _lib.SgnEpilogue:
+def _epilogue(bias, rowbias, rows_per_batch, residual, out_f16, geglu, nchw, ldo=0, act_silu=False) -> _lib.SgnEpilogue:
     _chk(bias, torch.float32, "bias")
     _chk(rowbias, torch.float32, "rowbias")
     _chk(residual, torch.float32, "residual")
@@ -75,13 +75,13 @@ def _epilogue(bias, rowbias, rows_per_batch, residual, out_f16, geglu, nchw, ldo
     e.rows_per_batch = int(rows_per_batch)
     e.d_residual = None if residual is None else residual.data_ptr()
     e.ldo = int(ldo)
-    e.out_f16, e.geglu, e.nchw = int(out_f16), int(geglu), int(nchw)
+    e.out_f16, e.geglu, e.nchw, e.act_silu = int(out_f16), int(geglu), int(nchw), int(act_silu)
     return e
 
 
 def gemm_f16(a: Tensor, w: Tensor, bias: Optional[Tensor] = None, *, rowbias: Optional[Tensor] = None,
              rows_per_batch: int = 0, residual: Optional[Tensor] = None, out_f16: bool = False, geglu: bool = False,
-             out: Optional[Tensor] = None) -> Tensor:
+             act_silu: bool = False, out: Optional[Tensor] = None) -> Tensor:
     """out[M,N] = a[M,K] @ w[N,K]^T + bias (+ rowbias[m // rows_per_batch]) (+ residual); geglu: [M, N/2] fp16."""
     _chk(a, torch.float16, "a")
     _chk(w, torch.float16, "w")
@@ -95,7 +95,7 @@ def gemm_f16(a: Tensor, w: Tensor, bias: Optional[Tensor] = None, *, rowbias: Op
         out = torch.empty(oshape, dtype=odt, device=a.device)
     elif out.dtype != odt or tuple(out.shape) != oshape or not out.is_contiguous():
         raise ValueError("bad `out` tensor")
-    e = _epilogue(bias, rowbias, rows_per_batch, residual, out_f16, geglu, False)
+    e = _epilogue(bias, rowbias, rows_per_batch, residual, out_f16, geglu, False, act_silu=act_silu)
     with torch.cuda.device(a.device), _span("k_gemm_tc (linear)", 2.0 * M * N * K):
         _lib.check(_lib.load().sgn_gemm_f16(_ptr(a), K, _ptr(w), K, M, N, K, C.byref(e), _ptr(out), _stream(a.device)))
     return out
@@ -277,3 +277,16 @@ def cfg_euler_step(x: Tensor, eps: Tensor, init: Optional[Tensor], mask: Optiona
     _call(x.device, _lib.load().sgn_cfg_euler_step, _ptr(x), _ptr(eps), _ptr(init), _ptr(mask), _ptr(noise), B, Cc, H, W,
           float(cfg_scale), float(sigma), float(sigma_down), float(sigma_up), _ptr(x_out), _ptr(den))
     return x_out, den
+
+
+def im2col3x3_split_f16(x: Tensor, in_nchw: bool, stride: int = 1):
+    """fp32 image (NCHW or NHWC) -> (fp16 [B*Ho*Wo, 2*Kp] = [hi | lo] patches, Ho, Wo, Kp) for a 3x3 / pad 1 conv."""
+    _chk(x, torch.float32, "x")
+    if in_nchw:
+        B, Cc, H, W = x.shape
+    else:
+        B, H, W, Cc = x.shape
+    Ho, Wo, Kp = (H - 1) // stride + 1, (W - 1) // stride + 1, (9 * Cc + 7) // 8 * 8
+    out = torch.empty((B * Ho * Wo, 2 * Kp), dtype=torch.float16, device=x.device)
+    _call(x.device, _lib.load().sgn_im2col3x3_split_f16, _ptr(x), int(in_nchw), B, H, W, Cc, stride, _ptr(out))
+    return out, Ho, Wo, Kp

@@ -234,6 +234,18 @@ class _Packed:
             self.t[key] = x.permute(0, 2, 3, 1).reshape(x.shape[0], -1).half().contiguous()
         return self.t[key]
 
+    def conv_split16(self, name: str) -> Tensor:
+        """[Co,Ci,3,3] -> fp16 [Co, 2*Kp] = [W | W], Kp = round_up(9*Ci, 8): weight of the hi/lo-split im2col GEMM."""
+        key = name + "#s16"
+        if key not in self.t:
+            x = self._get(name)
+            w = x.permute(0, 2, 3, 1).reshape(x.shape[0], -1)
+            kp = (w.shape[1] + 7) // 8 * 8
+            wp = torch.zeros((w.shape[0], kp), dtype=torch.float32, device=w.device)
+            wp[:, :w.shape[1]] = w
+            self.t[key] = torch.cat([wp, wp], 1).half().contiguous()
+        return self.t[key]
+
     def conv32(self, name: str) -> Tensor:
         """[Co,Ci,3,3] -> fp32 [Co,3,3,Ci] for the direct conv."""
         key = name + "#c32"
@@ -304,7 +316,11 @@ class _Net:
             if n.startswith(("time_embed", "label_emb")) or ".emb_layers." in n:
                 p.f32(n)
             elif "input_hint_block" in n:
-                (p.conv16 if shp[1] % 64 == 0 else p.conv32)(n)
+                if shp[1] % 64 == 0:
+                    p.conv16(n)
+                else:   # both fp32-exact routes stay available (hint_embedding picks per layer)
+                    p.conv_split16(n)
+                    p.conv32(n)
             elif len(shp) == 4 and shp[2] == 3:
                 (p.conv16 if shp[1] % 64 == 0 else p.conv32)(n)
             elif len(shp) == 4:
@@ -477,12 +493,21 @@ class ControlNetB200(_Net):
         p = self.p
         hint = _f32(hint, "hint")
         Bh, _, H, W = hint.shape
-        x, nchw = hint, True
+        # Two fp32-exact routes per layer, picked by measured cost on B200 (scratch/bench_hint.py): the direct CUDA-core
+        # conv for the wide, shallow layers (3->16, 16->16 @2048^2, 32->32 @1024^2: their im2col would be 1-2.4 GB), and
+        # the tensor cores for stride-2 / >= 64-channel layers: im2col with the fp32 activation split into fp16 hi + lo
+        # against [W | W] reproduces the fp32 conv to fp32 rounding.
+        x, nchw, cin = hint, True, self.cfg.hint_channels
         for j, (cout, stride) in enumerate(HINT_STACK):
             last = j == len(HINT_STACK) - 1
-            x = K.conv3x3_direct(x, nchw, p.conv32(f"input_hint_block.{2 * j}.weight"), p.f32(f"input_hint_block.{2 * j}.bias"),
-                                 stride=stride, act_silu=True, out_f16=last)
-            nchw = False
+            wn, bn = f"input_hint_block.{2 * j}.weight", f"input_hint_block.{2 * j}.bias"
+            if stride == 2 or cin >= 64:
+                col, ho, wo, _ = K.im2col3x3_split_f16(x, nchw, stride)
+                y = K.gemm_f16(col, p.conv_split16(wn), p.f32(bn), act_silu=True, out_f16=last)
+                x = y.view(Bh, ho, wo, cout)
+            else:
+                x = K.conv3x3_direct(x, nchw, p.conv32(wn), p.f32(bn), stride=stride, act_silu=True, out_f16=last)
+            nchw, cin = False, cout
         j = len(HINT_STACK)
         return K.conv3x3_f16(x, p.conv16(f"input_hint_block.{2 * j}.weight"), p.f32(f"input_hint_block.{2 * j}.bias"))
 

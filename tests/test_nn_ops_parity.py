@@ -121,3 +121,21 @@ def test_sheet_to_conditioning():
     assert torch.equal(hint[0], q.expand(3, Hs, Ws))
     ref = 1 - torch.round(F.avg_pool2d(mask[..., 0][None, None], 8))
     assert torch.equal(lat, ref)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,stride,nchw", [(1, 64, 48, 3, 16, 1, True), (1, 33, 31, 16, 32, 2, False),
+                                                        (2, 16, 16, 96, 256, 2, False), (1, 20, 20, 32, 32, 1, False)])
+def test_small_channel_conv_on_tensor_cores_is_fp32_exact(B, H, W, Cin, Cout, stride, nchw):
+    """hi/lo split im2col + [W | W] GEMM + SiLU epilogue == fp32 conv (weights fp16-representable)."""
+    x = _r((B, Cin, H, W), 1)
+    w = _r((Cout, Cin, 3, 3), 2, (9 * Cin) ** -0.5).half().float()
+    bias = _r((Cout,), 3)
+    ref = F.silu(F.conv2d(x, w, bias, stride=stride, padding=1))
+    xin = x if nchw else x.permute(0, 2, 3, 1).contiguous()
+    col, ho, wo, kp = K.im2col3x3_split_f16(xin, nchw, stride)
+    wk = w.permute(0, 2, 3, 1).reshape(Cout, -1)
+    wp = torch.zeros(Cout, kp, device="cuda")
+    wp[:, :wk.shape[1]] = wk
+    out = K.gemm_f16(col, torch.cat([wp, wp], 1).half().contiguous(), bias, act_silu=True)
+    assert (ho, wo) == tuple(ref.shape[2:])
+    assert rel_l2(out.view(B, ho, wo, Cout).permute(0, 3, 1, 2), ref) < 2e-6
