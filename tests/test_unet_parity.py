@@ -153,3 +153,44 @@ def test_cuda_graph_replay_is_bit_identical(nets):
     g.replay()
     torch.cuda.synchronize()
     assert torch.equal(out, eager)
+
+
+@pytest.mark.parametrize("level,hw", [(2, 32), (1, 32)])
+def test_full_width_blocks_match_oracle(level, hw):
+    """SDXL-base widths (1280 ch / 20 heads / 10-deep transformer at level 2, 640 ch / 10 heads at level 1, context 2048,
+    decoder ResBlock on the 2560- / 1920-channel concat) on the oracle's inputs: exercises the tile shapes, CTA-pair
+    GEMMs, ragged N tiles and 77-token cross-attention the benchmark uses, at a spatial size the oracle handles."""
+    cfg = R.UNetConfig()
+    ucfg = U.UNetConfig()
+    torch.manual_seed(5)
+    mc, ted = cfg.model_channels, 4 * cfg.model_channels
+    ch = mc * cfg.channel_mult[level]
+    cin = ch + (ch if level == 2 else 2 * ch)            # decoder concat: 2560 at level 2, 1920 at level 1
+    depth = 2                                            # two of the 10 / 2 blocks: same kernels, less oracle time
+    ref_rb = R.ResBlock(cin, ted, ch).cuda().eval()
+    ref_st = R.SpatialTransformer(ch, ch // 64, 64, depth, cfg.context_dim).cuda().eval()
+    with torch.no_grad():
+        for m in (ref_rb, ref_st):
+            for prm in m.parameters():
+                prm.copy_(prm.half().float())
+    # a one-block "network": reuse the engine's block walkers with a hand-made weight dict
+    sd = {f"output_blocks.0.0.{k}": v for k, v in ref_rb.state_dict().items()}
+    sd.update({f"output_blocks.0.1.{k}": v for k, v in ref_st.state_dict().items()})
+    net = U._Net.__new__(U._Net)
+    net.cfg, net.dev, net.heads_dim = ucfg, torch.device("cuda"), 64
+    net.p = U._Packed(sd, net.dev)
+    B = 2
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(B, cin, hw, hw, generator=g).cuda()
+    emb = torch.randn(B, ted, generator=g).cuda()
+    ctx = torch.randn(B, 77, cfg.context_dim, generator=g).cuda()
+    with torch.no_grad():
+        h_ref = ref_rb(x, emb)
+        out_ref = ref_st(h_ref, ctx)
+    ctx16 = K.cast_f16(ctx.reshape(-1, ctx.shape[-1]))
+    h = net.resblock("output_blocks.0.0", _act(x), emb)
+    e_rb = rel_l2(h.nchw(), h_ref)
+    out = net.transformer("output_blocks.0.1", _act(h_ref), depth, ctx16, 77)
+    e_st = rel_l2(out.nchw(), out_ref)
+    print(f"full width level {level}: resblock {e_rb:.1e} transformer(depth {depth}) {e_st:.1e}")
+    assert e_rb < TOL_ACT and e_st < TOL_ACT
