@@ -352,6 +352,7 @@ def main():
     total_ms, e2e_ms, k1_ms, unet_ms = t.tolist()
     # per-kernel-family split of the diffusion half: one extra EAGER step, every C-ABI call bracketed by CUDA events
     fam = unet.profile_eager() if (unet is not None and rank == 0 and not args.no_e2e) else {}
+    loop = unet.full_loop_ms() if (unet is not None and rank == 0 and not args.no_e2e) else None
 
     if rank == 0:
         pk = peaks()
@@ -401,6 +402,11 @@ def main():
                 "render": render_roof}
         else:
             line["roofline"] = render_roof
+        if loop is not None:
+            line["config3_full_inpaint_loop"] = {
+                "unet_evaluations": loop[0], "ms": loop[1], "ms_per_evaluation": loop[1] / loop[0],
+                "note": "render excluded; 20 configured steps at denoising strength 0.9 = 18 UNet+ControlNet CFG evaluations "
+                        "on the 2048^2 sheet latent, eager launches (no CUDA graph), VAE not included (SURVEY §8(f) row 1)"}
         if N == 1 and not args.no_cpu_baseline:
             val, cores, sample = cpu_baseline(render_runs=2, unet_runs=1, with_unet=unet is not None)
             line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}

@@ -648,6 +648,23 @@ class BenchUNet:
         self.graph.replay()
         return self.out
 
+    def full_loop_ms(self) -> Tuple[int, float]:
+        """BASELINE config 3 at latent level: the whole img2img trajectory the reference requests (20 configured steps,
+        denoising strength 0.9 -> 18 UNet+ControlNet evaluations, Euler-ancestral, CFG 7), eager launches.
+        -> (UNet evaluations, device milliseconds)."""
+        sig = img2img_sigmas()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        x = self.init + self.noise * sig[0]
+        a.record()
+        for i in range(len(sig) - 1):
+            x, _, _ = self.net.step(x, sig[i], sig[i + 1], self.context, self.y, self.hint, self.noise, self.init,
+                                    self.lat_mask)
+        b.record()
+        torch.cuda.synchronize()
+        if not bool(torch.isfinite(x).all()):
+            raise RuntimeError("non-finite latent after the denoising loop")
+        return len(sig) - 1, a.elapsed_time(b)
+
     def profile_eager(self) -> dict:
         """One eager step with every C-ABI call bracketed by CUDA events -> per-kernel-family time / FLOPs."""
         K.start_profile()

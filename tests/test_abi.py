@@ -50,3 +50,32 @@ def test_no_silent_cpu_fallback():
     rc = _lib.load().sgn_field_create(C.byref(d), C.byref(h))
     assert rc < 0 and not h
     assert _lib.load().sgn_last_error()
+
+
+def test_unet_operator_argument_errors_are_reported_without_a_gpu():
+    """Argument validation happens before any CUDA call: bad shapes / alignments come back as SGN_ERR_INVALID_ARG with
+    a message, on a box with or without a GPU."""
+    lib = _lib.load()
+    buf = (C.c_uint8 * 4096)()
+    p = C.addressof(buf)
+    p16 = (p + 15) & ~15
+    ep = _lib.SgnEpilogue()
+    assert lib.sgn_gemm_f16(p16, 60, p16, 60, 4, 16, 60, C.byref(ep), p16, None) == -1            # K % 8 != 0
+    assert b"multiples of 8" in lib.sgn_last_error()
+    assert lib.sgn_gemm_f16(p16 + 2, 64, p16, 64, 4, 16, 64, C.byref(ep), p16, None) == -1        # misaligned A
+    assert lib.sgn_gemm_f16(None, 64, p16, 64, 4, 16, 64, C.byref(ep), p16, None) == -1           # null pointer
+    assert lib.sgn_gemm_f16(None, 64, None, 64, 0, 16, 64, C.byref(ep), None, None) == 0          # empty M is a no-op
+    ep.geglu, ep.d_residual = 1, p16
+    assert lib.sgn_gemm_f16(p16, 64, p16, 64, 4, 16, 64, C.byref(ep), p16, None) == -1            # geglu + residual
+    ep = _lib.SgnEpilogue()
+    assert lib.sgn_conv3x3_f16(p16, p16, 1, 8, 8, 48, 16, C.byref(ep), p16, None) == -1           # Cin % 64 != 0
+    assert b"Cin % 64" in lib.sgn_last_error()
+    assert lib.sgn_attention_f16(p16, 60, p16, 64, p16, 64, 1, 1, 8, 8, 0.125, p16, 64, None) == -1   # stride % 8
+    assert lib.sgn_attention_f16(p16, 64, p16, 64, p16, 64, 1, 2, 8, 8, 0.125, p16, 64, None) == -1   # stride < heads*64
+    assert lib.sgn_group_norm_f16(p16, 1, 4, 30, 32, 1e-5, p16, p16, 0, p16, p16, None) == -1     # C % groups
+    assert lib.sgn_layer_norm_f16(p16, 4, 30, 1e-5, p16, p16, p16, None) == -1                    # C % 4
+    assert lib.sgn_linear_small(p16, p16, None, None, 9, 4, 4, 0, 0, p16, None) == -1             # more than 8 rows
+    assert lib.sgn_cfg_euler_step(p16, p16, p16, None, None, 1, 4, 2, 2, 7.0, 1.0, 0.5, 0.5, p16, None, None) == -1  # init w/o mask
+    assert lib.sgn_cfg_euler_step(p16, p16, None, None, None, 1, 4, 2, 2, 7.0, 0.0, 0.5, 0.5, p16, None, None) == -1  # sigma 0
+    assert lib.sgn_sheet_to_conditioning(p16, p16, 12, 16, p16, p16, None) == -1                  # sheet not multiple of 8
+    assert lib.sgn_group_norm_ws_doubles(2, 65536, 32) >= 2 * 32 * 3
