@@ -405,7 +405,7 @@ def main():
         if loop is not None:
             line["config3_full_inpaint_loop"] = {
                 "unet_evaluations": loop[0], "ms": loop[1], "ms_per_evaluation": loop[1] / loop[0],
-                "note": "render excluded; 20 configured steps at denoising strength 0.9 = 18 UNet+ControlNet CFG evaluations "
+                "note": "render excluded; 20 configured steps at denoising strength 0.9 = 19 UNet+ControlNet CFG evaluations "
                         "on the 2048^2 sheet latent, eager launches (no CUDA graph), VAE not included (SURVEY §8(f) row 1)"}
         if N == 1 and not args.no_cpu_baseline:
             val, cores, sample = cpu_baseline(render_runs=2, unet_runs=1, with_unet=unet is not None)

@@ -428,15 +428,29 @@ __global__ void __launch_bounds__(256) k_linear_small(const float* __restrict__ 
 #pragma unroll
   for (int b = 0; b < 8; ++b) acc[b] = 0.f;
   const float* wr = w + (size_t)n * K;
-  for (int k = lane; k < K; k += 32) {
-    const float wv = __ldg(wr + k);
+  if ((K & 3) == 0) {  // 16-byte loads: one weight float4 feeds all rows
+    const int k4 = K >> 2;
+    for (int k = lane; k < k4; k += 32) {
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(wr) + k);
 #pragma unroll
-    for (int b = 0; b < 8; ++b)
-      if (b < B) {
-        float xv = __ldg(x + (size_t)b * K + k);
-        if (silu_in) xv = silu(xv);
-        acc[b] = fmaf(xv, wv, acc[b]);
-      }
+      for (int b = 0; b < 8; ++b)
+        if (b < B) {
+          float4 xv = __ldg(reinterpret_cast<const float4*>(x + (size_t)b * K) + k);
+          if (silu_in) xv.x = silu(xv.x), xv.y = silu(xv.y), xv.z = silu(xv.z), xv.w = silu(xv.w);
+          acc[b] = fmaf(xv.x, wv.x, fmaf(xv.y, wv.y, fmaf(xv.z, wv.z, fmaf(xv.w, wv.w, acc[b]))));
+        }
+    }
+  } else {
+    for (int k = lane; k < K; k += 32) {
+      const float wv = __ldg(wr + k);
+#pragma unroll
+      for (int b = 0; b < 8; ++b)
+        if (b < B) {
+          float xv = __ldg(x + (size_t)b * K + k);
+          if (silu_in) xv = silu(xv);
+          acc[b] = fmaf(xv, wv, acc[b]);
+        }
+    }
   }
 #pragma unroll
   for (int b = 0; b < 8; ++b)

@@ -50,17 +50,28 @@ class FusedNerfactoGraph:
     @classmethod
     def from_state_dict(cls, sd: Mapping[str, Tensor], device="cuda", num_train_data: Optional[int] = None,
                         average_init_density: float = 0.01, render_opts: Optional[ops.RenderOptions] = None):
+        # nerfstudio is not installable here, so the parameter names cannot be checked against a real 1.0.2 checkpoint:
+        # both layouts the torch-fallback modules have used are accepted (MLPWithHashEncoding: `mlp_base.encoding` /
+        # `mlp_base.mlp`; older split modules: `mlp_base_grid` / `mlp_base_mlp`, `encoding` / `mlp_base`).
+        def pick(*cands: str) -> str:
+            for c in cands:
+                if c + ".hash_table" in sd or c + ".layers.0.weight" in sd:
+                    return c
+            raise KeyError(f"none of {cands} found in the state_dict (tcnn checkpoints store a flat `params` vector and "
+                           "are not supported: torch-fallback semantics are the contract, SURVEY §7)")
+
         def grid(prefix: str, levels: int, max_res: int) -> HashGridParams:
             table = sd[prefix + ".hash_table"].detach().float()
             log2 = (table.shape[0] // levels).bit_length() - 1
             return HashGridParams(table.to(device).contiguous(), hash_scalings(levels, 16, max_res), log2)
 
-        def lin(prefix: str) -> LinearParams:
-            return LinearParams(sd[prefix + ".weight"].detach().float().cpu(), sd[prefix + ".bias"].detach().float().cpu())
+        def mlp(prefix: str, n: int):
+            return [LinearParams(sd[f"{prefix}.layers.{i}.weight"].detach().float().cpu(),
+                                 sd[f"{prefix}.layers.{i}.bias"].detach().float().cpu()) for i in range(n)]
 
-        g = grid("field.mlp_base_grid", 16, 2048)
-        base = [lin("field.mlp_base_mlp.layers.0"), lin("field.mlp_base_mlp.layers.1")]
-        head = [lin(f"field.mlp_head.layers.{i}") for i in range(3)]
+        g = grid(pick("field.mlp_base.encoding", "field.mlp_base_grid"), 16, 2048)
+        base = mlp(pick("field.mlp_base.mlp", "field.mlp_base_mlp"), 2)
+        head = mlp(pick("field.mlp_head"), 3)
         emb = sd.get("field.embedding_appearance.embedding.weight")
         if emb is None:  # SIGNeRFPipeline.load_state_dict drops it (signerf_pipeline.py:110-111): fresh N(0,1) rows
             gen = torch.Generator().manual_seed(0)
@@ -68,11 +79,13 @@ class FusedNerfactoGraph:
         app = emb.detach().float().cpu().mean(dim=0)
         pg, pm = [], []
         for i, max_res in enumerate((128, 256)):
-            key = f"proposal_networks.{i}.encoding.hash_table"
-            if key not in sd:
-                break
-            pg.append(grid(f"proposal_networks.{i}.encoding", 5, max_res))
-            pm.append([lin(f"proposal_networks.{i}.mlp_base.layers.0"), lin(f"proposal_networks.{i}.mlp_base.layers.1")])
+            pre = f"proposal_networks.{i}"
+            try:
+                enc = pick(pre + ".mlp_base.encoding", pre + ".encoding")
+            except KeyError:
+                break   # load_model_with_proposal_weights=False drops the proposal networks (signerf_pipeline.py:113-118)
+            pg.append(grid(enc, 5, max_res))
+            pm.append(mlp(pick(pre + ".mlp_base.mlp", pre + ".mlp_base.1", pre + ".mlp_base"), 2))
         fld = NerfactoFieldB200(g, base, head, app, average_init_density, pg, pm)
         if render_opts is None and not pg:
             render_opts = ops.RenderOptions(mode="flat", num_samples=48)

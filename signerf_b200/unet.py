@@ -303,7 +303,10 @@ class _Net:
         if self.heads_dim != 64:
             raise ValueError("sgn_attention_f16 is specialised for head_dim 64 (SDXL)")
         self._prepack(schema)
+        self._pack_context_kv(schema)
         self.p.w = None  # drop the reference to the source state_dict: only packed copies stay resident
+        self._kv_ctx: Optional[Tensor] = None            # context the batched K/V projections were computed for
+        self._kv_out: Dict[int, Tensor] = {}
 
     # every parameter is packed exactly once, up front, so forward() never allocates weights
     def _prepack(self, schema) -> None:
@@ -328,15 +331,43 @@ class _Net:
             elif ".attn1.to_q" in n:
                 b = n[: -len("to_q.weight")]
                 p.cat16([b + "to_q.weight", b + "to_k.weight", b + "to_v.weight"])
-            elif ".attn2.to_k" in n:
-                b = n[: -len("to_k.weight")]
-                p.cat16([b + "to_k.weight", b + "to_v.weight"])
-            elif ".attn1.to_k" in n or ".attn1.to_v" in n or ".attn2.to_v" in n:
-                continue
+            elif ".attn1.to_k" in n or ".attn1.to_v" in n or ".attn2.to_k" in n or ".attn2.to_v" in n:
+                continue   # attn2 K/V: packed per channel width by _pack_context_kv
             elif "ff.net.0.proj.weight" in n:
                 p.geglu16(n, n[:-6] + "bias")
             else:
                 p.lin16(n)
+
+    def _pack_context_kv(self, schema) -> None:
+        """The cross-attention K/V projections of ALL transformer blocks read the same prompt context, so they are one
+        GEMM per channel width: weights [sum over blocks of (to_k | to_v), ctx_dim], block b at row offset _kv_off[b]."""
+        groups: Dict[int, List[str]] = {}
+        for n, shp in schema.items():
+            if n.endswith(".attn2.to_k.weight"):
+                groups.setdefault(shp[0], []).append(n[: -len(".attn2.to_k.weight")])
+        self._kv_w: Dict[int, Tensor] = {}
+        self._kv_off: Dict[str, int] = {}
+        for c, blocks in groups.items():
+            rows = []
+            for i, b in enumerate(blocks):
+                self._kv_off[b] = 2 * c * i
+                rows += [self.p._get(b + ".attn2.to_k.weight"), self.p._get(b + ".attn2.to_v.weight")]
+            self._kv_w[c] = torch.cat(rows, 0).half().contiguous()
+
+    def project_context(self, ctx16: Tensor) -> None:
+        """One K/V GEMM per channel width for the whole network (forward() calls this once per step)."""
+        self._kv_ctx = ctx16
+        self._kv_out = {c: K.gemm_f16(ctx16, w, None, out_f16=True) for c, w in self._kv_w.items()}
+
+    def context_kv(self, block: str, c: int, ctx16: Tensor) -> Tuple[Tensor, Tensor]:
+        """(k, v) [Bt*n_ctx, C] of transformer block `block`: slices of the batched projection when it was made for this
+        context, otherwise this block's own GEMM (block-level callers, tests)."""
+        off = self._kv_off[block]
+        if self._kv_ctx is ctx16:
+            kv = self._kv_out[c]
+            return kv[:, off:off + c], kv[:, off + c:off + 2 * c]
+        kv = K.gemm_f16(ctx16, self._kv_w[c][off:off + 2 * c], None, out_f16=True)
+        return kv[:, :c], kv[:, c:]
 
     # ------------------------------------------------------------------ building blocks
     def gn16(self, x: Act, name: str, eps: float, act_silu: bool) -> Tensor:
@@ -383,8 +414,8 @@ class _Net:
             K.gemm_f16(o16, p.lin16(b + ".attn1.to_out.0.weight"), p.f32(b + ".attn1.to_out.0.bias"), residual=t, out=t)
             a16 = K.layer_norm_f16(t, p.f32(b + ".norm2.weight"), p.f32(b + ".norm2.bias"))
             q = K.gemm_f16(a16, p.lin16(b + ".attn2.to_q.weight"), None, out_f16=True)
-            kv = K.gemm_f16(ctx16, p.cat16([b + ".attn2.to_k.weight", b + ".attn2.to_v.weight"]), None, out_f16=True)
-            o16 = K.attention_f16(q, kv[:, :c], kv[:, c:], x.B, heads)
+            k2, v2 = self.context_kv(b, c, ctx16)
+            o16 = K.attention_f16(q, k2, v2, x.B, heads)
             K.gemm_f16(o16, p.lin16(b + ".attn2.to_out.0.weight"), p.f32(b + ".attn2.to_out.0.bias"), residual=t, out=t)
             a16 = K.layer_norm_f16(t, p.f32(b + ".norm3.weight"), p.f32(b + ".norm3.bias"))
             wg, bg = p.geglu16(b + ".ff.net.0.proj.weight", b + ".ff.net.0.proj.bias")
@@ -450,6 +481,7 @@ class SDXLUNetB200(_Net):
         emb = self.embed(timesteps, y)
         n_ctx = context.shape[1]
         ctx16 = K.cast_f16(context.reshape(-1, context.shape[-1]))
+        self.project_context(ctx16)
         tap = (lambda n, a: taps.__setitem__(n, a.nchw())) if taps is not None else (lambda n, a: None)
         hs, h = self.encoder(x, emb, ctx16, n_ctx, on_block=lambda i, a: tap(f"input_blocks.{i}", a))
         control = list(control) if control is not None else None
@@ -516,6 +548,7 @@ class ControlNetB200(_Net):
         x, timesteps, context, y = (_f32(x, "x"), _f32(timesteps, "timesteps"), _f32(context, "context"), _f32(y, "y"))
         emb = self.embed(timesteps, y)
         ctx16 = K.cast_f16(context.reshape(-1, context.shape[-1]))
+        self.project_context(ctx16)
         guided = self.hint_embedding(hint)
         outs: List[Tensor] = []
         p = self.p
@@ -545,7 +578,8 @@ def sdxl_sigmas() -> Tensor:
 
 def img2img_sigmas(steps: int = 20, denoising_strength: float = 0.9) -> List[float]:
     """A1111 img2img with a k-diffusion sampler: get_sigmas(steps)[steps - t_enc - 1:], t_enc = int(min(s, .999)*steps)
-    (DiffuserConfig: num_inference_steps 20, denoising_strength 0.9 -> 18 UNet evaluations, diffuser.py:33-39)."""
+    (DiffuserConfig: num_inference_steps 20, denoising_strength 0.9 -> t_enc = 18, sigmas[1:] = 20 values = 19 UNet
+    evaluations: k-diffusion get_sigmas(20) returns 21 values and the slice keeps t_enc + 2 of them; diffuser.py:33-39)."""
     table = sdxl_sigmas()
     t = torch.linspace(len(table) - 1, 0, steps)
     log_s = table.log()
@@ -650,7 +684,7 @@ class BenchUNet:
 
     def full_loop_ms(self) -> Tuple[int, float]:
         """BASELINE config 3 at latent level: the whole img2img trajectory the reference requests (20 configured steps,
-        denoising strength 0.9 -> 18 UNet+ControlNet evaluations, Euler-ancestral, CFG 7), eager launches.
+        denoising strength 0.9 -> 19 UNet+ControlNet evaluations, Euler-ancestral, CFG 7), eager launches.
         -> (UNet evaluations, device milliseconds)."""
         sig = img2img_sigmas()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

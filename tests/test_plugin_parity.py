@@ -89,3 +89,33 @@ def test_render_camera_return_arity_quirk():
     assert len(gen.render_camera(graph, cam, with_condition=False)) == 4     # :783
     rgb, mask, cond = gen.render_camera(graph, cam)
     assert rgb.shape == (16, 16, 3) and mask.dtype == torch.bool and cond.shape == (16, 16, 1)
+
+
+@pytest.mark.parametrize("style", ["mlp_with_hash_encoding", "split_modules"])
+def test_graph_from_nerfacto_state_dict(style):
+    """FusedNerfactoGraph.from_state_dict maps a torch-fallback nerfacto checkpoint (both parameter layouts) onto the
+    fused field: renders are bit-identical to the field built directly from the same tensors."""
+    m = R.make_model(0, dense=True, table_scale=0.5, density_gain=20.0)
+    f = m.field
+    a, b, c, d = (("field.mlp_base.encoding", "field.mlp_base.mlp", "proposal_networks.%d.mlp_base.encoding",
+                   "proposal_networks.%d.mlp_base.mlp") if style == "mlp_with_hash_encoding" else
+                  ("field.mlp_base_grid", "field.mlp_base_mlp", "proposal_networks.%d.encoding", "proposal_networks.%d.mlp_base"))
+    sd = {a + ".hash_table": f.encoding.hash_table, "field.embedding_appearance.embedding.weight": f.embedding_appearance.weight}
+    for i, l in enumerate(f.mlp_base.layers):
+        sd[f"{b}.layers.{i}.weight"], sd[f"{b}.layers.{i}.bias"] = l.weight, l.bias
+    for i, l in enumerate(f.mlp_head.layers):
+        sd[f"field.mlp_head.layers.{i}.weight"], sd[f"field.mlp_head.layers.{i}.bias"] = l.weight, l.bias
+    for j, pn in enumerate(m.proposal_networks):
+        sd[(c % j) + ".hash_table"] = pn.encoding.hash_table
+        for i, l in enumerate(pn.mlp.layers):
+            sd[f"{d % j}.layers.{i}.weight"], sd[f"{d % j}.layers.{i}.bias"] = l.weight, l.bias
+    graph = P.FusedNerfactoGraph.from_state_dict(sd, average_init_density=f.average_init_density)
+    direct = P.FusedNerfactoGraph(field_from_oracle(m))
+    assert graph.render_opts.mode == "cascade" and len(graph.field.prop_grids) == 2
+    c2w, _ = ring_cameras(2, 24, 16)
+    cam = P.CameraBatch(c2w, 24.0, 24.0, 12.0, 8.0, 24, 16)
+    o1, o2 = graph.render_cameras(cam), direct.render_cameras(cam)
+    assert torch.equal(o1["rgb"], o2["rgb"]) and torch.equal(o1["depth"], o2["depth"])
+    # proposal networks dropped (load_model_with_proposal_weights=False): flat sampling of the main field
+    sd_np = {k: v for k, v in sd.items() if not k.startswith("proposal_networks")}
+    assert P.FusedNerfactoGraph.from_state_dict(sd_np).render_opts.mode == "flat"

@@ -128,7 +128,7 @@ def test_denoise_step_matches_oracle(nets):
     mask = (torch.rand(B, 1, h, w, generator=g) > 0.5).float().cuda()
     _, _, ctx, y, hint = _inputs(cfg, seed=13)
     sig = U.img2img_sigmas()
-    assert len(sig) == 20 and sig[-1] == 0.0            # start sigma + 18 steps' targets (the last one is 0)
+    assert len(sig) == 20 and sig[-1] == 0.0            # 20 sigmas = 19 Euler-ancestral steps, the last one onto sigma 0
     assert torch.allclose(torch.tensor(sig), R.img2img_schedule(), rtol=1e-6)
     x_ref, den_ref, eps_ref = R.denoise_step(ref_unet, ref_ctrl, x, sig[0], sig[1], ctx, y, hint, noise, init, mask)
     x_new, den, eps = net.step(x, sig[0], sig[1], ctx, y, hint, noise, init, mask)
@@ -179,6 +179,8 @@ def test_full_width_blocks_match_oracle(level, hw):
     net = U._Net.__new__(U._Net)
     net.cfg, net.dev, net.heads_dim = ucfg, torch.device("cuda"), 64
     net.p = U._Packed(sd, net.dev)
+    net._pack_context_kv({k: tuple(v.shape) for k, v in sd.items()})
+    net._kv_ctx, net._kv_out = None, {}
     B = 2
     g = torch.Generator().manual_seed(9)
     x = torch.randn(B, cin, hw, hw, generator=g).cuda()
