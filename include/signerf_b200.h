@@ -37,6 +37,12 @@ int sgn_abi_version(void);
 /* Number of kernel launches issued by this library on the calling process so far
  * (bench.py reports the delta over the timed region as `gpu_launches`). */
 uint64_t sgn_launch_count(void);
+/* Process-wide tuning knobs (set between launches, not thread-safe against concurrent launches):
+ *   "render_ctas_per_sm" 1..4 (default 4): resident renderer CTAs per SM; 1 leaves room for a co-resident GEMM CTA
+ *   "gemm_pair_stages"   5|6  (default 6): pipeline stages of the CTA-pair GEMM (5 = 160 KB shared memory)
+ * (Measured on B200, scratch/overlap.py: co-running a 1-CTA/SM renderer with the GEMMs on two streams is slower than
+ * running them back to back - 194 ms against 145 ms - so bench.py keeps the defaults and a single stream.) */
+int sgn_set_option(const char* name, int value);
 
 /* ------------------------------------------------------------------ field (A4/A5) */
 /* One multiresolution hash grid = nerfstudio HashEncoding, torch-fallback semantics

@@ -69,6 +69,7 @@ SIGNATURES = {
     "sgn_last_error": (C.c_char_p, []),
     "sgn_abi_version": (_i, []),
     "sgn_launch_count": (C.c_uint64, []),
+    "sgn_set_option": (_i, [C.c_char_p, _i]),
     "sgn_field_create": (_i, [C.POINTER(SgnFieldDesc), C.POINTER(_vp)]),
     "sgn_field_destroy": (None, [_vp]),
     "sgn_render_views": (_i, [_vp, _vp, _vp, _i, _i, _i, C.POINTER(SgnRenderOpts), _vp, _vp, _vp, _vp]),
@@ -126,6 +127,10 @@ def load() -> C.CDLL:
 def check(code: int) -> None:
     if code != SGN_OK:
         raise SgnError(code, load().sgn_last_error().decode("utf-8", "replace"))
+
+
+def set_option(name: str, value: int) -> None:
+    check(load().sgn_set_option(name.encode(), int(value)))
 
 
 def launch_count() -> int:

@@ -73,11 +73,15 @@ constexpr int kBK = 64;
 constexpr int kStageA = kBM * kBK * 2;    // 16 KB
 template <int kCluster> struct GemmCfg {
   static constexpr int kStageB = (256 / kCluster) * kBK * 2;  // 32 KB (single CTA) / 16 KB (half of B per pair CTA)
-  static constexpr int kStages = kCluster == 2 ? 6 : 4;
 };
+// pair shape: 6 stages (192 KB) by default; 5 stages (160 KB) measure the same in isolation and leave room for a small
+// co-resident CTA (sgn_set_option "gemm_pair_stages")
+constexpr size_t gemm_smem_bytes(int cluster, int stages) {
+  return 1024 + (size_t)stages * (kStageA + (256 / cluster) * kBK * 2) + 256;
+}
+int g_pair_stages = 6;
 constexpr int kAccStride = 256;           // TMEM columns between the two accumulator buffers
 constexpr int kConvTileW = 16, kConvTileH = 8;
-constexpr size_t kGemmSmem = 1024 + (size_t)4 * (kStageA + 32768) + 256;  // = 6 * (16 KB + 16 KB) for the pair shape
 
 struct GemmParams {
   int M, N, K;  // N = weight rows covered by tiles (multiple of block_n); n_valid <= N columns are stored
@@ -174,10 +178,10 @@ __device__ __forceinline__ void epilogue16(const GemmParams& p, const uint32_t* 
   }
 }
 
-template <int kCluster>
+template <int kCluster, int kStages>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  constexpr int kStages = GemmCfg<kCluster>::kStages, kStageB = GemmCfg<kCluster>::kStageB;
+  constexpr int kStageB = GemmCfg<kCluster>::kStageB;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
@@ -388,28 +392,30 @@ static int pick_cluster(const GemmParams& p) {
   return p.num_m_tiles >= 2 ? 2 : 1;
 }
 
-template <int kCluster>
+template <int kCluster, int kStages>
 static int launch_gemm_c(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
+  constexpr size_t smem = gemm_smem_bytes(kCluster, kStages);
   static bool attr_set = false;
   if (!attr_set) {
-    SGN_CUDA(cudaFuncSetAttribute(k_gemm_tc<kCluster>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+    SGN_CUDA(cudaFuncSetAttribute(k_gemm_tc<kCluster, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   const int groups = (p.num_m_tiles + kCluster - 1) / kCluster * p.num_n_tiles;
   const int grid = std::min(groups, sm_count() / kCluster) * kCluster;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kGemmThreads), cfg.dynamicSmemBytes = kGemmSmem, cfg.stream = st;
+  cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kGemmThreads), cfg.dynamicSmemBytes = smem, cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kCluster, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr, cfg.numAttrs = 1;
-  SGN_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tc<kCluster>, tmA, tmB, p));
+  SGN_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tc<kCluster, kStages>, tmA, tmB, p));
   SGN_LAUNCH_CHECK();
   return SGN_OK;
 }
 
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, int cluster, cudaStream_t st) {
-  return cluster == 2 ? launch_gemm_c<2>(tmA, tmB, p, st) : launch_gemm_c<1>(tmA, tmB, p, st);
+  if (cluster != 2) return launch_gemm_c<1, 4>(tmA, tmB, p, st);
+  return g_pair_stages == 5 ? launch_gemm_c<2, 5>(tmA, tmB, p, st) : launch_gemm_c<2, 6>(tmA, tmB, p, st);
 }
 
 static int fill_epilogue(GemmParams& p, const SgnEpilogue* ep, int n_valid, void* d_out) {

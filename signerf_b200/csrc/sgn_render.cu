@@ -347,6 +347,8 @@ void host_flat_bins(int S, float near_p, float far_p, std::vector<float>& out) {
   }
 }
 
+int g_render_ctas_per_sm = 4;  // sgn_set_option "render_ctas_per_sm": 1 leaves the SM mostly free for a co-resident kernel
+
 size_t mma_smem_bytes(int S, bool per_ray) {
   return sizeof(MlpPack) + kWarps * 32 * kStageStride * sizeof(__half) + 16 + (per_ray ? 0 : (size_t)(S + 1) * 4);
 }
@@ -379,7 +381,7 @@ int launch_render(const SgnField* f, const float* d_c2w, const float* d_intr, in
   const int blocks_needed = (p.num_tiles + kWarps - 1) / kWarps;
   if (mlp_mode == SGN_MLP_FP16_MMA) {
     size_t smem = mma_smem_bytes(S, per_ray);
-    int grid = std::min(blocks_needed, sm_count() * 4);
+    int grid = std::min(blocks_needed, sm_count() * g_render_ctas_per_sm);
     if (per_ray) {
       int rc = set_smem(k_render_mma<true>, smem);
       if (rc) return rc;
@@ -537,4 +539,23 @@ extern "C" int sgn_field_eval(const SgnField* f, const float* d_pos, const float
   }
   SGN_LAUNCH_CHECK();
   return SGN_OK;
+}
+
+namespace sgn { extern int g_pair_stages; }
+
+extern "C" int sgn_set_option(const char* name, int value) {
+  SGN_CHECK_ARG(name != nullptr, "null option name");
+  const std::string n(name);
+  if (n == "render_ctas_per_sm") {
+    SGN_CHECK_ARG(value >= 1 && value <= 4, "render_ctas_per_sm must be 1..4");
+    sgn::g_render_ctas_per_sm = value;
+    return SGN_OK;
+  }
+  if (n == "gemm_pair_stages") {
+    SGN_CHECK_ARG(value == 5 || value == 6, "gemm_pair_stages must be 5 or 6");
+    sgn::g_pair_stages = value;
+    return SGN_OK;
+  }
+  sgn::set_error("invalid argument: unknown option " + n);
+  return SGN_ERR_INVALID_ARG;
 }
