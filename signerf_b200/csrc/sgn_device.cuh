@@ -295,7 +295,9 @@ __device__ __forceinline__ void warp_field_eval(const GridDev& grid, const MlpPa
                                                 const uint32_t (&ash)[2][4], float& logit, float& cr, float& cg,
                                                 float& cb) {
   const float fs = sp->feat_scale;
-#pragma unroll
+  // the 4-level group is unrolled, the loop over groups is not: fully unrolled, the 16 levels + MLP exceed the 32 KB
+  // instruction cache (ncu: 15 % of warp samples stalled on no_instruction)
+#pragma unroll 1
   for (int l4 = 0; l4 < 4; ++l4) {
     uint32_t h[4];
 #pragma unroll
@@ -311,14 +313,18 @@ __device__ __forceinline__ void warp_field_eval(const GridDev& grid, const MlpPa
   const int base = lane & ~3;
   const uint32_t ld_row = (lane & 7) + 8 * ((lane >> 3) & 1);
   const uint32_t ld_col = 8 * (lane >> 4);
-#pragma unroll
+  // one copy of the MLP code for both 16-sample m-tiles (instruction-cache footprint, see above)
+#pragma unroll 1
   for (int m = 0; m < 2; ++m) {
     uint32_t af[2][4];
     uint32_t addr = smem_u32(stage + (16 * m + ld_row) * kStageStride + ld_col);
     ldmatrix_x4(af[0], addr);
     ldmatrix_x4(af[1], addr + 32);
     float lg0, lg1, c[4];
-    field_mlp_mtile(sp, lane, af, ash[m], lg0, lg1, c);
+    uint32_t am[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) am[i] = m ? ash[1][i] : ash[0][i];
+    field_mlp_mtile(sp, lane, af, am, lg0, lg1, c);
     // route rows {g, g+8} of this m-tile to lanes t = 2m, 2m+1 of the quad
     float lgA = __shfl_sync(0xffffffffu, lg0, base);
     float lgB = __shfl_sync(0xffffffffu, lg1, base);
