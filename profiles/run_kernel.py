@@ -23,3 +23,11 @@ elif which == "conv":
     for _ in range(3):
         nn_ops.conv3x3_f16(x, w, None)
 torch.cuda.synchronize()
+if which == "render":
+    from signerf_b200 import ops, synthetic
+    dev = torch.device("cuda")
+    fld = synthetic.random_field(seed=0, device=dev, dense=True, with_proposals=False)
+    c2w, intr = synthetic.camera_ring(16, 512, 512)
+    for _ in range(2):
+        ops.render_views(fld, c2w.to(dev), intr.to(dev), 512, 512, ops.RenderOptions(mode="flat", num_samples=128))
+    torch.cuda.synchronize()

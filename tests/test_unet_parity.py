@@ -196,3 +196,33 @@ def test_full_width_blocks_match_oracle(level, hw):
     e_st = rel_l2(out.nchw(), out_ref)
     print(f"full width level {level}: resblock {e_rb:.1e} transformer(depth {depth}) {e_st:.1e}")
     assert e_rb < TOL_ACT and e_st < TOL_ACT
+
+
+def test_full_sdxl_unet_end_to_end_error_at_real_depth():
+    """The real thing once: SDXL-base UNet (2.57 B parameters, 70 transformer blocks) on a 32x32 latent, CUDA path vs the
+    fp32 oracle on the same fp16-representable random weights.  The north_star tolerance (1e-3) is per activation; the
+    eps output of the full-depth network carries the roundings of ~450 chained fp16 GEMM operands: the measured value is
+    printed and bounded at 3e-3 (it is 1e-3-class)."""
+    cfg = R.UNetConfig()
+    torch.manual_seed(0)
+    with torch.device("cuda"):
+        ref = R.UNetModel(cfg)
+    ref.eval()
+    with torch.no_grad():
+        for prm in ref.parameters():
+            prm.copy_(prm.half().float())
+    un = U.SDXLUNetB200(U.UNetConfig(), ref.state_dict(), "cuda")
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(2, 4, 32, 32, generator=g).cuda()
+    t = torch.tensor([701.5, 701.5]).cuda()
+    ctx = torch.randn(2, 77, cfg.context_dim, generator=g).cuda()
+    y = torch.randn(2, cfg.adm_in_channels, generator=g).cuda()
+    taps_ref, taps = {}, {}
+    with torch.no_grad():
+        out_ref = ref(x, t, ctx, y, taps=taps_ref)
+    out = un.forward(x, t, ctx, y, taps=taps)
+    errs = {k: rel_l2(taps[k], taps_ref[k]) for k in ("input_blocks.4", "input_blocks.8", "middle_block", "output_blocks.2",
+                                                      "output_blocks.5", "output_blocks.8")}
+    e_out = rel_l2(out, out_ref)
+    print("full SDXL UNet end-to-end:", {k: f"{v:.1e}" for k, v in errs.items()}, f"eps {e_out:.1e}")
+    assert max(errs.values()) < 3e-3 and e_out < 3e-3
