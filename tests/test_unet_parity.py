@@ -200,9 +200,8 @@ def test_full_width_blocks_match_oracle(level, hw):
 
 def test_full_sdxl_unet_end_to_end_error_at_real_depth():
     """The real thing once: SDXL-base UNet (2.57 B parameters, 70 transformer blocks) on a 32x32 latent, CUDA path vs the
-    fp32 oracle on the same fp16-representable random weights.  The north_star tolerance (1e-3) is per activation; the
-    eps output of the full-depth network carries the roundings of ~450 chained fp16 GEMM operands: the measured value is
-    printed and bounded at 3e-3 (it is 1e-3-class)."""
+    fp32 oracle on the same fp16-representable random weights, end to end (no teacher forcing).  Measured on B200: worst
+    sampled activation 6.9e-4, eps 5.4e-4 relative L2 -> asserted at the north_star tolerance 1e-3."""
     cfg = R.UNetConfig()
     torch.manual_seed(0)
     with torch.device("cuda"):
@@ -225,4 +224,4 @@ def test_full_sdxl_unet_end_to_end_error_at_real_depth():
                                                       "output_blocks.5", "output_blocks.8")}
     e_out = rel_l2(out, out_ref)
     print("full SDXL UNet end-to-end:", {k: f"{v:.1e}" for k, v in errs.items()}, f"eps {e_out:.1e}")
-    assert max(errs.values()) < 3e-3 and e_out < 3e-3
+    assert max(errs.values()) < TOL_ACT and e_out < TOL_ACT
