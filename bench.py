@@ -205,6 +205,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-unet", action="store_true", help="time the render half only (profiling)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end and per-kernel passes (ncu runs only)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU tile exchange: fused NVLink peer stores (default) or one NCCL all-gather")
     ap.add_argument("--ncu-range", action="store_true",
                     help="cudaProfilerStart/Stop around the timed steps (run under `ncu --profile-from-start off`)")
     args = ap.parse_args()
@@ -255,6 +257,22 @@ def main():
         unet = unet_mod.BenchUNet(dev, sheet_hw=(layout.height, layout.width), seed=0)
 
     tiles = torch.empty((N, VIEWS, H, W, 6), dtype=torch.float32, device=dev) if N > 1 else None
+    # tile exchange: peer stores over NVLink fused with the packing (symmetric memory) - NCCL all-gather when the
+    # process group cannot provide symmetric memory (--exchange nccl forces it)
+    exchange, exchange_name = None, "single GPU"
+    if N > 1:
+        exchange_name = f"per-view x{N} + NCCL all-gather"
+        if args.exchange == "peer":
+            try:
+                exchange = sharding.PeerTileExchange(N, rank, VIEWS, H, W, dev)
+                exchange_name = f"per-view x{N} + fused NVLink peer stores (symmetric memory)"
+            except Exception as e:  # noqa: BLE001
+                print(f"[bench] symmetric-memory exchange unavailable ({type(e).__name__}: {e}); using NCCL all-gather",
+                      file=sys.stderr)
+        ok = torch.tensor([1 if exchange is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)      # all ranks must agree on the path
+        if int(ok) == 0:
+            exchange, exchange_name = None, f"per-view x{N} + NCCL all-gather"
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
     k1_events, unet_events = [], []
 
@@ -267,7 +285,9 @@ def main():
             b.record()
             k1_events.append((a, b))
         mask, cond, _ = ops.mask_condition(c2w, intr, depth, mopts)
-        if N > 1:
+        if N > 1 and exchange is not None:
+            rgb, _, cond, mask = sharding.unpack_tiles(exchange.exchange(rgb, depth, cond, mask))
+        elif N > 1:
             # pack [rgb3 | depth | cond | mask] per pixel and all-gather the per-view shards of all N grids
             packed = sharding.pack_tiles(rgb, depth, cond, mask).view(N, len(mine), H, W, sharding.PACK_CHANNELS)
             sharding.gather_grids(packed, VIEWS, N, rank, out=tiles)
@@ -370,7 +390,7 @@ def main():
                                    "AABB mask + 50x50 dilation + depth condition, 2048x2048 sheet" +
                                    (", + 1 SDXL+ControlNet UNet step (CFG 2)" if unet is not None else "; UNet step NOT YET BUILT (render half only)"),
                        "views": VIEWS, "height": H, "width": W, "samples_per_ray": SAMPLES, "sheet": [layout.height, layout.width],
-                       "unet": unet is not None, "sharding": f"per-view x{N} + all-gather" if N > 1 else "single GPU",
+                       "unet": unet is not None, "sharding": exchange_name,
                        "l2": "256 MiB memset between steps, outside the timed events"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(c2w_h.numel() * 4 + intr_h.numel() * 4),
                     "d2h_bytes_per_step": int(res_h.numel() * res_h.element_size())},

@@ -169,6 +169,14 @@ int sgn_sheet_cut(const float* d_sheet, int sheet_h, int sheet_w, int C, int row
 int sgn_blend_masked(const float* d_edited, const float* d_base, const float* d_mask, int64_t npix, int C,
                      float* d_out, void* stream);
 
+/* Multi-GPU exchange fused with the tile packing ("fused NVLink peer stores"): this rank's views
+ * (rank, rank+world, ...) of each grid g are written as packed pixels [r,g,b,depth,cond,mask] (6 fp32) directly into
+ * the tile buffer of grid g's owner, d_peer_ptrs[g] -> [v_loc*world, H, W, 6], a peer-mapped device pointer
+ * (torch symmetric memory / cudaIpc).  Inputs are [G, v_loc, H, W, C] contiguous.  The caller orders it between two
+ * cross-rank barriers; no reduction is involved, so results equal the NCCL all-gather bit for bit. */
+int sgn_scatter_tiles_peer(const float* d_rgb, const float* d_depth, const float* d_cond, const uint8_t* d_mask, int G,
+                           int v_loc, int H, int W, int world, int rank, const int64_t* d_peer_ptrs, void* stream);
+
 /* tensor_to_image quantisation (utils/image_tensor_converter.py:22-23,29-30):
  * uint8(x*255) by truncation with wrap-around, exactly numpy's float32 -> uint8 cast.          */
 int sgn_quantize_u8(const float* d_in, int64_t n, uint8_t* d_out, void* stream);

@@ -82,6 +82,7 @@ SIGNATURES = {
     "sgn_sheet_paste": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "sgn_sheet_cut": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "sgn_blend_masked": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp]),
+    "sgn_scatter_tiles_peer": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "sgn_quantize_u8": (_i, [_vp, _i64, _vp, _vp]),
     "sgn_gemm_f16": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, C.POINTER(SgnEpilogue), _vp, _vp]),
     "sgn_conv3x3_f16": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.POINTER(SgnEpilogue), _vp, _vp]),

@@ -277,6 +277,25 @@ __global__ void k_quantize(const float* __restrict__ in, size_t n, uint8_t* __re
     out[i] = (uint8_t)(__float2int_rz(__fmul_rn(in[i], 255.f)) & 0xff);
 }
 
+// Exchange step of the multi-GPU path fused with the tile packing: rank r holds views r, r+world, ... of every grid g and
+// stores the packed pixels [rgb | depth | cond | mask] straight into grid g's owner (rank g) through NVLink-mapped peer
+// pointers - an all-to-all without staging buffers or a collective launch.  peer[g] -> [num_views, H, W, 6] fp32.
+__global__ void k_scatter_tiles_peer(const float* __restrict__ rgb, const float* __restrict__ depth,
+                                     const float* __restrict__ cond, const uint8_t* __restrict__ mask, int G, int v_loc,
+                                     size_t hw, int world, int rank, const long long* __restrict__ peer) {
+  const size_t n = (size_t)G * v_loc * hw;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t pix = i % hw;
+    const size_t t = i / hw;            // local tile index = g * v_loc + j
+    const int j = (int)(t % v_loc), g = (int)(t / v_loc);
+    const int view = rank + j * world;  // global view id inside grid g
+    float2* dst = reinterpret_cast<float2*>(reinterpret_cast<float*>(peer[g]) + ((size_t)view * hw + pix) * 6);
+    dst[0] = make_float2(rgb[i * 3 + 0], rgb[i * 3 + 1]);
+    dst[1] = make_float2(rgb[i * 3 + 2], depth[i]);
+    dst[2] = make_float2(cond[i], (float)mask[i]);
+  }
+}
+
 }  // namespace sgn
 
 using namespace sgn;
@@ -375,6 +394,20 @@ extern "C" int sgn_quantize_u8(const float* d_in, int64_t n, uint8_t* d_out, voi
   if (n == 0) return SGN_OK;
   SGN_CHECK_ARG(d_in && d_out, "null pointer");
   k_quantize<<<grid_for((size_t)n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_in, (size_t)n, d_out);
+  SGN_LAUNCH_CHECK();
+  return SGN_OK;
+}
+
+extern "C" int sgn_scatter_tiles_peer(const float* d_rgb, const float* d_depth, const float* d_cond, const uint8_t* d_mask,
+                                      int G, int v_loc, int H, int W, int world, int rank, const int64_t* d_peer_ptrs,
+                                      void* stream) {
+  SGN_CHECK_ARG(G >= 0 && v_loc >= 0 && H > 0 && W > 0 && world >= 1 && rank >= 0 && rank < world, "bad shape / rank");
+  SGN_CHECK_ARG(G <= world, "one destination rank per grid: G <= world");
+  if (G == 0 || v_loc == 0) return SGN_OK;
+  SGN_CHECK_ARG(d_rgb && d_depth && d_cond && d_mask && d_peer_ptrs, "null pointer");
+  const size_t n = (size_t)G * v_loc * H * W;
+  k_scatter_tiles_peer<<<grid_for(n, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      d_rgb, d_depth, d_cond, d_mask, G, v_loc, (size_t)H * W, world, rank, reinterpret_cast<const long long*>(d_peer_ptrs));
   SGN_LAUNCH_CHECK();
   return SGN_OK;
 }

@@ -50,3 +50,42 @@ def gather_grids(packed_local: Tensor, num_views: int, world: int, rank: int, gr
     for r in range(world):
         out[:, r::world] = parts[r]
     return out
+
+
+class PeerTileExchange:
+    """The same exchange without a collective: every rank owns a symmetric-memory tile buffer [num_views, H, W, 6] for
+    ITS grid, and the producers store their packed tiles straight into the owner's buffer over NVLink
+    (`sgn_scatter_tiles_peer`), bracketed by two device-side barriers of the symmetric-memory handle:
+        barrier   - every rank has finished reading the tiles of the previous step
+        scatter   - rank r writes its views of grid g into rank g's buffer        (all-to-all, 1/world of the all-gather bytes)
+        barrier   - every store has landed
+    Bit-identical to `gather_grids(...)[rank]` (a pure permutation of the same fp32 values)."""
+
+    def __init__(self, world: int, rank: int, num_views: int, height: int, width: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        if num_views % world != 0:
+            raise ValueError("views must divide evenly over the ranks")
+        self.world, self.rank, self.num_views, self.h, self.w = world, rank, num_views, height, width
+        self.tiles = symm_mem.empty((num_views, height, width, PACK_CHANNELS), dtype=torch.float32, device=device)
+        grp = group if group is not None else dist.group.WORLD
+        self.handle = symm_mem.rendezvous(self.tiles, grp)
+        self.peer_ptrs = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64, device=device)
+
+    def exchange(self, rgb: Tensor, depth: Tensor, cond: Tensor, mask: Tensor) -> Tensor:
+        """Inputs: this rank's views of all `world` grids, [world * v_loc, H, W, C] (grid-major).  Returns this rank's
+        grid as packed tiles [num_views, H, W, 6] (valid until the next call)."""
+        import ctypes as C
+        from . import _lib
+        v_loc = self.num_views // self.world
+        if rgb.shape[0] != self.world * v_loc:
+            raise ValueError(f"expected {self.world * v_loc} local views, got {rgb.shape[0]}")
+        rgb, depth, cond = rgb.contiguous(), depth.contiguous(), cond.contiguous()
+        mask = mask.to(torch.uint8).contiguous()
+        self.handle.barrier(channel=0)
+        with torch.cuda.device(rgb.device):
+            _lib.check(_lib.load().sgn_scatter_tiles_peer(
+                C.c_void_p(rgb.data_ptr()), C.c_void_p(depth.data_ptr()), C.c_void_p(cond.data_ptr()),
+                C.c_void_p(mask.data_ptr()), self.world, v_loc, self.h, self.w, self.world, self.rank,
+                C.c_void_p(self.peer_ptrs.data_ptr()), C.c_void_p(torch.cuda.current_stream(rgb.device).cuda_stream)))
+        self.handle.barrier(channel=1)
+        return self.tiles
