@@ -27,6 +27,10 @@ import sys
 import threading
 import time
 
+# NCCL announces its version on STDOUT at NCCL_DEBUG=VERSION; the contract is ONE JSON line on stdout
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
