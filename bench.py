@@ -230,7 +230,19 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # communicator creation prints an "NCCL version" banner on STDOUT; the contract is ONE JSON line there, so fd 1
+        # points at stderr while the process group and its first collective come up
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     N = world
 
     fld = synthetic.random_field(seed=0, device=dev, dense=True, with_proposals=False)
