@@ -245,6 +245,9 @@ def main():
             os.close(saved)
     N = world
 
+    for opt, env in (("gemm_pair_stages", "SGN_GEMM_PAIR_STAGES"), ("render_ctas_per_sm", "SGN_RENDER_CTAS_PER_SM")):
+        if os.environ.get(env):   # tuning knobs of the library (sgn_set_option), for A/B runs
+            _lib.set_option(opt, int(os.environ[env]))
     fld = synthetic.random_field(seed=0, device=dev, dense=True, with_proposals=False)
     layout = ops.SheetLayout(ROWS, COLS, H, W, 0)
     ropts = ops.RenderOptions(mode="flat", num_samples=SAMPLES)

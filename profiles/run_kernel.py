@@ -31,3 +31,11 @@ if which == "render":
     for _ in range(2):
         ops.render_views(fld, c2w.to(dev), intr.to(dev), 512, 512, ops.RenderOptions(mode="flat", num_samples=128))
     torch.cuda.synchronize()
+if which == "gemm_mid":       # attention out-projection of the 1280-channel level: the most frequent GEMM shape
+    a = torch.randn(8192, 1280, device="cuda").half()
+    w = torch.randn(1280, 1280, device="cuda").half()
+    r = torch.randn(8192, 1280, device="cuda")
+    b = torch.randn(1280, device="cuda")
+    for _ in range(3):
+        nn_ops.gemm_f16(a, w, b, residual=r, out=r)
+    torch.cuda.synchronize()

@@ -95,12 +95,16 @@ struct GemmParams {
   void* out;
   long long ldo;
   int out_f16, geglu, nchw, act_silu;
+  int res_prefetch;  // 0: fetch the residual inside the epilogue (A/B knob SGN_GEMM_RES_PREFETCH=0)
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 
 // One 16-column group of one output row.
-__device__ __forceinline__ void epilogue16(const GemmParams& p, const uint32_t* acc, long long m, int b, int n0) {
+// `rpre`: the residual of these 16 columns already in registers (prefetched while the MMAs / the TMEM load were in
+// flight), or nullptr to fetch it here.
+__device__ __forceinline__ void epilogue16(const GemmParams& p, const uint32_t* acc, long long m, int b, int n0,
+                                           const float4* rpre = nullptr) {
   float v[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
@@ -134,7 +138,7 @@ __device__ __forceinline__ void epilogue16(const GemmParams& p, const uint32_t* 
       const float4* rp = reinterpret_cast<const float4*>(p.residual + m * p.ldo + n0);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        float4 t = rp[q];
+        float4 t = rpre ? rpre[q] : rp[q];
         v[4 * q] += t.x, v[4 * q + 1] += t.y, v[4 * q + 2] += t.z, v[4 * q + 3] += t.w;
       }
     }
@@ -318,20 +322,37 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         valid = m < p.M;
         b = p.rows_per_batch > 0 ? (int)(m / p.rows_per_batch) : 0;
       }
-      tc::mbar_wait(&tfull[buf], ph);
-      tc::tc_fence_after();
-      const uint32_t taddr = tmem_base + buf * kAccStride + ((uint32_t)lane_base << 16);
       const int n_base = n_tile * p.block_n;
       // the two warps of a lane quarter split the tile's columns in 32-wide chunks: even chunks / odd chunks
       int c0 = col_half * 32;
+      // The fp32 residual (the stream the UNet keeps adding into) is the epilogue's only global read: the first chunk's
+      // is fetched before the accumulator is even complete, the next chunk's while the current one is processed.
+      const bool res_pre = p.res_prefetch && p.residual != nullptr && !p.nchw && !p.geglu && valid;
+      float4 rcur[8], rnext[8];
+      auto prefetch = [&](int c, float4 (&r)[8]) -> bool {
+        const int n0 = n_base + c;
+        if (!res_pre || c + 32 > p.block_n || n0 + 32 > p.n_valid) return false;
+        const float4* rp = reinterpret_cast<const float4*>(p.residual + m * p.ldo + n0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) r[q] = rp[q];
+        return true;
+      };
+      bool cur_ok = prefetch(c0, rcur);
+      tc::mbar_wait(&tfull[buf], ph);
+      tc::tc_fence_after();
+      const uint32_t taddr = tmem_base + buf * kAccStride + ((uint32_t)lane_base << 16);
       for (; c0 + 32 <= p.block_n; c0 += 64) {
         uint32_t acc[32];
         tc::tmem_ld32(taddr + c0, acc);
+        const bool next_ok = prefetch(c0 + 64, rnext);
         tc::tmem_ld_wait();
         if (valid) {
-          epilogue16(p, acc, m, b, n_base + c0);
-          epilogue16(p, acc + 16, m, b, n_base + c0 + 16);
+          epilogue16(p, acc, m, b, n_base + c0, cur_ok ? rcur : nullptr);
+          epilogue16(p, acc + 16, m, b, n_base + c0 + 16, cur_ok ? rcur + 4 : nullptr);
         }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) rcur[q] = rnext[q];
+        cur_ok = next_ok;
       }
       if (c0 < p.block_n && c0 + 16 == p.block_n) {  // 16-column tail (block_n % 32 == 16) belongs to whoever reaches it
         uint32_t acc[16];
@@ -427,6 +448,8 @@ static int fill_epilogue(GemmParams& p, const SgnEpilogue* ep, int n_valid, void
   p.geglu = ep ? ep->geglu : 0;
   p.nchw = ep ? ep->nchw : 0;
   p.act_silu = ep ? ep->act_silu : 0;
+  static const int res_prefetch = [] { const char* e = getenv("SGN_GEMM_RES_PREFETCH"); return e ? atoi(e) : 1; }();
+  p.res_prefetch = res_prefetch;
   p.out = d_out;
   long long ld = ep ? ep->ldo : 0;
   p.ldo = ld > 0 ? ld : (p.geglu ? n_valid / 2 : n_valid);
