@@ -36,6 +36,7 @@ constexpr size_t kAttnSmem = 1024 + kTileBytes * (2 + 2 * kKvStages) + 256;
 
 struct AttnParams {
   int T_q, T_kv, n_kv_tiles;
+  int idle_ns;   // MMA-issuer back-off when neither tile has work (0 = spin)
   float scale_log2e;
   __half* out;
   long long ldo;
@@ -67,7 +68,16 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float ex2_v(float x) {   // pinned in program order (stays behind the named barrier)
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
+int g_attn_variant = 1;   // sgn_set_option "attn_variant"
+int g_attn_idle_ns = 0;   // sgn_set_option "attn_idle_ns"
+
+template <int kVariant>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -159,6 +169,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       // Event loop: serve whichever of {S_x free -> next Q K^T, P_x ready -> P V} is ready, per query tile.
       int qk_next[2] = {1, 1}, pv_next[2] = {0, 0};
       while (pv_next[0] < n_kv || pv_next[1] < n_kv) {
+        bool progress = false;
 #pragma unroll
         for (int x = 0; x < 2; ++x) {
           const int jq = qk_next[x];
@@ -167,6 +178,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             tc::tc_fence_after();
             issue_qk(x, jq);
             qk_next[x] = jq + 1;
+            progress = true;
           }
           const int jp = pv_next[x];
           if (jp < n_kv && tc::mbar_test(&p_full[x], jp & 1)) {
@@ -174,8 +186,10 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             issue_pv(x, jp);
             pv_next[x] = jp + 1;
             if (pv_next[x ^ 1] > jp) tc::umma_commit(&kv_empty[jp % kKvStages]);  // both tiles are through K/V(jp)
+            progress = true;
           }
         }
+        if (!progress && p.idle_ns > 0) __nanosleep(p.idle_ns);
       }
     }
   } else {  // ---------------- softmax warpgroups: x = 0 (warps 2-5) / 1 (warps 6-9); thread = query row = TMEM lane
@@ -237,26 +251,53 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const float neg_m = -m_run * sc;
       float psum0 = 0.f, psum1 = 0.f;
       named_sync(1 + x, 256);            // my turn on the MUFU pipe
+      if constexpr (kVariant == 0) {
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {      // 64 keys -> 32 packed columns per tcgen05.st
+        for (int c = 0; c < 2; ++c) {      // 64 keys -> 32 packed columns per tcgen05.st
+          uint32_t pk[32];
+  #pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            float e[8];
+  #pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float t = fmaf(__uint_as_float(s[c * 64 + g * 8 + q]), sc, neg_m);
+              e[q] = (kPolyEvery > 0 && (q % kPolyEvery) == kPolyEvery - 1) ? ex2_poly(t) : ex2(t);
+            }
+            psum0 += (e[0] + e[1]) + (e[2] + e[3]);
+            psum1 += (e[4] + e[5]) + (e[6] + e[7]);
+  #pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              __half2 h = __floats2half2_rn(e[2 * q], e[2 * q + 1]);
+              pk[g * 4 + q] = *reinterpret_cast<uint32_t*>(&h);
+            }
+          }
+          tc::tmem_st32(tp + c * 32, pk);
+        }
+      } else {
+        // Software-pipelined: the exponentials of block b+1 (16 keys, in place over the S registers) are issued before
+        // block b is summed and packed, so no MUFU result is consumed right behind its issue.
+        auto exp_block = [&](int b) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const float t = fmaf(__uint_as_float(s[b * 16 + q]), sc, neg_m);
+            s[b * 16 + q] = __float_as_uint(kVariant == 2 ? ex2_v(t) : ex2(t));
+          }
+        };
+        exp_block(0);
         uint32_t pk[32];
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          float e[8];
+        for (int b = 0; b < 8; ++b) {
+          if (b + 1 < 8) exp_block(b + 1);
+          const float* e = reinterpret_cast<const float*>(s) + b * 16;
+          psum0 += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[8] + e[9]) + (e[10] + e[11]));
+          psum1 += ((e[4] + e[5]) + (e[6] + e[7])) + ((e[12] + e[13]) + (e[14] + e[15]));
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float t = fmaf(__uint_as_float(s[c * 64 + g * 8 + q]), sc, neg_m);
-            e[q] = (kPolyEvery > 0 && (q % kPolyEvery) == kPolyEvery - 1) ? ex2_poly(t) : ex2(t);
-          }
-          psum0 += (e[0] + e[1]) + (e[2] + e[3]);
-          psum1 += (e[4] + e[5]) + (e[6] + e[7]);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
             __half2 h = __floats2half2_rn(e[2 * q], e[2 * q + 1]);
-            pk[g * 4 + q] = *reinterpret_cast<uint32_t*>(&h);
+            pk[(b & 3) * 8 + q] = *reinterpret_cast<uint32_t*>(&h);
           }
+          if ((b & 3) == 3) tc::tmem_st32(tp + (b >> 2) * 32, pk);
         }
-        tc::tmem_st32(tp + c * 32, pk);
       }
       named_arrive(2 - x, 256);          // hand the turn to the other warpgroup
       tc::tmem_st_wait();
@@ -311,7 +352,9 @@ extern "C" int sgn_attention_f16(const void* d_q, int64_t ldq, const void* d_k, 
                   reinterpret_cast<uintptr_t>(d_out)) & 15) == 0, "operands must be 16-byte aligned");
   static bool attr_set = false;
   if (!attr_set) {
-    SGN_CUDA(cudaFuncSetAttribute(k_attention_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
+    SGN_CUDA(cudaFuncSetAttribute(k_attention_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
+    SGN_CUDA(cudaFuncSetAttribute(k_attention_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
+    SGN_CUDA(cudaFuncSetAttribute(k_attention_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
     attr_set = true;
   }
   CUtensorMap tmQ, tmK, tmV;
@@ -332,7 +375,9 @@ extern "C" int sgn_attention_f16(const void* d_q, int64_t ldq, const void* d_k, 
   p.out = reinterpret_cast<__half*>(d_out);
   p.ldo = ldo;
   dim3 grid((T_q + kQPerCta - 1) / kQPerCta, heads, B);
-  k_attention_tc<<<grid, kAttnThreads, kAttnSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
+  p.idle_ns = g_attn_idle_ns;
+  auto kern = g_attn_variant == 1 ? k_attention_tc<1> : g_attn_variant == 2 ? k_attention_tc<2> : k_attention_tc<0>;
+  kern<<<grid, kAttnThreads, kAttnSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
   SGN_LAUNCH_CHECK();
   return SGN_OK;
 }

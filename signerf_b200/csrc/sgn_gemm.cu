@@ -76,8 +76,10 @@ template <int kCluster> struct GemmCfg {
 };
 // pair shape: 6 stages (192 KB) by default; 5 stages (160 KB) measure the same in isolation and leave room for a small
 // co-resident CTA (sgn_set_option "gemm_pair_stages")
+constexpr int kEpiWarps = 8;
+constexpr int kEpiStage = 32 * 32 * 4;    // one 32-row x 32-column fp32 chunk per epilogue warp (transpose staging)
 constexpr size_t gemm_smem_bytes(int cluster, int stages) {
-  return 1024 + (size_t)stages * (kStageA + (256 / cluster) * kBK * 2) + 256;
+  return 1024 + (size_t)stages * (kStageA + (256 / cluster) * kBK * 2) + kEpiWarps * kEpiStage + 256;
 }
 int g_pair_stages = 6;
 constexpr int kAccStride = 256;           // TMEM columns between the two accumulator buffers
@@ -96,15 +98,14 @@ struct GemmParams {
   long long ldo;
   int out_f16, geglu, nchw, act_silu;
   int res_prefetch;  // 0: fetch the residual inside the epilogue (A/B knob SGN_GEMM_RES_PREFETCH=0)
+  int coalesced;     // 1: 32-column chunks go through the shared-memory transpose (row-contiguous global accesses)
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
 
 // One 16-column group of one output row.
-// `rpre`: the residual of these 16 columns already in registers (prefetched while the MMAs / the TMEM load were in
-// flight), or nullptr to fetch it here.
-__device__ __forceinline__ void epilogue16(const GemmParams& p, const uint32_t* acc, long long m, int b, int n0,
-                                           const float4* rpre = nullptr) {
+// Row-per-thread path: ragged / NCHW chunks, 16-column tails, and everything when `coalesced` is off.
+__device__ __forceinline__ void epilogue16(const GemmParams& p, const uint32_t* acc, long long m, int b, int n0) {
   float v[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
@@ -138,7 +139,7 @@ __device__ __forceinline__ void epilogue16(const GemmParams& p, const uint32_t* 
       const float4* rp = reinterpret_cast<const float4*>(p.residual + m * p.ldo + n0);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        float4 t = rpre ? rpre[q] : rp[q];
+        float4 t = rp[q];
         v[4 * q] += t.x, v[4 * q + 1] += t.y, v[4 * q + 2] += t.z, v[4 * q + 3] += t.w;
       }
     }
@@ -182,15 +183,32 @@ __device__ __forceinline__ void epilogue16(const GemmParams& p, const uint32_t* 
   }
 }
 
-template <int kCluster, int kStages>
+// Cold path kept out of line (it would otherwise cost the hot epilogue its registers): re-reads `ncols` (16 or 32)
+// accumulator columns of this warp's lane quarter from TMEM and stores them row-per-thread.  Warp-collective.
+__device__ __noinline__ void epilogue_rows(const GemmParams& p, uint32_t taddr, int ncols, long long m, int b, int n0,
+                                           bool valid) {
+  for (int c = 0; c < ncols; c += 16) {
+    uint32_t acc[16];
+    tc::tmem_ld16(taddr + c, acc);
+    tc::tmem_ld_wait();
+    if (valid) epilogue16(p, acc, m, b, n0 + c);
+  }
+}
+
+// kEpi specialises the hot (coalesced) epilogue at compile time; the instruction footprint of the generic one
+// (erff-based GEGLU, SiLU, fp16 / fp32 stores all resident) misses the instruction cache with only 8 epilogue warps.
+//   0 generic (runtime flags)   1 fp32 output (+bias, +rowbias, +residual)   2 fp16 output (+bias)   3 GEGLU
+template <int kCluster, int kStages, int kEpi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+          const __grid_constant__ GemmParams p) {
   constexpr int kStageB = GemmCfg<kCluster>::kStageB;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + kStages * kStageA;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + kStages * kStageB);
+  uint8_t* sEpi = sB + kStages * kStageB;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sEpi + kEpiWarps * kEpiStage);
   uint64_t* empty = full + kStages;
   uint64_t* tfull = empty + kStages;
   uint64_t* tempty = tfull + 2;
@@ -301,22 +319,68 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int lane_base = (warp & 3) * 32;
     const int row = lane_base + lane;
     const int col_half = (warp - 2) >> 2;
+    // The in-place fp32 residual is the one operand that is not TMA-staged: its loads are latency x registers bound
+    // (8 float4 per thread in flight), so every thread asks L2 for the residual segment of its NEXT tile before it
+    // starts on the current one; by the time those loads are issued the lines are L2 hits.
+    auto l2_prefetch_tile = [&](int t) {
+      if (!p.res_prefetch || p.residual == nullptr || p.nchw || p.geglu || t >= total_tiles) return;
+      const int m_group = t / p.num_n_tiles, n_tile = t - m_group * p.num_n_tiles;
+      const int m_tile = m_group * kCluster + (int)cta_rank;
+      long long m;
+      if (p.conv) {
+        const int b = m_tile / tiles_per_img;
+        const int r = m_tile - b * tiles_per_img;
+        const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+        const int y = ty * kConvTileH + row / kConvTileW, x = tx * kConvTileW + row % kConvTileW;
+        if (!(y < p.H && x < p.W && m_tile < p.num_m_tiles)) return;
+        m = ((long long)b * p.H + y) * p.W + x;
+      } else {
+        m = (long long)m_tile * kBM + row;
+        if (m >= p.M) return;
+      }
+      const int n_base = n_tile * p.block_n;
+      for (int c = col_half * 32; c < p.block_n && n_base + c < p.n_valid; c += 64)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.residual + m * p.ldo + n_base + c));
+    };
+    l2_prefetch_tile(first_tile);
+    // Coalesced path: a 32 x 32 chunk (thread = accumulator row out of TMEM) is transposed through a 4 KB swizzled
+    // shared-memory patch so that 8 lanes cover 128 contiguous bytes of one output row: every global residual load /
+    // output store instruction then touches 4 full lines instead of 32 partial ones (the row-per-thread pattern costs
+    // 8x the L1 wavefronts, which bounded the short-K GEMMs of the transformer blocks).
+    float4* patch = reinterpret_cast<float4*>(sEpi + (warp - 2) * kEpiStage);   // [32 rows][8 float4], slot ^ (row & 7)
+    const int cq = lane & 7, rsub = lane >> 3;
     int i = 0;
     for (int t = first_tile; t < total_tiles; t += tile_step, ++i) {
+      l2_prefetch_tile(t + tile_step);
       const int buf = i & 1;
       const uint32_t ph = (i >> 1) & 1;
       const int m_group = t / p.num_n_tiles, n_tile = t - m_group * p.num_n_tiles;
       const int m_tile = m_group * kCluster + (int)cta_rank;
+      int tb = 0, ty0 = 0, tx0 = 0;
+      if (p.conv) {
+        tb = m_tile / tiles_per_img;
+        int r = m_tile - tb * tiles_per_img;
+        int ty = r / p.tiles_x;
+        ty0 = ty * kConvTileH, tx0 = (r - ty * p.tiles_x) * kConvTileW;
+      }
+      // Output row of patch row (q*4 + rsub) of this warp's lane quarter: m_q = m_base + (q>>2)*step_hi + (q&3)*4
+      // (linear: consecutive rows, step_hi = 16; conv: the tile is 8 image rows x 16 pixels, step_hi = W).
+      const bool tile_ok = m_tile < p.num_m_tiles;
+      const int ybase = ty0 + lane_base / kConvTileW, xbase = tx0 + rsub;
+      const long long m_base = p.conv ? ((long long)tb * p.H + ybase) * p.W + xbase : (long long)m_tile * kBM + lane_base + rsub;
+      const int step_hi = p.conv ? p.W : 16;
+      auto row_q = [&](int q, long long& m_out) -> bool {
+        m_out = m_base + (q >> 2) * step_hi + (q & 3) * 4;
+        return p.conv ? (tile_ok && ybase + (q >> 2) < p.H && xbase + (q & 3) * 4 < p.W) : (m_out < p.M);
+      };
       long long m;
-      int b;
+      int b = 0;
       bool valid;
       if (p.conv) {
-        b = m_tile / tiles_per_img;
-        int r = m_tile - b * tiles_per_img;
-        int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-        int y = ty * kConvTileH + row / kConvTileW, x = tx * kConvTileW + row % kConvTileW;
-        valid = y < p.H && x < p.W && m_tile < p.num_m_tiles;
-        m = ((long long)b * p.H + y) * p.W + x;
+        const int y = ty0 + row / kConvTileW, x = tx0 + row % kConvTileW;
+        valid = y < p.H && x < p.W && tile_ok;
+        m = ((long long)tb * p.H + y) * p.W + x;
+        b = tb;
       } else {
         m = (long long)m_tile * kBM + row;
         valid = m < p.M;
@@ -325,41 +389,87 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       const int n_base = n_tile * p.block_n;
       // the two warps of a lane quarter split the tile's columns in 32-wide chunks: even chunks / odd chunks
       int c0 = col_half * 32;
+      auto chunk_fast = [&](int c) -> bool { return p.coalesced && c + 32 <= p.block_n && n_base + c + 32 <= p.n_valid; };
       // The fp32 residual (the stream the UNet keeps adding into) is the epilogue's only global read: the first chunk's
       // is fetched before the accumulator is even complete, the next chunk's while the current one is processed.
-      const bool res_pre = p.res_prefetch && p.residual != nullptr && !p.nchw && !p.geglu && valid;
-      float4 rcur[8], rnext[8];
+      const bool res_pre = p.res_prefetch && p.residual != nullptr && !p.geglu;
+      // one residual buffer: a second one (next chunk in flight during this chunk's stores) spills, and with 230 KB of
+      // shared memory there is no L1 left to catch spills (measured: 38.6 vs 34.3 us on 8192x1280x1280)
+      float4 rcur[8];
       auto prefetch = [&](int c, float4 (&r)[8]) -> bool {
-        const int n0 = n_base + c;
-        if (!res_pre || c + 32 > p.block_n || n0 + 32 > p.n_valid) return false;
-        const float4* rp = reinterpret_cast<const float4*>(p.residual + m * p.ldo + n0);
+        if (!res_pre || !chunk_fast(c)) return false;
+        const int n0 = n_base + c + cq * 4;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) r[q] = rp[q];
+        for (int q = 0; q < 8; ++q) {
+          long long mq;
+          r[q] = row_q(q, mq) ? *reinterpret_cast<const float4*>(p.residual + mq * p.ldo + n0) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         return true;
       };
-      bool cur_ok = prefetch(c0, rcur);
+      bool cur_ok = prefetch(c0, rcur);   // first chunk: in flight while the tile's last MMAs complete
       tc::mbar_wait(&tfull[buf], ph);
       tc::tc_fence_after();
       const uint32_t taddr = tmem_base + buf * kAccStride + ((uint32_t)lane_base << 16);
+      if (p.coalesced == 2) c0 = p.block_n;   // debug (SGN_GEMM_COALESCED=2): no epilogue work, main loop only
       for (; c0 + 32 <= p.block_n; c0 += 64) {
+        if (!chunk_fast(c0)) {
+          epilogue_rows(p, taddr + c0, 32, m, b, n_base + c0, valid);
+          cur_ok = prefetch(c0 + 64, rcur);
+          continue;
+        }
         uint32_t acc[32];
         tc::tmem_ld32(taddr + c0, acc);
-        const bool next_ok = prefetch(c0 + 64, rnext);
         tc::tmem_ld_wait();
-        if (valid) {
-          epilogue16(p, acc, m, b, n_base + c0, cur_ok ? rcur : nullptr);
-          epilogue16(p, acc + 16, m, b, n_base + c0 + 16, cur_ok ? rcur + 4 : nullptr);
-        }
 #pragma unroll
-        for (int q = 0; q < 8; ++q) rcur[q] = rnext[q];
-        cur_ok = next_ok;
+        for (int q = 0; q < 8; ++q)   // row `lane` of the patch, float4 slot q at swizzled position q ^ (lane & 7)
+          patch[lane * 8 + (q ^ (lane & 7))] = make_float4(__uint_as_float(acc[4 * q]), __uint_as_float(acc[4 * q + 1]),
+                                                            __uint_as_float(acc[4 * q + 2]), __uint_as_float(acc[4 * q + 3]));
+        __syncwarp();
+        const bool e_rowbias = kEpi != 3 && p.rowbias != nullptr;
+        const bool e_geglu = kEpi == 3 || (kEpi == 0 && p.geglu);
+        const bool e_res = (kEpi == 0 || kEpi == 1) && p.residual != nullptr;
+        const bool e_silu = kEpi == 0 && p.act_silu;
+        const bool e_f16 = kEpi == 2 || (kEpi == 0 && p.out_f16);
+        const int n0 = n_base + c0 + cq * 4;
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0));
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int rr = q * 4 + rsub;
+          float4 v = patch[rr * 8 + (cq ^ (rr & 7))];
+          long long mq;
+          if (!row_q(q, mq)) continue;
+          v.x += bias4.x, v.y += bias4.y, v.z += bias4.z, v.w += bias4.w;
+          if (e_rowbias) {
+            const int bq = p.conv ? tb : (int)(mq / p.rows_per_batch);
+            const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.rowbias + (size_t)bq * p.n_valid + n0));
+            v.x += t4.x, v.y += t4.y, v.z += t4.z, v.w += t4.w;
+          }
+          if (e_geglu) {  // (value, gate) pairs -> 2 outputs
+            const __half2 h = __floats2half2_rn(v.x * gelu_erf(v.y), v.z * gelu_erf(v.w));
+            *reinterpret_cast<__half2*>(reinterpret_cast<__half*>(p.out) + mq * p.ldo + (n0 >> 1)) = h;
+            continue;
+          }
+          if (e_res) {
+            const float4 t4 = cur_ok ? rcur[q] : *reinterpret_cast<const float4*>(p.residual + mq * p.ldo + n0);
+            v.x += t4.x, v.y += t4.y, v.z += t4.z, v.w += t4.w;
+          }
+          if (e_silu) {
+            v.x = v.x / (1.f + __expf(-v.x)), v.y = v.y / (1.f + __expf(-v.y));
+            v.z = v.z / (1.f + __expf(-v.z)), v.w = v.w / (1.f + __expf(-v.w));
+          }
+          if (e_f16) {
+            __half2 h[2] = {__floats2half2_rn(v.x, v.y), __floats2half2_rn(v.z, v.w)};
+            *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + mq * p.ldo + n0) = *reinterpret_cast<uint2*>(h);
+          } else {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + mq * p.ldo + n0) = v;
+          }
+        }
+        __syncwarp();   // the patch is rewritten by the next chunk
+        cur_ok = prefetch(c0 + 64, rcur);   // L2 hits (l2_prefetch_tile), in flight across the next TMEM load + transpose
       }
-      if (c0 < p.block_n && c0 + 16 == p.block_n) {  // 16-column tail (block_n % 32 == 16) belongs to whoever reaches it
-        uint32_t acc[16];
-        tc::tmem_ld16(taddr + c0, acc);
-        tc::tmem_ld_wait();
-        if (valid) epilogue16(p, acc, m, b, n_base + c0);
-      }
+      if (c0 < p.block_n && c0 + 16 == p.block_n)  // 16-column tail (block_n % 32 == 16) belongs to whoever reaches it
+        epilogue_rows(p, taddr + c0, 16, m, b, n_base + c0, valid);
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -413,12 +523,12 @@ static int pick_cluster(const GemmParams& p) {
   return p.num_m_tiles >= 2 ? 2 : 1;
 }
 
-template <int kCluster, int kStages>
+template <int kCluster, int kStages, int kEpi>
 static int launch_gemm_c(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
   constexpr size_t smem = gemm_smem_bytes(kCluster, kStages);
   static bool attr_set = false;
   if (!attr_set) {
-    SGN_CUDA(cudaFuncSetAttribute(k_gemm_tc<kCluster, kStages>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SGN_CUDA(cudaFuncSetAttribute(k_gemm_tc<kCluster, kStages, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   const int groups = (p.num_m_tiles + kCluster - 1) / kCluster * p.num_n_tiles;
@@ -429,14 +539,21 @@ static int launch_gemm_c(const CUtensorMap& tmA, const CUtensorMap& tmB, const G
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kCluster, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr, cfg.numAttrs = 1;
-  SGN_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tc<kCluster, kStages>, tmA, tmB, p));
+  SGN_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tc<kCluster, kStages, kEpi>, tmA, tmB, p));
   SGN_LAUNCH_CHECK();
   return SGN_OK;
 }
 
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, int cluster, cudaStream_t st) {
-  if (cluster != 2) return launch_gemm_c<1, 4>(tmA, tmB, p, st);
-  return g_pair_stages == 5 ? launch_gemm_c<2, 5>(tmA, tmB, p, st) : launch_gemm_c<2, 6>(tmA, tmB, p, st);
+  if (cluster != 2) return launch_gemm_c<1, 4, 0>(tmA, tmB, p, st);
+  if (g_pair_stages == 5) return launch_gemm_c<2, 5, 0>(tmA, tmB, p, st);
+  static const int spec = [] { const char* e = getenv("SGN_GEMM_EPI_SPEC"); return e ? atoi(e) : 1; }();
+  if (spec && p.coalesced == 1 && !p.act_silu) {
+    if (p.geglu && !p.rowbias) return launch_gemm_c<2, 6, 3>(tmA, tmB, p, st);
+    if (p.out_f16 && !p.geglu && !p.residual) return launch_gemm_c<2, 6, 2>(tmA, tmB, p, st);
+    if (!p.out_f16 && !p.geglu) return launch_gemm_c<2, 6, 1>(tmA, tmB, p, st);
+  }
+  return launch_gemm_c<2, 6, 0>(tmA, tmB, p, st);
 }
 
 static int fill_epilogue(GemmParams& p, const SgnEpilogue* ep, int n_valid, void* d_out) {
@@ -450,9 +567,11 @@ static int fill_epilogue(GemmParams& p, const SgnEpilogue* ep, int n_valid, void
   p.act_silu = ep ? ep->act_silu : 0;
   static const int res_prefetch = [] { const char* e = getenv("SGN_GEMM_RES_PREFETCH"); return e ? atoi(e) : 1; }();
   p.res_prefetch = res_prefetch;
+  static const int coalesced = [] { const char* e = getenv("SGN_GEMM_COALESCED"); return e ? atoi(e) : 1; }();
   p.out = d_out;
   long long ld = ep ? ep->ldo : 0;
   p.ldo = ld > 0 ? ld : (p.geglu ? n_valid / 2 : n_valid);
+  p.coalesced = coalesced == 2 ? 2 : coalesced && !p.nchw && (p.ldo % ((p.out_f16 || p.geglu) ? 8 : 4)) == 0 && (n_valid % 4) == 0;
   SGN_CHECK_ARG(!p.rowbias || p.rows_per_batch > 0, "rowbias needs rows_per_batch");
   SGN_CHECK_ARG(!p.geglu || (n_valid % 16 == 0 && !p.residual && !p.nchw), "geglu needs N % 16 == 0 and no residual");
   SGN_CHECK_ARG(!p.nchw || !p.out_f16, "nchw output is fp32 only");

@@ -541,7 +541,7 @@ extern "C" int sgn_field_eval(const SgnField* f, const float* d_pos, const float
   return SGN_OK;
 }
 
-namespace sgn { extern int g_pair_stages; }
+namespace sgn { extern int g_pair_stages; extern int g_attn_variant; extern int g_attn_idle_ns; }
 
 extern "C" int sgn_set_option(const char* name, int value) {
   SGN_CHECK_ARG(name != nullptr, "null option name");
@@ -554,6 +554,16 @@ extern "C" int sgn_set_option(const char* name, int value) {
   if (n == "gemm_pair_stages") {
     SGN_CHECK_ARG(value == 5 || value == 6, "gemm_pair_stages must be 5 or 6");
     sgn::g_pair_stages = value;
+    return SGN_OK;
+  }
+  if (n == "attn_variant") {
+    SGN_CHECK_ARG(value >= 0 && value <= 2, "attn_variant must be 0..2");
+    sgn::g_attn_variant = value;
+    return SGN_OK;
+  }
+  if (n == "attn_idle_ns") {
+    SGN_CHECK_ARG(value >= 0 && value <= 1000, "attn_idle_ns must be 0..1000");
+    sgn::g_attn_idle_ns = value;
     return SGN_OK;
   }
   sgn::set_error("invalid argument: unknown option " + n);

@@ -17,6 +17,7 @@ from .ops import _ptr, _stream
 # bench.py brackets every C-ABI call with CUDA events (eager pass, outside the timed region) to split a step's device
 # time and algorithmic FLOPs by kernel family: the roofline numerators of the JSON line come from here.
 _PROFILE: Optional[dict] = None
+PROFILE_SHAPES = False   # scratch tooling: key GEMM / attention spans by shape
 
 
 def start_profile() -> None:
@@ -96,7 +97,7 @@ def gemm_f16(a: Tensor, w: Tensor, bias: Optional[Tensor] = None, *, rowbias: Op
     elif out.dtype != odt or tuple(out.shape) != oshape or not out.is_contiguous():
         raise ValueError("bad `out` tensor")
     e = _epilogue(bias, rowbias, rows_per_batch, residual, out_f16, geglu, False, act_silu=act_silu)
-    with torch.cuda.device(a.device), _span("k_gemm_tc (linear)", 2.0 * M * N * K):
+    with torch.cuda.device(a.device), _span(f"k_gemm_tc (linear) {M}x{N}x{K}{' geglu' if geglu else ''}{' res' if residual is not None else ''}{' f16' if out_f16 else ''}" if PROFILE_SHAPES else "k_gemm_tc (linear)", 2.0 * M * N * K):
         _lib.check(_lib.load().sgn_gemm_f16(_ptr(a), K, _ptr(w), K, M, N, K, C.byref(e), _ptr(out), _stream(a.device)))
     return out
 
@@ -118,7 +119,7 @@ def conv3x3_f16(x: Tensor, w: Tensor, bias: Optional[Tensor] = None, *, rowbias:
     elif out.dtype != odt or tuple(out.shape) != oshape or not out.is_contiguous():
         raise ValueError("bad `out` tensor")
     e = _epilogue(bias, rowbias, H * W if rowbias is not None else 0, residual, out_f16, False, nchw)
-    with torch.cuda.device(x.device), _span("k_gemm_tc (conv3x3)", 2.0 * B * H * W * N * 9 * Cin):
+    with torch.cuda.device(x.device), _span(f"k_gemm_tc (conv3x3) {B}x{H}x{W}x{Cin}->{N}" if PROFILE_SHAPES else "k_gemm_tc (conv3x3)", 2.0 * B * H * W * N * 9 * Cin):
         _lib.check(_lib.load().sgn_conv3x3_f16(_ptr(x), _ptr(w), B, H, W, Cin, N, C.byref(e), _ptr(out),
                                                _stream(x.device)))
     return out
@@ -133,7 +134,7 @@ def attention_f16(q: Tensor, k: Tensor, v: Tensor, batch: int, heads: int, out: 
     Tq, Tkv = q.shape[0] // batch, k.shape[0] // batch
     if out is None:
         out = torch.empty((q.shape[0], heads * 64), dtype=torch.float16, device=q.device)
-    with torch.cuda.device(q.device), _span("k_attention_tc", 4.0 * batch * heads * Tq * Tkv * 64):
+    with torch.cuda.device(q.device), _span(f"k_attention_tc {batch}x{heads}x{Tq}x{Tkv}" if PROFILE_SHAPES else "k_attention_tc", 4.0 * batch * heads * Tq * Tkv * 64):
         _lib.check(_lib.load().sgn_attention_f16(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0),
                                                  batch, heads, Tq, Tkv, 0.125, _ptr(out), out.stride(0),
                                                  _stream(q.device)))
