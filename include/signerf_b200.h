@@ -275,6 +275,49 @@ int sgn_sheet_to_conditioning(const float* d_cond, const float* d_mask, int Hs, 
 int sgn_im2col3x3_split_f16(const float* d_x, int in_nchw, int B, int H, int W, int C, int stride, void* d_out,
                             void* stream);
 
+/* ------------------------------------------------------------------ VAE + A1111 inpaint pre / post */
+/* What the A1111 server does around the denoising loop for the request of signerf/diffuser/diffuser.py:132-169
+ * (mask_blur 4, inpainting_fill 1, inpaint_full_res 0; A1111 modules/processing.py StableDiffusionProcessingImg2Img.init,
+ * decode_latent_batch, apply_overlay).  The autoencoder's convolutions / linears run on sgn_conv3x3_f16 / sgn_gemm_f16;
+ * signerf_b200/vae.py walks the ldm Encoder / Decoder graphs.  The integer image operators are bit-exact against
+ * cv2 4.13 / Pillow 12.2, which is where A1111 gets them from (tests/golden/inpaint.npz). */
+
+/* ldm Downsample (`F.pad(x, (0,1,0,1)); Conv2d(3, stride 2, padding 0)`): im2col of fp32 NHWC [B,H,W,C] ->
+ * fp16 [B*Ho*Wo, 9*C], Ho = (H-2)/2 + 1, input pixel (2oy+ky, 2ox+kx), zero beyond the bottom / right edge. */
+int sgn_im2col3x3_s2_asym_f16(const float* d_x, int B, int H, int W, int C, void* d_out, void* stream);
+/* ldm AttnBlock: out[m][:] = softmax(scale * scores[m][:]) as fp16; scores fp32 [M,N] (N % 4 == 0) from sgn_gemm_f16. */
+int sgn_softmax_rows_f16(const float* d_scores, int64_t M, int N, float scale, void* d_out, void* stream);
+/* quant_conv / post_quant_conv: 1x1 convolution over <= 16 channels, NCHW fp32; h_w [Cout,Cin], h_bias [Cout] on the
+ * HOST (they travel as kernel parameters); the input is multiplied by in_scale first (decode: 1 / scale_factor). */
+int sgn_pointwise_nchw(const float* d_x, const float* h_w, const float* h_bias, int B, int Cin, int Cout, int64_t HW,
+                       float in_scale, float* d_out, void* stream);
+/* DiagonalGaussianDistribution: d_moments [B,2Z,HW] = (mean | logvar); out [B,Z,HW] = scale * (mean + exp(0.5 *
+ * clamp(logvar,-30,20)) * noise); d_noise NULL = the mode. */
+int sgn_vae_sample_latent(const float* d_moments, const float* d_noise, int B, int Z, int64_t HW, float scale,
+                          float* d_out, void* stream);
+/* uint8 HWC [H,W,3] -> fp32 NCHW [1,3,H,W] = 2 * (v / 255) - 1, and back: uint8(255 * clamp((x + 1) / 2, 0, 1)). */
+int sgn_u8_to_vae_input(const uint8_t* d_img, int H, int W, float* d_out, void* stream);
+int sgn_vae_output_to_u8(const float* d_x, int H, int W, uint8_t* d_out, void* stream);
+
+/* cv2.GaussianBlur(src, (ksize,1) | (1,ksize), sigma) on CV_8U with BORDER_REFLECT_101, bit-exact: OpenCV's Q8 taps
+ * (error diffusion towards the centre, sum exactly 256), result (sum + 128) >> 8.  ksize odd, <= 63. */
+int sgn_gaussian_blur_u8(const uint8_t* d_in, int H, int W, int ksize, double sigma, int horizontal, uint8_t* d_out,
+                         void* stream);
+/* The ksize Q8 taps sgn_gaussian_blur_u8 uses (host-side probe for the parity tests). */
+int sgn_gaussian_kernel_q8(int ksize, double sigma, int* h_taps);
+/* PIL.Image.resize((w,h), BICUBIC) of one 8-bit band, bit-exact (Pillow Resample.c: 22-bit fixed-point taps, horizontal
+ * pass through uint8, then vertical).  d_ws: sgn_pil_resize_ws_bytes(H,W,h,w) bytes of device scratch. */
+int64_t sgn_pil_resize_ws_bytes(int H, int W, int h, int w);
+int sgn_pil_resize_bicubic_u8(const uint8_t* d_in, int H, int W, int h, int w, void* d_ws, uint8_t* d_out, void* stream);
+/* mask_for_overlay = clip(2 * blurred, 0, 255). */
+int sgn_inpaint_overlay_mask_u8(const uint8_t* d_blurred, int64_t n, uint8_t* d_overlay, void* stream);
+/* keep[i] = 1 - round(lat_u8[i] / 255): A1111's `mask = 1 - latmask`, the d_mask of sgn_cfg_euler_step. */
+int sgn_latent_keep_mask(const uint8_t* d_lat_u8, int64_t n, float* d_keep, void* stream);
+/* apply_overlay: PIL paste of the original through the inverted overlay mask + alpha_composite onto the generated image
+ * (Pillow's integer arithmetic); uint8 HWC in, uint8 HWC and / or fp32 HWC (= image_to_tensor: v / 255) out. */
+int sgn_overlay_composite_u8(const uint8_t* d_generated, const uint8_t* d_original, const uint8_t* d_overlay_mask, int H,
+                             int W, uint8_t* d_out_u8, float* d_out_f32, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

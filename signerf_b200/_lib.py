@@ -102,6 +102,19 @@ SIGNATURES = {
     "sgn_scale_repeat_f32": (_i, [_vp, _i64, _f, _i, _vp, _vp]),
     "sgn_sheet_to_conditioning": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "sgn_cfg_euler_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _f, _vp, _vp, _vp]),
+    "sgn_im2col3x3_s2_asym_f16": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "sgn_softmax_rows_f16": (_i, [_vp, _i64, _i, _f, _vp, _vp]),
+    "sgn_pointwise_nchw": (_i, [_vp, C.POINTER(_f), C.POINTER(_f), _i, _i, _i, _i64, _f, _vp, _vp]),
+    "sgn_vae_sample_latent": (_i, [_vp, _vp, _i, _i, _i64, _f, _vp, _vp]),
+    "sgn_u8_to_vae_input": (_i, [_vp, _i, _i, _vp, _vp]),
+    "sgn_vae_output_to_u8": (_i, [_vp, _i, _i, _vp, _vp]),
+    "sgn_gaussian_blur_u8": (_i, [_vp, _i, _i, _i, C.c_double, _i, _vp, _vp]),
+    "sgn_gaussian_kernel_q8": (_i, [_i, C.c_double, C.POINTER(_i)]),
+    "sgn_pil_resize_ws_bytes": (_i64, [_i, _i, _i, _i]),
+    "sgn_pil_resize_bicubic_u8": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "sgn_inpaint_overlay_mask_u8": (_i, [_vp, _i64, _vp, _vp]),
+    "sgn_latent_keep_mask": (_i, [_vp, _i64, _vp, _vp]),
+    "sgn_overlay_composite_u8": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -520,7 +520,7 @@ __global__ void k_hint_latmask(const float* __restrict__ cond, const float* __re
                                float* lat_mask) {
   const size_t n = (size_t)Hs * Ws;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const float q = (float)(unsigned char)(int)(__ldg(cond + i) * 255.f) * (1.f / 255.f);
+    const float q = (float)(unsigned char)(int)(__ldg(cond + i) * 255.f) * (1.f / 255.f);   // torch CUDA `x / 255.0` = x * (1/255)
     hint[i] = q, hint[n + i] = q, hint[2 * n + i] = q;
     const int h8 = Hs >> 3, w8 = Ws >> 3;
     if (i < (size_t)h8 * w8) {

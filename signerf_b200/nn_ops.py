@@ -83,9 +83,13 @@ def _epilogue(bias, rowbias, rows_per_batch, residual, out_f16, geglu, nchw, ldo
 def gemm_f16(a: Tensor, w: Tensor, bias: Optional[Tensor] = None, *, rowbias: Optional[Tensor] = None,
              rows_per_batch: int = 0, residual: Optional[Tensor] = None, out_f16: bool = False, geglu: bool = False,
              act_silu: bool = False, out: Optional[Tensor] = None) -> Tensor:
-    """out[M,N] = a[M,K] @ w[N,K]^T + bias (+ rowbias[m // rows_per_batch]) (+ residual); geglu: [M, N/2] fp16."""
-    _chk(a, torch.float16, "a")
-    _chk(w, torch.float16, "w")
+    """out[M,N] = a[M,K] @ w[N,K]^T + bias (+ rowbias[m // rows_per_batch]) (+ residual); geglu: [M, N/2] fp16.
+    a / w may be column-slice views of wider matrices (unit column stride, row stride a multiple of 8)."""
+    for t, n in ((a, "a"), (w, "w")):
+        if not t.is_cuda:
+            raise RuntimeError(f"{n} must be a CUDA tensor (signerf_b200 has no CPU path)")
+        if t.dtype != torch.float16 or t.dim() != 2 or t.stride(1) != 1 or t.stride(0) % 8 != 0:
+            raise ValueError(f"{n} must be an fp16 matrix with unit column stride and a row stride that is a multiple of 8")
     M, K = a.shape
     N = w.shape[0]
     if w.shape[1] != K:
@@ -98,7 +102,8 @@ def gemm_f16(a: Tensor, w: Tensor, bias: Optional[Tensor] = None, *, rowbias: Op
         raise ValueError("bad `out` tensor")
     e = _epilogue(bias, rowbias, rows_per_batch, residual, out_f16, geglu, False, act_silu=act_silu)
     with torch.cuda.device(a.device), _span(f"k_gemm_tc (linear) {M}x{N}x{K}{' geglu' if geglu else ''}{' res' if residual is not None else ''}{' f16' if out_f16 else ''}" if PROFILE_SHAPES else "k_gemm_tc (linear)", 2.0 * M * N * K):
-        _lib.check(_lib.load().sgn_gemm_f16(_ptr(a), K, _ptr(w), K, M, N, K, C.byref(e), _ptr(out), _stream(a.device)))
+        _lib.check(_lib.load().sgn_gemm_f16(_ptr(a), a.stride(0), _ptr(w), w.stride(0), M, N, K, C.byref(e), _ptr(out),
+                                            _stream(a.device)))
     return out
 
 

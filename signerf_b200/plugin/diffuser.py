@@ -10,8 +10,6 @@ from typing import Callable, List, Literal, Optional, Type
 import torch
 from torch import Tensor
 
-from .. import nn_ops as K
-from .. import ops
 from ..unet import SDXLDenoiserB200, img2img_sigmas
 from .base import InstantiateConfig
 
@@ -44,7 +42,8 @@ class InProcessSDXL:
     """The A1111 img2img request of diffuser.py:132-169 executed in-process on latents:
     t_enc = int(min(strength, 0.999) * steps) Euler-ancestral steps with CFG, ControlNet (weight, Balanced,
     guidance 0..1) and the inpaint blend.  Prompt conditioning (context [2,77,2048], y [2,2816]: cond then uncond) comes
-    from the caller — the CLIP text encoders and the VAE are §8(f) row 1; `codec` plugs a VAE in when there is one."""
+    from the caller (the CLIP text encoders run once per prompt and are not on the path); `codec` is the
+    signerf_b200.inpaint.A1111InpaintCodec (VAE + mask blur + latent mask + overlay) around the latent loop."""
 
     def __init__(self, denoiser: SDXLDenoiserB200, context: Tensor, y: Tensor,
                  codec: Optional[object] = None):
@@ -100,18 +99,14 @@ class Diffuser:
         """Sheet RGB [H,W,3] + mask [H,W,1] + condition [H,W,1] -> edited sheet [H,W,3] in [0,1]."""
         if self.backend is None:
             raise RuntimeError("Diffuser(mode='custom') needs an InProcessSDXL backend: call diffuser.attach(...)")
-        if self.backend.codec is None:
-            raise RuntimeError("no latent codec attached: the SDXL VAE is a §8(f) 'next' row — attach a codec object with "
-                               "encode(image[H,W,3]) -> latent[1,4,H/8,W/8] and decode(latent) -> image[H,W,3]")
-        H, W = original_image.shape[0], original_image.shape[1]
+        codec = self.backend.codec
+        if codec is None:
+            raise RuntimeError("no latent codec attached: build signerf_b200.inpaint.A1111InpaintCodec(VAEB200(...)) and pass "
+                               "it to InProcessSDXL(codec=...)")
         dev = self.backend.net.dev
-        img = ops.quantize_u8(original_image.to(dev)).float() / 255.0          # tensor_to_image truncation (diffuser.py:121)
-        mask = mask_image.to(dev).float() if mask_image is not None else torch.ones((H, W, 1), device=dev)
-        cond = condition_image.to(dev).float() if condition_image is not None else torch.zeros((H, W, 1), device=dev)
-        hint = torch.empty((1, 3, H, W), dtype=torch.float32, device=dev)
-        lat_mask = torch.empty((1, 1, H // 8, W // 8), dtype=torch.float32, device=dev)
-        K.make_hint_and_latent_mask(cond.contiguous(), mask.contiguous(), hint, lat_mask)
-        init = self.backend.codec.encode(img)
-        x = self.backend.denoise_latents(init, hint, lat_mask, self.num_inference_steps, self.denoising_strength,
-                                         self.guidance_scale, self.controlnet_conditioning_scale, self.seed)
-        return self.backend.codec.decode(x)
+        st = codec.prepare(original_image.to(dev, torch.float32), None if mask_image is None else mask_image.to(dev, torch.float32),
+                           None if condition_image is None else condition_image.to(dev, torch.float32))
+        x = self.backend.denoise_latents(st.init_latent, st.hint, st.keep_mask, self.num_inference_steps,
+                                         self.denoising_strength, self.guidance_scale, self.controlnet_conditioning_scale,
+                                         self.seed)
+        return codec.finish(x, st)

@@ -90,3 +90,52 @@ def test_cascade_runs_and_is_deterministic():
     a = R.render_rays(m, o, d, "cascade")
     b = R.render_rays(m, o, d, "cascade")
     assert torch.equal(a["rgb"], b["rgb"]) and torch.equal(a["depth"], b["depth"])
+
+
+# ---------------------------------------------------------------------------------------------- A1111 inpaint pre / post
+def test_inpaint_oracle_matches_cv2_and_pillow(golden_dir):
+    """oracle/inpaint_ref.py bit for bit against cv2.GaussianBlur / PIL resize / paste / alpha_composite outputs
+    (tests/golden/make_inpaint_golden.py): mask blur, overlay mask, latent mask, overlay compositing."""
+    from oracle import inpaint_ref as I
+    g = np.load(os.path.join(golden_dir, "inpaint.npz"))
+    for ci in range(4):
+        m = g[f"c{ci}_mask"]
+        for blur in (4, 2):
+            ks = 2 * int(2.5 * blur + 0.5) + 1
+            bx = I.gaussian_blur_u8_1d(m, ks, float(blur), 1)
+            assert np.array_equal(bx, g[f"c{ci}_blur{blur}_x"])
+            assert np.array_equal(I.gaussian_blur_u8_1d(bx, ks, float(blur), 0), g[f"c{ci}_blur{blur}_xy"])
+        blurred, overlay = I.a1111_mask_blur(m, 4)
+        assert np.array_equal(blurred, g[f"c{ci}_blur4_xy"]) and np.array_equal(overlay, g[f"c{ci}_overlay_mask"])
+        lat = g[f"c{ci}_lat_u8"]
+        assert np.array_equal(I.pil_resize_bicubic_u8(blurred, lat.shape), lat)
+        assert np.array_equal(I.a1111_latent_mask(blurred, lat.shape), g[f"c{ci}_latmask"])
+        assert np.array_equal(I.a1111_apply_overlay(g[f"c{ci}_gen"], g[f"c{ci}_orig"], overlay), g[f"c{ci}_composited"])
+    for ri in range(4):
+        assert np.array_equal(I.pil_resize_bicubic_u8(g[f"r{ri}_in"], g[f"r{ri}_out"].shape), g[f"r{ri}_out"])
+
+
+def test_gaussian_taps_sum_to_one_and_match_impulse(golden_dir):
+    from oracle import inpaint_ref as I
+    g = np.load(os.path.join(golden_dir, "inpaint.npz"))
+    assert I.gaussian_kernel_q8(21, 4.0).tolist() == [1, 2, 4, 5, 9, 11, 16, 19, 23, 25, 26, 25, 23, 19, 16, 11, 9, 5, 4, 2, 1]
+    for sigma, ks in ((4.0, 21), (2.0, 11), (1.5, 9)):
+        k = I.gaussian_kernel_q8(ks, sigma)
+        assert k.sum() == 256 and np.array_equal(k, k[::-1])
+        resp = g[f"impulse_s{sigma}_k{ks}"][0, 2 * ks - ks // 2: 2 * ks + ks // 2 + 1]
+        assert np.array_equal(resp, ((k * 255 + 128) >> 8).astype(np.uint8))
+
+
+def test_vae_oracle_shapes_and_parameter_count():
+    """oracle/vae_ref.py (parity unpinned): SDXL-VAE parameter count, /8 latent geometry, posterior sampling."""
+    from oracle import vae_ref as VR
+    assert sum(p.numel() for p in VR.AutoencoderKL().parameters()) == 83_653_863
+    m = VR.make_vae(VR.tiny_vae_config(), seed=0)
+    x = torch.rand(1, 3, 32, 48) * 2 - 1
+    mom = m.moments(x)
+    assert tuple(mom.shape) == (1, 8, 4, 6)
+    n = torch.randn(1, 4, 4, 6)
+    z0, z1 = m.encode(x), m.encode(x, n)
+    mean, logvar = mom.chunk(2, 1)
+    assert torch.allclose(z0, VR.SCALE_FACTOR * mean) and torch.allclose(z1, VR.SCALE_FACTOR * (mean + torch.exp(0.5 * logvar) * n))
+    assert tuple(m.decode(z0).shape) == (1, 3, 32, 48)
