@@ -20,6 +20,8 @@
 // case the warp multiplies its O rows by exp2(c (m_old - m_new)) through tcgen05.ld / tcgen05.st; otherwise P is taken
 // against the stale m (P <= 2^8, harmless in fp16 / fp32 accumulation).  O is read once, at the end.
 // Keys beyond T_kv (ragged last tile, 77-token context) are masked to -inf before the max.
+#include <algorithm>
+
 #include "sgn_common.cuh"
 #include "sgn_tc.cuh"
 
@@ -335,6 +337,139 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   }
 }
 
+
+// ------------------------------------------------------------------ short-context path (attn2: 77 prompt tokens)
+// With <= 80 keys a (image, head) has 10 KB of K and V: the tcgen05 kernel above spends its time on per-CTA set-up
+// (TMEM allocation, barrier init, one TMA round trip per tile) for a single key tile -- 36 us per launch at 8 192 x 1 280
+// where the bytes (Q in, O out) are worth 7 us.  This path is plain FlashAttention-2 on mma.sync: K / V of the head in
+// shared memory, 4 warps x 16 queries per tile, S and P in registers, several resident CTAs per SM to hide the loads.
+constexpr int kXaKv = 80;      // keys (padded; masked beyond T_kv)
+constexpr int kXaQ = 64;       // queries per tile (4 warps x 16)
+constexpr int kXaPitch = 72;   // halfs per shared-memory row: 144 B keeps ldmatrix conflict-free
+
+__device__ __forceinline__ void xa_mma(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void xa_ldsm_x4(uint32_t (&r)[4], const __half* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(tc::smem_u32(p)));
+}
+__device__ __forceinline__ void xa_ldsm_x2(uint32_t (&r)[2], const __half* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];\n" : "=r"(r[0]), "=r"(r[1]) : "r"(tc::smem_u32(p)));
+}
+__device__ __forceinline__ void xa_ldsm_x2_trans(uint32_t (&r)[2], const __half* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];\n" : "=r"(r[0]), "=r"(r[1]) : "r"(tc::smem_u32(p)));
+}
+__device__ __forceinline__ uint32_t xa_pack(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(128)
+k_cross_attention(const __half* __restrict__ q, long long ldq, const __half* __restrict__ k, long long ldk,
+                  const __half* __restrict__ v, long long ldv, int T_q, int T_kv, float scale_log2e,
+                  __half* __restrict__ out, long long ldo, int q_per_cta) {
+  __shared__ __align__(16) __half sK[kXaKv * kXaPitch];
+  __shared__ __align__(16) __half sV[kXaKv * kXaPitch];
+  __shared__ __align__(16) __half sQ[kXaQ * kXaPitch];
+  const int head = blockIdx.y, img = blockIdx.z;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  for (int c = tid; c < kXaKv * 8; c += 128) {
+    const int r = c >> 3, j = c & 7;
+    uint4 kv = zero, vv = zero;
+    if (r < T_kv) {
+      kv = *reinterpret_cast<const uint4*>(k + ((long long)img * T_kv + r) * ldk + head * kHeadDim + j * 8);
+      vv = *reinterpret_cast<const uint4*>(v + ((long long)img * T_kv + r) * ldv + head * kHeadDim + j * 8);
+    }
+    *reinterpret_cast<uint4*>(sK + r * kXaPitch + j * 8) = kv;
+    *reinterpret_cast<uint4*>(sV + r * kXaPitch + j * 8) = vv;
+  }
+  const int q_begin = blockIdx.x * q_per_cta;
+  const int q_end = min(T_q, q_begin + q_per_cta);
+  const int g = lane >> 2, col0 = (lane & 3) * 2;
+  for (int q0 = q_begin; q0 < q_end; q0 += kXaQ) {
+    __syncthreads();   // the previous tile's reads of sQ are done (first pass: nothing pending)
+    for (int c = tid; c < kXaQ * 8; c += 128) {
+      const int r = c >> 3, j = c & 7;
+      uint4 x = zero;
+      if (q0 + r < T_q) x = *reinterpret_cast<const uint4*>(q + ((long long)img * T_q + q0 + r) * ldq + head * kHeadDim + j * 8);
+      *reinterpret_cast<uint4*>(sQ + r * kXaPitch + j * 8) = x;
+    }
+    __syncthreads();
+    float s[kXaKv / 8][4];
+#pragma unroll
+    for (int nt = 0; nt < kXaKv / 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < kHeadDim / 16; ++kk) {
+      uint32_t a[4];
+      xa_ldsm_x4(a, sQ + (warp * 16 + (lane & 15)) * kXaPitch + kk * 16 + (lane >> 4) * 8);
+#pragma unroll
+      for (int nt = 0; nt < kXaKv / 8; ++nt) {
+        uint32_t b[2];
+        xa_ldsm_x2(b, sK + (nt * 8 + (lane & 7)) * kXaPitch + kk * 16 + ((lane >> 3) & 1) * 8);
+        xa_mma(s[nt], a, b);
+      }
+    }
+    // thread owns rows g and g + 8 of the warp's 16, columns nt*8 + col0 + {0,1}
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < kXaKv / 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (nt * 8 + col0 + (e & 1) >= T_kv) s[nt][e] = -INFINITY;
+      m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
+      m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    const float nm0 = -m0 * scale_log2e, nm1 = -m1 * scale_log2e;
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < kXaKv / 8; ++nt) {
+      s[nt][0] = ex2(fmaf(s[nt][0], scale_log2e, nm0));
+      s[nt][1] = ex2(fmaf(s[nt][1], scale_log2e, nm0));
+      s[nt][2] = ex2(fmaf(s[nt][2], scale_log2e, nm1));
+      s[nt][3] = ex2(fmaf(s[nt][3], scale_log2e, nm1));
+      l0 += s[nt][0] + s[nt][1];
+      l1 += s[nt][2] + s[nt][3];
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    float o[kHeadDim / 8][4];
+#pragma unroll
+    for (int nt = 0; nt < kHeadDim / 8; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < kXaKv / 16; ++kk) {   // P (registers) becomes the A operand: the C layout of two key tiles
+      uint32_t a[4] = {xa_pack(s[2 * kk][0], s[2 * kk][1]), xa_pack(s[2 * kk][2], s[2 * kk][3]),
+                       xa_pack(s[2 * kk + 1][0], s[2 * kk + 1][1]), xa_pack(s[2 * kk + 1][2], s[2 * kk + 1][3])};
+#pragma unroll
+      for (int nt = 0; nt < kHeadDim / 8; ++nt) {
+        uint32_t b[2];
+        xa_ldsm_x2_trans(b, sV + (kk * 16 + (lane & 15)) * kXaPitch + nt * 8);
+        xa_mma(o[nt], a, b);
+      }
+    }
+    const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+    const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+    __half* o0 = out + ((long long)img * T_q + r0) * ldo + head * kHeadDim + col0;
+    __half* o1 = out + ((long long)img * T_q + r1) * ldo + head * kHeadDim + col0;
+#pragma unroll
+    for (int nt = 0; nt < kHeadDim / 8; ++nt) {
+      if (r0 < T_q) *reinterpret_cast<uint32_t*>(o0 + nt * 8) = xa_pack(o[nt][0] * inv0, o[nt][1] * inv0);
+      if (r1 < T_q) *reinterpret_cast<uint32_t*>(o1 + nt * 8) = xa_pack(o[nt][2] * inv1, o[nt][3] * inv1);
+    }
+  }
+}
+
+int g_attn_short_kv = 1;   // sgn_set_option "attn_short_kv": 0 sends T_kv <= 80 through the tcgen05 kernel as well
+
 }  // namespace sgn
 
 using namespace sgn;
@@ -350,6 +485,19 @@ extern "C" int sgn_attention_f16(const void* d_q, int64_t ldq, const void* d_k, 
                 "row stride smaller than heads * 64");
   SGN_CHECK_ARG(((reinterpret_cast<uintptr_t>(d_q) | reinterpret_cast<uintptr_t>(d_k) | reinterpret_cast<uintptr_t>(d_v) |
                   reinterpret_cast<uintptr_t>(d_out)) & 15) == 0, "operands must be 16-byte aligned");
+  if (T_kv <= kXaKv && g_attn_short_kv) {
+    // ~4 resident waves: enough query tiles per CTA to amortise its K / V load, enough CTAs to fill the GPU
+    const int tiles = (T_q + kXaQ - 1) / kXaQ;
+    const long long want = 4ll * sm_count();
+    int tiles_per_cta = (int)std::max<long long>(1, std::min<long long>(8, (long long)tiles * heads * B / want));
+    dim3 grid((tiles + tiles_per_cta - 1) / tiles_per_cta, heads, B);
+    k_cross_attention<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __half*>(d_q), ldq, reinterpret_cast<const __half*>(d_k), ldk,
+        reinterpret_cast<const __half*>(d_v), ldv, T_q, T_kv, scale * 1.4426950408889634f,
+        reinterpret_cast<__half*>(d_out), ldo, tiles_per_cta * kXaQ);
+    SGN_LAUNCH_CHECK();
+    return SGN_OK;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     SGN_CUDA(cudaFuncSetAttribute(k_attention_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));

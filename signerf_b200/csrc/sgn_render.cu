@@ -541,7 +541,7 @@ extern "C" int sgn_field_eval(const SgnField* f, const float* d_pos, const float
   return SGN_OK;
 }
 
-namespace sgn { extern int g_pair_stages; extern int g_attn_variant; extern int g_attn_idle_ns; }
+namespace sgn { extern int g_pair_stages; extern int g_attn_variant; extern int g_attn_idle_ns; extern int g_attn_short_kv; }
 
 extern "C" int sgn_set_option(const char* name, int value) {
   SGN_CHECK_ARG(name != nullptr, "null option name");
@@ -559,6 +559,11 @@ extern "C" int sgn_set_option(const char* name, int value) {
   if (n == "attn_variant") {
     SGN_CHECK_ARG(value >= 0 && value <= 2, "attn_variant must be 0..2");
     sgn::g_attn_variant = value;
+    return SGN_OK;
+  }
+  if (n == "attn_short_kv") {
+    SGN_CHECK_ARG(value == 0 || value == 1, "attn_short_kv must be 0 or 1");
+    sgn::g_attn_short_kv = value;
     return SGN_OK;
   }
   if (n == "attn_idle_ns") {

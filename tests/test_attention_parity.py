@@ -19,7 +19,8 @@ def _ref(q, k, v, B, heads):
 
 
 @pytest.mark.parametrize("B,heads,Tq,Tkv", [(1, 1, 128, 128), (2, 2, 256, 256), (2, 3, 64, 64), (1, 2, 200, 333),
-                                            (2, 10, 1024, 1024), (2, 4, 256, 77), (1, 20, 4096, 4096)])
+                                            (2, 10, 1024, 1024), (2, 4, 256, 77), (1, 20, 4096, 4096), (2, 3, 200, 77), (1, 2, 70, 5),
+                                            (2, 5, 1000, 80), (1, 1, 64, 64), (2, 20, 4096, 77)])
 def test_attention_matches_fp32_reference(B, heads, Tq, Tkv):
     g = torch.Generator().manual_seed(Tq * 7 + Tkv)
     C = heads * 64
