@@ -55,10 +55,11 @@ class InProcessSDXL:
         sig = img2img_sigmas(steps, strength)
         g = torch.Generator(device=init_latent.device).manual_seed(int(seed))
         x = init_latent + torch.randn(init_latent.shape, generator=g, device=init_latent.device) * sig[0]
+        guided = self.net.ctrl.hint_embedding(hint) if self.net.ctrl is not None else None   # constant over the steps
         for i in range(len(sig) - 1):
             noise = torch.randn(init_latent.shape, generator=g, device=init_latent.device) if sig[i + 1] > 0 else None
             x, _, _ = self.net.step(x, sig[i], sig[i + 1], self.context, self.y, hint, noise, init_latent, latent_mask,
-                                    cfg_scale, control_weight)
+                                    cfg_scale, control_weight, guided=guided)
         return x
 
 

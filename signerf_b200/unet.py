@@ -359,6 +359,18 @@ class _Net:
         self._kv_ctx = ctx16
         self._kv_out = {c: K.gemm_f16(ctx16, w, None, out_f16=True) for c, w in self._kv_w.items()}
 
+    def context16(self, context: Tensor) -> Tensor:
+        """fp16 prompt context with the batched K/V projections made for it.  The prompt does not change between the
+        denoising steps of one request, so both are kept for as long as the caller passes the same (unmodified) tensor."""
+        capturing = torch.cuda.is_current_stream_capturing()
+        hit = (not capturing and getattr(self, "_ctx_ref", None) is context and self._ctx_version == context._version)
+        if not hit:
+            ctx16 = K.cast_f16(context.reshape(-1, context.shape[-1]))
+            self.project_context(ctx16)
+            # the cache holds the tensor itself (its storage cannot be recycled under us) and its in-place version
+            self._ctx_ref, self._ctx_version = (None, -1) if capturing else (context, context._version)
+        return self._kv_ctx
+
     def context_kv(self, block: str, c: int, ctx16: Tensor) -> Tuple[Tensor, Tensor]:
         """(k, v) [Bt*n_ctx, C] of transformer block `block`: slices of the batched projection when it was made for this
         context, otherwise this block's own GEMM (block-level callers, tests)."""
@@ -480,8 +492,7 @@ class SDXLUNetB200(_Net):
         x, timesteps, context, y = (_f32(x, "x"), _f32(timesteps, "timesteps"), _f32(context, "context"), _f32(y, "y"))
         emb = self.embed(timesteps, y)
         n_ctx = context.shape[1]
-        ctx16 = K.cast_f16(context.reshape(-1, context.shape[-1]))
-        self.project_context(ctx16)
+        ctx16 = self.context16(context)
         tap = (lambda n, a: taps.__setitem__(n, a.nchw())) if taps is not None else (lambda n, a: None)
         hs, h = self.encoder(x, emb, ctx16, n_ctx, on_block=lambda i, a: tap(f"input_blocks.{i}", a))
         control = list(control) if control is not None else None
@@ -543,13 +554,15 @@ class ControlNetB200(_Net):
         j = len(HINT_STACK)
         return K.conv3x3_f16(x, p.conv16(f"input_hint_block.{2 * j}.weight"), p.f32(f"input_hint_block.{2 * j}.bias"))
 
-    def forward(self, x: Tensor, hint: Tensor, timesteps: Tensor, context: Tensor, y: Tensor) -> List[Tensor]:
-        """`hint` may hold fewer images than `x` (the CFG pair shares one hint): image b uses hint b % Bh."""
+    def forward(self, x: Tensor, hint: Tensor, timesteps: Tensor, context: Tensor, y: Tensor,
+                guided: Optional[Tensor] = None) -> List[Tensor]:
+        """`hint` may hold fewer images than `x` (the CFG pair shares one hint): image b uses hint b % Bh.
+        `guided`: hint_embedding(hint) computed earlier (it depends on the hint only: once per request, not per step)."""
         x, timesteps, context, y = (_f32(x, "x"), _f32(timesteps, "timesteps"), _f32(context, "context"), _f32(y, "y"))
         emb = self.embed(timesteps, y)
-        ctx16 = K.cast_f16(context.reshape(-1, context.shape[-1]))
-        self.project_context(ctx16)
-        guided = self.hint_embedding(hint)
+        ctx16 = self.context16(context)
+        if guided is None:
+            guided = self.hint_embedding(hint)
         outs: List[Tensor] = []
         p = self.p
 
@@ -615,20 +628,22 @@ class SDXLDenoiserB200:
         self.unet = SDXLUNetB200(cfg, unet_weights, device)
         self.ctrl = ControlNetB200(cfg, ctrl_weights, device) if ctrl_weights is not None else None
 
-    def eps(self, x: Tensor, sigma: float, context: Tensor, y: Tensor, hint: Optional[Tensor], control_weight: float = 0.8) -> Tensor:
+    def eps(self, x: Tensor, sigma: float, context: Tensor, y: Tensor, hint: Optional[Tensor], control_weight: float = 0.8,
+            guided: Optional[Tensor] = None) -> Tensor:
         """eps for the stacked (cond, uncond) batch: x [B,4,h,w] -> [2B,4,h,w]."""
         B = x.shape[0]
         c_in = 1.0 / math.sqrt(sigma * sigma + 1.0)
         xin = K.scale_cat2(x, c_in)
         t = torch.full((2 * B,), sigma_to_t(sigma), dtype=torch.float32, device=self.dev)
-        control = self.ctrl.forward(xin, hint, t, context, y) if (self.ctrl is not None and hint is not None) else None
+        control = (self.ctrl.forward(xin, hint, t, context, y, guided=guided)
+                   if (self.ctrl is not None and hint is not None) else None)
         return self.unet.forward(xin, t, context, y, control=control, control_weight=control_weight)
 
     def step(self, x: Tensor, sigma: float, sigma_next: float, context: Tensor, y: Tensor, hint: Optional[Tensor],
              noise: Optional[Tensor] = None, init_latent: Optional[Tensor] = None, mask: Optional[Tensor] = None,
-             cfg_scale: float = 7.0, control_weight: float = 0.8):
+             cfg_scale: float = 7.0, control_weight: float = 0.8, guided: Optional[Tensor] = None):
         """-> (x_next, denoised, eps).  mask [B,1,h,w] = 1 where the original latent is kept."""
-        eps = self.eps(x, sigma, context, y, hint, control_weight)
+        eps = self.eps(x, sigma, context, y, hint, control_weight, guided)
         down, up = ancestral_step(sigma, sigma_next)
         x_next, den = K.cfg_euler_step(x, eps, init_latent, mask, noise if sigma_next > 0 else None, cfg_scale, sigma, down, up)
         return x_next, den, eps
@@ -690,9 +705,10 @@ class BenchUNet:
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         x = self.init + self.noise * sig[0]
         a.record()
+        guided = self.net.ctrl.hint_embedding(self.hint)       # once per request; the prompt K/V likewise (context16)
         for i in range(len(sig) - 1):
             x, _, _ = self.net.step(x, sig[i], sig[i + 1], self.context, self.y, self.hint, self.noise, self.init,
-                                    self.lat_mask)
+                                    self.lat_mask, guided=guided)
         b.record()
         torch.cuda.synchronize()
         if not bool(torch.isfinite(x).all()):
