@@ -274,6 +274,12 @@ int sgn_sheet_to_conditioning(const float* d_cond, const float* d_mask, int Hs, 
  * d_x fp32 NCHW (in_nchw) or NHWC. */
 int sgn_im2col3x3_split_f16(const float* d_x, int in_nchw, int B, int H, int W, int C, int stride, void* d_out,
                             void* stream);
+/* 3x3 / pad 1 conv for (Cin, Cout) in {(16,16), (16,32), (32,32)} at stride 1 and (16,32) at stride 2 (ControlNet
+ * input_hint_block at the sheet resolution) on mma.sync with the fp32 input split into fp16 hi + lo in shared memory: the fp32 convolution to fp32
+ * rounding for fp16-representable weights.  d_x fp32 NHWC, d_w16 fp16 [Cout, 9*Cin] (k = (ky*3+kx)*Cin + c), out NHWC
+ * fp32 / fp16 = act(conv + bias). */
+int sgn_conv3x3_small_tc(const float* d_x, const void* d_w16, const float* d_bias, int B, int H, int W, int Cin, int Cout,
+                         int stride, int act_silu, int out_f16, void* d_out, void* stream);
 
 /* ------------------------------------------------------------------ VAE + A1111 inpaint pre / post */
 /* What the A1111 server does around the denoising loop for the request of signerf/diffuser/diffuser.py:132-169

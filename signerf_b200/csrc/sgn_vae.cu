@@ -468,3 +468,168 @@ extern "C" int sgn_overlay_composite_u8(const uint8_t* d_generated, const uint8_
   SGN_LAUNCH_CHECK();
   return SGN_OK;
 }
+
+// ------------------------------------------------------------------ small-channel 3x3 conv on mma.sync, fp32-exact
+// ControlNet's input_hint_block at the sheet resolution (16 -> 16 @2048^2, 32 -> 32 @1024^2): too narrow for the
+// TMA / tcgen05 conv (Cin % 64) and, as a direct fp32 conv, 1.7 ms each on the CUDA cores.  Here a 16 x 16 pixel tile
+// (+halo) is split once into fp16 hi + lo halves in shared memory (x = hi + lo to 2^-22), and every tap is two
+// m16n8k16 MMAs (hi, lo) against the fp16 weights with fp32 accumulation: the fp32 convolution to fp32 rounding for
+// fp16-representable weights, the same trick as sgn_im2col3x3_split_f16 without materialising the im2col matrix.
+namespace sgn {
+
+__device__ __forceinline__ void sc_mma(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ uint32_t sc_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sc_ldsm_x4(uint32_t (&r)[4], const __half* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(sc_smem(p)));
+}
+__device__ __forceinline__ void sc_ldsm_x2(uint32_t (&r)[2], const __half* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];\n" : "=r"(r[0]), "=r"(r[1]) : "r"(sc_smem(p)));
+}
+
+constexpr int kScTile = 16;
+
+template <int CIN, int COUT, int STRIDE>
+struct ScCfg {
+  static constexpr int kHalo = (kScTile - 1) * STRIDE + 3;   // input tile edge: 18 (stride 1) / 33 (stride 2)
+  static constexpr int kPix = CIN + 8;        // halfs per pixel in shared memory (48 / 80 B: conflict-free ldmatrix rows)
+  static constexpr int kWRow = 9 * CIN + 8;   // halfs per weight row
+  static constexpr size_t kSmem = (size_t)(2 * kHalo * kHalo * kPix + COUT * kWRow) * sizeof(__half);
+};
+
+// H, W: input size; Ho, Wo: output size ((H-1)/STRIDE + 1: pad 1)
+template <int CIN, int COUT, int STRIDE>
+__global__ void __launch_bounds__(256)
+k_conv3x3_small_tc(const float* __restrict__ x, const __half* __restrict__ w, const float* __restrict__ bias, int H, int W,
+                   int Ho, int Wo, int act_silu, int out_f16, void* __restrict__ out) {
+  using Cfg = ScCfg<CIN, COUT, STRIDE>;
+  constexpr int kScHalo = Cfg::kHalo;
+  extern __shared__ __align__(16) uint8_t sc_raw[];
+  __half* s_hi = reinterpret_cast<__half*>(sc_raw);
+  __half* s_lo = s_hi + kScHalo * kScHalo * Cfg::kPix;
+  __half* s_w = s_lo + kScHalo * kScHalo * Cfg::kPix;
+  const int tiles_x = (Wo + kScTile - 1) / kScTile;
+  const int tx0 = (blockIdx.x % tiles_x) * kScTile, ty0 = (blockIdx.x / tiles_x) * kScTile;   // output coordinates
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // weights [COUT][9*CIN] fp16 -> padded rows (8 halfs = 16 B per copy)
+  for (int i = tid; i < COUT * (9 * CIN / 8); i += 256) {
+    const int r = i / (9 * CIN / 8), j = i % (9 * CIN / 8);
+    *reinterpret_cast<uint4*>(s_w + r * Cfg::kWRow + j * 8) = __ldg(reinterpret_cast<const uint4*>(w + (size_t)r * 9 * CIN) + j);
+  }
+  // input halo tile: fp32 NHWC -> hi / lo fp16
+  constexpr int c4n = CIN / 4;
+  for (int i = tid; i < kScHalo * kScHalo * c4n; i += 256) {
+    const int c4 = i % c4n, pix = i / c4n;
+    const int py = pix / kScHalo, px = pix % kScHalo;
+    const int iy = ty0 * STRIDE + py - 1, ix = tx0 * STRIDE + px - 1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (iy >= 0 && iy < H && ix >= 0 && ix < W)
+      v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)b * H + iy) * W + ix) * CIN) + c4);
+    const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+    uint2 uh, ul;
+    uh.x = *reinterpret_cast<const uint32_t*>(&h0), uh.y = *reinterpret_cast<const uint32_t*>(&h1);
+    ul.x = *reinterpret_cast<const uint32_t*>(&l0), ul.y = *reinterpret_cast<const uint32_t*>(&l1);
+    *reinterpret_cast<uint2*>(s_hi + pix * Cfg::kPix + c4 * 4) = uh;
+    *reinterpret_cast<uint2*>(s_lo + pix * Cfg::kPix + c4 * 4) = ul;
+  }
+  __syncthreads();
+  // warp -> output rows 2*warp, 2*warp+1 of the tile (one m16 tile = 16 pixels of a row); all COUT channels
+  float acc[2][COUT / 8][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < COUT / 8; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int dy = tap / 3, dx = tap % 3;
+#pragma unroll
+    for (int kc = 0; kc < CIN / 16; ++kc) {
+      uint32_t bf[COUT / 8][2];
+#pragma unroll
+      for (int nt = 0; nt < COUT / 8; ++nt)
+        sc_ldsm_x2(bf[nt], s_w + (nt * 8 + (lane & 7)) * Cfg::kWRow + tap * CIN + kc * 16 + ((lane >> 3) & 1) * 8);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int pix = ((warp * 2 + mt) * STRIDE + dy) * kScHalo + dx + (lane & 15) * STRIDE;
+        uint32_t ah[4], al[4];
+        sc_ldsm_x4(ah, s_hi + pix * Cfg::kPix + kc * 16 + (lane >> 4) * 8);
+        sc_ldsm_x4(al, s_lo + pix * Cfg::kPix + kc * 16 + (lane >> 4) * 8);
+#pragma unroll
+        for (int nt = 0; nt < COUT / 8; ++nt) {
+          sc_mma(acc[mt][nt], ah, bf[nt]);
+          sc_mma(acc[mt][nt], al, bf[nt]);
+        }
+      }
+    }
+  }
+  const int g = lane >> 2, c0 = (lane & 3) * 2;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+    const int oy = ty0 + warp * 2 + mt;
+    if (oy >= Ho) continue;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int ox = tx0 + g + half * 8;
+      if (ox >= Wo) continue;
+      const size_t o = (((size_t)b * Ho + oy) * Wo + ox) * COUT;
+#pragma unroll
+      for (int nt = 0; nt < COUT / 8; ++nt) {
+        float v0 = acc[mt][nt][half * 2] + (bias ? __ldg(bias + nt * 8 + c0) : 0.f);
+        float v1 = acc[mt][nt][half * 2 + 1] + (bias ? __ldg(bias + nt * 8 + c0 + 1) : 0.f);
+        if (act_silu) v0 = v0 / (1.f + __expf(-v0)), v1 = v1 / (1.f + __expf(-v1));
+        if (out_f16) {
+          const __half2 h = __floats2half2_rn(v0, v1);
+          *reinterpret_cast<__half2*>(reinterpret_cast<__half*>(out) + o + nt * 8 + c0) = h;
+        } else {
+          *reinterpret_cast<float2*>(reinterpret_cast<float*>(out) + o + nt * 8 + c0) = make_float2(v0, v1);
+        }
+      }
+    }
+  }
+}
+
+template <int CIN, int COUT, int STRIDE>
+static int launch_small_tc(const float* x, const void* w, const float* bias, int B, int H, int W, int act_silu, int out_f16,
+                           void* out, cudaStream_t st) {
+  using Cfg = ScCfg<CIN, COUT, STRIDE>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SGN_CUDA(cudaFuncSetAttribute(k_conv3x3_small_tc<CIN, COUT, STRIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
+    attr_set = true;
+  }
+  const int Ho = (H - 1) / STRIDE + 1, Wo = (W - 1) / STRIDE + 1;
+  dim3 grid(((Wo + kScTile - 1) / kScTile) * ((Ho + kScTile - 1) / kScTile), B);
+  k_conv3x3_small_tc<CIN, COUT, STRIDE><<<grid, 256, Cfg::kSmem, st>>>(x, reinterpret_cast<const __half*>(w), bias, H, W, Ho, Wo,
+                                                                      act_silu, out_f16, out);
+  SGN_LAUNCH_CHECK();
+  return SGN_OK;
+}
+
+}  // namespace sgn
+
+extern "C" int sgn_conv3x3_small_tc(const float* d_x, const void* d_w16, const float* d_bias, int B, int H, int W, int Cin,
+                                    int Cout, int stride, int act_silu, int out_f16, void* d_out, void* stream) {
+  SGN_CHECK_ARG(B >= 0 && H > 0 && W > 0 && (stride == 1 || stride == 2), "bad conv shape");
+  if (B == 0) return SGN_OK;
+  SGN_CHECK_ARG(d_x && d_w16 && d_out, "null pointer");
+  SGN_CHECK_ARG(((reinterpret_cast<uintptr_t>(d_x) | reinterpret_cast<uintptr_t>(d_w16) | reinterpret_cast<uintptr_t>(d_out)) & 15) == 0,
+                "operands must be 16-byte aligned");
+  cudaStream_t st = STV(stream);
+  if (stride == 1) {
+    if (Cin == 16 && Cout == 16) return sgn::launch_small_tc<16, 16, 1>(d_x, d_w16, d_bias, B, H, W, act_silu, out_f16, d_out, st);
+    if (Cin == 16 && Cout == 32) return sgn::launch_small_tc<16, 32, 1>(d_x, d_w16, d_bias, B, H, W, act_silu, out_f16, d_out, st);
+    if (Cin == 32 && Cout == 32) return sgn::launch_small_tc<32, 32, 1>(d_x, d_w16, d_bias, B, H, W, act_silu, out_f16, d_out, st);
+  } else if (Cin == 16 && Cout == 32) {
+    return sgn::launch_small_tc<16, 32, 2>(d_x, d_w16, d_bias, B, H, W, act_silu, out_f16, d_out, st);
+  }
+  sgn::set_error("invalid argument: sgn_conv3x3_small_tc handles (Cin, Cout) in {(16,16), (16,32), (32,32)} at stride 1 and "
+                 "(16,32) at stride 2");
+  return SGN_ERR_INVALID_ARG;
+}

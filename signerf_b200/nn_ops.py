@@ -236,6 +236,23 @@ def conv3x3_direct(x: Tensor, in_nchw: bool, w: Tensor, bias: Optional[Tensor], 
     return out
 
 
+def conv3x3_small_tc(x: Tensor, w16: Tensor, bias: Optional[Tensor], stride: int = 1, act_silu: bool = False,
+                     out_f16: bool = False) -> Tensor:
+    """fp32-exact 3x3 / p1 conv for 16 / 32 channels on mma.sync: x fp32 NHWC [B,H,W,Cin], w16 fp16 [Cout, 9*Cin]."""
+    _chk(x, torch.float32, "x")
+    _chk(w16, torch.float16, "w16")
+    _chk(bias, torch.float32, "bias")
+    B, H, W, Cin = x.shape
+    Cout = w16.shape[0]
+    if w16.shape[1] != 9 * Cin:
+        raise ValueError(f"w16 must be [Cout, {9 * Cin}], got {tuple(w16.shape)}")
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    out = torch.empty((B, Ho, Wo, Cout), dtype=torch.float16 if out_f16 else torch.float32, device=x.device)
+    _call(x.device, _lib.load().sgn_conv3x3_small_tc, _ptr(x), _ptr(w16), _ptr(bias), B, H, W, Cin, Cout, int(stride),
+          int(act_silu), int(out_f16), _ptr(out))
+    return out
+
+
 def linear_small(x: Tensor, w: Tensor, bias: Optional[Tensor], residual: Optional[Tensor] = None, silu_in: bool = False,
                  silu_out: bool = False) -> Tensor:
     _chk(x, torch.float32, "x")

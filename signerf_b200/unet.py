@@ -45,6 +45,7 @@ class UNetConfig:
     hint_channels: int = 3
 
 
+SMALL_TC_SHAPES = ((16, 16), (16, 32), (32, 32))   # (Cin, Cout) of sgn_conv3x3_small_tc
 HINT_STACK = ((16, 1), (16, 1), (32, 2), (32, 1), (96, 2), (96, 1), (256, 2))  # (out channels, stride) before the 256->mc conv
 
 
@@ -321,9 +322,11 @@ class _Net:
             elif "input_hint_block" in n:
                 if shp[1] % 64 == 0:
                     p.conv16(n)
-                else:   # both fp32-exact routes stay available (hint_embedding picks per layer)
+                else:   # the fp32-exact routes stay available (hint_embedding picks per layer)
                     p.conv_split16(n)
                     p.conv32(n)
+                    if (shp[1], shp[0]) in SMALL_TC_SHAPES:
+                        p.conv16(n)
             elif len(shp) == 4 and shp[2] == 3:
                 (p.conv16 if shp[1] % 64 == 0 else p.conv32)(n)
             elif len(shp) == 4:
@@ -544,7 +547,10 @@ class ControlNetB200(_Net):
         for j, (cout, stride) in enumerate(HINT_STACK):
             last = j == len(HINT_STACK) - 1
             wn, bn = f"input_hint_block.{2 * j}.weight", f"input_hint_block.{2 * j}.bias"
-            if stride == 2 or cin >= 64:
+            if not nchw and (cin, cout) in SMALL_TC_SHAPES and (stride == 1 or (cin, cout) == (16, 32)):
+                # 16 / 32 channels at the sheet resolution: hi / lo split in shared memory + mma.sync (fp32-exact, no im2col)
+                x = K.conv3x3_small_tc(x, p.conv16(wn), p.f32(bn), stride=stride, act_silu=True, out_f16=last)
+            elif stride == 2 or cin >= 64:
                 col, ho, wo, _ = K.im2col3x3_split_f16(x, nchw, stride)
                 y = K.gemm_f16(col, p.conv_split16(wn), p.f32(bn), act_silu=True, out_f16=last)
                 x = y.view(Bh, ho, wo, cout)

@@ -139,3 +139,22 @@ def test_small_channel_conv_on_tensor_cores_is_fp32_exact(B, H, W, Cin, Cout, st
     out = K.gemm_f16(col, torch.cat([wp, wp], 1).half().contiguous(), bias, act_silu=True)
     assert (ho, wo) == tuple(ref.shape[2:])
     assert rel_l2(out.view(B, ho, wo, Cout).permute(0, 3, 1, 2), ref) < 2e-6
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,stride", [(1, 64, 48, 16, 16, 1), (2, 33, 31, 16, 32, 1), (1, 50, 70, 32, 32, 1),
+                                                   (1, 16, 16, 32, 32, 1), (1, 5, 3, 16, 16, 1), (1, 64, 96, 16, 32, 2),
+                                                   (2, 33, 31, 16, 32, 2)])
+@pytest.mark.parametrize("out_f16", [False, True])
+def test_small_tc_conv_is_fp32_exact(B, H, W, Cin, Cout, stride, out_f16):
+    """sgn_conv3x3_small_tc: hi/lo split in shared memory + mma.sync == fp32 conv + SiLU (weights fp16-representable),
+    ragged tiles included."""
+    x = _r((B, Cin, H, W), 11) * 3
+    w = _r((Cout, Cin, 3, 3), 12, (9 * Cin) ** -0.5).half().float()
+    bias = _r((Cout,), 13)
+    ref = F.silu(F.conv2d(x, w, bias, stride=stride, padding=1))
+    w16 = w.permute(0, 2, 3, 1).reshape(Cout, -1).half().contiguous()
+    out = K.conv3x3_small_tc(x.permute(0, 2, 3, 1).contiguous(), w16, bias, stride=stride, act_silu=True, out_f16=out_f16)
+    assert out.dtype == (torch.float16 if out_f16 else torch.float32)
+    assert rel_l2(out.permute(0, 3, 1, 2), ref) < (6e-4 if out_f16 else 2e-6)
+    lin = K.conv3x3_small_tc(x.permute(0, 2, 3, 1).contiguous(), w16, None, stride=stride)
+    assert rel_l2(lin.permute(0, 3, 1, 2), F.conv2d(x, w, None, stride=stride, padding=1)) < 2e-6
