@@ -324,6 +324,26 @@ int sgn_latent_keep_mask(const uint8_t* d_lat_u8, int64_t n, float* d_keep, void
 int sgn_overlay_composite_u8(const uint8_t* d_generated, const uint8_t* d_original, const uint8_t* d_overlay_mask, int H,
                              int W, uint8_t* d_out_u8, float* d_out_f32, void* stream);
 
+/* ------------------------------------------------------------------ proxy-mesh depth + shape masking */
+/* Replaces reference Renderer.render_camera's depth output (signerf/renderer/renderer.py:149-196: pyrender
+ * OffscreenRenderer + IntrinsicsCamera(znear 1e-4, zfar 10) over the trimesh loaded in setup(), :64-131) for V views:
+ * OpenGL rasterisation rules (pixel centres at +0.5, 8 sub-pixel bits, top-left rule, LESS on a 24-bit depth buffer,
+ * back-face culling when cull_back), the Blender -> OpenGL axis swap of :134-146 applied to the camera poses, pyrender's
+ * buffer -> metric depth conversion; 0 = empty.
+ *   d_vertices [Nv,3] fp32 object space, d_faces [Nf,3] int32; h_model: 4x4 row-major double on the HOST = the object
+ *   pose already in OpenGL axes (convert @ [Rz Ry Rx diag(10 scale) | position]); d_c2w [V,3,4], d_intr [V,4] as K1;
+ *   d_ws: sgn_rasterize_ws_bytes(Nv,V,H,W) bytes of 16-byte aligned scratch; d_depth [V,H,W,1] fp32 out. */
+int64_t sgn_rasterize_ws_bytes(int Nv, int V, int H, int W);
+int sgn_rasterize_depth(const float* d_vertices, const int32_t* d_faces, int Nv, int Nf, const double* h_model,
+                        const float* d_c2w, const float* d_intr, int V, int H, int W, double znear, double zfar, int cull_back,
+                        void* d_ws, float* d_depth, void* stream);
+/* render_camera's masking_mode == "shape" branch (datasetgenerator.py:711-757) for V views: visible = (proxy < depth) &
+ * (proxy > 0) (inverted when inverse_mask), cv2.dilate, min over visible proxy depths - radius, max over the whole proxy
+ * image + radius (or manual_depth), condition = 1 - clamp(visible * proxy_n + ~visible * depth_n).  Same outputs /
+ * stats as sgn_mask_condition; SgnMaskOpts.aabb is ignored. */
+int sgn_mask_condition_shape(const float* d_proxy_depth, const float* d_depth, int V, int H, int W, const SgnMaskOpts* o,
+                             uint8_t* d_mask, float* d_cond, float* d_stats, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -116,6 +116,10 @@ SIGNATURES = {
     "sgn_inpaint_overlay_mask_u8": (_i, [_vp, _i64, _vp, _vp]),
     "sgn_latent_keep_mask": (_i, [_vp, _i64, _vp, _vp]),
     "sgn_overlay_composite_u8": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "sgn_rasterize_ws_bytes": (_i64, [_i, _i, _i, _i]),
+    "sgn_rasterize_depth": (_i, [_vp, _vp, _i, _i, C.POINTER(C.c_double), _vp, _vp, _i, _i, _i, C.c_double, C.c_double, _i,
+                                _vp, _vp, _vp]),
+    "sgn_mask_condition_shape": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(SgnMaskOpts), _vp, _vp, _vp, _vp]),
 }
 
 _lib: Optional[C.CDLL] = None

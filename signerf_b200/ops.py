@@ -194,6 +194,46 @@ def mask_condition(c2w: Tensor, intr: Tensor, depth: Tensor, opts: MaskOptions):
     return mask, cond, stats
 
 
+def mask_condition_shape(proxy_depth: Tensor, depth: Tensor, opts: MaskOptions):
+    """render_camera's "shape" masking branch for V views (proxy-mesh depth vs NeRF depth): same outputs as mask_condition."""
+    depth = _req(depth, torch.float32, "depth")
+    proxy_depth = _req(proxy_depth, torch.float32, "proxy_depth")
+    if proxy_depth.shape != depth.shape:
+        raise ValueError(f"proxy depth {tuple(proxy_depth.shape)} does not match depth {tuple(depth.shape)}")
+    V, H, W = depth.shape[0], depth.shape[1], depth.shape[2]
+    dev = depth.device
+    mask = torch.empty((V, H, W, 1), dtype=torch.uint8, device=dev)
+    cond = torch.empty((V, H, W, 1), dtype=torch.float32, device=dev)
+    stats = torch.empty((V, 4), dtype=torch.float32, device=dev)
+    o = opts.to_c()
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().sgn_mask_condition_shape(_ptr(proxy_depth), _ptr(depth), V, H, W, C.byref(o), _ptr(mask),
+                                                        _ptr(cond), _ptr(stats), _stream(dev)))
+    return mask, cond, stats
+
+
+def rasterize_depth(vertices: Tensor, faces: Tensor, model, c2w: Tensor, intr: Tensor, H: int, W: int, znear: float = 1e-4,
+                    zfar: float = 10.0, cull_back: bool = True) -> Tensor:
+    """Proxy-mesh metric depth [V,H,W,1] (0 = empty) with pyrender / OpenGL conventions; `model`: 4x4 object pose in
+    OpenGL axes (16 floats, row-major, host)."""
+    vertices = _req(vertices, torch.float32, "vertices")
+    if not faces.is_cuda or faces.dtype != torch.int32:
+        raise TypeError("faces must be a CUDA int32 tensor [Nf,3]")
+    faces = faces.contiguous()
+    c2w = _req(c2w[..., :3, :4], torch.float32, "c2w")
+    intr = _req(intr, torch.float32, "intr")
+    V, Nv, Nf = c2w.shape[0], vertices.shape[0], faces.shape[0]
+    dev = c2w.device
+    lib = _lib.load()
+    ws = torch.empty(max(16, int(lib.sgn_rasterize_ws_bytes(Nv, V, H, W))), dtype=torch.uint8, device=dev)
+    depth = torch.empty((V, H, W, 1), dtype=torch.float32, device=dev)
+    m = (C.c_double * 16)(*[float(x) for x in (model.flatten().tolist() if hasattr(model, "flatten") else model)])
+    with torch.cuda.device(dev):
+        _lib.check(lib.sgn_rasterize_depth(_ptr(vertices), _ptr(faces), Nv, Nf, m, _ptr(c2w), _ptr(intr), V, H, W,
+                                           float(znear), float(zfar), int(cull_back), _ptr(ws), _ptr(depth), _stream(dev)))
+    return depth
+
+
 def dilate_ellipse(mask: Tensor, ksize: Tuple[int, int]) -> Tensor:
     """cv2.dilate(mask, getStructuringElement(MORPH_ELLIPSE, ksize)) > 0 for [V,H,W] uint8 masks."""
     m = _req(mask, torch.uint8, "mask")

@@ -86,16 +86,20 @@ class DatasetGenerator:
     def render_views(self, graph, cameras) -> Tuple[Tensor, Tensor, Tensor]:
         """render_camera for V cameras at once (K1 + K2/K3, no host sync): rgb [V,H,W,3] fp32, mask [V,H,W,1] bool,
         condition [V,H,W,1] fp32."""
-        if self.masking_mode == "shape" or self.combine_shape_with_depth:
-            if self.renderer is None:
-                raise ValueError("Renderer is None but masking mode is shape")
-            self.renderer.render_camera(cameras)          # raises: proxy-mesh path not built (§8(f) row 2)
+        if self.combine_shape_with_depth:
+            raise NotImplementedError("combine_shape_with_depth (datasetgenerator.py:794-807) conditions on pyrender's SHADED "
+                                      "colour image, which the depth rasteriser does not produce")
+        if self.masking_mode == "shape" and self.renderer is None:
+            raise ValueError("Renderer is None but masking mode is shape")
         cam = as_camera_batch(cameras)
         graph.eval()
         out = graph.render_cameras(cam)
         graph.train()
         if out is None:
             raise RuntimeError("Render thread did not return any outputs")
+        if self.masking_mode == "shape":      # datasetgenerator.py:711-757, proxy depth from the CUDA rasteriser
+            mask, cond, _ = ops.mask_condition_shape(self.renderer.render_depths(cam), out["depth"], self._mask_options())
+            return out["rgb"], mask.bool(), cond
         c2w, intr = c2w_intr(cam, graph.device)
         mask, cond, _ = ops.mask_condition(c2w, intr, out["depth"], self._mask_options())
         return out["rgb"], mask.bool(), cond
@@ -110,8 +114,8 @@ class DatasetGenerator:
             out = graph.render_cameras(cam)
             graph.train()
             return out["rgb"][0], None, None, None
-        if combine_shape_with_depth and not self.combine_shape_with_depth:
-            self.renderer.render_camera(camera)
+        if combine_shape_with_depth:
+            raise NotImplementedError("combine_shape_with_depth needs pyrender's shaded colour image (datasetgenerator.py:794-807)")
         rgb, mask, cond = self.render_views(graph, cam)
         if not with_condition:
             return rgb[0], mask[0], None, None

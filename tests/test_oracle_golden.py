@@ -139,3 +139,57 @@ def test_vae_oracle_shapes_and_parameter_count():
     mean, logvar = mom.chunk(2, 1)
     assert torch.allclose(z0, VR.SCALE_FACTOR * mean) and torch.allclose(z1, VR.SCALE_FACTOR * (mean + torch.exp(0.5 * logvar) * n))
     assert tuple(m.decode(z0).shape) == (1, 3, 32, 48)
+
+
+# ---------------------------------------------------------------------------------------------- proxy-mesh depth (row (f)2)
+def test_mesh_oracle_against_analytic_depth():
+    """oracle/mesh_ref.py (parity unpinned: no pyrender here): a sphere and a fronto-parallel quad against their
+    analytic z-depth through the same camera model as K1 (pixel centres at +0.5, -z forward, y up)."""
+    from oracle import mesh_ref as M
+    H = W = 96
+    fx = fy = 96.0
+    cx = cy = 48.0
+    c2w = np.eye(4)[:3]
+    v, f = M.uv_sphere(1.0, 48, 96)
+    # object and camera poses both go through the Blender -> OpenGL swap, so their relative geometry is the nerfstudio
+    # one: with an identity c2w (looking down -z, y up) an object at world position p sits at camera-space p
+    model = M.object_pose([0.1, -0.05, -1.5], [0, 0, 0], [0.05, 0.05, 0.05])     # radius 10 * 0.05 = 0.5
+    cam = M.CONVERT @ np.eye(4)
+    centre_cam = cam[:3, :3].T @ (model[:3, 3] - cam[:3, 3])
+    assert np.allclose(centre_cam, [0.1, -0.05, -1.5])
+    d = M.rasterize_depth(v, f, model, c2w, (fx, fy, cx, cy), H, W)
+    ys, xs = np.mgrid[0:H, 0:W]
+    dirs = np.stack([(xs + 0.5 - cx) / fx, -(ys + 0.5 - cy) / fy, -np.ones_like(xs, dtype=np.float64)], -1)
+    a = (dirs ** 2).sum(-1)
+    b = -2 * (dirs @ centre_cam)
+    c = centre_cam @ centre_cam - 0.25
+    disc = b * b - 4 * a * c
+    t = np.where(disc > 0, (-b - np.sqrt(np.maximum(disc, 0))) / (2 * a), 0)
+    hit = (disc > 0) & (t > 0)
+    assert hit.sum() > 500 and ((d > 0) == hit).mean() > 0.995
+    both = (d > 0) & hit
+    err = np.abs(d - t)[both]                      # z-depth = t * |dir_z| = t
+    assert np.median(err) < 2e-3 and err.max() < 2e-2   # 24-bit buffer with znear 1e-4: ~1e-3 at depth 1.5; facets at the rim
+    # quad at camera-space depth 0.8 facing the camera: constant depth, exact coverage of its projected square
+    z0 = 0.8
+    q_cam = np.array([[-0.2, -0.2, -z0], [0.2, -0.2, -z0], [0.2, 0.2, -z0], [-0.2, 0.2, -z0]])
+    q_gl = (cam[:3, :3] @ q_cam.T).T + cam[:3, 3]
+    dq = M.rasterize_depth(q_gl.astype(np.float32), np.array([[0, 1, 2], [0, 2, 3]], np.int32), np.eye(4), c2w, (fx, fy, cx, cy), H, W)
+    assert (dq > 0).sum() == 48 * 48 and np.abs(dq[dq > 0] - z0).max() < 5e-4
+    back = M.rasterize_depth(q_gl.astype(np.float32), np.array([[0, 2, 1], [0, 3, 2]], np.int32), np.eye(4), c2w, (fx, fy, cx, cy), H, W)
+    assert (back > 0).sum() == 0                   # clockwise = back face, culled (pyrender's single-sided default)
+
+
+def test_obj_parser_and_shape_condition():
+    from oracle import mesh_ref as M
+    v, f = M.parse_obj("# c\nv 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvn 0 0 1\nf 1//1 2//1 3//1 4//1\nf -4 -3 -2\n")
+    assert v.shape == (4, 3) and f.tolist() == [[0, 1, 2], [0, 2, 3], [0, 1, 2]]
+    proxy = np.zeros((40, 40), np.float32)
+    proxy[10:20, 10:20] = 0.5
+    nerf = np.full((40, 40), 0.7, np.float32)
+    nerf[15:20, 10:20] = 0.3                      # NeRF surface in front of the proxy there
+    mask, cond, vis = M.shape_mask_condition(proxy, nerf, dilation=(3, 3), radius=0.1)
+    assert vis and mask[10:15, 10:20].all() and not mask[30, 30]
+    mn, mx = np.float32(0.5) - np.float32(0.1), np.float32(0.5) + np.float32(0.1)
+    assert np.isclose(cond[12, 12], 1 - (0.5 - mn) / (mx - mn)) and cond[30, 30] == 0.0     # far NeRF depth clamps to 0
+    assert not M.shape_mask_condition(np.zeros_like(proxy), nerf)[2]

@@ -119,3 +119,33 @@ def test_graph_from_nerfacto_state_dict(style):
     # proposal networks dropped (load_model_with_proposal_weights=False): flat sampling of the main field
     sd_np = {k: v for k, v in sd.items() if not k.startswith("proposal_networks")}
     assert P.FusedNerfactoGraph.from_state_dict(sd_np).render_opts.mode == "flat"
+
+
+def test_render_camera_shape_mode_matches_oracle():
+    """masking_mode='shape' (datasetgenerator.py:711-757): proxy-mesh depth from the CUDA rasteriser against the NeRF
+    depth, mask / condition against oracle/mesh_ref.py on the same depths."""
+    import numpy as np
+    from oracle import mesh_ref as M
+    H, W, Ssamp = 48, 40, 24
+    m = R.make_model(0, dense=True, table_scale=0.5, density_gain=20.0)
+    graph = P.FusedNerfactoGraph(field_from_oracle(m), ops.RenderOptions(mode="flat", num_samples=Ssamp, mlp_mode=ops.MLP_FP32))
+    gen = _generator(2, 2, H, W, 1)
+    gen.masking_mode = "shape"
+    v, f = M.uv_sphere(1.0, 10, 16)
+    c2w, intr = ring_cameras(2, W, H)
+    pos = (0.8 * c2w[0, :3, 3]).tolist()          # a small ball close to camera 0: in front of the dense field's surface
+    gen.renderer.scale = [0.002, 0.002, 0.002]
+    gen.renderer.position = pos
+    gen.renderer.set_mesh(v, f)
+    gen.renderer.setup()
+    cam = P.CameraBatch(c2w[:1], float(W), float(W), W / 2, H / 2, W, H)
+    rgb, mask, cond = gen.render_camera(graph, cam)
+    assert tuple(rgb.shape) == (H, W, 3) and tuple(mask.shape) == (H, W, 1) and mask.dtype == torch.bool
+    nerf = graph.render_cameras(cam)["depth"][0, ..., 0].cpu().numpy()
+    proxy = M.rasterize_depth(v, f, M.object_pose(pos, [0, 0, 0], [0.002] * 3), c2w[0].numpy(), intr[0].tolist(), H, W)
+    rm, rc, vis = M.shape_mask_condition(proxy, nerf, False, (7, 7), 0.1, None)
+    assert vis and np.array_equal(mask[..., 0].cpu().numpy(), rm) and np.allclose(cond[..., 0].cpu().numpy(), rc, atol=1e-6)
+    assert len(gen.render_camera(graph, cam, with_condition=False)) == 4       # the reference's arity quirk survives
+    gen.renderer = None
+    with pytest.raises(ValueError, match="Renderer is None"):
+        gen.render_camera(graph, cam)

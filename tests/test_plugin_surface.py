@@ -46,5 +46,12 @@ def test_defaults_and_error_behaviour():
     diff = P.Diffuser(P.DiffuserConfig(mode="custom"), "cpu")
     with pytest.raises(RuntimeError, match="backend"):
         diff.diffuse(torch.zeros(8, 8, 3), torch.zeros(8, 8, 3), torch.zeros(8, 8, 1), torch.zeros(8, 8, 1))
-    with pytest.raises(NotImplementedError):
-        P.Renderer(P.RendererConfig(), "cpu").render_camera(cams)
+    r = P.Renderer(P.RendererConfig(object_path="no/such/mesh.obj"), "cpu")
+    assert (r.scale, r.color, r.rotation) == ([0.1, 0.1, 0.1], [0.0, 0.0, 0.0, 1.0], [0, 0, 0])     # renderer.py:30-37
+    r.setup()                                   # renderer.py:68-75: prints and returns on a bad path
+    assert r.scene is None
+    with pytest.raises(AttributeError):         # the reference dereferences self.scene = None (renderer.py:183)
+        r.render_camera(cams)
+    r.object_path = "mesh.ply"
+    r.setup()
+    assert r.scene is None
