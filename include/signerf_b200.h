@@ -224,6 +224,11 @@ int sgn_attention_f16(const void* d_q, int64_t ldq, const void* d_k, int64_t ldk
 int64_t sgn_group_norm_ws_doubles(int B, int HW, int groups);
 int sgn_group_norm_f16(const float* d_x, int B, int HW, int C, int groups, float eps, const float* d_gamma,
                        const float* d_beta, int act_silu, double* d_ws, void* d_out, void* stream);
+/* Same, with the result split into two fp16 halves: d_out fp16 [B, HW, 2C] = [hi | lo], y = hi + lo to 2^-22.  A
+ * contraction against the weights repeated along K ([W | W], per tap for a conv) then reproduces the fp32 operator to
+ * fp32 rounding for fp16-representable weights (the VAE's "exact" mode, signerf_b200/vae.py). */
+int sgn_group_norm_split_f16(const float* d_x, int B, int HW, int C, int groups, float eps, const float* d_gamma,
+                             const float* d_beta, int act_silu, double* d_ws, void* d_out, void* stream);
 /* nn.LayerNorm(C) over the last dimension: fp32 [M, C] -> fp16 [M, C]. */
 int sgn_layer_norm_f16(const float* d_x, int64_t M, int C, float eps, const float* d_gamma, const float* d_beta,
                        void* d_out, void* stream);
@@ -291,6 +296,11 @@ int sgn_conv3x3_small_tc(const float* d_x, const void* d_w16, const float* d_bia
 /* ldm Downsample (`F.pad(x, (0,1,0,1)); Conv2d(3, stride 2, padding 0)`): im2col of fp32 NHWC [B,H,W,C] ->
  * fp16 [B*Ho*Wo, 9*C], Ho = (H-2)/2 + 1, input pixel (2oy+ky, 2ox+kx), zero beyond the bottom / right edge. */
 int sgn_im2col3x3_s2_asym_f16(const float* d_x, int B, int H, int W, int C, void* d_out, void* stream);
+/* hi / lo split producers for the VAE's exact mode: fp32 [M,C] -> fp16 [M,2C]; nearest x2 upsample fp32 NHWC ->
+ * fp16 [B,2H,2W,2C]; the asymmetric stride-2 im2col with rows [hi(9C) | lo(9C)]. */
+int sgn_split_f16(const float* d_x, int64_t M, int C, void* d_out, void* stream);
+int sgn_upsample2x_split_f16(const float* d_x, int B, int H, int W, int C, void* d_out, void* stream);
+int sgn_im2col3x3_s2_asym_split_f16(const float* d_x, int B, int H, int W, int C, void* d_out, void* stream);
 /* ldm AttnBlock: out[m][:] = softmax(scale * scores[m][:]) as fp16; scores fp32 [M,N] (N % 4 == 0) from sgn_gemm_f16. */
 int sgn_softmax_rows_f16(const float* d_scores, int64_t M, int N, float scale, void* d_out, void* stream);
 /* quant_conv / post_quant_conv: 1x1 convolution over <= 16 channels, NCHW fp32; h_w [Cout,Cin], h_bias [Cout] on the

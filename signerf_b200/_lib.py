@@ -104,6 +104,10 @@ SIGNATURES = {
     "sgn_cfg_euler_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _f, _vp, _vp, _vp]),
     "sgn_conv3x3_small_tc": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "sgn_im2col3x3_s2_asym_f16": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "sgn_group_norm_split_f16": (_i, [_vp, _i, _i, _i, _i, _f, _vp, _vp, _i, _vp, _vp, _vp]),
+    "sgn_split_f16": (_i, [_vp, _i64, _i, _vp, _vp]),
+    "sgn_upsample2x_split_f16": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "sgn_im2col3x3_s2_asym_split_f16": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "sgn_softmax_rows_f16": (_i, [_vp, _i64, _i, _f, _vp, _vp]),
     "sgn_pointwise_nchw": (_i, [_vp, C.POINTER(_f), C.POINTER(_f), _i, _i, _i, _i64, _f, _vp, _vp]),
     "sgn_vae_sample_latent": (_i, [_vp, _vp, _i, _i, _i64, _f, _vp, _vp]),

@@ -88,7 +88,9 @@ __global__ void __launch_bounds__(512) k_gn_finalize(const double2* __restrict__
   }
 }
 
-// Pass 2: y = (x - mean) * rstd * gamma + beta, optional SiLU, fp16 out.
+// Pass 2: y = (x - mean) * rstd * gamma + beta, optional SiLU, fp16 out.  kSplit: rows of 2C halfs = [hi(y) | lo(y)] with
+// y = hi + lo to 2^-22 (operands of the fp32-exact "doubled K" contractions of the VAE).
+template <bool kSplit>
 __global__ void __launch_bounds__(256) k_gn_apply(const float* __restrict__ x, int HW, int C, int G, float eps,
                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                                   const float2* __restrict__ stats, int act_silu, __half* out) {
@@ -102,7 +104,7 @@ __global__ void __launch_bounds__(256) k_gn_apply(const float* __restrict__ x, i
   const int c4n = C >> 2, cpg = C / G;
   const size_t n4 = (size_t)HW * c4n;
   const float4* xb = reinterpret_cast<const float4*>(x + ((size_t)b * HW) * C);
-  uint2* ob = reinterpret_cast<uint2*>(out + ((size_t)b * HW) * C);
+  uint2* ob = reinterpret_cast<uint2*>(out + ((size_t)b * HW) * C * (kSplit ? 2 : 1));
   auto norm4 = [&](size_t i, float4 v) {
     const int c = 4 * (int)(i % c4n), g0 = c / cpg, g1 = (c + 2) / cpg;  // cpg is even: a pair never straddles groups
     const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c)), bt = __ldg(reinterpret_cast<const float4*>(beta + c));
@@ -113,7 +115,18 @@ __global__ void __launch_bounds__(256) k_gn_apply(const float* __restrict__ x, i
     uint2 u;
     u.x = *reinterpret_cast<uint32_t*>(&h0);
     u.y = *reinterpret_cast<uint32_t*>(&h1);
-    ob[i] = u;
+    if (!kSplit) {
+      ob[i] = u;
+    } else {
+      const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+      __half2 l0 = __floats2half2_rn(a - f0.x, d - f0.y), l1 = __floats2half2_rn(e - f1.x, f - f1.y);
+      uint2 ul;
+      ul.x = *reinterpret_cast<uint32_t*>(&l0);
+      ul.y = *reinterpret_cast<uint32_t*>(&l1);
+      const size_t o = (i / c4n) * (size_t)(2 * c4n) + (i % c4n);
+      ob[o] = u;
+      ob[o + c4n] = ul;
+    }
   };
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -545,8 +558,8 @@ extern "C" int64_t sgn_group_norm_ws_doubles(int B, int HW, int groups) {
   return (int64_t)B * groups * (2 * chunks + 1);
 }
 
-extern "C" int sgn_group_norm_f16(const float* d_x, int B, int HW, int C, int groups, float eps, const float* d_gamma,
-                                  const float* d_beta, int act_silu, double* d_ws, void* d_out, void* stream) {
+static int group_norm_impl(const float* d_x, int B, int HW, int C, int groups, float eps, const float* d_gamma,
+                           const float* d_beta, int act_silu, double* d_ws, void* d_out, void* stream, bool split) {
   SGN_CHECK_ARG(B >= 0 && HW > 0 && C > 0 && groups > 0, "bad shape");
   if (B == 0) return SGN_OK;
   SGN_CHECK_ARG(d_x && d_gamma && d_beta && d_ws && d_out, "null pointer");
@@ -564,10 +577,24 @@ extern "C" int sgn_group_norm_f16(const float* d_x, int B, int HW, int C, int gr
   SGN_LAUNCH_CHECK();
   size_t n4 = (size_t)HW * (C / 4);
   dim3 g2((unsigned)std::max<size_t>(1, std::min<size_t>((n4 + 511) / 512, (size_t)sm_count() * 8 / std::max(1, B) + 1)), B);
-  k_gn_apply<<<g2, 256, 0, ST(stream)>>>(d_x, HW, C, groups, eps, d_gamma, d_beta, stats, act_silu,
-                                         reinterpret_cast<__half*>(d_out));
+  if (split)
+    k_gn_apply<true><<<g2, 256, 0, ST(stream)>>>(d_x, HW, C, groups, eps, d_gamma, d_beta, stats, act_silu,
+                                                 reinterpret_cast<__half*>(d_out));
+  else
+    k_gn_apply<false><<<g2, 256, 0, ST(stream)>>>(d_x, HW, C, groups, eps, d_gamma, d_beta, stats, act_silu,
+                                                  reinterpret_cast<__half*>(d_out));
   SGN_LAUNCH_CHECK();
   return SGN_OK;
+}
+
+extern "C" int sgn_group_norm_f16(const float* d_x, int B, int HW, int C, int groups, float eps, const float* d_gamma,
+                                  const float* d_beta, int act_silu, double* d_ws, void* d_out, void* stream) {
+  return group_norm_impl(d_x, B, HW, C, groups, eps, d_gamma, d_beta, act_silu, d_ws, d_out, stream, false);
+}
+
+extern "C" int sgn_group_norm_split_f16(const float* d_x, int B, int HW, int C, int groups, float eps, const float* d_gamma,
+                                        const float* d_beta, int act_silu, double* d_ws, void* d_out, void* stream) {
+  return group_norm_impl(d_x, B, HW, C, groups, eps, d_gamma, d_beta, act_silu, d_ws, d_out, stream, true);
 }
 
 extern "C" int sgn_layer_norm_f16(const float* d_x, int64_t M, int C, float eps, const float* d_gamma,

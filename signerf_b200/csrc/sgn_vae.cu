@@ -27,7 +27,17 @@ static inline int grid_1d_v(size_t n, int block, int per_sm = 8) {
 // ------------------------------------------------------------------ asymmetric stride-2 im2col
 // x [B,H,W,C] fp32 -> out [B*Ho*Wo, 9*C] fp16, k = (ky*3+kx)*C + c, input pixel (2*oy + ky, 2*ox + kx); the single
 // row / column of padding sits at the bottom / right.
-__global__ void k_im2col_s2_asym(const float* __restrict__ x, int B, int H, int W, int c4, int Ho, int Wo, __half* out) {
+__device__ __forceinline__ void split4(float4 v, uint2& hi, uint2& lo) {
+  const __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+  const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+  const __half2 l0 = __floats2half2_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2half2_rn(v.z - f1.x, v.w - f1.y);
+  hi.x = *reinterpret_cast<const uint32_t*>(&h0), hi.y = *reinterpret_cast<const uint32_t*>(&h1);
+  lo.x = *reinterpret_cast<const uint32_t*>(&l0), lo.y = *reinterpret_cast<const uint32_t*>(&l1);
+}
+
+// split: row = [hi(9C) | lo(9C)]
+__global__ void k_im2col_s2_asym(const float* __restrict__ x, int B, int H, int W, int c4, int Ho, int Wo, int split,
+                                 __half* out) {
   const size_t n = (size_t)B * Ho * Wo * 9 * c4;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     int c = (int)(i % c4);
@@ -41,11 +51,45 @@ __global__ void k_im2col_s2_asym(const float* __restrict__ x, int B, int H, int 
     int iy = 2 * oy + tap / 3, ix = 2 * ox + tap % 3;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (iy < H && ix < W) v = __ldg(reinterpret_cast<const float4*>(x) + (((size_t)b * H + iy) * W + ix) * c4 + c);
-    __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
-    uint2 u;
-    u.x = *reinterpret_cast<uint32_t*>(&h0);
-    u.y = *reinterpret_cast<uint32_t*>(&h1);
-    reinterpret_cast<uint2*>(out)[i] = u;
+    uint2 hi, lo;
+    split4(v, hi, lo);
+    if (!split) {
+      reinterpret_cast<uint2*>(out)[i] = hi;
+    } else {
+      const size_t row = i / (9 * (size_t)c4), k = i % (9 * (size_t)c4);
+      reinterpret_cast<uint2*>(out)[row * 18 * c4 + k] = hi;
+      reinterpret_cast<uint2*>(out)[row * 18 * c4 + 9 * c4 + k] = lo;
+    }
+  }
+}
+
+// fp32 [M, C] -> fp16 [M, 2C] = [hi | lo]
+__global__ void k_split_f16(const float* __restrict__ x, size_t M, int c4, __half* out) {
+  const size_t n = M * c4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint2 hi, lo;
+    split4(__ldg(reinterpret_cast<const float4*>(x) + i), hi, lo);
+    const size_t o = (i / c4) * (size_t)(2 * c4) + (i % c4);
+    reinterpret_cast<uint2*>(out)[o] = hi;
+    reinterpret_cast<uint2*>(out)[o + c4] = lo;
+  }
+}
+
+// nearest x2 upsample of fp32 NHWC -> fp16 [B, 2H, 2W, 2C] = [hi | lo]
+__global__ void k_upsample2x_split(const float* __restrict__ x, int B, int H, int W, int c4, __half* out) {
+  const size_t n = (size_t)B * 2 * H * 2 * W * c4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % c4);
+    size_t r = i / c4;
+    const int ox = (int)(r % (2 * W));
+    r /= 2 * W;
+    const int oy = (int)(r % (2 * H));
+    const int b = (int)(r / (2 * H));
+    uint2 hi, lo;
+    split4(__ldg(reinterpret_cast<const float4*>(x) + (((size_t)b * H + oy / 2) * W + ox / 2) * c4 + c), hi, lo);
+    const size_t o = (i / c4) * (size_t)(2 * c4) + c;
+    reinterpret_cast<uint2*>(out)[o] = hi;
+    reinterpret_cast<uint2*>(out)[o + c4] = lo;
   }
 }
 
@@ -323,13 +367,43 @@ static int64_t pil_ws_ints(int in_size, int out_size) {
 
 using namespace sgn;
 
+extern "C" int sgn_split_f16(const float* d_x, int64_t M, int C, void* d_out, void* stream) {
+  SGN_CHECK_ARG(M >= 0 && C > 0 && C % 4 == 0, "bad shape (C % 4)");
+  if (M == 0) return SGN_OK;
+  SGN_CHECK_ARG(d_x && d_out, "null pointer");
+  k_split_f16<<<grid_1d_v((size_t)M * (C / 4), 256), 256, 0, STV(stream)>>>(d_x, (size_t)M, C / 4, reinterpret_cast<__half*>(d_out));
+  SGN_LAUNCH_CHECK();
+  return SGN_OK;
+}
+
+extern "C" int sgn_upsample2x_split_f16(const float* d_x, int B, int H, int W, int C, void* d_out, void* stream) {
+  SGN_CHECK_ARG(B >= 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "bad shape (C % 4)");
+  if (B == 0) return SGN_OK;
+  SGN_CHECK_ARG(d_x && d_out, "null pointer");
+  k_upsample2x_split<<<grid_1d_v((size_t)B * 4 * H * W * (C / 4), 256), 256, 0, STV(stream)>>>(d_x, B, H, W, C / 4,
+                                                                                              reinterpret_cast<__half*>(d_out));
+  SGN_LAUNCH_CHECK();
+  return SGN_OK;
+}
+
+extern "C" int sgn_im2col3x3_s2_asym_split_f16(const float* d_x, int B, int H, int W, int C, void* d_out, void* stream) {
+  SGN_CHECK_ARG(B >= 0 && H >= 2 && W >= 2 && C > 0 && C % 4 == 0, "bad shape (C % 4, H, W >= 2)");
+  if (B == 0) return SGN_OK;
+  SGN_CHECK_ARG(d_x && d_out, "null pointer");
+  const int Ho = (H - 2) / 2 + 1, Wo = (W - 2) / 2 + 1;
+  const size_t n = (size_t)B * Ho * Wo * 9 * (C / 4);
+  k_im2col_s2_asym<<<grid_1d_v(n, 256), 256, 0, STV(stream)>>>(d_x, B, H, W, C / 4, Ho, Wo, 1, reinterpret_cast<__half*>(d_out));
+  SGN_LAUNCH_CHECK();
+  return SGN_OK;
+}
+
 extern "C" int sgn_im2col3x3_s2_asym_f16(const float* d_x, int B, int H, int W, int C, void* d_out, void* stream) {
   SGN_CHECK_ARG(B >= 0 && H >= 2 && W >= 2 && C > 0 && C % 4 == 0, "bad shape (C % 4, H, W >= 2)");
   if (B == 0) return SGN_OK;
   SGN_CHECK_ARG(d_x && d_out, "null pointer");
   const int Ho = (H - 2) / 2 + 1, Wo = (W - 2) / 2 + 1;
   const size_t n = (size_t)B * Ho * Wo * 9 * (C / 4);
-  k_im2col_s2_asym<<<grid_1d_v(n, 256), 256, 0, STV(stream)>>>(d_x, B, H, W, C / 4, Ho, Wo, reinterpret_cast<__half*>(d_out));
+  k_im2col_s2_asym<<<grid_1d_v(n, 256), 256, 0, STV(stream)>>>(d_x, B, H, W, C / 4, Ho, Wo, 0, reinterpret_cast<__half*>(d_out));
   SGN_LAUNCH_CHECK();
   return SGN_OK;
 }

@@ -152,8 +152,9 @@ def _call(dev, fn, *args) -> None:
 
 
 def group_norm_f16(x: Tensor, B: int, HW: int, groups: int, eps: float, gamma: Tensor, beta: Tensor, act_silu: bool,
-                   ws: Optional[Tensor] = None) -> Tensor:
-    """GroupNorm(groups) (+SiLU) of fp32 [B*HW, C] -> fp16 [B*HW, C]; ws: float64 scratch (allocated when None)."""
+                   ws: Optional[Tensor] = None, split: bool = False) -> Tensor:
+    """GroupNorm(groups) (+SiLU) of fp32 [B*HW, C] -> fp16 [B*HW, C]; ws: float64 scratch (allocated when None).
+    split: fp16 [B*HW, 2C] = [hi | lo] (y = hi + lo to 2^-22)."""
     _chk(x, torch.float32, "x")
     need = int(_lib.load().sgn_group_norm_ws_doubles(B, HW, groups))
     if ws is None:
@@ -161,9 +162,9 @@ def group_norm_f16(x: Tensor, B: int, HW: int, groups: int, eps: float, gamma: T
     _chk(ws, torch.float64, "ws")
     if ws.numel() < need:
         raise ValueError(f"GroupNorm scratch needs {need} doubles, got {ws.numel()}")
-    out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
-    _call(x.device, _lib.load().sgn_group_norm_f16, _ptr(x), B, HW, x.shape[1], groups, eps, _ptr(gamma), _ptr(beta),
-          int(act_silu), _ptr(ws), _ptr(out))
+    out = torch.empty((x.shape[0], x.shape[1] * (2 if split else 1)), dtype=torch.float16, device=x.device)
+    fn = _lib.load().sgn_group_norm_split_f16 if split else _lib.load().sgn_group_norm_f16
+    _call(x.device, fn, _ptr(x), B, HW, x.shape[1], groups, eps, _ptr(gamma), _ptr(beta), int(act_silu), _ptr(ws), _ptr(out))
     return out
 
 

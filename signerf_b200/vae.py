@@ -48,14 +48,33 @@ class VAEConfig:
 
 
 # ---------------------------------------------------------------------------------------------- operator front ends
-def im2col3x3_s2_asym_f16(x: Tensor, B: int, H: int, W: int):
-    """fp32 [B*H*W, C] -> (fp16 [B*Ho*Wo, 9C], Ho, Wo) for ldm Downsample (pad (0,1,0,1), 3x3, stride 2)."""
+def im2col3x3_s2_asym_f16(x: Tensor, B: int, H: int, W: int, split: bool = False):
+    """fp32 [B*H*W, C] -> (fp16 [B*Ho*Wo, 9C], Ho, Wo) for ldm Downsample (pad (0,1,0,1), 3x3, stride 2);
+    split: rows [hi(9C) | lo(9C)]."""
     _chk(x, torch.float32, "x")
     Cc = x.shape[-1]
     Ho, Wo = (H - 2) // 2 + 1, (W - 2) // 2 + 1
-    out = torch.empty((B * Ho * Wo, 9 * Cc), dtype=torch.float16, device=x.device)
-    _call(x.device, _lib.load().sgn_im2col3x3_s2_asym_f16, _ptr(x), B, H, W, Cc, _ptr(out))
+    out = torch.empty((B * Ho * Wo, (18 if split else 9) * Cc), dtype=torch.float16, device=x.device)
+    fn = _lib.load().sgn_im2col3x3_s2_asym_split_f16 if split else _lib.load().sgn_im2col3x3_s2_asym_f16
+    _call(x.device, fn, _ptr(x), B, H, W, Cc, _ptr(out))
     return out, Ho, Wo
+
+
+def split_f16(x: Tensor) -> Tensor:
+    """fp32 [M,C] -> fp16 [M,2C] = [hi | lo]."""
+    _chk(x, torch.float32, "x")
+    out = torch.empty((x.shape[0], 2 * x.shape[1]), dtype=torch.float16, device=x.device)
+    _call(x.device, _lib.load().sgn_split_f16, _ptr(x), x.shape[0], x.shape[1], _ptr(out))
+    return out
+
+
+def upsample2x_split_f16(x: Tensor, B: int, H: int, W: int) -> Tensor:
+    """fp32 [B*H*W, C] -> fp16 NHWC [B, 2H, 2W, 2C] = nearest upsample, [hi | lo]."""
+    _chk(x, torch.float32, "x")
+    Cc = x.shape[-1]
+    out = torch.empty((B, 2 * H, 2 * W, 2 * Cc), dtype=torch.float16, device=x.device)
+    _call(x.device, _lib.load().sgn_upsample2x_split_f16, _ptr(x), B, H, W, Cc, _ptr(out))
+    return out
 
 
 def softmax_rows_f16(scores: Tensor, scale: float, out: Optional[Tensor] = None) -> Tensor:
@@ -177,8 +196,13 @@ class VAEB200:
 
     ATTN_QUERY_CHUNK = 8192   # score slab = chunk x tokens fp32 (2 GB at 65 536 tokens)
 
-    def __init__(self, cfg: VAEConfig, weights: Mapping[str, Tensor], device="cuda", scale_factor: float = SCALE_FACTOR):
-        self.cfg, self.dev, self.scale_factor = cfg, torch.device(device), scale_factor
+    def __init__(self, cfg: VAEConfig, weights: Mapping[str, Tensor], device="cuda", scale_factor: float = SCALE_FACTOR,
+                 exact: bool = True):
+        """exact: every convolution / shortcut / down / upsample contraction takes its activation as fp16 hi + lo halves
+        against the weights repeated along K (2x the tensor-core FLOPs): the fp32 operator to fp32 rounding for
+        fp16-representable weights, as A1111 runs the SDXL VAE in fp32.  exact=False: single fp16 operand (1.5-2e-3
+        relative L2 on the decoded image).  The mid-block attention always runs with fp16 q / k / v."""
+        self.cfg, self.dev, self.scale_factor, self.exact = cfg, torch.device(device), scale_factor, bool(exact)
         if cfg.ch % 64 != 0:
             raise ValueError("the tensor-core conv needs channel counts that are multiples of 64")
         schema = vae_param_schema(cfg)
@@ -197,7 +221,7 @@ class VAEB200:
             elif n in ("encoder.conv_in.weight", "decoder.conv_in.weight"):
                 p.conv32(n)
             elif shp[2] == 3:
-                p.conv16(n)
+                (self._pack_lin if ".downsample.conv." in n else self._pack_conv)(n)   # the stride-2 conv is an im2col GEMM
             elif n.endswith(".q.weight"):      # q and k projections share one GEMM
                 b = n[: -len("q.weight")]
                 c = shp[0]
@@ -206,6 +230,8 @@ class VAEB200:
                 p.t[b + "qk.bias"] = torch.cat([p._get(b + "q.bias"), p._get(b + "k.bias")]).contiguous()
             elif n.endswith(".k.weight"):
                 continue
+            elif n.endswith(".nin_shortcut.weight"):
+                self._pack_lin(n)
             else:
                 p.lin16(n)
         # the two 1x1 quant convs travel as kernel parameters: keep them on the host
@@ -215,23 +241,46 @@ class VAEB200:
                             weights["post_quant_conv.bias"].detach().float().cpu())
         p.w = None
 
+    # ------------------------------------------------------------------ packing (exact mode repeats the weights along K)
+    def _pack_conv(self, name: str) -> Tensor:
+        """[Co,Ci,3,3] -> fp16 [Co, 9*Ci] tap-major; exact: [Co, 9*2Ci] with every tap's channel block repeated."""
+        key = name + ("#c16x2" if self.exact else "#c16")
+        if key not in self.p.t:
+            w = self.p._get(name).permute(0, 2, 3, 1)                       # [Co,3,3,Ci]
+            if self.exact:
+                w = torch.cat([w, w], dim=3)
+            self.p.t[key] = w.reshape(w.shape[0], -1).half().contiguous()
+        return self.p.t[key]
+
+    def _pack_lin(self, name: str, taps: int = 1) -> Tensor:
+        """1x1 conv / im2col GEMM weight [Co, K]; exact: [W | W]."""
+        key = name + ("#l16x2" if self.exact else "#l16")
+        if key not in self.p.t:
+            w = self.p._get(name)
+            w = (w.permute(0, 2, 3, 1) if w.dim() == 4 else w).reshape(w.shape[0], -1)
+            self.p.t[key] = (torch.cat([w, w], 1) if self.exact else w).half().contiguous()
+        return self.p.t[key]
+
     # ------------------------------------------------------------------ blocks
-    def _gn(self, x: Act, name: str, act: bool) -> Tensor:
-        return K.group_norm_f16(x.t, x.B, x.H * x.W, 32, 1e-6, self.p.f32(name + ".weight"), self.p.f32(name + ".bias"), act)
+    def _gn(self, x: Act, name: str, act: bool, split: Optional[bool] = None) -> Tensor:
+        return K.group_norm_f16(x.t, x.B, x.H * x.W, 32, 1e-6, self.p.f32(name + ".weight"), self.p.f32(name + ".bias"), act,
+                                split=self.exact if split is None else split)
 
     def resblock(self, pre: str, x: Act) -> Act:
         p = self.p
         cout = p.f32(pre + ".conv1.bias").shape[0]
         a16 = self._gn(x, pre + ".norm1", True)
-        h = K.conv3x3_f16(a16.view(x.B, x.H, x.W, x.C), p.conv16(pre + ".conv1.weight"), p.f32(pre + ".conv1.bias"))
+        h = K.conv3x3_f16(a16.view(x.B, x.H, x.W, -1), self._pack_conv(pre + ".conv1.weight"), p.f32(pre + ".conv1.bias"))
         b16 = self._gn(Act(h, x.B, x.H, x.W), pre + ".norm2", True)
         del a16, h
         if x.C != cout:
-            skip = K.gemm_f16(K.cast_f16(x.t), p.lin16(pre + ".nin_shortcut.weight"), p.f32(pre + ".nin_shortcut.bias"))
-            out = K.conv3x3_f16(b16.view(x.B, x.H, x.W, cout), p.conv16(pre + ".conv2.weight"), p.f32(pre + ".conv2.bias"),
+            x16 = split_f16(x.t) if self.exact else K.cast_f16(x.t)
+            skip = K.gemm_f16(x16, self._pack_lin(pre + ".nin_shortcut.weight"), p.f32(pre + ".nin_shortcut.bias"))
+            del x16
+            out = K.conv3x3_f16(b16.view(x.B, x.H, x.W, -1), self._pack_conv(pre + ".conv2.weight"), p.f32(pre + ".conv2.bias"),
                                 residual=skip, out=skip)
         else:
-            out = K.conv3x3_f16(b16.view(x.B, x.H, x.W, cout), p.conv16(pre + ".conv2.weight"), p.f32(pre + ".conv2.bias"),
+            out = K.conv3x3_f16(b16.view(x.B, x.H, x.W, -1), self._pack_conv(pre + ".conv2.weight"), p.f32(pre + ".conv2.bias"),
                                 residual=x.t)
         return Act(out, x.B, x.H, x.W)
 
@@ -239,7 +288,7 @@ class VAEB200:
         """AttnBlock: x + proj_out(softmax(q k^T / sqrt(C)) v), one head over all H*W tokens."""
         p = self.p
         c, T = x.C, x.H * x.W
-        h16 = self._gn(x, pre + ".norm", False)
+        h16 = self._gn(x, pre + ".norm", False, split=False)
         qk = K.gemm_f16(h16, p.t[pre + ".qk.weight"], p.t[pre + ".qk.bias"], out_f16=True)  # [B*T, 2C]
         o16 = torch.empty((x.B * T, c), dtype=torch.float16, device=self.dev)
         if T % 8 != 0:
@@ -268,7 +317,7 @@ class VAEB200:
 
     def _conv_out(self, side: str, h: Act) -> Tensor:
         a16 = self._gn(h, side + ".norm_out", True)
-        return K.conv3x3_f16(a16.view(h.B, h.H, h.W, h.C), self.p.conv16(side + ".conv_out.weight"),
+        return K.conv3x3_f16(a16.view(h.B, h.H, h.W, -1), self._pack_conv(side + ".conv_out.weight"),
                              self.p.f32(side + ".conv_out.bias"), nchw=True)
 
     # ------------------------------------------------------------------ public
@@ -282,9 +331,9 @@ class VAEB200:
             for j in range(cfg.num_res_blocks):
                 h = self.resblock(f"encoder.down.{i}.block.{j}", h)
             if i != n - 1:
-                col, ho, wo = im2col3x3_s2_asym_f16(h.t, h.B, h.H, h.W)
+                col, ho, wo = im2col3x3_s2_asym_f16(h.t, h.B, h.H, h.W, split=self.exact)
                 pre = f"encoder.down.{i}.downsample.conv"
-                h = Act(K.gemm_f16(col, p.conv16(pre + ".weight"), p.f32(pre + ".bias")), h.B, ho, wo)
+                h = Act(K.gemm_f16(col, self._pack_lin(pre + ".weight"), p.f32(pre + ".bias")), h.B, ho, wo)
                 del col
         h = self.mid("encoder.mid", h)
         return pointwise_nchw(self._conv_out("encoder", h), *self._quant)
@@ -304,7 +353,7 @@ class VAEB200:
                 h = self.resblock(f"decoder.up.{i}.block.{j}", h)
             if i != 0:
                 pre = f"decoder.up.{i}.upsample.conv"
-                u16 = K.upsample2x_f16(h.t, h.B, h.H, h.W)
-                h = Act(K.conv3x3_f16(u16, p.conv16(pre + ".weight"), p.f32(pre + ".bias")), h.B, 2 * h.H, 2 * h.W)
+                u16 = upsample2x_split_f16(h.t, h.B, h.H, h.W) if self.exact else K.upsample2x_f16(h.t, h.B, h.H, h.W)
+                h = Act(K.conv3x3_f16(u16, self._pack_conv(pre + ".weight"), p.f32(pre + ".bias")), h.B, 2 * h.H, 2 * h.W)
                 del u16
         return self._conv_out("decoder", h)

@@ -105,9 +105,9 @@ def test_softmax_rows_and_asym_im2col():
     assert (ho, wo) == (4, 5) and torch.equal(col.float(), ref.half().float())
 
 
-def _b200_vae(cfg, ref):
+def _b200_vae(cfg, ref, exact=True):
     from signerf_b200 import vae as V
-    return V.VAEB200(V.VAEConfig(**cfg.__dict__), ref.state_dict(), "cuda")
+    return V.VAEB200(V.VAEConfig(**cfg.__dict__), ref.state_dict(), "cuda", exact=exact)
 
 
 def test_vae_blocks_match_oracle():
@@ -132,28 +132,37 @@ def test_vae_blocks_match_oracle():
     x, a = act(128, 16, 24)
     assert rel_l2(net.attn("encoder.mid.attn_1", a).nchw(), ref.encoder.mid.attn_1(x)) < 1e-3
     x, a = act(64, 18, 12)
-    col, ho, wo = V.im2col3x3_s2_asym_f16(a.t, 1, 18, 12)
-    d = K.gemm_f16(col, net.p.conv16("encoder.down.0.downsample.conv.weight"), net.p.f32("encoder.down.0.downsample.conv.bias"))
-    assert rel_l2(Act(d, 1, ho, wo).nchw(), ref.encoder.down[0].downsample(x)) < 1e-3
+    col, ho, wo = V.im2col3x3_s2_asym_f16(a.t, 1, 18, 12, split=True)
+    d = K.gemm_f16(col, net._pack_lin("encoder.down.0.downsample.conv.weight"), net.p.f32("encoder.down.0.downsample.conv.bias"))
+    assert rel_l2(Act(d, 1, ho, wo).nchw(), ref.encoder.down[0].downsample(x)) < 1e-5
+    # the hi / lo operand split makes a ResnetBlock fp32-exact; the single-operand mode stays within 1e-3
+    x, a = act(64, 24, 16)
+    assert rel_l2(net.resblock("encoder.down.1.block.0", a).nchw(), ref.encoder.down[1].block[0](x)) < 1e-5
+    fast = _b200_vae(cfg, ref, exact=False)
+    assert 1e-5 < rel_l2(fast.resblock("encoder.down.1.block.0", a).nchw(), ref.encoder.down[1].block[0](x)) < 1e-3
 
 
-def _check_decode(got, ref):
-    """The decoder is ~30 fp16-operand convolutions deep (fp32 accumulate, fp32 residual stream): each rounds its input
-    once (2^-11), which accumulates to 1.5-2e-3 relative L2 on the output image (measured on B200).  The image is
-    quantised to uint8 right after (processing.py): an error of 3e-4 in [-1,1] units moves the 4-6 % of pixels that sit
-    within it of a quantisation edge by ONE level, never more."""
-    assert rel_l2(got, ref) < 2.5e-3
+def _check_decode(got, ref, exact=True):
+    """exact mode (hi / lo operand split): the only fp16 rounding left on the path is inside the mid-block attention.
+    Single-operand mode: the decoder is ~30 fp16-operand convolutions deep, each rounding its input once (2^-11), which
+    accumulates to 1.5-2e-3 relative L2 on the image (measured on B200) and moves the 4-6 % of pixels that sit within 3e-4
+    of a uint8 quantisation edge by ONE level, never more."""
     a, b = I.vae_output_to_u8(got[0].cpu().numpy()).astype(int), I.vae_output_to_u8(ref[0].cpu().numpy()).astype(int)
-    assert np.abs(a - b).max() <= 1 and (a != b).mean() < 0.08, (np.abs(a - b).max(), (a != b).mean())
+    if exact:
+        assert rel_l2(got, ref) < 1e-3
+        assert np.abs(a - b).max() <= 1 and (a != b).mean() < 0.02, (np.abs(a - b).max(), (a != b).mean())
+    else:
+        assert rel_l2(got, ref) < 2.5e-3
+        assert np.abs(a - b).max() <= 1 and (a != b).mean() < 0.08, (np.abs(a - b).max(), (a != b).mean())
 
 
-@pytest.mark.parametrize("hw", [(64, 64), (96, 160)])
-def test_vae_encode_decode_match_oracle(hw):
+@pytest.mark.parametrize("hw,exact", [((64, 64), True), ((96, 160), True), ((64, 64), False)])
+def test_vae_encode_decode_match_oracle(hw, exact):
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     cfg = VR.tiny_vae_config()
     ref = VR.make_vae(cfg, seed=0, device="cuda")
-    net = _b200_vae(cfg, ref)
+    net = _b200_vae(cfg, ref, exact)
     gen = torch.Generator().manual_seed(2)
     x = (torch.rand(1, 3, *hw, generator=gen) * 2 - 1).cuda()
     noise = torch.randn(1, 4, hw[0] // 8, hw[1] // 8, generator=gen).cuda()
@@ -162,7 +171,7 @@ def test_vae_encode_decode_match_oracle(hw):
     z = net.encode(x, noise)
     assert rel_l2(z, ref.encode(x, noise)) < 1e-3 and rel_l2(net.encode(x), ref.encode(x)) < 1e-3
     zr = ref.encode(x, noise)
-    _check_decode(net.decode(zr), ref.decode(zr))
+    _check_decode(net.decode(zr), ref.decode(zr), exact)
 
 
 def test_vae_full_width_decoder_tail_matches_oracle():
