@@ -4,6 +4,7 @@
 // linears, the sinusoidal timestep embedding and the fused CFG + inpaint-blend + Euler-ancestral sampler update.
 // Layout: NHWC.  The residual stream is fp32, everything handed to a tensor-core kernel is fp16.
 #include <algorithm>
+#include <cstdlib>
 
 #include "sgn_common.cuh"
 
@@ -188,11 +189,21 @@ __global__ void __launch_bounds__(256) k_layer_norm_reg(const float* __restrict_
   const int lane = threadIdx.x & 31;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long m = warp0; m < M; m += nwarps) {
-    const float4* xr = reinterpret_cast<const float4*>(x + m * C);
-    float4 v[NV];
+  // software pipeline over the warp's rows: the next row's loads are in flight while this one is reduced and stored,
+  // so the read and the write streams of the launch overlap instead of running as two phases
+  float4 v[NV], vn[NV];
+  if (warp0 < M) {
+    const float4* xr = reinterpret_cast<const float4*>(x + warp0 * C);
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] = xr[lane + 32 * i];
+  }
+  for (long long m = warp0; m < M; m += nwarps) {
+    const bool more = m + nwarps < M;
+    if (more) {
+      const float4* xr = reinterpret_cast<const float4*>(x + (m + nwarps) * C);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) vn[i] = xr[lane + 32 * i];
+    }
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
@@ -219,6 +230,10 @@ __global__ void __launch_bounds__(256) k_layer_norm_reg(const float* __restrict_
       u.x = *reinterpret_cast<uint32_t*>(&h0);
       u.y = *reinterpret_cast<uint32_t*>(&h1);
       orow[j] = u;
+    }
+    if (more) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[i] = vn[i];
     }
   }
 }
@@ -602,8 +617,11 @@ extern "C" int sgn_layer_norm_f16(const float* d_x, int64_t M, int C, float eps,
   SGN_CHECK_ARG(M >= 0 && C > 0 && C % 4 == 0, "C must be a multiple of 4");
   if (M == 0) return SGN_OK;
   SGN_CHECK_ARG(d_x && d_gamma && d_beta && d_out, "null pointer");
-  const int grid = grid_1d((size_t)M * 32, 256);
+  int grid = grid_1d((size_t)M * 32, 256);
   __half* o = reinterpret_cast<__half*>(d_out);
+  static const int ln_rows = [] { const char* e = getenv("SGN_LN_ROWS_PER_WARP"); return e ? atoi(e) : 4; }();
+  if (C % 128 == 0 && ln_rows > 1)   // register kernels: ~ln_rows rows per warp (pipelined), at least 2 blocks per SM
+    grid = std::max(std::min(grid, 2 * sm_count()), std::min(grid, (int)((M + 8 * ln_rows - 1) / (8 * ln_rows))));
   switch (C % 128 == 0 ? C / 128 : 0) {
     case 1: k_layer_norm_reg<1><<<grid, 256, 0, ST(stream)>>>(d_x, M, eps, d_gamma, d_beta, o); break;
     case 2: k_layer_norm_reg<2><<<grid, 256, 0, ST(stream)>>>(d_x, M, eps, d_gamma, d_beta, o); break;
