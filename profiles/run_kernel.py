@@ -39,3 +39,18 @@ if which == "gemm_mid":       # attention out-projection of the 1280-channel lev
     for _ in range(3):
         nn_ops.gemm_f16(a, w, b, residual=r, out=r)
     torch.cuda.synchronize()
+if which == "cross_attention":   # attn2 of the 1280-channel level: 4096 queries x 77 prompt tokens, 20 heads
+    B, heads, T = 2, 20, 4096
+    c = heads * 64
+    q = torch.randn(B * T, c, device="cuda").half()
+    kv = torch.randn(B * 77, 2 * c, device="cuda").half()
+    for _ in range(3):
+        nn_ops.attention_f16(q, kv[:, :c], kv[:, c:], B, heads)
+    torch.cuda.synchronize()
+if which == "hint_conv":         # ControlNet input_hint_block 16 -> 16 at the 2048^2 sheet, fp32-exact on mma.sync
+    x = torch.randn(1, 2048, 2048, 16, device="cuda")
+    w = torch.randn(16, 9 * 16, device="cuda").half()
+    b = torch.randn(16, device="cuda")
+    for _ in range(3):
+        nn_ops.conv3x3_small_tc(x, w, b, act_silu=True)
+    torch.cuda.synchronize()

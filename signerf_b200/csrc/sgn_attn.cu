@@ -373,7 +373,7 @@ k_cross_attention(const __half* __restrict__ q, long long ldq, const __half* __r
                   __half* __restrict__ out, long long ldo, int q_per_cta) {
   __shared__ __align__(16) __half sK[kXaKv * kXaPitch];
   __shared__ __align__(16) __half sV[kXaKv * kXaPitch];
-  __shared__ __align__(16) __half sQ[kXaQ * kXaPitch];
+  __shared__ __align__(16) __half sQ2[2][kXaQ * kXaPitch];   // double-buffered query tiles (cp.async)
   const int head = blockIdx.y, img = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
@@ -390,15 +390,24 @@ k_cross_attention(const __half* __restrict__ q, long long ldq, const __half* __r
   const int q_begin = blockIdx.x * q_per_cta;
   const int q_end = min(T_q, q_begin + q_per_cta);
   const int g = lane >> 2, col0 = (lane & 3) * 2;
-  for (int q0 = q_begin; q0 < q_end; q0 += kXaQ) {
-    __syncthreads();   // the previous tile's reads of sQ are done (first pass: nothing pending)
+  // 16-byte cp.async copies of one 64 x 64 query tile; rows past T_q are zero-filled (src-size 0)
+  auto load_q = [&](int q0, __half* dst) {
     for (int c = tid; c < kXaQ * 8; c += 128) {
       const int r = c >> 3, j = c & 7;
-      uint4 x = zero;
-      if (q0 + r < T_q) x = *reinterpret_cast<const uint4*>(q + ((long long)img * T_q + q0 + r) * ldq + head * kHeadDim + j * 8);
-      *reinterpret_cast<uint4*>(sQ + r * kXaPitch + j * 8) = x;
+      const bool ok = q0 + r < T_q;
+      const __half* src = q + ((long long)img * T_q + (ok ? q0 + r : 0)) * ldq + head * kHeadDim + j * 8;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tc::smem_u32(dst + r * kXaPitch + j * 8)), "l"(src),
+                   "r"(ok ? 16 : 0) : "memory");
     }
-    __syncthreads();
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  load_q(q_begin, sQ2[0]);
+  int buf = 0;
+  for (int q0 = q_begin; q0 < q_end; q0 += kXaQ, buf ^= 1) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();   // this tile (and, first pass, K / V) visible to all; the other buffer's readers are done
+    if (q0 + kXaQ < q_end) load_q(q0 + kXaQ, sQ2[buf ^ 1]);   // next tile in flight while this one is computed
+    const __half* sQ = sQ2[buf];
     float s[kXaKv / 8][4];
 #pragma unroll
     for (int nt = 0; nt < kXaKv / 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
