@@ -112,9 +112,9 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       tc::mbar_init(&s_full[s], 1);
-      tc::mbar_init(&p_full[s], 128);
+      tc::mbar_init(&p_full[s], 4);    // one arrival per softmax warp (128 per-thread arrivals serialise on the barrier word)
       tc::mbar_init(&o_full[s], 1);
-      tc::mbar_init(&s_free[s], 128);
+      tc::mbar_init(&s_free[s], 4);
     }
     tc::mbar_fence_init();
   }
@@ -205,7 +205,8 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t ts = tS + x * kKvTile + lane_addr;
     const uint32_t to = tO + x * kHeadDim + lane_addr;
 
-    if (x == 1) named_arrive(1, 256);  // group A takes the first turn
+    constexpr bool kTurns = true;   // (free-running groups measure the same as turn-taking)
+    if (kTurns && x == 1) named_arrive(1, 256);  // group A takes the first turn
     for (int j = 0; j < n_kv; ++j) {
       const int kv_rem = p.T_kv - j * kKvTile;  // >= 1
       tc::mbar_wait(&s_full[x], j & 1);
@@ -215,7 +216,8 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       for (int c = 0; c < 4; ++c) tc::tmem_ld32(ts + c * 32, s + c * 32);
       tc::tmem_ld_wait();
       tc::tc_fence_before();
-      tc::mbar_arrive(&s_free[x]);     // the issuer may overwrite S_x with Q_x K_{j+1}^T now
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&s_free[x]);     // the issuer may overwrite S_x with Q_x K_{j+1}^T now
       if (kv_rem < kKvTile) {
 #pragma unroll
         for (int q = 0; q < 128; ++q)
@@ -230,12 +232,18 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const float mx = fmaxf(mx0, mx1);
       // P_x(j-1) V(j-1) must be complete before P_x is rewritten or O_x rescaled; P_x(j) V(j) is not issued before
       // this thread arrives on p_full, so O_x is quiescent in between.
-      if (j > 0) {
+      // The wait is only needed before O is rescaled (rare) or P is rewritten (the first tcgen05.st, half a tile of
+      // exponentials later): variants >= 1 defer it, which takes the P.V latency off the softmax critical path.
+      constexpr bool kDeferO = kVariant >= 1;
+      bool o_ready = j == 0;
+      const bool grow = (mx - m_run) * sc > 8.f;   // also true on the first tile (m_run = -inf)
+      const bool any_grow = __any_sync(0xffffffffu, grow);
+      if (j > 0 && (!kDeferO || any_grow)) {
         tc::mbar_wait(&o_full[x], (j - 1) & 1);
         tc::tc_fence_after();
+        o_ready = true;
       }
-      const bool grow = (mx - m_run) * sc > 8.f;   // also true on the first tile (m_run = -inf)
-      if (__any_sync(0xffffffffu, grow) && j > 0) {
+      if (any_grow && j > 0) {
         const float alpha = grow ? ex2((m_run - mx) * sc) : 1.f;
         uint32_t o[16];
 #pragma unroll
@@ -252,7 +260,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       if (grow) m_run = mx;
       const float neg_m = -m_run * sc;
       float psum0 = 0.f, psum1 = 0.f;
-      named_sync(1 + x, 256);            // my turn on the MUFU pipe
+      if (kTurns) named_sync(1 + x, 256);            // my turn on the MUFU pipe
       if constexpr (kVariant == 0) {
 #pragma unroll
         for (int c = 0; c < 2; ++c) {      // 64 keys -> 32 packed columns per tcgen05.st
@@ -282,7 +290,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
           for (int q = 0; q < 16; ++q) {
             const float t = fmaf(__uint_as_float(s[b * 16 + q]), sc, neg_m);
-            s[b * 16 + q] = __float_as_uint(kVariant == 2 ? ex2_v(t) : ex2(t));
+            s[b * 16 + q] = __float_as_uint(ex2(t));
           }
         };
         exp_block(0);
@@ -298,16 +306,24 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             __half2 h = __floats2half2_rn(e[2 * q], e[2 * q + 1]);
             pk[(b & 3) * 8 + q] = *reinterpret_cast<uint32_t*>(&h);
           }
-          if ((b & 3) == 3) tc::tmem_st32(tp + (b >> 2) * 32, pk);
+          if ((b & 3) == 3) {
+            if (!o_ready) {   // warp-uniform
+              tc::mbar_wait(&o_full[x], (j - 1) & 1);
+              tc::tc_fence_after();
+              o_ready = true;
+            }
+            tc::tmem_st32(tp + (b >> 2) * 32, pk);
+          }
         }
       }
-      named_arrive(2 - x, 256);          // hand the turn to the other warpgroup
+      if (kTurns) named_arrive(2 - x, 256);          // hand the turn to the other warpgroup
       tc::tmem_st_wait();
       l_run += psum0 + psum1;
       tc::tc_fence_before();          // P_x written, O_x accesses done before the issuer touches them
-      tc::mbar_arrive(&p_full[x]);
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&p_full[x]);
     }
-    if (x == 0) named_sync(1, 256);      // absorb group B's last hand-over
+    if (kTurns && x == 0) named_sync(1, 256);      // absorb group B's last hand-over
     // O_x complete after the last P.V
     tc::mbar_wait(&o_full[x], (n_kv - 1) & 1);
     tc::tc_fence_after();
@@ -511,7 +527,6 @@ extern "C" int sgn_attention_f16(const void* d_q, int64_t ldq, const void* d_k, 
   if (!attr_set) {
     SGN_CUDA(cudaFuncSetAttribute(k_attention_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
     SGN_CUDA(cudaFuncSetAttribute(k_attention_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
-    SGN_CUDA(cudaFuncSetAttribute(k_attention_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
     attr_set = true;
   }
   CUtensorMap tmQ, tmK, tmV;
@@ -533,7 +548,7 @@ extern "C" int sgn_attention_f16(const void* d_q, int64_t ldq, const void* d_k, 
   p.ldo = ldo;
   dim3 grid((T_q + kQPerCta - 1) / kQPerCta, heads, B);
   p.idle_ns = g_attn_idle_ns;
-  auto kern = g_attn_variant == 1 ? k_attention_tc<1> : g_attn_variant == 2 ? k_attention_tc<2> : k_attention_tc<0>;
+  auto kern = g_attn_variant == 1 ? k_attention_tc<1> : k_attention_tc<0>;
   kern<<<grid, kAttnThreads, kAttnSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
   SGN_LAUNCH_CHECK();
   return SGN_OK;

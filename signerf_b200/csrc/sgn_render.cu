@@ -557,7 +557,7 @@ extern "C" int sgn_set_option(const char* name, int value) {
     return SGN_OK;
   }
   if (n == "attn_variant") {
-    SGN_CHECK_ARG(value >= 0 && value <= 2, "attn_variant must be 0..2");
+    SGN_CHECK_ARG(value >= 0 && value <= 1, "attn_variant must be 0 or 1");
     sgn::g_attn_variant = value;
     return SGN_OK;
   }
