@@ -177,3 +177,92 @@ class DatasetGenerator:
                 "edited": ops.sheet_cut(blended_sheet, lay, last, self.height, self.width),
                 "render_scaled": render_scaled, "mask_scaled": mask_scaled,
                 "condition_scaled": condition_reference_sheet[sl], "edited_scaled": edited_scaled}
+
+    # ------------------------------------------------------------------ dataset on disk
+    def init_directory(self) -> None:
+        """datasetgenerator.py:146-182"""
+        from .dataset_io import DatasetWriter
+        self._writer = DatasetWriter(self.config.path, self.dataset_name, self.downscale_factor)
+        w = self._writer
+        self.dataset_path, self.transforms_path, self.references_path = w.dataset_path, w.transforms_path, w.references_path
+        self.images_path, self.masks_path, self.conditions_path = w.images_path, w.masks_path, w.conditions_path
+        self.rendered_path, self.originals_path = w.rendered_path, w.originals_path
+        w.init_directory(self.config)
+
+    def save_generated_images(self, idx: int, images: Dict[str, Tensor], camera, current_transforms: dict,
+                              is_original: bool = False) -> dict:
+        """datasetgenerator.py:398-468 (PNG encoding on the writer's thread pool)."""
+        cam = as_camera_batch(camera)
+        return self._writer.save_generated_images(idx, images, cam.camera_to_worlds[0], cam.fx, cam.fy, cam.cx, cam.cy,
+                                                  cam.width, cam.height, current_transforms, is_original)
+
+    def generate_dataset(self, graph, reference_camera_to_worlds: Tensor, original_dataset=None,
+                         synthetic_camera_to_worlds: Optional[Tensor] = None, merge_with_original_dataset: bool = False) -> None:
+        """datasetgenerator.py:185-393: reference sheet, then one sheet per dataset camera (hot loop #1), optionally the
+        original photos merged in with inverted masks; directory + transforms.json in the reference's schema.
+        `original_dataset` is duck-typed on `.cameras` (camera_to_worlds / fx / fy / cx / cy / width / height, `.size`),
+        `._dataparser_outputs.image_filenames` and `.get_image_float32(idx)`."""
+        from .dataset_io import DatasetWriter
+        if original_dataset is None and synthetic_camera_to_worlds is None:
+            raise ValueError("Either original dataset or camera_to_worlds must be given")
+        if merge_with_original_dataset and (original_dataset is None or synthetic_camera_to_worlds is None):
+            raise ValueError("Original dataset and camera_to_worlds must be given to merge with original dataset")
+        self.init_directory()
+        self.renderer.setup()
+        if synthetic_camera_to_worlds is not None:
+            self.is_synthetic = True
+        tw, th = int(self.width // self.downscale_factor), int(self.height // self.downscale_factor)
+        dev = graph.device
+
+        def batch(c2w: Tensor) -> CameraBatch:
+            return CameraBatch(c2w.to(dev), self.fx, self.fy, self.cx, self.cy, int(self.width), int(self.height))
+
+        reference_cameras = batch(reference_camera_to_worlds)
+        cameras, original_filenames = None, None
+        if original_dataset is not None:
+            cameras = as_camera_batch(original_dataset.cameras)
+            original_filenames = list(original_dataset._dataparser_outputs.image_filenames)  # noqa: SLF001
+        if synthetic_camera_to_worlds is not None:
+            cameras = batch(synthetic_camera_to_worlds)
+            original_filenames = [None] * synthetic_camera_to_worlds.shape[0]
+        transforms = DatasetWriter.new_transforms(self.is_synthetic, merge_with_original_dataset, self.original_transform_matrix,
+                                                  self.original_scale_factor)
+        image_sheet, mask_sheet, cond_sheet, edited_sheet, references = self.generate_reference_sheet(graph, reference_cameras, tw, th)
+        self._writer.save_reference_sheets(image_sheet, mask_sheet, cond_sheet, edited_sheet)
+        idx = 0
+        transforms["reference_indices"] = []
+        for i in range(len(reference_cameras)):
+            transforms = self.save_generated_images(idx, references[i], reference_cameras[i], transforms)
+            transforms["reference_indices"].append(idx)
+            idx += 1
+        self._writer.write_transforms(transforms)
+        transforms["generated_indices"] = []
+        for i in range(len(cameras)):
+            filename = original_filenames[i]
+            images = self.generate_with_reference_sheet(graph, cameras[i], filename, tw, th, edited_sheet, cond_sheet)
+            transforms = self.save_generated_images(idx, images, cameras[i], transforms, filename is not None)
+            transforms["generated_indices"].append(idx)
+            idx += 1
+        self._writer.write_transforms(transforms)
+        if merge_with_original_dataset:
+            transforms["original_indices"] = []
+            ocams = as_camera_batch(original_dataset.cameras)
+            lay = ops.SheetLayout(1, 1, th, tw, 0)      # a 1 x 1 "sheet" = K4's bilinear resize (F.interpolate, :355-358)
+
+            def scaled(t: Tensor, threshold: Optional[float] = None) -> Tensor:
+                out = torch.zeros((lay.height, lay.width, t.shape[2]), dtype=torch.float32, device=dev)
+                ops.sheet_paste(t.to(dev, torch.float32)[None].contiguous(), out, lay, 0, **({} if threshold is None else {"threshold": threshold}))
+                return out[:th, :tw]
+
+            for i in range(len(ocams)):
+                image = original_dataset.get_image_float32(i).to(dev)
+                render, mask, condition = self.render_camera(graph, ocams[i])
+                mask = ~mask                           # the photos do not contain the object (:351-352)
+                images = {"render": render, "mask": mask, "condition": condition, "edited": image,
+                          "render_scaled": scaled(render), "mask_scaled": scaled(mask.float(), 0.5) > 0.5,
+                          "condition_scaled": scaled(condition), "edited_scaled": scaled(image)}
+                transforms = self.save_generated_images(idx, images, ocams[i], transforms, True)
+                transforms["original_indices"].append(idx)
+                idx += 1
+            self._writer.write_transforms(transforms)
+        self._writer.writer.close()
