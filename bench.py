@@ -455,7 +455,10 @@ def main():
                 "achieved": (tc[top]["flops"] / (tc[top]["ms"] / 1e3) / 1e12) if top else None,
                 "peak": pk["tensor"], "unit": "TFLOP/s",
                 "frac": (tc[top]["flops"] / (tc[top]["ms"] / 1e3) / 1e12 / pk["tensor"]) if top else None,
-                "traffic": None, "peak_source": pk["source"] + " (sustained bf16 cuBLAS)",
+                # ncu --set full of ONE launch of the dominant shape (2 x 10 heads x 16 384^2, profiles/r1_ncu_attention_summary.txt):
+                # dram read + write = 125.95 + 25.27 MB against 168 MB of q / k / v / o (K and V of a head stay in L2)
+                "traffic": 151.2e6 if top == "k_attention_tc" else None,
+                "peak_source": pk["source"] + " (sustained bf16 cuBLAS)",
                 "ms_per_step_in_kernel": tc[top]["ms"] if top else None, "launches_per_step": tc[top]["calls"] if top else None,
                 "algorithmic_flops_per_step": tc[top]["flops"] if top else None,
                 "unet_step": {"ms": unet_ms, "algorithmic_tflop": UNET_TFLOP_PER_STEP, "achieved": tf,

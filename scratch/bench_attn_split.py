@@ -1,0 +1,22 @@
+import sys, torch
+sys.path.insert(0, "/root/repo")
+from signerf_b200 import nn_ops, _lib
+def timeit(fn, n=8, warm=3):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n): fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / n
+for B, heads, T in ((2, 10, 16384), (2, 20, 4096), (1, 3, 1000)):
+    C = heads * 64
+    g = torch.Generator(device="cuda").manual_seed(0)
+    q, k, v = (torch.randn(B * T, C, device="cuda", generator=g).half() for _ in range(3))
+    ref = None
+    for split in (0, 1):
+        _lib.set_option("attn_split_rows", split)
+        out = torch.empty(B * T, C, device="cuda", dtype=torch.float16)
+        ms = timeit(lambda: nn_ops.attention_f16(q, k, v, B, heads, out=out))
+        if ref is None: ref = out.clone()
+        print(f"T{T} h{heads} split_rows={split}: {ms:.3f} ms {4*B*heads*T*T*64/ms/1e9:.0f} TF/s  maxdiff {(out.float()-ref.float()).abs().max().item():.2e}", flush=True)
