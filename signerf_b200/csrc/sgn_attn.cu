@@ -76,6 +76,14 @@ __device__ __forceinline__ float ex2_v(float x) {   // pinned in program order (
   return y;
 }
 
+// make -C signerf_b200/csrc trace: clock64 time stamps of CTA 0 (softmax warp 2 lane 0 and the issuer), read back by
+// scratch/attn_trace.py through sgn_debug_attn_trace
+#ifdef SGN_ATTN_TRACE
+__device__ long long g_trace[16 * 256];   // [event][key tile]
+#define TRACE(ev, j) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (j) < 256) g_trace[(ev) * 256 + (j)] = clock64(); } while (0)
+#else
+#define TRACE(ev, j) do { } while (0)
+#endif
 int g_attn_variant = 1;   // sgn_set_option "attn_variant"
 int g_attn_idle_ns = 0;   // sgn_set_option "attn_idle_ns"
 
@@ -178,6 +186,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           if (jq < n_kv && tc::mbar_test(&s_free[x], (jq - 1) & 1) &&
               tc::mbar_test(&kv_full[jq % kKvStages], (jq / kKvStages) & 1)) {
             tc::tc_fence_after();
+            if (x == 0) TRACE(8, jq);
             issue_qk(x, jq);
             qk_next[x] = jq + 1;
             progress = true;
@@ -185,6 +194,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           const int jp = pv_next[x];
           if (jp < n_kv && tc::mbar_test(&p_full[x], jp & 1)) {
             tc::tc_fence_after();
+            if (x == 0) TRACE(9, jp);
             issue_pv(x, jp);
             pv_next[x] = jp + 1;
             if (pv_next[x ^ 1] > jp) tc::umma_commit(&kv_empty[jp % kKvStages]);  // both tiles are through K/V(jp)
@@ -209,8 +219,11 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     if (kTurns && x == 1) named_arrive(1, 256);  // group A takes the first turn
     for (int j = 0; j < n_kv; ++j) {
       const int kv_rem = p.T_kv - j * kKvTile;  // >= 1
+      const bool tr = warp == 2 && lane == 0;
+      if (tr) TRACE(0, j);
       tc::mbar_wait(&s_full[x], j & 1);
       tc::tc_fence_after();
+      if (tr) TRACE(1, j);
       uint32_t s[128];
 #pragma unroll
       for (int c = 0; c < 4; ++c) tc::tmem_ld32(ts + c * 32, s + c * 32);
@@ -218,6 +231,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&s_free[x]);     // the issuer may overwrite S_x with Q_x K_{j+1}^T now
+      if (tr) TRACE(2, j);
       if (kv_rem < kKvTile) {
 #pragma unroll
         for (int q = 0; q < 128; ++q)
@@ -260,7 +274,9 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       if (grow) m_run = mx;
       const float neg_m = -m_run * sc;
       float psum0 = 0.f, psum1 = 0.f;
+      if (tr) TRACE(3, j);
       if (kTurns) named_sync(1 + x, 256);            // my turn on the MUFU pipe
+      if (tr) TRACE(4, j);
       if constexpr (kVariant == 0) {
 #pragma unroll
         for (int c = 0; c < 2; ++c) {      // 64 keys -> 32 packed columns per tcgen05.st
@@ -308,7 +324,9 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           }
           if ((b & 3) == 3) {
             if (!o_ready) {   // warp-uniform
+              if (tr) TRACE(5, j);
               tc::mbar_wait(&o_full[x], (j - 1) & 1);
+              if (tr) TRACE(6, j);
               tc::tc_fence_after();
               o_ready = true;
             }
@@ -322,6 +340,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tc::tc_fence_before();          // P_x written, O_x accesses done before the issuer touches them
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&p_full[x]);
+      if (tr) TRACE(7, j);
     }
     if (kTurns && x == 0) named_sync(1, 256);      // absorb group B's last hand-over
     // O_x complete after the last P.V
@@ -498,6 +517,12 @@ int g_attn_short_kv = 1;   // sgn_set_option "attn_short_kv": 0 sends T_kv <= 80
 }  // namespace sgn
 
 using namespace sgn;
+
+#ifdef SGN_ATTN_TRACE
+extern "C" int sgn_debug_attn_trace(long long* h_out) {
+  return cudaMemcpyFromSymbol(h_out, g_trace, sizeof(long long) * 16 * 256) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 extern "C" int sgn_attention_f16(const void* d_q, int64_t ldq, const void* d_k, int64_t ldk, const void* d_v,
                                  int64_t ldv, int B, int heads, int T_q, int T_kv, float scale, void* d_out,
