@@ -240,6 +240,9 @@ int sgn_upsample2x_f16(const float* d_x, int B, int H, int W, int C, void* d_out
  * folded in (sd-webui-controlnet hook: `h = cat([h, hs.pop() + control.pop()])`).  d_b2 may be NULL. */
 int sgn_concat_f32(const float* d_a, int Ca, const float* d_b, const float* d_b2, float scale, int Cb, int64_t P,
                    float* d_out, void* stream);
+/* Same, also emitting the result as fp16 [P, Ca+Cb] (operand of the ResBlock's 1x1 shortcut GEMM). */
+int sgn_concat_f32_f16(const float* d_a, int Ca, const float* d_b, const float* d_b2, float scale, int Cb, int64_t P,
+                       float* d_out, void* d_out16, void* stream);
 /* y += a * x (ControlNet middle-block residual). */
 int sgn_axpy_f32(const float* d_x, float a, int64_t n, float* d_y, void* stream);
 /* im2col of sgm Downsample (3x3 / stride 2 / pad 1): fp32 NHWC [B,H,W,C] -> fp16 [B*Ho*Wo, 9*C], feeding sgn_gemm_f16. */

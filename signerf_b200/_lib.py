@@ -93,6 +93,7 @@ SIGNATURES = {
     "sgn_cast_f16": (_i, [_vp, _i64, _vp, _vp]),
     "sgn_upsample2x_f16": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "sgn_concat_f32": (_i, [_vp, _i, _vp, _vp, _f, _i, _i64, _vp, _vp]),
+    "sgn_concat_f32_f16": (_i, [_vp, _i, _vp, _vp, _f, _i, _i64, _vp, _vp, _vp]),
     "sgn_axpy_f32": (_i, [_vp, _f, _i64, _vp, _vp]),
     "sgn_im2col3x3_s2_f16": (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "sgn_im2col3x3_split_f16": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),

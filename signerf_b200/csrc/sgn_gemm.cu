@@ -492,7 +492,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 // epilogue skips their columns).  Cost model fitted on B200: a k-block costs max(tensor time 2*bn cycles, load time
 // (16 KB + 64 B * bn) / 58 B/clk) -- the load side is latency x in-flight-bytes bound (192 KB of stages per SM against
 // ~1.7 us of loaded L2 latency), so wide tiles win even when they leave a partially filled last wave.
-static int pick_block_n(long long m_tiles, int N) {
+// `epi_res_kb`: > 0 for an fp32 in-place-residual GEMM with that many k-blocks.  With K <= 640 its tile time is set by the
+// epilogue (~90 cycles per output column per CTA: 1 KB of residual read + write at the ~11 B/clk an SM's epilogue warps
+// sustain), so the width that minimises rounds x columns wins, not the widest one (32768x640x640: 64.2 -> 54.8 us).
+static int pick_block_n(long long m_tiles, int N, int epi_res_kb = 0) {
   if (const char* e = getenv("SGN_GEMM_BN")) {  // tuning / debugging override
     int bn = atoi(e);
     if (bn >= 16 && bn <= 256 && bn % 16 == 0) return std::min(bn, (N + 15) / 16 * 16);
@@ -507,6 +510,7 @@ static int pick_block_n(long long m_tiles, int N) {
     long long rounds = (tiles + units - 1) / units;
     double t = std::max(2.0 * bn, 282.0 + 1.1 * bn);
     double cost = (double)rounds * (t + 40.0);                 // + per-tile epilogue hand-over
+    if (epi_res_kb > 0 && epi_res_kb <= 10) cost = (double)rounds * std::max(epi_res_kb * t, 90.0 * bn);
     if (cost < best_cost - 1e-9) best_cost = cost, best = bn;
   }
   return best;
@@ -598,9 +602,10 @@ extern "C" int sgn_gemm_f16(const void* d_a, int64_t lda, const void* d_w, int64
   int n_rows = (N + 15) / 16 * 16;  // weight rows past N are zero-filled by TMA
   p.N = n_rows;
   p.num_m_tiles = (M + kBM - 1) / kBM;
-  p.block_n = pick_block_n(p.num_m_tiles, n_rows);
-  p.num_n_tiles = (n_rows + p.block_n - 1) / p.block_n;
   p.num_k_blocks = (K + kBK - 1) / kBK;
+  const bool res32 = ep && ep->d_residual && !ep->out_f16 && !ep->geglu;
+  p.block_n = pick_block_n(p.num_m_tiles, n_rows, res32 ? p.num_k_blocks : 0);
+  p.num_n_tiles = (n_rows + p.block_n - 1) / p.block_n;
   p.conv = 0, p.tiles_x = p.tiles_y = 1;
   int rc = fill_epilogue(p, ep, N, d_out);
   if (rc) return rc;

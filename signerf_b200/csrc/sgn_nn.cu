@@ -270,8 +270,9 @@ __global__ void k_upsample2x_f16(const float* __restrict__ x, int B, int H, int 
 }
 
 // torch.cat([a, b + scale * b2], dim=channels): a [P,Ca], b / b2 [P,Cb] -> out [P, Ca+Cb]   (fp32)
+// out16 (optional): the same matrix as fp16, for the ResBlock's 1x1 shortcut GEMM (saves re-reading the fp32 result for a cast)
 __global__ void k_concat(const float* __restrict__ a, int ca4, const float* __restrict__ b, const float* __restrict__ b2,
-                         float scale, int cb4, size_t P, float* out) {
+                         float scale, int cb4, size_t P, float* out, __half* out16) {
   const int c4 = ca4 + cb4;
   const size_t n = P * c4;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -288,6 +289,13 @@ __global__ void k_concat(const float* __restrict__ a, int ca4, const float* __re
       }
     }
     reinterpret_cast<float4*>(out)[i] = v;
+    if (out16) {
+      __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&h0);
+      u.y = *reinterpret_cast<uint32_t*>(&h1);
+      reinterpret_cast<uint2*>(out16)[i] = u;
+    }
   }
 }
 
@@ -658,7 +666,19 @@ extern "C" int sgn_concat_f32(const float* d_a, int Ca, const float* d_b, const 
   if (P == 0) return SGN_OK;
   SGN_CHECK_ARG((Ca == 0 || d_a) && d_b && d_out, "null pointer");
   size_t n = (size_t)P * ((Ca + Cb) / 4);
-  k_concat<<<grid_1d(n, 256), 256, 0, ST(stream)>>>(d_a, Ca / 4, d_b, d_b2, scale, Cb / 4, (size_t)P, d_out);
+  k_concat<<<grid_1d(n, 256), 256, 0, ST(stream)>>>(d_a, Ca / 4, d_b, d_b2, scale, Cb / 4, (size_t)P, d_out, nullptr);
+  SGN_LAUNCH_CHECK();
+  return SGN_OK;
+}
+
+extern "C" int sgn_concat_f32_f16(const float* d_a, int Ca, const float* d_b, const float* d_b2, float scale, int Cb,
+                                  int64_t P, float* d_out, void* d_out16, void* stream) {
+  SGN_CHECK_ARG(P >= 0 && Ca >= 0 && Cb > 0 && Ca % 4 == 0 && Cb % 4 == 0, "channel counts must be multiples of 4");
+  if (P == 0) return SGN_OK;
+  SGN_CHECK_ARG((Ca == 0 || d_a) && d_b && d_out && d_out16, "null pointer");
+  size_t n = (size_t)P * ((Ca + Cb) / 4);
+  k_concat<<<grid_1d(n, 256), 256, 0, ST(stream)>>>(d_a, Ca / 4, d_b, d_b2, scale, Cb / 4, (size_t)P, d_out,
+                                                    reinterpret_cast<__half*>(d_out16));
   SGN_LAUNCH_CHECK();
   return SGN_OK;
 }

@@ -191,13 +191,18 @@ def upsample2x_f16(x: Tensor, B: int, H: int, W: int) -> Tensor:
     return out
 
 
-def concat_f32(a: Tensor, b: Tensor, b2: Optional[Tensor] = None, scale: float = 1.0) -> Tensor:
-    """cat([a, b + scale*b2], dim=1) of fp32 [P, C] matrices."""
+def concat_f32(a: Tensor, b: Tensor, b2: Optional[Tensor] = None, scale: float = 1.0, with_f16: bool = False):
+    """cat([a, b + scale*b2], dim=1) of fp32 [P, C] matrices; with_f16: -> (fp32, fp16 copy)."""
     _chk(a, torch.float32, "a")
     _chk(b, torch.float32, "b")
     _chk(b2, torch.float32, "b2")
     P = a.shape[0]
     out = torch.empty((P, a.shape[1] + b.shape[1]), dtype=torch.float32, device=a.device)
+    if with_f16:
+        out16 = torch.empty(out.shape, dtype=torch.float16, device=a.device)
+        _call(a.device, _lib.load().sgn_concat_f32_f16, _ptr(a), a.shape[1], _ptr(b), _ptr(b2), float(scale), b.shape[1], P,
+              _ptr(out), _ptr(out16))
+        return out, out16
     _call(a.device, _lib.load().sgn_concat_f32, _ptr(a), a.shape[1], _ptr(b), _ptr(b2), float(scale), b.shape[1], P, _ptr(out))
     return out
 

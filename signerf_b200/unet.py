@@ -278,6 +278,7 @@ class Act:
     B: int
     H: int
     W: int
+    t16: Optional[Tensor] = None    # fp16 copy of `t` when the producer made one (skip concat)
 
     @property
     def C(self) -> int:
@@ -407,7 +408,8 @@ class _Net:
                           p.f32(pre + ".in_layers.2.bias"), rowbias=e)
         b16 = self.gn16(Act(h, x.B, x.H, x.W), pre + ".out_layers.0", 1e-5, True)
         if x.C != cout:
-            skip = K.gemm_f16(K.cast_f16(x.t), p.lin16(pre + ".skip_connection.weight"), p.f32(pre + ".skip_connection.bias"))
+            x16 = x.t16 if x.t16 is not None else K.cast_f16(x.t)
+            skip = K.gemm_f16(x16, p.lin16(pre + ".skip_connection.weight"), p.f32(pre + ".skip_connection.bias"))
             out = K.conv3x3_f16(b16.view(x.B, x.H, x.W, cout), p.conv16(pre + ".out_layers.3.weight"),
                                 p.f32(pre + ".out_layers.3.bias"), residual=skip, out=skip)
         else:
@@ -514,8 +516,8 @@ class SDXLUNetB200(_Net):
                      ctx16: Tensor, n_ctx: int) -> Act:
         """output_blocks[i] on cat([h, skip + w * control]): ResBlock (+ SpatialTransformer) (+ Upsample)."""
         _, _, depth, up = _decoder_layout(self.cfg)[i]
-        cat = K.concat_f32(h.t, skip.t, control, control_weight)
-        h = self.resblock(f"output_blocks.{i}.0", Act(cat, h.B, h.H, h.W), emb)
+        cat, cat16 = K.concat_f32(h.t, skip.t, control, control_weight, with_f16=True)   # every decoder ResBlock has a shortcut
+        h = self.resblock(f"output_blocks.{i}.0", Act(cat, h.B, h.H, h.W, cat16), emb)
         k = 1
         if depth:
             h = self.transformer(f"output_blocks.{i}.1", h, depth, ctx16, n_ctx)
