@@ -158,3 +158,19 @@ def test_small_tc_conv_is_fp32_exact(B, H, W, Cin, Cout, stride, out_f16):
     assert rel_l2(out.permute(0, 3, 1, 2), ref) < (6e-4 if out_f16 else 2e-6)
     lin = K.conv3x3_small_tc(x.permute(0, 2, 3, 1).contiguous(), w16, None, stride=stride)
     assert rel_l2(lin.permute(0, 3, 1, 2), F.conv2d(x, w, None, stride=stride, padding=1)) < 2e-6
+
+
+def test_sdxl_vector_conditioning():
+    """y = [pooled | fourier256(orig_h, orig_w, crop_t, crop_l, target_h, target_w)] (sgm ConcatTimestepEmbedderND)."""
+    import math
+    from signerf_b200 import conditioning as Cn
+    pooled = _r((2, 1280), 21)
+    y = Cn.sdxl_vector(pooled, 2048, 1536, (0, 0))
+    assert tuple(y.shape) == (2, 2816) and torch.equal(y[:, :1280], pooled)
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(128, dtype=torch.float32) / 128).cuda()
+    ref = []
+    for v in (2048.0, 1536.0, 0.0, 0.0, 2048.0, 1536.0):
+        a = v * freqs
+        ref.append(torch.cat([torch.cos(a), torch.sin(a)]))
+    ref = torch.cat(ref)
+    assert torch.allclose(y[0, 1280:], ref, atol=2e-4) and torch.equal(y[0, 1280:], y[1, 1280:])
