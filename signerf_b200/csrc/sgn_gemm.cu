@@ -410,7 +410,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       tc::mbar_wait(&tfull[buf], ph);
       tc::tc_fence_after();
       const uint32_t taddr = tmem_base + buf * kAccStride + ((uint32_t)lane_base << 16);
-      if (p.coalesced == 2) c0 = p.block_n;   // debug (SGN_GEMM_COALESCED=2): no epilogue work, main loop only
       for (; c0 + 32 <= p.block_n; c0 += 64) {
         if (!chunk_fast(c0)) {
           epilogue_rows(p, taddr + c0, 32, m, b, n_base + c0, valid);
@@ -575,7 +574,7 @@ static int fill_epilogue(GemmParams& p, const SgnEpilogue* ep, int n_valid, void
   p.out = d_out;
   long long ld = ep ? ep->ldo : 0;
   p.ldo = ld > 0 ? ld : (p.geglu ? n_valid / 2 : n_valid);
-  p.coalesced = coalesced == 2 ? 2 : coalesced && !p.nchw && (p.ldo % ((p.out_f16 || p.geglu) ? 8 : 4)) == 0 && (n_valid % 4) == 0;
+  p.coalesced = coalesced && !p.nchw && (p.ldo % ((p.out_f16 || p.geglu) ? 8 : 4)) == 0 && (n_valid % 4) == 0;
   SGN_CHECK_ARG(!p.rowbias || p.rows_per_batch > 0, "rowbias needs rows_per_batch");
   SGN_CHECK_ARG(!p.geglu || (n_valid % 16 == 0 && !p.residual && !p.nchw), "geglu needs N % 16 == 0 and no residual");
   SGN_CHECK_ARG(!p.nchw || !p.out_f16, "nchw output is fp32 only");

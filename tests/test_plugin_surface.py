@@ -55,3 +55,20 @@ def test_defaults_and_error_behaviour():
     r.object_path = "mesh.ply"
     r.setup()
     assert r.scene is None
+
+
+def test_renderer_pose_and_obj_loader_match_oracle(tmp_path):
+    """plugin.Renderer's object pose (renderer.py:80-131) and OBJ reader against oracle/mesh_ref.py, on the CPU."""
+    import numpy as np
+    from oracle import mesh_ref as M
+    from signerf_b200.plugin.renderer import load_obj
+    r = P.Renderer(P.RendererConfig(position=[0.1, -0.2, 0.3], rotation=[10, 20, 30], scale=[0.1, 0.2, 0.3]), "cpu")
+    assert np.allclose(r.object_pose(), M.object_pose([0.1, -0.2, 0.3], [10, 20, 30], [0.1, 0.2, 0.3]), atol=1e-12)
+    r.rotation, r.scale = [0, 0, 90], [0.1, 0.1, 0.1]                       # GUI edit
+    pose = r.object_pose()
+    assert np.allclose(pose[:3, :3] @ np.array([1.0, 0, 0]), [0.0, 0.0, -1.0])   # x -> y (Rz 90), y -> -z_gl (axis swap), scale 10 * 0.1
+    text = "o quad\nv 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvt 0 0\nvn 0 0 1\nf 1/1/1 2/1/1 3/1/1 4/1/1\n"
+    (tmp_path / "q.obj").write_text(text)
+    v, f = load_obj(tmp_path / "q.obj")
+    vo, fo = M.parse_obj(text)
+    assert np.array_equal(v, vo) and np.array_equal(f, fo) and f.tolist() == [[0, 1, 2], [0, 2, 3]]
