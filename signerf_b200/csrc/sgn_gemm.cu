@@ -89,6 +89,10 @@ struct GemmParams {
   int M, N, K;  // N = weight rows covered by tiles (multiple of block_n); n_valid <= N columns are stored
   int n_valid;
   int block_n, num_m_tiles, num_n_tiles, num_k_blocks;
+  // Tail split: work items [0, tail_start) are full tiles; the tiles of the last, under-filled round are cut into
+  // tail_split column slices of tail_bn = block_n / tail_split each (work items tail_start .. total_items), so that a
+  // 2.16-wave GEMM (160 tiles on 74 CTA pairs) costs ~2.4 tile times instead of 3.  tail_split = 1: off.
+  int tail_start, tail_split, tail_bn, total_items;
   int conv, H, W, cin_blocks, tiles_x, tiles_y;
   const float* bias;
   const float* rowbias;
@@ -201,7 +205,7 @@ __device__ __noinline__ void epilogue_rows(const GemmParams& p, uint32_t taddr, 
 template <int kCluster, int kStages, int kEpi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-          const __grid_constant__ GemmParams p) {
+          const __grid_constant__ CUtensorMap tmBt, const __grid_constant__ GemmParams p) {
   constexpr int kStageB = GemmCfg<kCluster>::kStageB;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -241,18 +245,36 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   // work unit = kCluster vertically adjacent M tiles x one N tile; M tiles past the end are computed on zero-filled
   // rows and never stored
   const int m_groups = (p.num_m_tiles + kCluster - 1) / kCluster;
-  const int total_tiles = m_groups * p.num_n_tiles;
+  (void)m_groups;
+  const int total_tiles = p.total_items;
   const int first_tile = blockIdx.x / kCluster, tile_step = gridDim.x / kCluster;
+  // work item -> (M group, first column, width); tail items are column slices of the last round's tiles
+  auto decode = [&](int t, int& m_group, int& n0, int& bn) -> bool {
+    int tile = t, sub = 0;
+    const bool tail = t >= p.tail_start;
+    if (tail) {
+      const int u = t - p.tail_start;
+      tile = p.tail_start + u / p.tail_split;
+      sub = u - (u / p.tail_split) * p.tail_split;
+    }
+    m_group = tile / p.num_n_tiles;
+    const int n_tile = tile - m_group * p.num_n_tiles;
+    bn = tail ? p.tail_bn : p.block_n;
+    n0 = n_tile * p.block_n + sub * p.tail_bn;
+    return tail;
+  };
   const int tiles_per_img = p.tiles_x * p.tiles_y;
 
   if (warp == 0) {
     if (lane == 0) {  // ---------------- TMA producer
       int stage = 0;
       uint32_t phase = 0;
-      const int b_rows = p.block_n / kCluster;  // weight rows this CTA loads per k-block
-      const uint32_t tx_bytes = kCluster * (kStageA + (uint32_t)b_rows * (kBK * 2));  // both CTAs complete on the leader
       for (int t = first_tile; t < total_tiles; t += tile_step) {
-        const int m_group = t / p.num_n_tiles, n_tile = t - m_group * p.num_n_tiles;
+        int m_group, n0, bn;
+        const bool tail = decode(t, m_group, n0, bn);
+        const CUtensorMap* tmBx = tail ? &tmBt : &tmB;
+        const int b_rows = bn / kCluster;  // weight rows this CTA loads per k-block
+        const uint32_t tx_bytes = kCluster * (kStageA + (uint32_t)b_rows * (kBK * 2));  // both CTAs complete on the leader
         const int m_tile = m_group * kCluster + (int)cta_rank;
         int b = 0, x0 = 0, y0 = 0;
         if (p.conv) {
@@ -273,13 +295,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             tc::mbar_expect_tx(&full[stage], tx_bytes);
             if (p.conv) tc::tma_load_4d(sA + stage * kStageA, &tmA, &full[stage], cb * kBK, x0 + dx - 1, y0 + dy - 1, b);
             else tc::tma_load_2d(sA + stage * kStageA, &tmA, &full[stage], kb * kBK, m_tile * kBM);
-            tc::tma_load_2d(sB + stage * kStageB, &tmB, &full[stage], kb * kBK, n_tile * p.block_n);
+            tc::tma_load_2d(sB + stage * kStageB, tmBx, &full[stage], kb * kBK, n0);
           } else {
             const uint32_t lead_full = tc::mapa_u32(&full[stage], 0);
             if (cta_rank == 0) tc::mbar_expect_tx(&full[stage], tx_bytes);
             if (p.conv) tc::tma_load_4d_pair(sA + stage * kStageA, &tmA, lead_full, cb * kBK, x0 + dx - 1, y0 + dy - 1, b);
             else tc::tma_load_2d_pair(sA + stage * kStageA, &tmA, lead_full, kb * kBK, m_tile * kBM);
-            tc::tma_load_2d_pair(sB + stage * kStageB, &tmB, lead_full, kb * kBK, n_tile * p.block_n + (int)cta_rank * b_rows);
+            tc::tma_load_2d_pair(sB + stage * kStageB, tmBx, lead_full, kb * kBK, n0 + (int)cta_rank * b_rows);
           }
           if (++stage == kStages) stage = 0, phase ^= 1;
         }
@@ -287,7 +309,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     }
   } else if (warp == 1) {
     if (lane == 0 && cta_rank == 0) {  // ---------------- MMA issuer (pair: the leader issues for both SMs)
-      const uint32_t idesc = tc::umma_idesc_f16(kBM * kCluster, p.block_n, false, false);
+      const uint32_t idesc_full = tc::umma_idesc_f16(kBM * kCluster, p.block_n, false, false);
+      const uint32_t idesc_tail = tc::umma_idesc_f16(kBM * kCluster, p.tail_bn, false, false);
       int stage = 0;
       uint32_t phase = 0;
       int i = 0;
@@ -297,6 +320,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         tc::mbar_wait(&tempty[buf], ph ^ 1);
         tc::tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * kAccStride;
+        const uint32_t idesc = t >= p.tail_start ? idesc_tail : idesc_full;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           tc::mbar_wait(&full[stage], phase);
           tc::tc_fence_after();
@@ -324,7 +348,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     // starts on the current one; by the time those loads are issued the lines are L2 hits.
     auto l2_prefetch_tile = [&](int t) {
       if (!p.res_prefetch || p.residual == nullptr || p.nchw || p.geglu || t >= total_tiles) return;
-      const int m_group = t / p.num_n_tiles, n_tile = t - m_group * p.num_n_tiles;
+      int m_group, n_base, bn;
+      decode(t, m_group, n_base, bn);
       const int m_tile = m_group * kCluster + (int)cta_rank;
       long long m;
       if (p.conv) {
@@ -338,8 +363,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         m = (long long)m_tile * kBM + row;
         if (m >= p.M) return;
       }
-      const int n_base = n_tile * p.block_n;
-      for (int c = col_half * 32; c < p.block_n && n_base + c < p.n_valid; c += 64)
+      for (int c = col_half * 32; c < bn && n_base + c < p.n_valid; c += 64)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(p.residual + m * p.ldo + n_base + c));
     };
     l2_prefetch_tile(first_tile);
@@ -354,7 +378,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       l2_prefetch_tile(t + tile_step);
       const int buf = i & 1;
       const uint32_t ph = (i >> 1) & 1;
-      const int m_group = t / p.num_n_tiles, n_tile = t - m_group * p.num_n_tiles;
+      int m_group, n_base, bn;
+      decode(t, m_group, n_base, bn);
       const int m_tile = m_group * kCluster + (int)cta_rank;
       int tb = 0, ty0 = 0, tx0 = 0;
       if (p.conv) {
@@ -386,10 +411,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         valid = m < p.M;
         b = p.rows_per_batch > 0 ? (int)(m / p.rows_per_batch) : 0;
       }
-      const int n_base = n_tile * p.block_n;
       // the two warps of a lane quarter split the tile's columns in 32-wide chunks: even chunks / odd chunks
       int c0 = col_half * 32;
-      auto chunk_fast = [&](int c) -> bool { return p.coalesced && c + 32 <= p.block_n && n_base + c + 32 <= p.n_valid; };
+      auto chunk_fast = [&](int c) -> bool { return p.coalesced && c + 32 <= bn && n_base + c + 32 <= p.n_valid; };
       // The fp32 residual (the stream the UNet keeps adding into) is the epilogue's only global read: the first chunk's
       // is fetched before the accumulator is even complete, the next chunk's while the current one is processed.
       const bool res_pre = p.res_prefetch && p.residual != nullptr && !p.geglu;
@@ -410,7 +434,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       tc::mbar_wait(&tfull[buf], ph);
       tc::tc_fence_after();
       const uint32_t taddr = tmem_base + buf * kAccStride + ((uint32_t)lane_base << 16);
-      for (; c0 + 32 <= p.block_n; c0 += 64) {
+      for (; c0 + 32 <= bn; c0 += 64) {
         if (!chunk_fast(c0)) {
           epilogue_rows(p, taddr + c0, 32, m, b, n_base + c0, valid);
           cur_ok = prefetch(c0 + 64, rcur);
@@ -467,7 +491,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         __syncwarp();   // the patch is rewritten by the next chunk
         cur_ok = prefetch(c0 + 64, rcur);   // L2 hits (l2_prefetch_tile), in flight across the next TMEM load + transpose
       }
-      if (c0 < p.block_n && c0 + 16 == p.block_n)  // 16-column tail (block_n % 32 == 16) belongs to whoever reaches it
+      if (c0 < bn && c0 + 16 == bn)  // 16-column tail (width % 32 == 16) belongs to whoever reaches it
         epilogue_rows(p, taddr + c0, 16, m, b, n_base + c0, valid);
       tc::tc_fence_before();
       __syncwarp();
@@ -494,6 +518,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 // `epi_res_kb`: > 0 for an fp32 in-place-residual GEMM with that many k-blocks.  With K <= 640 its tile time is set by the
 // epilogue (~90 cycles per output column per CTA: 1 KB of residual read + write at the ~11 B/clk an SM's epilogue warps
 // sustain), so the width that minimises rounds x columns wins, not the widest one (32768x640x640: 64.2 -> 54.8 us).
+// column slices the tiles of an under-filled last round are cut into (1 = no split): see GemmParams::tail_split
+static int tail_split_for(int bn, long long rem, long long units) {
+  static const int enabled = [] { const char* e = getenv("SGN_GEMM_TAIL_SPLIT"); return e ? atoi(e) : 1; }();
+  if (!enabled || rem == 0 || rem * 2 > units) return 1;
+  int split = (int)std::min<long long>(4, units / rem);
+  while (split > 1 && (bn % (split * 32) != 0 || bn / split < 64)) --split;
+  return std::max(1, split);
+}
+
 static int pick_block_n(long long m_tiles, int N, int epi_res_kb = 0) {
   if (const char* e = getenv("SGN_GEMM_BN")) {  // tuning / debugging override
     int bn = atoi(e);
@@ -509,6 +542,10 @@ static int pick_block_n(long long m_tiles, int N, int epi_res_kb = 0) {
     long long rounds = (tiles + units - 1) / units;
     double t = std::max(2.0 * bn, 282.0 + 1.1 * bn);
     double cost = (double)rounds * (t + 40.0);                 // + per-tile epilogue hand-over
+    if (m_tiles >= 2 && tiles >= units) {                      // CTA pairs: an under-filled last round is cut into slices
+      const int split = tail_split_for(bn, tiles % units, units);
+      if (split > 1) cost = ((double)(tiles / units) + 1.6 / split) * (t + 40.0);   // narrow slices run ~1.6x slower per column
+    }
     if (epi_res_kb > 0 && epi_res_kb <= 10) cost = (double)rounds * std::max(epi_res_kb * t, 90.0 * bn);
     if (cost < best_cost - 1e-9) best_cost = cost, best = bn;
   }
@@ -527,36 +564,56 @@ static int pick_cluster(const GemmParams& p) {
 }
 
 template <int kCluster, int kStages, int kEpi>
-static int launch_gemm_c(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t st) {
+static int launch_gemm_c(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBt, const GemmParams& p,
+                         cudaStream_t st) {
   constexpr size_t smem = gemm_smem_bytes(kCluster, kStages);
   static bool attr_set = false;
   if (!attr_set) {
     SGN_CUDA(cudaFuncSetAttribute(k_gemm_tc<kCluster, kStages, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  const int groups = (p.num_m_tiles + kCluster - 1) / kCluster * p.num_n_tiles;
-  const int grid = std::min(groups, sm_count() / kCluster) * kCluster;
+  const int grid = std::min(p.total_items, sm_count() / kCluster) * kCluster;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kGemmThreads), cfg.dynamicSmemBytes = smem, cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kCluster, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr, cfg.numAttrs = 1;
-  SGN_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tc<kCluster, kStages, kEpi>, tmA, tmB, p));
+  SGN_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tc<kCluster, kStages, kEpi>, tmA, tmB, tmBt, p));
   SGN_LAUNCH_CHECK();
   return SGN_OK;
 }
 
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams& p, int cluster, cudaStream_t st) {
-  if (cluster != 2) return launch_gemm_c<1, 4, 0>(tmA, tmB, p, st);
-  if (g_pair_stages == 5) return launch_gemm_c<2, 5, 0>(tmA, tmB, p, st);
+// Tail split (see GemmParams): decided on the host once the tile shape is known; `tmBt` is the weight tensor map with the
+// narrower box.  Only when the last round is at most half full and the slices stay >= 64 columns wide.
+static int plan_tail(GemmParams& p, int cluster, const void* d_w, uint64_t k_elems, uint64_t n_rows_w, uint64_t ldw_bytes,
+                     const CUtensorMap& tmB, CUtensorMap* tmBt) {
+  const int units = std::max(1, sm_count() / cluster);
+  const int tiles = (p.num_m_tiles + cluster - 1) / cluster * p.num_n_tiles;
+  p.tail_start = tiles, p.tail_split = 1, p.tail_bn = p.block_n, p.total_items = tiles;
+  *tmBt = tmB;
+  const int rem = tiles % units;
+  if (cluster != 2 || tiles < units) return SGN_OK;
+  const int split = tail_split_for(p.block_n, rem, units);
+  if (split < 2) return SGN_OK;
+  p.tail_start = tiles - rem, p.tail_split = split, p.tail_bn = p.block_n / split;
+  p.total_items = p.tail_start + rem * split;
+  uint64_t dw[2] = {k_elems, n_rows_w}, sw[1] = {ldw_bytes};
+  uint32_t bw[2] = {kBK, (uint32_t)(p.tail_bn / cluster)};
+  return encode_tmap(tmBt, d_w, 2, dw, sw, bw, nullptr);
+}
+
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBt, GemmParams& p, int cluster,
+                       cudaStream_t st) {
+  if (cluster != 2) return launch_gemm_c<1, 4, 0>(tmA, tmB, tmBt, p, st);
+  if (g_pair_stages == 5) return launch_gemm_c<2, 5, 0>(tmA, tmB, tmBt, p, st);
   static const int spec = [] { const char* e = getenv("SGN_GEMM_EPI_SPEC"); return e ? atoi(e) : 1; }();
   if (spec && p.coalesced == 1 && !p.act_silu) {
-    if (p.geglu && !p.rowbias) return launch_gemm_c<2, 6, 3>(tmA, tmB, p, st);
-    if (p.out_f16 && !p.geglu && !p.residual) return launch_gemm_c<2, 6, 2>(tmA, tmB, p, st);
-    if (!p.out_f16 && !p.geglu) return launch_gemm_c<2, 6, 1>(tmA, tmB, p, st);
+    if (p.geglu && !p.rowbias) return launch_gemm_c<2, 6, 3>(tmA, tmB, tmBt, p, st);
+    if (p.out_f16 && !p.geglu && !p.residual) return launch_gemm_c<2, 6, 2>(tmA, tmB, tmBt, p, st);
+    if (!p.out_f16 && !p.geglu) return launch_gemm_c<2, 6, 1>(tmA, tmB, tmBt, p, st);
   }
-  return launch_gemm_c<2, 6, 0>(tmA, tmB, p, st);
+  return launch_gemm_c<2, 6, 0>(tmA, tmB, tmBt, p, st);
 }
 
 static int fill_epilogue(GemmParams& p, const SgnEpilogue* ep, int n_valid, void* d_out) {
@@ -618,7 +675,10 @@ extern "C" int sgn_gemm_f16(const void* d_a, int64_t lda, const void* d_w, int64
   uint32_t bw[2] = {kBK, (uint32_t)(p.block_n / cluster)};
   rc = encode_tmap(&tmB, d_w, 2, dw, sw, bw, nullptr);
   if (rc) return rc;
-  return launch_gemm(tmA, tmB, p, cluster, reinterpret_cast<cudaStream_t>(stream));
+  CUtensorMap tmBt;
+  rc = plan_tail(p, cluster, d_w, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, tmB, &tmBt);
+  if (rc) return rc;
+  return launch_gemm(tmA, tmB, tmBt, p, cluster, reinterpret_cast<cudaStream_t>(stream));
 }
 
 extern "C" int sgn_conv3x3_f16(const void* d_x, const void* d_w, int B, int H, int W, int C, int N,
@@ -657,5 +717,8 @@ extern "C" int sgn_conv3x3_f16(const void* d_x, const void* d_w, int B, int H, i
   uint32_t bw[2] = {kBK, (uint32_t)(p.block_n / cluster)};
   rc = encode_tmap(&tmB, d_w, 2, dw, sw, bw, nullptr);
   if (rc) return rc;
-  return launch_gemm(tmA, tmB, p, cluster, reinterpret_cast<cudaStream_t>(stream));
+  CUtensorMap tmBt;
+  rc = plan_tail(p, cluster, d_w, (uint64_t)9 * C, (uint64_t)N, (uint64_t)9 * C * 2, tmB, &tmBt);
+  if (rc) return rc;
+  return launch_gemm(tmA, tmB, tmBt, p, cluster, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -743,6 +743,10 @@ class BenchUNet:
 
     def profile_eager(self) -> dict:
         """One eager step with every C-ABI call bracketed by CUDA events -> per-kernel-family time / FLOPs."""
-        K.start_profile()
-        self._run()
-        return K.stop_profile()
+        two, self.net.two_streams = self.net.two_streams, False    # one stream: per-call events must not span the other network
+        try:
+            K.start_profile()
+            self._run()
+            return K.stop_profile()
+        finally:
+            self.net.two_streams = two
