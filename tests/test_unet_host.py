@@ -57,3 +57,19 @@ def test_missing_or_misshapen_weights_are_rejected():
     bad["out.2.bias"] = torch.zeros(5)
     with pytest.raises(ValueError):
         U.SDXLUNetB200(ucfg, bad, "cpu")
+
+
+def test_sigma_table_known_answers():
+    """Published constants of the SD / SDXL scaled-linear schedule (beta 0.00085 .. 0.012, 1000 steps) as k-diffusion's
+    DiscreteSchedule reports them in A1111: sigma_min 0.0292, sigma_max 14.6146; ancestral step: up^2 + down^2 = to^2."""
+    for table in (U.sdxl_sigmas(), R.sdxl_sigmas()):
+        assert len(table) == 1000
+        assert float(table[0]) == pytest.approx(0.029167, abs=2e-5) and float(table[-1]) == pytest.approx(14.614642, abs=2e-4)
+        assert bool((table[1:] > table[:-1]).all())
+    sig = U.img2img_sigmas(20, 0.9)
+    assert sig[-1] == 0.0 and all(a > b for a, b in zip(sig[:-1], sig[1:])) and sig[0] < 14.614642
+    for a, b in zip(sig[:-2], sig[1:-1]):
+        down, up = U.ancestral_step(a, b)
+        assert down ** 2 + up ** 2 == pytest.approx(b ** 2, rel=1e-9) and 0 < up <= b
+    assert U.ancestral_step(sig[-2], 0.0) == (0.0, 0.0)
+    assert U.sigma_to_t(float(U.sdxl_sigmas()[500])) == pytest.approx(500.0, abs=1e-3)
