@@ -207,6 +207,10 @@ typedef struct SgnEpilogue {
 int sgn_gemm_f16(const void* d_a, int64_t lda, const void* d_w, int64_t ldw, int M, int N, int K,
                  const SgnEpilogue* ep, void* d_out, void* stream);
 
+/* Host-side probe of the tile schedule sgn_gemm_f16 would use (no launch, works without a GPU: 148 SMs assumed then):
+ * h_plan[6] = {block_n, cluster size, tiles, tail split, work items, scheduling units}. */
+int sgn_gemm_plan(int M, int N, int K, int residual_f32, int* h_plan);
+
 /* 3x3 / stride 1 / pad 1 convolution as an implicit GEMM on tcgen05.  d_x fp16 NHWC [B,H,W,C] (C % 64 == 0),
  * d_w fp16 [N, 9*C] with k = (ky*3 + kx)*C + c  (torch weight.permute(0,2,3,1)); out [B*H*W, N]. */
 int sgn_conv3x3_f16(const void* d_x, const void* d_w, int B, int H, int W, int C, int N, const SgnEpilogue* ep,

@@ -85,6 +85,7 @@ SIGNATURES = {
     "sgn_scatter_tiles_peer": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "sgn_quantize_u8": (_i, [_vp, _i64, _vp, _vp]),
     "sgn_gemm_f16": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, C.POINTER(SgnEpilogue), _vp, _vp]),
+    "sgn_gemm_plan": (_i, [_i, _i, _i, _i, C.POINTER(_i)]),
     "sgn_conv3x3_f16": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.POINTER(SgnEpilogue), _vp, _vp]),
     "sgn_attention_f16": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _f, _vp, _i64, _vp]),
     "sgn_group_norm_ws_doubles": (_i64, [_i, _i, _i]),

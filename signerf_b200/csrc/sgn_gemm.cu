@@ -681,6 +681,26 @@ extern "C" int sgn_gemm_f16(const void* d_a, int64_t lda, const void* d_w, int64
   return launch_gemm(tmA, tmB, tmBt, p, cluster, reinterpret_cast<cudaStream_t>(stream));
 }
 
+extern "C" int sgn_gemm_plan(int M, int N, int K, int residual_f32, int* h_plan) {
+  SGN_CHECK_ARG(M > 0 && N > 0 && K > 0 && h_plan, "bad arguments");
+  GemmParams p{};
+  p.num_m_tiles = (M + kBM - 1) / kBM;
+  p.num_k_blocks = (K + kBK - 1) / kBK;
+  const int n_rows = (N + 15) / 16 * 16;
+  p.block_n = pick_block_n(p.num_m_tiles, n_rows, residual_f32 ? p.num_k_blocks : 0);
+  p.num_n_tiles = (n_rows + p.block_n - 1) / p.block_n;
+  const int cluster = pick_cluster(p);
+  const int units = std::max(1, sm_count() / cluster);
+  const int tiles = (p.num_m_tiles + cluster - 1) / cluster * p.num_n_tiles;
+  int split = 1;
+  if (cluster == 2 && tiles >= units) split = tail_split_for(p.block_n, tiles % units, units);
+  const int rem = tiles % units;
+  h_plan[0] = p.block_n, h_plan[1] = cluster, h_plan[2] = tiles, h_plan[3] = split;
+  h_plan[4] = split > 1 ? tiles - rem + rem * split : tiles;
+  h_plan[5] = units;
+  return SGN_OK;
+}
+
 extern "C" int sgn_conv3x3_f16(const void* d_x, const void* d_w, int B, int H, int W, int C, int N,
                                const SgnEpilogue* ep, void* d_out, void* stream) {
   SGN_CHECK_ARG(B >= 0 && H > 0 && W > 0 && C > 0 && N > 0, "bad conv shape");

@@ -79,3 +79,30 @@ def test_unet_operator_argument_errors_are_reported_without_a_gpu():
     assert lib.sgn_cfg_euler_step(p16, p16, None, None, None, 1, 4, 2, 2, 7.0, 0.0, 0.5, 0.5, p16, None, None) == -1  # sigma 0
     assert lib.sgn_sheet_to_conditioning(p16, p16, 12, 16, p16, p16, None) == -1                  # sheet not multiple of 8
     assert lib.sgn_group_norm_ws_doubles(2, 65536, 32) >= 2 * 32 * 3
+
+
+def test_gemm_tile_schedule_plans():
+    """sgn_gemm_plan (host-only probe, 148 SMs): the widths / tail splits the persistent GEMM picks for the UNet's shapes.
+    A 2.16-wave GEMM gets its last round cut into column slices; short-K in-place-residual GEMMs get narrower tiles."""
+    lib = _lib.load()
+
+    def plan(M, N, K, res=0):
+        p = (C.c_int * 6)()
+        assert lib.sgn_gemm_plan(M, N, K, res, p) == 0
+        return dict(zip(("bn", "cluster", "tiles", "split", "items", "units"), p))
+
+    a = plan(8192, 1280, 1280)
+    assert (a["bn"], a["cluster"], a["tiles"], a["units"]) == (256, 2, 160, 74) and a["split"] == 4 and a["items"] == 148 + 12 * 4
+    assert plan(8192, 1280, 5120, 1)["split"] == 4
+    b = plan(8192, 3840, 1280)                      # 6.9 waves: last round nearly full, nothing to split
+    assert b["split"] == 1 and b["items"] == b["tiles"]
+    c = plan(32768, 640, 640, 1)                    # epilogue-bound: narrower than the widest tile
+    assert c["bn"] < 256 and c["bn"] % 16 == 0
+    d = plan(100, 48, 64)                           # one M tile: single-CTA shape
+    assert d["cluster"] == 1 and d["split"] == 1
+    for M, N, K in ((8192, 10240, 1280), (32768, 5120, 640), (131072, 320, 320), (154, 153600, 2048)):
+        q = plan(M, N, K)
+        assert q["bn"] % 16 == 0 and 16 <= q["bn"] <= 256 and q["items"] >= q["tiles"]
+        if q["split"] > 1:
+            assert (q["bn"] // q["split"]) % 32 == 0 and q["bn"] // q["split"] >= 64
+    assert lib.sgn_gemm_plan(0, 8, 8, 0, (C.c_int * 6)()) < 0
