@@ -173,3 +173,93 @@ def read_transforms(path) -> Dict[str, Any]:
     out["original_transform_matrix"] = (np.array(meta["original_transform_matrix"], np.float32)
                                         if "original_transform_matrix" in meta else None)
     return out
+
+
+# ---------------------------------------------------------------------------------------------- DataparserOutputs contract
+from dataclasses import dataclass, field as _field  # noqa: E402
+
+
+@dataclass
+class GeneratedDataparserOutputs:
+    """The fields of nerfstudio's `DataparserOutputs` as `SIGNeRFDataParser` fills them for a GENERATED dataset
+    (signerf/data/signerf_dataparser.py:301-312) — what `SIGNeRFPipeline` / `DatasetGenerator` consume
+    (`.dataparser_transform`, `.dataparser_scale`, `.image_filenames`, `.cameras`; signerf_pipeline.py:53-55)."""
+    image_filenames: List[Path]
+    cameras: Any                               # plugin.base.CameraBatch-like: camera_to_worlds [N,3,4] + per-frame intrinsics
+    scene_box: Tensor                          # aabb [2,3] = +-scene_scale
+    mask_filenames: Optional[List[Path]]
+    dataparser_scale: float
+    dataparser_transform: Tensor               # [3,4]
+    metadata: Dict[str, Any] = _field(default_factory=dict)
+
+
+@dataclass
+class FrameCameras:
+    """Per-frame pinhole cameras of a generated dataset (the subset of nerfstudio `Cameras` the path reads)."""
+    camera_to_worlds: Tensor                   # [N,3,4]
+    fx: Tensor
+    fy: Tensor
+    cx: Tensor
+    cy: Tensor
+    width: Tensor
+    height: Tensor
+
+    def __len__(self) -> int:
+        return self.camera_to_worlds.shape[0]
+
+
+def parse_generated_dataset(data_dir, scene_scale: float = 1.0, downscale_factor: int = 1,
+                            depth_unit_scale_factor: float = 1e-3) -> GeneratedDataparserOutputs:
+    """`SIGNeRFDataParser._generate_dataparser_outputs` for a dataset written by `generate_dataset`
+    (signerf_dataparser.py:57-313): poses from `scene_transform_matrix` as they are (the file carries
+    `original_transform_matrix` / `original_scale_factor`, so no re-orientation or re-scaling: :210-228), masks only for
+    merged datasets (`original_indices` present; frames outside it get an all-white `white.png`, :156-169), cameras
+    rescaled by 1 / downscale_factor (nerfstudio `rescale_output_resolution`: focal lengths and principal point scale,
+    sizes floor), scene box +-scene_scale."""
+    root = Path(data_dir)
+    meta = json.loads((root / "transforms.json").read_text())
+    original_indices = meta.get("original_indices")
+    image_filenames: List[Path] = []
+    mask_filenames: List[Path] = []
+    poses, fx, fy, cx, cy, hh, ww = [], [], [], [], [], [], []
+    for idx, frame in enumerate(meta["frames"]):
+        fname = root / Path(frame["file_path"])
+        if not fname.exists():
+            continue
+        for lst, key in ((fx, "fl_x"), (fy, "fl_y"), (cx, "cx"), (cy, "cy")):
+            assert key in frame, f"{key} not specified in frame"
+            lst.append(float(frame[key]))
+        hh.append(int(frame["h"]))
+        ww.append(int(frame["w"]))
+        image_filenames.append(fname)
+        poses.append(np.array(frame["scene_transform_matrix"] if "scene_transform_matrix" in frame else frame["transform_matrix"]))
+        if "_mask_path" in frame:
+            mask_fname = root / Path(frame["_mask_path"])
+            if original_indices is not None and idx not in original_indices:
+                white = mask_fname.parent / "white.png"
+                if not white.exists():
+                    from PIL import Image
+                    Image.new("L", (ww[-1], hh[-1]), color=255).save(white)
+                mask_filenames.append(white)
+            else:
+                mask_filenames.append(mask_fname)
+    assert len(image_filenames) != 0, "No image files found."
+    assert len(mask_filenames) in (0, len(image_filenames)), "Different number of image and mask filenames."
+    poses_t = torch.from_numpy(np.array(poses).astype(np.float32))
+    if "original_transform_matrix" not in meta or "original_scale_factor" not in meta:
+        raise ValueError("not a SIGNeRF-generated dataset: original_transform_matrix / original_scale_factor missing "
+                         "(auto-orientation of foreign datasets is nerfstudio's job)")
+    if "original_indices" not in meta:
+        mask_filenames = []
+    s = 1.0 / float(downscale_factor)
+    cams = FrameCameras(poses_t[:, :3, :4], torch.tensor(fx) * s, torch.tensor(fy) * s, torch.tensor(cx) * s, torch.tensor(cy) * s,
+                        torch.floor(torch.tensor(ww, dtype=torch.float32) * s).to(torch.int32),
+                        torch.floor(torch.tensor(hh, dtype=torch.float32) * s).to(torch.int32))
+    a = float(scene_scale)
+    return GeneratedDataparserOutputs(
+        image_filenames=image_filenames, cameras=cams,
+        scene_box=torch.tensor([[-a, -a, -a], [a, a, a]], dtype=torch.float32),
+        mask_filenames=mask_filenames if len(mask_filenames) > 0 else None,
+        dataparser_scale=float(meta["original_scale_factor"]),
+        dataparser_transform=torch.tensor(meta["original_transform_matrix"], dtype=torch.float32),
+        metadata={"depth_filenames": None, "depth_unit_scale_factor": depth_unit_scale_factor})

@@ -68,8 +68,23 @@ def test_writer_layout_schema_and_read_back(tmp_path):
     assert rd["poses"].shape == (2, 4, 4) and np.allclose(rd["poses"][0, :3], c2w.numpy())
     assert rd["fx"] == [10.0, 10.0] and rd["width"] == [10, 10] and rd["reference_indices"] == [0] and rd["num_skipped"] == 0
     assert rd["mask_filenames"][0].name == "mask_0.png" and rd["is_synthetic"] is True and rd["original_scale_factor"] == 0.5
+    # DataparserOutputs contract (signerf_dataparser.py:210-228, :301-312): poses as stored, transform / scale from the file
+    dp = IO.parse_generated_dataset(tmp_path / "exp", scene_scale=2.0, downscale_factor=2)
+    assert len(dp.image_filenames) == 2 and dp.mask_filenames is None            # masks only for merged datasets
+    assert dp.dataparser_scale == 0.5 and torch.equal(dp.dataparser_transform, torch.eye(4)[:3])
+    assert torch.equal(dp.scene_box, torch.tensor([[-2.0, -2.0, -2.0], [2.0, 2.0, 2.0]]))
+    assert torch.allclose(dp.cameras.camera_to_worlds[0], c2w) and dp.cameras.fx.tolist() == [5.0, 5.0]
+    assert dp.cameras.width.tolist() == [5, 5] and dp.cameras.height.tolist() == [4, 4] and len(dp.cameras) == 2
+    assert dp.metadata == {"depth_filenames": None, "depth_unit_scale_factor": 1e-3}
+    T["original_indices"] = [1]                                                  # merged dataset: frame 0 gets a white mask
+    (tmp_path / "exp" / "transforms.json").write_text(json.dumps(T, indent=4))
+    Image.new("L", (10, 8)).save(tmp_path / "exp" / "masks" / "mask_1.png")
+    dp = IO.parse_generated_dataset(tmp_path / "exp")
+    assert [m.name for m in dp.mask_filenames] == ["white.png", "mask_1.png"]
+    assert np.array(Image.open(tmp_path / "exp" / "masks" / "white.png")).min() == 255
     os.remove(tmp_path / "exp" / "images" / "image_1.png")               # a frame whose image is gone is skipped (:104-107)
     assert IO.read_transforms(tmp_path / "exp" / "transforms.json")["num_skipped"] == 1
+    assert len(IO.parse_generated_dataset(tmp_path / "exp").image_filenames) == 1
 
 
 @pytest.mark.gpu
