@@ -105,6 +105,14 @@ typedef struct SgnRenderOpts {
 int sgn_render_views(const SgnField* f, const float* d_c2w, const float* d_intr, int V, int H, int W,
                      const SgnRenderOpts* opts, float* d_rgb, float* d_depth, float* d_acc, void* stream);
 
+/* The second half alone, for a caller that already holds the rays: nerfstudio's
+ * `Model.get_outputs_for_camera_ray_bundle(camera_ray_bundle)` (datasetgenerator.py:694) on a RayBundle's
+ * `origins` / `directions` (unit length, as `Cameras.generate_rays` returns them), flattened row-major.
+ *   d_origins, d_directions [N,3] fp32; d_rgb [N,3], d_depth [N], d_acc [N] or NULL (device).
+ * Same sampling / field / compositing as sgn_render_views (near / far planes from opts: NearFarCollider). */
+int sgn_render_rays(const SgnField* f, const float* d_origins, const float* d_directions, int64_t N,
+                    const SgnRenderOpts* opts, float* d_rgb, float* d_depth, float* d_acc, void* stream);
+
 /* Same call with HOST buffers: H2D of the cameras and D2H of the images happen inside
  * (this is the end-to-end entry bench.py times as `e2e`).                                    */
 int sgn_render_views_host(const SgnField* f, const float* h_c2w, const float* h_intr, int V, int H, int W,
@@ -145,6 +153,15 @@ typedef struct SgnMaskOpts {
 int sgn_mask_condition(const float* d_c2w, const float* d_intr, int V, int H, int W, const float* d_depth,
                        const SgnMaskOpts* opts, uint8_t* d_mask, float* d_cond, float* d_stats,
                        void* stream);
+
+/* The same branch with combine_shape_with_depth=True (datasetgenerator.py:794-807): mask / min / max exactly as above;
+ * where the proxy mesh is in front of the NeRF surface ((shape_depth < depth) & (shape_depth > 0)) the condition takes
+ * the R channel of the mesh's colour image / 255 instead of the normalised NeRF depth, then 1 - clamp(.,0,1).
+ *   d_shape_depth [V,H,W,1] fp32 (0 = empty), d_shape_color [V,H,W,3] uint8 = Renderer.render_camera's two outputs
+ *   (signerf/renderer/renderer.py:149-196).                                                      */
+int sgn_mask_condition_combined(const float* d_c2w, const float* d_intr, int V, int H, int W, const float* d_depth,
+                                const float* d_shape_depth, const uint8_t* d_shape_color, const SgnMaskOpts* opts,
+                                uint8_t* d_mask, float* d_cond, float* d_stats, void* stream);
 
 /* cv2.dilate(mask, getStructuringElement(MORPH_ELLIPSE, (kw, kh))) > 0 on V binary images.    */
 int sgn_dilate_ellipse(const uint8_t* d_in, int V, int H, int W, int kw, int kh, uint8_t* d_out,
@@ -354,6 +371,12 @@ int64_t sgn_rasterize_ws_bytes(int Nv, int V, int H, int W);
 int sgn_rasterize_depth(const float* d_vertices, const int32_t* d_faces, int Nv, int Nf, const double* h_model,
                         const float* d_c2w, const float* d_intr, int V, int H, int W, double znear, double zfar, int cull_back,
                         void* d_ws, float* d_depth, void* stream);
+/* The colour image `Renderer.render_camera` returns next to the depth (renderer.py:187-196): the scene holds one mesh lit
+ * by ambient light 1.0 only (renderer.py:129-130), so every covered pixel has the material's flat base colour and every
+ * other pixel pyrender's background.  d_depth [npix] fp32 (0 = empty) -> d_color [npix,3] uint8; h_fg / h_bg: 3 bytes on
+ * the HOST. */
+int sgn_shape_color_u8(const float* d_depth, int64_t npix, const uint8_t* h_fg_rgb, const uint8_t* h_bg_rgb,
+                       uint8_t* d_color, void* stream);
 /* render_camera's masking_mode == "shape" branch (datasetgenerator.py:711-757) for V views: visible = (proxy < depth) &
  * (proxy > 0) (inverted when inverse_mask), cv2.dilate, min over visible proxy depths - radius, max over the whole proxy
  * image + radius (or manual_depth), condition = 1 - clamp(visible * proxy_n + ~visible * depth_n).  Same outputs /

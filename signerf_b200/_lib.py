@@ -73,11 +73,13 @@ SIGNATURES = {
     "sgn_field_create": (_i, [C.POINTER(SgnFieldDesc), C.POINTER(_vp)]),
     "sgn_field_destroy": (None, [_vp]),
     "sgn_render_views": (_i, [_vp, _vp, _vp, _i, _i, _i, C.POINTER(SgnRenderOpts), _vp, _vp, _vp, _vp]),
+    "sgn_render_rays": (_i, [_vp, _vp, _vp, _i64, C.POINTER(SgnRenderOpts), _vp, _vp, _vp, _vp]),
     "sgn_render_views_host": (_i, [_vp, _vp, _vp, _i, _i, _i, C.POINTER(SgnRenderOpts), _vp, _vp, _vp]),
     "sgn_generate_rays": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "sgn_hash_encode": (_i, [_vp, _i, _vp, _i64, _vp, _vp, _vp]),
     "sgn_field_eval": (_i, [_vp, _vp, _vp, _i64, _i, _vp, _vp, _vp]),
     "sgn_mask_condition": (_i, [_vp, _vp, _i, _i, _i, _vp, C.POINTER(SgnMaskOpts), _vp, _vp, _vp, _vp]),
+    "sgn_mask_condition_combined": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, C.POINTER(SgnMaskOpts), _vp, _vp, _vp, _vp]),
     "sgn_dilate_ellipse": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "sgn_sheet_paste": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "sgn_sheet_cut": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _i, _i, _vp]),
@@ -125,6 +127,7 @@ SIGNATURES = {
     "sgn_rasterize_ws_bytes": (_i64, [_i, _i, _i, _i]),
     "sgn_rasterize_depth": (_i, [_vp, _vp, _i, _i, C.POINTER(C.c_double), _vp, _vp, _i, _i, _i, C.c_double, C.c_double, _i,
                                 _vp, _vp, _vp]),
+    "sgn_shape_color_u8": (_i, [_vp, _i64, _vp, _vp, _vp, _vp]),
     "sgn_mask_condition_shape": (_i, [_vp, _vp, _i, _i, _i, C.POINTER(SgnMaskOpts), _vp, _vp, _vp, _vp]),
 }
 

@@ -11,7 +11,7 @@
 
 namespace sgn {
 
-int launch_render(const SgnField* f, const float* d_c2w, const float* d_intr, int V, int H, int W, int S,
+int launch_render(const SgnField* f, const RaySource& src, int V, int H, int W, int S,
                   const float* d_bins, const float* d_ray_bins, int mlp_mode, float* d_rgb, float* d_depth,
                   float* d_acc, cudaStream_t st);
 void host_flat_bins(int S, float near_p, float far_p, std::vector<float>& out);
@@ -21,8 +21,7 @@ constexpr int kPThreads = kPWarps * 32;
 
 struct PropParams {
   const PropDev* net;
-  const float* c2w;
-  const float* intr;
+  RaySource src;
   const float* bins;      // shared euclid edges [S+1] or null
   const float* ray_bins;  // per-ray euclid edges [rays][S+1] or null
   float* weights;         // out [rays][S]
@@ -45,13 +44,13 @@ __global__ void __launch_bounds__(kPThreads) k_prop_weights(const __grid_constan
   for (int tile = blockIdx.x * kPWarps + warp; tile < p.num_tiles; tile += gridDim.x * kPWarps) {
     int v = tile / per_view, r = tile - v * per_view;
     int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-    int x = tx * 8 + (lane & 7), y = ty * 4 + (lane >> 3);
+    int x, y;
+    tile_xy(p.src, tx, ty, lane, x, y);
     bool valid = x < p.W && y < p.H;
     x = min(x, p.W - 1);
     y = min(y, p.H - 1);
-    const Camera cam = load_camera(p.c2w, p.intr, v);
-    float d[3];
-    ray_direction(cam, (float)x + 0.5f, (float)y + 0.5f, 0.f, 0.f, d);
+    float ro[3], d[3];
+    load_ray(p.src, v, x, y, ro, d);
     size_t ray = ((size_t)v * p.H + y) * p.W + x;
     const float* rb = kPerRayBins ? p.ray_bins + ray * (size_t)(p.S + 1) : nullptr;
     float* wout = p.weights + ray * (size_t)p.S;
@@ -61,9 +60,9 @@ __global__ void __launch_bounds__(kPThreads) k_prop_weights(const __grid_constan
       const float t1 = kPerRayBins ? __ldg(rb + i + 1) : sbins[i + 1];
       const float mid = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
       float px, py, pz;
-      const bool sel = contract_to_unit(__fadd_rn(cam.o[0], __fmul_rn(d[0], mid)),
-                                        __fadd_rn(cam.o[1], __fmul_rn(d[1], mid)),
-                                        __fadd_rn(cam.o[2], __fmul_rn(d[2], mid)), px, py, pz);
+      const bool sel = contract_to_unit(__fadd_rn(ro[0], __fmul_rn(d[0], mid)),
+                                        __fadd_rn(ro[1], __fmul_rn(d[1], mid)),
+                                        __fadd_rn(ro[2], __fmul_rn(d[2], mid)), px, py, pz);
       float feat[10];
 #pragma unroll
       for (int l = 0; l < 5; ++l) {
@@ -172,7 +171,7 @@ struct AsyncBuf {
   T* as() { return reinterpret_cast<T*>(p); }
 };
 
-int render_cascade(const SgnField* f, const float* d_c2w, const float* d_intr, int V, int H, int W,
+int render_cascade(const SgnField* f, const RaySource& src, int V, int H, int W,
                    const SgnRenderOpts* o, float* d_rgb, float* d_depth, float* d_acc, cudaStream_t st) {
   if (f->num_proposals != 2) {
     set_error("cascade mode needs a field created with 2 proposal networks");
@@ -221,12 +220,16 @@ int render_cascade(const SgnField* f, const float* d_c2w, const float* d_intr, i
     const int nv = std::min(views_per_chunk, V - v0);
     const int64_t rays = (int64_t)rays_per_view * nv;
     PropParams pp;
-    pp.c2w = d_c2w + (size_t)v0 * 12;
-    pp.intr = d_intr + (size_t)v0 * 4;
+    pp.src = src;
+    if (src.c2w) {
+      pp.src.c2w = src.c2w + (size_t)v0 * 12;
+      pp.src.intr = src.intr + (size_t)v0 * 4;
+    }
     pp.weights = wbuf.as<float>();
     pp.V = nv; pp.H = H; pp.W = W;
-    pp.tiles_x = (W + 7) / 8;
-    pp.tiles_y = (H + 3) / 4;
+    const int tw = 1 << src.tw_log2, th = 32 >> src.tw_log2;
+    pp.tiles_x = (W + tw - 1) / tw;
+    pp.tiles_y = (H + th - 1) / th;
     pp.num_tiles = nv * pp.tiles_x * pp.tiles_y;
     const int pblocks = std::min((pp.num_tiles + kPWarps - 1) / kPWarps, nsm * 8);
     const int rblocks = (int)std::min<int64_t>((rays + 127) / 128, (int64_t)nsm * 16);
@@ -250,7 +253,7 @@ int render_cascade(const SgnField* f, const float* d_c2w, const float* d_intr, i
     SGN_LAUNCH_CHECK();
     // main field on the final per-ray bins
     const size_t off = (size_t)v0 * rays_per_view;
-    int rc = launch_render(f, pp.c2w, pp.intr, nv, H, W, S2, nullptr, eu2.as<float>(), o->mlp_mode, d_rgb + off * 3,
+    int rc = launch_render(f, pp.src, nv, H, W, S2, nullptr, eu2.as<float>(), o->mlp_mode, d_rgb + off * 3,
                            d_depth + off, d_acc ? d_acc + off : nullptr, st);
     if (rc) return rc;
   }

@@ -83,6 +83,38 @@ __device__ __forceinline__ float ray_direction(const Camera& c, float x, float y
   return n;
 }
 
+// Where a kernel's rays come from: pinhole cameras (c2w / intr, the pixel grid of V views, warp tile 8x4 pixels) or an
+// explicit bundle of N rays (origins / directions [N,3]: nerfstudio's RayBundle as `get_outputs_for_camera_ray_bundle`
+// receives it, datasetgenerator.py:691-694; addressed as ONE H=1, W=N image with 32x1 warp tiles).
+struct RaySource {
+  const float* c2w;
+  const float* intr;
+  const float* rays_o;
+  const float* rays_d;
+  int tw_log2;  // log2 of the warp tile's width: 3 (8x4 pixels) for cameras, 5 (32 consecutive rays) for bundles
+};
+
+// pixel (x, y) of lane-row `row` of tile (tx, ty)
+__device__ __forceinline__ void tile_xy(const RaySource& rs, int tx, int ty, int row, int& x, int& y) {
+  x = (tx << rs.tw_log2) + (row & ((1 << rs.tw_log2) - 1));
+  y = ty * (32 >> rs.tw_log2) + (row >> rs.tw_log2);
+}
+
+// origin + unit direction of the ray through pixel (x, y) of view v (cameras) or ray x of the bundle
+__device__ __forceinline__ void load_ray(const RaySource& rs, int v, int x, int y, float o[3], float d[3]) {
+  if (rs.rays_o) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      o[k] = __ldg(rs.rays_o + 3 * (size_t)x + k);
+      d[k] = __ldg(rs.rays_d + 3 * (size_t)x + k);
+    }
+  } else {
+    const Camera cam = load_camera(rs.c2w, rs.intr, v);
+    o[0] = cam.o[0]; o[1] = cam.o[1]; o[2] = cam.o[2];
+    ray_direction(cam, (float)x + 0.5f, (float)y + 0.5f, 0.f, 0.f, d);
+  }
+}
+
 // ---------------------------------------------------------------- samplers (A3)
 __device__ __forceinline__ float spacing_fn(float x) {  // UniformLinDispPiecewiseSampler
   return x < 1.f ? __fmul_rn(x, 0.5f) : __fsub_rn(1.f, __fdiv_rn(1.f, __fmul_rn(2.f, x)));

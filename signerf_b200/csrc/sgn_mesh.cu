@@ -225,9 +225,33 @@ __global__ void __launch_bounds__(256) k_shape_condition(const float* __restrict
   }
 }
 
+// pyrender's colour image of a mesh lit by ambient light only (renderer.py:129-130): the flat material colour on
+// covered pixels, the scene background elsewhere.
+__global__ void __launch_bounds__(256) k_shape_color(const float* __restrict__ depth, size_t npix, uchar3 fg, uchar3 bg,
+                                                     uint8_t* __restrict__ out) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+    const uchar3 c = depth[i] > 0.f ? fg : bg;
+    out[3 * i + 0] = c.x;
+    out[3 * i + 1] = c.y;
+    out[3 * i + 2] = c.z;
+  }
+}
+
 }  // namespace sgn
 
 using namespace sgn;
+
+extern "C" int sgn_shape_color_u8(const float* d_depth, int64_t npix, const uint8_t* h_fg_rgb, const uint8_t* h_bg_rgb,
+                                  uint8_t* d_color, void* stream) {
+  SGN_CHECK_ARG(npix >= 0, "negative pixel count");
+  if (npix == 0) return SGN_OK;
+  SGN_CHECK_ARG(d_depth && h_fg_rgb && h_bg_rgb && d_color, "null pointer");
+  k_shape_color<<<grid_m((size_t)npix, 256), 256, 0, STM(stream)>>>(d_depth, (size_t)npix,
+                                                                    make_uchar3(h_fg_rgb[0], h_fg_rgb[1], h_fg_rgb[2]),
+                                                                    make_uchar3(h_bg_rgb[0], h_bg_rgb[1], h_bg_rgb[2]), d_color);
+  SGN_LAUNCH_CHECK();
+  return SGN_OK;
+}
 
 extern "C" int64_t sgn_rasterize_ws_bytes(int Nv, int V, int H, int W) {
   if (Nv <= 0 || V <= 0 || H <= 0 || W <= 0) return 0;

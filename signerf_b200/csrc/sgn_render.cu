@@ -27,8 +27,7 @@ struct RenderParams {
   GridDev grid;
   const MlpPack* pack;
   const MlpF32* f32;
-  const float* c2w;
-  const float* intr;
+  RaySource src;
   const float* bins;      // [S+1] euclidean edges shared by all rays, or
   const float* ray_bins;  // [V*H*W, S+1] per-ray euclidean edges (cascade)
   int V, H, W, S;
@@ -49,7 +48,8 @@ __device__ __forceinline__ TileCoord tile_pixel(const RenderParams& p, int tile,
   c.v = tile / per_view;
   int r = tile - c.v * per_view;
   int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-  int x = tx * kTileW + (row & 7), y = ty * kTileH + (row >> 3);
+  int x, y;
+  tile_xy(p.src, tx, ty, row, x, y);
   c.valid = (x < p.W) & (y < p.H);
   c.px = min(x, p.W - 1);
   c.py = min(y, p.H - 1);
@@ -97,9 +97,8 @@ __global__ void __launch_bounds__(kThreads, 4) k_render_mma(const __grid_constan
   for (int tile = blockIdx.x * kWarps + warp; tile < p.num_tiles; tile += gridDim.x * kWarps) {
     const TileCoord cf = tile_pixel(p, tile, lane);  // pixel whose features this lane computes
     const TileCoord cc = tile_pixel(p, tile, rc);    // pixel this lane composites
-    const Camera cam = load_camera(p.c2w, p.intr, cf.v);
-    float d[3];
-    ray_direction(cam, (float)cf.px + 0.5f, (float)cf.py + 0.5f, 0.f, 0.f, d);
+    float ro[3], d[3];
+    load_ray(p.src, cf.v, cf.px, cf.py, ro, d);
     uint32_t ash[2][4];
     {
       float sh[16];
@@ -126,9 +125,9 @@ __global__ void __launch_bounds__(kThreads, 4) k_render_mma(const __grid_constan
       }
       const float fmid = __fmul_rn(__fadd_rn(tf0, tf1), 0.5f);
       float px, py, pz;
-      const bool sel = contract_to_unit(__fadd_rn(cam.o[0], __fmul_rn(d[0], fmid)),
-                                        __fadd_rn(cam.o[1], __fmul_rn(d[1], fmid)),
-                                        __fadd_rn(cam.o[2], __fmul_rn(d[2], fmid)), px, py, pz);
+      const bool sel = contract_to_unit(__fadd_rn(ro[0], __fmul_rn(d[0], fmid)),
+                                        __fadd_rn(ro[1], __fmul_rn(d[1], fmid)),
+                                        __fadd_rn(ro[2], __fmul_rn(d[2], fmid)), px, py, pz);
       float logit, cr, cg, cbv;
       warp_field_eval(p.grid, sp, stage, lane, px, py, pz, ash, logit, cr, cg, cbv);
       const bool sel_c = __shfl_sync(0xffffffffu, (int)sel, rc) != 0;
@@ -156,9 +155,8 @@ __global__ void __launch_bounds__(kThreads) k_render_f32(const __grid_constant__
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int tile = blockIdx.x * kWarps + warp; tile < p.num_tiles; tile += gridDim.x * kWarps) {
     const TileCoord c = tile_pixel(p, tile, lane);
-    const Camera cam = load_camera(p.c2w, p.intr, c.v);
-    float d[3], sh[16];
-    ray_direction(cam, (float)c.px + 0.5f, (float)c.py + 0.5f, 0.f, 0.f, d);
+    float ro[3], d[3], sh[16];
+    load_ray(p.src, c.v, c.px, c.py, ro, d);
     sh16(d[0], d[1], d[2], sh);
     const float* rb = kPerRayBins ? p.ray_bins + (((size_t)c.v * p.H + c.py) * p.W + c.px) * (size_t)(p.S + 1) : nullptr;
     Composite comp;
@@ -168,9 +166,9 @@ __global__ void __launch_bounds__(kThreads) k_render_f32(const __grid_constant__
       const float t1 = kPerRayBins ? __ldg(rb + i + 1) : sbins[i + 1];
       const float mid = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
       float px, py, pz;
-      const bool sel = contract_to_unit(__fadd_rn(cam.o[0], __fmul_rn(d[0], mid)),
-                                        __fadd_rn(cam.o[1], __fmul_rn(d[1], mid)),
-                                        __fadd_rn(cam.o[2], __fmul_rn(d[2], mid)), px, py, pz);
+      const bool sel = contract_to_unit(__fadd_rn(ro[0], __fmul_rn(d[0], mid)),
+                                        __fadd_rn(ro[1], __fmul_rn(d[1], mid)),
+                                        __fadd_rn(ro[2], __fmul_rn(d[2], mid)), px, py, pz);
       float feat[32];
 #pragma unroll
       for (int l = 0; l < 16; ++l) {
@@ -361,20 +359,20 @@ static int set_smem(K kernel, size_t bytes) {
 }
 
 // Launch the main-field march.  d_bins: [S+1] shared edges, or d_ray_bins per ray.
-int launch_render(const SgnField* f, const float* d_c2w, const float* d_intr, int V, int H, int W, int S,
+int launch_render(const SgnField* f, const RaySource& src, int V, int H, int W, int S,
                   const float* d_bins, const float* d_ray_bins, int mlp_mode, float* d_rgb, float* d_depth,
                   float* d_acc, cudaStream_t st) {
   RenderParams p;
   p.grid = f->grid;
   p.pack = f->d_pack;
   p.f32 = f->d_f32;
-  p.c2w = d_c2w;
-  p.intr = d_intr;
+  p.src = src;
   p.bins = d_bins;
   p.ray_bins = d_ray_bins;
   p.V = V; p.H = H; p.W = W; p.S = S;
-  p.tiles_x = (W + kTileW - 1) / kTileW;
-  p.tiles_y = (H + kTileH - 1) / kTileH;
+  const int tw = 1 << src.tw_log2, th = 32 >> src.tw_log2;
+  p.tiles_x = (W + tw - 1) / tw;
+  p.tiles_y = (H + th - 1) / th;
   p.num_tiles = V * p.tiles_x * p.tiles_y;
   p.rgb = d_rgb; p.depth = d_depth; p.acc = d_acc;
   const bool per_ray = d_ray_bins != nullptr;
@@ -408,24 +406,20 @@ int launch_render(const SgnField* f, const float* d_c2w, const float* d_intr, in
   return SGN_OK;
 }
 
-int render_cascade(const SgnField* f, const float* d_c2w, const float* d_intr, int V, int H, int W,
+int render_cascade(const SgnField* f, const RaySource& src, int V, int H, int W,
                    const SgnRenderOpts* o, float* d_rgb, float* d_depth, float* d_acc, cudaStream_t st);
 
 }  // namespace sgn
 
 using namespace sgn;
 
-extern "C" int sgn_render_views(const SgnField* f, const float* d_c2w, const float* d_intr, int V, int H, int W,
-                                const SgnRenderOpts* o, float* d_rgb, float* d_depth, float* d_acc, void* stream) {
-  SGN_CHECK_ARG(f && o, "null field/opts");
-  SGN_CHECK_ARG(V >= 0 && H > 0 && W > 0, "bad image shape");
-  SGN_CHECK_ARG(V == 0 || (d_c2w && d_intr && d_rgb && d_depth), "null pointer");
+static int render_from(const SgnField* f, const RaySource& src, int V, int H, int W, const SgnRenderOpts* o,
+                       float* d_rgb, float* d_depth, float* d_acc, void* stream) {
   SGN_CHECK_ARG(o->mlp_mode == SGN_MLP_FP16_MMA || o->mlp_mode == SGN_MLP_FP32, "bad mlp_mode");
   SGN_CHECK_ARG(o->num_samples >= 1 && o->num_samples < kMaxBins, "num_samples must be 1..1024");
   SGN_CHECK_ARG(o->far_plane > o->near_plane && o->near_plane >= 0.f, "need 0 <= near < far");
-  if (V == 0) return SGN_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (o->mode == 1) return render_cascade(f, d_c2w, d_intr, V, H, W, o, d_rgb, d_depth, d_acc, st);
+  if (o->mode == 1) return render_cascade(f, src, V, H, W, o, d_rgb, d_depth, d_acc, st);
   SGN_CHECK_ARG(o->mode == 0, "mode must be 0 (flat) or 1 (cascade)");
   const int S = o->num_samples;
   std::vector<float> bins;
@@ -439,9 +433,36 @@ extern "C" int sgn_render_views(const SgnField* f, const float* d_c2w, const flo
   SGN_CUDA(cudaMemcpyAsync(d_bins, hb, (size_t)(S + 1) * 4, cudaMemcpyHostToDevice, st));
   // the pageable source must stay alive until the copy is consumed: it is staged synchronously by the
   // runtime for pageable memory, so `bins` may go out of scope after this call returns.
-  int rc = launch_render(f, d_c2w, d_intr, V, H, W, S, d_bins, nullptr, o->mlp_mode, d_rgb, d_depth, d_acc, st);
+  int rc = launch_render(f, src, V, H, W, S, d_bins, nullptr, o->mlp_mode, d_rgb, d_depth, d_acc, st);
   cudaFreeAsync(d_bins, st);
   return rc;
+}
+
+extern "C" int sgn_render_views(const SgnField* f, const float* d_c2w, const float* d_intr, int V, int H, int W,
+                                const SgnRenderOpts* o, float* d_rgb, float* d_depth, float* d_acc, void* stream) {
+  SGN_CHECK_ARG(f && o, "null field/opts");
+  SGN_CHECK_ARG(V >= 0 && H > 0 && W > 0, "bad image shape");
+  SGN_CHECK_ARG(V == 0 || (d_c2w && d_intr && d_rgb && d_depth), "null pointer");
+  if (V == 0) return SGN_OK;
+  const RaySource src{d_c2w, d_intr, nullptr, nullptr, 3};
+  return render_from(f, src, V, H, W, o, d_rgb, d_depth, d_acc, stream);
+}
+
+extern "C" int sgn_render_rays(const SgnField* f, const float* d_origins, const float* d_directions, int64_t N,
+                               const SgnRenderOpts* o, float* d_rgb, float* d_depth, float* d_acc, void* stream) {
+  SGN_CHECK_ARG(f && o, "null field/opts");
+  SGN_CHECK_ARG(N >= 0 && N < ((int64_t)1 << 31) - 64, "ray count must be in [0, 2^31)");
+  if (N == 0) return SGN_OK;
+  SGN_CHECK_ARG(d_origins && d_directions && d_rgb && d_depth, "null pointer");
+  // the sampling cascade keeps [rays, 257] scratch rows: bundles go through it 2^20 rays at a time
+  const int64_t chunk = o->mode == 1 ? ((int64_t)1 << 20) : N;
+  for (int64_t r0 = 0; r0 < N; r0 += chunk) {
+    const int64_t n = std::min(chunk, N - r0);
+    const RaySource src{nullptr, nullptr, d_origins + 3 * r0, d_directions + 3 * r0, 5};
+    int rc = render_from(f, src, 1, 1, (int)n, o, d_rgb + 3 * r0, d_depth + r0, d_acc ? d_acc + r0 : nullptr, stream);
+    if (rc) return rc;
+  }
+  return SGN_OK;
 }
 
 extern "C" int sgn_render_views_host(const SgnField* f, const float* h_c2w, const float* h_intr, int V, int H, int W,

@@ -140,9 +140,14 @@ __global__ void __launch_bounds__(256) k_dilate_runs(const int* __restrict__ pre
   }
 }
 
+// shape_depth / shape_color != nullptr: combine_shape_with_depth (datasetgenerator.py:794-807): where the proxy mesh is
+// in front of the NeRF surface the condition is the R channel of the mesh's colour image / 255 instead of the normalised
+// NeRF depth.
 __global__ void __launch_bounds__(256) k_condition(const float* __restrict__ depth, const ViewStats* __restrict__ stats,
                                                    int V, int npix, SgnMaskOpts o, float* __restrict__ cond,
-                                                   uint8_t* __restrict__ mask, float* __restrict__ out_stats) {
+                                                   uint8_t* __restrict__ mask, float* __restrict__ out_stats,
+                                                   const float* __restrict__ shape_depth = nullptr,
+                                                   const uint8_t* __restrict__ shape_color = nullptr) {
   const size_t n = (size_t)V * npix;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     int v = (int)(i / npix);
@@ -152,6 +157,10 @@ __global__ void __launch_bounds__(256) k_condition(const float* __restrict__ dep
       float mn = o.use_manual_depth ? o.manual_min : __fsub_rn(__uint_as_float(s.min_bits), o.depth_radius);
       float mx = o.use_manual_depth ? o.manual_max : __fadd_rn(__uint_as_float(s.max_bits), o.depth_radius);
       float nrm = __fdiv_rn(__fsub_rn(depth[i], mn), __fsub_rn(mx, mn));
+      if (shape_depth) {
+        const float sd = shape_depth[i];
+        if (sd > 0.f && sd < depth[i]) nrm = __fdiv_rn((float)shape_color[3 * i], 255.f);
+      }
       c = __fsub_rn(1.f, fminf(fmaxf(nrm, 0.f), 1.f));
     } else {
       mask[i] = 0;  // not visible: zero mask even when inverse_mask dilated nothing
@@ -309,8 +318,9 @@ extern "C" int sgn_dilate_ellipse(const uint8_t* d_in, int V, int H, int W, int 
   return dilate_impl(d_in, V, H, W, kw, kh, d_out, reinterpret_cast<cudaStream_t>(stream));
 }
 
-extern "C" int sgn_mask_condition(const float* d_c2w, const float* d_intr, int V, int H, int W, const float* d_depth,
-                                  const SgnMaskOpts* o, uint8_t* d_mask, float* d_cond, float* d_stats, void* stream) {
+static int mask_condition_impl(const float* d_c2w, const float* d_intr, int V, int H, int W, const float* d_depth,
+                               const SgnMaskOpts* o, const float* d_shape_depth, const uint8_t* d_shape_color,
+                               uint8_t* d_mask, float* d_cond, float* d_stats, void* stream) {
   SGN_CHECK_ARG(o != nullptr, "null opts");
   SGN_CHECK_ARG(V >= 0 && H > 0 && W > 0, "bad image shape");
   SGN_CHECK_ARG(V == 0 || (d_c2w && d_intr && d_depth && d_mask && d_cond), "null pointer");
@@ -331,7 +341,8 @@ extern "C" int sgn_mask_condition(const float* d_c2w, const float* d_intr, int V
   int rc = SGN_OK;
   if (dil) rc = dilate_impl(vis, V, H, W, o->dilate_w, o->dilate_h, d_mask, st);
   if (rc == SGN_OK) {
-    k_condition<<<grid_for((size_t)V * npix, 256), 256, 0, st>>>(d_depth, stats, V, (int)npix, *o, d_cond, d_mask, d_stats);
+    k_condition<<<grid_for((size_t)V * npix, 256), 256, 0, st>>>(d_depth, stats, V, (int)npix, *o, d_cond, d_mask, d_stats,
+                                                                 d_shape_depth, d_shape_color);
     count_launch();
     if (cudaPeekAtLastError() != cudaSuccess) {
       set_error(std::string("k_condition launch failed: ") + cudaGetErrorString(cudaGetLastError()));
@@ -341,6 +352,20 @@ extern "C" int sgn_mask_condition(const float* d_c2w, const float* d_intr, int V
   if (vis) cudaFreeAsync(vis, st);
   cudaFreeAsync(stats, st);
   return rc;
+}
+
+extern "C" int sgn_mask_condition(const float* d_c2w, const float* d_intr, int V, int H, int W, const float* d_depth,
+                                  const SgnMaskOpts* o, uint8_t* d_mask, float* d_cond, float* d_stats, void* stream) {
+  return mask_condition_impl(d_c2w, d_intr, V, H, W, d_depth, o, nullptr, nullptr, d_mask, d_cond, d_stats, stream);
+}
+
+extern "C" int sgn_mask_condition_combined(const float* d_c2w, const float* d_intr, int V, int H, int W,
+                                           const float* d_depth, const float* d_shape_depth,
+                                           const uint8_t* d_shape_color, const SgnMaskOpts* o, uint8_t* d_mask,
+                                           float* d_cond, float* d_stats, void* stream) {
+  SGN_CHECK_ARG(V == 0 || (d_shape_depth && d_shape_color), "null shape depth / colour");
+  return mask_condition_impl(d_c2w, d_intr, V, H, W, d_depth, o, d_shape_depth, d_shape_color, d_mask, d_cond, d_stats,
+                             stream);
 }
 
 extern "C" int sgn_sheet_paste(const void* d_src, int src_u8, int V, int H, int W, int C, float* d_sheet, int sheet_h,

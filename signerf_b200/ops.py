@@ -99,6 +99,27 @@ def render_views(fld: NerfactoFieldB200, c2w: Tensor, intr: Tensor, height: int,
     return (rgb, depth, acc) if want_acc else (rgb, depth)
 
 
+def render_rays(fld: NerfactoFieldB200, origins: Tensor, directions: Tensor, opts: RenderOptions, want_acc: bool = False):
+    """An explicit ray bundle (nerfstudio RayBundle.origins / .directions of any leading shape [..., 3]) ->
+    (rgb [...,3], depth [...,1][, acc [...,1]]): `get_outputs_for_camera_ray_bundle`'s contract (datasetgenerator.py:694)."""
+    dev = fld.device
+    lead = tuple(origins.shape[:-1])
+    o = _req(origins.reshape(-1, 3), torch.float32, "origins")
+    d = _req(directions.reshape(-1, 3), torch.float32, "directions")
+    if o.shape != d.shape:
+        raise ValueError(f"origins {tuple(origins.shape)} and directions {tuple(directions.shape)} differ")
+    n = o.shape[0]
+    rgb = torch.empty(lead + (3,), dtype=torch.float32, device=dev)
+    depth = torch.empty(lead + (1,), dtype=torch.float32, device=dev)
+    acc = torch.empty(lead + (1,), dtype=torch.float32, device=dev) if want_acc else None
+    keep: list = []
+    co = opts.to_c(keep)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().sgn_render_rays(fld.handle, _ptr(o), _ptr(d), n, C.byref(co), _ptr(rgb), _ptr(depth), _ptr(acc),
+                                               _stream(dev)))
+    return (rgb, depth, acc) if want_acc else (rgb, depth)
+
+
 def render_views_host(fld: NerfactoFieldB200, c2w: np.ndarray, intr: np.ndarray, height: int, width: int,
                       opts: RenderOptions, out_rgb: np.ndarray, out_depth: np.ndarray) -> None:
     """End-to-end entry with HOST buffers (cameras in, images out): H2D + kernels + D2H inside the call."""
@@ -194,6 +215,31 @@ def mask_condition(c2w: Tensor, intr: Tensor, depth: Tensor, opts: MaskOptions):
     return mask, cond, stats
 
 
+def mask_condition_combined(c2w: Tensor, intr: Tensor, depth: Tensor, shape_depth: Tensor, shape_color: Tensor, opts: MaskOptions):
+    """The "aabb" branch with combine_shape_with_depth (datasetgenerator.py:794-807): `shape_depth` [V,H,W,1] fp32 and
+    `shape_color` [V,H,W,3] uint8 are Renderer.render_camera's outputs; same returns as mask_condition."""
+    depth = _req(depth, torch.float32, "depth")
+    shape_depth = _req(shape_depth, torch.float32, "shape_depth")
+    if not shape_color.is_cuda or shape_color.dtype != torch.uint8:
+        raise TypeError("shape_color must be a CUDA uint8 tensor [V,H,W,3]")
+    shape_color = shape_color.contiguous()
+    V, H, W = depth.shape[0], depth.shape[1], depth.shape[2]
+    if tuple(shape_depth.shape[:3]) != (V, H, W) or tuple(shape_color.shape) != (V, H, W, 3):
+        raise ValueError("shape depth / colour do not match the depth images")
+    dev = depth.device
+    c2w = _req(c2w[..., :3, :4], torch.float32, "c2w")
+    intr = _req(intr, torch.float32, "intr")
+    mask = torch.empty((V, H, W, 1), dtype=torch.uint8, device=dev)
+    cond = torch.empty((V, H, W, 1), dtype=torch.float32, device=dev)
+    stats = torch.empty((V, 4), dtype=torch.float32, device=dev)
+    o = opts.to_c()
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().sgn_mask_condition_combined(_ptr(c2w), _ptr(intr), V, H, W, _ptr(depth), _ptr(shape_depth),
+                                                           _ptr(shape_color), C.byref(o), _ptr(mask), _ptr(cond), _ptr(stats),
+                                                           _stream(dev)))
+    return mask, cond, stats
+
+
 def mask_condition_shape(proxy_depth: Tensor, depth: Tensor, opts: MaskOptions):
     """render_camera's "shape" masking branch for V views (proxy-mesh depth vs NeRF depth): same outputs as mask_condition."""
     depth = _req(depth, torch.float32, "depth")
@@ -232,6 +278,17 @@ def rasterize_depth(vertices: Tensor, faces: Tensor, model, c2w: Tensor, intr: T
         _lib.check(lib.sgn_rasterize_depth(_ptr(vertices), _ptr(faces), Nv, Nf, m, _ptr(c2w), _ptr(intr), V, H, W,
                                            float(znear), float(zfar), int(cull_back), _ptr(ws), _ptr(depth), _stream(dev)))
     return depth
+
+
+def shape_color_u8(depth: Tensor, fg_rgb: Tuple[int, int, int], bg_rgb: Tuple[int, int, int] = (255, 255, 255)) -> Tensor:
+    """Flat-ambient colour image of the proxy mesh: depth [...,1] fp32 (0 = empty) -> uint8 [...,3]."""
+    depth = _req(depth, torch.float32, "depth")
+    out = torch.empty(tuple(depth.shape[:-1]) + (3,), dtype=torch.uint8, device=depth.device)
+    fg = (C.c_uint8 * 3)(*[int(c) for c in fg_rgb])
+    bg = (C.c_uint8 * 3)(*[int(c) for c in bg_rgb])
+    with torch.cuda.device(depth.device):
+        _lib.check(_lib.load().sgn_shape_color_u8(_ptr(depth), depth.numel(), fg, bg, _ptr(out), _stream(depth.device)))
+    return out
 
 
 def dilate_ellipse(mask: Tensor, ksize: Tuple[int, int]) -> Tensor:

@@ -213,7 +213,9 @@ def parse_generated_dataset(data_dir, scene_scale: float = 1.0, downscale_factor
     """`SIGNeRFDataParser._generate_dataparser_outputs` for a dataset written by `generate_dataset`
     (signerf_dataparser.py:57-313): poses from `scene_transform_matrix` as they are (the file carries
     `original_transform_matrix` / `original_scale_factor`, so no re-orientation or re-scaling: :210-228), masks only for
-    merged datasets (`original_indices` present; frames outside it get an all-white `white.png`, :156-169), cameras
+    merged datasets (`original_indices` present; frames outside it get an all-white `white.png`, :156-169); with
+    downscale_factor > 1 images / masks resolve to `images_<ds>/<name>` / `masks_<ds>/<name>` (`_get_fname`, :330-357:
+    existence check, returned paths and `white.png` all live there); cameras
     rescaled by 1 / downscale_factor (nerfstudio `rescale_output_resolution`: focal lengths and principal point scale,
     sizes floor), scene box +-scene_scale."""
     root = Path(data_dir)
@@ -222,8 +224,15 @@ def parse_generated_dataset(data_dir, scene_scale: float = 1.0, downscale_factor
     image_filenames: List[Path] = []
     mask_filenames: List[Path] = []
     poses, fx, fy, cx, cy, hh, ww = [], [], [], [], [], [], []
+    ds = int(downscale_factor)
+
+    def get_fname(filepath: Path, prefix: str) -> Path:
+        """`SIGNeRFDataParser._get_fname` (signerf_dataparser.py:330-357) for an explicit downscale factor: the
+        down-sampled copies live in `<prefix><ds>/<file name>` next to the full-resolution folder."""
+        return root / f"{prefix}{ds}" / filepath.name if ds > 1 else root / filepath
+
     for idx, frame in enumerate(meta["frames"]):
-        fname = root / Path(frame["file_path"])
+        fname = get_fname(Path(frame["file_path"]), "images_")
         if not fname.exists():
             continue
         for lst, key in ((fx, "fl_x"), (fy, "fl_y"), (cx, "cx"), (cy, "cy")):
@@ -234,7 +243,7 @@ def parse_generated_dataset(data_dir, scene_scale: float = 1.0, downscale_factor
         image_filenames.append(fname)
         poses.append(np.array(frame["scene_transform_matrix"] if "scene_transform_matrix" in frame else frame["transform_matrix"]))
         if "_mask_path" in frame:
-            mask_fname = root / Path(frame["_mask_path"])
+            mask_fname = get_fname(Path(frame["_mask_path"]), "masks_")
             if original_indices is not None and idx not in original_indices:
                 white = mask_fname.parent / "white.png"
                 if not white.exists():

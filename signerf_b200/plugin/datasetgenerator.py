@@ -83,26 +83,93 @@ class DatasetGenerator:
     def _layout(self, scaled_w: int, scaled_h: int) -> ops.SheetLayout:
         return ops.SheetLayout(self.rows, self.cols, scaled_h, scaled_w, self.border_width_between_images)
 
-    def render_views(self, graph, cameras) -> Tuple[Tensor, Tensor, Tensor]:
+    # ------------------------------------------------------------------ NeRF forward behind the reference's model contract
+    def _fused_graph(self, graph):
+        """The fused sm_100a renderer for `graph`.  A graph that offers `render_cameras` (plugin.FusedNerfactoGraph, or a
+        SIGNeRFModel carrying the `signerf.signerf` shim's override) is used as it is.  Any other nerfstudio `Model`
+        only promises the reference contract (`render_aabb`, `eval / train`, `device`,
+        `get_outputs_for_camera_ray_bundle`, datasetgenerator.py:691-701): its nerfacto parameters are packed into a
+        FusedNerfactoGraph once per weight version and that renderer is attached behind the call.  Returns None when
+        the parameters are not torch-fallback nerfacto tensors (tcnn `params` blobs, other model families)."""
+        if hasattr(graph, "render_cameras"):
+            return graph
+        if not hasattr(graph, "state_dict"):
+            return None
+        from .model import FusedNerfactoGraph
+        sd = graph.state_dict()
+        version = tuple((k, int(v.data_ptr()), int(getattr(v, "_version", 0))) for k, v in sd.items() if isinstance(v, Tensor))
+        cached = getattr(self, "_fused_cache", None)
+        if cached is not None and cached[0] is graph and cached[1] == version:
+            return cached[2]
+        cfg = getattr(graph, "config", None)
+        try:
+            fused = FusedNerfactoGraph.from_state_dict(
+                sd, device=graph.device, num_train_data=getattr(graph, "num_train_data", None),
+                average_init_density=float(getattr(cfg, "average_init_density", 0.01)), near_plane=float(getattr(cfg, "near_plane", 0.05)),
+                far_plane=float(getattr(cfg, "far_plane", 1000.0)))
+        except KeyError as e:
+            if not getattr(self, "_warned_no_fused", False):
+                print(f"[signerf_b200] fused renderer not attached ({e}); rendering through the model's own "
+                      "get_outputs_for_camera_ray_bundle")
+                self._warned_no_fused = True
+            fused = None
+        if cached is not None and cached[2] is not None and cached[2] is not fused:
+            cached[2].field.close()
+        self._fused_cache = (graph, version, fused)
+        return fused
+
+    def _nerf_outputs(self, graph, cameras, cam: CameraBatch) -> Dict[str, Tensor]:
+        """{"rgb" [V,H,W,3], "depth" [V,H,W,1]} of V cameras: datasetgenerator.py:691-701 for all of them at once."""
+        if getattr(graph, "render_aabb", None) is not None:
+            raise NotImplementedError("graph.render_aabb (the viewer's crop box, datasetgenerator.py:691) is not supported by the "
+                                      "fused renderer: disable the crop before generating")
+        fused = self._fused_graph(graph)
+        graph.eval()
+        try:
+            if fused is not None:
+                out = fused.render_cameras(cam)
+            else:   # the model's own forward, view by view, exactly as the reference calls it
+                views = [cameras] if not hasattr(cameras, "__len__") or getattr(cameras, "camera_to_worlds").dim() == 2 else \
+                    [cameras[i] for i in range(len(cam))]
+                outs = []
+                for c in views:
+                    if not hasattr(c, "generate_rays"):
+                        raise TypeError("this graph needs nerfstudio `Cameras` (camera.generate_rays) - plugin.CameraBatch only "
+                                        "drives the fused renderer")
+                    bundle = c.generate_rays(camera_indices=0, aabb_box=None)
+                    o = graph.get_outputs_for_camera_ray_bundle(bundle)
+                    if o is None:
+                        raise RuntimeError("Render thread did not return any outputs")
+                    outs.append(o)
+                out = {k: torch.stack([o[k] for o in outs]) for k in ("rgb", "depth")}
+        finally:
+            graph.train()
+        if out is None:
+            raise RuntimeError("Render thread did not return any outputs")
+        return out
+
+    def render_views(self, graph, cameras, combine_shape_with_depth: Optional[bool] = None) -> Tuple[Tensor, Tensor, Tensor]:
         """render_camera for V cameras at once (K1 + K2/K3, no host sync): rgb [V,H,W,3] fp32, mask [V,H,W,1] bool,
         condition [V,H,W,1] fp32."""
-        if self.combine_shape_with_depth:
-            raise NotImplementedError("combine_shape_with_depth (datasetgenerator.py:794-807) conditions on pyrender's SHADED "
-                                      "colour image, which the depth rasteriser does not produce")
+        combine = self.combine_shape_with_depth if combine_shape_with_depth is None else combine_shape_with_depth
         if self.masking_mode == "shape" and self.renderer is None:
             raise ValueError("Renderer is None but masking mode is shape")
         cam = as_camera_batch(cameras)
-        graph.eval()
-        out = graph.render_cameras(cam)
-        graph.train()
-        if out is None:
-            raise RuntimeError("Render thread did not return any outputs")
+        out = self._nerf_outputs(graph, cameras, cam)
+        rgb, depth = out["rgb"].to(torch.float32).contiguous(), out["depth"].to(torch.float32).contiguous()
         if self.masking_mode == "shape":      # datasetgenerator.py:711-757, proxy depth from the CUDA rasteriser
-            mask, cond, _ = ops.mask_condition_shape(self.renderer.render_depths(cam), out["depth"], self._mask_options())
-            return out["rgb"], mask.bool(), cond
-        c2w, intr = c2w_intr(cam, graph.device)
-        mask, cond, _ = ops.mask_condition(c2w, intr, out["depth"], self._mask_options())
-        return out["rgb"], mask.bool(), cond
+            mask, cond, _ = ops.mask_condition_shape(self.renderer.render_depths(cam), depth, self._mask_options())
+            return rgb, mask.bool(), cond
+        c2w, intr = c2w_intr(cam, depth.device)
+        if combine:                           # datasetgenerator.py:794-807
+            if self.renderer is None:
+                raise ValueError("Renderer is None but masking mode is shape")
+            shape_depth = self.renderer.render_depths(cam)
+            mask, cond, _ = ops.mask_condition_combined(c2w, intr, depth, shape_depth, self.renderer.render_colors(shape_depth),
+                                                        self._mask_options())
+        else:
+            mask, cond, _ = ops.mask_condition(c2w, intr, depth, self._mask_options())
+        return rgb, mask.bool(), cond
 
     # ------------------------------------------------------------------ reference API
     def render_camera(self, graph, camera, with_mask: bool = True, with_condition: bool = True,
@@ -110,13 +177,8 @@ class DatasetGenerator:
         """datasetgenerator.py:677-820 incl. its early-return arity quirk (4-tuples when a part is skipped)."""
         cam = as_camera_batch(camera)
         if not with_mask:
-            graph.eval()
-            out = graph.render_cameras(cam)
-            graph.train()
-            return out["rgb"][0], None, None, None
-        if combine_shape_with_depth:
-            raise NotImplementedError("combine_shape_with_depth needs pyrender's shaded colour image (datasetgenerator.py:794-807)")
-        rgb, mask, cond = self.render_views(graph, cam)
+            return self._nerf_outputs(graph, camera, cam)["rgb"][0], None, None, None
+        rgb, mask, cond = self.render_views(graph, camera, combine_shape_with_depth=combine_shape_with_depth)
         if not with_condition:
             return rgb[0], mask[0], None, None
         return rgb[0], mask[0], cond[0]
@@ -132,7 +194,7 @@ class DatasetGenerator:
         image_sheet = torch.ones((lay.height, lay.width, 3), dtype=torch.float32, device=dev)
         mask_sheet = torch.zeros((lay.height, lay.width, 1), dtype=torch.float32, device=dev)
         cond_sheet = torch.zeros((lay.height, lay.width, 1), dtype=torch.float32, device=dev)
-        rgb, mask, cond = self.render_views(graph, cam)
+        rgb, mask, cond = self.render_views(graph, cameras)
         ops.sheet_paste(rgb, image_sheet, lay, 0)
         ops.sheet_paste(mask, mask_sheet, lay, 0, threshold=0.5)
         ops.sheet_paste(cond, cond_sheet, lay, 0)
@@ -157,7 +219,10 @@ class DatasetGenerator:
         if filename is not None:   # original-dataset cameras use the photo for the last tile (:628-630)
             from PIL import Image
             import numpy as np
-            render = torch.from_numpy(np.array(Image.open(filename), dtype="float32") / 255.0).to(graph.device)
+            photo = Image.open(filename)
+            if photo.mode == "RGBA":       # image_to_tensor (utils/image_tensor_converter.py:46-47)
+                photo = photo.convert("RGB")
+            render = torch.from_numpy(np.array(photo, dtype="float32") / 255.0).to(graph.device)
         lay = self._layout(scaled_image_width, scaled_image_height)
         last = self.rows * self.cols - 1
         th, tw, b = scaled_image_height, scaled_image_width, self.border_width_between_images

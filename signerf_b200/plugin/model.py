@@ -11,7 +11,7 @@ from torch import Tensor
 from .. import ops
 from ..field import HashGridParams, LinearParams, NerfactoFieldB200
 from ..synthetic import hash_scalings
-from .base import CameraBatch, c2w_intr
+from .base import CameraBatch, as_camera_batch, c2w_intr
 
 
 class FusedNerfactoGraph:
@@ -36,20 +36,29 @@ class FusedNerfactoGraph:
     def render_cameras(self, cam: CameraBatch) -> Dict[str, Tensor]:
         """All views of `cam` in one launch: rgb [V,H,W,3], depth [V,H,W,1], accumulation [V,H,W,1]."""
         c2w, intr = c2w_intr(cam, self.device)
-        rgb, depth, acc = ops.render_views(self.field, c2w, intr, cam.height, cam.width, self.render_opts, want_acc=True)
+        h, w = cam.image_size()
+        rgb, depth, acc = ops.render_views(self.field, c2w, intr, h, w, self.render_opts, want_acc=True)
         return {"rgb": rgb, "depth": depth, "accumulation": acc}
 
     def get_outputs_for_camera_ray_bundle(self, camera_ray_bundle) -> Dict[str, Tensor]:
-        """nerfstudio passes a RayBundle; the fused path re-derives the rays from the camera the bundle was generated
-        from (`bundle.camera` attached by plugin.DatasetGenerator.render_camera), exactly as generate_rays does."""
-        cam = getattr(camera_ray_bundle, "camera", camera_ray_bundle)
-        out = self.render_cameras(cam)
+        """nerfstudio's `Model.get_outputs_for_camera_ray_bundle` (the call at datasetgenerator.py:694): a RayBundle with
+        `origins` / `directions` [H,W,3] (what `camera.generate_rays(camera_indices=0)` returns) -> {"rgb" [H,W,3],
+        "depth" [H,W,1], "accumulation" [H,W,1]} through `sgn_render_rays`.  A CameraBatch / Cameras passed instead of a
+        bundle is rendered from its pose (rays generated inside the kernel)."""
+        if hasattr(camera_ray_bundle, "origins") and hasattr(camera_ray_bundle, "directions"):
+            if getattr(camera_ray_bundle, "nears", None) is not None or getattr(camera_ray_bundle, "fars", None) is not None:
+                raise NotImplementedError("per-ray nears / fars (aabb_box colliders) are not supported: NearFarCollider planes only")
+            rgb, depth, acc = ops.render_rays(self.field, camera_ray_bundle.origins.to(self.device),
+                                              camera_ray_bundle.directions.to(self.device), self.render_opts, want_acc=True)
+            return {"rgb": rgb, "depth": depth, "accumulation": acc}
+        out = self.render_cameras(as_camera_batch(camera_ray_bundle))
         return {k: v[0] for k, v in out.items()}
 
     # nerfacto checkpoint -> field (names per SURVEY §8c; torch-fallback `implementation="torch"` checkpoints)
     @classmethod
     def from_state_dict(cls, sd: Mapping[str, Tensor], device="cuda", num_train_data: Optional[int] = None,
-                        average_init_density: float = 0.01, render_opts: Optional[ops.RenderOptions] = None):
+                        average_init_density: float = 0.01, render_opts: Optional[ops.RenderOptions] = None,
+                        near_plane: float = 0.05, far_plane: float = 1000.0, allow_flat: bool = False):
         # nerfstudio is not installable here, so the parameter names cannot be checked against a real 1.0.2 checkpoint:
         # both layouts the torch-fallback modules have used are accepted (MLPWithHashEncoding: `mlp_base.encoding` /
         # `mlp_base.mlp`; older split modules: `mlp_base_grid` / `mlp_base_mlp`, `encoding` / `mlp_base`).
@@ -86,7 +95,20 @@ class FusedNerfactoGraph:
                 break   # load_model_with_proposal_weights=False drops the proposal networks (signerf_pipeline.py:113-118)
             pg.append(grid(enc, 5, max_res))
             pm.append(mlp(pick(pre + ".mlp_base.mlp", pre + ".mlp_base.1", pre + ".mlp_base"), 2))
+        if len(pg) != 2 and render_opts is None and not allow_flat:
+            # With load_model_with_proposal_weights=False the reference still samples 256 -> 96 -> 48 through FRESHLY
+            # initialised proposal networks (signerf_pipeline.py:113-120, strict=False): flat sampling would give other
+            # depths / masks without a word.  The caller either hands over the model's live proposal networks or asks
+            # for flat sampling explicitly.
+            raise KeyError("proposal_networks.{0,1}.* missing from the state_dict: pass the live model's state_dict (its "
+                           "re-initialised proposal networks included), or allow_flat=True / explicit render_opts")
+        if "field.embedding_appearance.embedding.weight" not in sd:
+            import warnings
+            warnings.warn("appearance embedding missing from the state_dict: using the mean of a seeded N(0,1) table with "
+                          f"{num_train_data or 30} rows; the reference's fresh nn.Embedding has its own random rows")
         fld = NerfactoFieldB200(g, base, head, app, average_init_density, pg, pm)
-        if render_opts is None and not pg:
-            render_opts = ops.RenderOptions(mode="flat", num_samples=48)
+        if render_opts is None:
+            render_opts = (ops.RenderOptions(mode="cascade", num_samples=48, num_prop_samples=(256, 96), near_plane=near_plane,
+                                             far_plane=far_plane) if len(pg) == 2
+                           else ops.RenderOptions(mode="flat", num_samples=48, near_plane=near_plane, far_plane=far_plane))
         return cls(fld, render_opts)

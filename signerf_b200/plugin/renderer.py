@@ -1,8 +1,13 @@
 """Mirror of reference signerf/renderer/renderer.py (proxy-mesh depth through pyrender / EGL): same config fields,
 attributes, `setup()` / `render_camera()` signatures and error behaviour, with the depth coming from the CUDA z-buffer
 rasteriser `sgn_rasterize_depth` instead of an OpenGL context — no trimesh / pyrender / EGL needed,
-no GPU -> CPU -> GPU copy.  The colour image is the flat object colour over pyrender's white background (the reference
-only consumes it with combine_shape_with_depth, which needs pyrender's shaded colour and stays unsupported)."""
+no GPU -> CPU -> GPU copy.  The colour image (only consumed by combine_shape_with_depth, datasetgenerator.py:794-807) is
+what pyrender produces for this scene: ONE mesh lit by ambient light 1.0 and nothing else (renderer.py:129-130), i.e. the
+material's flat base colour on covered pixels over pyrender's default white background.  `RendererConfig.color` is never
+handed to pyrender by the reference (renderer.py:55 stores it, nothing reads it); the material is whatever trimesh finds
+in the OBJ — for the shipped models/bunny.obj the `bunny1.mtl` it names does not exist, so pyrender's default material
+for meshes without one applies ([EXT] pyrender `Mesh.from_trimesh`: baseColorFactor 0.3 -> 77/255; parity unpinned,
+`Renderer.material_base_color` is the knob)."""
 from __future__ import annotations
 
 import math
@@ -61,6 +66,7 @@ class Renderer:
         self.config, self.device = config, device
         self.position, self.rotation, self.scale = config.position, config.rotation, config.scale
         self.color, self.object_path = config.color, config.object_path
+        self.material_base_color = [0.3, 0.3, 0.3]   # [EXT] pyrender's default material (see the module docstring)
         self.scene = None          # (vertices, faces, model) once setup() succeeded
         self.mesh = None
 
@@ -105,11 +111,15 @@ class Renderer:
         cam = as_camera_batch(cameras)
         c2w, intr = c2w_intr(cam, self.device)
         v, f, model = self.scene
-        return ops.rasterize_depth(v, f, model, c2w, intr, cam.height, cam.width, znear=0.0001, zfar=10.0)
+        h, w = cam.image_size()
+        return ops.rasterize_depth(v, f, model, c2w, intr, h, w, znear=0.0001, zfar=10.0)
+
+    def render_colors(self, depths: Tensor) -> Tensor:
+        """Colour images uint8 [V,H,W,3] that go with `render_depths`' output (flat ambient shading, white background)."""
+        fg = tuple(int(math.floor(min(max(float(c), 0.0), 1.0) * 255.0 + 0.5)) for c in self.material_base_color[:3])
+        return ops.shape_color_u8(depths, fg, (255, 255, 255))
 
     def render_camera(self, camera) -> Tuple[Tensor, Tensor]:
         """-> (color uint8 [H,W,3], depth fp32 [H,W,1]) on the device, as renderer.py:149-196."""
-        depth = self.render_depths(camera)[0]
-        rgb = torch.tensor([int(round(255 * float(c))) for c in self.color[:3]], dtype=torch.uint8, device=depth.device)
-        color = torch.where(depth > 0, rgb.view(1, 1, 3), torch.full((1, 1, 3), 255, dtype=torch.uint8, device=depth.device))
-        return color, depth
+        depth = self.render_depths(camera)
+        return self.render_colors(depth)[0], depth[0]

@@ -49,7 +49,8 @@ def test_writer_layout_schema_and_read_back(tmp_path):
             "mask_scaled": torch.rand(4, 5, 1, generator=g) > 0.5, "condition_scaled": torch.rand(4, 5, 1, generator=g)}
     c2w = torch.tensor([[1.0, 0, 0, 0.1], [0, 1, 0, 0.2], [0, 0, 1, 0.3]])
     T = wr.save_generated_images(0, imgs, c2w, 10.0, 11.0, 5.0, 4.0, 10, 8, T)
-    T = wr.save_generated_images(1, {"edited": imgs["edited"], "render": imgs["render"]}, c2w, 10.0, 11.0, 5.0, 4.0, 10, 8, T, is_original=True)
+    T = wr.save_generated_images(1, {"edited": imgs["edited"], "render": imgs["render"], "edited_scaled": imgs["edited_scaled"]},
+                                 c2w, 10.0, 11.0, 5.0, 4.0, 10, 8, T, is_original=True)
     T["reference_indices"] = [0]
     T["generated_indices"] = [1]
     wr.write_transforms(T)
@@ -71,6 +72,9 @@ def test_writer_layout_schema_and_read_back(tmp_path):
     # DataparserOutputs contract (signerf_dataparser.py:210-228, :301-312): poses as stored, transform / scale from the file
     dp = IO.parse_generated_dataset(tmp_path / "exp", scene_scale=2.0, downscale_factor=2)
     assert len(dp.image_filenames) == 2 and dp.mask_filenames is None            # masks only for merged datasets
+    # _get_fname (signerf_dataparser.py:330-357): with downscale_factor 2 the files are the down-sampled copies
+    assert [f.relative_to(tmp_path / "exp").as_posix() for f in dp.image_filenames] == ["images_2/image_0.png", "images_2/image_1.png"]
+    assert tuple(Image.open(dp.image_filenames[0]).size) == (5, 4)               # == the rescaled camera size below
     assert dp.dataparser_scale == 0.5 and torch.equal(dp.dataparser_transform, torch.eye(4)[:3])
     assert torch.equal(dp.scene_box, torch.tensor([[-2.0, -2.0, -2.0], [2.0, 2.0, 2.0]]))
     assert torch.allclose(dp.cameras.camera_to_worlds[0], c2w) and dp.cameras.fx.tolist() == [5.0, 5.0]
@@ -82,6 +86,9 @@ def test_writer_layout_schema_and_read_back(tmp_path):
     dp = IO.parse_generated_dataset(tmp_path / "exp")
     assert [m.name for m in dp.mask_filenames] == ["white.png", "mask_1.png"]
     assert np.array(Image.open(tmp_path / "exp" / "masks" / "white.png")).min() == 255
+    dp2 = IO.parse_generated_dataset(tmp_path / "exp", downscale_factor=2)       # masks follow the images into masks_2/
+    assert [m.relative_to(tmp_path / "exp").as_posix() for m in dp2.mask_filenames] == ["masks_2/white.png", "masks_2/mask_1.png"]
+    assert (tmp_path / "exp" / "masks_2" / "white.png").exists()
     os.remove(tmp_path / "exp" / "images" / "image_1.png")               # a frame whose image is gone is skipped (:104-107)
     assert IO.read_transforms(tmp_path / "exp" / "transforms.json")["num_skipped"] == 1
     assert len(IO.parse_generated_dataset(tmp_path / "exp").image_filenames) == 1

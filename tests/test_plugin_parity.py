@@ -9,7 +9,7 @@ import signerf_b200.plugin as P
 from oracle import nerfacto_ref as R
 from oracle import sheet_ref as S
 from signerf_b200 import ops
-from tests.helpers import field_from_oracle, rel_l2, ring_cameras
+from tests.helpers import depth_agreement, field_from_oracle, rel_l2, ring_cameras
 
 pytestmark = pytest.mark.gpu
 
@@ -116,9 +116,161 @@ def test_graph_from_nerfacto_state_dict(style):
     cam = P.CameraBatch(c2w, 24.0, 24.0, 12.0, 8.0, 24, 16)
     o1, o2 = graph.render_cameras(cam), direct.render_cameras(cam)
     assert torch.equal(o1["rgb"], o2["rgb"]) and torch.equal(o1["depth"], o2["depth"])
-    # proposal networks dropped (load_model_with_proposal_weights=False): flat sampling of the main field
+    # proposal networks dropped from the checkpoint (load_model_with_proposal_weights=False): the reference keeps
+    # sampling through fresh proposal networks, so flat sampling has to be asked for, it is never a silent switch
     sd_np = {k: v for k, v in sd.items() if not k.startswith("proposal_networks")}
-    assert P.FusedNerfactoGraph.from_state_dict(sd_np).render_opts.mode == "flat"
+    with pytest.raises(KeyError, match="proposal_networks"):
+        P.FusedNerfactoGraph.from_state_dict(sd_np)
+    assert P.FusedNerfactoGraph.from_state_dict(sd_np, allow_flat=True).render_opts.mode == "flat"
+
+
+class _ContractOnlyModel(torch.nn.Module):
+    """What the reference's `graph` promises and nothing more (datasetgenerator.py:691-701): an nn.Module with nerfacto's
+    parameters, `render_aabb`, `device`, `config`, and a `get_outputs_for_camera_ray_bundle` that must never be needed."""
+
+    def __init__(self, m):
+        super().__init__()
+        self.field, self.proposal_networks = m.field, m.proposal_networks
+        self.render_aabb, self.num_train_data = None, 30
+        self.config = type("Cfg", (), {"average_init_density": m.field.average_init_density, "near_plane": 0.05, "far_plane": 1000.0})()
+        self.calls = 0
+
+    @property
+    def device(self):
+        return torch.device("cuda")
+
+    def state_dict(self, *a, **k):      # nerfstudio 1.0.2 parameter names (MLPWithHashEncoding layout)
+        f, sd = self.field, {}
+        sd["field.mlp_base.encoding.hash_table"] = f.encoding.hash_table
+        sd["field.embedding_appearance.embedding.weight"] = f.embedding_appearance.weight
+        for i, l in enumerate(f.mlp_base.layers):
+            sd[f"field.mlp_base.mlp.layers.{i}.weight"], sd[f"field.mlp_base.mlp.layers.{i}.bias"] = l.weight, l.bias
+        for i, l in enumerate(f.mlp_head.layers):
+            sd[f"field.mlp_head.layers.{i}.weight"], sd[f"field.mlp_head.layers.{i}.bias"] = l.weight, l.bias
+        for j, pn in enumerate(self.proposal_networks):
+            sd[f"proposal_networks.{j}.mlp_base.encoding.hash_table"] = pn.encoding.hash_table
+            for i, l in enumerate(pn.mlp.layers):
+                sd[f"proposal_networks.{j}.mlp_base.mlp.layers.{i}.weight"] = l.weight
+                sd[f"proposal_networks.{j}.mlp_base.mlp.layers.{i}.bias"] = l.bias
+        return sd
+
+    def get_outputs_for_camera_ray_bundle(self, bundle):
+        self.calls += 1
+        raise AssertionError("the fused renderer should have been attached behind this call")
+
+
+def test_reference_contract_graph_gets_the_fused_renderer_attached():
+    """A graph that only offers the reference contract (no `render_cameras`): DatasetGenerator packs its nerfacto
+    parameters into the fused renderer (once per weight version) and renders through it; results equal the direct path."""
+    m = R.make_model(0, dense=True, table_scale=0.5, density_gain=20.0)
+    model = _ContractOnlyModel(m)
+    gen = _generator(2, 2, 16, 24, 1)
+    c2w, _ = ring_cameras(3, 24, 16)
+    cams = P.CameraBatch(c2w, 24.0, 24.0, 12.0, 8.0, 24, 16)
+    rgb, mask, cond = gen.render_views(model, cams)
+    direct = P.FusedNerfactoGraph(field_from_oracle(m))
+    ref_rgb, ref_mask, ref_cond = gen.render_views(direct, cams)
+    assert model.calls == 0 and model.training                     # eval() for the render, train() afterwards (:693-695)
+    assert torch.equal(rgb, ref_rgb) and torch.equal(mask, ref_mask) and torch.equal(cond, ref_cond)
+    fused = gen._fused_cache[2]
+    gen.render_camera(model, cams[1])
+    assert gen._fused_cache[2] is fused                            # same weights: no re-pack
+    with torch.no_grad():
+        m.field.mlp_head.layers[2].bias.add_(0.25)                 # a fine-tune step changes the weights in place
+    rgb2, _, _ = gen.render_views(model, cams)
+    assert gen._fused_cache[2] is not fused and not torch.equal(rgb2, rgb)
+
+
+def test_get_outputs_for_camera_ray_bundle_on_an_explicit_bundle():
+    """plugin.FusedNerfactoGraph.get_outputs_for_camera_ray_bundle(RayBundle): origins / directions [H,W,3] as
+    `camera.generate_rays(camera_indices=0)` returns them -> same images as rendering from the camera pose (rays derived
+    inside the kernel), for both samplers; and against the oracle on the oracle's own rays."""
+    m = R.make_model(0, dense=True, table_scale=0.5, density_gain=20.0)
+    fld = field_from_oracle(m)
+    H, W = 20, 28
+    c2w, intr = ring_cameras(2, W, H)
+    cam = P.CameraBatch(c2w[1:2], float(W), float(W), W / 2, H / 2, W, H)
+    rays = R.generate_rays(c2w[1], *intr[1].tolist(), W, H)
+    bundle = type("RayBundle", (), {"origins": rays.origins.view(H, W, 3), "directions": rays.directions.view(H, W, 3),
+                                    "nears": None, "fars": None})()
+    for opts in (ops.RenderOptions(mode="flat", num_samples=24, mlp_mode=ops.MLP_FP32),
+                 ops.RenderOptions(mode="cascade", num_samples=48, num_prop_samples=(256, 96), mlp_mode=ops.MLP_FP32)):
+        graph = P.FusedNerfactoGraph(fld, opts)
+        out = graph.get_outputs_for_camera_ray_bundle(bundle)
+        assert tuple(out["rgb"].shape) == (H, W, 3) and tuple(out["depth"].shape) == (H, W, 1)
+        ref = R.render_view(m, c2w[1], *intr[1].tolist(), W, H, opts.mode, opts.num_samples if opts.mode == "flat" else None)
+        assert rel_l2(out["rgb"], ref["rgb"]) < 1e-3
+        moved, err = depth_agreement(out["depth"], ref["depth"], same_bin_rtol=1e-6 if opts.mode == "flat" else 1e-3)
+        assert moved <= 5e-3 and err < 2e-4
+        from_pose = graph.render_cameras(cam)
+        # the oracle's directions are within 2e-7 of the kernel's own (different division order): images agree to rounding
+        assert rel_l2(out["rgb"], from_pose["rgb"][0]) < 1e-4
+        assert tuple(graph.get_outputs_for_camera_ray_bundle(cam)["rgb"].shape) == (H, W, 3)       # a camera works too
+
+
+def test_combine_shape_with_depth_matches_restatement():
+    """aabb masking with combine_shape_with_depth=True (datasetgenerator.py:794-807): where the proxy mesh is in front of
+    the NeRF surface the condition is the mesh colour image's R channel / 255."""
+    import numpy as np
+    from oracle import mesh_ref as M
+    from oracle import sheet_ref as S
+    H, W = 48, 40
+    m = R.make_model(0, dense=True, table_scale=0.5, density_gain=20.0)
+    graph = P.FusedNerfactoGraph(field_from_oracle(m), ops.RenderOptions(mode="flat", num_samples=24, mlp_mode=ops.MLP_FP32))
+    gen = _generator(2, 2, H, W, 1)
+    gen.aabb = torch.tensor([[-0.3, -0.3, -0.3], [0.3, 0.3, 0.3]], device="cuda")
+    gen.mask_dialation = (7, 7)
+    v, f = M.uv_sphere(1.0, 10, 16)
+    c2w, intr = ring_cameras(2, W, H)
+    pos = (0.8 * c2w[0, :3, 3]).tolist()
+    gen.renderer.scale, gen.renderer.position = [0.002, 0.002, 0.002], pos
+    gen.renderer.set_mesh(v, f)
+    gen.renderer.setup()
+    cam = P.CameraBatch(c2w[:1], float(W), float(W), W / 2, H / 2, W, H)
+    rgb, mask, cond = gen.render_camera(graph, cam, combine_shape_with_depth=True)
+    _, mask0, cond0 = gen.render_camera(graph, cam)
+    color, sdepth = gen.renderer.render_camera(cam)
+    assert color.dtype == torch.uint8 and tuple(color.shape) == (H, W, 3)
+    covered = sdepth[..., 0] > 0
+    assert bool(covered.any()) and set(color[covered].unique().tolist()) == {77} and set(color[~covered].unique().tolist()) == {255}
+    # restatement of :794-807 on the kernel's own depths
+    nerf = graph.render_cameras(cam)["depth"][0].cpu()
+    rays = R.generate_rays(c2w[0], *intr[0].tolist(), W, H)
+    _, _, st = S.render_camera_aabb(rays.origins.view(H, W, 3), rays.directions.view(H, W, 3), nerf, gen.aabb.cpu(),
+                                    mask_dilation=(7, 7))
+    sd = sdepth.cpu()
+    vis = (sd < nerf) & (sd > 0)
+    nerf_n = (nerf - st["min"]) / (st["max"] - st["min"])
+    ref = 1 - torch.clamp(vis * (color[..., :1].cpu().float() / 255.0) + (~vis) * nerf_n, 0, 1)
+    assert bool(vis.any()) and torch.equal(mask, mask0)
+    assert torch.allclose(cond.cpu(), ref, atol=1e-6) and not torch.equal(cond, cond0)
+
+
+def test_per_camera_intrinsics_and_sizes_survive_indexing():
+    """plugin.CameraBatch keeps per-camera intrinsics (original datasets, datasetgenerator.py:331-334): cameras[i]
+    renders with ITS focal length / principal point / size, not camera 0's."""
+    m = R.make_model(0, dense=True, table_scale=0.5, density_gain=20.0)
+    graph = P.FusedNerfactoGraph(field_from_oracle(m), ops.RenderOptions(mode="flat", num_samples=16))
+    c2w, _ = ring_cameras(3, 24, 16)
+    cams = type("Cameras", (), {})()                 # nerfstudio Cameras attribute layout: [N,1] tensors
+    cams.camera_to_worlds = c2w
+    cams.fx, cams.fy = torch.tensor([[24.0], [30.0], [18.0]]), torch.tensor([[24.0], [31.0], [18.0]])
+    cams.cx, cams.cy = torch.tensor([[12.0], [11.0], [16.0]]), torch.tensor([[8.0], [7.5], [12.0]])
+    cams.width, cams.height = torch.tensor([[24], [24], [32]]), torch.tensor([[16], [16], [24]])
+    batch = P.base.as_camera_batch(cams)
+    assert batch.size_groups() == [((16, 24), [0, 1]), ((24, 32), [2])]
+    with pytest.raises(ValueError, match="different image sizes"):
+        graph.render_cameras(batch)
+    for i in range(3):
+        one = batch[i]
+        h, w = one.image_size()
+        assert (one.fx, one.fy, one.cx, one.cy, w, h) == (float(cams.fx[i]), float(cams.fy[i]), float(cams.cx[i]), float(cams.cy[i]),
+                                                          int(cams.width[i]), int(cams.height[i]))
+        out = graph.render_cameras(one)
+        ref = graph.render_cameras(P.CameraBatch(c2w[i:i + 1], one.fx, one.fy, one.cx, one.cy, w, h))
+        assert tuple(out["rgb"].shape) == (1, h, w, 3) and torch.equal(out["rgb"], ref["rgb"])
+    two = graph.render_cameras(batch[:2])             # same size, different intrinsics: one launch, per-view intr
+    assert torch.equal(two["rgb"][1], graph.render_cameras(batch[1])["rgb"][0])
 
 
 def test_render_camera_shape_mode_matches_oracle():

@@ -218,3 +218,24 @@ def test_full_size_properties_c2(fields):
     assert rel_l2(rgb_c[0], ref["rgb"]) < TOL
     moved, err = depth_agreement(depth_c[0], ref["depth"])
     assert moved <= MAX_MOVED_FP16 and err < 1e-6, (moved, err)
+
+
+@pytest.mark.parametrize("name", ["dense", "varied"])
+@pytest.mark.parametrize("crop", [(200, 136), (352, 300)])
+def test_c2_plain_depth_rel_l2_fp16_path(fields, name, crop):
+    """north_star tolerance stated on DEPTH itself, not on bin flips: plain relative L2 <= 1e-3 on 64x64 crops of the C2
+    view (512x512 camera, 128 samples/ray) rendered by the product's default fp16-MMA path, against the fp32 oracle."""
+    m, f = fields[name]
+    c2w, intr = ring_cameras(16, 512, 512)
+    x0, y0 = crop
+    intr_c = intr[:1].clone()
+    intr_c[0, 2] -= x0
+    intr_c[0, 3] -= y0
+    opts = ops.RenderOptions(mode="flat", num_samples=128)
+    rgb_c, depth_c = ops.render_views(f, c2w[:1].cuda(), intr_c.cuda(), 64, 64, opts)
+    ref = R.render_view(m, c2w[0], float(intr_c[0, 0]), float(intr_c[0, 1]), float(intr_c[0, 2]), float(intr_c[0, 3]), 64, 64, "flat", 128)
+    e_d, e_rgb = rel_l2(depth_c[0], ref["depth"]), rel_l2(rgb_c[0], ref["rgb"])
+    moved, _ = depth_agreement(depth_c[0], ref["depth"])
+    print(f"C2 crop {crop} field {name}: depth rel-L2 {e_d:.2e} ({moved:.2%} of rays in another bin), rgb rel-L2 {e_rgb:.2e}")
+    assert e_rgb < TOL
+    assert e_d < TOL

@@ -198,10 +198,13 @@ def test_full_width_blocks_match_oracle(level, hw):
     assert e_rb < TOL_ACT and e_st < TOL_ACT
 
 
-def test_full_sdxl_unet_end_to_end_error_at_real_depth():
-    """The real thing once: SDXL-base UNet (2.57 B parameters, 70 transformer blocks) on a 32x32 latent, CUDA path vs the
-    fp32 oracle on the same fp16-representable random weights, end to end (no teacher forcing).  Measured on B200: worst
-    sampled activation 6.9e-4, eps 5.4e-4 relative L2 -> asserted at the north_star tolerance 1e-3."""
+@pytest.mark.parametrize("hw", [32, 128])
+def test_full_sdxl_unet_end_to_end_error_at_real_depth(hw):
+    """The real thing once: SDXL-base UNet (2.57 B parameters, 70 transformer blocks) on a 32x32 and a 128x128 latent
+    (self-attention over 4 096 tokens at 640 channels and 1 024 at 1 280: 32 / 8 key tiles per row, so the lazy rescale and
+    the fp16 P accumulation run over many tiles), CUDA path vs the fp32 oracle on the same fp16-representable random
+    weights, end to end (no teacher forcing).  Measured on B200 at 32^2: worst sampled activation 6.9e-4, eps 5.4e-4
+    relative L2 -> asserted at the north_star tolerance 1e-3."""
     cfg = R.UNetConfig()
     torch.manual_seed(0)
     with torch.device("cuda"):
@@ -212,7 +215,7 @@ def test_full_sdxl_unet_end_to_end_error_at_real_depth():
             prm.copy_(prm.half().float())
     un = U.SDXLUNetB200(U.UNetConfig(), ref.state_dict(), "cuda")
     g = torch.Generator().manual_seed(21)
-    x = torch.randn(2, 4, 32, 32, generator=g).cuda()
+    x = torch.randn(2, 4, hw, hw, generator=g).cuda()
     t = torch.tensor([701.5, 701.5]).cuda()
     ctx = torch.randn(2, 77, cfg.context_dim, generator=g).cuda()
     y = torch.randn(2, cfg.adm_in_channels, generator=g).cuda()
@@ -223,5 +226,5 @@ def test_full_sdxl_unet_end_to_end_error_at_real_depth():
     errs = {k: rel_l2(taps[k], taps_ref[k]) for k in ("input_blocks.4", "input_blocks.8", "middle_block", "output_blocks.2",
                                                       "output_blocks.5", "output_blocks.8")}
     e_out = rel_l2(out, out_ref)
-    print("full SDXL UNet end-to-end:", {k: f"{v:.1e}" for k, v in errs.items()}, f"eps {e_out:.1e}")
+    print(f"full SDXL UNet end-to-end (latent {hw}^2):", {k: f"{v:.1e}" for k, v in errs.items()}, f"eps {e_out:.1e}")
     assert max(errs.values()) < TOL_ACT and e_out < TOL_ACT
