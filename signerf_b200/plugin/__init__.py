@@ -12,4 +12,6 @@ from .base import CameraBatch  # noqa: F401
 from .datasetgenerator import DatasetGenerator, DatasetGeneratorConfig  # noqa: F401
 from .diffuser import Diffuser, DiffuserConfig, InProcessSDXL  # noqa: F401
 from .model import FusedNerfactoGraph  # noqa: F401
+from .pipeline import SIGNeRFPipeline, SIGNeRFPipelineConfig  # noqa: F401
 from .renderer import Renderer, RendererConfig  # noqa: F401
+from . import base  # noqa: F401

@@ -183,6 +183,48 @@ class DatasetGenerator:
             return rgb[0], mask[0], None, None
         return rgb[0], mask[0], cond[0]
 
+    # ------------------------------------------------------------------ multi-GPU (one process per GPU, torch.distributed)
+    @staticmethod
+    def _dist() -> Tuple[int, int]:
+        """(rank, world) of the default process group; (0, 1) when the caller did not set one up."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+        return 0, 1
+
+    def _render_reference_views(self, graph, cameras, cam: CameraBatch) -> Tuple[Tensor, Tensor, Tensor]:
+        """The rows*cols-1 reference views (hot loop #2, datasetgenerator.py:517-519).  With `world` ranks the views are
+        independent units: rank r renders views v = r (mod world) and ONE all-gather of the packed tiles
+        (rgb | condition | mask, 5 floats per pixel) hands every rank the full set - bit-identical to rendering them all
+        on one GPU (pure partition, no reduction)."""
+        rank, world = self._dist()
+        if world == 1 or self._fused_graph(graph) is None:
+            return self.render_views(graph, cameras)
+        from .. import sharding
+        n = len(cam)
+        mine = sharding.views_of_rank(n, world, rank)
+        h, w = cam.image_size()
+        if mine:
+            rgb, mask, cond = self.render_views(graph, cam[mine])
+            local = torch.cat([rgb, cond, mask.to(torch.float32)], dim=-1).contiguous()
+        else:
+            local = torch.empty((0, h, w, 5), dtype=torch.float32, device=graph.device)
+        full = sharding.all_gather_views(local, n, world, rank)
+        return full[..., 0:3].contiguous(), full[..., 4:5] > 0.5, full[..., 3:4].contiguous()
+
+    def _diffuse_reference_sheet(self, image_sheet: Tensor, mask_sheet: Tensor, cond_sheet: Tensor, dev) -> Tensor:
+        """The ONE reference-sheet diffusion (datasetgenerator.py:558).  It does not shard (attention spans all tiles):
+        rank 0 runs it and broadcasts the edited sheet, so every rank continues from the same pixels whatever the
+        backend (a remote or non-deterministic diffuser is called once, as in the reference)."""
+        rank, world = self._dist()
+        if world == 1:
+            return self.diffuser.diffuse(image_sheet, image_sheet, mask_sheet, cond_sheet).to(dev)
+        import torch.distributed as dist
+        edited = (self.diffuser.diffuse(image_sheet, image_sheet, mask_sheet, cond_sheet).to(dev, torch.float32).contiguous()
+                  if rank == 0 else torch.empty_like(image_sheet))
+        dist.broadcast(edited, src=0)
+        return edited
+
     def generate_reference_sheet(self, graph, cameras, scaled_image_width: int, scaled_image_height: int):
         """datasetgenerator.py:470-593 -> (image_sheet, mask_sheet, condition_sheet, edited_sheet, references)."""
         cam = as_camera_batch(cameras)
@@ -194,11 +236,11 @@ class DatasetGenerator:
         image_sheet = torch.ones((lay.height, lay.width, 3), dtype=torch.float32, device=dev)
         mask_sheet = torch.zeros((lay.height, lay.width, 1), dtype=torch.float32, device=dev)
         cond_sheet = torch.zeros((lay.height, lay.width, 1), dtype=torch.float32, device=dev)
-        rgb, mask, cond = self.render_views(graph, cameras)
+        rgb, mask, cond = self._render_reference_views(graph, cameras, cam)
         ops.sheet_paste(rgb, image_sheet, lay, 0)
         ops.sheet_paste(mask, mask_sheet, lay, 0, threshold=0.5)
         ops.sheet_paste(cond, cond_sheet, lay, 0)
-        edited = self.diffuser.diffuse(image_sheet, image_sheet, mask_sheet, cond_sheet).to(dev)
+        edited = self._diffuse_reference_sheet(image_sheet, mask_sheet, cond_sheet, dev)
         edited_sheet = ops.blend_masked(edited, image_sheet, mask_sheet)
         references: List[Dict[str, Tensor]] = []
         th, tw, b = scaled_image_height, scaled_image_width, self.border_width_between_images
@@ -290,28 +332,42 @@ class DatasetGenerator:
         if synthetic_camera_to_worlds is not None:
             cameras = batch(synthetic_camera_to_worlds)
             original_filenames = [None] * synthetic_camera_to_worlds.shape[0]
+        rank, world = self._dist()
         transforms = DatasetWriter.new_transforms(self.is_synthetic, merge_with_original_dataset, self.original_transform_matrix,
                                                   self.original_scale_factor)
         image_sheet, mask_sheet, cond_sheet, edited_sheet, references = self.generate_reference_sheet(graph, reference_cameras, tw, th)
-        self._writer.save_reference_sheets(image_sheet, mask_sheet, cond_sheet, edited_sheet)
-        idx = 0
-        transforms["reference_indices"] = []
-        for i in range(len(reference_cameras)):
-            transforms = self.save_generated_images(idx, references[i], reference_cameras[i], transforms)
-            transforms["reference_indices"].append(idx)
-            idx += 1
-        self._writer.write_transforms(transforms)
-        transforms["generated_indices"] = []
-        for i in range(len(cameras)):
+        n_ref, n_gen = len(reference_cameras), len(cameras)
+        transforms["reference_indices"] = list(range(n_ref))
+        transforms["generated_indices"] = list(range(n_ref, n_ref + n_gen))
+        if rank == 0:
+            self._writer.save_reference_sheets(image_sheet, mask_sheet, cond_sheet, edited_sheet)
+            for i in range(n_ref):
+                transforms = self.save_generated_images(i, references[i], reference_cameras[i], transforms)
+            if world == 1:
+                self._writer.write_transforms(transforms)
+        # Hot loop #1 (datasetgenerator.py:331-338): every dataset camera owns its sheet (the edited reference tiles + its
+        # own last tile) and its own denoising trajectory - independent units, camera i -> rank i mod world, no data-path
+        # collective.  Each rank writes its own PNGs (file names carry the global index); the frames are gathered once at
+        # the end and rank 0 writes transforms.json in index order.
+        mine: Dict[str, list] = {"frames": []}
+        produced: List[Tuple[int, dict]] = []
+
+        def keep(idx: int) -> None:
+            produced.append((idx, mine["frames"].pop()))
+
+        for i in range(rank, n_gen, world):
             filename = original_filenames[i]
             images = self.generate_with_reference_sheet(graph, cameras[i], filename, tw, th, edited_sheet, cond_sheet)
-            transforms = self.save_generated_images(idx, images, cameras[i], transforms, filename is not None)
-            transforms["generated_indices"].append(idx)
-            idx += 1
-        self._writer.write_transforms(transforms)
+            self.save_generated_images(n_ref + i, images, cameras[i], mine, filename is not None)
+            keep(n_ref + i)
+        if world == 1:
+            transforms["frames"] += [f for _, f in produced]
+            produced = []
+            self._writer.write_transforms(transforms)
         if merge_with_original_dataset:
-            transforms["original_indices"] = []
             ocams = as_camera_batch(original_dataset.cameras)
+            base = n_ref + n_gen
+            transforms["original_indices"] = list(range(base, base + len(ocams)))
             lay = ops.SheetLayout(1, 1, th, tw, 0)      # a 1 x 1 "sheet" = K4's bilinear resize (F.interpolate, :355-358)
 
             def scaled(t: Tensor, threshold: Optional[float] = None) -> Tensor:
@@ -319,15 +375,29 @@ class DatasetGenerator:
                 ops.sheet_paste(t.to(dev, torch.float32)[None].contiguous(), out, lay, 0, **({} if threshold is None else {"threshold": threshold}))
                 return out[:th, :tw]
 
-            for i in range(len(ocams)):
+            for i in range(rank, len(ocams), world):
                 image = original_dataset.get_image_float32(i).to(dev)
-                render, mask, condition = self.render_camera(graph, ocams[i])
+                render, mask, condition = self.render_camera(graph, ocams[i], combine_shape_with_depth=self.combine_shape_with_depth)
                 mask = ~mask                           # the photos do not contain the object (:351-352)
                 images = {"render": render, "mask": mask, "condition": condition, "edited": image,
                           "render_scaled": scaled(render), "mask_scaled": scaled(mask.float(), 0.5) > 0.5,
                           "condition_scaled": scaled(condition), "edited_scaled": scaled(image)}
-                transforms = self.save_generated_images(idx, images, ocams[i], transforms, True)
-                transforms["original_indices"].append(idx)
-                idx += 1
+                self.save_generated_images(base + i, images, ocams[i], mine, True)
+                keep(base + i)
+            if world == 1:
+                transforms["frames"] += [f for _, f in produced]
+                produced = []
+        if world > 1:
+            import torch.distributed as dist
+            from .. import sharding
+            self._writer.writer.flush()                 # this rank's PNGs are on disk before anybody names them
+            parts: List[Optional[list]] = [None] * world
+            dist.all_gather_object(parts, produced)
+            if rank == 0:
+                transforms["frames"] += sharding.merge_frames(parts)
+        if rank == 0:
             self._writer.write_transforms(transforms)
         self._writer.writer.close()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()

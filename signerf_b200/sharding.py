@@ -52,6 +52,36 @@ def gather_grids(packed_local: Tensor, num_views: int, world: int, rank: int, gr
     return out
 
 
+def all_gather_views(local: Tensor, num_views: int, world: int, rank: int, group: Optional[object] = None) -> Tensor:
+    """local [len(views_of_rank(num_views, world, rank)), ...] -> [num_views, ...] on every rank, view v taken from rank
+    v % world.  `num_views` need not divide by `world` (the reference sheet has rows * cols - 1 views): short ranks pad
+    their shard to ceil(num_views / world) rows for the ONE all_gather and the padding is dropped afterwards."""
+    mine = views_of_rank(num_views, world, rank)
+    if local.shape[0] != len(mine):
+        raise ValueError(f"rank {rank} holds {local.shape[0]} views, expected {len(mine)}")
+    if world == 1:
+        return local
+    k = (num_views + world - 1) // world
+    padded = local.new_zeros((k,) + tuple(local.shape[1:]))
+    padded[:len(mine)] = local
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(parts, padded.contiguous(), group=group)
+    out = local.new_empty((num_views,) + tuple(local.shape[1:]))
+    for r in range(world):
+        n_r = len(range(r, num_views, world))
+        out[r::world] = parts[r][:n_r]
+    return out
+
+
+def merge_frames(per_rank: List[List[Tuple[int, dict]]]) -> List[dict]:
+    """[(global index, transforms.json frame)] lists of all ranks -> frames in index order (each index exactly once)."""
+    flat = sorted((pair for part in per_rank for pair in part), key=lambda p: p[0])
+    idx = [i for i, _ in flat]
+    if idx != sorted(set(idx)):
+        raise ValueError("two ranks produced the same frame index")
+    return [f for _, f in flat]
+
+
 class PeerTileExchange:
     """The same exchange without a collective: every rank owns a symmetric-memory tile buffer [num_views, H, W, 6] for
     ITS grid, and the producers store their packed tiles straight into the owner's buffer over NVLink
