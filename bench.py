@@ -109,9 +109,10 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- reference arm
-def cpu_oracle_sample(rays_per_sample: int = 8192):
+def cpu_oracle_sample(rays_per_sample: int):
     """Time the oracle (literal torch restatement of nerfstudio's torch nerfacto eval = the reference's Python
-    path) on a bounded sample of the C2 workload: `rays_per_sample` rays of view 0 x 128 samples."""
+    path) on a bounded sample of the C2 workload: `rays_per_sample` rays of view 0 x 128 samples, in chunks of
+    32 768 rays as `eval_num_rays_per_chunk` (signerf_config.py:32)."""
     from oracle import nerfacto_ref as R
     from tests.helpers import ring_cameras
     cores = os.cpu_count() or 1
@@ -123,13 +124,11 @@ def cpu_oracle_sample(rays_per_sample: int = 8192):
 
     def run():
         t = time.perf_counter()
-        R.render_rays(m, o, d, "flat", SAMPLES)
+        for i in range(0, o.shape[0], 1 << 15):
+            R.render_rays(m, o[i:i + (1 << 15)], d[i:i + (1 << 15)], "flat", SAMPLES)
         return time.perf_counter() - t
 
     return run, cores, rays_per_sample
-
-
-UNET_CPU_SHEET = 512   # the CPU sample of the diffusion half runs the full-width networks on a 512^2 sheet (latent 64^2)
 
 
 def unet_tflop(sheet: int) -> float:
@@ -140,15 +139,16 @@ def unet_tflop(sheet: int) -> float:
     return (UNET_TFLOP_PER_STEP - 34.7) * r + 34.7 * r * r
 
 
-def cpu_unet_sample():
+def cpu_unet_sample(sheet: int):
     """The reference's diffusion arithmetic (fp32 torch, `--no-half`) = oracle/sdxl_ref.py at full SDXL width on the host
-    cores, one CFG step incl. ControlNet on a 512^2 sheet; scaled to the 2048^2 sheet by algorithmic FLOPs."""
+    cores, one CFG step incl. ControlNet on a `sheet`^2 image; scaled to the 2048^2 sheet by algorithmic FLOPs
+    (1024^2 measured, x5.3)."""
     from oracle import sdxl_ref as X
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     cfg = X.UNetConfig()
     unet, ctrl = X.make_models(cfg, fast_init=True)
-    h = UNET_CPU_SHEET // 8
+    h = sheet // 8
     g = torch.Generator().manual_seed(1)
     x = torch.randn(1, 4, h, h, generator=g)
     ctx, y = torch.randn(2, 77, cfg.context_dim, generator=g), torch.randn(2, cfg.adm_in_channels, generator=g)
@@ -159,40 +159,46 @@ def cpu_unet_sample():
         X.denoise_step(unet, ctrl, x, 13.0, 10.0, ctx, y, hint, noise)
         return time.perf_counter() - t
 
-    return run, cores, unet_tflop(2048) / unet_tflop(UNET_CPU_SHEET)
+    return run, cores, unet_tflop(2048) / unet_tflop(sheet)
 
 
-def cpu_baseline(render_runs: int, unet_runs: int, with_unet: bool = True):
-    """-> (grids/s, cores, sample description) of the CPU path on bounded samples of the benchmark workload."""
-    run, cores, n = cpu_oracle_sample()
-    run()
-    per_grid = float(np.mean([run() for _ in range(render_runs)])) / n * VIEWS * H * W
-    sample = (f"render: {n} rays x {SAMPLES} samples of view 0 through oracle/nerfacto_ref.py, scaled to 16x512^2 rays "
-              f"({per_grid:.1f} s/grid)")
+def cpu_baseline(rays: int, render_runs: int, unet_sheet: int, unet_runs: int, with_unet: bool = True):
+    """-> (grids/s, cores, sample description, parts) of the CPU path on bounded samples of the benchmark workload."""
+    run, cores, n = cpu_oracle_sample(rays)
+    if n < H * W:
+        run()                                   # warm-up (a full view is its own warm-up: ~1 minute of CPU time)
+    t_r = float(np.mean([run() for _ in range(render_runs)]))
+    per_grid = t_r / n * VIEWS * H * W
+    parts = {"render_sample_rays": n, "render_sample_s": t_r, "render_s_per_grid_scaled": per_grid}
+    what = "one full 512x512 view" if n == H * W else f"{n} rays of view 0"
+    sample = (f"render: {what} x {SAMPLES} samples through oracle/nerfacto_ref.py in {t_r:.1f} s measured, x{VIEWS * H * W / n:.0f} "
+              f"to 16 views = {per_grid:.1f} s/grid")
     if with_unet:
-        urun, _, scale = cpu_unet_sample()
+        urun, _, scale = cpu_unet_sample(unet_sheet)
         t = float(np.mean([urun() for _ in range(unet_runs)]))
         per_grid += t * scale
+        parts.update({"unet_sample_sheet": unet_sheet, "unet_sample_s": t, "unet_flop_scale": scale, "unet_s_per_grid_scaled": t * scale})
         sample += (f"; diffusion: one fp32 UNet+ControlNet CFG step of oracle/sdxl_ref.py (full SDXL width) on a "
-                   f"{UNET_CPU_SHEET}^2 sheet = {t:.1f} s, scaled x{scale:.1f} by algorithmic FLOPs to the 2048^2 sheet")
-    return 1.0 / per_grid, cores, sample
+                   f"{unet_sheet}^2 sheet = {t:.1f} s measured, x{scale:.2f} by algorithmic FLOPs to the 2048^2 sheet")
+    return 1.0 / per_grid, cores, sample, parts
 
 
 def reference_arm(args):
     """The reference's own CPU implementation of the path = the oracle ports (nothing of the reference is installable
-    here: SURVEY §0), on all host cores, bounded samples; rank 0 only."""
+    here: SURVEY §0), on all host cores; rank 0 only.  Samples as SURVEY §8d specifies them: ONE full 512 x 512 x 128
+    view (1/16 of the grid's render) and ONE UNet+ControlNet step on a 1024^2 sheet (19.5 of the 103.96 TFLOP), each
+    measured once per run (they take about a minute each on 16 cores) and scaled to the grid."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     t0 = time.perf_counter()
-    val, cores, sample = cpu_baseline(render_runs=max(1, min(args.steps, 3)), unet_runs=max(1, min(args.steps, 2)),
-                                      with_unet=not args.no_unet)
+    val, cores, sample, parts = cpu_baseline(rays=H * W, render_runs=1, unet_sheet=1024, unet_runs=1, with_unet=not args.no_unet)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 / val, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "C3 4x4 grid 512x512, flat 128 samples/ray + 1 SDXL+ControlNet UNet step (CFG 2) on the "
                                    "2048^2 sheet; CPU arm measured on bounded samples and scaled (see cpu_baseline.sample)",
-                       "wall_s": None},
+                       "measured_vs_scaled": parts, "wall_s": None},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     line["config"]["wall_s"] = round(time.perf_counter() - t0, 1)
@@ -211,6 +217,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end and per-kernel passes (ncu runs only)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU tile exchange: fused NVLink peer stores (default) or one NCCL all-gather")
+    ap.add_argument("--config5-cameras", type=int, default=1,
+                    help="dataset cameras PER RANK of the BASELINE-config-5 generation sample (0 = skip)")
+    ap.add_argument("--config5-total", action="store_true", help="--config5-cameras is the TOTAL camera count (30 = the named job)")
     ap.add_argument("--ncu-range", action="store_true",
                     help="cudaProfilerStart/Stop around the timed steps (run under `ncu --profile-from-start off`)")
     args = ap.parse_args()
@@ -362,16 +371,61 @@ def main():
     k1_ms = sum(a.elapsed_time(b) for a, b in k1_events) / len(k1_events)
     unet_ms = sum(a.elapsed_time(b) for a, b in unet_events) / len(unet_events) if unet_events else 0.0
 
-    # e2e: host cameras (pinned) -> device, full step, result read back to the host, every step
+    # correctness carried by the line itself: grid 0's image / mask / condition sheets as rank 0 holds them after the
+    # per-view shard + exchange must be the bytes a single GPU produces (pure partition: SURVEY §4 item 3)
+    def sheet_digest(bufs) -> int:
+        acc = 0
+        for t in (bufs.image, bufs.mask, bufs.condition):
+            acc = (acc * 1000003 + int(t.contiguous().view(torch.int32).to(torch.int64).sum())) & 0xFFFFFFFFFFFFFFFF
+        return acc
+
+    step(c2w_d, intr_d)
+    torch.cuda.synchronize()
+    digest = sheet_digest(sheet.buffers) if rank == 0 else 0
+    digest_single = None
+    if rank == 0 and N > 1:
+        solo = ReferenceSheetRenderer(fld, layout, H, W, ropts, mopts)
+        digest_single = sheet_digest(solo(c2w_all[0].to(dev), intr_all[0].to(dev)))
+        del solo
+    sync_all()
+
+    # e2e: the same unit through the reference-facing plugin API, host buffers in, host result out, every step:
+    #   plugin.DatasetGenerator.generate_reference_sheet(graph, 15 reference cameras, w, h)   (datasetgenerator.py:470-593:
+    #       15 renders + masks / conditions, paste, Diffuser.diffuse on the sheet, blend, 15 tile cut-outs)
+    #   plugin.DatasetGenerator.render_camera(graph, the 16th = dataset camera)                (:677-820)
+    # with the cameras in pinned HOST memory (the plugin copies them to the device) and `Diffuser.diffuse` = the one
+    # UNet + ControlNet + sampler step of the metric, whose latent is read back to the host.
+    import signerf_b200.plugin as P
+
+    class OneStepDiffuser(P.Diffuser):
+        """`Diffuser.diffuse(original, rendered, mask, condition)` boundary (diffuser.py:92-106) running ONE step."""
+        latent = None
+
+        def diffuse(self, original_image, rendered_image, mask_image=None, condition_image=None):
+            if unet is not None:
+                OneStepDiffuser.latent = unet.step(original_image, mask_image, condition_image)
+            else:
+                OneStepDiffuser.latent = original_image
+            return original_image
+
+    gcfg = P.DatasetGeneratorConfig(rows=ROWS, cols=COLS, width=W, height=H, downscale_factor=1, fx=float(W), fy=float(W),
+                                    cx=W / 2.0, cy=H / 2.0)
+    gen = gcfg.setup(original_transform_matrix=torch.eye(4)[:3], original_scale_factor=1.0,
+                     transform_poses_to_original_space=lambda x: x, device=dev)
+    gen.diffuser = OneStepDiffuser(gcfg.diffuser, dev)
+    gen._dist = lambda: (0, 1)                    # every rank runs whole units here (DP over sheets: hot loop #1)
+    graph = P.FusedNerfactoGraph(fld, ropts)
+    c2w_e2e = c2w_all[rank].contiguous().pin_memory()           # this rank's grid: [16,3,4] in pinned host memory
     res_h = None
     e2e_evs = []
     sync_all()
     for i in range(0 if args.no_e2e else args.warmup + args.steps):
         a, b = ev(), ev()
         a.record()
-        c = c2w_h.to(dev, non_blocking=True)
-        it = intr_h.to(dev, non_blocking=True)
-        out = step(c, it)
+        cams = P.CameraBatch(c2w_e2e, float(W), float(W), W / 2.0, H / 2.0, W, H)
+        gen.generate_reference_sheet(graph, cams[:VIEWS - 1], W, H)
+        gen.render_camera(graph, cams[VIEWS - 1])
+        out = OneStepDiffuser.latent
         if res_h is None:
             res_h = torch.empty(out.shape, dtype=out.dtype).pin_memory()
         res_h.copy_(out, non_blocking=True)
@@ -418,6 +472,78 @@ def main():
         codec_ms = (e0.elapsed_time(e1), e1.elapsed_time(e2))
         del codec, st, edited
 
+    # C2' (the sampling the reference really uses, and the plugin's default): 256 -> 96 -> 48 cascade through both proposal
+    # networks at the benchmark size, timed beside the flat-128 headline (678.6 GB of algorithmic gathers)
+    cascade_ms = None
+    if rank == 0 and not args.no_e2e:
+        fld_c = synthetic.random_field(seed=0, device=dev, dense=True, with_proposals=True)
+        copts = ops.RenderOptions(mode="cascade", num_samples=48, num_prop_samples=(256, 96))
+        ops.render_views(fld_c, c2w_d, intr_d, H, W, copts)
+        torch.cuda.synchronize()
+        a, b = ev(), ev()
+        a.record()
+        ops.render_views(fld_c, c2w_d, intr_d, H, W, copts)
+        b.record()
+        torch.cuda.synchronize()
+        cascade_ms = a.elapsed_time(b)
+        fld_c.close()
+        del fld_c
+
+    # BASELINE config 5, generation half (the fine-tune half is §8(f) row 4): the whole product entry point
+    # plugin.DatasetGenerator.generate_dataset with masking_mode="shape" (proxy mesh through the CUDA rasteriser),
+    # Diffuser(mode="custom") = A1111 pre + VAE encode + 19 UNet+ControlNet evaluations + VAE decode + overlay per sheet,
+    # dataset cameras sharded i mod N over the ranks, PNGs + transforms.json written.  Default run: a bounded sample of
+    # `--config5-cameras` dataset cameras per rank; `--config5-cameras 30 --config5-total` runs the named 30-camera job.
+    config5 = None
+    if unet is not None and args.config5_cameras > 0 and not args.no_e2e:
+        import shutil
+        import tempfile
+        from signerf_b200 import inpaint as inpaint_mod
+        from signerf_b200 import vae as vae_mod
+        n_cam = args.config5_cameras if args.config5_total else args.config5_cameras * N
+        vcfg = vae_mod.VAEConfig()
+        codec5 = inpaint_mod.A1111InpaintCodec(vae_mod.VAEB200(vcfg, vae_mod.VAERandomWeights(vae_mod.vae_param_schema(vcfg), 2, dev), dev))
+        tmp = tempfile.mkdtemp(prefix="sgn_config5_") if rank == 0 else None
+        if world > 1:
+            box = [tmp]
+            dist.broadcast_object_list(box, src=0)
+            tmp = box[0]
+        g5 = P.DatasetGeneratorConfig(path=tmp, dataset_name="config5", rows=ROWS, cols=COLS, width=W, height=H, downscale_factor=1,
+                                      fx=float(W), fy=float(W), cx=W / 2.0, cy=H / 2.0, masking_mode="shape",
+                                      diffuser=P.DiffuserConfig(mode="custom"))
+        gen5 = g5.setup(original_transform_matrix=torch.eye(4)[:3], original_scale_factor=1.0,
+                        transform_poses_to_original_space=lambda x: x, device=dev)
+        gen5.diffuser.attach(P.InProcessSDXL(unet.net, unet.context, unet.y, codec5))
+        pv, pf = synthetic.proxy_mesh(4968)                      # as many triangles as the reference's models/bunny.obj
+        gen5.renderer.set_mesh(pv, pf)
+        gen5.renderer.scale = [0.01, 0.01, 0.01]                 # x10 "Blender ratio" -> a 0.1-radius object at the origin
+        # a transparent random-init field (sigma ~ 0.01): median depth = far plane, so the proxy is in front wherever it
+        # covers a pixel and the masks are not empty; rendered with the plugin's default sampling (256 -> 96 -> 48 cascade)
+        fld5 = synthetic.random_field(seed=0, device=dev, dense=False, with_proposals=True)
+        graph5 = P.FusedNerfactoGraph(fld5)
+        ref_c2w, _ = synthetic.camera_ring(VIEWS - 1, W, H)
+        syn_c2w, _ = synthetic.camera_ring(n_cam, W, H, phi_deg=(3.0, 357.0))
+        sync_all()
+        t0 = time.perf_counter()
+        gen5.generate_dataset(graph5, ref_c2w, synthetic_camera_to_worlds=syn_c2w)
+        sync_all()
+        t5 = time.perf_counter() - t0
+        frames = None
+        if rank == 0:
+            frames = len(json.load(open(os.path.join(tmp, "config5", "transforms.json")))["frames"])
+            shutil.rmtree(tmp, ignore_errors=True)
+        per_rank = (n_cam + N - 1) // N
+        config5 = {"dataset_cameras": n_cam, "reference_views": VIEWS - 1, "ranks": N, "seconds": t5, "frames_written": frames,
+                   "sheets_diffused_per_rank": 1 + per_rank, "seconds_per_sheet": t5 / (1 + per_rank),
+                   "dataset_views_per_s": n_cam / t5,
+                   "estimated_30_camera_seconds": t5 / (1 + per_rank) * (1 + (30 + N - 1) // N),
+                   "note": "BASELINE config 5, generation half through plugin.DatasetGenerator.generate_dataset: procedural proxy mesh "
+                           "with bunny.obj's 4 968 triangles (the reference's mesh file is not shipped), masking_mode='shape', 4x4 sheet of "
+                           "512^2 tiles, 20 configured steps at strength 0.9 = 19 UNet+ControlNet evaluations per sheet, eager launches, "
+                           "PNG encoding + transforms.json included, host wall clock; fine-tune rounds are SURVEY §8(f) row 4"}
+        fld5.close()
+        del codec5, gen5, graph5, fld5
+
     if rank == 0:
         pk = peaks()
         ms_per_step = total_ms / args.steps
@@ -436,8 +562,15 @@ def main():
                        "views": VIEWS, "height": H, "width": W, "samples_per_ray": SAMPLES, "sheet": [layout.height, layout.width],
                        "unet": unet is not None, "sharding": exchange_name,
                        "l2": "256 MiB memset between steps, outside the timed events"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(c2w_h.numel() * 4 + intr_h.numel() * 4),
-                    "d2h_bytes_per_step": int(res_h.numel() * res_h.element_size())},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(c2w_e2e.numel() * 4 + VIEWS * 4 * 4),
+                    "d2h_bytes_per_step": int(res_h.numel() * res_h.element_size()),
+                    "api": "signerf_b200.plugin.DatasetGenerator.generate_reference_sheet(graph, 15 cameras, 512, 512) + "
+                           "render_camera(graph, 16th camera); Diffuser.diffuse = one UNet+ControlNet step; cameras from pinned "
+                           "host memory, latent read back to the host"},
+            "sheet_checksum": {"grid0_u64": digest, "single_gpu_u64": digest_single,
+                               "bit_identical_to_single_gpu": (digest == digest_single) if digest_single is not None else None,
+                               "what": "wrapping int64 sum of the fp32 bit patterns of grid 0's image / mask / condition sheets on "
+                                       "rank 0 after the per-view shard + tile exchange; equals the N=1 line's value"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
@@ -478,9 +611,22 @@ def main():
                         "latent mask) + SDXL VAE encode + 20 configured steps at denoising strength 0.9 = 19 UNet+ControlNet CFG "
                         "evaluations on the 2048^2 sheet latent (eager launches) + VAE decode + overlay compositing; "
                         "random-init weights; prompt encoders excluded (once per prompt)"}
+        if cascade_ms is not None:
+            cb = VIEWS * H * W * (48 * RENDER_BYTES_PER_SAMPLE + 352 * 320 + RENDER_BYTES_PER_RAY)
+            line["render_cascade_c2prime"] = {
+                "ms": cascade_ms, "algorithmic_bytes": cb, "achieved_gbs": cb / (cascade_ms / 1e3) / 1e9,
+                "frac_of_hbm_peak": cb / (cascade_ms / 1e3) / 1e9 / pk["hbm"],
+                "note": "16 views 512^2, nerfacto's own sampling (256 -> 96 -> 48 through two proposal networks, then the main "
+                        "field on 48 samples): k_prop_weights x2, k_pdf_resample x2, k_render_mma per 4-view chunk; the "
+                        "plugin's default mode (FusedNerfactoGraph), not part of the headline unit (flat 128)"}
+        if config5 is not None:
+            line["config5_generation"] = config5
         if N == 1 and not args.no_cpu_baseline:
-            val, cores, sample = cpu_baseline(render_runs=2, unet_runs=1, with_unet=unet is not None)
-            line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+            # bounded: a quarter view (65 536 rays, ~15 s) and one 512^2-sheet step (~3 s); `--impl reference` measures the
+            # full view and the 1024^2 sheet
+            val, cores, sample, parts = cpu_baseline(rays=H * W // 4, render_runs=1, unet_sheet=512, unet_runs=1, with_unet=unet is not None)
+            line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                                    "measured_vs_scaled": parts}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -6,6 +6,9 @@ sys.path.insert(0, "/root/repo")
 from signerf_b200 import nn_ops
 
 which = sys.argv[1]
+if len(sys.argv) > 2:   # run_kernel.py attention <attn_variant>
+    from signerf_b200 import _lib
+    _lib.set_option("attn_variant", int(sys.argv[2]))
 if which == "attention":      # self-attention of the 640-channel level at the 2048^2 sheet
     B, heads, T = 2, 10, 16384
     qkv = torch.randn(B * T, 3 * heads * 64, device="cuda").half()

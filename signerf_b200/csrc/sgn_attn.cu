@@ -76,6 +76,71 @@ __device__ __forceinline__ float ex2_v(float x) {   // pinned in program order (
   return y;
 }
 
+// ---- packed fp32 pairs (Blackwell FFMA2 / FADD2: two lanes of fp32 per issue slot) and the 3-input maximum (FMNMX3):
+// the softmax warps are bound by issue slots next to the MUFU pipe, so every per-element instruction that can be halved is
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t pk2u(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+// the same operations pinned in program order (asm volatile): the fine-grained software pipeline of variants >= 8 is
+// written instruction by instruction and must not be re-bunched by the scheduler
+__device__ __forceinline__ uint64_t fma2_v(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add2_v(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t cvt_h2_v(float lo, float hi) {
+  uint32_t d;
+  asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+// exp2 of a pair on the FMA pipe: round-to-nearest split x = n + f (magic-number add), degree-3 minimax polynomial of 2^f
+// on [-0.5, 0.5] (max relative error 7.5e-5, a third of the fp16 rounding P gets anyway), exponent patched in with an
+// integer multiply-add.  6 packed FMA-pipe instructions + 2 IMAD + 2 FMNMX for two exponentials, none on the MUFU pipe.
+__device__ __forceinline__ void ex2_poly_pair(uint64_t t, uint32_t& e0, uint32_t& e1) {
+  float t0, t1;
+  upk2(t, t0, t1);
+  const uint64_t x = pk2(fmaxf(t0, -125.f), fmaxf(t1, -125.f));
+  const uint64_t magic = pk2(12582912.f, 12582912.f), neg_magic = pk2(-12582912.f, -12582912.f);
+  const uint64_t r = add2(x, magic);                       // low mantissa bits of each half hold round(x)
+  const uint64_t f = fma2(add2(r, neg_magic), pk2(-1.f, -1.f), x);   // x - round(x) in [-0.5, 0.5]
+  uint64_t p = fma2(f, pk2(0.05517100281f, 0.05517100281f), pk2(0.24260949573f, 0.24260949573f));
+  p = fma2(p, f, pk2(0.69326094686f, 0.69326094686f));
+  p = fma2(p, f, pk2(0.99992817475f, 0.99992817475f));
+  float p0, p1, r0, r1;
+  upk2(p, p0, p1);
+  upk2(r, r0, r1);
+  e0 = (uint32_t)(__float_as_int(p0) + (__float_as_int(r0) << 23));
+  e1 = (uint32_t)(__float_as_int(p1) + (__float_as_int(r1) << 23));
+}
+
 // make -C signerf_b200/csrc trace: clock64 time stamps of CTA 0 (softmax warp 2 lane 0 and the issuer), read back by
 // scratch/attn_trace.py through sgn_debug_attn_trace
 #ifdef SGN_ATTN_TRACE
@@ -84,7 +149,7 @@ __device__ long long g_trace[16 * 256];   // [event][key tile]
 #else
 #define TRACE(ev, j) do { } while (0)
 #endif
-int g_attn_variant = 1;   // sgn_set_option "attn_variant"
+int g_attn_variant = 2;   // sgn_set_option "attn_variant" (2 = packed math + MUFU turns: +4.5 % over 1 on B200)
 int g_attn_idle_ns = 0;   // sgn_set_option "attn_idle_ns"
 
 template <int kVariant>
@@ -215,7 +280,13 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t ts = tS + x * kKvTile + lane_addr;
     const uint32_t to = tO + x * kHeadDim + lane_addr;
 
-    constexpr bool kTurns = true;   // (free-running groups measure the same as turn-taking)
+    // variants: 0 / 1 scalar math (1 = software-pipelined exponentials, the round-1 kernel); >= 2 packed math (FFMA2 /
+    // FADD2 / FMNMX3): 2 turn-taking, 3 free-running groups, 4 / 5 the same with a quarter of the exponentials on the FMA
+    // pipe (ex2_poly_pair), 6 / 7 with three eighths
+    constexpr bool kPacked = kVariant >= 2;
+    constexpr bool kFine = kVariant >= 8;   // 8: pair-granular software pipeline, free-running groups; 9: with turns
+    constexpr bool kTurns = !(kVariant == 3 || kVariant == 5 || kVariant == 7 || kVariant == 8);
+    constexpr int kPolyOf8 = kVariant >= 6 ? 3 : (kVariant >= 4 ? 2 : 0);   // pairs out of every 8 that go to the FMA pipe
     if (kTurns && x == 1) named_arrive(1, 256);  // group A takes the first turn
     for (int j = 0; j < n_kv; ++j) {
       const int kv_rem = p.T_kv - j * kKvTile;  // >= 1
@@ -238,10 +309,24 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           if (q >= kv_rem) s[q] = 0xff800000u;  // -inf
       }
       float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]);
+      if constexpr (kPacked) {
+        float mx2 = __uint_as_float(s[2]), mx3 = __uint_as_float(s[3]);
 #pragma unroll
-      for (int q = 2; q < 128; q += 2) {
-        mx0 = fmaxf(mx0, __uint_as_float(s[q]));
-        mx1 = fmaxf(mx1, __uint_as_float(s[q + 1]));
+        for (int q = 4; q < 124; q += 8) {
+          mx0 = max3(mx0, __uint_as_float(s[q]), __uint_as_float(s[q + 1]));
+          mx1 = max3(mx1, __uint_as_float(s[q + 2]), __uint_as_float(s[q + 3]));
+          mx2 = max3(mx2, __uint_as_float(s[q + 4]), __uint_as_float(s[q + 5]));
+          mx3 = max3(mx3, __uint_as_float(s[q + 6]), __uint_as_float(s[q + 7]));
+        }
+        mx0 = max3(mx0, __uint_as_float(s[124]), __uint_as_float(s[125]));
+        mx1 = max3(mx1, __uint_as_float(s[126]), __uint_as_float(s[127]));
+        mx0 = max3(mx0, mx2, mx3);
+      } else {
+#pragma unroll
+        for (int q = 2; q < 128; q += 2) {
+          mx0 = fmaxf(mx0, __uint_as_float(s[q]));
+          mx1 = fmaxf(mx1, __uint_as_float(s[q + 1]));
+        }
       }
       const float mx = fmaxf(mx0, mx1);
       // P_x(j-1) V(j-1) must be complete before P_x is rewritten or O_x rescaled; P_x(j) V(j) is not issued before
@@ -299,6 +384,100 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           }
           tc::tmem_st32(tp + c * 32, pk);
         }
+      } else if constexpr (kFine) {
+        // Pair-granular software pipeline, every instruction pinned in program order: per pair of keys
+        //     FFMA2 (scale + shift of the NEXT pair) | MUFU.EX2 x2 (this pair) | FADD2 + F2FP (the pair 8 pairs back)
+        // so that the MUFU pipe (8 clk per warp instruction) never waits behind a burst of the other instructions: 5 issue
+        // slots per 16 MUFU clocks, and a MUFU result is consumed 128 clocks after its issue.
+        const uint64_t sc2 = pk2(sc, sc), nm2 = pk2(neg_m, neg_m);
+        uint64_t acc_a = pk2(0.f, 0.f), acc_b = pk2(0.f, 0.f);
+        uint32_t pk[32];
+        uint64_t t_cur = fma2_v(pk2u(s[0], s[1]), sc2, nm2);
+#pragma unroll
+        for (int i = 0; i < 64 + 8; ++i) {      // i: pair index of the exponentials; i - 8: pair being summed / packed
+          uint64_t t_next = t_cur;
+          if (i + 1 < 64) t_next = fma2_v(pk2u(s[2 * i + 2], s[2 * i + 3]), sc2, nm2);
+          if (i < 64) {
+            float t0, t1;
+            upk2(t_cur, t0, t1);
+            s[2 * i] = __float_as_uint(ex2_v(t0));
+            s[2 * i + 1] = __float_as_uint(ex2_v(t1));
+          }
+          t_cur = t_next;
+          if (i >= 8) {
+            const int c = i - 8;
+            const uint64_t e2 = pk2u(s[2 * c], s[2 * c + 1]);
+            if (c & 1) acc_b = add2_v(acc_b, e2);
+            else acc_a = add2_v(acc_a, e2);
+            pk[c & 31] = cvt_h2_v(__uint_as_float(s[2 * c]), __uint_as_float(s[2 * c + 1]));
+            if ((c & 31) == 31) {
+              if (!o_ready) {   // warp-uniform
+                if (tr) TRACE(5, j);
+                tc::mbar_wait(&o_full[x], (j - 1) & 1);
+                if (tr) TRACE(6, j);
+                tc::tc_fence_after();
+                o_ready = true;
+              }
+              tc::tmem_st32(tp + (c >> 5) * 32, pk);
+            }
+          }
+        }
+        float a0, a1, b0, b1;
+        upk2(acc_a, a0, a1);
+        upk2(acc_b, b0, b1);
+        psum0 = a0 + a1;
+        psum1 = b0 + b1;
+      } else if constexpr (kPacked) {
+        // Packed math: scale + shift as FFMA2, row sums as FADD2, 2 packed accumulator chains; software-pipelined by
+        // one 16-key block like variant 1.  kPolyOf8 of every 8 pairs take the polynomial instead of MUFU.EX2.
+        const uint64_t sc2 = pk2(sc, sc), nm2 = pk2(neg_m, neg_m);
+        uint64_t acc_a = pk2(0.f, 0.f), acc_b = pk2(0.f, 0.f);
+        auto exp_block = [&](int b) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const uint64_t t = fma2(pk2u(s[b * 16 + 2 * q], s[b * 16 + 2 * q + 1]), sc2, nm2);
+            if (q < kPolyOf8) {
+              ex2_poly_pair(t, s[b * 16 + 2 * q], s[b * 16 + 2 * q + 1]);
+            } else {
+              float t0, t1;
+              upk2(t, t0, t1);
+              s[b * 16 + 2 * q] = __float_as_uint(ex2(t0));
+              s[b * 16 + 2 * q + 1] = __float_as_uint(ex2(t1));
+            }
+          }
+        };
+        exp_block(0);
+        uint32_t pk[32];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          if (b + 1 < 8) exp_block(b + 1);
+#pragma unroll
+          for (int q = 0; q < 8; q += 2) {
+            acc_a = add2(acc_a, pk2u(s[b * 16 + 2 * q], s[b * 16 + 2 * q + 1]));
+            acc_b = add2(acc_b, pk2u(s[b * 16 + 2 * q + 2], s[b * 16 + 2 * q + 3]));
+          }
+          const float* e = reinterpret_cast<const float*>(s) + b * 16;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            __half2 h = __floats2half2_rn(e[2 * q], e[2 * q + 1]);
+            pk[(b & 3) * 8 + q] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          if ((b & 3) == 3) {
+            if (!o_ready) {   // warp-uniform
+              if (tr) TRACE(5, j);
+              tc::mbar_wait(&o_full[x], (j - 1) & 1);
+              if (tr) TRACE(6, j);
+              tc::tc_fence_after();
+              o_ready = true;
+            }
+            tc::tmem_st32(tp + (b >> 2) * 32, pk);
+          }
+        }
+        float a0, a1, b0, b1;
+        upk2(acc_a, a0, a1);
+        upk2(acc_b, b0, b1);
+        psum0 = a0 + a1;
+        psum1 = b0 + b1;
       } else {
         // Software-pipelined: the exponentials of block b+1 (16 keys, in place over the S registers) are issued before
         // block b is summed and packed, so no MUFU result is consumed right behind its issue.
@@ -552,6 +731,14 @@ extern "C" int sgn_attention_f16(const void* d_q, int64_t ldq, const void* d_k, 
   if (!attr_set) {
     SGN_CUDA(cudaFuncSetAttribute(k_attention_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
     SGN_CUDA(cudaFuncSetAttribute(k_attention_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
+    SGN_CUDA(cudaFuncSetAttribute(k_attention_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
+    SGN_CUDA(cudaFuncSetAttribute(k_attention_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
+    SGN_CUDA(cudaFuncSetAttribute(k_attention_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
+    SGN_CUDA(cudaFuncSetAttribute(k_attention_tc<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
+    SGN_CUDA(cudaFuncSetAttribute(k_attention_tc<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
+    SGN_CUDA(cudaFuncSetAttribute(k_attention_tc<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
+    SGN_CUDA(cudaFuncSetAttribute(k_attention_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
+    SGN_CUDA(cudaFuncSetAttribute(k_attention_tc<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
     attr_set = true;
   }
   CUtensorMap tmQ, tmK, tmV;
@@ -573,7 +760,11 @@ extern "C" int sgn_attention_f16(const void* d_q, int64_t ldq, const void* d_k, 
   p.ldo = ldo;
   dim3 grid((T_q + kQPerCta - 1) / kQPerCta, heads, B);
   p.idle_ns = g_attn_idle_ns;
-  auto kern = g_attn_variant == 1 ? k_attention_tc<1> : k_attention_tc<0>;
+  using Kern = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, AttnParams);
+  static const Kern kerns[10] = {k_attention_tc<0>, k_attention_tc<1>, k_attention_tc<2>, k_attention_tc<3>,
+                                 k_attention_tc<4>, k_attention_tc<5>, k_attention_tc<6>, k_attention_tc<7>,
+                                 k_attention_tc<8>, k_attention_tc<9>};
+  Kern kern = kerns[g_attn_variant % 10];
   kern<<<grid, kAttnThreads, kAttnSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
   SGN_LAUNCH_CHECK();
   return SGN_OK;

@@ -163,7 +163,7 @@ struct AsyncBuf {
   void* p = nullptr;
   cudaStream_t st;
   explicit AsyncBuf(cudaStream_t s) : st(s) {}
-  cudaError_t alloc(size_t bytes) { return cudaMallocAsync(&p, bytes, st); }
+  cudaError_t alloc(size_t bytes) { return scratch_alloc(&p, bytes, st); }
   ~AsyncBuf() {
     if (p) cudaFreeAsync(p, st);
   }

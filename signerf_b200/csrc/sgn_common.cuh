@@ -41,6 +41,30 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::mem
     SGN_CUDA(cudaPeekAtLastError());       \
   } while (0)
 
+// Stream-ordered scratch memory.  The device's default memory pool releases freed blocks back to the driver at every
+// synchronisation point unless told otherwise (release threshold 0): a caller that synchronises between two entry points
+// (any host read-back does) then pays a fresh driver allocation per call - 10-15 ms for the small buffers, hundreds of ms
+// for the sampling cascade's gigabytes.  The first allocation on a device lifts the threshold, so scratch is recycled.
+inline cudaError_t scratch_alloc(void** p, size_t bytes, cudaStream_t st) {
+  static std::atomic<uint32_t> pool_ready{0};   // bit d: device d's pool keeps its memory
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const uint32_t bit = 1u << (dev & 31);
+  if (!(pool_ready.load(std::memory_order_relaxed) & bit)) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    pool_ready.fetch_or(bit, std::memory_order_relaxed);
+  }
+  return cudaMallocAsync(p, bytes, st);
+}
+template <class T>
+inline cudaError_t scratch_alloc(T** p, size_t bytes, cudaStream_t st) {
+  return scratch_alloc(reinterpret_cast<void**>(p), bytes, st);
+}
+
 constexpr int kMaxLevels = 16;
 constexpr uint32_t kPrimeY = 2654435761u;  // HashEncoding.hash_fn primes (x prime is 1)
 constexpr uint32_t kPrimeZ = 805459861u;

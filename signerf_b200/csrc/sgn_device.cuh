@@ -431,6 +431,7 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-
 struct Composite {
   float cum_dd = 0.f, r = 0.f, g = 0.f, b = 0.f, acc = 0.f, cumw = 0.f, depth = 0.f;
   float lr = 0.f, lg = 0.f, lb = 0.f;
+  float margin = 0.f;  // distance of 0.5 from the cumulative weights either side of the median pick (see finish)
   bool found = false;
   __device__ __forceinline__ void step(float sigma, float delta, float tmid, float cr, float cg, float cb) {
     float dd = delta * sigma;
@@ -442,7 +443,11 @@ struct Composite {
     r = fmaf(w, cr, r); g = fmaf(w, cg, g); b = fmaf(w, cb, b);
     acc += w;
     cumw += w;
-    if (!found && cumw >= 0.5f) { found = true; depth = tmid; }
+    if (!found && cumw >= 0.5f) {
+      found = true;
+      depth = tmid;
+      margin = fminf(cumw - 0.5f, 0.5f - (cumw - w));   // how far the pick is from moving to a neighbouring bin
+    }
     lr = cr; lg = cg; lb = cb;
   }
   // RGBRenderer("last_sample") + eval clamp; DepthRenderer("median") with the index clamp to S-1.
@@ -452,6 +457,7 @@ struct Composite {
     out_rgb[1] = fminf(fmaxf(fmaf(lg, rem, g), 0.f), 1.f);
     out_rgb[2] = fminf(fmaxf(fmaf(lb, rem, b), 0.f), 1.f);
     out_depth = found ? depth : last_tmid;
+    if (!found) margin = 0.5f - cumw;   // never reached one half: the pick is the last bin unless the total weight grows
   }
 };
 

@@ -299,8 +299,8 @@ extern "C" int sgn_mask_condition_shape(const float* d_proxy_depth, const float*
   const size_t npix = (size_t)H * W;
   ShapeStats* stats = nullptr;
   uint8_t* vis = nullptr;
-  SGN_CUDA(cudaMallocAsync(&stats, sizeof(ShapeStats) * V, st));
-  SGN_CUDA(cudaMallocAsync(&vis, (size_t)V * npix, st));
+  SGN_CUDA(scratch_alloc(&stats, sizeof(ShapeStats) * V, st));
+  SGN_CUDA(scratch_alloc(&vis, (size_t)V * npix, st));
   k_shape_stats_init<<<(V + 127) / 128, 128, 0, st>>>(stats, V);
   SGN_LAUNCH_CHECK();
   const int bpv = std::max(1, std::min((int)((npix + 255) / 256), std::max(1, sm_count() * 8 / V)));

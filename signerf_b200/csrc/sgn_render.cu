@@ -35,6 +35,11 @@ struct RenderParams {
   float* rgb;
   float* depth;
   float* acc;
+  // near-tie refinement of the median depth (fp16-MMA path): pixels whose pick sits within `refine_delta` of moving to a
+  // neighbouring bin are appended here and re-marched with the fp32 density by k_refine_depth
+  uint32_t* refine_list;
+  uint32_t* refine_count;
+  float refine_delta;
 };
 
 struct TileCoord {
@@ -66,6 +71,7 @@ __device__ __forceinline__ void store_pixel(const RenderParams& p, const TileCoo
   p.rgb[pix * 3 + 2] = o[2];
   p.depth[pix] = d;
   if (p.acc) p.acc[pix] = comp.acc;
+  if (p.refine_list && comp.margin < p.refine_delta) p.refine_list[atomicAdd(p.refine_count, 1u)] = (uint32_t)pix;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -183,6 +189,94 @@ __global__ void __launch_bounds__(kThreads) k_render_f32(const __grid_constant__
       last_mid = mid;
     }
     store_pixel(p, c, comp, last_mid);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Median depth is a discrete pick: the mid-point of the first bin whose cumulative weight reaches one half.  The fp16
+// tensor-core MLP carries the density logit to ~1e-3, the cumulative weight to a few 1e-4, so a ray whose pick sits that
+// close to a bin boundary can land in the neighbouring bin - a whole bin of depth error (4 % at 128 bins), which a few
+// rays in a thousand are enough to push the image's relative L2 past the 1e-3 contract.  k_render_mma lists those rays
+// (margin < delta); this kernel re-marches ONLY them with the density in fp32 (hash features + base MLP on CUDA cores,
+// the same arithmetic as k_render_f32; colour is not needed) and rewrites their depth.  One lane per listed ray.
+struct DensityF32 {
+  float w0[64 * 32];
+  float b0[64];
+  float w1[64];   // row 0 of base layer 1: the density logit
+  float b1;
+  float avg;
+};
+
+template <bool kPerRayBins>
+__global__ void __launch_bounds__(kThreads) k_refine_depth(const __grid_constant__ RenderParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  DensityF32* sw = reinterpret_cast<DensityF32*>(smem);
+  float* sbins = reinterpret_cast<float*>(smem + sizeof(DensityF32));
+  for (int i = threadIdx.x; i < 64 * 32; i += kThreads) sw->w0[i] = p.f32->w_base0[i];
+  for (int i = threadIdx.x; i < 64; i += kThreads) {
+    sw->b0[i] = p.f32->b_base0[i];
+    sw->w1[i] = p.f32->w_base1[i];
+  }
+  if (threadIdx.x == 0) {
+    sw->b1 = p.f32->b_base1[0];
+    sw->avg = p.f32->avg_density;
+  }
+  if (!kPerRayBins)
+    for (int i = threadIdx.x; i <= p.S; i += kThreads) sbins[i] = p.bins[i];
+  __syncthreads();
+  const uint32_t n = min(*p.refine_count, (uint32_t)((size_t)p.V * p.H * p.W));
+  for (uint32_t e = blockIdx.x * kThreads + threadIdx.x; e < n; e += gridDim.x * kThreads) {
+    const uint32_t pix = p.refine_list[e];
+    const int v = (int)(pix / ((uint32_t)p.H * p.W));
+    const uint32_t r = pix - (uint32_t)v * p.H * p.W;
+    const int y = (int)(r / p.W), x = (int)(r - (uint32_t)y * p.W);
+    float ro[3], d[3];
+    load_ray(p.src, v, x, y, ro, d);
+    const float* rb = kPerRayBins ? p.ray_bins + (size_t)pix * (size_t)(p.S + 1) : nullptr;
+    float cum_dd = 0.f, cumw = 0.f, depth = 0.f, last_mid = 0.f;
+    bool found = false;
+    for (int i = 0; i < p.S && !found; ++i) {
+      const float t0 = kPerRayBins ? __ldg(rb + i) : sbins[i];
+      const float t1 = kPerRayBins ? __ldg(rb + i + 1) : sbins[i + 1];
+      const float mid = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+      float px, py, pz;
+      const bool sel = contract_to_unit(__fadd_rn(ro[0], __fmul_rn(d[0], mid)), __fadd_rn(ro[1], __fmul_rn(d[1], mid)),
+                                        __fadd_rn(ro[2], __fmul_rn(d[2], mid)), px, py, pz);
+      float sigma = 0.f;
+      if (sel) {
+        float feat[32];
+#pragma unroll
+        for (int l = 0; l < 16; ++l) {
+          float2 f = encode_level(p.grid.table + (size_t)l * p.grid.size, p.grid.mask, p.grid.res[l], px, py, pz);
+          feat[2 * l] = f.x;
+          feat[2 * l + 1] = f.y;
+        }
+        float logit = sw->b1;
+        for (int nn = 0; nn < 64; ++nn) {
+          float a = sw->b0[nn];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) a = fmaf(sw->w0[nn * 32 + k], feat[k], a);
+          logit = fmaf(sw->w1[nn], fmaxf(a, 0.f), logit);
+        }
+        sigma = sw->avg * expf(logit);
+      }
+      const float dd = __fsub_rn(t1, t0) * sigma;
+      float w = (1.f - expf(-dd)) * expf(-cum_dd);
+      cum_dd += dd;
+      if (w != w) w = 0.f;
+      cumw += w;
+      if (cumw >= 0.5f) {
+        found = true;
+        depth = mid;
+      }
+      last_mid = mid;
+    }
+    if (!found) {   // the loop ran to the end: DepthRenderer clamps the index to the last sample
+      const float t0 = kPerRayBins ? __ldg(rb + p.S - 1) : sbins[p.S - 1];
+      const float t1 = kPerRayBins ? __ldg(rb + p.S) : sbins[p.S];
+      last_mid = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+    }
+    p.depth[pix] = found ? depth : last_mid;
   }
 }
 
@@ -346,6 +440,8 @@ void host_flat_bins(int S, float near_p, float far_p, std::vector<float>& out) {
 }
 
 int g_render_ctas_per_sm = 4;  // sgn_set_option "render_ctas_per_sm": 1 leaves the SM mostly free for a co-resident kernel
+int g_refine_depth = 1;        // sgn_set_option "render_refine_depth": fp32 re-march of near-tie median picks (fp16-MMA path)
+float g_refine_delta = 1e-3f;  // sgn_set_option "render_refine_delta_ppm": margin below which a ray is re-marched
 
 size_t mma_smem_bytes(int S, bool per_ray) {
   return sizeof(MlpPack) + kWarps * 32 * kStageStride * sizeof(__half) + 16 + (per_ray ? 0 : (size_t)(S + 1) * 4);
@@ -375,9 +471,23 @@ int launch_render(const SgnField* f, const RaySource& src, int V, int H, int W, 
   p.tiles_y = (H + th - 1) / th;
   p.num_tiles = V * p.tiles_x * p.tiles_y;
   p.rgb = d_rgb; p.depth = d_depth; p.acc = d_acc;
+  p.refine_list = nullptr; p.refine_count = nullptr; p.refine_delta = 0.f;
   const bool per_ray = d_ray_bins != nullptr;
   const int blocks_needed = (p.num_tiles + kWarps - 1) / kWarps;
   if (mlp_mode == SGN_MLP_FP16_MMA) {
+    uint32_t* d_list = nullptr;
+    const size_t npix = (size_t)V * H * W;
+    if (g_refine_depth && npix < ((size_t)1 << 32)) {
+      SGN_CUDA(scratch_alloc(&d_list, (npix + 1) * sizeof(uint32_t), st));
+      SGN_CUDA(cudaMemsetAsync(d_list, 0, sizeof(uint32_t), st));
+      p.refine_count = d_list;
+      p.refine_list = d_list + 1;
+      p.refine_delta = g_refine_delta;
+    }
+    struct FreeList {
+      uint32_t* q; cudaStream_t s;
+      ~FreeList() { if (q) cudaFreeAsync(q, s); }
+    } free_list{d_list, st};
     size_t smem = mma_smem_bytes(S, per_ray);
     int grid = std::min(blocks_needed, sm_count() * g_render_ctas_per_sm);
     if (per_ray) {
@@ -388,6 +498,20 @@ int launch_render(const SgnField* f, const RaySource& src, int V, int H, int W, 
       int rc = set_smem(k_render_mma<false>, smem);
       if (rc) return rc;
       k_render_mma<false><<<grid, kThreads, smem, st>>>(p);
+    }
+    if (d_list) {
+      SGN_LAUNCH_CHECK();
+      const size_t rsmem = sizeof(DensityF32) + (per_ray ? 0 : (size_t)(S + 1) * 4);
+      const int rgrid = std::min((int)((npix + kThreads - 1) / kThreads), sm_count() * 8);
+      if (per_ray) {
+        int rc = set_smem(k_refine_depth<true>, rsmem);
+        if (rc) return rc;
+        k_refine_depth<true><<<rgrid, kThreads, rsmem, st>>>(p);
+      } else {
+        int rc = set_smem(k_refine_depth<false>, rsmem);
+        if (rc) return rc;
+        k_refine_depth<false><<<rgrid, kThreads, rsmem, st>>>(p);
+      }
     }
   } else {
     size_t smem = f32_smem_bytes(S, per_ray);
@@ -429,7 +553,7 @@ static int render_from(const SgnField* f, const RaySource& src, int V, int H, in
     hb = bins.data();
   }
   float* d_bins = nullptr;
-  SGN_CUDA(cudaMallocAsync(&d_bins, (size_t)(S + 1) * 4, st));
+  SGN_CUDA(scratch_alloc(&d_bins, (size_t)(S + 1) * 4, st));
   SGN_CUDA(cudaMemcpyAsync(d_bins, hb, (size_t)(S + 1) * 4, cudaMemcpyHostToDevice, st));
   // the pageable source must stay alive until the copy is consumed: it is staged synchronously by the
   // runtime for pageable memory, so `bins` may go out of scope after this call returns.
@@ -572,13 +696,23 @@ extern "C" int sgn_set_option(const char* name, int value) {
     sgn::g_render_ctas_per_sm = value;
     return SGN_OK;
   }
+  if (n == "render_refine_depth") {
+    SGN_CHECK_ARG(value == 0 || value == 1, "render_refine_depth must be 0 or 1");
+    sgn::g_refine_depth = value;
+    return SGN_OK;
+  }
+  if (n == "render_refine_delta_ppm") {
+    SGN_CHECK_ARG(value >= 0 && value <= 500000, "render_refine_delta_ppm must be 0..500000");
+    sgn::g_refine_delta = (float)value * 1e-6f;
+    return SGN_OK;
+  }
   if (n == "gemm_pair_stages") {
     SGN_CHECK_ARG(value == 5 || value == 6, "gemm_pair_stages must be 5 or 6");
     sgn::g_pair_stages = value;
     return SGN_OK;
   }
   if (n == "attn_variant") {
-    SGN_CHECK_ARG(value >= 0 && value <= 1, "attn_variant must be 0 or 1");
+    SGN_CHECK_ARG(value >= 0 && value <= 9, "attn_variant must be 0..9");
     sgn::g_attn_variant = value;
     return SGN_OK;
   }

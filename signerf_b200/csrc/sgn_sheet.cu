@@ -204,7 +204,7 @@ static int dilate_impl(const uint8_t* d_in, int V, int H, int W, int kw, int kh,
     return SGN_ERR_INVALID_ARG;
   }
   int* pre = nullptr;
-  SGN_CUDA(cudaMallocAsync(&pre, (size_t)V * H * (W + 1) * sizeof(int), st));
+  SGN_CUDA(scratch_alloc(&pre, (size_t)V * H * (W + 1) * sizeof(int), st));
   k_row_prefix<<<grid_for((size_t)V * H * 32, 256), 256, 0, st>>>(d_in, V * H, W, pre);
   SGN_LAUNCH_CHECK();
   k_dilate_runs<<<grid_for((size_t)V * H * W, 256), 256, 0, st>>>(pre, V, H, W, se, d_out);
@@ -331,8 +331,8 @@ static int mask_condition_impl(const float* d_c2w, const float* d_intr, int V, i
   ViewStats* stats = nullptr;
   uint8_t* vis = nullptr;
   const bool dil = o->dilate_w > 0;
-  SGN_CUDA(cudaMallocAsync(&stats, sizeof(ViewStats) * V, st));
-  if (dil) SGN_CUDA(cudaMallocAsync(&vis, (size_t)V * npix, st));
+  SGN_CUDA(scratch_alloc(&stats, sizeof(ViewStats) * V, st));
+  if (dil) SGN_CUDA(scratch_alloc(&vis, (size_t)V * npix, st));
   k_stats_init<<<(V + 127) / 128, 128, 0, st>>>(stats, V);
   SGN_LAUNCH_CHECK();
   int bpv = std::max(1, std::min((int)((npix + 255) / 256), std::max(1, nsm() * 8 / V)));

@@ -68,3 +68,30 @@ def camera_ring(n: int, width: int, height: int, radius: float = 0.5, theta_deg:
     c2w[:, :, 0], c2w[:, :, 1], c2w[:, :, 2], c2w[:, :, 3] = x, y, z, pos
     intr = torch.tensor([[float(width), float(width), width / 2.0, height / 2.0]]).repeat(n, 1)
     return c2w, intr
+
+
+def proxy_mesh(num_faces: int = 4968, bump: float = 0.15) -> Tuple[np.ndarray, np.ndarray]:
+    """A closed, bumpy unit-sphere-like proxy with about `num_faces` triangles (vertices [Nv,3] fp32, faces [Nf,3] int32,
+    outward winding) standing in for the reference's models/bunny.obj (4 968 faces) where that file is not available."""
+    n_lon = max(8, int(round(math.sqrt(num_faces / 2.0 * 54.0 / 46.0))))
+    n_lat = max(3, int(round(num_faces / (2.0 * n_lon))) + 1)
+    verts = [(0.0, 0.0, 1.0)]
+    for i in range(1, n_lat):
+        th = math.pi * i / n_lat
+        for j in range(n_lon):
+            ph = 2.0 * math.pi * j / n_lon
+            r = 1.0 + bump * math.sin(3.0 * th) * math.cos(4.0 * ph)
+            verts.append((r * math.sin(th) * math.cos(ph), r * math.sin(th) * math.sin(ph), r * math.cos(th)))
+    verts.append((0.0, 0.0, -1.0))
+    south = len(verts) - 1
+    ring = lambda i, j: 1 + (i - 1) * n_lon + (j % n_lon)  # noqa: E731
+    faces = []
+    for j in range(n_lon):
+        faces.append((0, ring(1, j), ring(1, j + 1)))
+        faces.append((south, ring(n_lat - 1, j + 1), ring(n_lat - 1, j)))
+    for i in range(1, n_lat - 1):
+        for j in range(n_lon):
+            a, b, c, d = ring(i, j), ring(i, j + 1), ring(i + 1, j), ring(i + 1, j + 1)
+            faces.append((a, c, d))
+            faces.append((a, d, b))
+    return np.asarray(verts, np.float32), np.asarray(faces, np.int32)
