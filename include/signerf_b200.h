@@ -384,6 +384,43 @@ int sgn_shape_color_u8(const float* d_depth, int64_t npix, const uint8_t* h_fg_r
 int sgn_mask_condition_shape(const float* d_proxy_depth, const float* d_depth, int V, int H, int W, const SgnMaskOpts* o,
                              uint8_t* d_mask, float* d_cond, float* d_stats, void* stream);
 
+/* ------------------------------------------------------------------ the NeRF fine-tune step
+ * `SIGNeRFModel` trains with nerfacto's forward and `get_loss_dict` (signerf/signerf.py:41-82) between two dataset
+ * generations.  These entry points are the main field's forward + backward on a batch of rays, the image loss and the
+ * optimizer update, fp32 end to end (gradients = torch autograd through nerfstudio's torch modules).
+ *
+ * Parameters: the hash table stays the caller's tensor (SgnHashGrid.d_table, updated in place by sgn_adam_step); the MLPs
+ * live in the field's fp32 parameter block of sgn_mlp_param_count() floats, layout (row-major [out][in], nn.Linear):
+ *   w_base0[64*32] w_base1[16*64] w_head0[64*32] w_head1[64*64] w_head2[3*64] b_base0[64] b_base1[16] b_head0[64]
+ *   b_head1[64] b_head2[4] avg_density pad[3]
+ * w_head0's 32 input columns are [SH 16 | unused | geo 15]; b_head0 carries the mean appearance embedding folded in
+ * (b + W_app . mean(embedding)), as the eval renderer uses it.  Gradient buffers use the same layouts and are ACCUMULATED
+ * into (zero them per step). */
+int64_t sgn_mlp_param_count(void);
+int sgn_field_mlp_params(const SgnField* f, float** d_params);
+/* Re-derives the fp16 tensor-core fragments (and the feature scale) the renderer uses from the fp32 parameter block and
+ * the current hash table - call after optimizer steps, before the next sgn_render_*.  Synchronises the stream. */
+int sgn_field_refresh(SgnField* f, void* stream);
+/* Forward of N rays x S samples through the main field: d_bins [S+1] euclidean bin edges shared by all rays, or
+ * d_ray_bins [N,S+1] (exactly one non-NULL).  Outputs: d_sigma [N,S], d_color [N,S,3] (kept by the caller for the backward),
+ * d_rgb [N,3] = sum w c + c_last (1 - sum w) without the eval clamp, d_acc [N] or NULL. */
+int sgn_train_forward(const SgnField* f, const float* d_origins, const float* d_directions, int64_t N, const float* d_bins,
+                      const float* d_ray_bins, int S, float* d_sigma, float* d_color, float* d_rgb, float* d_acc,
+                      void* stream);
+/* Backward: d_grad_rgb [N,3] = dL/drgb -> d_grad_table [L*T,2] and d_grad_mlp [sgn_mlp_param_count()] (+=).
+ * d_ws: sgn_train_ws_bytes(N, S) bytes of 16-byte aligned scratch. */
+int64_t sgn_train_ws_bytes(int64_t N, int S);
+int sgn_train_backward(const SgnField* f, const float* d_origins, const float* d_directions, int64_t N, const float* d_bins,
+                       const float* d_ray_bins, int S, const float* d_sigma, const float* d_color, const float* d_grad_rgb,
+                       float* d_grad_table, float* d_grad_mlp, void* d_ws, int64_t ws_bytes, void* stream);
+/* `rgb_loss` of signerf/signerf.py:36-47: nerfstudio L1Loss (l1 = 1) or MSELoss (l1 = 0) = mean over all n elements;
+ * d_loss [1]; d_grad [n] = d loss / d pred, or NULL. */
+int sgn_rgb_loss(const float* d_pred, const float* d_target, int64_t n, int l1, float* d_loss, float* d_grad, void* stream);
+/* torch.optim.Adam as nerfstudio's AdamOptimizerConfig sets it up (signerf_config.py:43-50: lr 1e-2, eps 1e-15, betas
+ * 0.9 / 0.999, no weight decay); `step` counts from 1. */
+int sgn_adam_step(float* d_param, const float* d_grad, float* d_m, float* d_v, int64_t n, float lr, float beta1, float beta2,
+                  float eps, int step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

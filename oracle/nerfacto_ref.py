@@ -471,3 +471,39 @@ def make_model(seed: int = 0, dense: bool = False, table_scale: Optional[float] 
             for p in model.proposal_networks:
                 p.mlp.layers[-1].bias[0] = 6.0
     return model.eval()
+
+
+# --------------------------------------------------------------------------- training step
+def render_rays_train(model: NerfactoRef, rays_o: Tensor, rays_d: Tensor, num_samples: int) -> Tensor:
+    """NerfactoModel.get_outputs WHILE TRAINING, restricted to what signerf_b200/train.py covers: the main field on the
+    flat piecewise bins, autograd enabled.  RGBRenderer only applies nan_to_num / clamp when `not self.training`, so rgb is
+    the raw composite.  -> rgb [N,3] with a graph back to hash table and MLP parameters."""
+    n = rays_o.shape[0]
+    nears = torch.ones_like(rays_o[..., 0:1]) * model.near
+    fars = torch.ones_like(rays_o[..., 0:1]) * model.far
+    samples = initial_samples(n, num_samples, make_to_euclid(nears, fars))
+    positions = positions_of(rays_o, rays_d, samples)
+    density, geo = model.field.get_density(positions)
+    dirs = rays_d[:, None, :].expand(-1, positions.shape[1], -1)
+    rgb = model.field.get_rgb(dirs, geo)
+    weights = get_weights(samples, density)
+    comp = torch.sum(weights * rgb, dim=-2)
+    return comp + rgb[..., -1, :] * (1.0 - torch.sum(weights, dim=-2))
+
+
+def signerf_rgb_loss(pred: Tensor, target: Tensor, use_l1: bool = True) -> Tensor:
+    """signerf/signerf.py:36-47: `self.rgb_loss(image, output)` with nerfstudio's L1Loss = nn.L1Loss / MSELoss = nn.MSELoss."""
+    return torch.nn.functional.l1_loss(target, pred) if use_l1 else torch.nn.functional.mse_loss(target, pred)
+
+
+def patch_sample_method(batch_size: int, num_images: int, image_height: int, image_width: int, patch_size: int,
+                        generator: Optional[torch.Generator] = None) -> Tensor:
+    """signerf/data/signerf_patch_pixel_sampler.py:60-78 (the unmasked branch), with an explicit RNG."""
+    sub_bs = batch_size // (patch_size ** 2)
+    indices = torch.rand((sub_bs, 3), generator=generator) * torch.tensor(
+        [num_images, image_height - patch_size, image_width - patch_size])
+    indices = indices.view(sub_bs, 1, 1, 3).broadcast_to(sub_bs, patch_size, patch_size, 3).clone()
+    yys, xxs = torch.meshgrid(torch.arange(patch_size), torch.arange(patch_size), indexing="ij")
+    indices[:, ..., 1] += yys
+    indices[:, ..., 2] += xxs
+    return torch.floor(indices).long().flatten(0, 2)

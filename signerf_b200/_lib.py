@@ -73,6 +73,14 @@ SIGNATURES = {
     "sgn_field_create": (_i, [C.POINTER(SgnFieldDesc), C.POINTER(_vp)]),
     "sgn_field_destroy": (None, [_vp]),
     "sgn_render_views": (_i, [_vp, _vp, _vp, _i, _i, _i, C.POINTER(SgnRenderOpts), _vp, _vp, _vp, _vp]),
+    "sgn_mlp_param_count": (_i64, []),
+    "sgn_field_mlp_params": (_i, [_vp, C.POINTER(_vp)]),
+    "sgn_field_refresh": (_i, [_vp, _vp]),
+    "sgn_train_forward": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "sgn_train_ws_bytes": (_i64, [_i64, _i]),
+    "sgn_train_backward": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "sgn_rgb_loss": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp]),
+    "sgn_adam_step": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _i, _vp]),
     "sgn_render_rays": (_i, [_vp, _vp, _vp, _i64, C.POINTER(SgnRenderOpts), _vp, _vp, _vp, _vp]),
     "sgn_render_views_host": (_i, [_vp, _vp, _vp, _i, _i, _i, C.POINTER(SgnRenderOpts), _vp, _vp, _vp]),
     "sgn_generate_rays": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),

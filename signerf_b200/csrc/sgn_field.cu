@@ -76,6 +76,54 @@ static int fill_grid(const SgnHashGrid& g, GridDev* out, const char* name) {
   return SGN_OK;
 }
 
+// fp16 tensor-core fragments of the fp32 parameter block (kernel order: w_head0 columns [SH16 | slot | geo15], folded bias)
+static void pack_from_f32(const MlpF32& Q, float feat_scale, MlpPack& P) {
+  memset(&P, 0, sizeof(P));
+  pack_b_pairs(P.w_base0, 64, 32, [&](int n, int k) { return Q.w_base0[n * 32 + k]; });
+  pack_b_pairs(P.w_base1, 16, 64, [&](int n, int k) { return Q.w_base1[n * 64 + k]; });
+  pack_b_pairs(P.w_head0, 64, 32, [&](int n, int k) { return Q.w_head0[n * 32 + k]; });
+  pack_b_pairs(P.w_head1, 64, 64, [&](int n, int k) { return Q.w_head1[n * 64 + k]; });
+  pack_b_n8(P.w_head2, 64, [&](int n, int k) { return n < 3 ? Q.w_head2[n * 64 + k] : 0.f; });
+  memcpy(P.b_base0, Q.b_base0, sizeof(P.b_base0));
+  memcpy(P.b_base1, Q.b_base1, sizeof(P.b_base1));
+  memcpy(P.b_head0, Q.b_head0, sizeof(P.b_head0));
+  memcpy(P.b_head1, Q.b_head1, sizeof(P.b_head1));
+  for (int n = 0; n < 3; ++n) P.b_head2[n] = Q.b_head2[n];
+  P.feat_scale = feat_scale;
+  P.inv_feat_scale = 1.f / feat_scale;
+  P.avg_density = Q.avg_density;
+}
+
+// power of two that maps max|table| into fp16's comfortable range; synchronises `st`
+static int table_feat_scale(const GridDev& g, cudaStream_t st, float* out) {
+  unsigned int* d_max = nullptr;
+  const size_t n = (size_t)g.num_levels * g.size * 2;
+  SGN_CUDA(cudaMalloc(&d_max, 4));
+  cudaMemsetAsync(d_max, 0, 4, st);
+  k_max_abs<<<296, 256, 0, st>>>(reinterpret_cast<const float*>(g.table), n, d_max);
+  count_launch();
+  unsigned int bits = 0;
+  cudaError_t e = cudaMemcpyAsync(&bits, d_max, 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_max);
+  if (e != cudaSuccess) {
+    set_error(std::string("hash-table scan failed: ") + cudaGetErrorString(e));
+    return SGN_ERR_CUDA;
+  }
+  float maxabs;
+  memcpy(&maxabs, &bits, 4);
+  float scale = 1.f;
+  if (maxabs > 0.f && std::isfinite(maxabs)) {
+    int ex = (int)std::ceil(std::log2((double)maxabs));
+    int sh = 14 - ex;
+    if (sh > 60) sh = 60;
+    if (sh < -60) sh = -60;
+    scale = std::ldexp(1.f, sh);
+  }
+  *out = scale;
+  return SGN_OK;
+}
+
 static bool lin_is(const SgnLinear& l, int in, int out) {
   return l.h_weight && l.h_bias && l.in_dim == in && l.out_dim == out;
 }
@@ -112,40 +160,15 @@ extern "C" int sgn_field_create(const SgnFieldDesc* d, SgnField** out) {
   int rc = fill_grid(d->grid, &f->grid, "grid");
   if (rc != SGN_OK) { delete f; return rc; }
 
-  // ---- feature scale: power of two that maps max|table| into fp16's comfortable range
-  unsigned int* d_max = nullptr;
-  float maxabs = 0.f;
-  {
-    size_t n = (size_t)f->grid.num_levels * f->grid.size * 2;
-    if (cudaMalloc(&d_max, 4) != cudaSuccess) { delete f; set_error("cudaMalloc failed"); return SGN_ERR_CUDA; }
-    cudaMemset(d_max, 0, 4);
-    k_max_abs<<<296, 256>>>(d->grid.d_table, n, d_max);
-    count_launch();
-    unsigned int bits = 0;
-    cudaError_t e = cudaMemcpy(&bits, d_max, 4, cudaMemcpyDeviceToHost);
-    cudaFree(d_max);
-    if (e != cudaSuccess) {
-      delete f;
-      set_error(std::string("hash-table scan failed: ") + cudaGetErrorString(e));
-      return SGN_ERR_CUDA;
-    }
-    memcpy(&maxabs, &bits, 4);
-  }
   float feat_scale = 1.f;
-  if (maxabs > 0.f && std::isfinite(maxabs)) {
-    int e = (int)std::ceil(std::log2((double)maxabs));
-    int s = 14 - e;
-    if (s > 60) s = 60;
-    if (s < -60) s = -60;
-    feat_scale = std::ldexp(1.f, s);
-  }
+  rc = table_feat_scale(f->grid, 0, &feat_scale);
+  if (rc != SGN_OK) { delete f; return rc; }
 
   // ---- pack MLPs
   std::vector<MlpPack> packv(1);
   std::vector<MlpF32> f32v(1);
   MlpPack& P = packv[0];
   MlpF32& Q = f32v[0];
-  memset(&P, 0, sizeof(P));
   memset(&Q, 0, sizeof(Q));
   const float* B0 = d->base[0].h_weight;
   const float* B1 = d->base[1].h_weight;
@@ -158,17 +181,12 @@ extern "C" int sgn_field_create(const SgnFieldDesc* d, SgnField** out) {
     if (k == 16) return 0.f;
     return H0[n * 63 + 15 + (k - 16)];
   };
-  pack_b_pairs(P.w_base0, 64, 32, [&](int n, int k) { return B0[n * 32 + k]; });
-  pack_b_pairs(P.w_base1, 16, 64, [&](int n, int k) { return B1[n * 64 + k]; });
-  pack_b_pairs(P.w_head0, 64, 32, h0);
-  pack_b_pairs(P.w_head1, 64, 64, [&](int n, int k) { return H1[n * 64 + k]; });
-  pack_b_n8(P.w_head2, 64, [&](int n, int k) { return n < 3 ? H2[n * 64 + k] : 0.f; });
   for (int n = 0; n < 64; ++n) {
     double acc = d->head[0].h_bias[n];
     for (int a = 0; a < 32; ++a) acc += (double)H0[n * 63 + 31 + a] * (double)d->h_appearance[a];
-    P.b_head0[n] = Q.b_head0[n] = (float)acc;
-    P.b_base0[n] = Q.b_base0[n] = d->base[0].h_bias[n];
-    P.b_head1[n] = Q.b_head1[n] = d->head[1].h_bias[n];
+    Q.b_head0[n] = (float)acc;
+    Q.b_base0[n] = d->base[0].h_bias[n];
+    Q.b_head1[n] = d->head[1].h_bias[n];
     for (int k = 0; k < 32; ++k) {
       Q.w_base0[n * 32 + k] = B0[n * 32 + k];
       Q.w_head0[n * 32 + k] = h0(n, k);
@@ -176,16 +194,15 @@ extern "C" int sgn_field_create(const SgnFieldDesc* d, SgnField** out) {
     for (int k = 0; k < 64; ++k) Q.w_head1[n * 64 + k] = H1[n * 64 + k];
   }
   for (int n = 0; n < 16; ++n) {
-    P.b_base1[n] = Q.b_base1[n] = d->base[1].h_bias[n];
+    Q.b_base1[n] = d->base[1].h_bias[n];
     for (int k = 0; k < 64; ++k) Q.w_base1[n * 64 + k] = B1[n * 64 + k];
   }
   for (int n = 0; n < 3; ++n) {
-    P.b_head2[n] = Q.b_head2[n] = d->head[2].h_bias[n];
+    Q.b_head2[n] = d->head[2].h_bias[n];
     for (int k = 0; k < 64; ++k) Q.w_head2[n * 64 + k] = H2[n * 64 + k];
   }
-  P.feat_scale = feat_scale;
-  P.inv_feat_scale = 1.f / feat_scale;
-  P.avg_density = Q.avg_density = d->average_init_density;
+  Q.avg_density = d->average_init_density;
+  pack_from_f32(Q, feat_scale, P);
 
   auto fail = [&](const char* what) {
     set_error(std::string(what) + ": " + cudaGetErrorString(cudaGetLastError()));
@@ -217,6 +234,22 @@ extern "C" int sgn_field_create(const SgnFieldDesc* d, SgnField** out) {
     if (cudaMemcpy(f->d_prop[i], &pd, sizeof(pd), cudaMemcpyHostToDevice) != cudaSuccess) return fail("upload prop");
   }
   *out = f;
+  return SGN_OK;
+}
+
+extern "C" int sgn_field_refresh(SgnField* f, void* stream) {
+  SGN_CHECK_ARG(f != nullptr, "null field");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  float feat_scale = 1.f;
+  int rc = table_feat_scale(f->grid, st, &feat_scale);
+  if (rc != SGN_OK) return rc;
+  std::vector<MlpF32> q(1);
+  std::vector<MlpPack> p(1);
+  SGN_CUDA(cudaMemcpyAsync(q.data(), f->d_f32, sizeof(MlpF32), cudaMemcpyDeviceToHost, st));
+  SGN_CUDA(cudaStreamSynchronize(st));
+  pack_from_f32(q[0], feat_scale, p[0]);
+  SGN_CUDA(cudaMemcpyAsync(f->d_pack, p.data(), sizeof(MlpPack), cudaMemcpyHostToDevice, st));
+  SGN_CUDA(cudaStreamSynchronize(st));
   return SGN_OK;
 }
 

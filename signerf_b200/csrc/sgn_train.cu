@@ -1,0 +1,490 @@
+// SURVEY §8(f) row 4 - the NeRF fine-tune step that alternates with dataset generation (BASELINE config 5's
+// "refinement rounds"): forward + BACKWARD of the main nerfacto field on a batch of rays, the SIGNeRF image loss
+// (reference signerf/signerf.py:41-52: L1Loss or MSELoss on rgb) and the Adam update nerfstudio configures for the
+// `fields` parameter group (signerf_config.py:43-50).
+//
+// The batch of a training step is small next to a reference-sheet render (16 patches of 32 x 32 rays x 48 samples =
+// 0.8 M samples against 537 M), so this path is organised for exactness and simplicity, fp32 end to end on CUDA cores:
+//   k_train_field      one thread per SAMPLE: hash features -> base / head MLP -> sigma, colour (kept for the backward)
+//   k_train_composite  one thread per RAY: weights, rgb = sum w c + c_last (1 - sum w)  (training: no clamp)
+//   k_train_ray_bwd    one thread per RAY: dL/dsigma_i, dL/dc_i from dL/drgb with the suffix sums of the transmittance
+//   k_train_field_bwd  one thread per SAMPLE: recomputes the activations, back-propagates to the hash features
+//                      (scatter-add into the table gradient, fp32 vector atomics) and writes the layer deltas /
+//                      activations the weight gradients are outer products of
+//   k_outer_reduce     dW[n][k] = sum_samples delta[n] * act[k]: skinny GEMM (<= 64 x 64 outputs, the sample axis is the
+//                      reduction), 64 x 64 register tile per CTA, one atomicAdd per output per CTA
+// Gradients follow torch autograd through nerfstudio's torch modules: trunc_exp's backward clamps its argument at 15,
+// ReLU' = (h > 0), the selector multiplies the density only.  The appearance embedding enters as the folded bias of head
+// layer 0 (eval semantics: mean embedding), i.e. it is a constant of the step.
+#include <algorithm>
+
+#include "sgn_device.cuh"
+
+namespace sgn {
+
+constexpr int kDeltaDim = 212;   // [da0 64 | dout1 16 | da1 64 | da2 64 | dpre 3 | pad 1]
+constexpr int kActDim = 256;     // [feat 32 | h0 64 | hin 32 | h1 64 | h2 64]
+
+struct TrainRays {
+  const float* origins;
+  const float* dirs;
+  const float* bins;      // [S+1] shared euclidean edges, or
+  const float* ray_bins;  // [N, S+1] per ray
+  int64_t N;
+  int S;
+};
+
+__device__ __forceinline__ void sample_interval(const TrainRays& r, int64_t ray, int i, float& t0, float& t1) {
+  if (r.ray_bins) {
+    t0 = __ldg(r.ray_bins + ray * (r.S + 1) + i);
+    t1 = __ldg(r.ray_bins + ray * (r.S + 1) + i + 1);
+  } else {
+    t0 = __ldg(r.bins + i);
+    t1 = __ldg(r.bins + i + 1);
+  }
+}
+
+__device__ __forceinline__ bool sample_position(const TrainRays& r, int64_t ray, int i, float& px, float& py, float& pz) {
+  float t0, t1;
+  sample_interval(r, ray, i, t0, t1);
+  const float mid = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+  const float* o = r.origins + 3 * ray;
+  const float* d = r.dirs + 3 * ray;
+  return contract_to_unit(__fadd_rn(__ldg(o), __fmul_rn(__ldg(d), mid)), __fadd_rn(__ldg(o + 1), __fmul_rn(__ldg(d + 1), mid)),
+                          __fadd_rn(__ldg(o + 2), __fmul_rn(__ldg(d + 2), mid)), px, py, pz);
+}
+
+// ---------------------------------------------------------------- forward
+__global__ void __launch_bounds__(128) k_train_field(const GridDev grid, const MlpF32* __restrict__ w32, const TrainRays r,
+                                                     float* __restrict__ sigma, float* __restrict__ color) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  MlpF32* sw = reinterpret_cast<MlpF32*>(smem);
+  for (int i = threadIdx.x; i < (int)(sizeof(MlpF32) / 16); i += blockDim.x)
+    reinterpret_cast<uint4*>(sw)[i] = reinterpret_cast<const uint4*>(w32)[i];
+  __syncthreads();
+  const int64_t total = r.N * r.S;
+  for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < total; s += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t ray = s / r.S;
+    const int i = (int)(s - ray * r.S);
+    float px, py, pz, sh[16], feat[32];
+    const bool sel = sample_position(r, ray, i, px, py, pz);
+    sh16(__ldg(r.dirs + 3 * ray), __ldg(r.dirs + 3 * ray + 1), __ldg(r.dirs + 3 * ray + 2), sh);
+#pragma unroll
+    for (int l = 0; l < 16; ++l) {
+      float2 f = encode_level(grid.table + (size_t)l * grid.size, grid.mask, grid.res[l], px, py, pz);
+      feat[2 * l] = f.x;
+      feat[2 * l + 1] = f.y;
+    }
+    float logit, c3[3];
+    field_mlp_f32(sw, feat, sh, logit, c3);
+    sigma[s] = sel ? sw->avg_density * expf(logit) : 0.f;
+    color[3 * s + 0] = sigmoidf_(c3[0]);
+    color[3 * s + 1] = sigmoidf_(c3[1]);
+    color[3 * s + 2] = sigmoidf_(c3[2]);
+  }
+}
+
+__global__ void k_train_composite(const TrainRays r, const float* __restrict__ sigma, const float* __restrict__ color,
+                                  float* __restrict__ rgb, float* __restrict__ acc_out) {
+  for (int64_t ray = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; ray < r.N; ray += (int64_t)gridDim.x * blockDim.x) {
+    float cum = 0.f, acc = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+    const float* sg = sigma + ray * r.S;
+    const float* cl = color + 3 * ray * r.S;
+    for (int i = 0; i < r.S; ++i) {
+      float t0, t1;
+      sample_interval(r, ray, i, t0, t1);
+      const float dd = __fsub_rn(t1, t0) * sg[i];
+      float w = (1.f - expf(-dd)) * expf(-cum);
+      cum += dd;
+      if (w != w) w = 0.f;
+      cr = fmaf(w, cl[3 * i], cr);
+      cg = fmaf(w, cl[3 * i + 1], cg);
+      cb = fmaf(w, cl[3 * i + 2], cb);
+      acc += w;
+    }
+    const float rem = 1.f - acc;   // RGBRenderer("last_sample"); no clamp while training
+    rgb[3 * ray + 0] = fmaf(cl[3 * (r.S - 1)], rem, cr);
+    rgb[3 * ray + 1] = fmaf(cl[3 * (r.S - 1) + 1], rem, cg);
+    rgb[3 * ray + 2] = fmaf(cl[3 * (r.S - 1) + 2], rem, cb);
+    if (acc_out) acc_out[ray] = acc;
+  }
+}
+
+// ---------------------------------------------------------------- backward, ray level
+// C = sum_i w_i (c_i - c_L) + c_L with L the last sample, w_i = (1 - e^{-dd_i}) e^{-sum_{j<i} dd_j}, dd_i = delta_i sigma_i:
+//   dL/dc_i  = g w_i (+ g (1 - sum w) for i = L)
+//   dL/ddd_k = G_k T_k e^{-dd_k} - sum_{i>k} G_i w_i,   G_i = g . (c_i - c_L)
+__global__ void k_train_ray_bwd(const TrainRays r, const float* __restrict__ sigma, const float* __restrict__ color,
+                                const float* __restrict__ grad_rgb, float* __restrict__ gsigma, float* __restrict__ gcolor) {
+  for (int64_t ray = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; ray < r.N; ray += (int64_t)gridDim.x * blockDim.x) {
+    const float* sg = sigma + ray * r.S;
+    const float* cl = color + 3 * ray * r.S;
+    float* gs = gsigma + ray * r.S;
+    float* gc = gcolor + 3 * ray * r.S;
+    const float g0 = grad_rgb[3 * ray], g1 = grad_rgb[3 * ray + 1], g2 = grad_rgb[3 * ray + 2];
+    const float l0 = cl[3 * (r.S - 1)], l1 = cl[3 * (r.S - 1) + 1], l2 = cl[3 * (r.S - 1) + 2];
+    // pass 1: weights (kept in gs as scratch) and their sum
+    float cum = 0.f, acc = 0.f;
+    for (int i = 0; i < r.S; ++i) {
+      float t0, t1;
+      sample_interval(r, ray, i, t0, t1);
+      const float dd = __fsub_rn(t1, t0) * sg[i];
+      float w = (1.f - expf(-dd)) * expf(-cum);
+      cum += dd;
+      if (w != w) w = 0.f;
+      gs[i] = w;
+      gc[3 * i] = expf(-cum);   // transmittance behind sample i (scratch; rewritten below)
+      acc += w;
+    }
+    // pass 2, back to front: suffix sum of G_i w_i; T_k e^{-dd_k} = transmittance behind sample k
+    float suffix = 0.f;
+    for (int i = r.S - 1; i >= 0; --i) {
+      float t0, t1;
+      sample_interval(r, ray, i, t0, t1);
+      const float delta = __fsub_rn(t1, t0);
+      const float w = gs[i];
+      const float G = g0 * (cl[3 * i] - l0) + g1 * (cl[3 * i + 1] - l1) + g2 * (cl[3 * i + 2] - l2);
+      const float t_after = gc[3 * i];
+      gs[i] = delta * (G * t_after - suffix);
+      suffix += G * w;
+      const float wc = (i == r.S - 1) ? w + (1.f - acc) : w;
+      gc[3 * i] = g0 * wc;
+      gc[3 * i + 1] = g1 * wc;
+      gc[3 * i + 2] = g2 * wc;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- backward, sample level
+struct FieldBwd {
+  GridDev grid;
+  const MlpF32* w32;
+  TrainRays rays;
+  const float* gsigma;
+  const float* gcolor;
+  float* grad_table;   // [L * T, 2], accumulated
+  float* deltas;       // [kDeltaDim, cap]: one row per delta component, samples of the chunk along the row, so that the
+  float* acts;         // [kActDim, cap]    per-thread "arrays" below are coalesced across the warp
+  int64_t first, count;   // samples [first, first + count) of the batch
+  int64_t cap;            // row length of deltas / acts
+};
+
+__global__ void __launch_bounds__(128) k_train_field_bwd(const __grid_constant__ FieldBwd p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  MlpF32* w = reinterpret_cast<MlpF32*>(smem);
+  for (int i = threadIdx.x; i < (int)(sizeof(MlpF32) / 16); i += blockDim.x)
+    reinterpret_cast<uint4*>(w)[i] = reinterpret_cast<const uint4*>(p.w32)[i];
+  __syncthreads();
+  const TrainRays& r = p.rays;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < p.count; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = p.first + e;
+    const int64_t ray = s / r.S;
+    const int i = (int)(s - ray * r.S);
+    // strided views: X(i) is element i of this thread's vector
+    auto col = [&](float* base, int off) { return base + (size_t)off * p.cap + e; };
+#define SGN_AT(ptr, i) (ptr)[(size_t)(i) * p.cap]
+    float px, py, pz, sh[16];
+    const bool sel = sample_position(r, ray, i, px, py, pz);
+    sh16(__ldg(r.dirs + 3 * ray), __ldg(r.dirs + 3 * ray + 1), __ldg(r.dirs + 3 * ray + 2), sh);
+    // ---- forward with the activations written to A (they are read back below: L1 / L2 resident)
+    float* feat = col(p.acts, 0);
+    float* h0 = col(p.acts, 32);
+    float* hin = col(p.acts, 96);
+    float* h1 = col(p.acts, 128);
+    float* h2 = col(p.acts, 192);
+#pragma unroll
+    for (int l = 0; l < 16; ++l) {
+      float2 f = encode_level(p.grid.table + (size_t)l * p.grid.size, p.grid.mask, p.grid.res[l], px, py, pz);
+      SGN_AT(feat, 2 * l) = f.x;
+      SGN_AT(feat, 2 * l + 1) = f.y;
+    }
+    for (int n = 0; n < 64; ++n) {
+      float a = w->b_base0[n];
+      for (int k = 0; k < 32; ++k) a = fmaf(w->w_base0[n * 32 + k], SGN_AT(feat, k), a);
+      SGN_AT(h0, n) = fmaxf(a, 0.f);
+    }
+    for (int k = 0; k < 16; ++k) SGN_AT(hin, k) = sh[k];
+    float logit = 0.f;
+    for (int n = 0; n < 16; ++n) {
+      float a = w->b_base1[n];
+      for (int k = 0; k < 64; ++k) a = fmaf(w->w_base1[n * 64 + k], SGN_AT(h0, k), a);
+      if (n == 0) logit = a;
+      SGN_AT(hin, 16 + n) = n == 0 ? 0.f : a;
+    }
+    for (int n = 0; n < 64; ++n) {
+      float a = w->b_head0[n];
+      for (int k = 0; k < 32; ++k) a = fmaf(w->w_head0[n * 32 + k], SGN_AT(hin, k), a);
+      SGN_AT(h1, n) = fmaxf(a, 0.f);
+    }
+    for (int n = 0; n < 64; ++n) {
+      float a = w->b_head1[n];
+      for (int k = 0; k < 64; ++k) a = fmaf(w->w_head1[n * 64 + k], SGN_AT(h1, k), a);
+      SGN_AT(h2, n) = fmaxf(a, 0.f);
+    }
+    float dpre[3];
+    for (int c = 0; c < 3; ++c) {
+      float a = w->b_head2[c];
+      for (int k = 0; k < 64; ++k) a = fmaf(w->w_head2[c * 64 + k], SGN_AT(h2, k), a);
+      const float cl = sigmoidf_(a);
+      dpre[c] = p.gcolor[3 * s + c] * cl * (1.f - cl);
+    }
+    // ---- backward
+    float* da0 = col(p.deltas, 0);
+    float* dout1 = col(p.deltas, 64);
+    float* da1 = col(p.deltas, 80);
+    float* da2 = col(p.deltas, 144);
+    float* dp = col(p.deltas, 208);
+    SGN_AT(dp, 0) = dpre[0]; SGN_AT(dp, 1) = dpre[1]; SGN_AT(dp, 2) = dpre[2]; SGN_AT(dp, 3) = 0.f;
+    for (int k = 0; k < 64; ++k) {
+      const float g = w->w_head2[k] * dpre[0] + w->w_head2[64 + k] * dpre[1] + w->w_head2[128 + k] * dpre[2];
+      SGN_AT(da2, k) = SGN_AT(h2, k) > 0.f ? g : 0.f;
+    }
+    for (int k = 0; k < 64; ++k) {
+      float g = 0.f;
+      for (int n = 0; n < 64; ++n) g = fmaf(w->w_head1[n * 64 + k], SGN_AT(da2, n), g);
+      SGN_AT(da1, k) = SGN_AT(h1, k) > 0.f ? g : 0.f;
+    }
+    // trunc_exp backward: d exp(x) = exp(clamp(x, max = 15)); the selector multiplies the density only
+    SGN_AT(dout1, 0) = sel ? p.gsigma[s] * w->avg_density * expf(fminf(logit, 15.f)) : 0.f;
+    for (int n = 1; n < 16; ++n) {
+      float g = 0.f;
+      for (int m = 0; m < 64; ++m) g = fmaf(w->w_head0[m * 32 + 16 + n], SGN_AT(da1, m), g);
+      SGN_AT(dout1, n) = g;
+    }
+    for (int k = 0; k < 64; ++k) {
+      float g = 0.f;
+      for (int n = 0; n < 16; ++n) g = fmaf(w->w_base1[n * 64 + k], SGN_AT(dout1, n), g);
+      SGN_AT(da0, k) = SGN_AT(h0, k) > 0.f ? g : 0.f;
+    }
+    // ---- hash features: scatter-add into the table gradient
+#pragma unroll 1
+    for (int l = 0; l < 16; ++l) {
+      float g0 = 0.f, g1 = 0.f;
+      for (int n = 0; n < 64; ++n) {
+        const float dn = SGN_AT(da0, n);
+        g0 = fmaf(w->w_base0[n * 32 + 2 * l], dn, g0);
+        g1 = fmaf(w->w_base0[n * 32 + 2 * l + 1], dn, g1);
+      }
+      const LevelCoords L = level_coords(p.grid.res[l], px, py, pz);
+      uint32_t idx[8];
+      corner_rows(L, p.grid.mask, idx);
+      const float mx = 1.f - L.ox, my = 1.f - L.oy, mz = 1.f - L.oz;
+      // corner order of HashEncoding.pytorch_fwd: 0 ccc, 1 cfc, 2 ffc, 3 fcc, 4 ccf, 5 cff, 6 fff, 7 fcf (x, y, z)
+      const float wt[8] = {L.ox * L.oy * L.oz, L.ox * my * L.oz, mx * my * L.oz, mx * L.oy * L.oz,
+                           L.ox * L.oy * mz,   L.ox * my * mz,   mx * my * mz,   mx * L.oy * mz};
+      float2* gt = reinterpret_cast<float2*>(p.grad_table) + (size_t)l * p.grid.size;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) atomicAdd(gt + idx[c], make_float2(wt[c] * g0, wt[c] * g1));
+    }
+#undef SGN_AT
+  }
+}
+
+// dW[n][k] += sum_s D[s][doff + n] * A[s][aoff + k]  (n < N <= 64, k < K <= 64);  db[n] += sum_s D[s][doff + n]
+// 256 threads own a 64 x 64 register tile (4 x 4 each); samples are staged 32 at a time through shared memory.
+__global__ void __launch_bounds__(256) k_outer_reduce(const float* __restrict__ D, int doff, int N, const float* __restrict__ A,
+                                                      int aoff, int K, int64_t count, int64_t cap, int ldw,
+                                                      float* __restrict__ dW, float* __restrict__ db, int per_cta) {
+  __shared__ float sD[32][64 + 1];
+  __shared__ float sA[32][64 + 1];
+  const int tn = (threadIdx.x >> 4) * 4, tk = (threadIdx.x & 15) * 4;
+  float acc[4][4] = {};
+  float bacc = 0.f;   // thread t < 64 sums column t of D
+  const int64_t s0 = (int64_t)blockIdx.x * per_cta, s1 = min(count, s0 + per_cta);
+  for (int64_t base = s0; base < s1; base += 32) {
+    const int rows = (int)min((int64_t)32, s1 - base);
+    for (int e = threadIdx.x; e < 32 * 64; e += 256) {
+      const int rr = e & 31, cc = e >> 5;     // consecutive threads read consecutive samples of one component row
+      sD[rr][cc] = (rr < rows && cc < N) ? D[(size_t)(doff + cc) * cap + base + rr] : 0.f;
+      sA[rr][cc] = (rr < rows && cc < K) ? A[(size_t)(aoff + cc) * cap + base + rr] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int rr = 0; rr < 32; ++rr) {
+      float d[4], a[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        d[q] = sD[rr][tn + q];
+        a[q] = sA[rr][tk + q];
+      }
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(d[x], a[y], acc[x][y]);
+    }
+    if (threadIdx.x < 64)
+      for (int rr = 0; rr < 32; ++rr) bacc += sD[rr][threadIdx.x];
+    __syncthreads();
+  }
+#pragma unroll
+  for (int x = 0; x < 4; ++x)
+#pragma unroll
+    for (int y = 0; y < 4; ++y)
+      if (tn + x < N && tk + y < K) atomicAdd(dW + (tn + x) * ldw + tk + y, acc[x][y]);
+  if (db && threadIdx.x < N) atomicAdd(db + threadIdx.x, bacc);
+}
+
+// ---------------------------------------------------------------- loss + optimizer
+// nerfstudio L1Loss / MSELoss = torch.nn.L1Loss / MSELoss (mean over all elements); one block, fixed summation order.
+__global__ void __launch_bounds__(1024) k_rgb_loss(const float* __restrict__ pred, const float* __restrict__ target, int64_t n,
+                                                   int l1, float* __restrict__ loss, float* __restrict__ grad) {
+  __shared__ double part[1024];
+  double acc = 0.0;
+  const float inv = 1.f / (float)n;
+  for (int64_t i = threadIdx.x; i < n; i += 1024) {
+    const float d = pred[i] - target[i];
+    if (l1) {
+      acc += fabsf(d);
+      if (grad) grad[i] = d > 0.f ? inv : (d < 0.f ? -inv : 0.f);
+    } else {
+      acc += (double)d * d;
+      if (grad) grad[i] = 2.f * d * inv;
+    }
+  }
+  part[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 512; o; o >>= 1) {
+    if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *loss = (float)(part[0] / (double)n);
+}
+
+// torch.optim.Adam (nerfstudio AdamOptimizerConfig: betas (0.9, 0.999), eps 1e-15, no weight decay, no amsgrad)
+__global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                       int64_t n, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= (lr / bc1) * (mi / denom);
+  }
+}
+
+static int blocks_for(int64_t n, int threads, int per_sm) {
+  return (int)std::max<int64_t>(1, std::min<int64_t>((n + threads - 1) / threads, (int64_t)sm_count() * per_sm));
+}
+
+}  // namespace sgn
+
+using namespace sgn;
+
+extern "C" int64_t sgn_mlp_param_count(void) { return (int64_t)(sizeof(MlpF32) / sizeof(float)); }
+
+extern "C" int sgn_field_mlp_params(const SgnField* f, float** d_params) {
+  SGN_CHECK_ARG(f && d_params, "null pointer");
+  *d_params = reinterpret_cast<float*>(f->d_f32);
+  return SGN_OK;
+}
+
+static int check_rays(const SgnField* f, const float* o, const float* d, int64_t N, const float* bins, const float* ray_bins, int S) {
+  SGN_CHECK_ARG(f != nullptr, "null field");
+  SGN_CHECK_ARG(N >= 0 && S >= 1 && S <= 1024 && N * (int64_t)S < ((int64_t)1 << 40), "bad batch shape");
+  SGN_CHECK_ARG(N == 0 || (o && d), "null rays");
+  SGN_CHECK_ARG((bins != nullptr) != (ray_bins != nullptr), "exactly one of the shared bins / per-ray bins must be given");
+  return SGN_OK;
+}
+
+extern "C" int sgn_train_forward(const SgnField* f, const float* d_origins, const float* d_directions, int64_t N,
+                                 const float* d_bins, const float* d_ray_bins, int S, float* d_sigma, float* d_color,
+                                 float* d_rgb, float* d_acc, void* stream) {
+  int rc = check_rays(f, d_origins, d_directions, N, d_bins, d_ray_bins, S);
+  if (rc) return rc;
+  if (N == 0) return SGN_OK;
+  SGN_CHECK_ARG(d_sigma && d_color && d_rgb, "null output");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const TrainRays r{d_origins, d_directions, d_bins, d_ray_bins, N, S};
+  static bool attr = false;
+  if (!attr) {
+    SGN_CUDA(cudaFuncSetAttribute(k_train_field, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MlpF32)));
+    SGN_CUDA(cudaFuncSetAttribute(k_train_field_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MlpF32)));
+    attr = true;
+  }
+  k_train_field<<<blocks_for(N * S, 128, 8), 128, sizeof(MlpF32), st>>>(f->grid, f->d_f32, r, d_sigma, d_color);
+  SGN_LAUNCH_CHECK();
+  k_train_composite<<<blocks_for(N, 128, 8), 128, 0, st>>>(r, d_sigma, d_color, d_rgb, d_acc);
+  SGN_LAUNCH_CHECK();
+  return SGN_OK;
+}
+
+constexpr int64_t kBwdChunk = 1 << 18;   // samples per back-propagation chunk (deltas + activations: 490 MB of scratch)
+
+extern "C" int64_t sgn_train_ws_bytes(int64_t N, int S) {
+  if (N <= 0 || S <= 0) return 0;
+  const int64_t samples = N * S;
+  return samples * 4 * (int64_t)sizeof(float) + std::min(samples, kBwdChunk) * (kDeltaDim + kActDim) * (int64_t)sizeof(float) + 256;
+}
+
+extern "C" int sgn_train_backward(const SgnField* f, const float* d_origins, const float* d_directions, int64_t N,
+                                  const float* d_bins, const float* d_ray_bins, int S, const float* d_sigma,
+                                  const float* d_color, const float* d_grad_rgb, float* d_grad_table, float* d_grad_mlp,
+                                  void* d_ws, int64_t ws_bytes, void* stream) {
+  int rc = check_rays(f, d_origins, d_directions, N, d_bins, d_ray_bins, S);
+  if (rc) return rc;
+  if (N == 0) return SGN_OK;
+  SGN_CHECK_ARG(d_sigma && d_color && d_grad_rgb && d_grad_table && d_grad_mlp && d_ws, "null pointer");
+  SGN_CHECK_ARG(ws_bytes >= sgn_train_ws_bytes(N, S), "workspace smaller than sgn_train_ws_bytes");
+  SGN_CHECK_ARG((reinterpret_cast<uintptr_t>(d_ws) & 15) == 0, "workspace must be 16-byte aligned");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const TrainRays r{d_origins, d_directions, d_bins, d_ray_bins, N, S};
+  const int64_t samples = N * S;
+  float* gsigma = reinterpret_cast<float*>(d_ws);
+  float* gcolor = gsigma + samples;
+  float* deltas = gcolor + 3 * samples;
+  float* acts = deltas + std::min(samples, kBwdChunk) * kDeltaDim;
+  static bool attr = false;
+  if (!attr) {
+    SGN_CUDA(cudaFuncSetAttribute(k_train_field_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MlpF32)));
+    attr = true;
+  }
+  k_train_ray_bwd<<<blocks_for(N, 128, 8), 128, 0, st>>>(r, d_sigma, d_color, d_grad_rgb, gsigma, gcolor);
+  SGN_LAUNCH_CHECK();
+  MlpF32* G = reinterpret_cast<MlpF32*>(d_grad_mlp);   // gradients in the parameter block's own layout
+  for (int64_t first = 0; first < samples; first += kBwdChunk) {
+    FieldBwd p;
+    p.grid = f->grid; p.w32 = f->d_f32; p.rays = r; p.gsigma = gsigma; p.gcolor = gcolor;
+    p.grad_table = d_grad_table; p.deltas = deltas; p.acts = acts;
+    p.first = first; p.count = std::min(kBwdChunk, samples - first);
+    p.cap = std::min(samples, kBwdChunk);
+    k_train_field_bwd<<<blocks_for(p.count, 128, 8), 128, sizeof(MlpF32), st>>>(p);
+    SGN_LAUNCH_CHECK();
+    const int per_cta = 1024;
+    const int ctas = (int)((p.count + per_cta - 1) / per_cta);
+    // layer            deltas (offset, N)  activations (offset, K)
+    k_outer_reduce<<<ctas, 256, 0, st>>>(deltas, 0, 64, acts, 0, 32, p.count, p.cap, 32, G->w_base0, G->b_base0, per_cta);
+    SGN_LAUNCH_CHECK();
+    k_outer_reduce<<<ctas, 256, 0, st>>>(deltas, 64, 16, acts, 32, 64, p.count, p.cap, 64, G->w_base1, G->b_base1, per_cta);
+    SGN_LAUNCH_CHECK();
+    k_outer_reduce<<<ctas, 256, 0, st>>>(deltas, 80, 64, acts, 96, 32, p.count, p.cap, 32, G->w_head0, G->b_head0, per_cta);
+    SGN_LAUNCH_CHECK();
+    k_outer_reduce<<<ctas, 256, 0, st>>>(deltas, 144, 64, acts, 128, 64, p.count, p.cap, 64, G->w_head1, G->b_head1, per_cta);
+    SGN_LAUNCH_CHECK();
+    k_outer_reduce<<<ctas, 256, 0, st>>>(deltas, 208, 3, acts, 192, 64, p.count, p.cap, 64, G->w_head2, G->b_head2, per_cta);
+    SGN_LAUNCH_CHECK();
+  }
+  return SGN_OK;
+}
+
+extern "C" int sgn_rgb_loss(const float* d_pred, const float* d_target, int64_t n, int l1, float* d_loss, float* d_grad,
+                            void* stream) {
+  SGN_CHECK_ARG(n > 0 && d_pred && d_target && d_loss, "bad loss arguments");
+  k_rgb_loss<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_pred, d_target, n, l1, d_loss, d_grad);
+  SGN_LAUNCH_CHECK();
+  return SGN_OK;
+}
+
+extern "C" int sgn_adam_step(float* d_param, const float* d_grad, float* d_m, float* d_v, int64_t n, float lr, float beta1,
+                             float beta2, float eps, int step, void* stream) {
+  SGN_CHECK_ARG(n >= 0 && step >= 1 && lr >= 0.f && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f, "bad Adam arguments");
+  if (n == 0) return SGN_OK;
+  SGN_CHECK_ARG(d_param && d_grad && d_m && d_v, "null pointer");
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2 = sqrtf(1.f - powf(beta2, (float)step));
+  k_adam<<<blocks_for(n, 256, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(d_param, d_grad, d_m, d_v, n, lr, beta1,
+                                                                                     beta2, eps, bc1, bc2);
+  SGN_LAUNCH_CHECK();
+  return SGN_OK;
+}
