@@ -220,6 +220,8 @@ def main():
     ap.add_argument("--config5-cameras", type=int, default=1,
                     help="dataset cameras PER RANK of the BASELINE-config-5 generation sample (0 = skip)")
     ap.add_argument("--config5-total", action="store_true", help="--config5-cameras is the TOTAL camera count (30 = the named job)")
+    ap.add_argument("--config5-rounds", type=int, default=1, help="generation + fine-tune rounds (BASELINE config 5 names 3)")
+    ap.add_argument("--config5-train-steps", type=int, default=20, help="fine-tune steps after each generation (0 = none)")
     ap.add_argument("--ncu-range", action="store_true",
                     help="cudaProfilerStart/Stop around the timed steps (run under `ncu --profile-from-start off`)")
     args = ap.parse_args()
@@ -523,20 +525,45 @@ def main():
         graph5 = P.FusedNerfactoGraph(fld5)
         ref_c2w, _ = synthetic.camera_ring(VIEWS - 1, W, H)
         syn_c2w, _ = synthetic.camera_ring(n_cam, W, H, phi_deg=(3.0, 357.0))
-        sync_all()
-        t0 = time.perf_counter()
-        gen5.generate_dataset(graph5, ref_c2w, synthetic_camera_to_worlds=syn_c2w)
-        sync_all()
-        t5 = time.perf_counter() - t0
-        frames = None
+        # refinement rounds: generation alternates with fine-tuning of the NeRF on the generated images (edit_loop.py)
+        from signerf_b200 import edit_loop
+        from signerf_b200 import train as train_mod
+        tuner = edit_loop.FineTuner(train_mod.FieldTrainer(fld5), num_samples=48, rays_per_batch=max(1024, 16384 // N),
+                                    seed=rank)
+        rounds, gen_s, train_s, train_losses, frames = [], 0.0, 0.0, [], None
+        for rnd in range(args.config5_rounds):
+            gen5.dataset_name = f"config5_round{rnd}"
+            sync_all()
+            t0 = time.perf_counter()
+            gen5.generate_dataset(graph5, ref_c2w, synthetic_camera_to_worlds=syn_c2w)
+            sync_all()
+            t1 = time.perf_counter()
+            imgs, cw, it_ = edit_loop.load_generated_images(os.path.join(tmp, gen5.dataset_name))
+            losses = tuner.fit(imgs, cw, it_, args.config5_train_steps) if args.config5_train_steps > 0 else []
+            sync_all()
+            t2 = time.perf_counter()
+            gen_s += t1 - t0
+            train_s += t2 - t1
+            train_losses.append(losses)
+            rounds.append({"generate_s": t1 - t0, "fine_tune_s": t2 - t1})
+            if rank == 0:
+                frames = len(json.load(open(os.path.join(tmp, gen5.dataset_name, "transforms.json")))["frames"])
+        t5 = gen_s / max(1, args.config5_rounds)
         if rank == 0:
-            frames = len(json.load(open(os.path.join(tmp, "config5", "transforms.json")))["frames"])
             shutil.rmtree(tmp, ignore_errors=True)
         per_rank = (n_cam + N - 1) // N
         config5 = {"dataset_cameras": n_cam, "reference_views": VIEWS - 1, "ranks": N, "seconds": t5, "frames_written": frames,
                    "sheets_diffused_per_rank": 1 + per_rank, "seconds_per_sheet": t5 / (1 + per_rank),
                    "dataset_views_per_s": n_cam / t5,
                    "estimated_30_camera_seconds": t5 / (1 + per_rank) * (1 + (30 + N - 1) // N),
+                   "refinement_rounds": args.config5_rounds, "fine_tune_steps_per_round": args.config5_train_steps,
+                   "rounds": rounds, "total_seconds": gen_s + train_s,
+                   "fine_tune_ms_per_step": (train_s / max(1, args.config5_rounds * args.config5_train_steps) * 1e3)
+                   if args.config5_train_steps > 0 else None,
+                   "fine_tune_losses_rank0": train_losses,
+                   "fine_tune_note": "main field only (hash grid + MLPs), L1 rgb loss on 32x32 patches of the generated images, "
+                                     "16 384 rays x 48 flat samples per step over all ranks, Adam lr 1e-2; gradients all-reduced "
+                                     "across ranks; proposal networks / LPIPS / regularisers not trained (DESIGN.md)",
                    "note": "BASELINE config 5, generation half through plugin.DatasetGenerator.generate_dataset: procedural proxy mesh "
                            "with bunny.obj's 4 968 triangles (the reference's mesh file is not shipped), masking_mode='shape', 4x4 sheet of "
                            "512^2 tiles, 20 configured steps at strength 0.9 = 19 UNet+ControlNet evaluations per sheet, eager launches, "
