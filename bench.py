@@ -605,7 +605,12 @@ def main():
                        "frac": k1_gbs / pk["hbm"], "traffic": 97.6e6, "peak_source": pk["source"], "ms_per_launch": k1_ms,
                        "algorithmic_bytes_per_launch": k1_bytes,
                        "note": "hash tables (64 MiB) stay L2-resident: ncu dram bytes per launch are 97.6 MB (profiles/), "
-                               "so the algorithmic-gather figure can exceed the HBM copy peak"}
+                               "so the algorithmic-gather figure can exceed the HBM copy peak",
+                       # the ceiling that actually binds (profiles/r2_ncu_render_summary.txt, r2_k1_wavefronts_per_level.txt):
+                       # 2.15e9 LDG.64 per launch touch 4.28 distinct 128-B lines each (levels 12-15: 10-16 lines, 66 % of the
+                       # work; levels 0-4: 1.1-1.3 lines, 8 %) and keep the L1 LSU data pipe 80 % busy
+                       "l1_ceiling": {"bound": "l1 lsu data pipe (wavefronts)", "frac": 0.803, "ldg_per_launch": 2.1496e9,
+                                      "tag_requests_per_ldg": 4.28, "source": "ncu --set full, one launch (profiles/r2_ncu_render_summary.txt)"}}
         if unet is not None:
             tf = UNET_TFLOP_PER_STEP / (unet_ms / 1e3)
             tc = {k: v for k, v in fam.items() if v["flops"] > 0}
