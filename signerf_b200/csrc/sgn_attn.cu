@@ -284,14 +284,18 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     // FADD2 / FMNMX3): 2 turn-taking, 3 free-running groups, 4 / 5 the same with a quarter of the exponentials on the FMA
     // pipe (ex2_poly_pair), 6 / 7 with three eighths
     constexpr bool kPacked = kVariant >= 2;
-    constexpr bool kFine = kVariant >= 8;   // 8: pair-granular software pipeline, free-running groups; 9: with turns
+    constexpr bool kFine = kVariant == 8 || kVariant == 9;   // 8: pair-granular software pipeline, free-running groups; 9: with turns
+    // 10 / 11: variant 2 with the MUFU turn taken earlier - at the top of the key tile (10: the other group only finishes its
+    // P store while this one loads / scans / exponentiates) or after the S load (11)
+    constexpr int kTurnAt = kVariant == 10 ? 1 : (kVariant == 11 ? 2 : 0);
     constexpr bool kTurns = !(kVariant == 3 || kVariant == 5 || kVariant == 7 || kVariant == 8);
-    constexpr int kPolyOf8 = kVariant >= 6 ? 3 : (kVariant >= 4 ? 2 : 0);   // pairs out of every 8 that go to the FMA pipe
+    constexpr int kPolyOf8 = (kVariant == 6 || kVariant == 7) ? 3 : ((kVariant == 4 || kVariant == 5) ? 2 : 0);   // pairs out of every 8 that go to the FMA pipe
     if (kTurns && x == 1) named_arrive(1, 256);  // group A takes the first turn
     for (int j = 0; j < n_kv; ++j) {
       const int kv_rem = p.T_kv - j * kKvTile;  // >= 1
       const bool tr = warp == 2 && lane == 0;
       if (tr) TRACE(0, j);
+      if (kTurns && kTurnAt == 1) named_sync(1 + x, 256);
       tc::mbar_wait(&s_full[x], j & 1);
       tc::tc_fence_after();
       if (tr) TRACE(1, j);
@@ -303,6 +307,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&s_free[x]);     // the issuer may overwrite S_x with Q_x K_{j+1}^T now
       if (tr) TRACE(2, j);
+      if (kTurns && kTurnAt == 2) named_sync(1 + x, 256);
       if (kv_rem < kKvTile) {
 #pragma unroll
         for (int q = 0; q < 128; ++q)
@@ -360,7 +365,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const float neg_m = -m_run * sc;
       float psum0 = 0.f, psum1 = 0.f;
       if (tr) TRACE(3, j);
-      if (kTurns) named_sync(1 + x, 256);            // my turn on the MUFU pipe
+      if (kTurns && kTurnAt == 0) named_sync(1 + x, 256);            // my turn on the MUFU pipe
       if (tr) TRACE(4, j);
       if constexpr (kVariant == 0) {
 #pragma unroll
@@ -739,6 +744,8 @@ extern "C" int sgn_attention_f16(const void* d_q, int64_t ldq, const void* d_k, 
     SGN_CUDA(cudaFuncSetAttribute(k_attention_tc<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
     SGN_CUDA(cudaFuncSetAttribute(k_attention_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
     SGN_CUDA(cudaFuncSetAttribute(k_attention_tc<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
+    SGN_CUDA(cudaFuncSetAttribute(k_attention_tc<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
+    SGN_CUDA(cudaFuncSetAttribute(k_attention_tc<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
     attr_set = true;
   }
   CUtensorMap tmQ, tmK, tmV;
@@ -761,10 +768,10 @@ extern "C" int sgn_attention_f16(const void* d_q, int64_t ldq, const void* d_k, 
   dim3 grid((T_q + kQPerCta - 1) / kQPerCta, heads, B);
   p.idle_ns = g_attn_idle_ns;
   using Kern = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, AttnParams);
-  static const Kern kerns[10] = {k_attention_tc<0>, k_attention_tc<1>, k_attention_tc<2>, k_attention_tc<3>,
+  static const Kern kerns[12] = {k_attention_tc<0>, k_attention_tc<1>, k_attention_tc<2>, k_attention_tc<3>,
                                  k_attention_tc<4>, k_attention_tc<5>, k_attention_tc<6>, k_attention_tc<7>,
-                                 k_attention_tc<8>, k_attention_tc<9>};
-  Kern kern = kerns[g_attn_variant % 10];
+                                 k_attention_tc<8>, k_attention_tc<9>, k_attention_tc<10>, k_attention_tc<11>};
+  Kern kern = kerns[g_attn_variant % 12];
   kern<<<grid, kAttnThreads, kAttnSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
   SGN_LAUNCH_CHECK();
   return SGN_OK;

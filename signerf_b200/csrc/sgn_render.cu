@@ -712,7 +712,7 @@ extern "C" int sgn_set_option(const char* name, int value) {
     return SGN_OK;
   }
   if (n == "attn_variant") {
-    SGN_CHECK_ARG(value >= 0 && value <= 9, "attn_variant must be 0..9");
+    SGN_CHECK_ARG(value >= 0 && value <= 11, "attn_variant must be 0..11");
     sgn::g_attn_variant = value;
     return SGN_OK;
   }
