@@ -581,7 +581,9 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16 operands, f32 accumulate (tcgen05 UNet; f32 hash gather/composite + f16 mma MLP in the renderer)",
+            "dtype": "f16 operands, f32 accumulate (tcgen05 UNet on fp16-representable weights, as the fp16 checkpoints the "
+                     "reference up-casts are; f32 hash gather/composite + f16 mma MLP on genuine fp32 NeRF weights in the renderer, "
+                     "near-tie median depths re-marched in f32)",
             "data": "synthetic",
             "config": {"workload": "C3 4x4 grid of 512x512 views, flat 128 samples/ray, nerfacto field (16-level 2^19 hash + MLPs), "
                                    "AABB mask + 50x50 dilation + depth condition, 2048x2048 sheet" +

@@ -384,6 +384,21 @@ int sgn_shape_color_u8(const float* d_depth, int64_t npix, const uint8_t* h_fg_r
 int sgn_mask_condition_shape(const float* d_proxy_depth, const float* d_depth, int V, int H, int W, const SgnMaskOpts* o,
                              uint8_t* d_mask, float* d_cond, float* d_stats, void* stream);
 
+/* ------------------------------------------------------------------ prompt conditioning ("also" clause)
+ * The A1111 server the reference posts to (diffuser.py:132-180, `prompt` / `negative_prompt`) encodes the prompt with
+ * SDXL's two text transformers once per request: CLIP ViT-L/14 (12 layers, width 768, quick_gelu) and OpenCLIP ViT-bigG/14
+ * (32 layers, width 1280, gelu), both causal over 77 tokens, head_dim 64.  The layers run on sgn_layer_norm_f16 /
+ * sgn_gemm_f16 plus the three entry points below (signerf_b200/text_encoder.py walks them). */
+/* softmax(Q K^T * scale + causal mask) V for self-attention over T <= 80 tokens (query i sees keys <= i); layout as
+ * sgn_attention_f16. */
+int sgn_attention_causal_f16(const void* d_q, int64_t ldq, const void* d_k, int64_t ldk, const void* d_v, int64_t ldv,
+                             int B, int heads, int T, float scale, void* d_out, int64_t ldo, void* stream);
+/* fp32 [n] -> fp16 [n]: mode 0 quick_gelu x * sigmoid(1.702 x), mode 1 exact (erf) GELU. */
+int sgn_act_f16(const float* d_x, int64_t n, int mode, void* d_out, void* stream);
+/* CLIPTextEmbeddings: out[r] = token_table[ids[r]] + position_table[r % T]; ids int32 [rows], tables fp32 [vocab | T, width]. */
+int sgn_embed_tokens(const int32_t* d_ids, const float* d_token_table, const float* d_position_table, int rows, int T,
+                     int width, int vocab, float* d_out, void* stream);
+
 /* ------------------------------------------------------------------ the NeRF fine-tune step
  * `SIGNeRFModel` trains with nerfacto's forward and `get_loss_dict` (signerf/signerf.py:41-82) between two dataset
  * generations.  These entry points are the main field's forward + backward on a batch of rays, the image loss and the

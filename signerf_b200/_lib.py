@@ -73,6 +73,9 @@ SIGNATURES = {
     "sgn_field_create": (_i, [C.POINTER(SgnFieldDesc), C.POINTER(_vp)]),
     "sgn_field_destroy": (None, [_vp]),
     "sgn_render_views": (_i, [_vp, _vp, _vp, _i, _i, _i, C.POINTER(SgnRenderOpts), _vp, _vp, _vp, _vp]),
+    "sgn_attention_causal_f16": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _f, _vp, _i64, _vp]),
+    "sgn_act_f16": (_i, [_vp, _i64, _i, _vp, _vp]),
+    "sgn_embed_tokens": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "sgn_mlp_param_count": (_i64, []),
     "sgn_field_mlp_params": (_i, [_vp, C.POINTER(_vp)]),
     "sgn_field_refresh": (_i, [_vp, _vp]),

@@ -589,7 +589,7 @@ __device__ __forceinline__ uint32_t xa_pack(float lo, float hi) {
 __global__ void __launch_bounds__(128)
 k_cross_attention(const __half* __restrict__ q, long long ldq, const __half* __restrict__ k, long long ldk,
                   const __half* __restrict__ v, long long ldv, int T_q, int T_kv, float scale_log2e,
-                  __half* __restrict__ out, long long ldo, int q_per_cta) {
+                  __half* __restrict__ out, long long ldo, int q_per_cta, int causal) {
   __shared__ __align__(16) __half sK[kXaKv * kXaPitch];
   __shared__ __align__(16) __half sV[kXaKv * kXaPitch];
   __shared__ __align__(16) __half sQ2[2][kXaQ * kXaPitch];   // double-buffered query tiles (cp.async)
@@ -646,8 +646,12 @@ k_cross_attention(const __half* __restrict__ q, long long ldq, const __half* __r
 #pragma unroll
     for (int nt = 0; nt < kXaKv / 8; ++nt) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if (nt * 8 + col0 + (e & 1) >= T_kv) s[nt][e] = -INFINITY;
+      for (int e = 0; e < 4; ++e) {
+        const int key = nt * 8 + col0 + (e & 1);
+        // causal (CLIP text transformers): query i attends to keys <= i; rows g / g + 8 of the warp's 16
+        const int qrow = q0 + warp * 16 + g + ((e & 2) ? 8 : 0);
+        if (key >= T_kv || (causal && key > qrow)) s[nt][e] = -INFINITY;
+      }
       m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
       m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
     }
@@ -708,9 +712,8 @@ extern "C" int sgn_debug_attn_trace(long long* h_out) {
 }
 #endif
 
-extern "C" int sgn_attention_f16(const void* d_q, int64_t ldq, const void* d_k, int64_t ldk, const void* d_v,
-                                 int64_t ldv, int B, int heads, int T_q, int T_kv, float scale, void* d_out,
-                                 int64_t ldo, void* stream) {
+static int attention_impl(const void* d_q, int64_t ldq, const void* d_k, int64_t ldk, const void* d_v, int64_t ldv, int B,
+                          int heads, int T_q, int T_kv, float scale, void* d_out, int64_t ldo, int causal, void* stream) {
   SGN_CHECK_ARG(B >= 0 && heads > 0 && T_q > 0 && T_kv > 0, "bad attention shape");
   if (B == 0) return SGN_OK;
   SGN_CHECK_ARG(d_q && d_k && d_v && d_out, "null pointer");
@@ -719,7 +722,8 @@ extern "C" int sgn_attention_f16(const void* d_q, int64_t ldq, const void* d_k, 
                 "row stride smaller than heads * 64");
   SGN_CHECK_ARG(((reinterpret_cast<uintptr_t>(d_q) | reinterpret_cast<uintptr_t>(d_k) | reinterpret_cast<uintptr_t>(d_v) |
                   reinterpret_cast<uintptr_t>(d_out)) & 15) == 0, "operands must be 16-byte aligned");
-  if (T_kv <= kXaKv && g_attn_short_kv) {
+  SGN_CHECK_ARG(!causal || (T_kv <= kXaKv && T_q == T_kv), "causal attention is built for self-attention over <= 80 tokens");
+  if (T_kv <= kXaKv && (g_attn_short_kv || causal)) {
     // ~4 resident waves: enough query tiles per CTA to amortise its K / V load, enough CTAs to fill the GPU
     const int tiles = (T_q + kXaQ - 1) / kXaQ;
     const long long want = 4ll * sm_count();
@@ -728,7 +732,7 @@ extern "C" int sgn_attention_f16(const void* d_q, int64_t ldq, const void* d_k, 
     k_cross_attention<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const __half*>(d_q), ldq, reinterpret_cast<const __half*>(d_k), ldk,
         reinterpret_cast<const __half*>(d_v), ldv, T_q, T_kv, scale * 1.4426950408889634f,
-        reinterpret_cast<__half*>(d_out), ldo, tiles_per_cta * kXaQ);
+        reinterpret_cast<__half*>(d_out), ldo, tiles_per_cta * kXaQ, causal);
     SGN_LAUNCH_CHECK();
     return SGN_OK;
   }
@@ -775,4 +779,16 @@ extern "C" int sgn_attention_f16(const void* d_q, int64_t ldq, const void* d_k, 
   kern<<<grid, kAttnThreads, kAttnSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
   SGN_LAUNCH_CHECK();
   return SGN_OK;
+}
+
+extern "C" int sgn_attention_f16(const void* d_q, int64_t ldq, const void* d_k, int64_t ldk, const void* d_v,
+                                 int64_t ldv, int B, int heads, int T_q, int T_kv, float scale, void* d_out,
+                                 int64_t ldo, void* stream) {
+  return attention_impl(d_q, ldq, d_k, ldk, d_v, ldv, B, heads, T_q, T_kv, scale, d_out, ldo, 0, stream);
+}
+
+extern "C" int sgn_attention_causal_f16(const void* d_q, int64_t ldq, const void* d_k, int64_t ldk, const void* d_v,
+                                        int64_t ldv, int B, int heads, int T, float scale, void* d_out, int64_t ldo,
+                                        void* stream) {
+  return attention_impl(d_q, ldq, d_k, ldk, d_v, ldv, B, heads, T, T, scale, d_out, ldo, 1, stream);
 }

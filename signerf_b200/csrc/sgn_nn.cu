@@ -733,6 +733,46 @@ extern "C" int sgn_linear_small(const float* d_x, const float* d_w, const float*
   return SGN_OK;
 }
 
+// ---- CLIP text encoders (prompt conditioning, once per prompt)
+// mode 0: quick_gelu x * sigmoid(1.702 x) (CLIP-L); mode 1: exact GELU (OpenCLIP bigG)
+__global__ void k_act_f16(const float* __restrict__ x, size_t n, int mode, __half* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    const float y = mode == 0 ? v / (1.f + expf(-1.702f * v)) : 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+    out[i] = __float2half_rn(y);
+  }
+}
+// CLIPTextEmbeddings: token_embedding[ids] + position_embedding[position], rows of `width` floats
+__global__ void k_embed_tokens(const int* __restrict__ ids, const float* __restrict__ tok, const float* __restrict__ pos,
+                               int rows, int T, int width, int vocab, float* __restrict__ out) {
+  const size_t n = (size_t)rows * width;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / width), c = (int)(i - (size_t)r * width);
+    const int id = min(max(ids[r], 0), vocab - 1);
+    out[i] = tok[(size_t)id * width + c] + pos[(size_t)(r % T) * width + c];
+  }
+}
+
+extern "C" int sgn_act_f16(const float* d_x, int64_t n, int mode, void* d_out, void* stream) {
+  SGN_CHECK_ARG(n >= 0 && (mode == 0 || mode == 1), "mode must be 0 (quick_gelu) or 1 (gelu)");
+  if (n == 0) return SGN_OK;
+  SGN_CHECK_ARG(d_x && d_out, "null pointer");
+  k_act_f16<<<grid_1d((size_t)n, 256), 256, 0, ST(stream)>>>(d_x, (size_t)n, mode, reinterpret_cast<__half*>(d_out));
+  SGN_LAUNCH_CHECK();
+  return SGN_OK;
+}
+
+extern "C" int sgn_embed_tokens(const int32_t* d_ids, const float* d_token_table, const float* d_position_table, int rows,
+                                int T, int width, int vocab, float* d_out, void* stream) {
+  SGN_CHECK_ARG(rows >= 0 && T > 0 && width > 0 && vocab > 0, "bad embedding shape");
+  if (rows == 0) return SGN_OK;
+  SGN_CHECK_ARG(d_ids && d_token_table && d_position_table && d_out, "null pointer");
+  k_embed_tokens<<<grid_1d((size_t)rows * width, 256), 256, 0, ST(stream)>>>(d_ids, d_token_table, d_position_table, rows, T,
+                                                                             width, vocab, d_out);
+  SGN_LAUNCH_CHECK();
+  return SGN_OK;
+}
+
 extern "C" int sgn_timestep_embedding(const float* d_t, int B, int dim, float* d_out, void* stream) {
   SGN_CHECK_ARG(B > 0 && dim > 0 && dim % 2 == 0, "dim must be even");
   SGN_CHECK_ARG(d_t && d_out, "null pointer");
