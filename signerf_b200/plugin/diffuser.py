@@ -46,21 +46,57 @@ class InProcessSDXL:
     signerf_b200.inpaint.A1111InpaintCodec (VAE + mask blur + latent mask + overlay) around the latent loop."""
 
     def __init__(self, denoiser: SDXLDenoiserB200, context: Tensor, y: Tensor,
-                 codec: Optional[object] = None):
+                 codec: Optional[object] = None, use_graph: bool = True):
         self.net, self.context, self.y, self.codec = denoiser, context, y, codec
+        self.use_graph = use_graph          # replay the whole trajectory as ONE CUDA graph (captured per request shape)
+        self._graphs: dict = {}
+
+    def _trajectory(self, init_latent: Tensor, hint: Tensor, latent_mask: Tensor, noises: Tensor, sig, cfg_scale: float,
+                    control_weight: float, context: Tensor, y: Tensor) -> Tensor:
+        """The t_enc + 1 sampler steps on latents; `noises` [len(sig), 1,4,h,w]: row 0 seeds x, row i+1 is step i's."""
+        x = init_latent + noises[0] * sig[0]
+        guided = self.net.ctrl.hint_embedding(hint) if self.net.ctrl is not None else None   # constant over the steps
+        for i in range(len(sig) - 1):
+            noise = noises[i + 1] if sig[i + 1] > 0 else None
+            x, _, _ = self.net.step(x, sig[i], sig[i + 1], context, y, hint, noise, init_latent, latent_mask,
+                                    cfg_scale, control_weight, guided=guided)
+        return x
 
     def denoise_latents(self, init_latent: Tensor, hint: Tensor, latent_mask: Tensor, steps: int, strength: float,
                         cfg_scale: float, control_weight: float, seed: int) -> Tensor:
         """init_latent [1,4,h,w]; hint [1,3,8h,8w] in [0,1]; latent_mask [1,1,h,w] = 1 where the original is kept."""
         sig = img2img_sigmas(steps, strength)
-        g = torch.Generator(device=init_latent.device).manual_seed(int(seed))
-        x = init_latent + torch.randn(init_latent.shape, generator=g, device=init_latent.device) * sig[0]
-        guided = self.net.ctrl.hint_embedding(hint) if self.net.ctrl is not None else None   # constant over the steps
-        for i in range(len(sig) - 1):
-            noise = torch.randn(init_latent.shape, generator=g, device=init_latent.device) if sig[i + 1] > 0 else None
-            x, _, _ = self.net.step(x, sig[i], sig[i + 1], self.context, self.y, hint, noise, init_latent, latent_mask,
-                                    cfg_scale, control_weight, guided=guided)
-        return x
+        dev = init_latent.device
+        g = torch.Generator(device=dev).manual_seed(int(seed))
+        # the same Philox stream as drawing step by step: one randn per sampler step, in order
+        noises = torch.stack([torch.randn(init_latent.shape, generator=g, device=dev) for _ in range(len(sig))])
+        if not self.use_graph:
+            return self._trajectory(init_latent, hint, latent_mask, noises, sig, cfg_scale, control_weight, self.context, self.y)
+        # Every sigma is a host scalar known up front, so the 19 UNet + ControlNet evaluations of a request (about 30 000
+        # kernel launches) replay as one CUDA graph; the graph is keyed by everything that is baked into it.
+        key = (tuple(init_latent.shape), tuple(hint.shape), int(steps), float(strength), float(cfg_scale), float(control_weight))
+        slot = self._graphs.get(key)
+        if slot is None:
+            bufs = {"init": torch.empty_like(init_latent), "hint": torch.empty_like(hint), "mask": torch.empty_like(latent_mask),
+                    "noise": torch.empty_like(noises), "ctx": torch.empty_like(self.context), "y": torch.empty_like(self.y)}
+            for k, src in (("init", init_latent), ("hint", hint), ("mask", latent_mask), ("noise", noises), ("ctx", self.context),
+                           ("y", self.y)):
+                bufs[k].copy_(src)
+            run = lambda: self._trajectory(bufs["init"], bufs["hint"], bufs["mask"], bufs["noise"], sig,  # noqa: E731
+                                           cfg_scale, control_weight, bufs["ctx"], bufs["y"])
+            self.net.step(bufs["init"], sig[0], sig[1], bufs["ctx"], bufs["y"], bufs["hint"], bufs["noise"][1], bufs["init"],
+                          bufs["mask"], cfg_scale, control_weight)     # one eager step: lazy initialisation outside capture
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = run()
+            slot = self._graphs[key] = (graph, bufs, out)
+        graph, bufs, out = slot
+        for k, src in (("init", init_latent), ("hint", hint), ("mask", latent_mask), ("noise", noises), ("ctx", self.context),
+                       ("y", self.y)):
+            bufs[k].copy_(src)
+        graph.replay()
+        return out.clone()
 
 
 class Diffuser:
