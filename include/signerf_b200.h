@@ -239,6 +239,15 @@ int sgn_conv3x3_f16(const void* d_x, const void* d_w, int B, int H, int W, int C
 int sgn_attention_f16(const void* d_q, int64_t ldq, const void* d_k, int64_t ldk, const void* d_v, int64_t ldv,
                       int B, int heads, int T_q, int T_kv, float scale, void* d_out, int64_t ldo, void* stream);
 
+/* Same, with a caller-owned workspace: (query tile, head, image) work items that would only fill part of a last wave
+ * of CTAs are cut into key ranges whose partial (O, m, l) the last-arriving CTA combines (4.32 waves at T = 4 096 x 20
+ * heads x 2 images on 148 SMs become 4 + 0.34).  sgn_attention_workspace_bytes = bytes this shape needs on the current
+ * device (0: no split, d_ws may be NULL); the workspace is scratch, nothing survives the call. */
+int64_t sgn_attention_workspace_bytes(int B, int heads, int T_q, int T_kv);
+int sgn_attention_f16_ws(const void* d_q, int64_t ldq, const void* d_k, int64_t ldk, const void* d_v, int64_t ldv,
+                         int B, int heads, int T_q, int T_kv, float scale, void* d_out, int64_t ldo, void* d_ws,
+                         int64_t ws_bytes, void* stream);
+
 /* GroupNorm (sgm `normalization` = GroupNorm32(32, C), eps 1e-5; SpatialTransformer.norm eps 1e-6) + optional SiLU.
  * d_x fp32 [B, HW, C] -> d_out fp16 [B, HW, C].  d_ws: scratch of sgn_group_norm_ws_doubles(B, HW, groups) doubles
  * (per-chunk partial sums, reduced in a fixed order: results are run-to-run bit-identical). */

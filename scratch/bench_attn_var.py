@@ -9,8 +9,8 @@ def timeit(fn, n=8, warm=3):
     for _ in range(n): fn()
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / n
-variants = [int(v) for v in sys.argv[1].split(",")] if len(sys.argv) > 1 else [0, 1, 2]
-idles = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0, 40]
+variants = [int(v) for v in sys.argv[1].split(",")] if len(sys.argv) > 1 else list(range(16))
+idles = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0]
 for B, heads, T in ((2, 10, 16384), (2, 20, 4096)):
     C = heads * 64
     g = torch.Generator(device="cuda").manual_seed(0)

@@ -101,6 +101,8 @@ SIGNATURES = {
     "sgn_gemm_plan": (_i, [_i, _i, _i, _i, C.POINTER(_i)]),
     "sgn_conv3x3_f16": (_i, [_vp, _vp, _i, _i, _i, _i, _i, C.POINTER(SgnEpilogue), _vp, _vp]),
     "sgn_attention_f16": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _f, _vp, _i64, _vp]),
+    "sgn_attention_f16_ws": (_i, [_vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _f, _vp, _i64, _vp, _i64, _vp]),
+    "sgn_attention_workspace_bytes": (_i64, [_i, _i, _i, _i]),
     "sgn_group_norm_ws_doubles": (_i64, [_i, _i, _i]),
     "sgn_group_norm_f16": (_i, [_vp, _i, _i, _i, _i, _f, _vp, _vp, _i, _vp, _vp, _vp]),
     "sgn_layer_norm_f16": (_i, [_vp, _i64, _i, _f, _vp, _vp, _vp, _vp]),

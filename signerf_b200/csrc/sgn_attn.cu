@@ -32,47 +32,29 @@ constexpr int kHeadDim = 64;
 constexpr int kQTile = 128, kKvTile = 128;
 constexpr int kQPerCta = 2 * kQTile;
 constexpr int kKvStages = 4;
-constexpr int kPolyEvery = 0;  // N > 0: every Nth exponential on the FMA pipe (measured slower on B200: issue-bound)
 constexpr int kTileBytes = 128 * 64 * 2;  // one [128 x 64] fp16 tile, 128-B rows, SWIZZLE_128B
 constexpr size_t kAttnSmem = 1024 + kTileBytes * (2 + 2 * kKvStages) + 256;
 
 struct AttnParams {
   int T_q, T_kv, n_kv_tiles;
-  int idle_ns;   // MMA-issuer back-off when neither tile has work (0 = spin)
+  int n_qt, heads;   // work item -> (query pair tile, head, image): item = qt + n_qt * (head + heads * image)
+  int n_full, split; // CTAs [0, n_full) take a whole item; the others 1/split of the key tiles of one of the tail items
+  int idle_ns;       // MMA-issuer back-off when neither tile has work (0 = spin; polling issuer only)
   float scale_log2e;
   __half* out;
   long long ldo;
+  float* part;       // [tail item][split][66][256]: unnormalised O (64 columns), m, l of every query row
+  unsigned* count;   // [tail item] arrivals (zero at launch; the combining CTA resets its counter)
 };
 
 // named barriers 1 / 2: the exp2 sections of the two softmax warpgroups take turns on the MUFU pipe, which staggers
 // them by half a period: while one exponentiates, the other loads its next S row and finds the row maximum.
 __device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void named_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-
-// exp2 on the FMA / ALU pipes (Cody-Waite + degree-4 polynomial, rel. error < 5e-5, far below the fp16 rounding of P):
-// a quarter of the row goes this way so that the MUFU pipe (16 ex2/clk/SM) stops being the binding unit.
-__device__ __forceinline__ float ex2_poly(float x) {
-  x = fmaxf(x, -120.f);
-  const float t = x + 12582912.f;            // 1.5 * 2^23: the low mantissa bits of t hold round(x)
-  const float f = x - (t - 12582912.f);      // f in [-0.5, 0.5]
-  float p = fmaf(f, 0.0096181291f, 0.0555041087f);
-  p = fmaf(p, f, 0.2402265070f);
-  p = fmaf(p, f, 0.6931471806f);
-  p = fmaf(p, f, 1.0f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));   // * 2^round(x)
-}
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float ex2_v(float x) {   // pinned in program order (stays behind the named barrier)
-  float y;
-  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 
@@ -104,58 +86,42 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
 }
-// the same operations pinned in program order (asm volatile): the fine-grained software pipeline of variants >= 8 is
-// written instruction by instruction and must not be re-bunched by the scheduler
-__device__ __forceinline__ uint64_t fma2_v(uint64_t a, uint64_t b, uint64_t c) {
-  uint64_t d;
-  asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ uint64_t add2_v(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ uint32_t cvt_h2_v(float lo, float hi) {
-  uint32_t d;
-  asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-  return d;
-}
-// exp2 of a pair on the FMA pipe: round-to-nearest split x = n + f (magic-number add), degree-3 minimax polynomial of 2^f
-// on [-0.5, 0.5] (max relative error 7.5e-5, a third of the fp16 rounding P gets anyway), exponent patched in with an
-// integer multiply-add.  6 packed FMA-pipe instructions + 2 IMAD + 2 FMNMX for two exponentials, none on the MUFU pipe.
-__device__ __forceinline__ void ex2_poly_pair(uint64_t t, uint32_t& e0, uint32_t& e1) {
-  float t0, t1;
-  upk2(t, t0, t1);
-  const uint64_t x = pk2(fmaxf(t0, -125.f), fmaxf(t1, -125.f));
-  const uint64_t magic = pk2(12582912.f, 12582912.f), neg_magic = pk2(-12582912.f, -12582912.f);
-  const uint64_t r = add2(x, magic);                       // low mantissa bits of each half hold round(x)
-  const uint64_t f = fma2(add2(r, neg_magic), pk2(-1.f, -1.f), x);   // x - round(x) in [-0.5, 0.5]
-  uint64_t p = fma2(f, pk2(0.05517100281f, 0.05517100281f), pk2(0.24260949573f, 0.24260949573f));
-  p = fma2(p, f, pk2(0.69326094686f, 0.69326094686f));
-  p = fma2(p, f, pk2(0.99992817475f, 0.99992817475f));
-  float p0, p1, r0, r1;
-  upk2(p, p0, p1);
-  upk2(r, r0, r1);
-  e0 = (uint32_t)(__float_as_int(p0) + (__float_as_int(r0) << 23));
-  e1 = (uint32_t)(__float_as_int(p1) + (__float_as_int(r1) << 23));
-}
 
-// make -C signerf_b200/csrc trace: clock64 time stamps of CTA 0 (softmax warp 2 lane 0 and the issuer), read back by
-// scratch/attn_trace.py through sgn_debug_attn_trace
+// make -C signerf_b200/csrc trace: clock64 time stamps of CTA 0 (lane 0 of the first warp of each softmax group and the
+// issuer), read back by scratch/attn_trace.py through sgn_debug_attn_trace
 #ifdef SGN_ATTN_TRACE
-__device__ long long g_trace[16 * 256];   // [event][key tile]
-#define TRACE(ev, j) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (j) < 256) g_trace[(ev) * 256 + (j)] = clock64(); } while (0)
+__device__ long long g_trace[32 * 256];   // [event + 16 * query tile][key tile]
+#define TRACE(ev, j) do { if (blockIdx.x == 0 && (j) < 256) g_trace[(ev) * 256 + (j)] = clock64(); } while (0)
 #else
 #define TRACE(ev, j) do { } while (0)
 #endif
-int g_attn_variant = 2;   // sgn_set_option "attn_variant" (2 = packed math + MUFU turns: +4.5 % over 1 on B200)
+// sgn_set_option "attn_variant" (bit flags): 1 = row maximum over eight FMNMX3 chains instead of four, 2 = free-running
+// softmax groups (no MUFU turns), 4 = the MMA issuer follows the static event order with blocking waits instead of
+// polling, 8 = producer / issuer are the two highest warps of the CTA instead of the two lowest
+int g_attn_variant = 12;  // static issuer order + producer / issuer on the highest warps: +2-3 % over 0 on B200
 int g_attn_idle_ns = 0;   // sgn_set_option "attn_idle_ns"
+int g_attn_split = 1;     // sgn_set_option "attn_split": 0 = never split the tail items over the keys
 
-template <int kVariant>
+__device__ __forceinline__ void decode_item(const AttnParams& p, int cta, int& item, int& part, int& kv0, int& n_kv) {
+  item = cta, part = 0, kv0 = 0, n_kv = p.n_kv_tiles;
+  if (cta >= p.n_full) {
+    const int r = cta - p.n_full;
+    item = p.n_full + r / p.split;
+    part = r % p.split;
+    kv0 = (int)((long long)part * p.n_kv_tiles / p.split);
+    n_kv = (int)((long long)(part + 1) * p.n_kv_tiles / p.split) - kv0;
+  }
+}
+
+template <int kFlags>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  constexpr bool kMax8 = (kFlags & 1) != 0;
+  constexpr bool kTurns = (kFlags & 2) == 0;
+  constexpr bool kStatic = (kFlags & 4) != 0;
+  constexpr bool kHigh = (kFlags & 8) != 0;
+  constexpr int kWarpProd = kHigh ? 8 : 0, kWarpIssue = kHigh ? 9 : 1;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;                          // Q_A, Q_B
@@ -169,10 +135,15 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   uint64_t* o_full = p_full + 2;               // P_x(j) V(j) complete (one phase per key tile)
   uint64_t* s_free = o_full + 2;               // S_x(j) is in registers
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
+  uint32_t* last_flag = tmem_slot + 1;         // split items: this CTA is the last of its item to arrive
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, head = blockIdx.y, img = blockIdx.z;
-  const int n_kv = p.n_kv_tiles;
+  // Work decode.  A launch is n_full whole items (one CTA each, all keys) followed by the tail items that would only
+  // fill part of a last wave: those are cut into `split` key ranges (one CTA each) whose partial (O, m, l) are combined
+  // by whichever CTA of the item finishes last.
+  int item, part, kv0, n_kv;   // n_kv: key tiles of this CTA, counted from 0 by j below; kv0: its first key tile
+  decode_item(p, blockIdx.x, item, part, kv0, n_kv);
+  const int qt = item % p.n_qt, head = (item / p.n_qt) % p.heads, img = item / (p.n_qt * p.heads);
 
   if (threadIdx.x == 0) {
     tc::tma_prefetch_desc(&tmQ);
@@ -191,7 +162,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
     tc::mbar_fence_init();
   }
-  if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
+  if (warp == kWarpIssue) tc::tmem_alloc(tmem_slot, 512);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -200,7 +171,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const uint32_t tO = tmem_base + 256;   // O_A cols 256..319, O_B cols 320..383
   const uint32_t tP = tmem_base + 384;   // P_A cols 384..447, P_B cols 448..511 (fp16 pairs: 128 keys = 64 columns)
 
-  if (warp == 0) {
+  if (warp == kWarpProd) {
     if (lane == 0) {  // ---------------- TMA producer
       tc::mbar_expect_tx(bar_q, 2 * kTileBytes);
       tc::tma_load_2d(sQ, &tmQ, bar_q, head * kHeadDim, img * p.T_q + qt * kQPerCta);
@@ -210,12 +181,12 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const uint32_t ph = (j / kKvStages) & 1;
         tc::mbar_wait(&kv_empty[s], ph ^ 1);
         tc::mbar_expect_tx(&kv_full[s], 2 * kTileBytes);
-        const int row = img * p.T_kv + j * kKvTile;
+        const int row = img * p.T_kv + (kv0 + j) * kKvTile;
         tc::tma_load_2d(sK + s * kTileBytes, &tmK, &kv_full[s], head * kHeadDim, row);
         tc::tma_load_2d(sV + s * kTileBytes, &tmV, &kv_full[s], head * kHeadDim, row);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kWarpIssue) {
     if (lane == 0) {  // ---------------- MMA issuer
       const uint32_t idesc_qk = tc::umma_idesc_f16(128, kKvTile, false, false);
       const uint32_t idesc_pv = tc::umma_idesc_f16(128, kHeadDim, false, true);  // B = V, MN-major
@@ -241,36 +212,65 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tc::tc_fence_after();
       issue_qk(0, 0);
       issue_qk(1, 0);
-      // Event loop: serve whichever of {S_x free -> next Q K^T, P_x ready -> P V} is ready, per query tile.
-      int qk_next[2] = {1, 1}, pv_next[2] = {0, 0};
-      while (pv_next[0] < n_kv || pv_next[1] < n_kv) {
-        bool progress = false;
-#pragma unroll
-        for (int x = 0; x < 2; ++x) {
-          const int jq = qk_next[x];
-          if (jq < n_kv && tc::mbar_test(&s_free[x], (jq - 1) & 1) &&
-              tc::mbar_test(&kv_full[jq % kKvStages], (jq / kKvStages) & 1)) {
+      if constexpr (kStatic) {
+        // The steady-state order of the events is fixed by the softmax groups' turns (S_B(j) read, P_A(j) stored,
+        // S_A(j+1) read, P_B(j) stored, ...): wait for them in that order with blocking (hardware-suspended) waits instead
+        // of polling four barriers from the sub-partition that also hosts two softmax warps.
+        for (int j = 0; j < n_kv; ++j) {
+          if (j + 1 < n_kv) {
+            tc::mbar_wait(&kv_full[(j + 1) % kKvStages], ((j + 1) / kKvStages) & 1);
+            tc::mbar_wait(&s_free[0], j & 1);
             tc::tc_fence_after();
-            if (x == 0) TRACE(8, jq);
-            issue_qk(x, jq);
-            qk_next[x] = jq + 1;
-            progress = true;
-          }
-          const int jp = pv_next[x];
-          if (jp < n_kv && tc::mbar_test(&p_full[x], jp & 1)) {
+            TRACE(8, j + 1);
+            issue_qk(0, j + 1);
+            tc::mbar_wait(&s_free[1], j & 1);
             tc::tc_fence_after();
-            if (x == 0) TRACE(9, jp);
-            issue_pv(x, jp);
-            pv_next[x] = jp + 1;
-            if (pv_next[x ^ 1] > jp) tc::umma_commit(&kv_empty[jp % kKvStages]);  // both tiles are through K/V(jp)
-            progress = true;
+            TRACE(24, j + 1);
+            issue_qk(1, j + 1);
           }
+          tc::mbar_wait(&p_full[0], j & 1);
+          tc::tc_fence_after();
+          TRACE(9, j);
+          issue_pv(0, j);
+          tc::mbar_wait(&p_full[1], j & 1);
+          tc::tc_fence_after();
+          TRACE(25, j);
+          issue_pv(1, j);
+          tc::umma_commit(&kv_empty[j % kKvStages]);   // both tiles are through K/V(j)
         }
-        if (!progress && p.idle_ns > 0) __nanosleep(p.idle_ns);
+      } else {
+        // Event loop: serve whichever of {S_x free -> next Q K^T, P_x ready -> P V} is ready, per query tile.
+        int qk_next[2] = {1, 1}, pv_next[2] = {0, 0};
+        while (pv_next[0] < n_kv || pv_next[1] < n_kv) {
+          bool progress = false;
+#pragma unroll
+          for (int x = 0; x < 2; ++x) {
+            const int jq = qk_next[x];
+            if (jq < n_kv && tc::mbar_test(&s_free[x], (jq - 1) & 1) &&
+                tc::mbar_test(&kv_full[jq % kKvStages], (jq / kKvStages) & 1)) {
+              tc::tc_fence_after();
+              TRACE(8 + 16 * x, jq);
+              issue_qk(x, jq);
+              qk_next[x] = jq + 1;
+              progress = true;
+            }
+            const int jp = pv_next[x];
+            if (jp < n_kv && tc::mbar_test(&p_full[x], jp & 1)) {
+              tc::tc_fence_after();
+              TRACE(9 + 16 * x, jp);
+              issue_pv(x, jp);
+              pv_next[x] = jp + 1;
+              if (pv_next[x ^ 1] > jp) tc::umma_commit(&kv_empty[jp % kKvStages]);  // both tiles are through K/V(jp)
+              progress = true;
+            }
+          }
+          if (!progress && p.idle_ns > 0) __nanosleep(p.idle_ns);
+        }
       }
     }
-  } else {  // ---------------- softmax warpgroups: x = 0 (warps 2-5) / 1 (warps 6-9); thread = query row = TMEM lane
-    const int x = (warp - 2) >> 2;
+  } else {  // ---------------- softmax warpgroups: x = 0 / 1 (four warps each); thread = query row = TMEM lane
+    const int sw = kHigh ? warp : warp - 2;
+    const int x = sw >> 2;
     const int lane_base = (warp & 3) * 32;
     const int row = lane_base + lane;
     const uint32_t lane_addr = (uint32_t)lane_base << 16;
@@ -279,26 +279,18 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t tp = tP + x * 64 + lane_addr;
     const uint32_t ts = tS + x * kKvTile + lane_addr;
     const uint32_t to = tO + x * kHeadDim + lane_addr;
+    const bool tr = (sw & 3) == 0 && lane == 0;
+    const int te = 16 * x;
 
-    // variants: 0 / 1 scalar math (1 = software-pipelined exponentials, the round-1 kernel); >= 2 packed math (FFMA2 /
-    // FADD2 / FMNMX3): 2 turn-taking, 3 free-running groups, 4 / 5 the same with a quarter of the exponentials on the FMA
-    // pipe (ex2_poly_pair), 6 / 7 with three eighths
-    constexpr bool kPacked = kVariant >= 2;
-    constexpr bool kFine = kVariant == 8 || kVariant == 9;   // 8: pair-granular software pipeline, free-running groups; 9: with turns
-    // 10 / 11: variant 2 with the MUFU turn taken earlier - at the top of the key tile (10: the other group only finishes its
-    // P store while this one loads / scans / exponentiates) or after the S load (11)
-    constexpr int kTurnAt = kVariant == 10 ? 1 : (kVariant == 11 ? 2 : 0);
-    constexpr bool kTurns = !(kVariant == 3 || kVariant == 5 || kVariant == 7 || kVariant == 8);
-    constexpr int kPolyOf8 = (kVariant == 6 || kVariant == 7) ? 3 : ((kVariant == 4 || kVariant == 5) ? 2 : 0);   // pairs out of every 8 that go to the FMA pipe
+    int kv_left = p.T_kv - kv0 * kKvTile;   // keys from this tile on
     if (kTurns && x == 1) named_arrive(1, 256);  // group A takes the first turn
     for (int j = 0; j < n_kv; ++j) {
-      const int kv_rem = p.T_kv - j * kKvTile;  // >= 1
-      const bool tr = warp == 2 && lane == 0;
-      if (tr) TRACE(0, j);
-      if (kTurns && kTurnAt == 1) named_sync(1 + x, 256);
+      const int kv_rem = kv_left;  // >= 1
+      kv_left -= kKvTile;
+      if (tr) TRACE(te + 0, j);
       tc::mbar_wait(&s_full[x], j & 1);
       tc::tc_fence_after();
-      if (tr) TRACE(1, j);
+      if (tr) TRACE(te + 1, j);
       uint32_t s[128];
 #pragma unroll
       for (int c = 0; c < 4; ++c) tc::tmem_ld32(ts + c * 32, s + c * 32);
@@ -306,15 +298,28 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&s_free[x]);     // the issuer may overwrite S_x with Q_x K_{j+1}^T now
-      if (tr) TRACE(2, j);
-      if (kTurns && kTurnAt == 2) named_sync(1 + x, 256);
+      if (tr) TRACE(te + 2, j);
       if (kv_rem < kKvTile) {
 #pragma unroll
         for (int q = 0; q < 128; ++q)
           if (q >= kv_rem) s[q] = 0xff800000u;  // -inf
       }
-      float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]);
-      if constexpr (kPacked) {
+      float mx;
+      if constexpr (kMax8) {
+        float m8[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) m8[c] = max3(__uint_as_float(s[c]), __uint_as_float(s[8 + c]), __uint_as_float(s[16 + c]));
+#pragma unroll
+        for (int q = 24; q < 120; q += 16) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) m8[c] = max3(m8[c], __uint_as_float(s[q + c]), __uint_as_float(s[q + 8 + c]));
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) m8[c] = fmaxf(m8[c], __uint_as_float(s[120 + c]));
+        mx = fmaxf(max3(m8[0], m8[1], m8[2]), max3(m8[3], m8[4], m8[5]));
+        mx = max3(mx, m8[6], m8[7]);
+      } else {
+        float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]);
         float mx2 = __uint_as_float(s[2]), mx3 = __uint_as_float(s[3]);
 #pragma unroll
         for (int q = 4; q < 124; q += 8) {
@@ -325,29 +330,26 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
         mx0 = max3(mx0, __uint_as_float(s[124]), __uint_as_float(s[125]));
         mx1 = max3(mx1, __uint_as_float(s[126]), __uint_as_float(s[127]));
-        mx0 = max3(mx0, mx2, mx3);
-      } else {
-#pragma unroll
-        for (int q = 2; q < 128; q += 2) {
-          mx0 = fmaxf(mx0, __uint_as_float(s[q]));
-          mx1 = fmaxf(mx1, __uint_as_float(s[q + 1]));
-        }
+        mx = fmaxf(max3(mx0, mx2, mx3), mx1);
       }
-      const float mx = fmaxf(mx0, mx1);
       // P_x(j-1) V(j-1) must be complete before P_x is rewritten or O_x rescaled; P_x(j) V(j) is not issued before
-      // this thread arrives on p_full, so O_x is quiescent in between.
-      // The wait is only needed before O is rescaled (rare) or P is rewritten (the first tcgen05.st, half a tile of
-      // exponentials later): variants >= 1 defer it, which takes the P.V latency off the softmax critical path.
-      constexpr bool kDeferO = kVariant >= 1;
+      // this thread arrives on p_full, so O_x is quiescent in between.  The wait is only needed before O is rescaled
+      // (rare) or P is rewritten (the first tcgen05.st, half a tile of exponentials later), which takes the P.V
+      // latency off the softmax critical path.
       bool o_ready = j == 0;
+      auto wait_o = [&]() {
+        if (!o_ready) {   // warp-uniform
+          if (tr) TRACE(te + 5, j);
+          tc::mbar_wait(&o_full[x], (j - 1) & 1);
+          if (tr) TRACE(te + 6, j);
+          tc::tc_fence_after();
+          o_ready = true;
+        }
+      };
       const bool grow = (mx - m_run) * sc > 8.f;   // also true on the first tile (m_run = -inf)
       const bool any_grow = __any_sync(0xffffffffu, grow);
-      if (j > 0 && (!kDeferO || any_grow)) {
-        tc::mbar_wait(&o_full[x], (j - 1) & 1);
-        tc::tc_fence_after();
-        o_ready = true;
-      }
       if (any_grow && j > 0) {
+        wait_o();
         const float alpha = grow ? ex2((m_run - mx) * sc) : 1.f;
         uint32_t o[16];
 #pragma unroll
@@ -363,194 +365,138 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
       if (grow) m_run = mx;
       const float neg_m = -m_run * sc;
-      float psum0 = 0.f, psum1 = 0.f;
-      if (tr) TRACE(3, j);
-      if (kTurns && kTurnAt == 0) named_sync(1 + x, 256);            // my turn on the MUFU pipe
-      if (tr) TRACE(4, j);
-      if constexpr (kVariant == 0) {
+      if (tr) TRACE(te + 3, j);
+      if (kTurns) named_sync(1 + x, 256);            // my turn on the MUFU pipe
+      if (tr) TRACE(te + 4, j);
+      // Packed math: scale + shift as FFMA2, row sums as FADD2, 2 packed accumulator chains; software-pipelined by one
+      // 16-key block: the exponentials of block b+1 (in place over the S registers) are issued before block b is summed
+      // and packed, so no MUFU result is consumed right behind its issue.
+      const uint64_t sc2 = pk2(sc, sc), nm2 = pk2(neg_m, neg_m);
+      uint64_t acc_a = pk2(0.f, 0.f), acc_b = pk2(0.f, 0.f);
+      auto exp_block = [&](int b) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {      // 64 keys -> 32 packed columns per tcgen05.st
-          uint32_t pk[32];
-  #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            float e[8];
-  #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float t = fmaf(__uint_as_float(s[c * 64 + g * 8 + q]), sc, neg_m);
-              e[q] = (kPolyEvery > 0 && (q % kPolyEvery) == kPolyEvery - 1) ? ex2_poly(t) : ex2(t);
-            }
-            psum0 += (e[0] + e[1]) + (e[2] + e[3]);
-            psum1 += (e[4] + e[5]) + (e[6] + e[7]);
-  #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              __half2 h = __floats2half2_rn(e[2 * q], e[2 * q + 1]);
-              pk[g * 4 + q] = *reinterpret_cast<uint32_t*>(&h);
-            }
-          }
-          tc::tmem_st32(tp + c * 32, pk);
+        for (int q = 0; q < 8; ++q) {
+          const uint64_t t = fma2(pk2u(s[b * 16 + 2 * q], s[b * 16 + 2 * q + 1]), sc2, nm2);
+          float t0, t1;
+          upk2(t, t0, t1);
+          s[b * 16 + 2 * q] = __float_as_uint(ex2(t0));
+          s[b * 16 + 2 * q + 1] = __float_as_uint(ex2(t1));
         }
-      } else if constexpr (kFine) {
-        // Pair-granular software pipeline, every instruction pinned in program order: per pair of keys
-        //     FFMA2 (scale + shift of the NEXT pair) | MUFU.EX2 x2 (this pair) | FADD2 + F2FP (the pair 8 pairs back)
-        // so that the MUFU pipe (8 clk per warp instruction) never waits behind a burst of the other instructions: 5 issue
-        // slots per 16 MUFU clocks, and a MUFU result is consumed 128 clocks after its issue.
-        const uint64_t sc2 = pk2(sc, sc), nm2 = pk2(neg_m, neg_m);
-        uint64_t acc_a = pk2(0.f, 0.f), acc_b = pk2(0.f, 0.f);
-        uint32_t pk[32];
-        uint64_t t_cur = fma2_v(pk2u(s[0], s[1]), sc2, nm2);
+      };
+      exp_block(0);
+      uint32_t pk[32];
 #pragma unroll
-        for (int i = 0; i < 64 + 8; ++i) {      // i: pair index of the exponentials; i - 8: pair being summed / packed
-          uint64_t t_next = t_cur;
-          if (i + 1 < 64) t_next = fma2_v(pk2u(s[2 * i + 2], s[2 * i + 3]), sc2, nm2);
-          if (i < 64) {
-            float t0, t1;
-            upk2(t_cur, t0, t1);
-            s[2 * i] = __float_as_uint(ex2_v(t0));
-            s[2 * i + 1] = __float_as_uint(ex2_v(t1));
-          }
-          t_cur = t_next;
-          if (i >= 8) {
-            const int c = i - 8;
-            const uint64_t e2 = pk2u(s[2 * c], s[2 * c + 1]);
-            if (c & 1) acc_b = add2_v(acc_b, e2);
-            else acc_a = add2_v(acc_a, e2);
-            pk[c & 31] = cvt_h2_v(__uint_as_float(s[2 * c]), __uint_as_float(s[2 * c + 1]));
-            if ((c & 31) == 31) {
-              if (!o_ready) {   // warp-uniform
-                if (tr) TRACE(5, j);
-                tc::mbar_wait(&o_full[x], (j - 1) & 1);
-                if (tr) TRACE(6, j);
-                tc::tc_fence_after();
-                o_ready = true;
-              }
-              tc::tmem_st32(tp + (c >> 5) * 32, pk);
-            }
-          }
+      for (int b = 0; b < 8; ++b) {
+        if (b + 1 < 8) exp_block(b + 1);
+#pragma unroll
+        for (int q = 0; q < 8; q += 2) {
+          acc_a = add2(acc_a, pk2u(s[b * 16 + 2 * q], s[b * 16 + 2 * q + 1]));
+          acc_b = add2(acc_b, pk2u(s[b * 16 + 2 * q + 2], s[b * 16 + 2 * q + 3]));
         }
-        float a0, a1, b0, b1;
-        upk2(acc_a, a0, a1);
-        upk2(acc_b, b0, b1);
-        psum0 = a0 + a1;
-        psum1 = b0 + b1;
-      } else if constexpr (kPacked) {
-        // Packed math: scale + shift as FFMA2, row sums as FADD2, 2 packed accumulator chains; software-pipelined by
-        // one 16-key block like variant 1.  kPolyOf8 of every 8 pairs take the polynomial instead of MUFU.EX2.
-        const uint64_t sc2 = pk2(sc, sc), nm2 = pk2(neg_m, neg_m);
-        uint64_t acc_a = pk2(0.f, 0.f), acc_b = pk2(0.f, 0.f);
-        auto exp_block = [&](int b) {
+        const float* e = reinterpret_cast<const float*>(s) + b * 16;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const uint64_t t = fma2(pk2u(s[b * 16 + 2 * q], s[b * 16 + 2 * q + 1]), sc2, nm2);
-            if (q < kPolyOf8) {
-              ex2_poly_pair(t, s[b * 16 + 2 * q], s[b * 16 + 2 * q + 1]);
-            } else {
-              float t0, t1;
-              upk2(t, t0, t1);
-              s[b * 16 + 2 * q] = __float_as_uint(ex2(t0));
-              s[b * 16 + 2 * q + 1] = __float_as_uint(ex2(t1));
-            }
-          }
-        };
-        exp_block(0);
-        uint32_t pk[32];
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-          if (b + 1 < 8) exp_block(b + 1);
-#pragma unroll
-          for (int q = 0; q < 8; q += 2) {
-            acc_a = add2(acc_a, pk2u(s[b * 16 + 2 * q], s[b * 16 + 2 * q + 1]));
-            acc_b = add2(acc_b, pk2u(s[b * 16 + 2 * q + 2], s[b * 16 + 2 * q + 3]));
-          }
-          const float* e = reinterpret_cast<const float*>(s) + b * 16;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            __half2 h = __floats2half2_rn(e[2 * q], e[2 * q + 1]);
-            pk[(b & 3) * 8 + q] = *reinterpret_cast<uint32_t*>(&h);
-          }
-          if ((b & 3) == 3) {
-            if (!o_ready) {   // warp-uniform
-              if (tr) TRACE(5, j);
-              tc::mbar_wait(&o_full[x], (j - 1) & 1);
-              if (tr) TRACE(6, j);
-              tc::tc_fence_after();
-              o_ready = true;
-            }
-            tc::tmem_st32(tp + (b >> 2) * 32, pk);
-          }
+        for (int q = 0; q < 8; ++q) {
+          __half2 h = __floats2half2_rn(e[2 * q], e[2 * q + 1]);
+          pk[(b & 3) * 8 + q] = *reinterpret_cast<uint32_t*>(&h);
         }
-        float a0, a1, b0, b1;
-        upk2(acc_a, a0, a1);
-        upk2(acc_b, b0, b1);
-        psum0 = a0 + a1;
-        psum1 = b0 + b1;
-      } else {
-        // Software-pipelined: the exponentials of block b+1 (16 keys, in place over the S registers) are issued before
-        // block b is summed and packed, so no MUFU result is consumed right behind its issue.
-        auto exp_block = [&](int b) {
-#pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            const float t = fmaf(__uint_as_float(s[b * 16 + q]), sc, neg_m);
-            s[b * 16 + q] = __float_as_uint(ex2(t));
-          }
-        };
-        exp_block(0);
-        uint32_t pk[32];
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-          if (b + 1 < 8) exp_block(b + 1);
-          const float* e = reinterpret_cast<const float*>(s) + b * 16;
-          psum0 += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[8] + e[9]) + (e[10] + e[11]));
-          psum1 += ((e[4] + e[5]) + (e[6] + e[7])) + ((e[12] + e[13]) + (e[14] + e[15]));
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            __half2 h = __floats2half2_rn(e[2 * q], e[2 * q + 1]);
-            pk[(b & 3) * 8 + q] = *reinterpret_cast<uint32_t*>(&h);
-          }
-          if ((b & 3) == 3) {
-            if (!o_ready) {   // warp-uniform
-              if (tr) TRACE(5, j);
-              tc::mbar_wait(&o_full[x], (j - 1) & 1);
-              if (tr) TRACE(6, j);
-              tc::tc_fence_after();
-              o_ready = true;
-            }
-            tc::tmem_st32(tp + (b >> 2) * 32, pk);
-          }
+        if ((b & 3) == 3) {
+          wait_o();
+          tc::tmem_st32(tp + (b >> 2) * 32, pk);
         }
       }
       if (kTurns) named_arrive(2 - x, 256);          // hand the turn to the other warpgroup
+      float a0, a1, b0, b1;
+      upk2(acc_a, a0, a1);
+      upk2(acc_b, b0, b1);
       tc::tmem_st_wait();
-      l_run += psum0 + psum1;
+      l_run += (a0 + a1) + (b0 + b1);
       tc::tc_fence_before();          // P_x written, O_x accesses done before the issuer touches them
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&p_full[x]);
-      if (tr) TRACE(7, j);
+      if (tr) TRACE(te + 7, j);
     }
     if (kTurns && x == 0) named_sync(1, 256);      // absorb group B's last hand-over
     // O_x complete after the last P.V
     tc::mbar_wait(&o_full[x], (n_kv - 1) & 1);
     tc::tc_fence_after();
-    const int q_row = qt * kQPerCta + x * kQTile + row;
-    const float inv = 1.f / l_run;
-    __half* orow = p.out + ((long long)img * p.T_q + q_row) * p.ldo + head * kHeadDim;
+    // the work decode again, from an opaque copy of the CTA index: nothing of it stays live across the key loop
+    int cta;
+    asm volatile("mov.u32 %0, %%ctaid.x;" : "=r"(cta));
+    int item_e, part_e, kv0_e, n_kv_e;
+    decode_item(p, cta, item_e, part_e, kv0_e, n_kv_e);
+    const bool is_part = cta >= p.n_full;
+    const int q_row = (item_e % p.n_qt) * kQPerCta + x * kQTile + row;
+    __half* orow = p.out + ((long long)(item_e / (p.n_qt * p.heads)) * p.T_q + q_row) * p.ldo + ((item_e / p.n_qt) % p.heads) * kHeadDim;
+    if (!is_part) {
+      const float inv = 1.f / l_run;
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t o[32];
-      tc::tmem_ld32(to + c * 32, o);
-      tc::tmem_ld_wait();
-      if (q_row < p.T_q) {
-        __half2 h[16];
+      for (int c = 0; c < 2; ++c) {
+        uint32_t o[32];
+        tc::tmem_ld32(to + c * 32, o);
+        tc::tmem_ld_wait();
+        if (q_row < p.T_q) {
+          __half2 h[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          h[i] = __floats2half2_rn(__uint_as_float(o[2 * i]) * inv, __uint_as_float(o[2 * i + 1]) * inv);
+          for (int i = 0; i < 16; ++i)
+            h[i] = __floats2half2_rn(__uint_as_float(o[2 * i]) * inv, __uint_as_float(o[2 * i + 1]) * inv);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(orow + c * 32)[i] = reinterpret_cast<uint4*>(h)[i];
+          for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(orow + c * 32)[i] = reinterpret_cast<uint4*>(h)[i];
+        }
+      }
+    } else {
+      // Partial result of this key range: unnormalised O, m, l, column-major over the 256 query rows of the item so
+      // that a warp's stores coalesce.  The CTA of the item that arrives last folds the `split` partials together.
+      const int r256 = x * kQTile + row;
+      float* base = p.part + (size_t)(item_e - p.n_full) * p.split * 66 * 256;
+      float* mine = base + (size_t)part_e * 66 * 256 + r256;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t o[32];
+        tc::tmem_ld32(to + c * 32, o);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mine[(c * 32 + i) * 256] = __uint_as_float(o[i]);
+      }
+      mine[64 * 256] = m_run;
+      mine[65 * 256] = l_run;
+      __threadfence();
+      named_sync(3, 256);
+      if (sw == 0 && lane == 0) {
+        const unsigned prev = atomicAdd(&p.count[item_e - p.n_full], 1u);
+        const bool last = prev == (unsigned)p.split - 1;
+        if (last) p.count[item_e - p.n_full] = 0;   // ready for the next launch
+        *last_flag = last ? 1u : 0u;
+      }
+      named_sync(3, 256);
+      if (*last_flag) {
+        __threadfence();
+        float m_all = -INFINITY;
+        for (int q = 0; q < p.split; ++q) m_all = fmaxf(m_all, __ldcg(base + (size_t)q * 66 * 256 + 64 * 256 + r256));
+        float acc[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+        float l_all = 0.f;
+        for (int q = 0; q < p.split; ++q) {
+          const float* src = base + (size_t)q * 66 * 256 + r256;
+          const float w = ex2((__ldcg(src + 64 * 256) - m_all) * sc);
+          l_all = fmaf(w, __ldcg(src + 65 * 256), l_all);
+#pragma unroll
+          for (int i = 0; i < 64; ++i) acc[i] = fmaf(w, __ldcg(src + i * 256), acc[i]);
+        }
+        if (q_row < p.T_q) {
+          const float inv = 1.f / l_all;
+          __half2 h[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) h[i] = __floats2half2_rn(acc[2 * i] * inv, acc[2 * i + 1] * inv);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) reinterpret_cast<uint4*>(orow)[i] = reinterpret_cast<uint4*>(h)[i];
+        }
       }
     }
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kWarpIssue) {
     __syncwarp();
     tc::tmem_dealloc(tmem_base, 512);
   }
@@ -708,12 +654,36 @@ using namespace sgn;
 
 #ifdef SGN_ATTN_TRACE
 extern "C" int sgn_debug_attn_trace(long long* h_out) {
-  return cudaMemcpyFromSymbol(h_out, g_trace, sizeof(long long) * 16 * 256) == cudaSuccess ? 0 : -1;
+  return cudaMemcpyFromSymbol(h_out, g_trace, sizeof(long long) * 32 * 256) == cudaSuccess ? 0 : -1;
 }
 #endif
 
+// How a launch of `items` (query pair tile, head, image) work items with n_kv key tiles each is laid over n_sm SMs (one
+// CTA per SM at a time): whole waves run one CTA per item; the items of an under-filled last wave are cut into `split`
+// key ranges when that shortens the tail (cost in key-tile periods, + 2 per CTA for its prologue and the partial
+// store / combine).  T = 4 096 with 20 heads x 2 images on 148 SMs: 640 items = 4.32 waves -> 592 whole items + 48 x 3
+// parts of 10-11 key tiles, 128 + 13 instead of 160 periods.
+static void plan_split(int items, int n_kv, int n_sm, int* n_full, int* split) {
+  *n_full = items;
+  *split = 1;
+  const int rem = items % n_sm;
+  if (rem == 0 || !g_attn_split) return;
+  int best = 1;
+  double best_cost = n_kv + 2;
+  for (int s = 2; s <= 8 && n_kv / s >= 4; ++s) {
+    const double cost = (double)((rem * s + n_sm - 1) / n_sm) * ((n_kv + s - 1) / s + 2);
+    if (cost < 0.95 * best_cost) best = s, best_cost = cost;
+  }
+  if (best > 1) *n_full = items - rem, *split = best;
+}
+
+static size_t split_workspace_bytes(int tail_items, int split) {
+  return (size_t)tail_items * split * 66 * 256 * sizeof(float) + (size_t)tail_items * sizeof(unsigned);
+}
+
 static int attention_impl(const void* d_q, int64_t ldq, const void* d_k, int64_t ldk, const void* d_v, int64_t ldv, int B,
-                          int heads, int T_q, int T_kv, float scale, void* d_out, int64_t ldo, int causal, void* stream) {
+                          int heads, int T_q, int T_kv, float scale, void* d_out, int64_t ldo, int causal, void* d_ws,
+                          int64_t ws_bytes, void* stream) {
   SGN_CHECK_ARG(B >= 0 && heads > 0 && T_q > 0 && T_kv > 0, "bad attention shape");
   if (B == 0) return SGN_OK;
   SGN_CHECK_ARG(d_q && d_k && d_v && d_out, "null pointer");
@@ -723,33 +693,28 @@ static int attention_impl(const void* d_q, int64_t ldq, const void* d_k, int64_t
   SGN_CHECK_ARG(((reinterpret_cast<uintptr_t>(d_q) | reinterpret_cast<uintptr_t>(d_k) | reinterpret_cast<uintptr_t>(d_v) |
                   reinterpret_cast<uintptr_t>(d_out)) & 15) == 0, "operands must be 16-byte aligned");
   SGN_CHECK_ARG(!causal || (T_kv <= kXaKv && T_q == T_kv), "causal attention is built for self-attention over <= 80 tokens");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (T_kv <= kXaKv && (g_attn_short_kv || causal)) {
     // ~4 resident waves: enough query tiles per CTA to amortise its K / V load, enough CTAs to fill the GPU
     const int tiles = (T_q + kXaQ - 1) / kXaQ;
     const long long want = 4ll * sm_count();
     int tiles_per_cta = (int)std::max<long long>(1, std::min<long long>(8, (long long)tiles * heads * B / want));
     dim3 grid((tiles + tiles_per_cta - 1) / tiles_per_cta, heads, B);
-    k_cross_attention<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+    k_cross_attention<<<grid, 128, 0, st>>>(
         reinterpret_cast<const __half*>(d_q), ldq, reinterpret_cast<const __half*>(d_k), ldk,
         reinterpret_cast<const __half*>(d_v), ldv, T_q, T_kv, scale * 1.4426950408889634f,
         reinterpret_cast<__half*>(d_out), ldo, tiles_per_cta * kXaQ, causal);
     SGN_LAUNCH_CHECK();
     return SGN_OK;
   }
+  using Kern = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, AttnParams);
+  static const Kern kerns[16] = {k_attention_tc<0>,  k_attention_tc<1>,  k_attention_tc<2>,  k_attention_tc<3>,
+                                 k_attention_tc<4>,  k_attention_tc<5>,  k_attention_tc<6>,  k_attention_tc<7>,
+                                 k_attention_tc<8>,  k_attention_tc<9>,  k_attention_tc<10>, k_attention_tc<11>,
+                                 k_attention_tc<12>, k_attention_tc<13>, k_attention_tc<14>, k_attention_tc<15>};
   static bool attr_set = false;
   if (!attr_set) {
-    SGN_CUDA(cudaFuncSetAttribute(k_attention_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
-    SGN_CUDA(cudaFuncSetAttribute(k_attention_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
-    SGN_CUDA(cudaFuncSetAttribute(k_attention_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
-    SGN_CUDA(cudaFuncSetAttribute(k_attention_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
-    SGN_CUDA(cudaFuncSetAttribute(k_attention_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
-    SGN_CUDA(cudaFuncSetAttribute(k_attention_tc<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
-    SGN_CUDA(cudaFuncSetAttribute(k_attention_tc<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
-    SGN_CUDA(cudaFuncSetAttribute(k_attention_tc<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
-    SGN_CUDA(cudaFuncSetAttribute(k_attention_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
-    SGN_CUDA(cudaFuncSetAttribute(k_attention_tc<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
-    SGN_CUDA(cudaFuncSetAttribute(k_attention_tc<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
-    SGN_CUDA(cudaFuncSetAttribute(k_attention_tc<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
+    for (Kern k : kerns) SGN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
     attr_set = true;
   }
   CUtensorMap tmQ, tmK, tmV;
@@ -769,26 +734,54 @@ static int attention_impl(const void* d_q, int64_t ldq, const void* d_k, int64_t
   p.scale_log2e = scale * 1.4426950408889634f;
   p.out = reinterpret_cast<__half*>(d_out);
   p.ldo = ldo;
-  dim3 grid((T_q + kQPerCta - 1) / kQPerCta, heads, B);
+  p.n_qt = (T_q + kQPerCta - 1) / kQPerCta;
+  p.heads = heads;
+  const int items = p.n_qt * heads * B;
+  p.n_full = items, p.split = 1;
+  p.part = nullptr, p.count = nullptr;
+  if (d_ws) {   // key-range split of the tail items needs the caller's workspace
+    plan_split(items, p.n_kv_tiles, sm_count(), &p.n_full, &p.split);
+    if (p.split > 1) {
+      const int tail = items - p.n_full;
+      const size_t need = split_workspace_bytes(tail, p.split);
+      SGN_CHECK_ARG((reinterpret_cast<uintptr_t>(d_ws) & 15) == 0 && ws_bytes >= (int64_t)need,
+                    "attention workspace too small or misaligned (sgn_attention_workspace_bytes)");
+      p.part = reinterpret_cast<float*>(d_ws);
+      p.count = reinterpret_cast<unsigned*>(p.part + (size_t)tail * p.split * 66 * 256);
+      SGN_CUDA(cudaMemsetAsync(p.count, 0, (size_t)tail * sizeof(unsigned), st));
+    }
+  }
   p.idle_ns = g_attn_idle_ns;
-  using Kern = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, AttnParams);
-  static const Kern kerns[12] = {k_attention_tc<0>, k_attention_tc<1>, k_attention_tc<2>, k_attention_tc<3>,
-                                 k_attention_tc<4>, k_attention_tc<5>, k_attention_tc<6>, k_attention_tc<7>,
-                                 k_attention_tc<8>, k_attention_tc<9>, k_attention_tc<10>, k_attention_tc<11>};
-  Kern kern = kerns[g_attn_variant % 12];
-  kern<<<grid, kAttnThreads, kAttnSmem, reinterpret_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
+  Kern kern = kerns[g_attn_variant & 15];
+  kern<<<p.n_full + (items - p.n_full) * p.split, kAttnThreads, kAttnSmem, st>>>(tmQ, tmK, tmV, p);
   SGN_LAUNCH_CHECK();
   return SGN_OK;
+}
+
+extern "C" int64_t sgn_attention_workspace_bytes(int B, int heads, int T_q, int T_kv) {
+  if (B <= 0 || heads <= 0 || T_q <= 0 || T_kv <= 0 || (T_kv <= kXaKv && g_attn_short_kv)) return 0;
+  int dev_ok = 0;
+  if (cudaGetDeviceCount(&dev_ok) != cudaSuccess || dev_ok == 0) return 0;
+  const int n_qt = (T_q + kQPerCta - 1) / kQPerCta, items = n_qt * heads * B;
+  int n_full, split;
+  plan_split(items, (T_kv + kKvTile - 1) / kKvTile, sm_count(), &n_full, &split);
+  return split > 1 ? (int64_t)split_workspace_bytes(items - n_full, split) : 0;
+}
+
+extern "C" int sgn_attention_f16_ws(const void* d_q, int64_t ldq, const void* d_k, int64_t ldk, const void* d_v,
+                                    int64_t ldv, int B, int heads, int T_q, int T_kv, float scale, void* d_out,
+                                    int64_t ldo, void* d_ws, int64_t ws_bytes, void* stream) {
+  return attention_impl(d_q, ldq, d_k, ldk, d_v, ldv, B, heads, T_q, T_kv, scale, d_out, ldo, 0, d_ws, ws_bytes, stream);
 }
 
 extern "C" int sgn_attention_f16(const void* d_q, int64_t ldq, const void* d_k, int64_t ldk, const void* d_v,
                                  int64_t ldv, int B, int heads, int T_q, int T_kv, float scale, void* d_out,
                                  int64_t ldo, void* stream) {
-  return attention_impl(d_q, ldq, d_k, ldk, d_v, ldv, B, heads, T_q, T_kv, scale, d_out, ldo, 0, stream);
+  return attention_impl(d_q, ldq, d_k, ldk, d_v, ldv, B, heads, T_q, T_kv, scale, d_out, ldo, 0, nullptr, 0, stream);
 }
 
 extern "C" int sgn_attention_causal_f16(const void* d_q, int64_t ldq, const void* d_k, int64_t ldk, const void* d_v,
                                         int64_t ldv, int B, int heads, int T, float scale, void* d_out, int64_t ldo,
                                         void* stream) {
-  return attention_impl(d_q, ldq, d_k, ldk, d_v, ldv, B, heads, T, T, scale, d_out, ldo, 1, stream);
+  return attention_impl(d_q, ldq, d_k, ldk, d_v, ldv, B, heads, T, T, scale, d_out, ldo, 1, nullptr, 0, stream);
 }

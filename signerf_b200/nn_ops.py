@@ -140,9 +140,12 @@ def attention_f16(q: Tensor, k: Tensor, v: Tensor, batch: int, heads: int, out: 
     if out is None:
         out = torch.empty((q.shape[0], heads * 64), dtype=torch.float16, device=q.device)
     with torch.cuda.device(q.device), _span(f"k_attention_tc {batch}x{heads}x{Tq}x{Tkv}" if PROFILE_SHAPES else "k_attention_tc", 4.0 * batch * heads * Tq * Tkv * 64):
-        _lib.check(_lib.load().sgn_attention_f16(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0),
-                                                 batch, heads, Tq, Tkv, 0.125, _ptr(out), out.stride(0),
-                                                 _stream(q.device)))
+        lib = _lib.load()
+        need = int(lib.sgn_attention_workspace_bytes(batch, heads, Tq, Tkv))   # > 0: tail items are split over the keys
+        ws = torch.empty(need, dtype=torch.uint8, device=q.device) if need else None
+        _lib.check(lib.sgn_attention_f16_ws(_ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0),
+                                            batch, heads, Tq, Tkv, 0.125, _ptr(out), out.stride(0),
+                                            _ptr(ws) if need else None, need, _stream(q.device)))
     return out
 
 
