@@ -27,28 +27,43 @@
 
 namespace sgn {
 
-constexpr int kAttnThreads = 320;
 constexpr int kHeadDim = 64;
-constexpr int kQTile = 128, kKvTile = 128;
-constexpr int kQPerCta = 2 * kQTile;
-constexpr int kKvStages = 4;
-constexpr int kTileBytes = 128 * 64 * 2;  // one [128 x 64] fp16 tile, 128-B rows, SWIZZLE_128B
-constexpr size_t kAttnSmem = 1024 + kTileBytes * (2 + 2 * kKvStages) + 256;
+constexpr int kQTile = 128;
+constexpr int kQTileBytes = 128 * 64 * 2;  // one [128 x 64] fp16 tile, 128-B rows, SWIZZLE_128B
+
+// Shape of one CTA: kGroups query tiles of 128 rows (one softmax warpgroup each) share every K / V tile of kKv keys.
+//   <2, 128>: S 2x128 + O 2x64 + P 2x64 = 512 TMEM columns, two softmax warps per SM sub-partition taking MUFU turns
+//   <3, 64> : S 3x64 + P 3x32 + O 3x64 = 480 columns, three free-running softmax warps per sub-partition: a warp's serial
+//             chain per key tile (S load, row maximum, exponentials, P store, two barrier round trips) is what bounds the
+//             two-group kernel (~2 950 cycles per 2 x 128 x 128 scores against 2 048 of MUFU time); with half-size tiles
+//             and a third warp the MUFU pipe always has an exponential to issue
+template <int kGroups, int kKv>
+struct AttnShape {
+  static constexpr int kThreads = (2 + 4 * kGroups) * 32;
+  static constexpr int kQPerCta = kGroups * kQTile;
+  static constexpr int kKvBytes = kKv * 64 * 2;
+  static constexpr int kStages = kKv == 128 ? 4 : 6;
+  static constexpr size_t kSmem = 1024 + (size_t)kQTileBytes * kGroups + (size_t)2 * kStages * kKvBytes + 256;
+  static constexpr int kColS = 0, kColP = kGroups * kKv, kColO = kColP + kGroups * kKv / 2;   // TMEM column map
+  static_assert(kColO + kGroups * kHeadDim <= 512, "tensor memory");
+};
 
 struct AttnParams {
   int T_q, T_kv, n_kv_tiles;
-  int n_qt, heads;   // work item -> (query pair tile, head, image): item = qt + n_qt * (head + heads * image)
+  int n_qt, heads;   // work item -> (query tile group, head, image): item = qt + n_qt * (head + heads * image)
   int n_full, split; // CTAs [0, n_full) take a whole item; the others 1/split of the key tiles of one of the tail items
-  int idle_ns;       // MMA-issuer back-off when neither tile has work (0 = spin; polling issuer only)
+  int idle_ns;       // MMA-issuer back-off when no tile has work (0 = spin; polling issuer only)
   float scale_log2e;
   __half* out;
   long long ldo;
-  float* part;       // [tail item][split][66][256]: unnormalised O (64 columns), m, l of every query row
+  float* part;       // [tail item][split][66][rows per CTA]: unnormalised O (64 columns), m, l of every query row
   unsigned* count;   // [tail item] arrivals (zero at launch; the combining CTA resets its counter)
 };
 
-// named barriers 1 / 2: the exp2 sections of the two softmax warpgroups take turns on the MUFU pipe, which staggers
-// them by half a period: while one exponentiates, the other loads its next S row and finds the row maximum.
+// named barriers 1 / 2: the exp2 sections of the two softmax warpgroups of the <2, 128> shape take turns on the MUFU
+// pipe, which staggers them by half a period: while one exponentiates, the other loads its next S row and finds the row
+// maximum.  (ptxas moves about half of a tile's MUFU instructions above the bar.sync; pinning them behind it with data
+// dependencies was measured slower - DESIGN.md.)
 __device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void named_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
@@ -87,18 +102,19 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
   return d;
 }
 
-// make -C signerf_b200/csrc trace: clock64 time stamps of CTA 0 (lane 0 of the first warp of each softmax group and the
-// issuer), read back by scratch/attn_trace.py through sgn_debug_attn_trace
+// make -C signerf_b200/csrc trace: clock64 time stamps of CTA 0 (lane 0 of the first warp of softmax groups 0 / 1 and
+// the issuer), read back by scratch/attn_trace.py through sgn_debug_attn_trace
 #ifdef SGN_ATTN_TRACE
 __device__ long long g_trace[32 * 256];   // [event + 16 * query tile][key tile]
-#define TRACE(ev, j) do { if (blockIdx.x == 0 && (j) < 256) g_trace[(ev) * 256 + (j)] = clock64(); } while (0)
+#define TRACE(ev, j) do { if (blockIdx.x == 0 && (j) < 256 && (ev) < 32) g_trace[(ev) * 256 + (j)] = clock64(); } while (0)
 #else
 #define TRACE(ev, j) do { } while (0)
 #endif
-// sgn_set_option "attn_variant" (bit flags): 1 = row maximum over eight FMNMX3 chains instead of four, 2 = free-running
-// softmax groups (no MUFU turns), 4 = the MMA issuer follows the static event order with blocking waits instead of
-// polling, 8 = producer / issuer are the two highest warps of the CTA instead of the two lowest
-int g_attn_variant = 12;  // static issuer order + producer / issuer on the highest warps: +2-3 % over 0 on B200
+// sgn_set_option "attn_variant" (bit flags): 1 = the MMA issuer follows the static event order with blocking waits
+// instead of polling, 2 = producer / issuer are the two highest warps of the CTA instead of the two lowest
+int g_attn_variant = 3;
+int g_attn_shape = 0;     // sgn_set_option "attn_shape": 0 = two query tiles x 128-key tiles (default), 1 = three x 64-key tiles (measured slower:
+                          // every tcgen05.mma costs >= 60 cycles whatever its N, so 64-key Q K^T tiles saturate the tensor pipe)
 int g_attn_idle_ns = 0;   // sgn_set_option "attn_idle_ns"
 int g_attn_split = 1;     // sgn_set_option "attn_split": 0 = never split the tail items over the keys
 
@@ -113,28 +129,30 @@ __device__ __forceinline__ void decode_item(const AttnParams& p, int cta, int& i
   }
 }
 
-template <int kFlags>
-__global__ void __launch_bounds__(kAttnThreads, 1)
+template <int kFlags, int kGroups, int kKv>
+__global__ void __launch_bounds__((2 + 4 * kGroups) * 32, 1)
 k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
-  constexpr bool kMax8 = (kFlags & 1) != 0;
-  constexpr bool kTurns = (kFlags & 2) == 0;
-  constexpr bool kStatic = (kFlags & 4) != 0;
-  constexpr bool kHigh = (kFlags & 8) != 0;
-  constexpr int kWarpProd = kHigh ? 8 : 0, kWarpIssue = kHigh ? 9 : 1;
+  using Sh = AttnShape<kGroups, kKv>;
+  constexpr bool kTurns = kGroups == 2;
+  constexpr bool kStatic = (kFlags & 1) != 0;
+  constexpr bool kHigh = (kFlags & 2) != 0;
+  constexpr int kWarpProd = kHigh ? 4 * kGroups : 0, kWarpIssue = kHigh ? 4 * kGroups + 1 : 1;
+  constexpr int kStages = Sh::kStages, kKvBytes = Sh::kKvBytes;
+  constexpr int kSoftThreads = 128 * kGroups;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sQ = smem;                          // Q_A, Q_B
-  uint8_t* sK = sQ + 2 * kTileBytes;
-  uint8_t* sV = sK + kKvStages * kTileBytes;
-  uint64_t* bar_q = reinterpret_cast<uint64_t*>(sV + kKvStages * kTileBytes);
+  uint8_t* sQ = smem;                          // Q_0 .. Q_{kGroups-1}
+  uint8_t* sK = sQ + kGroups * kQTileBytes;
+  uint8_t* sV = sK + kStages * kKvBytes;
+  uint64_t* bar_q = reinterpret_cast<uint64_t*>(sV + kStages * kKvBytes);
   uint64_t* kv_full = bar_q + 1;
-  uint64_t* kv_empty = kv_full + kKvStages;
-  uint64_t* s_full = kv_empty + kKvStages;     // [2] per query tile
-  uint64_t* p_full = s_full + 2;
-  uint64_t* o_full = p_full + 2;               // P_x(j) V(j) complete (one phase per key tile)
-  uint64_t* s_free = o_full + 2;               // S_x(j) is in registers
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
+  uint64_t* kv_empty = kv_full + kStages;
+  uint64_t* s_full = kv_empty + kStages;       // [kGroups] per query tile
+  uint64_t* p_full = s_full + kGroups;
+  uint64_t* o_full = p_full + kGroups;         // P_x(j) V(j) complete (one phase per key tile)
+  uint64_t* s_free = o_full + kGroups;         // S_x(j) is in registers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + kGroups);
   uint32_t* last_flag = tmem_slot + 1;         // split items: this CTA is the last of its item to arrive
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -150,11 +168,11 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     tc::tma_prefetch_desc(&tmK);
     tc::tma_prefetch_desc(&tmV);
     tc::mbar_init(bar_q, 1);
-    for (int s = 0; s < kKvStages; ++s) {
+    for (int s = 0; s < kStages; ++s) {
       tc::mbar_init(&kv_full[s], 1);
       tc::mbar_init(&kv_empty[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kGroups; ++s) {
       tc::mbar_init(&s_full[s], 1);
       tc::mbar_init(&p_full[s], 4);    // one arrival per softmax warp (128 per-thread arrivals serialise on the barrier word)
       tc::mbar_init(&o_full[s], 1);
@@ -167,87 +185,137 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base;         // S_A cols 0..127, S_B cols 128..255
-  const uint32_t tO = tmem_base + 256;   // O_A cols 256..319, O_B cols 320..383
-  const uint32_t tP = tmem_base + 384;   // P_A cols 384..447, P_B cols 448..511 (fp16 pairs: 128 keys = 64 columns)
+  const uint32_t tS = tmem_base + Sh::kColS;   // S_x: kKv fp32 columns each
+  const uint32_t tP = tmem_base + Sh::kColP;   // P_x: fp16 pairs, kKv / 2 columns each
+  const uint32_t tO = tmem_base + Sh::kColO;   // O_x: 64 fp32 columns each
 
   if (warp == kWarpProd) {
     if (lane == 0) {  // ---------------- TMA producer
-      tc::mbar_expect_tx(bar_q, 2 * kTileBytes);
-      tc::tma_load_2d(sQ, &tmQ, bar_q, head * kHeadDim, img * p.T_q + qt * kQPerCta);
-      tc::tma_load_2d(sQ + kTileBytes, &tmQ, bar_q, head * kHeadDim, img * p.T_q + qt * kQPerCta + kQTile);
+      tc::mbar_expect_tx(bar_q, kGroups * kQTileBytes);
+#pragma unroll
+      for (int x = 0; x < kGroups; ++x)
+        tc::tma_load_2d(sQ + x * kQTileBytes, &tmQ, bar_q, head * kHeadDim, img * p.T_q + qt * Sh::kQPerCta + x * kQTile);
       for (int j = 0; j < n_kv; ++j) {
-        const int s = j % kKvStages;
-        const uint32_t ph = (j / kKvStages) & 1;
+        const int s = j % kStages;
+        const uint32_t ph = (j / kStages) & 1;
         tc::mbar_wait(&kv_empty[s], ph ^ 1);
-        tc::mbar_expect_tx(&kv_full[s], 2 * kTileBytes);
-        const int row = img * p.T_kv + (kv0 + j) * kKvTile;
-        tc::tma_load_2d(sK + s * kTileBytes, &tmK, &kv_full[s], head * kHeadDim, row);
-        tc::tma_load_2d(sV + s * kTileBytes, &tmV, &kv_full[s], head * kHeadDim, row);
+        tc::mbar_expect_tx(&kv_full[s], 2 * kKvBytes);
+        const int row = img * p.T_kv + (kv0 + j) * kKv;
+        tc::tma_load_2d(sK + s * kKvBytes, &tmK, &kv_full[s], head * kHeadDim, row);
+        tc::tma_load_2d(sV + s * kKvBytes, &tmV, &kv_full[s], head * kHeadDim, row);
       }
     }
   } else if (warp == kWarpIssue) {
     if (lane == 0) {  // ---------------- MMA issuer
-      const uint32_t idesc_qk = tc::umma_idesc_f16(128, kKvTile, false, false);
+      const uint32_t idesc_qk = tc::umma_idesc_f16(128, kKv, false, false);
       const uint32_t idesc_pv = tc::umma_idesc_f16(128, kHeadDim, false, true);  // B = V, MN-major
       auto issue_qk = [&](int x, int j) {
-        const uint64_t dq = tc::umma_desc_sw128(tc::smem_u32(sQ + x * kTileBytes));
-        const uint64_t dk = tc::umma_desc_sw128(tc::smem_u32(sK + (j % kKvStages) * kTileBytes));
+        const uint64_t dq = tc::umma_desc_sw128(tc::smem_u32(sQ + x * kQTileBytes));
+        const uint64_t dk = tc::umma_desc_sw128(tc::smem_u32(sK + (j % kStages) * kKvBytes));
 #pragma unroll
         for (int k = 0; k < kHeadDim / 16; ++k)
-          tc::umma_f16_ss(tS + x * kKvTile, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
+          tc::umma_f16_ss(tS + x * kKv, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
         tc::umma_commit(&s_full[x]);
       };
       auto issue_pv = [&](int x, int j) {
-        const uint64_t dv = tc::umma_desc_sw128(tc::smem_u32(sV + (j % kKvStages) * kTileBytes));
+        const uint64_t dv = tc::umma_desc_sw128(tc::smem_u32(sV + (j % kStages) * kKvBytes));
 #pragma unroll
-        for (int kk = 0; kk < kKvTile / 16; ++kk) {
+        for (int kk = 0; kk < kKv / 16; ++kk) {
           // A = P_x in TMEM: 16 keys = 8 columns;  B = V: 16 keys = 16 rows = 2 KB
-          tc::umma_f16_ts(tO + x * kHeadDim, tP + x * 64 + kk * 8, dv + kk * (2048 >> 4), idesc_pv, (j | kk) != 0);
+          tc::umma_f16_ts(tO + x * kHeadDim, tP + x * (kKv / 2) + kk * 8, dv + kk * (2048 >> 4), idesc_pv, (j | kk) != 0);
         }
         tc::umma_commit(&o_full[x]);
       };
       tc::mbar_wait(bar_q, 0);
       tc::mbar_wait(&kv_full[0], 0);
       tc::tc_fence_after();
-      issue_qk(0, 0);
-      issue_qk(1, 0);
-      if constexpr (kStatic) {
-        // The steady-state order of the events is fixed by the softmax groups' turns (S_B(j) read, P_A(j) stored,
-        // S_A(j+1) read, P_B(j) stored, ...): wait for them in that order with blocking (hardware-suspended) waits instead
-        // of polling four barriers from the sub-partition that also hosts two softmax warps.
+#pragma unroll
+      for (int x = 0; x < kGroups; ++x) issue_qk(x, 0);
+      if constexpr (kStatic && kGroups == 3) {
+        // Free-running groups move in lock step (they share every K / V tile and the MUFU pipe), so their events come in
+        // bunches: wait for all of S(j) to be read, then issue the next Q K^T of ALL groups with the k-steps interleaved
+        // (group 0 k0, group 1 k0, group 2 k0, group 0 k1, ...), likewise the P V.  The tensor pipe runs MMAs in issue
+        // order and a k-step accumulating into the same tile waits for its predecessor to drain - at N = 64 (32 cycles of
+        // math) that latency is most of the MMA's time; three independent accumulators back to back fill it.
+        auto issue_qk_all = [&](int j) {
+          const uint64_t dk = tc::umma_desc_sw128(tc::smem_u32(sK + (j % kStages) * kKvBytes));
+#pragma unroll
+          for (int k = 0; k < kHeadDim / 16; ++k) {
+#pragma unroll
+            for (int x = 0; x < kGroups; ++x) {
+              const uint64_t dq = tc::umma_desc_sw128(tc::smem_u32(sQ + x * kQTileBytes));
+              tc::umma_f16_ss(tS + x * kKv, dq + 2 * k, dk + 2 * k, idesc_qk, k != 0);
+            }
+          }
+#pragma unroll
+          for (int x = 0; x < kGroups; ++x) tc::umma_commit(&s_full[x]);
+        };
+        auto issue_pv_all = [&](int j) {
+          const uint64_t dv = tc::umma_desc_sw128(tc::smem_u32(sV + (j % kStages) * kKvBytes));
+#pragma unroll
+          for (int kk = 0; kk < kKv / 16; ++kk) {
+#pragma unroll
+            for (int x = 0; x < kGroups; ++x)
+              tc::umma_f16_ts(tO + x * kHeadDim, tP + x * (kKv / 2) + kk * 8, dv + kk * (2048 >> 4), idesc_pv, (j | kk) != 0);
+          }
+#pragma unroll
+          for (int x = 0; x < kGroups; ++x) tc::umma_commit(&o_full[x]);
+        };
         for (int j = 0; j < n_kv; ++j) {
           if (j + 1 < n_kv) {
-            tc::mbar_wait(&kv_full[(j + 1) % kKvStages], ((j + 1) / kKvStages) & 1);
-            tc::mbar_wait(&s_free[0], j & 1);
+            tc::mbar_wait(&kv_full[(j + 1) % kStages], ((j + 1) / kStages) & 1);
+#pragma unroll
+            for (int x = 0; x < kGroups; ++x) tc::mbar_wait(&s_free[x], j & 1);
             tc::tc_fence_after();
             TRACE(8, j + 1);
-            issue_qk(0, j + 1);
-            tc::mbar_wait(&s_free[1], j & 1);
-            tc::tc_fence_after();
             TRACE(24, j + 1);
-            issue_qk(1, j + 1);
+            issue_qk_all(j + 1);
           }
-          tc::mbar_wait(&p_full[0], j & 1);
+#pragma unroll
+          for (int x = 0; x < kGroups; ++x) tc::mbar_wait(&p_full[x], j & 1);
           tc::tc_fence_after();
           TRACE(9, j);
-          issue_pv(0, j);
-          tc::mbar_wait(&p_full[1], j & 1);
-          tc::tc_fence_after();
           TRACE(25, j);
-          issue_pv(1, j);
-          tc::umma_commit(&kv_empty[j % kKvStages]);   // both tiles are through K/V(j)
+          issue_pv_all(j);
+          tc::umma_commit(&kv_empty[j % kStages]);   // every tile is through K/V(j)
+        }
+      } else if constexpr (kStatic) {
+        // The steady-state order of the events is fixed by the softmax groups' turns (S_1(j) read, P_0(j) stored,
+        // S_0(j+1) read, P_1(j) stored, ...): wait for them in that order with blocking (hardware-suspended) waits instead
+        // of polling all the barriers from a sub-partition that also hosts softmax warps.
+        for (int j = 0; j < n_kv; ++j) {
+          if (j + 1 < n_kv) {
+            tc::mbar_wait(&kv_full[(j + 1) % kStages], ((j + 1) / kStages) & 1);
+#pragma unroll
+            for (int x = 0; x < kGroups; ++x) {
+              tc::mbar_wait(&s_free[x], j & 1);
+              tc::tc_fence_after();
+              TRACE(8 + 16 * x, j + 1);
+              issue_qk(x, j + 1);
+            }
+          }
+#pragma unroll
+          for (int x = 0; x < kGroups; ++x) {
+            tc::mbar_wait(&p_full[x], j & 1);
+            tc::tc_fence_after();
+            TRACE(9 + 16 * x, j);
+            issue_pv(x, j);
+          }
+          tc::umma_commit(&kv_empty[j % kStages]);   // every tile is through K/V(j)
         }
       } else {
         // Event loop: serve whichever of {S_x free -> next Q K^T, P_x ready -> P V} is ready, per query tile.
-        int qk_next[2] = {1, 1}, pv_next[2] = {0, 0};
-        while (pv_next[0] < n_kv || pv_next[1] < n_kv) {
+        int qk_next[kGroups], pv_next[kGroups];
+#pragma unroll
+        for (int x = 0; x < kGroups; ++x) qk_next[x] = 1, pv_next[x] = 0;
+        int pv_done = 0;   // key tiles every group's P.V has been issued for
+        while (pv_done < n_kv) {
           bool progress = false;
 #pragma unroll
-          for (int x = 0; x < 2; ++x) {
+          for (int x = 0; x < kGroups; ++x) {
             const int jq = qk_next[x];
             if (jq < n_kv && tc::mbar_test(&s_free[x], (jq - 1) & 1) &&
-                tc::mbar_test(&kv_full[jq % kKvStages], (jq / kKvStages) & 1)) {
+                tc::mbar_test(&kv_full[jq % kStages], (jq / kStages) & 1)) {
               tc::tc_fence_after();
               TRACE(8 + 16 * x, jq);
               issue_qk(x, jq);
@@ -260,7 +328,13 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
               TRACE(9 + 16 * x, jp);
               issue_pv(x, jp);
               pv_next[x] = jp + 1;
-              if (pv_next[x ^ 1] > jp) tc::umma_commit(&kv_empty[jp % kKvStages]);  // both tiles are through K/V(jp)
+              int lo = pv_next[0];
+#pragma unroll
+              for (int y = 1; y < kGroups; ++y) lo = min(lo, pv_next[y]);
+              if (lo > pv_done) {   // every tile is through K/V(pv_done)
+                tc::umma_commit(&kv_empty[pv_done % kStages]);
+                pv_done = lo;
+              }
               progress = true;
             }
           }
@@ -268,7 +342,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
       }
     }
-  } else {  // ---------------- softmax warpgroups: x = 0 / 1 (four warps each); thread = query row = TMEM lane
+  } else {  // ---------------- softmax warpgroups (four warps each); thread = query row = TMEM lane
     const int sw = kHigh ? warp : warp - 2;
     const int x = sw >> 2;
     const int lane_base = (warp & 3) * 32;
@@ -276,66 +350,50 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t lane_addr = (uint32_t)lane_base << 16;
     const float sc = p.scale_log2e;
     float m_run = -INFINITY, l_run = 0.f;
-    const uint32_t tp = tP + x * 64 + lane_addr;
-    const uint32_t ts = tS + x * kKvTile + lane_addr;
+    const uint32_t tp = tP + x * (kKv / 2) + lane_addr;
+    const uint32_t ts = tS + x * kKv + lane_addr;
     const uint32_t to = tO + x * kHeadDim + lane_addr;
-    const bool tr = (sw & 3) == 0 && lane == 0;
+    const bool tr = (sw & 3) == 0 && lane == 0 && x < 2;
     const int te = 16 * x;
 
-    int kv_left = p.T_kv - kv0 * kKvTile;   // keys from this tile on
-    if (kTurns && x == 1) named_arrive(1, 256);  // group A takes the first turn
+    int kv_left = p.T_kv - kv0 * kKv;   // keys from this tile on
+    if (kTurns && x == 1) named_arrive(1, 256);  // group 0 takes the first turn
     for (int j = 0; j < n_kv; ++j) {
       const int kv_rem = kv_left;  // >= 1
-      kv_left -= kKvTile;
+      kv_left -= kKv;
       if (tr) TRACE(te + 0, j);
       tc::mbar_wait(&s_full[x], j & 1);
       tc::tc_fence_after();
       if (tr) TRACE(te + 1, j);
-      uint32_t s[128];
+      uint32_t s[kKv];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tc::tmem_ld32(ts + c * 32, s + c * 32);
+      for (int c = 0; c < kKv / 32; ++c) tc::tmem_ld32(ts + c * 32, s + c * 32);
       tc::tmem_ld_wait();
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&s_free[x]);     // the issuer may overwrite S_x with Q_x K_{j+1}^T now
       if (tr) TRACE(te + 2, j);
-      if (kv_rem < kKvTile) {
+      if (kv_rem < kKv) {
 #pragma unroll
-        for (int q = 0; q < 128; ++q)
+        for (int q = 0; q < kKv; ++q)
           if (q >= kv_rem) s[q] = 0xff800000u;  // -inf
       }
-      float mx;
-      if constexpr (kMax8) {
-        float m8[8];
+      float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]);
+      float mx2 = __uint_as_float(s[2]), mx3 = __uint_as_float(s[3]);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) m8[c] = max3(__uint_as_float(s[c]), __uint_as_float(s[8 + c]), __uint_as_float(s[16 + c]));
-#pragma unroll
-        for (int q = 24; q < 120; q += 16) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) m8[c] = max3(m8[c], __uint_as_float(s[q + c]), __uint_as_float(s[q + 8 + c]));
-        }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) m8[c] = fmaxf(m8[c], __uint_as_float(s[120 + c]));
-        mx = fmaxf(max3(m8[0], m8[1], m8[2]), max3(m8[3], m8[4], m8[5]));
-        mx = max3(mx, m8[6], m8[7]);
-      } else {
-        float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]);
-        float mx2 = __uint_as_float(s[2]), mx3 = __uint_as_float(s[3]);
-#pragma unroll
-        for (int q = 4; q < 124; q += 8) {
-          mx0 = max3(mx0, __uint_as_float(s[q]), __uint_as_float(s[q + 1]));
-          mx1 = max3(mx1, __uint_as_float(s[q + 2]), __uint_as_float(s[q + 3]));
-          mx2 = max3(mx2, __uint_as_float(s[q + 4]), __uint_as_float(s[q + 5]));
-          mx3 = max3(mx3, __uint_as_float(s[q + 6]), __uint_as_float(s[q + 7]));
-        }
-        mx0 = max3(mx0, __uint_as_float(s[124]), __uint_as_float(s[125]));
-        mx1 = max3(mx1, __uint_as_float(s[126]), __uint_as_float(s[127]));
-        mx = fmaxf(max3(mx0, mx2, mx3), mx1);
+      for (int q = 4; q < kKv - 4; q += 8) {
+        mx0 = max3(mx0, __uint_as_float(s[q]), __uint_as_float(s[q + 1]));
+        mx1 = max3(mx1, __uint_as_float(s[q + 2]), __uint_as_float(s[q + 3]));
+        mx2 = max3(mx2, __uint_as_float(s[q + 4]), __uint_as_float(s[q + 5]));
+        mx3 = max3(mx3, __uint_as_float(s[q + 6]), __uint_as_float(s[q + 7]));
       }
+      mx0 = max3(mx0, __uint_as_float(s[kKv - 4]), __uint_as_float(s[kKv - 3]));
+      mx1 = max3(mx1, __uint_as_float(s[kKv - 2]), __uint_as_float(s[kKv - 1]));
+      const float mx = fmaxf(max3(mx0, mx2, mx3), mx1);
       // P_x(j-1) V(j-1) must be complete before P_x is rewritten or O_x rescaled; P_x(j) V(j) is not issued before
       // this thread arrives on p_full, so O_x is quiescent in between.  The wait is only needed before O is rescaled
-      // (rare) or P is rewritten (the first tcgen05.st, half a tile of exponentials later), which takes the P.V
-      // latency off the softmax critical path.
+      // (rare) or P is rewritten (the first tcgen05.st, 64 exponentials later), which takes the P.V latency off the
+      // softmax critical path.
       bool o_ready = j == 0;
       auto wait_o = [&]() {
         if (!o_ready) {   // warp-uniform
@@ -386,8 +444,8 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       exp_block(0);
       uint32_t pk[32];
 #pragma unroll
-      for (int b = 0; b < 8; ++b) {
-        if (b + 1 < 8) exp_block(b + 1);
+      for (int b = 0; b < kKv / 16; ++b) {
+        if (b + 1 < kKv / 16) exp_block(b + 1);
 #pragma unroll
         for (int q = 0; q < 8; q += 2) {
           acc_a = add2(acc_a, pk2u(s[b * 16 + 2 * q], s[b * 16 + 2 * q + 1]));
@@ -415,7 +473,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       if (lane == 0) tc::mbar_arrive(&p_full[x]);
       if (tr) TRACE(te + 7, j);
     }
-    if (kTurns && x == 0) named_sync(1, 256);      // absorb group B's last hand-over
+    if (kTurns && x == 0) named_sync(1, 256);      // absorb group 1's last hand-over
     // O_x complete after the last P.V
     tc::mbar_wait(&o_full[x], (n_kv - 1) & 1);
     tc::tc_fence_after();
@@ -425,7 +483,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     int item_e, part_e, kv0_e, n_kv_e;
     decode_item(p, cta, item_e, part_e, kv0_e, n_kv_e);
     const bool is_part = cta >= p.n_full;
-    const int q_row = (item_e % p.n_qt) * kQPerCta + x * kQTile + row;
+    const int q_row = (item_e % p.n_qt) * Sh::kQPerCta + x * kQTile + row;
     __half* orow = p.out + ((long long)(item_e / (p.n_qt * p.heads)) * p.T_q + q_row) * p.ldo + ((item_e / p.n_qt) % p.heads) * kHeadDim;
     if (!is_part) {
       const float inv = 1.f / l_run;
@@ -444,44 +502,45 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
       }
     } else {
-      // Partial result of this key range: unnormalised O, m, l, column-major over the 256 query rows of the item so
-      // that a warp's stores coalesce.  The CTA of the item that arrives last folds the `split` partials together.
-      const int r256 = x * kQTile + row;
-      float* base = p.part + (size_t)(item_e - p.n_full) * p.split * 66 * 256;
-      float* mine = base + (size_t)part_e * 66 * 256 + r256;
+      // Partial result of this key range: unnormalised O, m, l, column-major over the query rows of the item so that a
+      // warp's stores coalesce.  The CTA of the item that arrives last folds the `split` partials together.
+      constexpr int kRows = Sh::kQPerCta;
+      const int r_cta = x * kQTile + row;
+      float* base = p.part + (size_t)(item_e - p.n_full) * p.split * 66 * kRows;
+      float* mine = base + (size_t)part_e * 66 * kRows + r_cta;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         uint32_t o[32];
         tc::tmem_ld32(to + c * 32, o);
         tc::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) mine[(c * 32 + i) * 256] = __uint_as_float(o[i]);
+        for (int i = 0; i < 32; ++i) mine[(c * 32 + i) * kRows] = __uint_as_float(o[i]);
       }
-      mine[64 * 256] = m_run;
-      mine[65 * 256] = l_run;
+      mine[64 * kRows] = m_run;
+      mine[65 * kRows] = l_run;
       __threadfence();
-      named_sync(3, 256);
+      named_sync(3, kSoftThreads);
       if (sw == 0 && lane == 0) {
         const unsigned prev = atomicAdd(&p.count[item_e - p.n_full], 1u);
         const bool last = prev == (unsigned)p.split - 1;
         if (last) p.count[item_e - p.n_full] = 0;   // ready for the next launch
         *last_flag = last ? 1u : 0u;
       }
-      named_sync(3, 256);
+      named_sync(3, kSoftThreads);
       if (*last_flag) {
         __threadfence();
         float m_all = -INFINITY;
-        for (int q = 0; q < p.split; ++q) m_all = fmaxf(m_all, __ldcg(base + (size_t)q * 66 * 256 + 64 * 256 + r256));
+        for (int q = 0; q < p.split; ++q) m_all = fmaxf(m_all, __ldcg(base + (size_t)q * 66 * kRows + 64 * kRows + r_cta));
         float acc[64];
 #pragma unroll
         for (int i = 0; i < 64; ++i) acc[i] = 0.f;
         float l_all = 0.f;
         for (int q = 0; q < p.split; ++q) {
-          const float* src = base + (size_t)q * 66 * 256 + r256;
-          const float w = ex2((__ldcg(src + 64 * 256) - m_all) * sc);
-          l_all = fmaf(w, __ldcg(src + 65 * 256), l_all);
+          const float* src = base + (size_t)q * 66 * kRows + r_cta;
+          const float w = ex2((__ldcg(src + 64 * kRows) - m_all) * sc);
+          l_all = fmaf(w, __ldcg(src + 65 * kRows), l_all);
 #pragma unroll
-          for (int i = 0; i < 64; ++i) acc[i] = fmaf(w, __ldcg(src + i * 256), acc[i]);
+          for (int i = 0; i < 64; ++i) acc[i] = fmaf(w, __ldcg(src + i * kRows), acc[i]);
         }
         if (q_row < p.T_q) {
           const float inv = 1.f / l_all;
@@ -663,22 +722,27 @@ extern "C" int sgn_debug_attn_trace(long long* h_out) {
 // key ranges when that shortens the tail (cost in key-tile periods, + 2 per CTA for its prologue and the partial
 // store / combine).  T = 4 096 with 20 heads x 2 images on 148 SMs: 640 items = 4.32 waves -> 592 whole items + 48 x 3
 // parts of 10-11 key tiles, 128 + 13 instead of 160 periods.
-static void plan_split(int items, int n_kv, int n_sm, int* n_full, int* split) {
+static void plan_split(int items, int n_kv, int n_sm, int* n_full, int* split, int min_tiles = 4) {
   *n_full = items;
   *split = 1;
   const int rem = items % n_sm;
   if (rem == 0 || !g_attn_split) return;
   int best = 1;
   double best_cost = n_kv + 2;
-  for (int s = 2; s <= 8 && n_kv / s >= 4; ++s) {
+  for (int s = 2; s <= 8 && n_kv / s >= min_tiles; ++s) {
     const double cost = (double)((rem * s + n_sm - 1) / n_sm) * ((n_kv + s - 1) / s + 2);
     if (cost < 0.95 * best_cost) best = s, best_cost = cost;
   }
   if (best > 1) *n_full = items - rem, *split = best;
 }
 
-static size_t split_workspace_bytes(int tail_items, int split) {
-  return (size_t)tail_items * split * 66 * 256 * sizeof(float) + (size_t)tail_items * sizeof(unsigned);
+static size_t split_workspace_bytes(int tail_items, int split, int rows_per_cta) {
+  return (size_t)tail_items * split * 66 * rows_per_cta * sizeof(float) + (size_t)tail_items * sizeof(unsigned);
+}
+// rows per CTA / keys per tile of the configured shape (sgn_set_option "attn_shape")
+static void shape_dims(int* rows_per_cta, int* kv_tile) {
+  *rows_per_cta = g_attn_shape == 1 ? AttnShape<3, 64>::kQPerCta : AttnShape<2, 128>::kQPerCta;
+  *kv_tile = g_attn_shape == 1 ? 64 : 128;
 }
 
 static int attention_impl(const void* d_q, int64_t ldq, const void* d_k, int64_t ldk, const void* d_v, int64_t ldv, int B,
@@ -708,33 +772,38 @@ static int attention_impl(const void* d_q, int64_t ldq, const void* d_k, int64_t
     return SGN_OK;
   }
   using Kern = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, AttnParams);
-  static const Kern kerns[16] = {k_attention_tc<0>,  k_attention_tc<1>,  k_attention_tc<2>,  k_attention_tc<3>,
-                                 k_attention_tc<4>,  k_attention_tc<5>,  k_attention_tc<6>,  k_attention_tc<7>,
-                                 k_attention_tc<8>,  k_attention_tc<9>,  k_attention_tc<10>, k_attention_tc<11>,
-                                 k_attention_tc<12>, k_attention_tc<13>, k_attention_tc<14>, k_attention_tc<15>};
+  static const Kern kerns[2][4] = {
+      {k_attention_tc<0, 2, 128>, k_attention_tc<1, 2, 128>, k_attention_tc<2, 2, 128>, k_attention_tc<3, 2, 128>},
+      {k_attention_tc<0, 3, 64>, k_attention_tc<1, 3, 64>, k_attention_tc<2, 3, 64>, k_attention_tc<3, 3, 64>}};
+  static const size_t smem_of[2] = {AttnShape<2, 128>::kSmem, AttnShape<3, 64>::kSmem};
+  static const int threads_of[2] = {AttnShape<2, 128>::kThreads, AttnShape<3, 64>::kThreads};
   static bool attr_set = false;
   if (!attr_set) {
-    for (Kern k : kerns) SGN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAttnSmem));
+    for (int sh = 0; sh < 2; ++sh)
+      for (Kern k : kerns[sh]) SGN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of[sh]));
     attr_set = true;
   }
+  const int shape = g_attn_shape == 1 ? 1 : 0;
+  int rows_per_cta, kv_tile;
+  shape_dims(&rows_per_cta, &kv_tile);
   CUtensorMap tmQ, tmK, tmV;
-  const uint32_t box[2] = {kHeadDim, 128};
+  const uint32_t box[2] = {kHeadDim, 128}, box_kv[2] = {kHeadDim, (uint32_t)kv_tile};
   const uint64_t cols = (uint64_t)heads * kHeadDim;
   uint64_t dq[2] = {cols, (uint64_t)B * T_q}, sq[1] = {(uint64_t)ldq * 2};
   uint64_t dk[2] = {cols, (uint64_t)B * T_kv}, sk[1] = {(uint64_t)ldk * 2}, sv[1] = {(uint64_t)ldv * 2};
   int rc = encode_tmap(&tmQ, d_q, 2, dq, sq, box, nullptr);
   if (rc) return rc;
-  rc = encode_tmap(&tmK, d_k, 2, dk, sk, box, nullptr);
+  rc = encode_tmap(&tmK, d_k, 2, dk, sk, box_kv, nullptr);
   if (rc) return rc;
-  rc = encode_tmap(&tmV, d_v, 2, dk, sv, box, nullptr);
+  rc = encode_tmap(&tmV, d_v, 2, dk, sv, box_kv, nullptr);
   if (rc) return rc;
   AttnParams p;
   p.T_q = T_q, p.T_kv = T_kv;
-  p.n_kv_tiles = (T_kv + kKvTile - 1) / kKvTile;
+  p.n_kv_tiles = (T_kv + kv_tile - 1) / kv_tile;
   p.scale_log2e = scale * 1.4426950408889634f;
   p.out = reinterpret_cast<__half*>(d_out);
   p.ldo = ldo;
-  p.n_qt = (T_q + kQPerCta - 1) / kQPerCta;
+  p.n_qt = (T_q + rows_per_cta - 1) / rows_per_cta;
   p.heads = heads;
   const int items = p.n_qt * heads * B;
   p.n_full = items, p.split = 1;
@@ -743,17 +812,17 @@ static int attention_impl(const void* d_q, int64_t ldq, const void* d_k, int64_t
     plan_split(items, p.n_kv_tiles, sm_count(), &p.n_full, &p.split);
     if (p.split > 1) {
       const int tail = items - p.n_full;
-      const size_t need = split_workspace_bytes(tail, p.split);
+      const size_t need = split_workspace_bytes(tail, p.split, rows_per_cta);
       SGN_CHECK_ARG((reinterpret_cast<uintptr_t>(d_ws) & 15) == 0 && ws_bytes >= (int64_t)need,
                     "attention workspace too small or misaligned (sgn_attention_workspace_bytes)");
       p.part = reinterpret_cast<float*>(d_ws);
-      p.count = reinterpret_cast<unsigned*>(p.part + (size_t)tail * p.split * 66 * 256);
+      p.count = reinterpret_cast<unsigned*>(p.part + (size_t)tail * p.split * 66 * rows_per_cta);
       SGN_CUDA(cudaMemsetAsync(p.count, 0, (size_t)tail * sizeof(unsigned), st));
     }
   }
   p.idle_ns = g_attn_idle_ns;
-  Kern kern = kerns[g_attn_variant & 15];
-  kern<<<p.n_full + (items - p.n_full) * p.split, kAttnThreads, kAttnSmem, st>>>(tmQ, tmK, tmV, p);
+  Kern kern = kerns[shape][g_attn_variant & 3];
+  kern<<<p.n_full + (items - p.n_full) * p.split, threads_of[shape], smem_of[shape], st>>>(tmQ, tmK, tmV, p);
   SGN_LAUNCH_CHECK();
   return SGN_OK;
 }
@@ -762,10 +831,12 @@ extern "C" int64_t sgn_attention_workspace_bytes(int B, int heads, int T_q, int 
   if (B <= 0 || heads <= 0 || T_q <= 0 || T_kv <= 0 || (T_kv <= kXaKv && g_attn_short_kv)) return 0;
   int dev_ok = 0;
   if (cudaGetDeviceCount(&dev_ok) != cudaSuccess || dev_ok == 0) return 0;
-  const int n_qt = (T_q + kQPerCta - 1) / kQPerCta, items = n_qt * heads * B;
+  int rows_per_cta, kv_tile;
+  shape_dims(&rows_per_cta, &kv_tile);
+  const int n_qt = (T_q + rows_per_cta - 1) / rows_per_cta, items = n_qt * heads * B;
   int n_full, split;
-  plan_split(items, (T_kv + kKvTile - 1) / kKvTile, sm_count(), &n_full, &split);
-  return split > 1 ? (int64_t)split_workspace_bytes(items - n_full, split) : 0;
+  plan_split(items, (T_kv + kv_tile - 1) / kv_tile, sm_count(), &n_full, &split);
+  return split > 1 ? (int64_t)split_workspace_bytes(items - n_full, split, rows_per_cta) : 0;
 }
 
 extern "C" int sgn_attention_f16_ws(const void* d_q, int64_t ldq, const void* d_k, int64_t ldk, const void* d_v,

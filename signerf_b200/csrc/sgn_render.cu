@@ -686,7 +686,7 @@ extern "C" int sgn_field_eval(const SgnField* f, const float* d_pos, const float
   return SGN_OK;
 }
 
-namespace sgn { extern int g_pair_stages; extern int g_attn_variant; extern int g_attn_idle_ns; extern int g_attn_short_kv; extern int g_attn_split; }
+namespace sgn { extern int g_pair_stages; extern int g_attn_variant; extern int g_attn_idle_ns; extern int g_attn_short_kv; extern int g_attn_split; extern int g_attn_shape; }
 
 extern "C" int sgn_set_option(const char* name, int value) {
   SGN_CHECK_ARG(name != nullptr, "null option name");
@@ -712,13 +712,18 @@ extern "C" int sgn_set_option(const char* name, int value) {
     return SGN_OK;
   }
   if (n == "attn_variant") {
-    SGN_CHECK_ARG(value >= 0 && value <= 15, "attn_variant must be 0..15 (bit flags, see sgn_attn.cu)");
+    SGN_CHECK_ARG(value >= 0 && value <= 3, "attn_variant must be 0..3 (bit flags, see sgn_attn.cu)");
     sgn::g_attn_variant = value;
     return SGN_OK;
   }
   if (n == "attn_short_kv") {
     SGN_CHECK_ARG(value == 0 || value == 1, "attn_short_kv must be 0 or 1");
     sgn::g_attn_short_kv = value;
+    return SGN_OK;
+  }
+  if (n == "attn_shape") {
+    SGN_CHECK_ARG(value == 0 || value == 1, "attn_shape must be 0 (2 x 128 rows, 128-key tiles) or 1 (3 x 128 rows, 64-key tiles)");
+    sgn::g_attn_shape = value;
     return SGN_OK;
   }
   if (n == "attn_split") {
