@@ -9,7 +9,7 @@ var = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 _lib.set_option("attn_variant", var)
 shape = int(sys.argv[4]) if len(sys.argv) > 4 else 1
 _lib.set_option("attn_shape", shape)
-kvt = 64 if shape == 1 else 128
+kvt = 96 if shape == 1 else 128
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
 heads = int(sys.argv[3]) if len(sys.argv) > 3 else 10
 B = 2
@@ -34,3 +34,7 @@ for x, g in ((0, "A"), (1, "B")):
     print(f"           QK(j+1) issue after s_free(j): {np.mean(t[o + 8, sl1] - t[o + 2, sl]):.0f}   s_full(j+1) seen after QK issue: {np.mean(t[o + 1, sl1] - t[o + 8, sl1]):.0f}"
           f"   PV(j) issue after p_full(j): {np.mean(t[o + 9, sl] - t[o + 7, sl]):.0f}")
 if shape == 0: print(f"  A turn-got -> B turn-got {np.mean(t[20, sl] - t[4, sl]):.0f}; B turn-got -> A next {np.mean(t[4, sl1] - t[20, sl]):.0f}")
+if shape == 1:
+    base = t[0, lo]
+    for j in range(lo, lo + 4):
+        print(f"  tile {j}: " + " | ".join(f"g{x}: top {t[16*x+0, j]-base:.0f} s_full {t[16*x+1, j]-base:.0f} ld {t[16*x+2, j]-base:.0f} p_full {t[16*x+7, j]-base:.0f} PVissue {t[16*x+9, j]-base:.0f} issued {t[16*x+10, j]-base:.0f}" for x in (0, 1)))

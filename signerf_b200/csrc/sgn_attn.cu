@@ -32,19 +32,25 @@ constexpr int kQTile = 128;
 constexpr int kQTileBytes = 128 * 64 * 2;  // one [128 x 64] fp16 tile, 128-B rows, SWIZZLE_128B
 
 // Shape of one CTA: kGroups query tiles of 128 rows (one softmax warpgroup each) share every K / V tile of kKv keys.
-//   <2, 128>: S 2x128 + O 2x64 + P 2x64 = 512 TMEM columns, two softmax warps per SM sub-partition taking MUFU turns
-//   <3, 64> : S 3x64 + P 3x32 + O 3x64 = 480 columns, three free-running softmax warps per sub-partition: a warp's serial
-//             chain per key tile (S load, row maximum, exponentials, P store, two barrier round trips) is what bounds the
-//             two-group kernel (~2 950 cycles per 2 x 128 x 128 scores against 2 048 of MUFU time); with half-size tiles
-//             and a third warp the MUFU pipe always has an exponential to issue
+//   <2, 128>: S 2x128 + O 2x64 + P 2x64 = 512 TMEM columns, two softmax warps per SM sub-partition taking MUFU turns;
+//             S_x is released as soon as it is in registers, so Q_x K_{j+1}^T runs under the exponentials of tile j
+//   <3, 96> : three free-running softmax warps per sub-partition.  S 3x96 + O 3x64 = 480 columns only fit with P_x
+//             written over the first 48 columns of S_x (each thread overwrites its own row after reading it), so
+//             Q_x K_{j+1}^T follows P_x V_j on the tensor pipe and a group idles through both - while the other two keep
+//             the MUFU pipe busy.  (Three 64-key tiles without the aliasing were measured too: every tcgen05.mma costs
+//             >= 60 cycles whatever its N - scratch/mma_bench - so 64-key Q K^T tiles make the tensor pipe the limit.)
 template <int kGroups, int kKv>
 struct AttnShape {
-  static constexpr int kThreads = (2 + 4 * kGroups) * 32;
+  static constexpr bool kAlias = kKv == 96;
+  static constexpr bool kRegMove = kGroups == 3;   // setmaxnreg (see the kernel)
+  static constexpr int kThreads = kRegMove ? 512 : (2 + 4 * kGroups) * 32;
   static constexpr int kQPerCta = kGroups * kQTile;
   static constexpr int kKvBytes = kKv * 64 * 2;
-  static constexpr int kStages = kKv == 128 ? 4 : 6;
+  static constexpr int kStages = 4;
   static constexpr size_t kSmem = 1024 + (size_t)kQTileBytes * kGroups + (size_t)2 * kStages * kKvBytes + 256;
-  static constexpr int kColS = 0, kColP = kGroups * kKv, kColO = kColP + kGroups * kKv / 2;   // TMEM column map
+  // TMEM column map
+  static constexpr int kColS = 0, kColP = kAlias ? 0 : kGroups * kKv, kStrideP = kAlias ? kKv : kKv / 2;
+  static constexpr int kColO = kAlias ? kGroups * kKv : kColP + kGroups * kKv / 2;
   static_assert(kColO + kGroups * kHeadDim <= 512, "tensor memory");
 };
 
@@ -113,8 +119,7 @@ __device__ long long g_trace[32 * 256];   // [event + 16 * query tile][key tile]
 // sgn_set_option "attn_variant" (bit flags): 1 = the MMA issuer follows the static event order with blocking waits
 // instead of polling, 2 = producer / issuer are the two highest warps of the CTA instead of the two lowest
 int g_attn_variant = 3;
-int g_attn_shape = 0;     // sgn_set_option "attn_shape": 0 = two query tiles x 128-key tiles (default), 1 = three x 64-key tiles (measured slower:
-                          // every tcgen05.mma costs >= 60 cycles whatever its N, so 64-key Q K^T tiles saturate the tensor pipe)
+int g_attn_shape = 0;     // sgn_set_option "attn_shape": 0 = two query tiles x 128-key tiles (default), 1 = three x 96-key tiles with P aliased over S
 int g_attn_idle_ns = 0;   // sgn_set_option "attn_idle_ns"
 int g_attn_split = 1;     // sgn_set_option "attn_split": 0 = never split the tail items over the keys
 
@@ -129,14 +134,18 @@ __device__ __forceinline__ void decode_item(const AttnParams& p, int cta, int& i
   }
 }
 
+// Registers are handed out per group of four warps: ten warps are charged as twelve (168 registers per thread), fourteen
+// as sixteen (128).  The three-group shape therefore launches sixteen warps - softmax warps 0-11, producer 12, issuer 13,
+// two idle - and moves registers with setmaxnreg: the last warpgroup keeps 56 per thread, the softmax warpgroups get 152.
 template <int kFlags, int kGroups, int kKv>
-__global__ void __launch_bounds__((2 + 4 * kGroups) * 32, 1)
+__global__ void __launch_bounds__(AttnShape<kGroups, kKv>::kThreads, 1)
 k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   using Sh = AttnShape<kGroups, kKv>;
   constexpr bool kTurns = kGroups == 2;
+  constexpr bool kAlias = Sh::kAlias;
   constexpr bool kStatic = (kFlags & 1) != 0;
-  constexpr bool kHigh = (kFlags & 2) != 0;
+  constexpr bool kHigh = (kFlags & 2) != 0 || Sh::kRegMove;
   constexpr int kWarpProd = kHigh ? 4 * kGroups : 0, kWarpIssue = kHigh ? 4 * kGroups + 1 : 1;
   constexpr int kStages = Sh::kStages, kKvBytes = Sh::kKvBytes;
   constexpr int kSoftThreads = 128 * kGroups;
@@ -189,7 +198,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const uint32_t tP = tmem_base + Sh::kColP;   // P_x: fp16 pairs, kKv / 2 columns each
   const uint32_t tO = tmem_base + Sh::kColO;   // O_x: 64 fp32 columns each
 
-  if (warp == kWarpProd) {
+  auto role_producer = [&]() {
     if (lane == 0) {  // ---------------- TMA producer
       tc::mbar_expect_tx(bar_q, kGroups * kQTileBytes);
 #pragma unroll
@@ -205,7 +214,8 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tc::tma_load_2d(sV + s * kKvBytes, &tmV, &kv_full[s], head * kHeadDim, row);
       }
     }
-  } else if (warp == kWarpIssue) {
+  };
+  auto role_issuer = [&]() {
     if (lane == 0) {  // ---------------- MMA issuer
       const uint32_t idesc_qk = tc::umma_idesc_f16(128, kKv, false, false);
       const uint32_t idesc_pv = tc::umma_idesc_f16(128, kHeadDim, false, true);  // B = V, MN-major
@@ -222,16 +232,49 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
         for (int kk = 0; kk < kKv / 16; ++kk) {
           // A = P_x in TMEM: 16 keys = 8 columns;  B = V: 16 keys = 16 rows = 2 KB
-          tc::umma_f16_ts(tO + x * kHeadDim, tP + x * (kKv / 2) + kk * 8, dv + kk * (2048 >> 4), idesc_pv, (j | kk) != 0);
+          tc::umma_f16_ts(tO + x * kHeadDim, tP + x * Sh::kStrideP + kk * 8, dv + kk * (2048 >> 4), idesc_pv, (j | kk) != 0);
         }
-        tc::umma_commit(&o_full[x]);
+        if (!kAlias) tc::umma_commit(&o_full[x]);
       };
       tc::mbar_wait(bar_q, 0);
       tc::mbar_wait(&kv_full[0], 0);
       tc::tc_fence_after();
 #pragma unroll
       for (int x = 0; x < kGroups; ++x) issue_qk(x, 0);
-      if constexpr (kStatic && kGroups == 3) {
+      if constexpr (kAlias) {
+        // P_x(j) lives in S_x: one event per group and key tile.  P_x(j) stored -> P_x V_j, then Q_x K_{j+1}^T into the
+        // same columns (the tensor pipe runs them in issue order), one commit: S_x(j+1) complete implies O_x up to date.
+        int pv_next[kGroups];
+#pragma unroll
+        for (int x = 0; x < kGroups; ++x) pv_next[x] = 0;
+        int pv_done = 0;   // key tiles every group's P.V has been issued for
+        while (pv_done < n_kv) {
+          bool progress = false;
+#pragma unroll
+          for (int x = 0; x < kGroups; ++x) {
+            const int jp = pv_next[x];
+            if (jp < n_kv && tc::mbar_test(&p_full[x], jp & 1) &&
+                (jp + 1 >= n_kv || tc::mbar_test(&kv_full[(jp + 1) % kStages], ((jp + 1) / kStages) & 1))) {
+              tc::tc_fence_after();
+              TRACE(9 + 16 * x, jp);
+              issue_pv(x, jp);
+              if (jp + 1 < n_kv) issue_qk(x, jp + 1);      // commits s_full[x]
+              else tc::umma_commit(&o_full[x]);
+              TRACE(10 + 16 * x, jp);
+              pv_next[x] = jp + 1;
+              int lo = pv_next[0];
+#pragma unroll
+              for (int y = 1; y < kGroups; ++y) lo = min(lo, pv_next[y]);
+              if (lo > pv_done) {   // every group is through K/V(pv_done)
+                tc::umma_commit(&kv_empty[pv_done % kStages]);
+                pv_done = lo;
+              }
+              progress = true;
+            }
+          }
+          if (!progress && p.idle_ns > 0) __nanosleep(p.idle_ns);
+        }
+      } else if constexpr (kStatic && kGroups == 3) {
         // Free-running groups move in lock step (they share every K / V tile and the MUFU pipe), so their events come in
         // bunches: wait for all of S(j) to be read, then issue the next Q K^T of ALL groups with the k-steps interleaved
         // (group 0 k0, group 1 k0, group 2 k0, group 0 k1, ...), likewise the P V.  The tensor pipe runs MMAs in issue
@@ -256,7 +299,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           for (int kk = 0; kk < kKv / 16; ++kk) {
 #pragma unroll
             for (int x = 0; x < kGroups; ++x)
-              tc::umma_f16_ts(tO + x * kHeadDim, tP + x * (kKv / 2) + kk * 8, dv + kk * (2048 >> 4), idesc_pv, (j | kk) != 0);
+              tc::umma_f16_ts(tO + x * kHeadDim, tP + x * Sh::kStrideP + kk * 8, dv + kk * (2048 >> 4), idesc_pv, (j | kk) != 0);
           }
 #pragma unroll
           for (int x = 0; x < kGroups; ++x) tc::umma_commit(&o_full[x]);
@@ -342,7 +385,9 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
       }
     }
-  } else {  // ---------------- softmax warpgroups (four warps each); thread = query row = TMEM lane
+  };
+  // softmax warpgroups (four warps each); thread = query row = TMEM lane
+  auto role_softmax = [&]() {
     const int sw = kHigh ? warp : warp - 2;
     const int x = sw >> 2;
     const int lane_base = (warp & 3) * 32;
@@ -350,7 +395,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t lane_addr = (uint32_t)lane_base << 16;
     const float sc = p.scale_log2e;
     float m_run = -INFINITY, l_run = 0.f;
-    const uint32_t tp = tP + x * (kKv / 2) + lane_addr;
+    const uint32_t tp = tP + x * Sh::kStrideP + lane_addr;
     const uint32_t ts = tS + x * kKv + lane_addr;
     const uint32_t to = tO + x * kHeadDim + lane_addr;
     const bool tr = (sw & 3) == 0 && lane == 0 && x < 2;
@@ -371,7 +416,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tc::tmem_ld_wait();
       tc::tc_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&s_free[x]);     // the issuer may overwrite S_x with Q_x K_{j+1}^T now
+      if (!kAlias && lane == 0) tc::mbar_arrive(&s_free[x]);     // the issuer may overwrite S_x with Q_x K_{j+1}^T now
       if (tr) TRACE(te + 2, j);
       if (kv_rem < kKv) {
 #pragma unroll
@@ -394,7 +439,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       // this thread arrives on p_full, so O_x is quiescent in between.  The wait is only needed before O is rescaled
       // (rare) or P is rewritten (the first tcgen05.st, 64 exponentials later), which takes the P.V latency off the
       // softmax critical path.
-      bool o_ready = j == 0;
+      bool o_ready = kAlias || j == 0;   // aliased: S_x(j) complete implies P_x(j-1) V(j-1) complete
       auto wait_o = [&]() {
         if (!o_ready) {   // warp-uniform
           if (tr) TRACE(te + 5, j);
@@ -460,6 +505,9 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         if ((b & 3) == 3) {
           wait_o();
           tc::tmem_st32(tp + (b >> 2) * 32, pk);
+        } else if (b == kKv / 16 - 1) {   // 96 keys: the last two blocks are 16 packed columns
+          static_assert((kKv / 16) % 4 == 0 || (kKv / 16) % 4 == 2, "P store granularity");
+          tc::tmem_st16(tp + (b >> 2) * 32, pk);
         }
       }
       if (kTurns) named_arrive(2 - x, 256);          // hand the turn to the other warpgroup
@@ -475,7 +523,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
     if (kTurns && x == 0) named_sync(1, 256);      // absorb group 1's last hand-over
     // O_x complete after the last P.V
-    tc::mbar_wait(&o_full[x], (n_kv - 1) & 1);
+    tc::mbar_wait(&o_full[x], kAlias ? 0 : (n_kv - 1) & 1);   // aliased: committed once, behind the last P.V
     tc::tc_fence_after();
     // the work decode again, from an opaque copy of the CTA index: nothing of it stays live across the key loop
     int cta;
@@ -552,6 +600,20 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
       }
     }
+  };
+  if constexpr (Sh::kRegMove) {
+    if (warp >= 4 * kGroups) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+      if (warp == kWarpProd) role_producer();
+      else if (warp == kWarpIssue) role_issuer();
+    } else {
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+      role_softmax();
+    }
+  } else {
+    if (warp == kWarpProd) role_producer();
+    else if (warp == kWarpIssue) role_issuer();
+    else role_softmax();
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -741,8 +803,8 @@ static size_t split_workspace_bytes(int tail_items, int split, int rows_per_cta)
 }
 // rows per CTA / keys per tile of the configured shape (sgn_set_option "attn_shape")
 static void shape_dims(int* rows_per_cta, int* kv_tile) {
-  *rows_per_cta = g_attn_shape == 1 ? AttnShape<3, 64>::kQPerCta : AttnShape<2, 128>::kQPerCta;
-  *kv_tile = g_attn_shape == 1 ? 64 : 128;
+  *rows_per_cta = g_attn_shape == 1 ? AttnShape<3, 96>::kQPerCta : AttnShape<2, 128>::kQPerCta;
+  *kv_tile = g_attn_shape == 1 ? 96 : 128;
 }
 
 static int attention_impl(const void* d_q, int64_t ldq, const void* d_k, int64_t ldk, const void* d_v, int64_t ldv, int B,
@@ -774,9 +836,9 @@ static int attention_impl(const void* d_q, int64_t ldq, const void* d_k, int64_t
   using Kern = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, AttnParams);
   static const Kern kerns[2][4] = {
       {k_attention_tc<0, 2, 128>, k_attention_tc<1, 2, 128>, k_attention_tc<2, 2, 128>, k_attention_tc<3, 2, 128>},
-      {k_attention_tc<0, 3, 64>, k_attention_tc<1, 3, 64>, k_attention_tc<2, 3, 64>, k_attention_tc<3, 3, 64>}};
-  static const size_t smem_of[2] = {AttnShape<2, 128>::kSmem, AttnShape<3, 64>::kSmem};
-  static const int threads_of[2] = {AttnShape<2, 128>::kThreads, AttnShape<3, 64>::kThreads};
+      {k_attention_tc<0, 3, 96>, k_attention_tc<1, 3, 96>, k_attention_tc<2, 3, 96>, k_attention_tc<3, 3, 96>}};
+  static const size_t smem_of[2] = {AttnShape<2, 128>::kSmem, AttnShape<3, 96>::kSmem};
+  static const int threads_of[2] = {AttnShape<2, 128>::kThreads, AttnShape<3, 96>::kThreads};
   static bool attr_set = false;
   if (!attr_set) {
     for (int sh = 0; sh < 2; ++sh)
