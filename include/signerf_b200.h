@@ -419,24 +419,78 @@ int sgn_embed_tokens(const int32_t* d_ids, const float* d_token_table, const flo
  *   b_head1[64] b_head2[4] avg_density pad[3]
  * w_head0's 32 input columns are [SH 16 | unused | geo 15]; b_head0 carries the mean appearance embedding folded in
  * (b + W_app . mean(embedding)), as the eval renderer uses it.  Gradient buffers use the same layouts and are ACCUMULATED
- * into (zero them per step). */
+ * into (zero them per step).  Not built: the normal regularisers of `predict_normals` (orientation / pred-normal losses,
+ * signerf.py:69-80; they need the second derivative of the hash grid) and LPIPS's VGG (a host-side torch term). */
 int64_t sgn_mlp_param_count(void);
 int sgn_field_mlp_params(const SgnField* f, float** d_params);
 /* Re-derives the fp16 tensor-core fragments (and the feature scale) the renderer uses from the fp32 parameter block and
  * the current hash table - call after optimizer steps, before the next sgn_render_*.  Synchronises the stream. */
 int sgn_field_refresh(SgnField* f, void* stream);
 /* Forward of N rays x S samples through the main field: d_bins [S+1] euclidean bin edges shared by all rays, or
- * d_ray_bins [N,S+1] (exactly one non-NULL).  Outputs: d_sigma [N,S], d_color [N,S,3] (kept by the caller for the backward),
- * d_rgb [N,3] = sum w c + c_last (1 - sum w) without the eval clamp, d_acc [N] or NULL. */
+ * d_ray_bins [N,S+1] (exactly one non-NULL).  d_head_bias [N,64] or NULL: per-ray bias of the head's first layer
+ * (sgn_appearance_bias: training with per-image appearance embeddings; NULL = the folded mean embedding, eval semantics).
+ * Outputs: d_sigma [N,S], d_color [N,S,3] (kept by the caller for the backward), d_rgb [N,3] = sum w c + c_last (1 - sum w)
+ * without the eval clamp, d_acc [N] or NULL. */
 int sgn_train_forward(const SgnField* f, const float* d_origins, const float* d_directions, int64_t N, const float* d_bins,
-                      const float* d_ray_bins, int S, float* d_sigma, float* d_color, float* d_rgb, float* d_acc,
-                      void* stream);
-/* Backward: d_grad_rgb [N,3] = dL/drgb -> d_grad_table [L*T,2] and d_grad_mlp [sgn_mlp_param_count()] (+=).
- * d_ws: sgn_train_ws_bytes(N, S) bytes of 16-byte aligned scratch. */
+                      const float* d_ray_bins, int S, const float* d_head_bias, float* d_sigma, float* d_color, float* d_rgb,
+                      float* d_acc, void* stream);
+/* Backward: d_grad_rgb [N,3] = dL/drgb and, optionally, d_grad_weights [N,S] = the gradient of loss terms that read the
+ * final level's weights directly (sgn_distortion_loss) -> d_grad_table [L*T,2], d_grad_mlp [sgn_mlp_param_count()] and,
+ * when d_head_bias was given, d_grad_head_bias [N,64] (all +=).  d_ws: sgn_train_ws_bytes(N, S) bytes, 16-byte aligned. */
 int64_t sgn_train_ws_bytes(int64_t N, int S);
 int sgn_train_backward(const SgnField* f, const float* d_origins, const float* d_directions, int64_t N, const float* d_bins,
-                       const float* d_ray_bins, int S, const float* d_sigma, const float* d_color, const float* d_grad_rgb,
-                       float* d_grad_table, float* d_grad_mlp, void* d_ws, int64_t ws_bytes, void* stream);
+                       const float* d_ray_bins, int S, const float* d_head_bias, const float* d_sigma, const float* d_color,
+                       const float* d_grad_rgb, const float* d_grad_weights, float* d_grad_table, float* d_grad_mlp,
+                       float* d_grad_head_bias, void* d_ws, int64_t ws_bytes, void* stream);
+/* Per-image appearance embedding while training ([EXT] NerfactoField.get_outputs: embedding_appearance(camera_indices)
+ * concatenated to the head's input): head_bias[ray] = bias + W_app . E[camera[ray]], with W_app [64,32] the head's first
+ * layer's appearance columns, bias [64], E [num_images,32], camera indices int32 [N]; the backward accumulates (+=) the
+ * gradients of all three from d_grad_head_bias [N,64]. */
+int sgn_appearance_bias(const float* d_w_app, const float* d_bias, const float* d_embedding, int num_images,
+                        const int32_t* d_camera_indices, int64_t N, float* d_head_bias, void* stream);
+int sgn_appearance_bias_backward(const float* d_w_app, const float* d_embedding, int num_images, const int32_t* d_camera_indices,
+                                 const float* d_grad_head_bias, int64_t N, float* d_grad_w_app, float* d_grad_bias,
+                                 float* d_grad_embedding, void* stream);
+
+/* --- the proposal half of the training step ([EXT] nerfstudio ProposalNetworkSampler in training mode, losses.py
+ * interlevel_loss / distortion_loss as signerf/signerf.py:62-68 adds them to the loss dict) ---
+ * A proposal network's trainable parameters: its 5-level hash table (the caller's SgnHashGrid.d_table) and
+ * sgn_prop_param_count() = 193 contiguous floats inside the field, layout w0[16*10] b0[16] w1[16] b1 (row-major nn.Linear). */
+int64_t sgn_prop_param_count(void);
+int sgn_field_prop_params(const SgnField* f, int level, float** d_params);
+/* Samples of one training batch, all caller-allocated: level 0 = the S0 stratified initial bins, level 1 / 2 = the PDF
+ * re-samplings (S1, S2 bins).  d_spacing / d_euclid [N, S_l + 1] bin edges in the spacing domain / in metres; d_sigma /
+ * d_weights [N, S_l] of the proposal network evaluated on level l (l = 0, 1). */
+typedef struct SgnTrainSamples {
+  float* d_spacing[3];
+  float* d_euclid[3];
+  float* d_sigma[2];
+  float* d_weights[2];
+} SgnTrainSamples;
+/* ProposalNetworkSampler.generate_ray_samples while training, _anneal = 1: d_jitter [3,N] uniform draws in [0,1) (initial
+ * sampler, PDF level 1, PDF level 2; one per ray = single_jitter) or NULL for the eval bins (bin centres).  The draws are
+ * inputs so that the oracle and this path sample the same bins.  d_ws: sgn_train_sample_ws_bytes bytes, 16-byte aligned. */
+int64_t sgn_train_sample_ws_bytes(int64_t N, int S0, int S1);
+int sgn_train_sample(const SgnField* f, const float* d_origins, const float* d_directions, int64_t N, int S0, int S1, int S2,
+                     float near_plane, float far_plane, const float* d_jitter, const SgnTrainSamples* out, void* d_ws,
+                     int64_t ws_bytes, void* stream);
+/* RaySamples.get_weights: d_euclid [N,S+1], d_sigma [N,S] -> d_weights [N,S]. */
+int sgn_weights_from_density(const float* d_euclid, const float* d_sigma, int64_t N, int S, float* d_weights, void* stream);
+/* losses.py lossfun_outer of one proposal level against the final level's histogram (weights detached), mean over
+ * N * S_final, times mult: d_loss [1] += the term, d_grad_weights_prop [N,S_prop] = its gradient (overwritten).
+ * d_ws: N * (S_prop + 1) floats. */
+int sgn_interlevel_loss(const float* d_spacing_final, const float* d_weights_final, int S_final, const float* d_spacing_prop,
+                        const float* d_weights_prop, int S_prop, int64_t N, float mult, float* d_loss,
+                        float* d_grad_weights_prop, void* d_ws, int64_t ws_bytes, void* stream);
+/* losses.py distortion_loss on the final level (mip-NeRF 360 eq. 15), mean over rays, times mult: d_loss [1] += the term,
+ * d_grad_weights [N,S] = its gradient (overwritten; NULL to skip) - feed it to sgn_train_backward. */
+int sgn_distortion_loss(const float* d_spacing, const float* d_weights, int64_t N, int S, float mult, float* d_loss,
+                        float* d_grad_weights, void* stream);
+/* Backward of proposal network `level` on its N x S samples: d_grad_weights [N,S] -> d_grad_table [5*T,2],
+ * d_grad_mlp [sgn_prop_param_count()] (+=).  d_ws: N * S floats. */
+int sgn_prop_backward(const SgnField* f, int level, const float* d_origins, const float* d_directions, int64_t N, int S,
+                      const float* d_euclid, const float* d_sigma, const float* d_grad_weights, float* d_grad_table,
+                      float* d_grad_mlp, void* d_ws, int64_t ws_bytes, void* stream);
 /* `rgb_loss` of signerf/signerf.py:36-47: nerfstudio L1Loss (l1 = 1) or MSELoss (l1 = 0) = mean over all n elements;
  * d_loss [1]; d_grad [n] = d loss / d pred, or NULL. */
 int sgn_rgb_loss(const float* d_pred, const float* d_target, int64_t n, int l1, float* d_loss, float* d_grad, void* stream);

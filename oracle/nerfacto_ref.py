@@ -317,8 +317,10 @@ def flat_bin_edges(num_samples: int, near: float, far: float) -> Tensor:
 
 
 def pdf_resample(samples: SamplesRef, weights: Tensor, num_samples: int, to_euclid,
-                 histogram_padding: float = 0.01, eps: float = 1e-5) -> SamplesRef:
-    """PDFSampler.generate_ray_samples, eval branch, include_original=False."""
+                 histogram_padding: float = 0.01, eps: float = 1e-5, jitter: Optional[Tensor] = None) -> SamplesRef:
+    """PDFSampler.generate_ray_samples, include_original=False.  jitter None: the eval branch (bin centres);
+    jitter [N,1] in [0,1): the training branch with single_jitter=True, `u + rand((N,1)) / num_bins`, with the random
+    numbers handed in so that the CUDA path can be checked on the same draws."""
     num_bins = num_samples + 1
     weights = weights[..., 0] + histogram_padding
     weights_sum = torch.sum(weights, dim=-1, keepdim=True)
@@ -329,8 +331,11 @@ def pdf_resample(samples: SamplesRef, weights: Tensor, num_samples: int, to_eucl
     cdf = torch.min(torch.ones_like(pdf), torch.cumsum(pdf, dim=-1))
     cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], dim=-1)
     u = torch.linspace(0.0, 1.0 - (1.0 / num_bins), steps=num_bins)
-    u = u + 1.0 / (2 * num_bins)
-    u = u.expand(size=(*cdf.shape[:-1], num_bins)).contiguous()
+    if jitter is None:
+        u = u + 1.0 / (2 * num_bins)
+        u = u.expand(size=(*cdf.shape[:-1], num_bins)).contiguous()
+    else:
+        u = (u.expand(size=(*cdf.shape[:-1], num_bins)) + jitter / num_bins).contiguous()
     existing_bins = torch.cat([samples.spacing_starts[..., 0], samples.spacing_ends[..., -1:, 0]], dim=-1)
     inds = torch.searchsorted(cdf, u, side="right")
     below = torch.clamp(inds - 1, 0, existing_bins.shape[-1] - 1)
@@ -494,6 +499,134 @@ def render_rays_train(model: NerfactoRef, rays_o: Tensor, rays_d: Tensor, num_sa
 def signerf_rgb_loss(pred: Tensor, target: Tensor, use_l1: bool = True) -> Tensor:
     """signerf/signerf.py:36-47: `self.rgb_loss(image, output)` with nerfstudio's L1Loss = nn.L1Loss / MSELoss = nn.MSELoss."""
     return torch.nn.functional.l1_loss(target, pred) if use_l1 else torch.nn.functional.mse_loss(target, pred)
+
+
+def initial_samples_train(num_rays: int, num_samples: int, to_euclid, t_rand: Tensor) -> SamplesRef:
+    """SpacedSampler.generate_ray_samples with train_stratified while training, single_jitter=True: every ray shifts all
+    its bins by one draw t_rand [N,1] between the neighbouring bin centres."""
+    bins = torch.linspace(0.0, 1.0, num_samples + 1)[None, ...]
+    bin_centers = (bins[..., 1:] + bins[..., :-1]) / 2.0
+    bin_upper = torch.cat([bin_centers, bins[..., -1:]], -1)
+    bin_lower = torch.cat([bins[..., :1], bin_centers], -1)
+    bins = bin_lower + (bin_upper - bin_lower) * t_rand
+    euclid = to_euclid(bins)
+    return SamplesRef(euclid[..., :-1, None], euclid[..., 1:, None], bins[..., :-1, None], bins[..., 1:, None])
+
+
+def sdist_of(s: SamplesRef) -> Tensor:
+    """losses.py ray_samples_to_sdist: the S+1 spacing-domain bin edges of a ray."""
+    return torch.cat([s.spacing_starts[..., 0], s.spacing_ends[..., -1:, 0]], dim=-1)
+
+
+def outer(t0_starts: Tensor, t0_ends: Tensor, t1_starts: Tensor, t1_ends: Tensor, y1: Tensor) -> Tensor:
+    """losses.py outer: for every interval of t0, the mass of the t1 histogram that could fall inside it (upper bound)."""
+    cy1 = torch.cat([torch.zeros_like(y1[..., :1]), torch.cumsum(y1, dim=-1)], dim=-1)
+    idx_lo = torch.searchsorted(t1_starts.contiguous(), t0_starts.contiguous(), side="right") - 1
+    idx_lo = torch.clamp(idx_lo, min=0, max=y1.shape[-1] - 1)
+    idx_hi = torch.searchsorted(t1_ends.contiguous(), t0_ends.contiguous(), side="right")
+    idx_hi = torch.clamp(idx_hi, min=0, max=y1.shape[-1] - 1)
+    cy1_lo = torch.take_along_dim(cy1[..., :-1], idx_lo, dim=-1)
+    cy1_hi = torch.take_along_dim(cy1[..., 1:], idx_hi, dim=-1)
+    return cy1_hi - cy1_lo
+
+
+def lossfun_outer(t: Tensor, w: Tensor, t_env: Tensor, w_env: Tensor) -> Tensor:
+    """losses.py lossfun_outer (mip-NeRF 360 proposal loss): penalise the proposal histogram where it under-covers w."""
+    eps = torch.finfo(torch.float32).eps
+    w_outer = outer(t[..., :-1], t[..., 1:], t_env[..., :-1], t_env[..., 1:], w_env)
+    return torch.clip(w - w_outer, min=0) ** 2 / (w + eps)
+
+
+def interlevel_loss(weights_list: List[Tensor], samples_list: List[SamplesRef]) -> Tensor:
+    """losses.py interlevel_loss: the final level's (detached) histogram against every proposal level's."""
+    c = sdist_of(samples_list[-1]).detach()
+    w = weights_list[-1][..., 0].detach()
+    loss = 0.0
+    for samples, weights in zip(samples_list[:-1], weights_list[:-1]):
+        loss = loss + torch.mean(lossfun_outer(c, w, sdist_of(samples), weights[..., 0]))
+    return loss
+
+
+def lossfun_distortion(t: Tensor, w: Tensor) -> Tensor:
+    """losses.py lossfun_distortion (mip-NeRF 360 eq. 15)."""
+    ut = (t[..., 1:] + t[..., :-1]) / 2
+    dut = torch.abs(ut[..., :, None] - ut[..., None, :])
+    loss_inter = torch.sum(w * torch.sum(w[..., None, :] * dut, dim=-1), dim=-1)
+    loss_intra = torch.sum(w**2 * (t[..., 1:] - t[..., :-1]), dim=-1) / 3
+    return loss_inter + loss_intra
+
+
+def distortion_loss(weights_list: List[Tensor], samples_list: List[SamplesRef]) -> Tensor:
+    """losses.py distortion_loss: on the final level (metrics_dict["distortion"] of NerfactoModel while training)."""
+    return torch.mean(lossfun_distortion(sdist_of(samples_list[-1]), weights_list[-1][..., 0]))
+
+
+def samples_from_edges(spacing: Tensor, euclid: Tensor) -> SamplesRef:
+    """[N,S+1] bin edges (spacing domain, metres) -> SamplesRef."""
+    return SamplesRef(euclid[..., :-1, None], euclid[..., 1:, None], spacing[..., :-1, None], spacing[..., 1:, None])
+
+
+def forward_train(model: NerfactoRef, rays_o: Tensor, rays_d: Tensor, jitter: Optional[Tensor] = None,
+                  camera_indices: Optional[Tensor] = None, update_proposals: bool = True,
+                  fixed_samples: Optional[List[SamplesRef]] = None) -> Dict[str, object]:
+    """NerfactoModel.get_outputs WHILE TRAINING (models/nerfacto.py get_outputs + ProposalNetworkSampler.generate_ray_samples
+    with _anneal = 1, i.e. past proposal_weights_anneal_max_num_iters, as a fine-tune of a trained scene is): stratified
+    initial bins, two proposal levels with PDF re-sampling, the main field on the last level, autograd on.
+    jitter [3, N] = the three per-ray draws (initial sampler, PDF level 1, PDF level 2); None = bin centres (eval bins).
+    camera_indices [N]: per-ray rows of the appearance embedding (training semantics); None = the mean (eval semantics).
+    update_proposals False = a step between two proposal updates (`proposal_update_every`): densities under no_grad.
+    fixed_samples: the three levels' bins handed in instead of sampled (gradient checks on identical sample positions:
+    the samplers carry no gradient, but a 1e-6 shift of a bin edge moves a sample across cells of the finest hash levels)."""
+    n = rays_o.shape[0]
+    nears = torch.ones_like(rays_o[..., 0:1]) * model.near
+    fars = torch.ones_like(rays_o[..., 0:1]) * model.far
+    to_euclid = make_to_euclid(nears, fars)
+    counts = list(model.num_proposal_samples) + [model.num_nerf_samples]
+    jit = (lambda i: None) if jitter is None else (lambda i: jitter[i].reshape(n, 1))
+    if fixed_samples is not None:
+        samples = fixed_samples[0]
+    else:
+        samples = initial_samples(n, counts[0], to_euclid) if jitter is None else initial_samples_train(n, counts[0], to_euclid, jit(0))
+    weights_list, samples_list = [], []
+    for i, net in enumerate(model.proposal_networks):
+        positions = positions_of(rays_o, rays_d, samples)
+        if update_proposals:
+            density = net.density(positions)
+        else:
+            with torch.no_grad():
+                density = net.density(positions)
+        w = get_weights(samples, density)
+        weights_list.append(w)
+        samples_list.append(samples)
+        if fixed_samples is not None:
+            samples = fixed_samples[i + 1]
+        else:
+            samples = pdf_resample(samples, w.detach(), counts[i + 1], to_euclid, jitter=jit(i + 1))
+    positions = positions_of(rays_o, rays_d, samples)
+    density, geo = model.field.get_density(positions)
+    dirs = rays_d[:, None, :].expand(-1, positions.shape[1], -1)
+    if camera_indices is None:
+        rgb = model.field.get_rgb(dirs, geo)
+    else:
+        d = sh_components_deg4(((dirs + 1.0) / 2.0).reshape(-1, 3))
+        app = model.field.embedding_appearance(camera_indices)[:, None, :].expand(-1, positions.shape[1], -1)
+        h = torch.cat([d, geo.reshape(-1, model.field.geo_feat_dim), app.reshape(-1, model.field.appearance_embedding_dim)], dim=-1)
+        rgb = model.field.mlp_head(h).view(*dirs.shape[:-1], -1)
+    weights = get_weights(samples, density)
+    weights_list.append(weights)
+    samples_list.append(samples)
+    comp = torch.sum(weights * rgb, dim=-2)
+    rgb_out = comp + rgb[..., -1, :] * (1.0 - torch.sum(weights, dim=-2))
+    return {"rgb": rgb_out, "weights_list": weights_list, "samples_list": samples_list}
+
+
+def signerf_loss_dict(out: Dict[str, object], target: Tensor, use_l1: bool = True, interlevel_loss_mult: float = 1.0,
+                      distortion_loss_mult: float = 0.002) -> Dict[str, Tensor]:
+    """SIGNeRFModel.get_loss_dict while training, without the LPIPS term (signerf/signerf.py:41-82; the multipliers are
+    NerfactoModelConfig's defaults, which signerf_config.py leaves untouched)."""
+    return {"rgb_loss": signerf_rgb_loss(out["rgb"], target, use_l1),
+            "interlevel_loss": interlevel_loss_mult * interlevel_loss(out["weights_list"], out["samples_list"]),
+            "distortion_loss": distortion_loss_mult * distortion_loss(out["weights_list"], out["samples_list"])}
 
 
 def patch_sample_method(batch_size: int, num_images: int, image_height: int, image_width: int, patch_size: int,

@@ -62,6 +62,11 @@ class SgnEpilogue(C.Structure):
                 ("nchw", C.c_int), ("act_silu", C.c_int)]
 
 
+class SgnTrainSamples(C.Structure):
+    _fields_ = [("d_spacing", C.c_void_p * 3), ("d_euclid", C.c_void_p * 3), ("d_sigma", C.c_void_p * 2),
+                ("d_weights", C.c_void_p * 2)]
+
+
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
 # name -> (restype, argtypes); every symbol include/signerf_b200.h declares.
@@ -79,9 +84,19 @@ SIGNATURES = {
     "sgn_mlp_param_count": (_i64, []),
     "sgn_field_mlp_params": (_i, [_vp, C.POINTER(_vp)]),
     "sgn_field_refresh": (_i, [_vp, _vp]),
-    "sgn_train_forward": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "sgn_train_forward": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sgn_train_ws_bytes": (_i64, [_i64, _i]),
-    "sgn_train_backward": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "sgn_train_backward": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "sgn_appearance_bias": (_i, [_vp, _vp, _vp, _i, _vp, _i64, _vp, _vp]),
+    "sgn_appearance_bias_backward": (_i, [_vp, _vp, _i, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "sgn_prop_param_count": (_i64, []),
+    "sgn_field_prop_params": (_i, [_vp, _i, C.POINTER(_vp)]),
+    "sgn_train_sample_ws_bytes": (_i64, [_i64, _i, _i]),
+    "sgn_train_sample": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _f, _f, _vp, C.POINTER(SgnTrainSamples), _vp, _i64, _vp]),
+    "sgn_weights_from_density": (_i, [_vp, _vp, _i64, _i, _vp, _vp]),
+    "sgn_interlevel_loss": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i64, _f, _vp, _vp, _vp, _i64, _vp]),
+    "sgn_distortion_loss": (_i, [_vp, _vp, _i64, _i, _f, _vp, _vp, _vp]),
+    "sgn_prop_backward": (_i, [_vp, _i, _vp, _vp, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "sgn_rgb_loss": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp]),
     "sgn_adam_step": (_i, [_vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _i, _vp]),
     "sgn_render_rays": (_i, [_vp, _vp, _vp, _i64, C.POINTER(SgnRenderOpts), _vp, _vp, _vp, _vp]),

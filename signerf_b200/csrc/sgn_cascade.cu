@@ -94,6 +94,7 @@ struct PdfParams {
   const float* spacing_in;    // shared [S+1] or per-ray [rays][S+1] spacing-domain bins
   int spacing_per_ray;
   const float* u;             // [nb] sample positions in cdf space
+  const float* jitter;        // training (PDFSampler.train_stratified, single_jitter): [rays] draws, u_j + draw / nb; else null
   float* cdf_scratch;         // [rays][S+1]
   float* spacing_out;         // [rays][nb]
   float* euclid_out;          // [rays][nb]
@@ -102,7 +103,8 @@ struct PdfParams {
   int S, nb;
 };
 
-// PDFSampler.generate_ray_samples (eval, include_original=False): one thread per ray.
+// PDFSampler.generate_ray_samples (include_original=False): one thread per ray.  Eval: u = bin centres of the cdf axis;
+// training: u = linspace(0, 1 - 1/nb, nb) + rand((rays, 1)) / nb with the draws handed in.
 __global__ void k_pdf_resample(const __grid_constant__ PdfParams p) {
   const float pad_hist = 0.01f, eps = 1e-5f;
   for (int64_t ray = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; ray < p.rays;
@@ -124,8 +126,9 @@ __global__ void k_pdf_resample(const __grid_constant__ PdfParams p) {
     }
     // searchsorted(cdf, u, side="right") by a forward merge: both sequences ascend.
     int idx = 0;
+    const float shift = p.jitter ? __fdiv_rn(__ldg(p.jitter + ray), (float)p.nb) : 0.f;
     for (int j = 0; j < p.nb; ++j) {
-      const float u = __ldg(p.u + j);
+      const float u = p.jitter ? __fadd_rn(__ldg(p.u + j), shift) : __ldg(p.u + j);
       while (idx <= p.S && !(cdf[idx] > u)) ++idx;  // first idx with cdf[idx] > u, or S+1
       const int below = min(max(idx - 1, 0), p.S), above = min(idx, p.S);
       const float c0 = cdf[below], c1 = cdf[above];
@@ -143,7 +146,7 @@ __global__ void k_pdf_resample(const __grid_constant__ PdfParams p) {
 static float h_spacing(float x) { return x < 1.f ? x / 2.f : 1.f - 1.f / (2.f * x); }
 
 // u = linspace(0, 1 - 1/nb, nb) + 1/(2 nb), evaluated like torch (fp32 symmetric linspace).
-static void host_pdf_u(int nb, std::vector<float>& u) {
+void host_pdf_u(int nb, std::vector<float>& u) {
   u.resize(nb);
   const float end = (float)(1.0 - 1.0 / (double)nb);
   const float step = nb > 1 ? (end - 0.f) / (float)(nb - 1) : 0.f;
@@ -153,10 +156,23 @@ static void host_pdf_u(int nb, std::vector<float>& u) {
     u[i] = base + add;
   }
 }
-static void host_linspace01(int n, std::vector<float>& out) {
+void host_linspace01(int n, std::vector<float>& out) {
   out.resize(n);
   float step = 1.f / (float)(n - 1);
   for (int i = 0; i < n; ++i) out[i] = i < n / 2 ? step * (float)i : 1.f - step * (float)(n - i - 1);
+}
+
+// One PDF re-sampling pass over per-ray spacing bins (the training sampler's entry, sgn_train_prop.cu).
+int launch_pdf_resample(const float* weights, const float* spacing_in, const float* u, const float* jitter, float* cdf_scratch,
+                        float* spacing_out, float* euclid_out, float s_near, float s_far, int64_t rays, int S, int nb,
+                        cudaStream_t st) {
+  PdfParams q;
+  q.weights = weights; q.spacing_in = spacing_in; q.spacing_per_ray = 1; q.u = u; q.jitter = jitter;
+  q.cdf_scratch = cdf_scratch; q.spacing_out = spacing_out; q.euclid_out = euclid_out;
+  q.s_near = s_near; q.s_far = s_far; q.rays = rays; q.S = S; q.nb = nb;
+  k_pdf_resample<<<(int)std::max<int64_t>(1, std::min<int64_t>((rays + 127) / 128, (int64_t)sm_count() * 16)), 128, 0, st>>>(q);
+  SGN_LAUNCH_CHECK();
+  return SGN_OK;
 }
 
 struct AsyncBuf {
@@ -238,7 +254,7 @@ int render_cascade(const SgnField* f, const RaySource& src, int V, int H, int W,
     k_prop_weights<false><<<pblocks, kPThreads, (S0 + 1) * 4, st>>>(pp);
     SGN_LAUNCH_CHECK();
     PdfParams q;
-    q.weights = wbuf.as<float>(); q.spacing_in = d_sp0; q.spacing_per_ray = 0; q.u = d_u1;
+    q.weights = wbuf.as<float>(); q.spacing_in = d_sp0; q.spacing_per_ray = 0; q.u = d_u1; q.jitter = nullptr;
     q.cdf_scratch = cdfbuf.as<float>(); q.spacing_out = sp1.as<float>(); q.euclid_out = eu1.as<float>();
     q.s_near = s_near; q.s_far = s_far; q.rays = rays; q.S = S0; q.nb = S1 + 1;
     k_pdf_resample<<<rblocks, 128, 0, st>>>(q);

@@ -388,8 +388,9 @@ __device__ __forceinline__ void warp_stage_sh(__half* __restrict__ stage, int la
 }
 
 // ---------------------------------------------------------------- fp32 CUDA-core MLP (parity path)
+// head_bias: 64 per-ray values replacing b_head0 (training with per-image appearance embeddings), or null.
 static __device__ __noinline__ void field_mlp_f32(const MlpF32* __restrict__ w, const float feat[32], const float sh[16],
-                                           float& logit, float rgb[3]) {
+                                           float& logit, float rgb[3], const float* __restrict__ head_bias = nullptr) {
   float h[64];
   for (int n = 0; n < 64; ++n) {
     float a = w->b_base0[n];
@@ -408,7 +409,7 @@ static __device__ __noinline__ void field_mlp_f32(const MlpF32* __restrict__ w, 
   logit = hin[16];
   hin[16] = 0.f;
   for (int n = 0; n < 64; ++n) {
-    float a = w->b_head0[n];
+    float a = head_bias ? __ldg(head_bias + n) : w->b_head0[n];
     for (int k = 0; k < 32; ++k) a = fmaf(w->w_head0[n * 32 + k], hin[k], a);
     h[n] = fmaxf(a, 0.f);
   }

@@ -32,6 +32,7 @@ struct TrainRays {
   const float* ray_bins;  // [N, S+1] per ray
   int64_t N;
   int S;
+  const float* head_bias = nullptr;   // [N, 64] per-ray bias of head layer 0 (b + W_app . embedding[camera]), or null
 };
 
 __device__ __forceinline__ void sample_interval(const TrainRays& r, int64_t ray, int i, float& t0, float& t1) {
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(128) k_train_field(const GridDev grid, const M
       feat[2 * l + 1] = f.y;
     }
     float logit, c3[3];
-    field_mlp_f32(sw, feat, sh, logit, c3);
+    field_mlp_f32(sw, feat, sh, logit, c3, r.head_bias ? r.head_bias + 64 * ray : nullptr);
     sigma[s] = sel ? sw->avg_density * expf(logit) : 0.f;
     color[3 * s + 0] = sigmoidf_(c3[0]);
     color[3 * s + 1] = sigmoidf_(c3[1]);
@@ -113,9 +114,11 @@ __global__ void k_train_composite(const TrainRays r, const float* __restrict__ s
 // ---------------------------------------------------------------- backward, ray level
 // C = sum_i w_i (c_i - c_L) + c_L with L the last sample, w_i = (1 - e^{-dd_i}) e^{-sum_{j<i} dd_j}, dd_i = delta_i sigma_i:
 //   dL/dc_i  = g w_i (+ g (1 - sum w) for i = L)
-//   dL/ddd_k = G_k T_k e^{-dd_k} - sum_{i>k} G_i w_i,   G_i = g . (c_i - c_L)
+//   dL/ddd_k = G_k T_k e^{-dd_k} - sum_{i>k} G_i w_i,   G_i = dL/dw_i = g . (c_i - c_L) + gweights_i
+// gweights [N,S]: gradient of the terms that read the weights directly (distortion loss), or null.
 __global__ void k_train_ray_bwd(const TrainRays r, const float* __restrict__ sigma, const float* __restrict__ color,
-                                const float* __restrict__ grad_rgb, float* __restrict__ gsigma, float* __restrict__ gcolor) {
+                                const float* __restrict__ grad_rgb, const float* __restrict__ gweights,
+                                float* __restrict__ gsigma, float* __restrict__ gcolor) {
   for (int64_t ray = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; ray < r.N; ray += (int64_t)gridDim.x * blockDim.x) {
     const float* sg = sigma + ray * r.S;
     const float* cl = color + 3 * ray * r.S;
@@ -143,7 +146,8 @@ __global__ void k_train_ray_bwd(const TrainRays r, const float* __restrict__ sig
       sample_interval(r, ray, i, t0, t1);
       const float delta = __fsub_rn(t1, t0);
       const float w = gs[i];
-      const float G = g0 * (cl[3 * i] - l0) + g1 * (cl[3 * i + 1] - l1) + g2 * (cl[3 * i + 2] - l2);
+      const float G = g0 * (cl[3 * i] - l0) + g1 * (cl[3 * i + 1] - l1) + g2 * (cl[3 * i + 2] - l2) +
+                      (gweights ? gweights[ray * r.S + i] : 0.f);
       const float t_after = gc[3 * i];
       gs[i] = delta * (G * t_after - suffix);
       suffix += G * w;
@@ -212,7 +216,7 @@ __global__ void __launch_bounds__(128) k_train_field_bwd(const __grid_constant__
       SGN_AT(hin, 16 + n) = n == 0 ? 0.f : a;
     }
     for (int n = 0; n < 64; ++n) {
-      float a = w->b_head0[n];
+      float a = r.head_bias ? __ldg(r.head_bias + 64 * ray + n) : w->b_head0[n];
       for (int k = 0; k < 32; ++k) a = fmaf(w->w_head0[n * 32 + k], SGN_AT(hin, k), a);
       SGN_AT(h1, n) = fmaxf(a, 0.f);
     }
@@ -278,6 +282,72 @@ __global__ void __launch_bounds__(128) k_train_field_bwd(const __grid_constant__
     }
 #undef SGN_AT
   }
+}
+
+// grad_head_bias[ray][n] += sum over the ray's samples inside the chunk of da1[n] (rows 80..143 of the delta slab): the
+// gradient of the per-ray bias of head layer 0, from which the appearance embedding's gradients follow.
+__global__ void k_ray_bias_reduce(const float* __restrict__ deltas, int64_t first, int64_t count, int64_t cap, int S,
+                                  float* __restrict__ grad_head_bias) {
+  const int64_t ray0 = first / S, ray1 = (first + count - 1) / S;
+  const int64_t total = (ray1 - ray0 + 1) * 64;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(e / (ray1 - ray0 + 1));            // consecutive threads: consecutive rays of one component row
+    const int64_t ray = ray0 + (e - (int64_t)n * (ray1 - ray0 + 1));
+    const int64_t s0 = max(ray * S, first), s1 = min((ray + 1) * S, first + count);
+    const float* row = deltas + (size_t)(80 + n) * cap - first;
+    float acc = 0.f;
+    for (int64_t s = s0; s < s1; ++s) acc += row[s];
+    grad_head_bias[ray * 64 + n] += acc;
+  }
+}
+
+// Appearance embedding (NerfactoField while training: embedding_appearance(camera_indices) concatenated to the head's
+// input): head_bias[ray] = b + W_app . E[cam[ray]];  W_app [64,32] = the head's columns 31..62, E [M,32].
+__global__ void k_appearance_bias(const float* __restrict__ w_app, const float* __restrict__ b, const float* __restrict__ emb,
+                                  const int32_t* __restrict__ cam, int64_t N, float* __restrict__ head_bias) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < N * 64; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t ray = e >> 6;
+    const int n = (int)(e & 63);
+    const float* row = emb + (size_t)__ldg(cam + ray) * 32;
+    float a = __ldg(b + n);
+#pragma unroll
+    for (int k = 0; k < 32; ++k) a = fmaf(__ldg(w_app + n * 32 + k), __ldg(row + k), a);
+    head_bias[e] = a;
+  }
+}
+
+// ... and its backward: gW_app[n][k] += sum_ray g[ray][n] E[cam][k], gb[n] += sum_ray g[ray][n], gE[cam][k] += sum_n W_app[n][k] g[ray][n].
+// 256 threads own the 64 x 32 outputs (8 each) of one slab of rays.
+__global__ void __launch_bounds__(256) k_appearance_bwd(const float* __restrict__ w_app, const float* __restrict__ emb,
+                                                        const int32_t* __restrict__ cam, const float* __restrict__ g, int64_t N,
+                                                        int per_cta, float* __restrict__ gw_app, float* __restrict__ gb,
+                                                        float* __restrict__ gemb) {
+  __shared__ float sw[64 * 32];
+  __shared__ float sg[64];
+  __shared__ float se[32];
+  for (int i = threadIdx.x; i < 64 * 32; i += 256) sw[i] = w_app[i];
+  const int n = threadIdx.x >> 2, k0 = (threadIdx.x & 3) * 8;
+  float acc[8] = {}, bacc = 0.f;
+  const int64_t r0 = (int64_t)blockIdx.x * per_cta, r1 = min(N, r0 + per_cta);
+  for (int64_t ray = r0; ray < r1; ++ray) {
+    __syncthreads();
+    const int c = __ldg(cam + ray);
+    if (threadIdx.x < 64) sg[threadIdx.x] = g[ray * 64 + threadIdx.x];
+    else if (threadIdx.x < 96) se[threadIdx.x - 64] = emb[(size_t)c * 32 + threadIdx.x - 64];
+    __syncthreads();
+    const float gn = sg[n];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = fmaf(gn, se[k0 + q], acc[q]);
+    if ((threadIdx.x & 3) == 0) bacc += gn;
+    if (threadIdx.x < 32) {
+      float ge = 0.f;
+      for (int m = 0; m < 64; ++m) ge = fmaf(sw[m * 32 + threadIdx.x], sg[m], ge);
+      atomicAdd(gemb + (size_t)c * 32 + threadIdx.x, ge);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) atomicAdd(gw_app + n * 32 + k0 + q, acc[q]);
+  if ((threadIdx.x & 3) == 0) atomicAdd(gb + n, bacc);
 }
 
 // dW[n][k] += sum_s D[s][doff + n] * A[s][aoff + k]  (n < N <= 64, k < K <= 64);  db[n] += sum_s D[s][doff + n]
@@ -389,14 +459,14 @@ static int check_rays(const SgnField* f, const float* o, const float* d, int64_t
 }
 
 extern "C" int sgn_train_forward(const SgnField* f, const float* d_origins, const float* d_directions, int64_t N,
-                                 const float* d_bins, const float* d_ray_bins, int S, float* d_sigma, float* d_color,
-                                 float* d_rgb, float* d_acc, void* stream) {
+                                 const float* d_bins, const float* d_ray_bins, int S, const float* d_head_bias, float* d_sigma,
+                                 float* d_color, float* d_rgb, float* d_acc, void* stream) {
   int rc = check_rays(f, d_origins, d_directions, N, d_bins, d_ray_bins, S);
   if (rc) return rc;
   if (N == 0) return SGN_OK;
   SGN_CHECK_ARG(d_sigma && d_color && d_rgb, "null output");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const TrainRays r{d_origins, d_directions, d_bins, d_ray_bins, N, S};
+  const TrainRays r{d_origins, d_directions, d_bins, d_ray_bins, N, S, d_head_bias};
   static bool attr = false;
   if (!attr) {
     SGN_CUDA(cudaFuncSetAttribute(k_train_field, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MlpF32)));
@@ -419,8 +489,9 @@ extern "C" int64_t sgn_train_ws_bytes(int64_t N, int S) {
 }
 
 extern "C" int sgn_train_backward(const SgnField* f, const float* d_origins, const float* d_directions, int64_t N,
-                                  const float* d_bins, const float* d_ray_bins, int S, const float* d_sigma,
-                                  const float* d_color, const float* d_grad_rgb, float* d_grad_table, float* d_grad_mlp,
+                                  const float* d_bins, const float* d_ray_bins, int S, const float* d_head_bias,
+                                  const float* d_sigma, const float* d_color, const float* d_grad_rgb,
+                                  const float* d_grad_weights, float* d_grad_table, float* d_grad_mlp, float* d_grad_head_bias,
                                   void* d_ws, int64_t ws_bytes, void* stream) {
   int rc = check_rays(f, d_origins, d_directions, N, d_bins, d_ray_bins, S);
   if (rc) return rc;
@@ -428,8 +499,10 @@ extern "C" int sgn_train_backward(const SgnField* f, const float* d_origins, con
   SGN_CHECK_ARG(d_sigma && d_color && d_grad_rgb && d_grad_table && d_grad_mlp && d_ws, "null pointer");
   SGN_CHECK_ARG(ws_bytes >= sgn_train_ws_bytes(N, S), "workspace smaller than sgn_train_ws_bytes");
   SGN_CHECK_ARG((reinterpret_cast<uintptr_t>(d_ws) & 15) == 0, "workspace must be 16-byte aligned");
+  SGN_CHECK_ARG((d_head_bias != nullptr) == (d_grad_head_bias != nullptr),
+                "d_head_bias and d_grad_head_bias are given together (per-image appearance) or not at all");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const TrainRays r{d_origins, d_directions, d_bins, d_ray_bins, N, S};
+  const TrainRays r{d_origins, d_directions, d_bins, d_ray_bins, N, S, d_head_bias};
   const int64_t samples = N * S;
   float* gsigma = reinterpret_cast<float*>(d_ws);
   float* gcolor = gsigma + samples;
@@ -440,7 +513,7 @@ extern "C" int sgn_train_backward(const SgnField* f, const float* d_origins, con
     SGN_CUDA(cudaFuncSetAttribute(k_train_field_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MlpF32)));
     attr = true;
   }
-  k_train_ray_bwd<<<blocks_for(N, 128, 8), 128, 0, st>>>(r, d_sigma, d_color, d_grad_rgb, gsigma, gcolor);
+  k_train_ray_bwd<<<blocks_for(N, 128, 8), 128, 0, st>>>(r, d_sigma, d_color, d_grad_rgb, d_grad_weights, gsigma, gcolor);
   SGN_LAUNCH_CHECK();
   MlpF32* G = reinterpret_cast<MlpF32*>(d_grad_mlp);   // gradients in the parameter block's own layout
   for (int64_t first = 0; first < samples; first += kBwdChunk) {
@@ -464,7 +537,36 @@ extern "C" int sgn_train_backward(const SgnField* f, const float* d_origins, con
     SGN_LAUNCH_CHECK();
     k_outer_reduce<<<ctas, 256, 0, st>>>(deltas, 208, 3, acts, 192, 64, p.count, p.cap, 64, G->w_head2, G->b_head2, per_cta);
     SGN_LAUNCH_CHECK();
+    if (d_grad_head_bias) {
+      k_ray_bias_reduce<<<blocks_for((p.count / S + 2) * 64, 128, 8), 128, 0, st>>>(deltas, first, p.count, p.cap, S, d_grad_head_bias);
+      SGN_LAUNCH_CHECK();
+    }
   }
+  return SGN_OK;
+}
+
+extern "C" int sgn_appearance_bias(const float* d_w_app, const float* d_bias, const float* d_embedding, int num_images,
+                                   const int32_t* d_camera_indices, int64_t N, float* d_head_bias, void* stream) {
+  SGN_CHECK_ARG(N >= 0 && num_images >= 1, "bad shape");
+  if (N == 0) return SGN_OK;
+  SGN_CHECK_ARG(d_w_app && d_bias && d_embedding && d_camera_indices && d_head_bias, "null pointer");
+  k_appearance_bias<<<blocks_for(N * 64, 256, 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      d_w_app, d_bias, d_embedding, d_camera_indices, N, d_head_bias);
+  SGN_LAUNCH_CHECK();
+  return SGN_OK;
+}
+
+extern "C" int sgn_appearance_bias_backward(const float* d_w_app, const float* d_embedding, int num_images,
+                                            const int32_t* d_camera_indices, const float* d_grad_head_bias, int64_t N,
+                                            float* d_grad_w_app, float* d_grad_bias, float* d_grad_embedding, void* stream) {
+  SGN_CHECK_ARG(N >= 0 && num_images >= 1, "bad shape");
+  if (N == 0) return SGN_OK;
+  SGN_CHECK_ARG(d_w_app && d_embedding && d_camera_indices && d_grad_head_bias && d_grad_w_app && d_grad_bias && d_grad_embedding,
+                "null pointer");
+  const int per_cta = (int)std::max<int64_t>(16, (N + 2 * sm_count() - 1) / (2 * sm_count()));
+  k_appearance_bwd<<<(int)((N + per_cta - 1) / per_cta), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      d_w_app, d_embedding, d_camera_indices, d_grad_head_bias, N, per_cta, d_grad_w_app, d_grad_bias, d_grad_embedding);
+  SGN_LAUNCH_CHECK();
   return SGN_OK;
 }
 

@@ -1,9 +1,11 @@
 """BASELINE config 5 — "full SIGNeRF edit loop: proxy mesh, 30 cameras, refinement rounds": dataset generation
 (plugin.DatasetGenerator.generate_dataset, reference datasetgenerator.py:185-393) alternating with NeRF fine-tuning on the
 generated images (the reference's trainer swaps the pipeline onto the generated dataset and trains SIGNeRFModel on it,
-signerf_trainer.py:219-235; here the slice of that training signerf_b200/train.py covers: main field, L1 image loss on
-32 x 32 patches, Adam).  Multi-GPU: generation shards the dataset cameras over the ranks; training is data-parallel - every
-rank draws its own patches and the gradients are summed with ONE all-reduce per step (the path's only reduction)."""
+signerf_trainer.py:219-235; here the training step of signerf_b200/train.py: with a `NerfactoTrainer` the whole nerfacto
+step - proposal sampler in training mode, rgb + interlevel + distortion losses, per-image appearance embeddings, Adam on
+fields and proposal networks; with a `FieldTrainer` the main-field slice on flat bins).  Multi-GPU: generation shards the
+dataset cameras over the ranks; training is data-parallel - every rank draws its own patches and the gradients are summed
+with ONE flattened all-reduce per step (the path's only reduction)."""
 from __future__ import annotations
 
 import json
@@ -15,7 +17,7 @@ import torch
 from torch import Tensor
 
 from . import ops
-from .train import FieldTrainer, PatchPixelSampler, PatchPixelSamplerConfig
+from .train import FieldTrainer, NerfactoTrainer, PatchPixelSampler, PatchPixelSamplerConfig
 
 
 def load_generated_images(dataset_dir) -> Tuple[Tensor, Tensor, Tensor]:
@@ -37,7 +39,7 @@ def load_generated_images(dataset_dir) -> Tuple[Tensor, Tensor, Tensor]:
 
 
 class FineTuner:
-    """K fine-tune steps of the main field on a set of posed images."""
+    """K fine-tune steps on a set of posed images."""
 
     def __init__(self, trainer: FieldTrainer, num_samples: int = 48, rays_per_batch: int = 16384, patch_size: int = 32,
                  near: float = 0.05, far: float = 1000.0, seed: int = 0):
@@ -57,11 +59,27 @@ class FineTuner:
         origins, dirs, _, _ = ops.generate_rays(c2w.to(dev), intr.to(dev), h, w)          # [N,H,W,3] each
         world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         losses = []
+        full = isinstance(tr, NerfactoTrainer)
         for it in range(steps):
             idx = self.sampler.sample_method(self.sampler.num_rays_per_batch, n, h, w, device=dev, generator=self.gen)
             i, y, x = idx[:, 0], idx[:, 1], idx[:, 2]
             o, d, target = origins[i, y, x].contiguous(), dirs[i, y, x].contiguous(), images[i, y, x].contiguous()
-            if world == 1:
+            if full:
+                jitter = torch.rand((3, o.shape[0]), device=dev, generator=self.gen)
+                cams = i.to(torch.int32) if tr.embedding is not None and tr.embedding.shape[0] >= n else None
+                out = tr.forward_backward(o, d, target, jitter, cams)
+                if world > 1:
+                    grads = tr.all_gradients()
+                    flat = torch.cat([g.reshape(-1) for g in grads])
+                    dist.all_reduce(flat)
+                    flat.mul_(1.0 / world)
+                    off = 0
+                    for g in grads:
+                        g.copy_(flat[off:off + g.numel()].view_as(g))
+                        off += g.numel()
+                tr.optimizer_step()
+                loss = sum(out.values())
+            elif world == 1:
                 loss = tr.step(o, d, self.bins, target)
             else:
                 from . import train as T

@@ -9,9 +9,12 @@ Mirrors, on the reference side,
     it plugs in as any differentiable function of the rendered rgb through `render_rays_train` (a torch.autograd.Function
     whose backward is the CUDA backward of the field);
   * nerfstudio's Adam on the `fields` parameter group (signerf_config.py:43-50).
-What this slice does NOT train yet: the proposal networks (interlevel loss), the distortion / normal regularisers and
-per-image appearance embeddings (the mean embedding stays folded into the head's bias, as in the eval renderer); the rays'
-bins come from the caller (the eval cascade's, or the flat piecewise bins)."""
+`FieldTrainer` is the main-field slice (caller's bins, mean appearance embedding folded into the head's bias);
+`NerfactoTrainer` is the whole nerfacto training step as `SIGNeRFModel` inherits it (signerf.py:62-68): the proposal
+sampler in training mode (stratified bins, jittered PDF re-sampling; the draws are inputs), the two proposal networks
+trained by `interlevel_loss`, `distortion_loss` on the final level, per-image appearance embeddings, and Adam on the
+`fields` and `proposal_networks` groups.  NOT built: the normal regularisers of `predict_normals` (signerf.py:69-80; they
+need second derivatives of the hash grid), the camera optimizer and the lr schedulers (host-side scalars)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -117,8 +120,9 @@ def _bins_args(bins: Tensor, n_rays: int):
     raise ValueError(f"bins must be [S+1] or [N,S+1], got {tuple(bins.shape)}")
 
 
-def train_forward(fld: NerfactoFieldB200, origins: Tensor, directions: Tensor, bins: Tensor):
-    """-> (rgb [N,3], acc [N], saved (sigma [N,S], color [N,S,3])); rgb is not clamped (training-mode RGBRenderer)."""
+def train_forward(fld: NerfactoFieldB200, origins: Tensor, directions: Tensor, bins: Tensor, head_bias: Optional[Tensor] = None):
+    """-> (rgb [N,3], acc [N], saved (sigma [N,S], color [N,S,3])); rgb is not clamped (training-mode RGBRenderer).
+    head_bias [N,64]: per-ray bias of the head's first layer (`appearance_bias`), None = folded mean embedding."""
     o = _req(origins.reshape(-1, 3), torch.float32, "origins")
     d = _req(directions.reshape(-1, 3), torch.float32, "directions")
     n = o.shape[0]
@@ -129,14 +133,18 @@ def train_forward(fld: NerfactoFieldB200, origins: Tensor, directions: Tensor, b
     rgb = torch.empty((n, 3), dtype=torch.float32, device=dev)
     acc = torch.empty((n,), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(_lib.load().sgn_train_forward(fld.handle, _ptr(o), _ptr(d), n, _ptr(shared), _ptr(per_ray), S, _ptr(sigma),
-                                                 _ptr(color), _ptr(rgb), _ptr(acc), _stream(dev)))
+        hb = None if head_bias is None else _req(head_bias.reshape(n, 64), torch.float32, "head_bias")
+        _lib.check(_lib.load().sgn_train_forward(fld.handle, _ptr(o), _ptr(d), n, _ptr(shared), _ptr(per_ray), S, _ptr(hb),
+                                                 _ptr(sigma), _ptr(color), _ptr(rgb), _ptr(acc), _stream(dev)))
     return rgb, acc, (sigma, color)
 
 
 def train_backward(fld: NerfactoFieldB200, origins: Tensor, directions: Tensor, bins: Tensor, saved, grad_rgb: Tensor,
-                   grad_table: Tensor, grad_mlp: Tensor) -> None:
-    """Accumulates dL/d(hash table) into grad_table [L*T,2] and dL/d(MLP block) into grad_mlp [sgn_mlp_param_count()]."""
+                   grad_table: Tensor, grad_mlp: Tensor, grad_weights: Optional[Tensor] = None,
+                   head_bias: Optional[Tensor] = None, grad_head_bias: Optional[Tensor] = None) -> None:
+    """Accumulates dL/d(hash table) into grad_table [L*T,2] and dL/d(MLP block) into grad_mlp [sgn_mlp_param_count()];
+    grad_weights [N,S]: gradient of the terms reading the weights directly (distortion loss); head_bias / grad_head_bias
+    [N,64]: the per-ray appearance bias of the forward and where its gradient accumulates."""
     o = _req(origins.reshape(-1, 3), torch.float32, "origins")
     d = _req(directions.reshape(-1, 3), torch.float32, "directions")
     n = o.shape[0]
@@ -150,8 +158,12 @@ def train_backward(fld: NerfactoFieldB200, origins: Tensor, directions: Tensor, 
     need = int(lib.sgn_train_ws_bytes(n, S))
     ws = torch.empty(need, dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(lib.sgn_train_backward(fld.handle, _ptr(o), _ptr(d), n, _ptr(shared), _ptr(per_ray), S, _ptr(sigma), _ptr(color),
-                                          _ptr(g), _ptr(grad_table), _ptr(grad_mlp), _ptr(ws), need, _stream(dev)))
+        gw = None if grad_weights is None else _req(grad_weights.reshape(n, S), torch.float32, "grad_weights")
+        hb = None if head_bias is None else _req(head_bias.reshape(n, 64), torch.float32, "head_bias")
+        ghb = None if grad_head_bias is None else _req(grad_head_bias.reshape(n, 64), torch.float32, "grad_head_bias")
+        _lib.check(lib.sgn_train_backward(fld.handle, _ptr(o), _ptr(d), n, _ptr(shared), _ptr(per_ray), S, _ptr(hb), _ptr(sigma),
+                                          _ptr(color), _ptr(g), _ptr(gw), _ptr(grad_table), _ptr(grad_mlp), _ptr(ghb), _ptr(ws),
+                                          need, _stream(dev)))
 
 
 def rgb_loss(pred: Tensor, target: Tensor, use_l1: bool = True, want_grad: bool = True) -> Tuple[Tensor, Optional[Tensor]]:
@@ -263,3 +275,234 @@ def render_rays_train(trainer: FieldTrainer, origins: Tensor, directions: Tensor
     grad_mlp` through the CUDA backward (call `trainer.zero_grad()` before, `trainer.optimizer_step()` after)."""
     anchor = torch.zeros(1, device=trainer.field.device, requires_grad=True)     # makes the output require grad
     return _RenderRaysTrain.apply(trainer, origins, directions, bins, anchor)
+
+
+# ---------------------------------------------------------------------------------------------- proposal half of the step
+@dataclass
+class TrainSamples:
+    """One batch's sampling cascade (levels 0..2 = initial / after proposal 0 / after proposal 1)."""
+    spacing: Tuple[Tensor, Tensor, Tensor]      # [N, S_l + 1] bin edges, spacing domain
+    euclid: Tuple[Tensor, Tensor, Tensor]       # [N, S_l + 1] bin edges, metres
+    sigma: Tuple[Tensor, Tensor]                # [N, S_l] proposal densities on level l
+    weights: Tuple[Tensor, Tensor]              # [N, S_l] proposal weights on level l
+
+
+def train_sample(fld: NerfactoFieldB200, origins: Tensor, directions: Tensor, counts: Tuple[int, int, int] = (256, 96, 48),
+                 near: float = 0.05, far: float = 1000.0, jitter: Optional[Tensor] = None) -> TrainSamples:
+    """ProposalNetworkSampler.generate_ray_samples while training; jitter [3,N] uniform draws, None = eval bins."""
+    o = _req(origins.reshape(-1, 3), torch.float32, "origins")
+    d = _req(directions.reshape(-1, 3), torch.float32, "directions")
+    n, dev = o.shape[0], fld.device
+    S = tuple(int(c) for c in counts)
+    f32 = dict(dtype=torch.float32, device=dev)
+    sp = tuple(torch.empty((n, c + 1), **f32) for c in S)
+    eu = tuple(torch.empty((n, c + 1), **f32) for c in S)
+    sg = tuple(torch.empty((n, c), **f32) for c in S[:2])
+    w = tuple(torch.empty((n, c), **f32) for c in S[:2])
+    out = _lib.SgnTrainSamples()
+    for l in range(3):
+        out.d_spacing[l], out.d_euclid[l] = sp[l].data_ptr(), eu[l].data_ptr()
+    for l in range(2):
+        out.d_sigma[l], out.d_weights[l] = sg[l].data_ptr(), w[l].data_ptr()
+    j = None if jitter is None else _req(jitter.reshape(3, n), torch.float32, "jitter")
+    lib = _lib.load()
+    need = int(lib.sgn_train_sample_ws_bytes(n, S[0], S[1]))
+    ws = torch.empty(max(need, 16), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.sgn_train_sample(fld.handle, _ptr(o), _ptr(d), n, S[0], S[1], S[2], float(near), float(far), _ptr(j),
+                                        C.byref(out), _ptr(ws), need, _stream(dev)))
+    return TrainSamples(sp, eu, sg, w)
+
+
+def weights_from_density(euclid: Tensor, sigma: Tensor) -> Tensor:
+    """RaySamples.get_weights: [N,S+1] bin edges, [N,S] densities -> [N,S]."""
+    e, s = _req(euclid, torch.float32, "euclid"), _req(sigma, torch.float32, "sigma")
+    w = torch.empty_like(s)
+    with torch.cuda.device(s.device):
+        _lib.check(_lib.load().sgn_weights_from_density(_ptr(e), _ptr(s), s.shape[0], s.shape[1], _ptr(w), _stream(s.device)))
+    return w
+
+
+def interlevel_loss(spacing_final: Tensor, weights_final: Tensor, spacing_prop: Tensor, weights_prop: Tensor, loss: Tensor,
+                    mult: float = 1.0) -> Tensor:
+    """One proposal level's term of losses.py interlevel_loss: loss [1] += term, returns d term / d weights_prop [N,Sp]."""
+    n, sf, spn = weights_final.shape[0], weights_final.shape[1], weights_prop.shape[1]
+    g = torch.empty_like(weights_prop)
+    ws = torch.empty(n * (spn + 1), dtype=torch.float32, device=g.device)
+    with torch.cuda.device(g.device):
+        _lib.check(_lib.load().sgn_interlevel_loss(_ptr(_req(spacing_final, torch.float32, "spacing_final")),
+                                                   _ptr(_req(weights_final, torch.float32, "weights_final")), sf,
+                                                   _ptr(_req(spacing_prop, torch.float32, "spacing_prop")),
+                                                   _ptr(_req(weights_prop, torch.float32, "weights_prop")), spn, n, float(mult),
+                                                   _ptr(loss), _ptr(g), _ptr(ws), ws.numel() * 4, _stream(g.device)))
+    return g
+
+
+def distortion_loss(spacing: Tensor, weights: Tensor, loss: Tensor, mult: float = 0.002, want_grad: bool = True) -> Optional[Tensor]:
+    """losses.py distortion_loss on the final level: loss [1] += mult * mean, returns its gradient w.r.t. the weights."""
+    w = _req(weights, torch.float32, "weights")
+    g = torch.empty_like(w) if want_grad else None
+    with torch.cuda.device(w.device):
+        _lib.check(_lib.load().sgn_distortion_loss(_ptr(_req(spacing, torch.float32, "spacing")), _ptr(w), w.shape[0], w.shape[1],
+                                                   float(mult), _ptr(loss), _ptr(g), _stream(w.device)))
+    return g
+
+
+def prop_backward(fld: NerfactoFieldB200, level: int, origins: Tensor, directions: Tensor, euclid: Tensor, sigma: Tensor,
+                  grad_weights: Tensor, grad_table: Tensor, grad_mlp: Tensor) -> None:
+    """dL/d(weights of proposal level) -> that network's hash-table and MLP gradients (+=)."""
+    o = _req(origins.reshape(-1, 3), torch.float32, "origins")
+    d = _req(directions.reshape(-1, 3), torch.float32, "directions")
+    n, S = sigma.shape
+    ws = torch.empty(n * S, dtype=torch.float32, device=fld.device)
+    with torch.cuda.device(fld.device):
+        _lib.check(_lib.load().sgn_prop_backward(fld.handle, level, _ptr(o), _ptr(d), n, S, _ptr(_req(euclid, torch.float32, "euclid")),
+                                                 _ptr(_req(sigma, torch.float32, "sigma")),
+                                                 _ptr(_req(grad_weights, torch.float32, "grad_weights")),
+                                                 _ptr(_req(grad_table, torch.float32, "grad_table")),
+                                                 _ptr(_req(grad_mlp, torch.float32, "grad_mlp")), _ptr(ws), ws.numel() * 4,
+                                                 _stream(fld.device)))
+
+
+def appearance_bias(w_app: Tensor, bias: Tensor, embedding: Tensor, camera_indices: Tensor) -> Tensor:
+    """head_bias [N,64] = bias + W_app . embedding[camera]  (NerfactoField while training)."""
+    cam = _req(camera_indices, torch.int32, "camera_indices")
+    out = torch.empty((cam.shape[0], 64), dtype=torch.float32, device=cam.device)
+    with torch.cuda.device(cam.device):
+        _lib.check(_lib.load().sgn_appearance_bias(_ptr(_req(w_app, torch.float32, "w_app")), _ptr(_req(bias, torch.float32, "bias")),
+                                                   _ptr(_req(embedding, torch.float32, "embedding")), embedding.shape[0], _ptr(cam),
+                                                   cam.shape[0], _ptr(out), _stream(cam.device)))
+    return out
+
+
+def appearance_bias_backward(w_app: Tensor, embedding: Tensor, camera_indices: Tensor, grad_head_bias: Tensor, grad_w_app: Tensor,
+                             grad_bias: Tensor, grad_embedding: Tensor) -> None:
+    cam = _req(camera_indices, torch.int32, "camera_indices")
+    with torch.cuda.device(cam.device):
+        _lib.check(_lib.load().sgn_appearance_bias_backward(
+            _ptr(_req(w_app, torch.float32, "w_app")), _ptr(_req(embedding, torch.float32, "embedding")), embedding.shape[0],
+            _ptr(cam), _ptr(_req(grad_head_bias, torch.float32, "grad_head_bias")), cam.shape[0],
+            _ptr(_req(grad_w_app, torch.float32, "grad_w_app")), _ptr(_req(grad_bias, torch.float32, "grad_bias")),
+            _ptr(_req(grad_embedding, torch.float32, "grad_embedding")), _stream(cam.device)))
+
+
+class NerfactoTrainer(FieldTrainer):
+    """The whole training step of `SIGNeRFModel` short of LPIPS and the normal regularisers: `get_outputs` while training
+    + `get_loss_dict` (signerf/signerf.py:41-68) + Adam on `fields` and `proposal_networks` (signerf_config.py:43-50).
+    `embedding` [num_images, 32]: the per-image appearance table (SIGNeRF re-initialises it when it loads the pretrained
+    scene, signerf_pipeline.py:110-111); None trains with the folded mean embedding like `FieldTrainer`."""
+
+    def __init__(self, fld: NerfactoFieldB200, embedding: Optional[Tensor] = None, counts: Tuple[int, int, int] = (256, 96, 48),
+                 near: float = 0.05, far: float = 1000.0, interlevel_loss_mult: float = 1.0, distortion_loss_mult: float = 0.002,
+                 **kw):
+        super().__init__(fld, **kw)
+        if len(fld.prop_grids) != 2:
+            raise ValueError("NerfactoTrainer needs a field with its two proposal networks")
+        lib, dev = _lib.load(), fld.device
+        self.counts, self.near, self.far = tuple(counts), near, far
+        self.interlevel_mult, self.distortion_mult = interlevel_loss_mult, distortion_loss_mult
+        n_prop = int(lib.sgn_prop_param_count())
+        self.prop_tables = [g.table for g in fld.prop_grids]
+        self.prop_mlps = []
+        for l in range(2):
+            ptr = C.c_void_p()
+            _lib.check(lib.sgn_field_prop_params(fld.handle, l, C.byref(ptr)))
+            with torch.cuda.device(dev):
+                self.prop_mlps.append(torch.as_tensor(_DevicePtr(int(ptr.value), n_prop), device=dev))
+        self.grad_prop_tables = [torch.zeros_like(t) for t in self.prop_tables]
+        self.grad_prop_mlps = [torch.zeros(n_prop, dtype=torch.float32, device=dev) for _ in range(2)]
+        for l in range(2):
+            self.state[f"prop_table{l}"] = (torch.zeros_like(self.prop_tables[l]), torch.zeros_like(self.prop_tables[l]))
+            self.state[f"prop_mlp{l}"] = (torch.zeros(n_prop, device=dev), torch.zeros(n_prop, device=dev))
+        self.embedding = None if embedding is None else embedding.detach().to(dev, torch.float32).contiguous()
+        if self.embedding is not None:
+            self.grad_embedding = torch.zeros_like(self.embedding)
+            self.state["embedding"] = (torch.zeros_like(self.embedding), torch.zeros_like(self.embedding))
+        self.loss_dict: Dict[str, Tensor] = {}
+
+    def zero_grad(self) -> None:
+        super().zero_grad()
+        for g in self.grad_prop_tables + self.grad_prop_mlps:
+            g.zero_()
+        self.grad_w_app.zero_()
+        self.grad_b_head0.zero_()
+        if self.embedding is not None:
+            self.grad_embedding.zero_()
+
+    def forward_backward(self, origins: Tensor, directions: Tensor, target_rgb: Tensor, jitter: Optional[Tensor] = None,
+                         camera_indices: Optional[Tensor] = None,
+                         extra_loss: Optional[Callable[[Tensor], Tensor]] = None) -> Dict[str, Tensor]:
+        """Gradients of rgb_loss + interlevel_loss + distortion_loss (+ extra_loss(rgb), the LPIPS hook) into every grad_*
+        buffer; returns the loss dict (device scalars)."""
+        fld, dev = self.field, self.field.device
+        self.zero_grad()
+        smp = train_sample(fld, origins, directions, self.counts, self.near, self.far, jitter)
+        per_image = self.embedding is not None and camera_indices is not None
+        hb = appearance_bias(self.w_app, self.b_head0, self.embedding, camera_indices.to(dev, torch.int32)) if per_image else None
+        rgb, _, saved = train_forward(fld, origins, directions, smp.euclid[2], hb)
+        w_final = weights_from_density(smp.euclid[2], saved[0])
+        loss_rgb, grad_rgb = rgb_loss(rgb, target_rgb.reshape(-1, 3).to(dev), self.use_l1)
+        inter = torch.zeros(1, dtype=torch.float32, device=dev)
+        dist_l = torch.zeros(1, dtype=torch.float32, device=dev)
+        g_prop = [interlevel_loss(smp.spacing[2], w_final, smp.spacing[l], smp.weights[l], inter, self.interlevel_mult) for l in range(2)]
+        g_wf = distortion_loss(smp.spacing[2], w_final, dist_l, self.distortion_mult)
+        out = {"rgb_loss": loss_rgb, "interlevel_loss": inter, "distortion_loss": dist_l}
+        if extra_loss is not None:
+            leaf = rgb.detach().requires_grad_(True)
+            extra = extra_loss(leaf)
+            (g_extra,) = torch.autograd.grad(extra, leaf)
+            grad_rgb = grad_rgb + g_extra
+            out["lpips_loss"] = extra.detach().reshape(1)
+        ghb = torch.zeros_like(hb) if per_image else None
+        train_backward(fld, origins, directions, smp.euclid[2], saved, grad_rgb, self.grad_table, self.grad_mlp, g_wf, hb, ghb)
+        if per_image:
+            appearance_bias_backward(self.w_app, self.embedding, camera_indices.to(dev, torch.int32), ghb, self.grad_w_app,
+                                     self.grad_b_head0, self.grad_embedding)
+        for l in range(2):
+            prop_backward(fld, l, origins, directions, smp.euclid[l], smp.sigma[l], g_prop[l], self.grad_prop_tables[l],
+                          self.grad_prop_mlps[l])
+        self._per_image = per_image
+        self.loss_dict = out
+        return out
+
+    def all_gradients(self):
+        """Every gradient buffer of the step (for a data-parallel all-reduce)."""
+        g = [self.grad_table, self.grad_mlp, self.grad_w_app, self.grad_b_head0] + self.grad_prop_tables + self.grad_prop_mlps
+        return g + ([self.grad_embedding] if self.embedding is not None else [])
+
+    def optimizer_step(self) -> None:
+        lib, dev = _lib.load(), self.field.device
+        if getattr(self, "_per_image", False):
+            # per-image embeddings: W_app / b / E got their own gradients; the block's (folded) b_head0 slot is not a
+            # parameter of this mode - it is rewritten from the mean embedding for the eval renderer below
+            self.steps += 1
+            mlp_block_views(self.grad_mlp)["b_head0"].zero_()
+            todo = [("table", self.table, self.grad_table, self.table.numel()), ("mlp", self.mlp, self.grad_mlp, self.trainable),
+                    ("w_app", self.w_app, self.grad_w_app, self.w_app.numel()),
+                    ("b_head0", self.b_head0, self.grad_b_head0, self.b_head0.numel()),
+                    ("embedding", self.embedding, self.grad_embedding, self.embedding.numel())]
+            with torch.cuda.device(dev):
+                for key, param, grad, n in todo:
+                    m, v = self.state[key]
+                    _lib.check(lib.sgn_adam_step(_ptr(param), _ptr(grad), _ptr(m), _ptr(v), n, self.lr, self.betas[0],
+                                                 self.betas[1], self.eps, self.steps, _stream(dev)))
+            self.app_mean = self.embedding.mean(dim=0)
+            mlp_block_views(self.mlp)["b_head0"].copy_(self.b_head0 + self.w_app @ self.app_mean)
+        else:
+            super().optimizer_step()
+        with torch.cuda.device(dev):
+            for l in range(2):
+                for key, param, grad in ((f"prop_table{l}", self.prop_tables[l], self.grad_prop_tables[l]),
+                                         (f"prop_mlp{l}", self.prop_mlps[l], self.grad_prop_mlps[l])):
+                    m, v = self.state[key]
+                    _lib.check(lib.sgn_adam_step(_ptr(param), _ptr(grad), _ptr(m), _ptr(v), param.numel(), self.lr, self.betas[0],
+                                                 self.betas[1], self.eps, self.steps, _stream(dev)))
+
+    def train_step(self, origins: Tensor, directions: Tensor, target_rgb: Tensor, jitter: Optional[Tensor] = None,
+                   camera_indices: Optional[Tensor] = None, extra_loss: Optional[Callable[[Tensor], Tensor]] = None) -> Dict[str, Tensor]:
+        """forward + losses + backward + Adam; jitter None draws the three per-ray uniforms on the device."""
+        if jitter is None:
+            jitter = torch.rand((3, origins.reshape(-1, 3).shape[0]), device=self.field.device)
+        out = self.forward_backward(origins, directions, target_rgb, jitter, camera_indices, extra_loss)
+        self.optimizer_step()
+        return out

@@ -149,3 +149,114 @@ def test_adam_steps_match_torch_and_reduce_the_loss():
     with torch.no_grad():
         ref_after = R.render_rays_train(m, o, d, S).clamp(0, 1)
     assert rel_l2(after, ref_after) < 2e-3        # fp16 tensor-core renderer on the UPDATED weights vs the updated oracle
+
+
+# ---------------------------------------------------------------------------------------------- the whole nerfacto step
+def _setup_full(n_rays=160, counts=(64, 32, 16), seed=3):
+    from tests.helpers import field_from_oracle, ring_cameras
+    m = R.make_model(seed, dense=True, table_scale=0.5, density_gain=20.0, log2_hashmap_size=14,
+                     num_proposal_samples=counts[:2], num_nerf_samples=counts[2])
+    m.train()
+    fld = field_from_oracle(m, with_proposals=True)
+    c2w, intr = ring_cameras(4, 32, 24)
+    rays = [R.generate_rays(c2w[v], *intr[v].tolist(), 32, 24) for v in range(4)]
+    g = torch.Generator().manual_seed(seed)
+    pick = torch.randperm(4 * 32 * 24, generator=g)[:n_rays]
+    o = torch.cat([r.origins for r in rays])[pick].contiguous()
+    d = torch.cat([r.directions for r in rays])[pick].contiguous()
+    target = torch.rand(n_rays, 3, generator=g)
+    jitter = torch.rand(3, n_rays, generator=g)
+    cams = torch.randint(0, 30, (n_rays,), generator=g)
+    return m, fld, o, d, target, jitter, cams
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("jittered", [True, False])
+def test_training_sampler_matches_oracle(jittered):
+    """ProposalNetworkSampler while training (stratified initial bins, jittered PDF re-sampling on the same draws) and in
+    its eval form: bin edges of all three levels and both proposal weight sets."""
+    m, fld, o, d, _, jitter, _ = _setup_full(counts=(256, 96, 48))
+    with torch.no_grad():
+        ref = R.forward_train(m, o, d, jitter if jittered else None)
+    smp = T.train_sample(fld, o.cuda(), d.cuda(), (256, 96, 48), m.near, m.far, jitter.cuda() if jittered else None)
+    for l in range(3):
+        sp_ref = R.sdist_of(ref["samples_list"][l])
+        assert rel_l2(smp.spacing[l], sp_ref) < 1e-5, l
+        assert float((smp.spacing[l].cpu() - sp_ref).abs().max()) < 2e-4, l
+    assert torch.equal(smp.spacing[0].cpu(), R.sdist_of(ref["samples_list"][0]))        # level 0 is arithmetic on the draws only
+    for l in range(2):
+        assert rel_l2(smp.weights[l], ref["weights_list"][l][..., 0]) < 1e-4, l
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("per_image", [True, False])
+def test_full_step_losses_and_gradients_match_autograd(per_image):
+    """get_outputs while training + get_loss_dict (signerf.py:41-68 without LPIPS / normals): rgb, interlevel and distortion
+    losses and the gradient of their sum with respect to EVERY trained tensor - main field, both proposal networks, the
+    appearance embedding - against torch autograd through the oracle on the same draws."""
+    m, fld, o, d, target, jitter, cams = _setup_full()
+    tr = T.NerfactoTrainer(fld, embedding=m.field.embedding_appearance.weight if per_image else None, counts=(64, 32, 16),
+                           near=m.near, far=m.far)
+    ours = tr.forward_backward(o.cuda(), d.cuda(), target.cuda(), jitter.cuda(), cams.cuda() if per_image else None)
+    torch.cuda.synchronize()
+    # The oracle differentiates on OUR bins (the samplers carry no gradient and are compared in the test above): an fp32
+    # rounding difference of a bin edge would move samples across cells of the finest hash levels.
+    smp = T.train_sample(fld, o.cuda(), d.cuda(), (64, 32, 16), m.near, m.far, jitter.cuda())
+    fixed = [R.samples_from_edges(smp.spacing[l].cpu(), smp.euclid[l].cpu()) for l in range(3)]
+    out = R.forward_train(m, o, d, jitter, cams if per_image else None, fixed_samples=fixed)
+    ld = R.signerf_loss_dict(out, target)
+    sum(ld.values()).backward()
+    for k in ("rgb_loss", "interlevel_loss", "distortion_loss"):
+        a, b = float(ours[k]), float(ld[k].detach())
+        assert abs(a - b) < 1e-4 * max(abs(b), 1e-3), (k, a, b)
+    f = m.field
+    app_mean = f.embedding_appearance.weight.detach().mean(dim=0)
+    g = T.nerfstudio_gradients(tr.grad_table, tr.grad_mlp, app_mean)
+    ref = {"field.mlp_base.encoding.hash_table": f.encoding.hash_table.grad}
+    for i, l in enumerate(f.mlp_base.layers):
+        ref[f"field.mlp_base.mlp.layers.{i}.weight"], ref[f"field.mlp_base.mlp.layers.{i}.bias"] = l.weight.grad, l.bias.grad
+    for i, l in enumerate(f.mlp_head.layers):
+        ref[f"field.mlp_head.layers.{i}.weight"], ref[f"field.mlp_head.layers.{i}.bias"] = l.weight.grad, l.bias.grad
+    if per_image:                     # the appearance columns / bias / table have their own buffers in this mode
+        h0 = f.mlp_head.layers[0]
+        g["field.mlp_head.layers.0.weight"] = torch.cat([g["field.mlp_head.layers.0.weight"][:, :31], tr.grad_w_app], dim=1)
+        g["field.mlp_head.layers.0.bias"] = tr.grad_b_head0
+        g["field.embedding_appearance.weight"] = tr.grad_embedding
+        ref["field.embedding_appearance.weight"] = f.embedding_appearance.weight.grad
+        assert float(h0.weight.grad[:, 31:].abs().max()) > 0
+    errs = {k: rel_l2(g[k], ref[k]) for k in ref}
+    for l, p in enumerate(m.proposal_networks):
+        v = tr.grad_prop_mlps[l]
+        errs[f"prop{l}.table"] = rel_l2(tr.grad_prop_tables[l], p.encoding.hash_table.grad)
+        errs[f"prop{l}.w0"] = rel_l2(v[:160].view(16, 10), p.mlp.layers[0].weight.grad)
+        errs[f"prop{l}.b0"] = rel_l2(v[160:176], p.mlp.layers[0].bias.grad)
+        errs[f"prop{l}.w1"] = rel_l2(v[176:192].view(1, 16), p.mlp.layers[1].weight.grad)
+        errs[f"prop{l}.b1"] = rel_l2(v[192:193], p.mlp.layers[1].bias.grad)
+        assert float(p.encoding.hash_table.grad.abs().max()) > 0
+    print("gradient rel-L2:", {k.replace("field.", ""): f"{v:.1e}" for k, v in errs.items()})
+    assert max(errs.values()) < 1e-3, errs
+
+
+@pytest.mark.gpu
+def test_full_training_steps_reduce_the_losses_and_move_every_group():
+    """Five whole steps (sampler, three losses, both backward passes, Adam on fields + proposal_networks + embedding):
+    the summed loss goes down, every parameter group moves, and the eval cascade renders with the updated networks."""
+    from signerf_b200 import ops
+    m, fld, o, d, target, jitter, cams = _setup_full(n_rays=256)
+    tr = T.NerfactoTrainer(fld, embedding=m.field.embedding_appearance.weight, counts=(64, 32, 16), near=m.near, far=m.far)
+    before = [t.clone() for t in (tr.table, tr.mlp, tr.prop_tables[0], tr.prop_mlps[1], tr.embedding, tr.w_app)]
+    oc, dc, tc, jc, cc = o.cuda(), d.cuda(), target.cuda(), jitter.cuda(), cams.cuda()
+    opts = ops.RenderOptions(mode="cascade", num_samples=16, num_prop_samples=(64, 32))
+    rgb0 = ops.render_rays(fld, oc, dc, opts)[0].clone()
+    totals, rows = [], []
+    for _ in range(12):
+        out = tr.train_step(oc, dc, tc, jc, cc)
+        rows.append({k: round(float(v), 5) for k, v in out.items()})
+        totals.append(sum(float(v) for v in out.values()))
+    print("loss dicts:", rows[0], rows[-1], [round(t, 4) for t in totals])
+    assert min(totals[-3:]) < totals[0], totals
+    after = (tr.table, tr.mlp, tr.prop_tables[0], tr.prop_mlps[1], tr.embedding, tr.w_app)
+    assert all(not torch.equal(a, b) for a, b in zip(after, before))
+    tr.refresh_renderer()
+    rgb1 = ops.render_rays(fld, oc, dc, opts)[0]
+    assert not torch.equal(rgb0, rgb1) and bool(torch.isfinite(rgb1).all())
