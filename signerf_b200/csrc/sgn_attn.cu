@@ -110,6 +110,9 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
 
 // make -C signerf_b200/csrc trace: clock64 time stamps of CTA 0 (lane 0 of the first warp of softmax groups 0 / 1 and
 // the issuer), read back by scratch/attn_trace.py through sgn_debug_attn_trace
+#ifndef SGN_ATTN_PROBE
+#define SGN_ATTN_PROBE 0
+#endif
 #ifdef SGN_ATTN_TRACE
 __device__ long long g_trace[32 * 256];   // [event + 16 * query tile][key tile]
 #define TRACE(ev, j) do { if (blockIdx.x == 0 && (j) < 256 && (ev) < 32) g_trace[(ev) * 256 + (j)] = clock64(); } while (0)
@@ -411,8 +414,14 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       tc::tc_fence_after();
       if (tr) TRACE(te + 1, j);
       uint32_t s[kKv];
+#if SGN_ATTN_PROBE & 32   // probe 32: only a quarter of the S row is read from tensor memory
+      tc::tmem_ld32(ts, s);
+#pragma unroll
+      for (int c = 32; c < kKv; ++c) s[c] = s[c & 31] + c;
+#else
 #pragma unroll
       for (int c = 0; c < kKv / 32; ++c) tc::tmem_ld32(ts + c * 32, s + c * 32);
+#endif
       tc::tmem_ld_wait();
       tc::tc_fence_before();
       __syncwarp();
@@ -425,8 +434,13 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
       float mx0 = __uint_as_float(s[0]), mx1 = __uint_as_float(s[1]);
       float mx2 = __uint_as_float(s[2]), mx3 = __uint_as_float(s[3]);
+#if SGN_ATTN_PROBE & 4   // probe 4: the maximum of every 8th key only
+#pragma unroll
+      for (int q = 4; q < kKv - 4; q += 64) {
+#else
 #pragma unroll
       for (int q = 4; q < kKv - 4; q += 8) {
+#endif
         mx0 = max3(mx0, __uint_as_float(s[q]), __uint_as_float(s[q + 1]));
         mx1 = max3(mx1, __uint_as_float(s[q + 2]), __uint_as_float(s[q + 3]));
         mx2 = max3(mx2, __uint_as_float(s[q + 4]), __uint_as_float(s[q + 5]));
@@ -479,9 +493,13 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       auto exp_block = [&](int b) {
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
+#if SGN_ATTN_PROBE & 1   // timing probe (wrong results): no scale / shift in front of the exponential
+          float t0 = __uint_as_float(s[b * 16 + 2 * q]), t1 = __uint_as_float(s[b * 16 + 2 * q + 1]);
+#else
           const uint64_t t = fma2(pk2u(s[b * 16 + 2 * q], s[b * 16 + 2 * q + 1]), sc2, nm2);
           float t0, t1;
           upk2(t, t0, t1);
+#endif
           s[b * 16 + 2 * q] = __float_as_uint(ex2(t0));
           s[b * 16 + 2 * q + 1] = __float_as_uint(ex2(t1));
         }
@@ -491,20 +509,31 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
       for (int b = 0; b < kKv / 16; ++b) {
         if (b + 1 < kKv / 16) exp_block(b + 1);
+#if !(SGN_ATTN_PROBE & 2)   // probe 2: no row sum
 #pragma unroll
         for (int q = 0; q < 8; q += 2) {
           acc_a = add2(acc_a, pk2u(s[b * 16 + 2 * q], s[b * 16 + 2 * q + 1]));
           acc_b = add2(acc_b, pk2u(s[b * 16 + 2 * q + 2], s[b * 16 + 2 * q + 3]));
         }
+#endif
         const float* e = reinterpret_cast<const float*>(s) + b * 16;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
+#if SGN_ATTN_PROBE & 16   // probe 16: no fp32 -> fp16 pack
+          pk[(b & 3) * 8 + q] = s[b * 16 + 2 * q] ^ s[b * 16 + 2 * q + 1];
+#else
           __half2 h = __floats2half2_rn(e[2 * q], e[2 * q + 1]);
           pk[(b & 3) * 8 + q] = *reinterpret_cast<uint32_t*>(&h);
+#endif
         }
         if ((b & 3) == 3) {
           wait_o();
+#if SGN_ATTN_PROBE & 8    // probe 8: P is not stored (one column keeps the registers alive)
+          tc::tmem_st16(tp + (b >> 2) * 32, pk);
+          asm volatile("" ::"r"(pk[16] ^ pk[17] ^ pk[18] ^ pk[19] ^ pk[20] ^ pk[21] ^ pk[22] ^ pk[23] ^ pk[24] ^ pk[25] ^ pk[26] ^ pk[27] ^ pk[28] ^ pk[29] ^ pk[30] ^ pk[31]));
+#else
           tc::tmem_st32(tp + (b >> 2) * 32, pk);
+#endif
         } else if (b == kKv / 16 - 1) {   // 96 keys: the last two blocks are 16 packed columns
           static_assert((kKv / 16) % 4 == 0 || (kKv / 16) % 4 == 2, "P store granularity");
           tc::tmem_st16(tp + (b >> 2) * 32, pk);
