@@ -178,6 +178,50 @@ __device__ __forceinline__ void corner_rows(const LevelCoords& L, uint32_t mask,
   idx[7] = (L.xf ^ L.yc ^ L.zf) & mask;
 }
 
+// Hash-table gradient of one level, scatter-add with the lanes of a warp merged first.  Consecutive lanes hold
+// consecutive samples of a ray; at the coarse levels (and wherever the PDF sampler concentrates samples) whole runs of them
+// sit in the same cell, i.e. hit the same eight rows.  Runs of equal cells are summed with a segmented shuffle reduction and
+// only the first lane of a run issues the eight vector atomics (a coarse level otherwise takes millions of atomics on a
+// few thousand addresses).  Must be called by all 32 lanes; lanes without work pass g0 = g1 = 0.
+__device__ __forceinline__ void scatter_level_merged(float2* __restrict__ gt, const LevelCoords& L, uint32_t mask, float g0,
+                                                     float g1, int lane) {
+  const unsigned full = 0xffffffffu;
+  bool same = true;   // same cell as the previous lane: the six corner coordinates agree (the primes are odd: bijective)
+  same &= __shfl_up_sync(full, L.xf, 1) == L.xf;
+  same &= __shfl_up_sync(full, L.yf, 1) == L.yf;
+  same &= __shfl_up_sync(full, L.zf, 1) == L.zf;
+  same &= __shfl_up_sync(full, L.xc, 1) == L.xc;
+  same &= __shfl_up_sync(full, L.yc, 1) == L.yc;
+  same &= __shfl_up_sync(full, L.zc, 1) == L.zc;
+  const bool head = lane == 0 || !same;
+  const unsigned heads = __ballot_sync(full, head);
+  const unsigned after = lane == 31 ? 0u : heads & ~((2u << lane) - 1u);
+  const int end = after ? __ffs(after) - 1 : 32;   // first lane of the next run
+  const float mx = 1.f - L.ox, my = 1.f - L.oy, mz = 1.f - L.oz;
+  // corner order of HashEncoding.pytorch_fwd: 0 ccc, 1 cfc, 2 ffc, 3 fcc, 4 ccf, 5 cff, 6 fff, 7 fcf (x, y, z)
+  const float wt[8] = {L.ox * L.oy * L.oz, L.ox * my * L.oz, mx * my * L.oz, mx * L.oy * L.oz,
+                       L.ox * L.oy * mz,   L.ox * my * mz,   mx * my * mz,   mx * L.oy * mz};
+  float vx[8], vy[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) vx[c] = wt[c] * g0, vy[c] = wt[c] * g1;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const bool take = lane + o < end;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float ux = __shfl_down_sync(full, vx[c], o), uy = __shfl_down_sync(full, vy[c], o);
+      if (take) vx[c] += ux, vy[c] += uy;
+    }
+  }
+  if (head) {
+    uint32_t idx[8];
+    corner_rows(L, mask, idx);
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (vx[c] != 0.f || vy[c] != 0.f) atomicAdd(gt + idx[c], make_float2(vx[c], vy[c]));
+  }
+}
+
 __device__ __forceinline__ float2 lerp2(float2 a, float wa, float2 b, float wb) {
   return make_float2(fmaf(a.x, wa, b.x * wb), fmaf(a.y, wa, b.y * wb));
 }

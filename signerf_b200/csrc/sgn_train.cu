@@ -160,6 +160,28 @@ __global__ void k_train_ray_bwd(const TrainRays r, const float* __restrict__ sig
 }
 
 // ---------------------------------------------------------------- backward, sample level
+// sum_k wrow[k] * x[k]: x in registers, wrow a 16-byte aligned row of the shared-memory weights (four per load)
+template <int K>
+__device__ __forceinline__ float dot_row(const float* __restrict__ wrow, const float (&x)[K]) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+  for (int k = 0; k < K; k += 4) {
+    const float4 w4 = *reinterpret_cast<const float4*>(wrow + k);
+    a0 = fmaf(w4.x, x[k], a0), a1 = fmaf(w4.y, x[k + 1], a1), a2 = fmaf(w4.z, x[k + 2], a2), a3 = fmaf(w4.w, x[k + 3], a3);
+  }
+  return (a0 + a1) + (a2 + a3);
+}
+// acc[k] += wrow[k] * v
+template <int K>
+__device__ __forceinline__ void axpy_row(const float* __restrict__ wrow, float v, float (&acc)[K]) {
+#pragma unroll
+  for (int k = 0; k < K; k += 4) {
+    const float4 w4 = *reinterpret_cast<const float4*>(wrow + k);
+    acc[k] = fmaf(w4.x, v, acc[k]), acc[k + 1] = fmaf(w4.y, v, acc[k + 1]);
+    acc[k + 2] = fmaf(w4.z, v, acc[k + 2]), acc[k + 3] = fmaf(w4.w, v, acc[k + 3]);
+  }
+}
+
 struct FieldBwd {
   GridDev grid;
   const MlpF32* w32;
@@ -173,14 +195,23 @@ struct FieldBwd {
   int64_t cap;            // row length of deltas / acts
 };
 
-__global__ void __launch_bounds__(128) k_train_field_bwd(const __grid_constant__ FieldBwd p) {
+__global__ void __launch_bounds__(128, 3) k_train_field_bwd(const __grid_constant__ FieldBwd p) {
   extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ float s_fgrad[32 * 128];   // [feature][thread]: d loss / d hash features, read back by the rolled level loop
   MlpF32* w = reinterpret_cast<MlpF32*>(smem);
   for (int i = threadIdx.x; i < (int)(sizeof(MlpF32) / 16); i += blockDim.x)
     reinterpret_cast<uint4*>(w)[i] = reinterpret_cast<const uint4*>(p.w32)[i];
   __syncthreads();
   const TrainRays& r = p.rays;
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < p.count; e += (int64_t)gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  // every lane of a warp runs the same number of iterations (the scatter-add below merges lanes with shuffles); lanes
+  // past the end redo the last sample with zero gradients
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t iters = (p.count + stride - 1) / stride;
+  for (int64_t it = 0; it < iters; ++it) {
+    const int64_t e_raw = it * stride + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const bool live = e_raw < p.count;
+    const int64_t e = live ? e_raw : p.count - 1;
     const int64_t s = p.first + e;
     const int64_t ray = s / r.S;
     const int i = (int)(s - ray * r.S);
@@ -190,7 +221,11 @@ __global__ void __launch_bounds__(128) k_train_field_bwd(const __grid_constant__
     float px, py, pz, sh[16];
     const bool sel = sample_position(r, ray, i, px, py, pz);
     sh16(__ldg(r.dirs + 3 * ray), __ldg(r.dirs + 3 * ray + 1), __ldg(r.dirs + 3 * ray + 2), sh);
-    // ---- forward with the activations written to A (they are read back below: L1 / L2 resident)
+    // Layer arithmetic: the input vector of a layer sits in registers (x32 / x64, statically indexed), the weights come
+    // out of shared memory four at a time (one LDS.128 per four FMAs, the same address for the whole warp), the outputs
+    // go to the activation / delta slabs (k_outer_reduce reads them) and are read back as the next layer's registers.
+    // Transposed products (delta through W^T) run in accumulate form: acc[k] += W[n][k] * delta_n over a runtime n.
+    float x32[32], x64[64];
     float* feat = col(p.acts, 0);
     float* h0 = col(p.acts, 32);
     float* hin = col(p.acts, 96);
@@ -199,37 +234,40 @@ __global__ void __launch_bounds__(128) k_train_field_bwd(const __grid_constant__
 #pragma unroll
     for (int l = 0; l < 16; ++l) {
       float2 f = encode_level(p.grid.table + (size_t)l * p.grid.size, p.grid.mask, p.grid.res[l], px, py, pz);
+      x32[2 * l] = f.x, x32[2 * l + 1] = f.y;
       SGN_AT(feat, 2 * l) = f.x;
       SGN_AT(feat, 2 * l + 1) = f.y;
     }
-    for (int n = 0; n < 64; ++n) {
-      float a = w->b_base0[n];
-      for (int k = 0; k < 32; ++k) a = fmaf(w->w_base0[n * 32 + k], SGN_AT(feat, k), a);
-      SGN_AT(h0, n) = fmaxf(a, 0.f);
-    }
-    for (int k = 0; k < 16; ++k) SGN_AT(hin, k) = sh[k];
+#pragma unroll 2
+    for (int n = 0; n < 64; ++n) SGN_AT(h0, n) = fmaxf(w->b_base0[n] + dot_row<32>(w->w_base0 + n * 32, x32), 0.f);
+#pragma unroll
+    for (int k = 0; k < 64; ++k) x64[k] = SGN_AT(h0, k);
     float logit = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) x32[k] = sh[k];
+#pragma unroll
     for (int n = 0; n < 16; ++n) {
-      float a = w->b_base1[n];
-      for (int k = 0; k < 64; ++k) a = fmaf(w->w_base1[n * 64 + k], SGN_AT(h0, k), a);
+      const float a = w->b_base1[n] + dot_row<64>(w->w_base1 + n * 64, x64);
       if (n == 0) logit = a;
-      SGN_AT(hin, 16 + n) = n == 0 ? 0.f : a;
+      x32[16 + n] = n == 0 ? 0.f : a;
     }
+#pragma unroll
+    for (int k = 0; k < 32; ++k) SGN_AT(hin, k) = x32[k];
+#pragma unroll 2
     for (int n = 0; n < 64; ++n) {
-      float a = r.head_bias ? __ldg(r.head_bias + 64 * ray + n) : w->b_head0[n];
-      for (int k = 0; k < 32; ++k) a = fmaf(w->w_head0[n * 32 + k], SGN_AT(hin, k), a);
-      SGN_AT(h1, n) = fmaxf(a, 0.f);
+      const float b = r.head_bias ? __ldg(r.head_bias + 64 * ray + n) : w->b_head0[n];
+      SGN_AT(h1, n) = fmaxf(b + dot_row<32>(w->w_head0 + n * 32, x32), 0.f);
     }
-    for (int n = 0; n < 64; ++n) {
-      float a = w->b_head1[n];
-      for (int k = 0; k < 64; ++k) a = fmaf(w->w_head1[n * 64 + k], SGN_AT(h1, k), a);
-      SGN_AT(h2, n) = fmaxf(a, 0.f);
-    }
+#pragma unroll
+    for (int k = 0; k < 64; ++k) x64[k] = SGN_AT(h1, k);
+#pragma unroll 1
+    for (int n = 0; n < 64; ++n) SGN_AT(h2, n) = fmaxf(w->b_head1[n] + dot_row<64>(w->w_head1 + n * 64, x64), 0.f);
+#pragma unroll
+    for (int k = 0; k < 64; ++k) x64[k] = SGN_AT(h2, k);
     float dpre[3];
+#pragma unroll
     for (int c = 0; c < 3; ++c) {
-      float a = w->b_head2[c];
-      for (int k = 0; k < 64; ++k) a = fmaf(w->w_head2[c * 64 + k], SGN_AT(h2, k), a);
-      const float cl = sigmoidf_(a);
+      const float cl = sigmoidf_(w->b_head2[c] + dot_row<64>(w->w_head2 + c * 64, x64));
       dpre[c] = p.gcolor[3 * s + c] * cl * (1.f - cl);
     }
     // ---- backward
@@ -239,46 +277,63 @@ __global__ void __launch_bounds__(128) k_train_field_bwd(const __grid_constant__
     float* da2 = col(p.deltas, 144);
     float* dp = col(p.deltas, 208);
     SGN_AT(dp, 0) = dpre[0]; SGN_AT(dp, 1) = dpre[1]; SGN_AT(dp, 2) = dpre[2]; SGN_AT(dp, 3) = 0.f;
-    for (int k = 0; k < 64; ++k) {
+#pragma unroll
+    for (int k = 0; k < 64; ++k) {   // x64 = h2 -> da2 (stored for the n-loop below and for k_outer_reduce)
       const float g = w->w_head2[k] * dpre[0] + w->w_head2[64 + k] * dpre[1] + w->w_head2[128 + k] * dpre[2];
-      SGN_AT(da2, k) = SGN_AT(h2, k) > 0.f ? g : 0.f;
+      SGN_AT(da2, k) = x64[k] > 0.f ? g : 0.f;
     }
-    for (int k = 0; k < 64; ++k) {
-      float g = 0.f;
-      for (int n = 0; n < 64; ++n) g = fmaf(w->w_head1[n * 64 + k], SGN_AT(da2, n), g);
-      SGN_AT(da1, k) = SGN_AT(h1, k) > 0.f ? g : 0.f;
+#pragma unroll
+    for (int k = 0; k < 64; ++k) x64[k] = 0.f;
+#pragma unroll 1
+    for (int n = 0; n < 64; n += 4) {   // the four scalars of a trip are in flight together
+      const float v0 = SGN_AT(da2, n), v1 = SGN_AT(da2, n + 1), v2 = SGN_AT(da2, n + 2), v3 = SGN_AT(da2, n + 3);
+      axpy_row<64>(w->w_head1 + n * 64, v0, x64);
+      axpy_row<64>(w->w_head1 + n * 64 + 64, v1, x64);
+      axpy_row<64>(w->w_head1 + n * 64 + 128, v2, x64);
+      axpy_row<64>(w->w_head1 + n * 64 + 192, v3, x64);
     }
+#pragma unroll
+    for (int k = 0; k < 64; ++k) SGN_AT(da1, k) = SGN_AT(h1, k) > 0.f ? x64[k] : 0.f;
     // trunc_exp backward: d exp(x) = exp(clamp(x, max = 15)); the selector multiplies the density only
-    SGN_AT(dout1, 0) = sel ? p.gsigma[s] * w->avg_density * expf(fminf(logit, 15.f)) : 0.f;
-    for (int n = 1; n < 16; ++n) {
-      float g = 0.f;
-      for (int m = 0; m < 64; ++m) g = fmaf(w->w_head0[m * 32 + 16 + n], SGN_AT(da1, m), g);
-      SGN_AT(dout1, n) = g;
+    float d16[16];
+#pragma unroll
+    for (int n = 0; n < 16; ++n) d16[n] = 0.f;
+#pragma unroll 1
+    for (int m = 0; m < 64; m += 4) {
+      const float v0 = SGN_AT(da1, m), v1 = SGN_AT(da1, m + 1), v2 = SGN_AT(da1, m + 2), v3 = SGN_AT(da1, m + 3);
+      axpy_row<16>(w->w_head0 + m * 32 + 16, v0, d16);
+      axpy_row<16>(w->w_head0 + m * 32 + 48, v1, d16);
+      axpy_row<16>(w->w_head0 + m * 32 + 80, v2, d16);
+      axpy_row<16>(w->w_head0 + m * 32 + 112, v3, d16);
     }
-    for (int k = 0; k < 64; ++k) {
-      float g = 0.f;
-      for (int n = 0; n < 16; ++n) g = fmaf(w->w_base1[n * 64 + k], SGN_AT(dout1, n), g);
-      SGN_AT(da0, k) = SGN_AT(h0, k) > 0.f ? g : 0.f;
+    d16[0] = sel ? p.gsigma[s] * w->avg_density * expf(fminf(logit, 15.f)) : 0.f;
+#pragma unroll
+    for (int n = 0; n < 16; ++n) SGN_AT(dout1, n) = d16[n];
+#pragma unroll
+    for (int k = 0; k < 64; ++k) x64[k] = 0.f;
+#pragma unroll
+    for (int n = 0; n < 16; ++n) axpy_row<64>(w->w_base1 + n * 64, d16[n], x64);
+#pragma unroll
+    for (int k = 0; k < 64; ++k) SGN_AT(da0, k) = SGN_AT(h0, k) > 0.f ? x64[k] : 0.f;
+    // ---- hash features: d feat = W_base0^T da0, then the scatter-add into the table gradient
+#pragma unroll
+    for (int k = 0; k < 32; ++k) x32[k] = 0.f;
+#pragma unroll 1
+    for (int n = 0; n < 64; n += 4) {
+      const float v0 = SGN_AT(da0, n), v1 = SGN_AT(da0, n + 1), v2 = SGN_AT(da0, n + 2), v3 = SGN_AT(da0, n + 3);
+      axpy_row<32>(w->w_base0 + n * 32, v0, x32);
+      axpy_row<32>(w->w_base0 + n * 32 + 32, v1, x32);
+      axpy_row<32>(w->w_base0 + n * 32 + 64, v2, x32);
+      axpy_row<32>(w->w_base0 + n * 32 + 96, v3, x32);
     }
-    // ---- hash features: scatter-add into the table gradient
+    // the level loop stays rolled (its body is long): the 32 feature gradients go through a shared-memory column
+#pragma unroll
+    for (int k = 0; k < 32; ++k) s_fgrad[k * 128 + threadIdx.x] = live ? x32[k] : 0.f;
 #pragma unroll 1
     for (int l = 0; l < 16; ++l) {
-      float g0 = 0.f, g1 = 0.f;
-      for (int n = 0; n < 64; ++n) {
-        const float dn = SGN_AT(da0, n);
-        g0 = fmaf(w->w_base0[n * 32 + 2 * l], dn, g0);
-        g1 = fmaf(w->w_base0[n * 32 + 2 * l + 1], dn, g1);
-      }
       const LevelCoords L = level_coords(p.grid.res[l], px, py, pz);
-      uint32_t idx[8];
-      corner_rows(L, p.grid.mask, idx);
-      const float mx = 1.f - L.ox, my = 1.f - L.oy, mz = 1.f - L.oz;
-      // corner order of HashEncoding.pytorch_fwd: 0 ccc, 1 cfc, 2 ffc, 3 fcc, 4 ccf, 5 cff, 6 fff, 7 fcf (x, y, z)
-      const float wt[8] = {L.ox * L.oy * L.oz, L.ox * my * L.oz, mx * my * L.oz, mx * L.oy * L.oz,
-                           L.ox * L.oy * mz,   L.ox * my * mz,   mx * my * mz,   mx * L.oy * mz};
       float2* gt = reinterpret_cast<float2*>(p.grad_table) + (size_t)l * p.grid.size;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) atomicAdd(gt + idx[c], make_float2(wt[c] * g0, wt[c] * g1));
+      scatter_level_merged(gt, L, p.grid.mask, s_fgrad[(2 * l) * 128 + threadIdx.x], s_fgrad[(2 * l + 1) * 128 + threadIdx.x], lane);
     }
 #undef SGN_AT
   }
@@ -352,11 +407,23 @@ __global__ void __launch_bounds__(256) k_appearance_bwd(const float* __restrict_
 
 // dW[n][k] += sum_s D[s][doff + n] * A[s][aoff + k]  (n < N <= 64, k < K <= 64);  db[n] += sum_s D[s][doff + n]
 // 256 threads own a 64 x 64 register tile (4 x 4 each); samples are staged 32 at a time through shared memory.
-__global__ void __launch_bounds__(256) k_outer_reduce(const float* __restrict__ D, int doff, int N, const float* __restrict__ A,
-                                                      int aoff, int K, int64_t count, int64_t cap, int ldw,
-                                                      float* __restrict__ dW, float* __restrict__ db, int per_cta) {
-  __shared__ float sD[32][64 + 1];
-  __shared__ float sA[32][64 + 1];
+struct OuterLayer {
+  int doff, N, aoff, K, ldw;
+  float* dW;
+  float* db;
+};
+struct OuterParams {
+  OuterLayer layer[5];   // blockIdx.y
+};
+__global__ void __launch_bounds__(256) k_outer_reduce(const float* __restrict__ D, const float* __restrict__ A,
+                                                      const __grid_constant__ OuterParams op, int64_t count, int64_t cap,
+                                                      int per_cta) {
+  const OuterLayer& ly = op.layer[blockIdx.y];
+  const int doff = ly.doff, N = ly.N, aoff = ly.aoff, K = ly.K, ldw = ly.ldw;
+  float* __restrict__ dW = ly.dW;
+  float* __restrict__ db = ly.db;
+  __shared__ __align__(16) float sD[32][64 + 4];   // row pitch 68 floats: 16-byte aligned rows for the float4 reads below
+  __shared__ __align__(16) float sA[32][64 + 4];
   const int tn = (threadIdx.x >> 4) * 4, tk = (threadIdx.x & 15) * 4;
   float acc[4][4] = {};
   float bacc = 0.f;   // thread t < 64 sums column t of D
@@ -369,14 +436,10 @@ __global__ void __launch_bounds__(256) k_outer_reduce(const float* __restrict__ 
       sA[rr][cc] = (rr < rows && cc < K) ? A[(size_t)(aoff + cc) * cap + base + rr] : 0.f;
     }
     __syncthreads();
-#pragma unroll 4
+#pragma unroll 8
     for (int rr = 0; rr < 32; ++rr) {
-      float d[4], a[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        d[q] = sD[rr][tn + q];
-        a[q] = sA[rr][tk + q];
-      }
+      const float4 d4 = *reinterpret_cast<const float4*>(&sD[rr][tn]), a4 = *reinterpret_cast<const float4*>(&sA[rr][tk]);
+      const float d[4] = {d4.x, d4.y, d4.z, d4.w}, a[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
       for (int x = 0; x < 4; ++x)
 #pragma unroll
@@ -524,18 +587,18 @@ extern "C" int sgn_train_backward(const SgnField* f, const float* d_origins, con
     p.cap = std::min(samples, kBwdChunk);
     k_train_field_bwd<<<blocks_for(p.count, 128, 8), 128, sizeof(MlpF32), st>>>(p);
     SGN_LAUNCH_CHECK();
-    const int per_cta = 1024;
+    // the five weight gradients in one launch (blockIdx.y = layer): 512-sample slabs keep ~1 000 CTAs in flight, which is
+    // what hides the latency of the slab loads (one 32-sample stage at a time per CTA)
+    const int per_cta = 512;
     const int ctas = (int)((p.count + per_cta - 1) / per_cta);
-    // layer            deltas (offset, N)  activations (offset, K)
-    k_outer_reduce<<<ctas, 256, 0, st>>>(deltas, 0, 64, acts, 0, 32, p.count, p.cap, 32, G->w_base0, G->b_base0, per_cta);
-    SGN_LAUNCH_CHECK();
-    k_outer_reduce<<<ctas, 256, 0, st>>>(deltas, 64, 16, acts, 32, 64, p.count, p.cap, 64, G->w_base1, G->b_base1, per_cta);
-    SGN_LAUNCH_CHECK();
-    k_outer_reduce<<<ctas, 256, 0, st>>>(deltas, 80, 64, acts, 96, 32, p.count, p.cap, 32, G->w_head0, G->b_head0, per_cta);
-    SGN_LAUNCH_CHECK();
-    k_outer_reduce<<<ctas, 256, 0, st>>>(deltas, 144, 64, acts, 128, 64, p.count, p.cap, 64, G->w_head1, G->b_head1, per_cta);
-    SGN_LAUNCH_CHECK();
-    k_outer_reduce<<<ctas, 256, 0, st>>>(deltas, 208, 3, acts, 192, 64, p.count, p.cap, 64, G->w_head2, G->b_head2, per_cta);
+    OuterParams op;
+    //             deltas (offset, N)  activations (offset, K)  ld
+    op.layer[0] = {0, 64, 0, 32, 32, G->w_base0, G->b_base0};
+    op.layer[1] = {64, 16, 32, 64, 64, G->w_base1, G->b_base1};
+    op.layer[2] = {80, 64, 96, 32, 32, G->w_head0, G->b_head0};
+    op.layer[3] = {144, 64, 128, 64, 64, G->w_head1, G->b_head1};
+    op.layer[4] = {208, 3, 192, 64, 64, G->w_head2, G->b_head2};
+    k_outer_reduce<<<dim3(ctas, 5), 256, 0, st>>>(deltas, acts, op, p.count, p.cap, per_cta);
     SGN_LAUNCH_CHECK();
     if (d_grad_head_bias) {
       k_ray_bias_reduce<<<blocks_for((p.count / S + 2) * 64, 128, 8), 128, 0, st>>>(deltas, first, p.count, p.cap, S, d_grad_head_bias);

@@ -276,19 +276,13 @@ __global__ void __launch_bounds__(128) k_prop_bwd(const PropDev* __restrict__ ne
       }
     }
     warp_add(160 + 32, d_out);                              // db1
-    if (live && d_out != 0.f) {
+    // hash features: scatter-add, runs of samples in the same cell merged inside the warp (scatter_level_merged)
+    const bool any = live && d_out != 0.f;
 #pragma unroll 1
-      for (int l = 0; l < 5; ++l) {
-        const LevelCoords L = level_coords(net.grid.res[l], px, py, pz);
-        uint32_t idx[8];
-        corner_rows(L, net.grid.mask, idx);
-        const float mx = 1.f - L.ox, my = 1.f - L.oy, mz = 1.f - L.oz;
-        const float wt[8] = {L.ox * L.oy * L.oz, L.ox * my * L.oz, mx * my * L.oz, mx * L.oy * L.oz,
-                             L.ox * L.oy * mz,   L.ox * my * mz,   mx * my * mz,   mx * L.oy * mz};
-        float2* gt = reinterpret_cast<float2*>(grad_table) + (size_t)l * net.grid.size;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) atomicAdd(gt + idx[c], make_float2(wt[c] * dfeat[2 * l], wt[c] * dfeat[2 * l + 1]));
-      }
+    for (int l = 0; l < 5; ++l) {
+      const LevelCoords L = level_coords(net.grid.res[l], px, py, pz);
+      float2* gt = reinterpret_cast<float2*>(grad_table) + (size_t)l * net.grid.size;
+      scatter_level_merged(gt, L, net.grid.mask, any ? dfeat[2 * l] : 0.f, any ? dfeat[2 * l + 1] : 0.f, lane);
     }
   }
   __syncthreads();
