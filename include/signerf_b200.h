@@ -287,6 +287,12 @@ int sgn_conv3x3_direct(const float* d_x, int in_nchw, const float* d_w, const fl
 /* out[b] = act_out(W act_in(x[b]) + bias (+ residual[b])) for B <= 8 rows, fp32 (time_embed, label_emb, emb_layers). */
 int sgn_linear_small(const float* d_x, const float* d_w, const float* d_bias, const float* d_residual, int B, int N,
                      int K, int silu_in, int silu_out, float* d_out, void* stream);
+/* The `emb_layers` projections of every ResBlock of a network in one launch ([EXT] sgm ResBlock.forward:
+ * `emb_out = self.emb_layers(emb)`, which depends on emb only): d_w [N, K] / d_bias [N] are the blocks' weights concatenated
+ * along the rows, d_seg_offsets int32 [num_segments + 1] the row range of every block; block j's result is the contiguous
+ * [B, N_j] matrix at d_out + B * seg[j] - bit for bit what sgn_linear_small gives per block. */
+int sgn_linear_small_segments(const float* d_x, const float* d_w, const float* d_bias, int B, int N, int K, int silu_in,
+                              const int32_t* d_seg_offsets, int num_segments, float* d_out, void* stream);
 /* sgm timestep_embedding(t, dim, max_period=10000): [cos | sin]. */
 int sgn_timestep_embedding(const float* d_t, int B, int dim, float* d_out, void* stream);
 

@@ -130,6 +130,7 @@ SIGNATURES = {
     "sgn_im2col3x3_split_f16": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "sgn_conv3x3_direct": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "sgn_linear_small": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "sgn_linear_small_segments": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
     "sgn_timestep_embedding": (_i, [_vp, _i, _i, _vp, _vp]),
     "sgn_scale_repeat_f32": (_i, [_vp, _i64, _f, _i, _vp, _vp]),
     "sgn_sheet_to_conditioning": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),

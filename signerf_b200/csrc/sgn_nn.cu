@@ -501,6 +501,41 @@ __global__ void __launch_bounds__(256) k_linear_small(const float* __restrict__ 
     }
 }
 
+// The emb_layers projections of ALL ResBlocks of a network in one launch (they only depend on emb): row n of the
+// concatenated weight belongs to segment j (seg[j] <= n < seg[j+1]); segment j's output is its own contiguous [B, N_j]
+// block at out + B * seg[j], i.e. exactly what the per-block call would have produced.
+__global__ void __launch_bounds__(256) k_linear_small_seg(const float* __restrict__ x, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, int B, int N, int K, int silu_in,
+                                                          const int* __restrict__ seg, int nseg, float* out) {
+  const int lane = threadIdx.x & 31;
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (n >= N) return;
+  float acc[8];
+#pragma unroll
+  for (int b = 0; b < 8; ++b) acc[b] = 0.f;
+  const float4* wr = reinterpret_cast<const float4*>(w + (size_t)n * K);
+  for (int k = lane; k < (K >> 2); k += 32) {
+    const float4 wv = __ldg(wr + k);
+#pragma unroll
+    for (int b = 0; b < 8; ++b)
+      if (b < B) {
+        float4 xv = __ldg(reinterpret_cast<const float4*>(x + (size_t)b * K) + k);
+        if (silu_in) xv.x = silu(xv.x), xv.y = silu(xv.y), xv.z = silu(xv.z), xv.w = silu(xv.w);
+        acc[b] = fmaf(xv.x, wv.x, fmaf(xv.y, wv.y, fmaf(xv.z, wv.z, fmaf(xv.w, wv.w, acc[b]))));   // k_linear_small's order
+      }
+  }
+#pragma unroll
+  for (int b = 0; b < 8; ++b)
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc[b] += __shfl_xor_sync(0xffffffffu, acc[b], o);
+  if (lane == 0) {
+    int j = 0;
+    while (j + 1 < nseg && __ldg(seg + j + 1) <= n) ++j;
+    const int s0 = __ldg(seg + j), nj = __ldg(seg + j + 1) - s0;
+    for (int b = 0; b < B; ++b) out[(size_t)B * s0 + (size_t)b * nj + (n - s0)] = acc[b] + (bias ? __ldg(bias + n) : 0.f);
+  }
+}
+
 // sgm timestep_embedding(t, dim): [cos(t f_i) | sin(t f_i)], f_i = exp(-ln(10000) i / half), fp32 like torch
 __global__ void k_timestep_embedding(const float* __restrict__ t, int B, int dim, float* out) {
   const int half_d = dim / 2;
@@ -729,6 +764,16 @@ extern "C" int sgn_linear_small(const float* d_x, const float* d_w, const float*
   SGN_CHECK_ARG(d_x && d_w && d_out, "null pointer");
   k_linear_small<<<(N * 32 + 255) / 256, 256, 0, ST(stream)>>>(d_x, d_w, d_bias, d_residual, B, N, K, silu_in, silu_out,
                                                                d_out);
+  SGN_LAUNCH_CHECK();
+  return SGN_OK;
+}
+
+extern "C" int sgn_linear_small_segments(const float* d_x, const float* d_w, const float* d_bias, int B, int N, int K, int silu_in,
+                                         const int32_t* d_seg_offsets, int num_segments, float* d_out, void* stream) {
+  SGN_CHECK_ARG(B >= 1 && B <= 8 && N > 0 && K > 0 && K % 4 == 0 && num_segments >= 1, "sgn_linear_small_segments: 1..8 rows, K % 4 == 0");
+  SGN_CHECK_ARG(d_x && d_w && d_seg_offsets && d_out, "null pointer");
+  k_linear_small_seg<<<(N * 32 + 255) / 256, 256, 0, ST(stream)>>>(d_x, d_w, d_bias, B, N, K, silu_in, d_seg_offsets, num_segments,
+                                                                   d_out);
   SGN_LAUNCH_CHECK();
   return SGN_OK;
 }

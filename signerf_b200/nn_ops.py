@@ -245,6 +245,21 @@ def conv3x3_direct(x: Tensor, in_nchw: bool, w: Tensor, bias: Optional[Tensor], 
     return out
 
 
+def linear_small_segments(x: Tensor, w_cat: Tensor, b_cat: Tensor, seg_offsets: Tensor, silu_in: bool = False) -> Tensor:
+    """Several small linears on the same input in one launch: w_cat [sum N_j, K], seg_offsets int32 [nseg + 1] (device);
+    -> flat fp32 buffer in which segment j is the contiguous [B, N_j] matrix at B * seg[j]."""
+    _chk(x, torch.float32, "x")
+    _chk(w_cat, torch.float32, "w_cat")
+    _chk(b_cat, torch.float32, "b_cat")
+    _chk(seg_offsets, torch.int32, "seg_offsets")
+    B, Kd = x.shape
+    N = w_cat.shape[0]
+    out = torch.empty(B * N, dtype=torch.float32, device=x.device)
+    _call(x.device, _lib.load().sgn_linear_small_segments, _ptr(x), _ptr(w_cat), _ptr(b_cat), B, N, Kd, int(silu_in),
+          _ptr(seg_offsets), seg_offsets.numel() - 1, _ptr(out))
+    return out
+
+
 def conv3x3_small_tc(x: Tensor, w16: Tensor, bias: Optional[Tensor], stride: int = 1, act_silu: bool = False,
                      out_f16: bool = False) -> Tensor:
     """fp32-exact 3x3 / p1 conv for 16 / 32 channels on mma.sync: x fp32 NHWC [B,H,W,Cin], w16 fp16 [Cout, 9*Cin]."""

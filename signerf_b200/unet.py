@@ -306,6 +306,7 @@ class _Net:
             raise ValueError("sgn_attention_f16 is specialised for head_dim 64 (SDXL)")
         self._prepack(schema)
         self._pack_context_kv(schema)
+        self._pack_emb_layers(schema)
         self.p.w = None  # drop the reference to the source state_dict: only packed copies stay resident
         self._kv_ctx: Optional[Tensor] = None            # context the batched K/V projections were computed for
         self._kv_out: Dict[int, Tensor] = {}
@@ -329,7 +330,7 @@ class _Net:
                     if (shp[1], shp[0]) in SMALL_TC_SHAPES:
                         p.conv16(n)
             elif len(shp) == 4 and shp[2] == 3:
-                (p.conv16 if shp[1] % 64 == 0 else p.conv32)(n)
+                (p.conv16 if shp[1] % 64 == 0 else p.conv_split16)(n)
             elif len(shp) == 4:
                 p.lin16(n)
             elif ".attn1.to_q" in n:
@@ -357,6 +358,32 @@ class _Net:
                 self._kv_off[b] = 2 * c * i
                 rows += [self.p._get(b + ".attn2.to_k.weight"), self.p._get(b + ".attn2.to_v.weight")]
             self._kv_w[c] = torch.cat(rows, 0).half().contiguous()
+
+    def _pack_emb_layers(self, schema) -> None:
+        """Every ResBlock projects the same emb (`emb_layers`: SiLU -> Linear): one launch for the whole network, weights
+        concatenated along the rows, block `pre` at rows _emb_off[pre] .. + cout."""
+        pres = [n[: -len(".emb_layers.1.weight")] for n in schema if n.endswith(".emb_layers.1.weight")]
+        self._emb_off: Dict[str, Tuple[int, int]] = {}
+        off = 0
+        for pre in pres:
+            cout = schema[pre + ".emb_layers.1.weight"][0]
+            self._emb_off[pre] = (off, cout)
+            off += cout
+        self._emb_w = torch.cat([self.p.f32(pre + ".emb_layers.1.weight") for pre in pres], 0).contiguous()
+        self._emb_b = torch.cat([self.p.f32(pre + ".emb_layers.1.bias") for pre in pres], 0).contiguous()
+        self._emb_seg = torch.tensor([self._emb_off[pre][0] for pre in pres] + [off], dtype=torch.int32, device=self.dev)
+        self._emb_for: Optional[Tensor] = None           # the emb tensor the batched projections were computed for
+        self._emb_out: Optional[Tensor] = None
+
+    def emb_projection(self, pre: str, emb: Tensor) -> Tensor:
+        """emb_layers(emb) of ResBlock `pre` [Bt, cout]: a view of the batched projection when it was made for this emb
+        (embed() does that), otherwise the block's own small linear (block-level callers, tests)."""
+        if getattr(self, "_emb_for", None) is emb:
+            off, cout = self._emb_off[pre]
+            B = emb.shape[0]
+            return self._emb_out[B * off:B * (off + cout)].view(B, cout)
+        p = self.p
+        return K.linear_small(emb, p.f32(pre + ".emb_layers.1.weight"), p.f32(pre + ".emb_layers.1.bias"), silu_in=True)
 
     def project_context(self, ctx16: Tensor) -> None:
         """One K/V GEMM per channel width for the whole network (forward() calls this once per step)."""
@@ -397,13 +424,16 @@ class _Net:
         a = K.linear_small(te, p.f32("time_embed.0.weight"), p.f32("time_embed.0.bias"), silu_out=True)
         a = K.linear_small(a, p.f32("time_embed.2.weight"), p.f32("time_embed.2.bias"))
         b = K.linear_small(y, p.f32("label_emb.0.0.weight"), p.f32("label_emb.0.0.bias"), silu_out=True)
-        return K.linear_small(b, p.f32("label_emb.0.2.weight"), p.f32("label_emb.0.2.bias"), residual=a)
+        emb = K.linear_small(b, p.f32("label_emb.0.2.weight"), p.f32("label_emb.0.2.bias"), residual=a)
+        self._emb_out = K.linear_small_segments(emb, self._emb_w, self._emb_b, self._emb_seg, silu_in=True)
+        self._emb_for = emb
+        return emb
 
     def resblock(self, pre: str, x: Act, emb: Tensor) -> Act:
         p = self.p
         cout = p.f32(pre + ".in_layers.2.bias").shape[0]
         a16 = self.gn16(x, pre + ".in_layers.0", 1e-5, True)
-        e = K.linear_small(emb, p.f32(pre + ".emb_layers.1.weight"), p.f32(pre + ".emb_layers.1.bias"), silu_in=True)
+        e = self.emb_projection(pre, emb)
         h = K.conv3x3_f16(a16.view(x.B, x.H, x.W, x.C), p.conv16(pre + ".in_layers.2.weight"),
                           p.f32(pre + ".in_layers.2.bias"), rowbias=e)
         b16 = self.gn16(Act(h, x.B, x.H, x.W), pre + ".out_layers.0", 1e-5, True)
@@ -457,10 +487,19 @@ class _Net:
         blk = _encoder_layout(self.cfg)[0][i]
         pre = f"input_blocks.{i}"
         if blk[0] == "conv_in":
+            # 4 -> 320 channels: the latent's patches as fp16 [hi | lo] pairs against [W | W] on the tensor cores (the
+            # fp32 conv to fp32 rounding, like the hint stack's stride-2 layers); the direct CUDA-core conv took 0.4-0.6 ms
             B, _, H, W = x_nchw.shape
-            t = K.conv3x3_direct(x_nchw, True, self.p.conv32(pre + ".0.weight"), self.p.f32(pre + ".0.bias"),
-                                 residual=first_residual)
-            return Act(t.view(B * H * W, -1), B, H, W)
+            col, _, _, _ = K.im2col3x3_split_f16(x_nchw, True, 1)
+            w16, bias = self.p.conv_split16(pre + ".0.weight"), self.p.f32(pre + ".0.bias")
+            if first_residual is None:
+                t = K.gemm_f16(col, w16, bias)
+            else:                                      # ControlNet: + guided hint, one hint per CFG pair (image b uses hint b % Bh)
+                res = first_residual.reshape(first_residual.shape[0], H * W, -1)
+                t = torch.empty((B * H * W, w16.shape[0]), dtype=torch.float32, device=col.device)
+                for b in range(B):
+                    K.gemm_f16(col[b * H * W:(b + 1) * H * W], w16, bias, residual=res[b % res.shape[0]], out=t[b * H * W:(b + 1) * H * W])
+            return Act(t, B, H, W)
         if blk[0] == "res":
             h = self.resblock(pre + ".0", h, emb)
             return self.transformer(pre + ".1", h, blk[3], ctx16, n_ctx) if blk[3] else h
