@@ -260,3 +260,40 @@ def test_full_training_steps_reduce_the_losses_and_move_every_group():
     tr.refresh_renderer()
     rgb1 = ops.render_rays(fld, oc, dc, opts)[0]
     assert not torch.equal(rgb0, rgb1) and bool(torch.isfinite(rgb1).all())
+
+
+@pytest.mark.gpu
+def test_training_entry_points_reject_bad_arguments_and_accept_empty_batches():
+    """Error behaviour through the C ABI: a field without proposal networks cannot run the training sampler, workspaces
+    that are too small are refused, empty batches are no-ops."""
+    import ctypes as C
+    from signerf_b200 import _lib
+    from tests.helpers import field_from_oracle
+    m = R.make_model(0, dense=True, log2_hashmap_size=12)
+    bare = field_from_oracle(m, with_proposals=False)
+    o = torch.zeros(4, 3, device="cuda")
+    d = torch.tensor([[0.0, 0.0, 1.0]], device="cuda").repeat(4, 1)
+    with pytest.raises(_lib.SgnError, match="2 proposal networks"):
+        T.train_sample(bare, o, d, (16, 8, 4))
+    with pytest.raises(ValueError):
+        T.NerfactoTrainer(bare)
+    full = field_from_oracle(m, with_proposals=True)
+    lib = _lib.load()
+    smp = T.train_sample(full, o, d, (16, 8, 4), m.near, m.far, torch.rand(3, 4, device="cuda"))
+    assert all(bool(torch.isfinite(t).all()) for t in smp.spacing + smp.euclid + smp.sigma + smp.weights)
+    assert all(bool((t[:, 1:] >= t[:, :-1]).all()) for t in smp.spacing)                 # bin edges ascend along every ray
+    # empty batch: every entry point returns OK without touching memory
+    e = torch.zeros(0, 3, device="cuda")
+    empty = T.train_sample(full, e, e, (16, 8, 4))
+    assert empty.spacing[0].shape == (0, 17)
+    rgb, acc, saved = T.train_forward(full, e, e, torch.linspace(0.05, 10.0, 5, device="cuda"))
+    assert rgb.shape == (0, 3)
+    # too-small workspace
+    ws = torch.empty(16, dtype=torch.uint8, device="cuda")
+    gw = torch.zeros(4, 16, device="cuda")
+    rc = lib.sgn_prop_backward(full.handle, 0, o.data_ptr(), d.data_ptr(), 4, 16, smp.euclid[0].data_ptr(), smp.sigma[0].data_ptr(),
+                               gw.data_ptr(), gw.data_ptr(), gw.data_ptr(), ws.data_ptr(), 16, None)
+    assert rc != 0 and b"workspace" in lib.sgn_last_error()
+    rc = lib.sgn_prop_backward(full.handle, 5, o.data_ptr(), d.data_ptr(), 4, 16, smp.euclid[0].data_ptr(), smp.sigma[0].data_ptr(),
+                               gw.data_ptr(), gw.data_ptr(), gw.data_ptr(), ws.data_ptr(), 16, None)
+    assert rc != 0 and b"no such proposal network" in lib.sgn_last_error()
