@@ -41,8 +41,9 @@ def _oracle_views(m, c2w, intr, H, W, gen, S_samples):
     return renders, masks, conds
 
 
-def test_generate_reference_sheet_and_with_reference_sheet():
-    rows, cols, H, W, ds, Ssamp = 2, 2, 48, 40, 2, 24
+@pytest.mark.parametrize("rows,cols", [(2, 2), (2, 3)])       # (2, 3) = the reference's default sheet (datasetgenerator.py:62-65)
+def test_generate_reference_sheet_and_with_reference_sheet(rows, cols):
+    H, W, ds, Ssamp = 48, 40, 2, 24
     th, tw = H // ds, W // ds
     m = R.make_model(0, dense=True, table_scale=0.5, density_gain=20.0)
     graph = P.FusedNerfactoGraph(field_from_oracle(m), ops.RenderOptions(mode="flat", num_samples=Ssamp, mlp_mode=ops.MLP_FP32))
@@ -52,15 +53,15 @@ def test_generate_reference_sheet_and_with_reference_sheet():
     img, msk, cnd, edited, refs = gen.generate_reference_sheet(graph, cams, tw, th)
     renders, masks, conds = _oracle_views(m, c2w[:-1], intr[:-1], H, W, gen, Ssamp)
     img_r, msk_r, cnd_r = S.reference_sheet(renders, masks, conds, rows, cols, th, tw, 0)
-    assert img.shape == img_r.shape == (2 * th, 2 * tw, 3)
+    assert img.shape == img_r.shape == ((rows * th + 7) // 8 * 8, (cols * tw + 7) // 8 * 8, 3)     # sheet sides ceil to x8 (:498-508)
     assert rel_l2(img, img_r) < 2e-5 and rel_l2(cnd, cnd_r) < 1e-3
     assert float((msk.cpu() != msk_r).float().mean()) < 2e-3            # median-depth bin flips at the box boundary
     edited_r = S.blend(1.0 - 0.5 * img_r, img_r, msk_r)
     same = (msk.cpu() == msk_r).expand_as(edited_r)
     assert torch.allclose(edited.cpu()[same], edited_r[same], atol=1e-4)
-    assert len(refs) == 3 and set(refs[0]) == {"render", "mask", "condition", "render_scaled", "mask_scaled",
+    assert len(refs) == rows * cols - 1 and set(refs[0]) == {"render", "mask", "condition", "render_scaled", "mask_scaled",
                                                "condition_scaled", "edited", "edited_scaled"}
-    for i in range(3):
+    for i in range(rows * cols - 1):
         assert rel_l2(refs[i]["render"], renders[i]) < 2e-5
         assert refs[i]["edited"].shape == (H, W, 3) and refs[i]["edited_scaled"].shape == (th, tw, 3)
         assert torch.allclose(refs[i]["edited"].cpu(), S.cut_tile(edited.cpu(), i, cols, th, tw, 0, H, W), atol=1e-6)
@@ -70,7 +71,8 @@ def test_generate_reference_sheet_and_with_reference_sheet():
     out = gen.generate_with_reference_sheet(graph, cam_last, None, tw, th, img_arg, cnd_arg)
     r_l, m_l, c_l = _oracle_views(m, c2w[-1:], intr[-1:], H, W, gen, Ssamp)
     rs = S._interp(r_l[0], th, tw)
-    assert rel_l2(img_arg[th:, tw:], rs) < 2e-5 and torch.equal(img_arg[:th], edited[:th])
+    y0, x0 = (rows - 1) * th, (cols - 1) * tw                      # the last tile
+    assert rel_l2(img_arg[y0:y0 + th, x0:x0 + tw], rs) < 2e-5 and torch.equal(img_arg[:y0], edited[:y0])
     assert rel_l2(out["render_scaled"], rs) < 2e-5 and out["edited"].shape == (H, W, 3)
     ms = S._interp(m_l[0].float(), th, tw) > 0.5
     exp = (1.0 - 0.5 * rs) * ms + rs * (~ms)
