@@ -250,6 +250,43 @@ class FieldTrainer:
         self.optimizer_step()
         return loss
 
+    def state_dict(self) -> Dict[str, Tensor]:
+        """The trained parameters under nerfstudio's torch-fallback names (the `_model.` part of a pipeline checkpoint,
+        signerf_trainer.py:278-306): what `load_into` copies back into the reference's model and what
+        `plugin.FusedNerfactoGraph.from_state_dict` reads.  Detached copies."""
+        v = mlp_block_views(self.mlp)
+        wh0 = torch.cat([v["w_head0"][:, :16], v["w_head0"][:, 17:32], self.w_app], dim=1)      # SH 16 | geo 15 | appearance 32
+        sd = {"field.mlp_base.encoding.hash_table": self.table,
+              "field.mlp_base.mlp.layers.0.weight": v["w_base0"], "field.mlp_base.mlp.layers.0.bias": v["b_base0"],
+              "field.mlp_base.mlp.layers.1.weight": v["w_base1"], "field.mlp_base.mlp.layers.1.bias": v["b_base1"],
+              "field.mlp_head.layers.0.weight": wh0, "field.mlp_head.layers.0.bias": self.b_head0,
+              "field.mlp_head.layers.1.weight": v["w_head1"], "field.mlp_head.layers.1.bias": v["b_head1"],
+              "field.mlp_head.layers.2.weight": v["w_head2"], "field.mlp_head.layers.2.bias": v["b_head2"][:3]}
+        return {k: t.detach().clone() for k, t in sd.items()}
+
+    # the other parameter layout nerfstudio's torch-fallback modules have used (plugin/model.py from_state_dict)
+    _ALT_NAMES = (("field.mlp_base.encoding.", "field.mlp_base_grid."), ("field.mlp_base.mlp.", "field.mlp_base_mlp."),
+                  (".mlp_base.encoding.", ".encoding."), (".mlp_base.mlp.", ".mlp_base."))
+
+    def load_into(self, model: torch.nn.Module) -> list:
+        """Copy the trained parameters into the matching tensors of a nerfstudio model (`pipeline.model`), in place, so that
+        the reference's own checkpointing / viewer / eval see the fine-tuned field.  Returns the names written."""
+        target = dict(model.state_dict(keep_vars=True))
+        written = []
+        with torch.no_grad():
+            for name, value in self.state_dict().items():
+                cands = [name] + [name.replace(a, b) for a, b in self._ALT_NAMES if a in name]
+                hit = next((c for c in cands if c in target), None)
+                if hit is None:
+                    if name.startswith("field.embedding_appearance"):
+                        continue                       # SIGNeRF re-creates the table per dataset (signerf_pipeline.py:110-111)
+                    raise KeyError(f"the model has no parameter for {name} (tried {cands})")
+                if tuple(target[hit].shape) != tuple(value.shape):
+                    raise ValueError(f"{hit}: model has shape {tuple(target[hit].shape)}, trained tensor {tuple(value.shape)}")
+                target[hit].copy_(value.to(target[hit].device, target[hit].dtype))
+                written.append(hit)
+        return written
+
     def refresh_renderer(self) -> None:
         """Re-derive the tensor-core fragments from the updated parameters before the next sgn_render_* call."""
         with torch.cuda.device(self.field.device):
@@ -464,6 +501,17 @@ class NerfactoTrainer(FieldTrainer):
         self._per_image = per_image
         self.loss_dict = out
         return out
+
+    def state_dict(self) -> Dict[str, Tensor]:
+        sd = super().state_dict()
+        if self.embedding is not None:
+            sd["field.embedding_appearance.embedding.weight"] = self.embedding.detach().clone()
+        for l in range(2):
+            pre, m = f"proposal_networks.{l}.mlp_base", self.prop_mlps[l]
+            sd[pre + ".encoding.hash_table"] = self.prop_tables[l].detach().clone()
+            sd[pre + ".mlp.layers.0.weight"], sd[pre + ".mlp.layers.0.bias"] = m[:160].view(16, 10).clone(), m[160:176].clone()
+            sd[pre + ".mlp.layers.1.weight"], sd[pre + ".mlp.layers.1.bias"] = m[176:192].view(1, 16).clone(), m[192:193].clone()
+        return sd
 
     def all_gradients(self):
         """Every gradient buffer of the step (for a data-parallel all-reduce)."""

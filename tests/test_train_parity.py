@@ -297,3 +297,37 @@ def test_training_entry_points_reject_bad_arguments_and_accept_empty_batches():
     rc = lib.sgn_prop_backward(full.handle, 5, o.data_ptr(), d.data_ptr(), 4, 16, smp.euclid[0].data_ptr(), smp.sigma[0].data_ptr(),
                                gw.data_ptr(), gw.data_ptr(), gw.data_ptr(), ws.data_ptr(), 16, None)
     assert rc != 0 and b"no such proposal network" in lib.sgn_last_error()
+
+
+@pytest.mark.gpu
+def test_trained_parameters_round_trip_to_nerfstudio_names():
+    """After fine-tuning, `state_dict()` carries every trained tensor under nerfstudio's names: a renderer rebuilt from it
+    renders what the trained field renders, and `load_into` writes the same values into a reference-style module."""
+    import signerf_b200.plugin as P
+    from signerf_b200 import ops
+    m, fld, o, d, target, jitter, cams = _setup_full(n_rays=128)
+    tr = T.NerfactoTrainer(fld, embedding=m.field.embedding_appearance.weight, counts=(64, 32, 16), near=m.near, far=m.far)
+    for _ in range(3):
+        tr.train_step(o.cuda(), d.cuda(), target.cuda(), jitter.cuda(), cams.cuda())
+    tr.refresh_renderer()
+    sd = tr.state_dict()
+    assert sd["field.mlp_head.layers.0.weight"].shape == (64, 63) and sd["proposal_networks.1.mlp_base.mlp.layers.1.weight"].shape == (1, 16)
+    opts = ops.RenderOptions(mode="cascade", num_samples=16, num_prop_samples=(64, 32), near_plane=m.near, far_plane=m.far)
+    rebuilt = P.FusedNerfactoGraph.from_state_dict(sd, average_init_density=m.field.average_init_density, render_opts=opts)
+    a = ops.render_rays(fld, o.cuda(), d.cuda(), opts)
+    b = ops.render_rays(rebuilt.field, o.cuda(), d.cuda(), opts)
+    assert rel_l2(a[0], b[0]) < 1e-5 and rel_l2(a[1], b[1]) < 1e-5
+    from tests.test_plugin_parity import _ContractOnlyModel       # an nn.Module exposing the oracle's live parameters under nerfstudio's names
+    model = _ContractOnlyModel(m)
+    before = m.field.encoding.hash_table.detach().clone()
+    written = tr.load_into(model)
+    assert "field.mlp_base.encoding.hash_table" in written and "proposal_networks.0.mlp_base.encoding.hash_table" in written
+    assert not torch.equal(before, m.field.encoding.hash_table) and torch.equal(m.field.encoding.hash_table.cpu(), tr.table.cpu())
+    assert torch.equal(m.field.mlp_head.layers[0].weight[:, 31:].cpu(), tr.w_app.cpu())
+    assert torch.equal(m.proposal_networks[1].mlp.layers[0].weight.detach().cpu().flatten(), tr.prop_mlps[1][:160].cpu())
+    assert torch.equal(m.field.embedding_appearance.weight.detach().cpu(), tr.embedding.cpu())
+    # ... and the oracle on the written-back weights renders what the fine-tuned field renders (eval cascade, fp16 MLP path)
+    m.eval()
+    with torch.no_grad():
+        ref = R.render_rays(m, o, d, "cascade")
+    assert rel_l2(a[0], ref["rgb"]) < 2e-3
