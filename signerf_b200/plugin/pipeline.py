@@ -128,3 +128,29 @@ class SIGNeRFPipeline(VanillaPipeline):
 
     def forward(self):
         pass
+
+    # ------------------------------------------------------------------ the training step on the CUDA kernels (opt-in)
+    def enable_fused_training(self, **kw) -> None:
+        """Route `get_train_loss_dict` ([EXT] VanillaPipeline.get_train_loss_dict: next_train -> model forward ->
+        get_metrics_dict -> get_loss_dict) through `signerf_b200.train.FusedTrainingStep`: same batches from the same
+        datamanager, the same loss-dict keys, gradients into the model's own parameters - the trainer's optimizers,
+        schedulers, GradScaler and checkpoints do not notice.  `kw`: FusedTrainingStep options."""
+        from ..train import FusedTrainingStep
+        cfg = getattr(self.model, "config", None)
+        opts = dict(near=float(getattr(cfg, "near_plane", 0.05)), far=float(getattr(cfg, "far_plane", 1000.0)),
+                    average_init_density=float(getattr(cfg, "average_init_density", 0.01)), use_l1=bool(getattr(cfg, "use_l1", True)),
+                    interlevel_loss_mult=float(getattr(cfg, "interlevel_loss_mult", 1.0)),
+                    distortion_loss_mult=float(getattr(cfg, "distortion_loss_mult", 0.002)),
+                    counts=tuple(getattr(cfg, "num_proposal_samples_per_ray", (256, 96))) + (int(getattr(cfg, "num_nerf_samples_per_ray", 48)),))
+        opts.update(kw)
+        self._fused_step = FusedTrainingStep(self.model, **opts)
+
+    def get_train_loss_dict(self, step: int):
+        fused = getattr(self, "_fused_step", None)
+        if fused is None:
+            return super().get_train_loss_dict(step)
+        ray_bundle, batch = self.datamanager.next_train(step)
+        cams = ray_bundle.camera_indices.reshape(-1).to(dtype=__import__("torch").int32)
+        loss_dict = fused.loss_dict(ray_bundle.origins.reshape(-1, 3), ray_bundle.directions.reshape(-1, 3),
+                                    batch["image"].to(ray_bundle.origins.device)[..., :3], cams)
+        return {}, loss_dict, {"distortion": loss_dict["distortion_loss"].detach() / max(fused.trainer.distortion_mult, 1e-30)}

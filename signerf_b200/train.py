@@ -554,3 +554,123 @@ class NerfactoTrainer(FieldTrainer):
         out = self.forward_backward(origins, directions, target_rgb, jitter, camera_indices, extra_loss)
         self.optimizer_step()
         return out
+
+
+# ---------------------------------------------------------------------------------------------- behind nerfstudio's own optimizers
+class _AttachGradients(torch.autograd.Function):
+    """value = the summed loss of the step; the gradients were already computed by the CUDA backward - hand them to
+    autograd as the gradients of the model's own parameters (scaled by the upstream gradient: GradScaler, loss weights)."""
+
+    @staticmethod
+    def forward(ctx, value: Tensor, grads, *params):
+        ctx.grads = grads
+        return value.clone()
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        return (None, None) + tuple(g * gr for gr in ctx.grads)
+
+
+class FusedTrainingStep:
+    """`SIGNeRFModel`'s training step - `get_outputs` while training + `get_loss_dict` (signerf.py:41-68) - on the CUDA
+    kernels, BEHIND the reference's own parameters and optimizers: `loss_dict(...)` returns the reference's loss dict whose
+    sum back-propagates (one autograd node) into the `.grad` of the model's own tensors, so nerfstudio's `Optimizers`
+    (Adam + ExponentialDecay per group, signerf_config.py:43-58), GradScaler and checkpointing stay exactly as they are.
+
+    `model`: a torch-fallback nerfacto / SIGNeRF model (`pipeline.model`) on the GPU - anything whose `state_dict` carries
+    nerfstudio's parameter names.  The hash tables and the appearance table are used IN PLACE (no copies: the optimizer's
+    updates are seen at once); the small MLP tensors are re-uploaded into the field's parameter block at every call."""
+
+    def __init__(self, model: torch.nn.Module, counts: Tuple[int, int, int] = (256, 96, 48), near: float = 0.05, far: float = 1000.0,
+                 average_init_density: float = 0.01, use_l1: bool = True, interlevel_loss_mult: float = 1.0,
+                 distortion_loss_mult: float = 0.002):
+        from .plugin.model import FusedNerfactoGraph
+        self.model = model
+        sd = dict(model.state_dict(keep_vars=True))
+
+        def find(name: str) -> Tensor:
+            for cand in [name] + [name.replace(a, b) for a, b in FieldTrainer._ALT_NAMES if a in name]:
+                if cand in sd:
+                    return sd[cand]
+            raise KeyError(f"the model has no parameter {name}")
+
+        names = ["field.mlp_base.encoding.hash_table"]
+        names += [f"field.mlp_base.mlp.layers.{i}.{p}" for i in range(2) for p in ("weight", "bias")]
+        names += [f"field.mlp_head.layers.{i}.{p}" for i in range(3) for p in ("weight", "bias")]
+        names += ["field.embedding_appearance.embedding.weight"]
+        for l in range(2):
+            names += [f"proposal_networks.{l}.mlp_base.encoding.hash_table"]
+            names += [f"proposal_networks.{l}.mlp_base.mlp.layers.{i}.{p}" for i in range(2) for p in ("weight", "bias")]
+        self.params: Dict[str, Tensor] = {n: find(n) for n in names}
+        for n, t in self.params.items():
+            if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError(f"{n} must be a contiguous fp32 CUDA tensor (the kernels read the model's tensors in place)")
+        detached = {n: t.detach() for n, t in self.params.items()}
+        emb = detached["field.embedding_appearance.embedding.weight"]
+        graph = FusedNerfactoGraph.from_state_dict(detached, device=emb.device, average_init_density=average_init_density,
+                                                   near_plane=near, far_plane=far)
+        self.field = graph.field
+        if self.field.grid.table.data_ptr() != detached["field.mlp_base.encoding.hash_table"].data_ptr():
+            raise RuntimeError("the hash table was copied: it must be usable in place")
+        self.trainer = NerfactoTrainer(self.field, embedding=emb, counts=counts, near=near, far=far, use_l1=use_l1,
+                                       interlevel_loss_mult=interlevel_loss_mult, distortion_loss_mult=distortion_loss_mult)
+        self.trainer.embedding = emb                                   # the model's table itself, not a copy
+
+    def _sync_from_model(self) -> None:
+        """The model's current MLP tensors -> the field's parameter blocks (tables / embedding are shared storage)."""
+        p, tr = self.params, self.trainer
+        v = mlp_block_views(tr.mlp)
+        with torch.no_grad():
+            for i, (w, b) in enumerate((("w_base0", "b_base0"), ("w_base1", "b_base1"))):
+                v[w].copy_(p[f"field.mlp_base.mlp.layers.{i}.weight"])
+                v[b].copy_(p[f"field.mlp_base.mlp.layers.{i}.bias"])
+            h0 = p["field.mlp_head.layers.0.weight"]
+            v["w_head0"][:, :16].copy_(h0[:, :16])
+            v["w_head0"][:, 16].zero_()
+            v["w_head0"][:, 17:32].copy_(h0[:, 16:31])
+            tr.w_app.copy_(h0[:, 31:63])
+            tr.b_head0.copy_(p["field.mlp_head.layers.0.bias"])
+            v["w_head1"].copy_(p["field.mlp_head.layers.1.weight"]), v["b_head1"].copy_(p["field.mlp_head.layers.1.bias"])
+            v["w_head2"].copy_(p["field.mlp_head.layers.2.weight"]), v["b_head2"][:3].copy_(p["field.mlp_head.layers.2.bias"])
+            tr.app_mean = tr.embedding.mean(dim=0)
+            v["b_head0"].copy_(tr.b_head0 + tr.w_app @ tr.app_mean)    # folded bias: what the eval renderer uses
+            for l in range(2):
+                pre, m = f"proposal_networks.{l}.mlp_base.mlp.layers", tr.prop_mlps[l]
+                m[:160].copy_(p[pre + ".0.weight"].reshape(-1)), m[160:176].copy_(p[pre + ".0.bias"])
+                m[176:192].copy_(p[pre + ".1.weight"].reshape(-1)), m[192:193].copy_(p[pre + ".1.bias"])
+
+    def _gradients(self) -> Dict[str, Tensor]:
+        tr = self.trainer
+        g = nerfstudio_gradients(tr.grad_table, tr.grad_mlp, tr.app_mean)
+        g["field.mlp_head.layers.0.weight"] = torch.cat([g["field.mlp_head.layers.0.weight"][:, :31], tr.grad_w_app], dim=1)
+        g["field.mlp_head.layers.0.bias"] = tr.grad_b_head0
+        g["field.embedding_appearance.embedding.weight"] = tr.grad_embedding
+        for l in range(2):
+            pre, m = f"proposal_networks.{l}.mlp_base", tr.grad_prop_mlps[l]
+            g[pre + ".encoding.hash_table"] = tr.grad_prop_tables[l]
+            g[pre + ".mlp.layers.0.weight"], g[pre + ".mlp.layers.0.bias"] = m[:160].view(16, 10), m[160:176]
+            g[pre + ".mlp.layers.1.weight"], g[pre + ".mlp.layers.1.bias"] = m[176:192].view(1, 16), m[192:193]
+        return g
+
+    def loss_dict(self, origins: Tensor, directions: Tensor, target_rgb: Tensor, camera_indices: Tensor,
+                  jitter: Optional[Tensor] = None, extra_loss: Optional[Callable[[Tensor], Tensor]] = None) -> Dict[str, Tensor]:
+        """One batch -> {"rgb_loss", "interlevel_loss", "distortion_loss" (, "lpips_loss")}.  `sum(values).backward()` leaves
+        the step's gradients in the model's parameters; the individual entries carry the reference's values (only
+        "rgb_loss" holds the autograd node, for the sum of all terms)."""
+        self._sync_from_model()
+        if jitter is None:
+            jitter = torch.rand((3, origins.reshape(-1, 3).shape[0]), device=self.field.device)
+        out = self.trainer.forward_backward(origins, directions, target_rgb, jitter, camera_indices, extra_loss)
+        grads = self._gradients()
+        order = list(self.params)
+        others = sum(v for k, v in out.items() if k != "rgb_loss")
+        total = _AttachGradients.apply((out["rgb_loss"] + others).reshape(()), [grads[n].clone() for n in order],
+                                       *[self.params[n] for n in order])
+        res = {k: v.reshape(()).detach() for k, v in out.items()}
+        res["rgb_loss"] = total - others.reshape(()).detach()          # value = rgb loss, gradient = that of the whole sum
+        return res
+
+    def refresh_renderer(self) -> None:
+        """After optimizer steps: the model's tensors -> parameter block -> the eval renderer's tensor-core fragments."""
+        self._sync_from_model()
+        self.trainer.refresh_renderer()

@@ -331,3 +331,77 @@ def test_trained_parameters_round_trip_to_nerfstudio_names():
     with torch.no_grad():
         ref = R.render_rays(m, o, d, "cascade")
     assert rel_l2(a[0], ref["rgb"]) < 2e-3
+
+
+@pytest.mark.gpu
+def test_fused_training_step_behind_the_models_own_parameters_and_optimizer():
+    """FusedTrainingStep: the CUDA step's gradients land in `.grad` of the MODEL's tensors (nerfstudio names, used in place),
+    equal to torch autograd through the oracle, scale with the upstream gradient (GradScaler), and torch.optim.Adam on the
+    model's parameters - the reference's own optimizer - is what updates the field the kernels read."""
+    import copy
+    from tests.test_plugin_parity import _ContractOnlyModel
+    m_cpu = R.make_model(3, dense=True, table_scale=0.5, density_gain=20.0, log2_hashmap_size=14,
+                         num_proposal_samples=(64, 32), num_nerf_samples=16)
+    m_cpu.train()
+    m_gpu = copy.deepcopy(m_cpu).cuda()
+    model = _ContractOnlyModel(m_gpu)
+    step = T.FusedTrainingStep(model, counts=(64, 32, 16), near=m_cpu.near, far=m_cpu.far,
+                               average_init_density=m_cpu.field.average_init_density)
+    assert step.field.grid.table.data_ptr() == m_gpu.field.encoding.hash_table.data_ptr()          # in place, no copy
+    _, _, o, d, target, jitter, cams = _setup_full(n_rays=128)
+    oc, dc, tc, jc, cc = o.cuda(), d.cuda(), target.cuda(), jitter.cuda(), cams.cuda()
+    ld = step.loss_dict(oc, dc, tc, cc, jc)
+    (3.0 * sum(ld.values())).backward()                                 # an upstream factor, as a GradScaler applies
+    smp = T.train_sample(step.field, oc, dc, (64, 32, 16), m_cpu.near, m_cpu.far, jc)
+    fixed = [R.samples_from_edges(smp.spacing[l].cpu(), smp.euclid[l].cpu()) for l in range(3)]
+    ref = R.signerf_loss_dict(R.forward_train(m_cpu, o, d, jitter, cams, fixed_samples=fixed), target)
+    (3.0 * sum(ref.values())).backward()
+    for k in ref:
+        assert abs(float(ld[k]) - float(ref[k].detach())) < 1e-4 * max(abs(float(ref[k].detach())), 1e-3), k
+    errs = {n: rel_l2(pg.grad, pc.grad) for (n, pg), (_, pc) in zip(m_gpu.named_parameters(), m_cpu.named_parameters())
+            if pc.grad is not None}
+    print("grad rel-L2 through FusedTrainingStep:", {k: f"{v:.1e}" for k, v in errs.items()})
+    assert len(errs) >= 19 and max(errs.values()) < 1e-3, errs
+    # the model's own optimizer drives the training; the kernels see its updates (tables in place, MLPs re-uploaded)
+    opt = torch.optim.Adam(m_gpu.parameters(), lr=1e-2, eps=1e-15)
+    totals = []
+    for _ in range(12):
+        opt.zero_grad()
+        ld = step.loss_dict(oc, dc, tc, cc, jc)
+        total = sum(ld.values())
+        total.backward()
+        opt.step()
+        totals.append(float(total))
+    assert min(totals[-3:]) < totals[0], totals
+
+
+@pytest.mark.gpu
+def test_pipeline_get_train_loss_dict_routes_through_the_fused_step():
+    """plugin.SIGNeRFPipeline.enable_fused_training(): `get_train_loss_dict(step)` keeps VanillaPipeline's contract
+    (batches from datamanager.next_train, the reference's loss-dict keys, a `distortion` metric) and leaves the gradients
+    in the model's parameters."""
+    import copy
+    import signerf_b200.plugin as P
+    from tests.test_plugin_parity import _ContractOnlyModel
+    m = R.make_model(3, dense=True, table_scale=0.5, density_gain=20.0, log2_hashmap_size=14)
+    m_gpu = copy.deepcopy(m).cuda().train()
+    model = _ContractOnlyModel(m_gpu)
+    model.config.num_proposal_samples_per_ray, model.config.num_nerf_samples_per_ray = (64, 32), 16
+    _, _, o, d, target, _, cams = _setup_full(n_rays=64)
+
+    class _Bundle:
+        origins, directions, camera_indices = o.cuda(), d.cuda(), cams.cuda()[:, None]
+
+    class _DM:
+        def next_train(self, step):
+            return _Bundle(), {"image": target}
+
+    pipe = P.SIGNeRFPipeline.__new__(P.SIGNeRFPipeline)
+    pipe.datamanager, pipe._model = _DM(), model
+    pipe.enable_fused_training()
+    assert pipe._fused_step.trainer.counts == (64, 32, 16)
+    outputs, loss_dict, metrics = pipe.get_train_loss_dict(step=0)
+    assert set(loss_dict) == {"rgb_loss", "interlevel_loss", "distortion_loss"} and "distortion" in metrics
+    sum(loss_dict.values()).backward()
+    assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for n, p in m_gpu.named_parameters() if "scalings" not in n)
+    assert float(m_gpu.field.encoding.hash_table.grad.abs().max()) > 0 and float(m_gpu.proposal_networks[1].encoding.hash_table.grad.abs().max()) > 0
