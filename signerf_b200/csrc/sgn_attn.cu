@@ -691,17 +691,6 @@ k_cross_attention(const __half* __restrict__ q, long long ldq, const __half* __r
   __shared__ __align__(16) __half sQ2[2][kXaQ * kXaPitch];   // double-buffered query tiles (cp.async)
   const int head = blockIdx.y, img = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-  for (int c = tid; c < kXaKv * 8; c += 128) {
-    const int r = c >> 3, j = c & 7;
-    uint4 kv = zero, vv = zero;
-    if (r < T_kv) {
-      kv = *reinterpret_cast<const uint4*>(k + ((long long)img * T_kv + r) * ldk + head * kHeadDim + j * 8);
-      vv = *reinterpret_cast<const uint4*>(v + ((long long)img * T_kv + r) * ldv + head * kHeadDim + j * 8);
-    }
-    *reinterpret_cast<uint4*>(sK + r * kXaPitch + j * 8) = kv;
-    *reinterpret_cast<uint4*>(sV + r * kXaPitch + j * 8) = vv;
-  }
   const int q_begin = blockIdx.x * q_per_cta;
   const int q_end = min(T_q, q_begin + q_per_cta);
   const int g = lane >> 2, col0 = (lane & 3) * 2;
@@ -716,7 +705,20 @@ k_cross_attention(const __half* __restrict__ q, long long ldq, const __half* __r
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  load_q(q_begin, sQ2[0]);
+  load_q(q_begin, sQ2[0]);   // the first query tile is in flight while K / V of the head are staged
+  {
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    for (int c = tid; c < kXaKv * 8; c += 128) {
+      const int r = c >> 3, j = c & 7;
+      uint4 kv = zero, vv = zero;
+      if (r < T_kv) {
+        kv = *reinterpret_cast<const uint4*>(k + ((long long)img * T_kv + r) * ldk + head * kHeadDim + j * 8);
+        vv = *reinterpret_cast<const uint4*>(v + ((long long)img * T_kv + r) * ldv + head * kHeadDim + j * 8);
+      }
+      *reinterpret_cast<uint4*>(sK + r * kXaPitch + j * 8) = kv;
+      *reinterpret_cast<uint4*>(sV + r * kXaPitch + j * 8) = vv;
+    }
+  }
   int buf = 0;
   for (int q0 = q_begin; q0 < q_end; q0 += kXaQ, buf ^= 1) {
     asm volatile("cp.async.wait_group 0;" ::: "memory");

@@ -19,12 +19,19 @@ void host_flat_bins(int S, float near_p, float far_p, std::vector<float>& out);
 constexpr int kPWarps = 4;
 constexpr int kPThreads = kPWarps * 32;
 
+// Intermediate per-ray arrays of the cascade (proposal weights, cdf, the bins between the two proposal levels) live in
+// "slot" layout: ray slot t = tile * 32 + lane (the lane that marches the ray in every kernel here), element i of a
+// length-len array at ((t >> 5) * len + i) * 32 + (t & 31).  A warp that walks i in lock step then touches ONE 128-byte
+// line per access; the row-major [ray][len] layout cost 32 lines per access (8.2 ms per k_pdf_resample over a million
+// rays, 40 % of the cascade).  Slots of lanes outside a ragged image edge are computed like the clamped pixel and ignored.
+__device__ __forceinline__ int64_t slot_at(int64_t t, int len, int i) { return ((t >> 5) * len + i) * 32 + (t & 31); }
+
 struct PropParams {
   const PropDev* net;
   RaySource src;
   const float* bins;      // shared euclid edges [S+1] or null
-  const float* ray_bins;  // per-ray euclid edges [rays][S+1] or null
-  float* weights;         // out [rays][S]
+  const float* ray_bins;  // per-ray euclid edges, slot layout [slots][S+1], or null
+  float* weights;         // out, slot layout [slots][S]
   int V, H, W, S;
   int tiles_x, tiles_y, num_tiles;
 };
@@ -51,13 +58,12 @@ __global__ void __launch_bounds__(kPThreads) k_prop_weights(const __grid_constan
     y = min(y, p.H - 1);
     float ro[3], d[3];
     load_ray(p.src, v, x, y, ro, d);
-    size_t ray = ((size_t)v * p.H + y) * p.W + x;
-    const float* rb = kPerRayBins ? p.ray_bins + ray * (size_t)(p.S + 1) : nullptr;
-    float* wout = p.weights + ray * (size_t)p.S;
+    (void)valid;
+    const int64_t slot = (int64_t)tile * 32 + lane;
     float cum = 0.f;
-    float t0 = kPerRayBins ? __ldg(rb) : sbins[0];
+    float t0 = kPerRayBins ? __ldg(p.ray_bins + slot_at(slot, p.S + 1, 0)) : sbins[0];
     for (int i = 0; i < p.S; ++i) {
-      const float t1 = kPerRayBins ? __ldg(rb + i + 1) : sbins[i + 1];
+      const float t1 = kPerRayBins ? __ldg(p.ray_bins + slot_at(slot, p.S + 1, i + 1)) : sbins[i + 1];
       const float mid = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
       float px, py, pz;
       const bool sel = contract_to_unit(__fadd_rn(ro[0], __fmul_rn(d[0], mid)),
@@ -83,7 +89,7 @@ __global__ void __launch_bounds__(kPThreads) k_prop_weights(const __grid_constan
       float w = (1.f - expf(-dd)) * expf(-cum);
       cum += dd;
       if (w != w) w = 0.f;
-      if (valid) wout[i] = w;
+      p.weights[slot_at(slot, p.S, i)] = w;
       t0 = t1;
     }
   }
@@ -99,46 +105,68 @@ struct PdfParams {
   float* spacing_out;         // [rays][nb]
   float* euclid_out;          // [rays][nb]
   float s_near, s_far;
-  int64_t rays;
+  int64_t rays;               // rays (row-major layout) or ray slots (slot layout)
   int S, nb;
+  // slot layout only: where euclid_out goes.  0: slot layout (feeds the next proposal level); 1: row-major [ray][nb] of the
+  // image (what k_render_* read), for which the slot's pixel is decoded like in k_prop_weights
+  int euclid_row_major;
+  RaySource src;
+  int H, W, tiles_x, per_view;
 };
 
 // PDFSampler.generate_ray_samples (include_original=False): one thread per ray.  Eval: u = bin centres of the cdf axis;
 // training: u = linspace(0, 1 - 1/nb, nb) + rand((rays, 1)) / nb with the draws handed in.
+template <bool kSlot>
 __global__ void k_pdf_resample(const __grid_constant__ PdfParams p) {
   const float pad_hist = 0.01f, eps = 1e-5f;
   for (int64_t ray = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; ray < p.rays;
        ray += (int64_t)gridDim.x * blockDim.x) {
-    const float* w = p.weights + ray * p.S;
-    const float* sb = p.spacing_in + (p.spacing_per_ray ? ray * (int64_t)(p.S + 1) : 0);
-    float* cdf = p.cdf_scratch + ray * (int64_t)(p.S + 1);
+    auto at = [&](int len, int i) -> int64_t { return kSlot ? slot_at(ray, len, i) : ray * (int64_t)len + i; };
+    const float* w = p.weights;
+    const float* sb = p.spacing_in;
+    float* cdf = p.cdf_scratch;
+    int64_t out_ray = -1;   // row-major euclid output of the slot's pixel (-1: lane outside the image)
+    if (kSlot && p.euclid_row_major) {
+      const int tile = (int)(ray >> 5), lane = (int)(ray & 31);
+      const int v = tile / p.per_view, r = tile - v * p.per_view;
+      const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
+      int x, y;
+      tile_xy(p.src, tx, ty, lane, x, y);
+      if (x < p.W && y < p.H) out_ray = ((int64_t)v * p.H + y) * p.W + x;
+    }
     float sum = 0.f;
-    for (int i = 0; i < p.S; ++i) sum += __fadd_rn(w[i], pad_hist);
+    for (int i = 0; i < p.S; ++i) sum += __fadd_rn(w[at(p.S, i)], pad_hist);
     const float padding = fmaxf(eps - sum, 0.f);
     const float padw = __fdiv_rn(padding, (float)p.S);
     sum += padding;
     float run = 0.f;
-    cdf[0] = 0.f;
+    cdf[at(p.S + 1, 0)] = 0.f;
     for (int i = 0; i < p.S; ++i) {
-      float pdf = __fdiv_rn(__fadd_rn(__fadd_rn(w[i], pad_hist), padw), sum);
+      float pdf = __fdiv_rn(__fadd_rn(__fadd_rn(w[at(p.S, i)], pad_hist), padw), sum);
       run = __fadd_rn(run, pdf);
-      cdf[i + 1] = fminf(1.f, run);
+      cdf[at(p.S + 1, i + 1)] = fminf(1.f, run);
     }
     // searchsorted(cdf, u, side="right") by a forward merge: both sequences ascend.
     int idx = 0;
     const float shift = p.jitter ? __fdiv_rn(__ldg(p.jitter + ray), (float)p.nb) : 0.f;
     for (int j = 0; j < p.nb; ++j) {
       const float u = p.jitter ? __fadd_rn(__ldg(p.u + j), shift) : __ldg(p.u + j);
-      while (idx <= p.S && !(cdf[idx] > u)) ++idx;  // first idx with cdf[idx] > u, or S+1
+      while (idx <= p.S && !(cdf[at(p.S + 1, idx)] > u)) ++idx;  // first idx with cdf[idx] > u, or S+1
       const int below = min(max(idx - 1, 0), p.S), above = min(idx, p.S);
-      const float c0 = cdf[below], c1 = cdf[above];
-      const float b0 = __ldg(sb + below), b1 = __ldg(sb + above);
+      const float c0 = cdf[at(p.S + 1, below)], c1 = cdf[at(p.S + 1, above)];
+      const float b0 = p.spacing_per_ray ? __ldg(sb + at(p.S + 1, below)) : __ldg(sb + below);
+      const float b1 = p.spacing_per_ray ? __ldg(sb + at(p.S + 1, above)) : __ldg(sb + above);
       float t = __fdiv_rn(__fsub_rn(u, c0), __fsub_rn(c1, c0));
       if (t != t) t = 0.f;                  // nan_to_num(nan=0); +-inf fall to the clip below
       t = fminf(fmaxf(t, 0.f), 1.f);
       const float nbv = __fadd_rn(b0, __fmul_rn(t, __fsub_rn(b1, b0)));
-      p.spacing_out[ray * p.nb + j] = nbv;
-      p.euclid_out[ray * p.nb + j] = to_euclid(nbv, p.s_near, p.s_far);
+      p.spacing_out[at(p.nb, j)] = nbv;
+      const float e = to_euclid(nbv, p.s_near, p.s_far);
+      if (kSlot && p.euclid_row_major) {
+        if (out_ray >= 0) p.euclid_out[out_ray * p.nb + j] = e;
+      } else {
+        p.euclid_out[at(p.nb, j)] = e;
+      }
     }
   }
 }
@@ -169,8 +197,8 @@ int launch_pdf_resample(const float* weights, const float* spacing_in, const flo
   PdfParams q;
   q.weights = weights; q.spacing_in = spacing_in; q.spacing_per_ray = 1; q.u = u; q.jitter = jitter;
   q.cdf_scratch = cdf_scratch; q.spacing_out = spacing_out; q.euclid_out = euclid_out;
-  q.s_near = s_near; q.s_far = s_far; q.rays = rays; q.S = S; q.nb = nb;
-  k_pdf_resample<<<(int)std::max<int64_t>(1, std::min<int64_t>((rays + 127) / 128, (int64_t)sm_count() * 16)), 128, 0, st>>>(q);
+  q.s_near = s_near; q.s_far = s_far; q.rays = rays; q.S = S; q.nb = nb; q.euclid_row_major = 0;
+  k_pdf_resample<false><<<(int)std::max<int64_t>(1, std::min<int64_t>((rays + 127) / 128, (int64_t)sm_count() * 16)), 128, 0, st>>>(q);
   SGN_LAUNCH_CHECK();
   return SGN_OK;
 }
@@ -211,18 +239,21 @@ int render_cascade(const SgnField* f, const RaySource& src, int V, int H, int W,
 
   const size_t rays_per_view = (size_t)H * W;
   const int views_per_chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)V, ((size_t)1 << 20) / rays_per_view));
-  const size_t max_rays = rays_per_view * views_per_chunk;
   const int Smax = std::max(S0, S1);
+  const int tw0 = 1 << src.tw_log2, th0 = 32 >> src.tw_log2;
+  const size_t slots_per_view = (size_t)((W + tw0 - 1) / tw0) * ((H + th0 - 1) / th0) * 32;   // >= rays per view (ragged edges)
+  const size_t max_slots = slots_per_view * views_per_chunk;
+  const size_t max_rays = rays_per_view * views_per_chunk;
 
   AsyncBuf small(st), wbuf(st), cdfbuf(st), sp1(st), eu1(st), sp2(st), eu2(st);
   const size_t small_floats = (size_t)(S0 + 1) * 2 + (S1 + 1) + (S2 + 1);
   SGN_CUDA(small.alloc(small_floats * 4));
-  SGN_CUDA(wbuf.alloc(max_rays * Smax * 4));
-  SGN_CUDA(cdfbuf.alloc(max_rays * (Smax + 1) * 4));
-  SGN_CUDA(sp1.alloc(max_rays * (S1 + 1) * 4));
-  SGN_CUDA(eu1.alloc(max_rays * (S1 + 1) * 4));
-  SGN_CUDA(sp2.alloc(max_rays * (S2 + 1) * 4));
-  SGN_CUDA(eu2.alloc(max_rays * (S2 + 1) * 4));
+  SGN_CUDA(wbuf.alloc(max_slots * Smax * 4));
+  SGN_CUDA(cdfbuf.alloc(max_slots * (Smax + 1) * 4));
+  SGN_CUDA(sp1.alloc(max_slots * (S1 + 1) * 4));
+  SGN_CUDA(eu1.alloc(max_slots * (S1 + 1) * 4));
+  SGN_CUDA(sp2.alloc(max_slots * (S2 + 1) * 4));
+  SGN_CUDA(eu2.alloc(max_rays * (S2 + 1) * 4));     // the final bins are row-major: k_render_* read them by pixel
   float* d_e0 = small.as<float>();
   float* d_sp0 = d_e0 + (S0 + 1);
   float* d_u1 = d_sp0 + (S0 + 1);
@@ -248,7 +279,9 @@ int render_cascade(const SgnField* f, const RaySource& src, int V, int H, int W,
     pp.tiles_y = (H + th - 1) / th;
     pp.num_tiles = nv * pp.tiles_x * pp.tiles_y;
     const int pblocks = std::min((pp.num_tiles + kPWarps - 1) / kPWarps, nsm * 8);
-    const int rblocks = (int)std::min<int64_t>((rays + 127) / 128, (int64_t)nsm * 16);
+    const int64_t slots = (int64_t)pp.num_tiles * 32;
+    const int rblocks = (int)std::min<int64_t>((slots + 127) / 128, (int64_t)nsm * 16);
+    (void)rays;
     // stage 0: shared bins
     pp.net = f->d_prop[0]; pp.bins = d_e0; pp.ray_bins = nullptr; pp.S = S0;
     k_prop_weights<false><<<pblocks, kPThreads, (S0 + 1) * 4, st>>>(pp);
@@ -256,8 +289,9 @@ int render_cascade(const SgnField* f, const RaySource& src, int V, int H, int W,
     PdfParams q;
     q.weights = wbuf.as<float>(); q.spacing_in = d_sp0; q.spacing_per_ray = 0; q.u = d_u1; q.jitter = nullptr;
     q.cdf_scratch = cdfbuf.as<float>(); q.spacing_out = sp1.as<float>(); q.euclid_out = eu1.as<float>();
-    q.s_near = s_near; q.s_far = s_far; q.rays = rays; q.S = S0; q.nb = S1 + 1;
-    k_pdf_resample<<<rblocks, 128, 0, st>>>(q);
+    q.s_near = s_near; q.s_far = s_far; q.rays = slots; q.S = S0; q.nb = S1 + 1;
+    q.euclid_row_major = 0; q.src = pp.src; q.H = H; q.W = W; q.tiles_x = pp.tiles_x; q.per_view = pp.tiles_x * pp.tiles_y;
+    k_pdf_resample<true><<<rblocks, 128, 0, st>>>(q);
     SGN_LAUNCH_CHECK();
     // stage 1: per-ray bins
     pp.net = f->d_prop[1]; pp.bins = nullptr; pp.ray_bins = eu1.as<float>(); pp.S = S1;
@@ -265,7 +299,8 @@ int render_cascade(const SgnField* f, const RaySource& src, int V, int H, int W,
     SGN_LAUNCH_CHECK();
     q.spacing_in = sp1.as<float>(); q.spacing_per_ray = 1; q.u = d_u2;
     q.spacing_out = sp2.as<float>(); q.euclid_out = eu2.as<float>(); q.S = S1; q.nb = S2 + 1;
-    k_pdf_resample<<<rblocks, 128, 0, st>>>(q);
+    q.euclid_row_major = 1;
+    k_pdf_resample<true><<<rblocks, 128, 0, st>>>(q);
     SGN_LAUNCH_CHECK();
     // main field on the final per-ray bins
     const size_t off = (size_t)v0 * rays_per_view;
