@@ -39,10 +39,14 @@ struct PropParams {
 // Proposal density + RaySamples.get_weights for every sample of every ray of the chunk.
 template <bool kPerRayBins>
 __global__ void __launch_bounds__(kPThreads) k_prop_weights(const __grid_constant__ PropParams p) {
-  __shared__ PropDev net;
+  __shared__ __align__(16) PropDev net;
+  __shared__ __align__(16) float wT[10 * 16];   // hidden layer's weights as [k][n]
+  __shared__ __align__(16) float sb0[16], sw1[16];   // 16-byte aligned copies (PropDev's arrays sit at odd multiples of 8)
   extern __shared__ float sbins[];
   for (int i = threadIdx.x; i < (int)(sizeof(PropDev) / 4); i += kPThreads)
     reinterpret_cast<uint32_t*>(&net)[i] = reinterpret_cast<const uint32_t*>(p.net)[i];
+  for (int i = threadIdx.x; i < 160; i += kPThreads) wT[(i % 10) * 16 + i / 10] = p.net->w0[i];
+  if (threadIdx.x < 16) sb0[threadIdx.x] = p.net->b0[threadIdx.x], sw1[threadIdx.x] = p.net->w1[threadIdx.x];
   if (!kPerRayBins)
     for (int i = threadIdx.x; i <= p.S; i += kPThreads) sbins[i] = p.bins[i];
   __syncthreads();
@@ -76,13 +80,29 @@ __global__ void __launch_bounds__(kPThreads) k_prop_weights(const __grid_constan
         feat[2 * l] = f.x;
         feat[2 * l + 1] = f.y;
       }
+      // hidden layer from the [k][n] copy of the weights: one LDS.128 feeds four neurons (193 scalar loads per sample were
+      // as expensive as the 40 gathers); every neuron still sums k = 0..9 in order and the output sums n = 0..15 in order
+      float a[16];
+#pragma unroll
+      for (int n4 = 0; n4 < 4; ++n4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(sb0 + 4 * n4);
+        a[4 * n4] = b4.x, a[4 * n4 + 1] = b4.y, a[4 * n4 + 2] = b4.z, a[4 * n4 + 3] = b4.w;
+      }
+#pragma unroll
+      for (int k = 0; k < 10; ++k) {
+#pragma unroll
+        for (int n4 = 0; n4 < 4; ++n4) {
+          const float4 w4 = *reinterpret_cast<const float4*>(wT + k * 16 + 4 * n4);
+          a[4 * n4] = fmaf(w4.x, feat[k], a[4 * n4]), a[4 * n4 + 1] = fmaf(w4.y, feat[k], a[4 * n4 + 1]);
+          a[4 * n4 + 2] = fmaf(w4.z, feat[k], a[4 * n4 + 2]), a[4 * n4 + 3] = fmaf(w4.w, feat[k], a[4 * n4 + 3]);
+        }
+      }
       float out = net.b1;
 #pragma unroll
-      for (int n = 0; n < 16; ++n) {
-        float a = net.b0[n];
-#pragma unroll
-        for (int k = 0; k < 10; ++k) a = fmaf(net.w0[n * 10 + k], feat[k], a);
-        out = fmaf(net.w1[n], fmaxf(a, 0.f), out);
+      for (int n4 = 0; n4 < 4; ++n4) {
+        const float4 v4 = *reinterpret_cast<const float4*>(sw1 + 4 * n4);
+        out = fmaf(v4.x, fmaxf(a[4 * n4], 0.f), out), out = fmaf(v4.y, fmaxf(a[4 * n4 + 1], 0.f), out);
+        out = fmaf(v4.z, fmaxf(a[4 * n4 + 2], 0.f), out), out = fmaf(v4.w, fmaxf(a[4 * n4 + 3], 0.f), out);
       }
       const float sigma = sel ? net.avg_density * expf(out) : 0.f;
       const float dd = __fsub_rn(t1, t0) * sigma;

@@ -39,6 +39,7 @@ struct RenderParams {
   // neighbouring bin are appended here and re-marched with the fp32 density by k_refine_depth
   uint32_t* refine_list;
   uint32_t* refine_count;
+  uint32_t* refine_flags;   // one bit per pixel, set by the march; k_refine_compact turns it into the (locally sorted) list
   float refine_delta;
 };
 
@@ -71,7 +72,7 @@ __device__ __forceinline__ void store_pixel(const RenderParams& p, const TileCoo
   p.rgb[pix * 3 + 2] = o[2];
   p.depth[pix] = d;
   if (p.acc) p.acc[pix] = comp.acc;
-  if (p.refine_list && comp.margin < p.refine_delta) p.refine_list[atomicAdd(p.refine_count, 1u)] = (uint32_t)pix;
+  if (p.refine_flags && comp.margin < p.refine_delta) atomicOr(p.refine_flags + (pix >> 5), 1u << (pix & 31));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -207,6 +208,45 @@ struct DensityF32 {
   float avg;
 };
 
+// Flag bitmap -> list of pixel ids.  Every block turns 1 024 words (32 768 consecutive pixels) into one contiguous,
+// ascending run of the list, so the 32 lanes of a k_refine_depth warp re-march pixels that are neighbours in the image:
+// their gathers share cache lines.  (Appending from the march with one atomic per ray left the list in random order - every
+// gather its own 32-byte sector: 3.7 ms per million rays in cascade mode, where ~10 % of the rays are listed.)
+__global__ void __launch_bounds__(1024) k_refine_compact(const uint32_t* __restrict__ flags, uint32_t num_words,
+                                                          uint32_t* __restrict__ count, uint32_t* __restrict__ list) {
+  __shared__ uint32_t warp_sum[32];
+  __shared__ uint32_t base;
+  const uint32_t w = blockIdx.x * 1024u + threadIdx.x;
+  uint32_t bits = w < num_words ? flags[w] : 0u;
+  const uint32_t cnt = __popc(bits);
+  uint32_t incl = cnt;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += u;
+  }
+  if (lane == 31) warp_sum[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t v = warp_sum[lane], t = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t u = __shfl_up_sync(0xffffffffu, t, o);
+      if (lane >= o) t += u;
+    }
+    warp_sum[lane] = t - v;                       // exclusive prefix of the warps
+    if (lane == 31) base = t ? atomicAdd(count, t) : 0u;
+  }
+  __syncthreads();
+  uint32_t at = base + warp_sum[wid] + incl - cnt;
+  while (bits) {
+    const int b = __ffs(bits) - 1;
+    bits &= bits - 1;
+    list[at++] = (w << 5) + (uint32_t)b;
+  }
+}
+
 template <bool kPerRayBins>
 __global__ void __launch_bounds__(kThreads) k_refine_depth(const __grid_constant__ RenderParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -251,12 +291,25 @@ __global__ void __launch_bounds__(kThreads) k_refine_depth(const __grid_constant
           feat[2 * l] = f.x;
           feat[2 * l + 1] = f.y;
         }
+        // four neurons at a time, weights as LDS.128 (one load per four FMAs instead of one per FMA); every neuron's sum and
+        // the logit keep k_render_f32's order of operations, so the result is bit for bit the fp32 path's
         float logit = sw->b1;
-        for (int nn = 0; nn < 64; ++nn) {
-          float a = sw->b0[nn];
+#pragma unroll 1
+        for (int nn = 0; nn < 64; nn += 4) {
+          float a0 = sw->b0[nn], a1 = sw->b0[nn + 1], a2 = sw->b0[nn + 2], a3 = sw->b0[nn + 3];
+          const float4* r0 = reinterpret_cast<const float4*>(sw->w0 + nn * 32);
 #pragma unroll
-          for (int k = 0; k < 32; ++k) a = fmaf(sw->w0[nn * 32 + k], feat[k], a);
-          logit = fmaf(sw->w1[nn], fmaxf(a, 0.f), logit);
+          for (int k = 0; k < 8; ++k) {
+            const float4 u0 = r0[k], u1 = r0[8 + k], u2 = r0[16 + k], u3 = r0[24 + k];
+            a0 = fmaf(u0.x, feat[4 * k], a0), a0 = fmaf(u0.y, feat[4 * k + 1], a0), a0 = fmaf(u0.z, feat[4 * k + 2], a0), a0 = fmaf(u0.w, feat[4 * k + 3], a0);
+            a1 = fmaf(u1.x, feat[4 * k], a1), a1 = fmaf(u1.y, feat[4 * k + 1], a1), a1 = fmaf(u1.z, feat[4 * k + 2], a1), a1 = fmaf(u1.w, feat[4 * k + 3], a1);
+            a2 = fmaf(u2.x, feat[4 * k], a2), a2 = fmaf(u2.y, feat[4 * k + 1], a2), a2 = fmaf(u2.z, feat[4 * k + 2], a2), a2 = fmaf(u2.w, feat[4 * k + 3], a2);
+            a3 = fmaf(u3.x, feat[4 * k], a3), a3 = fmaf(u3.y, feat[4 * k + 1], a3), a3 = fmaf(u3.z, feat[4 * k + 2], a3), a3 = fmaf(u3.w, feat[4 * k + 3], a3);
+          }
+          logit = fmaf(sw->w1[nn], fmaxf(a0, 0.f), logit);
+          logit = fmaf(sw->w1[nn + 1], fmaxf(a1, 0.f), logit);
+          logit = fmaf(sw->w1[nn + 2], fmaxf(a2, 0.f), logit);
+          logit = fmaf(sw->w1[nn + 3], fmaxf(a3, 0.f), logit);
         }
         sigma = sw->avg * expf(logit);
       }
@@ -471,17 +524,20 @@ int launch_render(const SgnField* f, const RaySource& src, int V, int H, int W, 
   p.tiles_y = (H + th - 1) / th;
   p.num_tiles = V * p.tiles_x * p.tiles_y;
   p.rgb = d_rgb; p.depth = d_depth; p.acc = d_acc;
-  p.refine_list = nullptr; p.refine_count = nullptr; p.refine_delta = 0.f;
+  p.refine_list = nullptr; p.refine_count = nullptr; p.refine_flags = nullptr; p.refine_delta = 0.f;
   const bool per_ray = d_ray_bins != nullptr;
   const int blocks_needed = (p.num_tiles + kWarps - 1) / kWarps;
   if (mlp_mode == SGN_MLP_FP16_MMA) {
     uint32_t* d_list = nullptr;
     const size_t npix = (size_t)V * H * W;
+    const size_t nwords = (npix + 31) / 32;
     if (g_refine_depth && npix < ((size_t)1 << 32)) {
-      SGN_CUDA(scratch_alloc(&d_list, (npix + 1) * sizeof(uint32_t), st));
-      SGN_CUDA(cudaMemsetAsync(d_list, 0, sizeof(uint32_t), st));
+      SGN_CUDA(scratch_alloc(&d_list, (npix + 1 + nwords) * sizeof(uint32_t), st));   // count | list | flag bitmap
       p.refine_count = d_list;
       p.refine_list = d_list + 1;
+      p.refine_flags = d_list + 1 + npix;
+      SGN_CUDA(cudaMemsetAsync(d_list, 0, sizeof(uint32_t), st));
+      SGN_CUDA(cudaMemsetAsync(p.refine_flags, 0, nwords * sizeof(uint32_t), st));
       p.refine_delta = g_refine_delta;
     }
     struct FreeList {
@@ -500,6 +556,8 @@ int launch_render(const SgnField* f, const RaySource& src, int V, int H, int W, 
       k_render_mma<false><<<grid, kThreads, smem, st>>>(p);
     }
     if (d_list) {
+      SGN_LAUNCH_CHECK();
+      k_refine_compact<<<(unsigned)((nwords + 1023) / 1024), 1024, 0, st>>>(p.refine_flags, (uint32_t)nwords, p.refine_count, p.refine_list);
       SGN_LAUNCH_CHECK();
       const size_t rsmem = sizeof(DensityF32) + (per_ray ? 0 : (size_t)(S + 1) * 4);
       const int rgrid = std::min((int)((npix + kThreads - 1) / kThreads), sm_count() * 8);
