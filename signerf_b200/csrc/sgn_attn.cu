@@ -34,6 +34,9 @@ constexpr int kQTileBytes = 128 * 64 * 2;  // one [128 x 64] fp16 tile, 128-B ro
 // Shape of one CTA: kGroups query tiles of 128 rows (one softmax warpgroup each) share every K / V tile of kKv keys.
 //   <2, 128>: S 2x128 + O 2x64 + P 2x64 = 512 TMEM columns, two softmax warps per SM sub-partition taking MUFU turns;
 //             S_x is released as soon as it is in registers, so Q_x K_{j+1}^T runs under the exponentials of tile j
+//   <1, 128>: ONE softmax group per CTA and two CTAs per SM (256 TMEM columns, two K / V stages, 81 KB each): the two
+//             query tiles of an SM no longer share K / V loads, barriers or the MMA-issuing thread (sgn_set_option
+//             "attn_shape" 2; measured against the default in DESIGN.md)
 //   <3, 96> : three free-running softmax warps per sub-partition.  S 3x96 + O 3x64 = 480 columns only fit with P_x
 //             written over the first 48 columns of S_x (each thread overwrites its own row after reading it), so
 //             Q_x K_{j+1}^T follows P_x V_j on the tensor pipe and a group idles through both - while the other two keep
@@ -46,12 +49,14 @@ struct AttnShape {
   static constexpr int kThreads = kRegMove ? 512 : (2 + 4 * kGroups) * 32;
   static constexpr int kQPerCta = kGroups * kQTile;
   static constexpr int kKvBytes = kKv * 64 * 2;
-  static constexpr int kStages = 4;
+  static constexpr int kStages = kGroups == 1 ? 2 : 4;   // <1, 128>: two CTAs per SM, 81 KB each
+  static constexpr int kCtasPerSm = kGroups == 1 ? 2 : 1;
   static constexpr size_t kSmem = 1024 + (size_t)kQTileBytes * kGroups + (size_t)2 * kStages * kKvBytes + 256;
   // TMEM column map
   static constexpr int kColS = 0, kColP = kAlias ? 0 : kGroups * kKv, kStrideP = kAlias ? kKv : kKv / 2;
   static constexpr int kColO = kAlias ? kGroups * kKv : kColP + kGroups * kKv / 2;
   static_assert(kColO + kGroups * kHeadDim <= 512, "tensor memory");
+  static constexpr int kTmemCols = kColO + kGroups * kHeadDim <= 256 ? 256 : 512;   // allocation (a power of two)
 };
 
 struct AttnParams {
@@ -122,7 +127,7 @@ __device__ long long g_trace[32 * 256];   // [event + 16 * query tile][key tile]
 // sgn_set_option "attn_variant" (bit flags): 1 = the MMA issuer follows the static event order with blocking waits
 // instead of polling, 2 = producer / issuer are the two highest warps of the CTA instead of the two lowest
 int g_attn_variant = 3;
-int g_attn_shape = 0;     // sgn_set_option "attn_shape": 0 = two query tiles x 128-key tiles (default), 1 = three x 96-key tiles with P aliased over S
+int g_attn_shape = 0;     // sgn_set_option "attn_shape": 0 = two query tiles x 128-key tiles (default), 1 = three x 96-key tiles with P aliased over S, 2 = one query tile per CTA, two CTAs per SM
 int g_attn_idle_ns = 0;   // sgn_set_option "attn_idle_ns"
 int g_attn_split = 1;     // sgn_set_option "attn_split": 0 = never split the tail items over the keys
 
@@ -141,7 +146,7 @@ __device__ __forceinline__ void decode_item(const AttnParams& p, int cta, int& i
 // as sixteen (128).  The three-group shape therefore launches sixteen warps - softmax warps 0-11, producer 12, issuer 13,
 // two idle - and moves registers with setmaxnreg: the last warpgroup keeps 56 per thread, the softmax warpgroups get 152.
 template <int kFlags, int kGroups, int kKv>
-__global__ void __launch_bounds__(AttnShape<kGroups, kKv>::kThreads, 1)
+__global__ void __launch_bounds__(AttnShape<kGroups, kKv>::kThreads, AttnShape<kGroups, kKv>::kCtasPerSm)
 k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   using Sh = AttnShape<kGroups, kKv>;
@@ -192,7 +197,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
     tc::mbar_fence_init();
   }
-  if (warp == kWarpIssue) tc::tmem_alloc(tmem_slot, 512);
+  if (warp == kWarpIssue) tc::tmem_alloc(tmem_slot, Sh::kTmemCols);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -648,7 +653,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   __syncthreads();
   if (warp == kWarpIssue) {
     __syncwarp();
-    tc::tmem_dealloc(tmem_base, 512);
+    tc::tmem_dealloc(tmem_base, Sh::kTmemCols);
   }
 }
 
@@ -834,7 +839,7 @@ static size_t split_workspace_bytes(int tail_items, int split, int rows_per_cta)
 }
 // rows per CTA / keys per tile of the configured shape (sgn_set_option "attn_shape")
 static void shape_dims(int* rows_per_cta, int* kv_tile) {
-  *rows_per_cta = g_attn_shape == 1 ? AttnShape<3, 96>::kQPerCta : AttnShape<2, 128>::kQPerCta;
+  *rows_per_cta = g_attn_shape == 1 ? AttnShape<3, 96>::kQPerCta : g_attn_shape == 2 ? AttnShape<1, 128>::kQPerCta : AttnShape<2, 128>::kQPerCta;
   *kv_tile = g_attn_shape == 1 ? 96 : 128;
 }
 
@@ -865,18 +870,19 @@ static int attention_impl(const void* d_q, int64_t ldq, const void* d_k, int64_t
     return SGN_OK;
   }
   using Kern = void (*)(CUtensorMap, CUtensorMap, CUtensorMap, AttnParams);
-  static const Kern kerns[2][4] = {
+  static const Kern kerns[3][4] = {
       {k_attention_tc<0, 2, 128>, k_attention_tc<1, 2, 128>, k_attention_tc<2, 2, 128>, k_attention_tc<3, 2, 128>},
-      {k_attention_tc<0, 3, 96>, k_attention_tc<1, 3, 96>, k_attention_tc<2, 3, 96>, k_attention_tc<3, 3, 96>}};
-  static const size_t smem_of[2] = {AttnShape<2, 128>::kSmem, AttnShape<3, 96>::kSmem};
-  static const int threads_of[2] = {AttnShape<2, 128>::kThreads, AttnShape<3, 96>::kThreads};
+      {k_attention_tc<0, 3, 96>, k_attention_tc<1, 3, 96>, k_attention_tc<2, 3, 96>, k_attention_tc<3, 3, 96>},
+      {k_attention_tc<0, 1, 128>, k_attention_tc<1, 1, 128>, k_attention_tc<2, 1, 128>, k_attention_tc<3, 1, 128>}};
+  static const size_t smem_of[3] = {AttnShape<2, 128>::kSmem, AttnShape<3, 96>::kSmem, AttnShape<1, 128>::kSmem};
+  static const int threads_of[3] = {AttnShape<2, 128>::kThreads, AttnShape<3, 96>::kThreads, AttnShape<1, 128>::kThreads};
   static bool attr_set = false;
   if (!attr_set) {
-    for (int sh = 0; sh < 2; ++sh)
+    for (int sh = 0; sh < 3; ++sh)
       for (Kern k : kerns[sh]) SGN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of[sh]));
     attr_set = true;
   }
-  const int shape = g_attn_shape == 1 ? 1 : 0;
+  const int shape = g_attn_shape == 1 ? 1 : g_attn_shape == 2 ? 2 : 0;
   int rows_per_cta, kv_tile;
   shape_dims(&rows_per_cta, &kv_tile);
   CUtensorMap tmQ, tmK, tmV;
@@ -902,7 +908,7 @@ static int attention_impl(const void* d_q, int64_t ldq, const void* d_k, int64_t
   p.n_full = items, p.split = 1;
   p.part = nullptr, p.count = nullptr;
   if (d_ws) {   // key-range split of the tail items needs the caller's workspace
-    plan_split(items, p.n_kv_tiles, sm_count(), &p.n_full, &p.split);
+    plan_split(items, p.n_kv_tiles, sm_count() * (g_attn_shape == 2 ? 2 : 1), &p.n_full, &p.split);
     if (p.split > 1) {
       const int tail = items - p.n_full;
       const size_t need = split_workspace_bytes(tail, p.split, rows_per_cta);
@@ -928,7 +934,7 @@ extern "C" int64_t sgn_attention_workspace_bytes(int B, int heads, int T_q, int 
   shape_dims(&rows_per_cta, &kv_tile);
   const int n_qt = (T_q + rows_per_cta - 1) / rows_per_cta, items = n_qt * heads * B;
   int n_full, split;
-  plan_split(items, (T_kv + kv_tile - 1) / kv_tile, sm_count(), &n_full, &split);
+  plan_split(items, (T_kv + kv_tile - 1) / kv_tile, sm_count() * (g_attn_shape == 2 ? 2 : 1), &n_full, &split);
   return split > 1 ? (int64_t)split_workspace_bytes(items - n_full, split, rows_per_cta) : 0;
 }
 

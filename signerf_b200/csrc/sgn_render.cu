@@ -780,7 +780,7 @@ extern "C" int sgn_set_option(const char* name, int value) {
     return SGN_OK;
   }
   if (n == "attn_shape") {
-    SGN_CHECK_ARG(value == 0 || value == 1, "attn_shape must be 0 (2 x 128 rows, 128-key tiles) or 1 (3 x 128 rows, 64-key tiles)");
+    SGN_CHECK_ARG(value >= 0 && value <= 2, "attn_shape must be 0 (2 x 128 rows, 128-key tiles), 1 (3 x 128 rows, 96-key tiles) or 2 (128 rows, two CTAs per SM)");
     sgn::g_attn_shape = value;
     return SGN_OK;
   }
