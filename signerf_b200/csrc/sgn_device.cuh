@@ -157,12 +157,15 @@ __device__ __forceinline__ LevelCoords level_coords(float res, float px, float p
   L.ox = __fsub_rn(qx, fx);
   L.oy = __fsub_rn(qy, fy);
   L.oz = __fsub_rn(qz, fz);
-  L.xf = (uint32_t)(int)fx;
-  L.xc = (uint32_t)(int)ceilf(qx);
-  L.yf = (uint32_t)(int)fy * kPrimeY;
-  L.yc = (uint32_t)(int)ceilf(qy) * kPrimeY;
-  L.zf = (uint32_t)(int)fz * kPrimeZ;
-  L.zc = (uint32_t)(int)ceilf(qz) * kPrimeZ;
+  // ceil(q) = floor(q) + (q > floor(q)) for the non-negative coordinates of the unit cube: an integer add instead of a second
+  // round + convert pair per axis (both run on the quarter-rate XU pipe: 96 of K1's 192 conversions per sample)
+  const uint32_t ix = (uint32_t)(int)fx, iy = (uint32_t)(int)fy, iz = (uint32_t)(int)fz;
+  L.xf = ix;
+  L.xc = ix + (L.ox > 0.f ? 1u : 0u);
+  L.yf = iy * kPrimeY;
+  L.yc = (iy + (L.oy > 0.f ? 1u : 0u)) * kPrimeY;
+  L.zf = iz * kPrimeZ;
+  L.zc = (iz + (L.oz > 0.f ? 1u : 0u)) * kPrimeZ;
   return L;
 }
 
