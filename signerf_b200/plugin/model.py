@@ -54,6 +54,20 @@ class FusedNerfactoGraph:
         out = self.render_cameras(as_camera_batch(camera_ray_bundle))
         return {k: v[0] for k, v in out.items()}
 
+    @classmethod
+    def from_checkpoint(cls, path, device="cuda", **kw):
+        """A nerfstudio checkpoint file (`step-%09d.ckpt`, signerf_trainer.py:278-306: {"step", "pipeline", "optimizers", ...}
+        with the model under `pipeline["_model.*"]`, DDP's `module.` prefix possibly in front) -> fused renderer.  `kw` as
+        `from_state_dict`; the per-image appearance table stays in (eval uses its mean)."""
+        ckpt = torch.load(str(path), map_location="cpu", weights_only=False)
+        pipe = ckpt["pipeline"] if isinstance(ckpt, dict) and "pipeline" in ckpt else ckpt
+        model = {k[len("_model."):]: v for k, v in pipe.items() if k.startswith("_model.")}
+        if model and all(k.startswith("module.") for k in model):
+            model = {k[len("module."):]: v for k, v in model.items()}
+        if not model:
+            raise KeyError("no `_model.` tensors in the checkpoint's pipeline state")
+        return cls.from_state_dict(model, device=device, **kw)
+
     # nerfacto checkpoint -> field (names per SURVEY §8c; torch-fallback `implementation="torch"` checkpoints)
     @classmethod
     def from_state_dict(cls, sd: Mapping[str, Tensor], device="cuda", num_train_data: Optional[int] = None,

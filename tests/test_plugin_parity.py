@@ -126,6 +126,25 @@ def test_graph_from_nerfacto_state_dict(style):
     assert P.FusedNerfactoGraph.from_state_dict(sd_np, allow_flat=True).render_opts.mode == "flat"
 
 
+def test_graph_from_nerfstudio_checkpoint_file(tmp_path):
+    """FusedNerfactoGraph.from_checkpoint reads the file nerfstudio's trainer writes ({"step", "pipeline": {"_model.*"}})."""
+    m = R.make_model(0, dense=True, table_scale=0.5, density_gain=20.0)
+    model = _ContractOnlyModel(m)
+    pipe = {"_model.module." + k: v.detach().clone() for k, v in model.state_dict().items()}     # as DDP saves it
+    pipe["datamanager.train_camera_optimizer.pose_adjustment"] = torch.zeros(3, 6)
+    path = tmp_path / "step-000030000.ckpt"
+    torch.save({"step": 30000, "pipeline": pipe, "optimizers": {}}, path)
+    graph = P.FusedNerfactoGraph.from_checkpoint(path, average_init_density=m.field.average_init_density)
+    direct = P.FusedNerfactoGraph(field_from_oracle(m))
+    c2w, _ = ring_cameras(2, 24, 16)
+    cam = P.CameraBatch(c2w, 24.0, 24.0, 12.0, 8.0, 24, 16)
+    o1, o2 = graph.render_cameras(cam), direct.render_cameras(cam)
+    assert torch.equal(o1["rgb"], o2["rgb"]) and torch.equal(o1["depth"], o2["depth"])
+    torch.save({"pipeline": {"datamanager.x": torch.zeros(1)}}, path)
+    with pytest.raises(KeyError, match="_model"):
+        P.FusedNerfactoGraph.from_checkpoint(path)
+
+
 class _ContractOnlyModel(torch.nn.Module):
     """What the reference's `graph` promises and nothing more (datasetgenerator.py:691-701): an nn.Module with nerfacto's
     parameters, `render_aabb`, `device`, `config`, and a `get_outputs_for_camera_ray_bundle` that must never be needed."""
