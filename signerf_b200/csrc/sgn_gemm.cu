@@ -240,6 +240,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
   __syncthreads();
   if (kCluster > 1) tc::cluster_sync_all();  // peer barriers initialised before any remote arrive / completion
   tc::tc_fence_after();
+  // Programmatic dependent launch (launch_gemm_c): everything above - tensor-map prefetch, barrier init, TMEM allocation,
+  // the cluster hand-shake - ran while the previous kernel on the stream was still draining its last CTAs; nothing that
+  // kernel wrote is read, and nothing is written, before this point.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t cta_rank = kCluster > 1 ? tc::cluster_ctarank() : 0;
   // work unit = kCluster vertically adjacent M tiles x one N tile; M tiles past the end are computed on zero-filled
@@ -563,6 +567,11 @@ static int pick_cluster(const GemmParams& p) {
   return p.num_m_tiles >= 2 ? 2 : 1;
 }
 
+static const int g_gemm_pdl = [] {
+  const char* e = getenv("SGN_GEMM_PDL");
+  return e == nullptr || atoi(e) != 0;
+}();
+
 template <int kCluster, int kStages, int kEpi>
 static int launch_gemm_c(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmBt, const GemmParams& p,
                          cudaStream_t st) {
@@ -575,10 +584,15 @@ static int launch_gemm_c(const CUtensorMap& tmA, const CUtensorMap& tmB, const C
   const int grid = std::min(p.total_items, sm_count() / kCluster) * kCluster;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kGemmThreads), cfg.dynamicSmemBytes = smem, cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = kCluster, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr, cfg.numAttrs = 1;
+  // programmatic dependent launch: the GEMM's CTAs may be scheduled (and run their prologue up to griddepcontrol.wait) as
+  // soon as the previous kernel's CTAs leave the SMs, instead of after its completion + a launch latency (690 GEMM launches
+  // per UNet step).  SGN_GEMM_PDL=0 restores the plain stream order.
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = g_gemm_pdl ? 2 : 1;
   SGN_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tc<kCluster, kStages, kEpi>, tmA, tmB, tmBt, p));
   SGN_LAUNCH_CHECK();
   return SGN_OK;
