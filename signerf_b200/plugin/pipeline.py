@@ -151,6 +151,18 @@ class SIGNeRFPipeline(VanillaPipeline):
             return super().get_train_loss_dict(step)
         ray_bundle, batch = self.datamanager.next_train(step)
         cams = ray_bundle.camera_indices.reshape(-1).to(dtype=__import__("torch").int32)
-        loss_dict = fused.loss_dict(ray_bundle.origins.reshape(-1, 3), ray_bundle.directions.reshape(-1, 3),
-                                    batch["image"].to(ray_bundle.origins.device)[..., :3], cams)
+        image = batch["image"].to(ray_bundle.origins.device)[..., :3]
+        # the LPIPS term of signerf.py:49-60 stays the MODEL's own module (torchmetrics' pretrained network, a host-side torch
+        # term): it sees the rendered rgb as patches and its gradient joins the CUDA backward through `extra_loss`
+        extra, cfg = None, getattr(self.model, "config", None)
+        if getattr(cfg, "use_lpips", False) and getattr(self.model, "lpips", None) is not None:
+            ps, mult, lpips = int(getattr(cfg, "patch_size", 32)), float(getattr(cfg, "lpips_loss_mult", 1.0)), self.model.lpips
+
+            def patches(t):
+                return (t.reshape(-1, ps, ps, 3).permute(0, 3, 1, 2) * 2 - 1).clamp(-1, 1)
+
+            gt = patches(image.reshape(-1, 3))
+            extra = lambda rgb: mult * lpips(patches(rgb), gt)                     # noqa: E731
+        loss_dict = fused.loss_dict(ray_bundle.origins.reshape(-1, 3), ray_bundle.directions.reshape(-1, 3), image, cams,
+                                    extra_loss=extra)
         return {}, loss_dict, {"distortion": loss_dict["distortion_loss"].detach() / max(fused.trainer.distortion_mult, 1e-30)}

@@ -402,6 +402,19 @@ def test_pipeline_get_train_loss_dict_routes_through_the_fused_step():
     assert pipe._fused_step.trainer.counts == (64, 32, 16)
     outputs, loss_dict, metrics = pipe.get_train_loss_dict(step=0)
     assert set(loss_dict) == {"rgb_loss", "interlevel_loss", "distortion_loss"} and "distortion" in metrics
+    # use_lpips (the reference's default): the model's own LPIPS module joins as a torch term on 8 x 8 patches of the batch
+    model.config.use_lpips, model.config.patch_size, model.config.lpips_loss_mult = True, 8, 0.5
+    seen = {}
+
+    def fake_lpips(a, b):
+        seen["shapes"] = (tuple(a.shape), tuple(b.shape), float(a.min()) >= -1.0, float(b.max()) <= 1.0)
+        return ((a - b) ** 2).mean()
+
+    model.lpips = fake_lpips
+    _, with_lpips, _ = pipe.get_train_loss_dict(step=1)
+    assert set(with_lpips) == {"rgb_loss", "interlevel_loss", "distortion_loss", "lpips_loss"} and float(with_lpips["lpips_loss"]) > 0
+    assert seen["shapes"] == ((1, 3, 8, 8), (1, 3, 8, 8), True, True)
+    model.config.use_lpips = False
     sum(loss_dict.values()).backward()
     assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for n, p in m_gpu.named_parameters() if "scalings" not in n)
     assert float(m_gpu.field.encoding.hash_table.grad.abs().max()) > 0 and float(m_gpu.proposal_networks[1].encoding.hash_table.grad.abs().max()) > 0
