@@ -545,7 +545,8 @@ def main():
         from signerf_b200 import edit_loop
         from signerf_b200 import train as train_mod
         emb5 = torch.randn(n_cam + VIEWS, 32, generator=torch.Generator().manual_seed(11))     # one row per generated image
-        tuner = edit_loop.FineTuner(train_mod.NerfactoTrainer(fld5, embedding=emb5), num_samples=48,
+        tuner = edit_loop.FineTuner(train_mod.NerfactoTrainer(fld5, embedding=emb5, pred_normals=synthetic.random_pred_normals()),
+                                    num_samples=48,
                                     rays_per_batch=max(1024, 16384 // N), seed=rank)
         rounds, gen_s, train_s, train_losses, frames = [], 0.0, 0.0, [], None
         for rnd in range(args.config5_rounds):
@@ -581,10 +582,11 @@ def main():
                    "fine_tune_losses_rank0": train_losses,
                    "fine_tune_note": "whole nerfacto step (train.NerfactoTrainer): proposal sampler in training mode (256 -> 96 -> 48, "
                                      "stratified + jittered PDF re-sampling), main field + both proposal networks + per-image "
-                                     "appearance embeddings, L1 rgb + interlevel + distortion losses on 32x32 patches of the "
+                                     "appearance embeddings + the normal-prediction branch (predict_normals), L1 rgb + "
+                                     "interlevel + distortion + orientation + pred-normal losses on 32x32 patches of the "
                                      "generated images, 16 384 rays per step over all ranks, Adam lr 1e-2 on fields and "
                                      "proposal_networks; gradients all-reduced across ranks (one flattened all-reduce); LPIPS (no "
-                                     "VGG weights offline) and the predict_normals regularisers are not part of the step (DESIGN.md)",
+                                     "pretrained weights offline) is not part of the step (DESIGN.md)",
                    "note": "BASELINE config 5, generation half through plugin.DatasetGenerator.generate_dataset: procedural proxy mesh "
                            "with bunny.obj's 4 968 triangles (the reference's mesh file is not shipped), masking_mode='shape', 4x4 sheet of "
                            "512^2 tiles, 20 configured steps at strength 0.9 = 19 UNet+ControlNet evaluations per sheet replayed as ONE CUDA graph, "

@@ -425,8 +425,7 @@ int sgn_embed_tokens(const int32_t* d_ids, const float* d_token_table, const flo
  *   b_head1[64] b_head2[4] avg_density pad[3]
  * w_head0's 32 input columns are [SH 16 | unused | geo 15]; b_head0 carries the mean appearance embedding folded in
  * (b + W_app . mean(embedding)), as the eval renderer uses it.  Gradient buffers use the same layouts and are ACCUMULATED
- * into (zero them per step).  Not built: the normal regularisers of `predict_normals` (orientation / pred-normal losses,
- * signerf.py:69-80; they need the second derivative of the hash grid) and LPIPS's VGG (a host-side torch term). */
+ * into (zero them per step).  LPIPS's pretrained network stays a host-side torch term. */
 int64_t sgn_mlp_param_count(void);
 int sgn_field_mlp_params(const SgnField* f, float** d_params);
 /* Re-derives the fp16 tensor-core fragments (and the feature scale) the renderer uses from the fp32 parameter block and
@@ -441,13 +440,14 @@ int sgn_train_forward(const SgnField* f, const float* d_origins, const float* d_
                       const float* d_ray_bins, int S, const float* d_head_bias, float* d_sigma, float* d_color, float* d_rgb,
                       float* d_acc, void* stream);
 /* Backward: d_grad_rgb [N,3] = dL/drgb and, optionally, d_grad_weights [N,S] = the gradient of loss terms that read the
- * final level's weights directly (sgn_distortion_loss) -> d_grad_table [L*T,2], d_grad_mlp [sgn_mlp_param_count()] and,
- * when d_head_bias was given, d_grad_head_bias [N,64] (all +=).  d_ws: sgn_train_ws_bytes(N, S) bytes, 16-byte aligned. */
+ * final level's weights directly (sgn_distortion_loss) and d_grad_geo [N,S,15] = dL / d(geo features) of the normal
+ * prediction branch (sgn_train_normals_backward) -> d_grad_table [L*T,2], d_grad_mlp [sgn_mlp_param_count()] and, when
+ * d_head_bias was given, d_grad_head_bias [N,64] (all +=).  d_ws: sgn_train_ws_bytes(N, S) bytes, 16-byte aligned. */
 int64_t sgn_train_ws_bytes(int64_t N, int S);
 int sgn_train_backward(const SgnField* f, const float* d_origins, const float* d_directions, int64_t N, const float* d_bins,
                        const float* d_ray_bins, int S, const float* d_head_bias, const float* d_sigma, const float* d_color,
-                       const float* d_grad_rgb, const float* d_grad_weights, float* d_grad_table, float* d_grad_mlp,
-                       float* d_grad_head_bias, void* d_ws, int64_t ws_bytes, void* stream);
+                       const float* d_grad_rgb, const float* d_grad_weights, const float* d_grad_geo, float* d_grad_table,
+                       float* d_grad_mlp, float* d_grad_head_bias, void* d_ws, int64_t ws_bytes, void* stream);
 /* Per-image appearance embedding while training ([EXT] NerfactoField.get_outputs: embedding_appearance(camera_indices)
  * concatenated to the head's input): head_bias[ray] = bias + W_app . E[camera[ray]], with W_app [64,32] the head's first
  * layer's appearance columns, bias [64], E [num_images,32], camera indices int32 [N]; the backward accumulates (+=) the
@@ -457,6 +457,29 @@ int sgn_appearance_bias(const float* d_w_app, const float* d_bias, const float* 
 int sgn_appearance_bias_backward(const float* d_w_app, const float* d_embedding, int num_images, const int32_t* d_camera_indices,
                                  const float* d_grad_head_bias, int64_t N, float* d_grad_w_app, float* d_grad_bias,
                                  float* d_grad_embedding, void* stream);
+
+/* --- the normal regularisers of `predict_normals=True` (signerf_config.py:33; loss terms signerf/signerf.py:69-80) ---
+ * Parameter block of the prediction branch ([EXT] NerfactoField.mlp_pred_normals + PredNormalsFieldHead), fp32,
+ * sgn_pred_normals_param_count() = 10 308 floats, 16-byte aligned, nn.Linear row-major [out][in]:
+ *   w1[64*64] w2[64*64] w_head[3*64] w0[64*27] b0[64] b1[64] b2[64] b_head[3] pad[1]
+ * (input of layer 0: NeRFEncoding of the raw position, 12 values, then the 15 geo features).
+ * Forward on the final level's bins d_ray_bins [N,S+1]: d_normals [N,S,3] = -normalize(d density_logit / d p), the analytic
+ * normals ([EXT] Field.get_normals: no graph, constants of the step); d_pred_normals [N,S,3] = the branch's output. */
+int64_t sgn_pred_normals_param_count(void);
+int sgn_train_normals_forward(const SgnField* f, const float* d_pn_params, const float* d_origins, const float* d_directions,
+                              int64_t N, const float* d_ray_bins, int S, float* d_normals, float* d_pred_normals, void* stream);
+/* [EXT] losses.py orientation_loss / pred_normal_loss on the (detached) weights [N,S], means over the rays times the
+ * multipliers: d_loss_* [1] += the terms; d_grad_pred [N,S,3] = d pred_normal term / d pred_normals (overwritten).  The
+ * orientation term has no gradient (weights and analytic normals carry no graph). */
+int sgn_normal_losses(const float* d_weights, const float* d_normals, const float* d_pred_normals, const float* d_directions,
+                      int64_t N, int S, float orientation_mult, float pred_normal_mult, float* d_loss_orientation,
+                      float* d_loss_pred_normal, float* d_grad_pred, void* stream);
+/* Backward of the prediction branch: d_grad_pred -> d_grad_pn_params [sgn_pred_normals_param_count()] (+=) and d_grad_geo
+ * [N,S,15] (overwritten; feed it to sgn_train_backward).  d_ws: sgn_train_normals_ws_bytes(N, S) bytes, 16-byte aligned. */
+int64_t sgn_train_normals_ws_bytes(int64_t N, int S);
+int sgn_train_normals_backward(const SgnField* f, const float* d_pn_params, const float* d_origins, const float* d_directions,
+                               int64_t N, const float* d_ray_bins, int S, const float* d_grad_pred, float* d_grad_pn_params,
+                               float* d_grad_geo, void* d_ws, int64_t ws_bytes, void* stream);
 
 /* --- the proposal half of the training step ([EXT] nerfstudio ProposalNetworkSampler in training mode, losses.py
  * interlevel_loss / distortion_loss as signerf/signerf.py:62-68 adds them to the loss dict) ---

@@ -186,7 +186,7 @@ class NerfactoFieldRef(nn.Module):
 
     def __init__(self, num_images=30, num_levels=16, base_res=16, max_res=2048, log2_hashmap_size=19,
                  features_per_level=2, hidden_dim=64, geo_feat_dim=15, hidden_dim_color=64,
-                 appearance_embedding_dim=32, average_init_density=0.01):
+                 appearance_embedding_dim=32, average_init_density=0.01, use_pred_normals=False):
         super().__init__()
         self.geo_feat_dim = geo_feat_dim
         self.average_init_density = average_init_density
@@ -196,6 +196,13 @@ class NerfactoFieldRef(nn.Module):
         self.embedding_appearance = nn.Embedding(num_images, appearance_embedding_dim)
         self.mlp_head = MLPRef(16 + geo_feat_dim + appearance_embedding_dim, 3, hidden_dim_color, 3,
                                out_activation=nn.Sigmoid())
+        # predict_normals=True (signerf_config.py:33): NeRFEncoding(in_dim=3, num_frequencies=2, min_freq_exp=0, max_freq_exp=1)
+        # of the RAW positions (12 values) | geo features -> MLP(3 layers, 64 wide, out 64, no out activation) ->
+        # PredNormalsFieldHead = Linear(64, 3) + Tanh, normalised (fields/nerfacto_field.py, field_components/field_heads.py)
+        self.use_pred_normals = use_pred_normals
+        if use_pred_normals:
+            self.mlp_pred_normals = MLPRef(geo_feat_dim + 12, 3, 64, 64)
+            self.field_head_pred_normals = nn.Linear(64, 3)
 
     def contracted_positions(self, positions: Tensor) -> Tuple[Tensor, Tensor]:
         positions = contract_linf(positions)
@@ -220,6 +227,43 @@ class NerfactoFieldRef(nn.Module):
         return self.mlp_head(h).view(*directions.shape[:-1], -1)
 
 
+def nerf_encoding_2freq(x: Tensor) -> Tensor:
+    """NeRFEncoding.pytorch_fwd, in_dim 3, frequencies 2^0 and 2^1, include_input=False: sin of [2 pi x f | 2 pi x f + pi/2]."""
+    scaled = (2 * torch.pi * x)[..., None] * (2 ** torch.linspace(0.0, 1.0, 2))
+    scaled = scaled.view(*scaled.shape[:-2], -1)
+    return torch.sin(torch.cat([scaled, scaled + torch.pi / 2.0], dim=-1))
+
+
+def normals_and_pred_normals(field: "NerfactoFieldRef", positions: Tensor):
+    """Field.forward(compute_normals=True) + the PRED_NORMALS head.  -> (density [..,1], geo, analytic normals [..,3]
+    WITHOUT a graph (Field.get_normals: autograd.grad of the density logit w.r.t. the contracted sample locations,
+    retain_graph only, then -normalize), predicted normals [..,3] with a graph into mlp_pred_normals, its head and - through
+    the geo features - the base MLP and the hash table)."""
+    p, selector = field.contracted_positions(positions)
+    p = p.detach().requires_grad_(True)
+    with torch.enable_grad():
+        h = field.mlp_base(field.encoding(p.view(-1, 3))).view(*p.shape[:-1], -1)
+        logit, geo = torch.split(h, [1, field.geo_feat_dim], dim=-1)
+        density = field.average_init_density * torch.exp(logit) * selector[..., None]
+        (g,) = torch.autograd.grad(logit, p, grad_outputs=torch.ones_like(logit), retain_graph=True)
+    normals = -torch.nn.functional.normalize(g, dim=-1)
+    inp = torch.cat([nerf_encoding_2freq(positions.reshape(-1, 3)), geo.reshape(-1, field.geo_feat_dim)], dim=-1)
+    x = field.mlp_pred_normals(inp).view(*positions.shape[:-1], -1)
+    pred = torch.nn.functional.normalize(torch.tanh(field.field_head_pred_normals(x)), dim=-1)
+    return density, geo, normals, pred
+
+
+def orientation_loss(weights: Tensor, normals: Tensor, viewdirs: Tensor) -> Tensor:
+    """losses.py orientation_loss (Ref-NeRF): back-facing normals along the ray, per ray."""
+    n_dot_v = (normals * (-viewdirs)[..., None, :]).sum(dim=-1)
+    return (weights[..., 0] * torch.fmin(torch.zeros_like(n_dot_v), n_dot_v) ** 2).sum(dim=-1)
+
+
+def pred_normal_loss(weights: Tensor, normals: Tensor, pred_normals: Tensor) -> Tensor:
+    """losses.py pred_normal_loss: predicted against analytic normals, per ray."""
+    return (weights[..., 0] * (1.0 - torch.sum(normals * pred_normals, dim=-1))).sum(dim=-1)
+
+
 class NerfactoRef(nn.Module):
     """models/nerfacto.py populate_modules with SIGNeRF's overrides (signerf_config.py:32-35)."""
 
@@ -227,13 +271,14 @@ class NerfactoRef(nn.Module):
                  num_proposal_samples=(256, 96), num_nerf_samples=48,
                  proposal_net_args=({"hidden_dim": 16, "log2_hashmap_size": 17, "num_levels": 5, "max_res": 128},
                                     {"hidden_dim": 16, "log2_hashmap_size": 17, "num_levels": 5, "max_res": 256}),
-                 log2_hashmap_size=19, num_levels=16, max_res=2048):
+                 log2_hashmap_size=19, num_levels=16, max_res=2048, predict_normals=False):
         super().__init__()
         self.near, self.far = near, far
         self.num_proposal_samples = tuple(num_proposal_samples)
         self.num_nerf_samples = num_nerf_samples
         self.field = NerfactoFieldRef(num_images=num_images, average_init_density=average_init_density,
-                                      log2_hashmap_size=log2_hashmap_size, num_levels=num_levels, max_res=max_res)
+                                      log2_hashmap_size=log2_hashmap_size, num_levels=num_levels, max_res=max_res,
+                                      use_pred_normals=predict_normals)
         self.proposal_networks = nn.ModuleList(
             DensityFieldRef(**a, average_init_density=average_init_density) for a in proposal_net_args)
 
@@ -603,7 +648,11 @@ def forward_train(model: NerfactoRef, rays_o: Tensor, rays_d: Tensor, jitter: Op
         else:
             samples = pdf_resample(samples, w.detach(), counts[i + 1], to_euclid, jitter=jit(i + 1))
     positions = positions_of(rays_o, rays_d, samples)
-    density, geo = model.field.get_density(positions)
+    normals = pred_normals = None
+    if getattr(model.field, "use_pred_normals", False):
+        density, geo, normals, pred_normals = normals_and_pred_normals(model.field, positions)
+    else:
+        density, geo = model.field.get_density(positions)
     dirs = rays_d[:, None, :].expand(-1, positions.shape[1], -1)
     if camera_indices is None:
         rgb = model.field.get_rgb(dirs, geo)
@@ -617,16 +666,26 @@ def forward_train(model: NerfactoRef, rays_o: Tensor, rays_d: Tensor, jitter: Op
     samples_list.append(samples)
     comp = torch.sum(weights * rgb, dim=-2)
     rgb_out = comp + rgb[..., -1, :] * (1.0 - torch.sum(weights, dim=-2))
-    return {"rgb": rgb_out, "weights_list": weights_list, "samples_list": samples_list}
+    out = {"rgb": rgb_out, "weights_list": weights_list, "samples_list": samples_list}
+    if normals is not None:   # models/nerfacto.py get_outputs, `if self.training and self.config.predict_normals`
+        out["rendered_orientation_loss"] = orientation_loss(weights.detach(), normals, rays_d)
+        out["rendered_pred_normal_loss"] = pred_normal_loss(weights.detach(), normals.detach(), pred_normals)
+        out["normals"], out["pred_normals"] = normals, pred_normals
+    return out
 
 
 def signerf_loss_dict(out: Dict[str, object], target: Tensor, use_l1: bool = True, interlevel_loss_mult: float = 1.0,
-                      distortion_loss_mult: float = 0.002) -> Dict[str, Tensor]:
+                      distortion_loss_mult: float = 0.002, orientation_loss_mult: float = 0.0001,
+                      pred_normal_loss_mult: float = 0.001) -> Dict[str, Tensor]:
     """SIGNeRFModel.get_loss_dict while training, without the LPIPS term (signerf/signerf.py:41-82; the multipliers are
     NerfactoModelConfig's defaults, which signerf_config.py leaves untouched)."""
-    return {"rgb_loss": signerf_rgb_loss(out["rgb"], target, use_l1),
-            "interlevel_loss": interlevel_loss_mult * interlevel_loss(out["weights_list"], out["samples_list"]),
-            "distortion_loss": distortion_loss_mult * distortion_loss(out["weights_list"], out["samples_list"])}
+    ld = {"rgb_loss": signerf_rgb_loss(out["rgb"], target, use_l1),
+          "interlevel_loss": interlevel_loss_mult * interlevel_loss(out["weights_list"], out["samples_list"]),
+          "distortion_loss": distortion_loss_mult * distortion_loss(out["weights_list"], out["samples_list"])}
+    if "rendered_orientation_loss" in out:      # signerf.py:69-80, NerfactoModelConfig's multipliers 1e-4 / 1e-3
+        ld["orientation_loss"] = orientation_loss_mult * torch.mean(out["rendered_orientation_loss"])
+        ld["pred_normal_loss"] = pred_normal_loss_mult * torch.mean(out["rendered_pred_normal_loss"])
+    return ld
 
 
 def patch_sample_method(batch_size: int, num_images: int, image_height: int, image_width: int, patch_size: int,

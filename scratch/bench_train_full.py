@@ -13,7 +13,16 @@ idx = samp.sample_method(samp.num_rays_per_batch, 16, 512, 512, device=dev)
 cams = idx[:, 0].to(torch.int32).contiguous()
 o, d = o[idx[:, 0], idx[:, 1], idx[:, 2]].contiguous(), d[idx[:, 0], idx[:, 1], idx[:, 2]].contiguous()
 target = torch.rand(o.shape[0], 3, device=dev)
-tr = T.NerfactoTrainer(fld, embedding=torch.randn(16, 32))
+def random_pred_normals(seed=5):
+    g = torch.Generator().manual_seed(seed)
+    lin = lambda o, i: ((torch.rand(o, i, generator=g) * 2 - 1) / i ** 0.5, (torch.rand(o, generator=g) * 2 - 1) / i ** 0.5)
+    p = {}
+    for j, (o_, i_) in enumerate(((64, 27), (64, 64), (64, 64))):
+        p[f"field.mlp_pred_normals.layers.{j}.weight"], p[f"field.mlp_pred_normals.layers.{j}.bias"] = lin(o_, i_)
+    p["field.field_head_pred_normals.net.weight"], p["field.field_head_pred_normals.net.bias"] = lin(3, 64)
+    return p
+with_normals = len(sys.argv) > 2 and sys.argv[2] == "normals"
+tr = T.NerfactoTrainer(fld, embedding=torch.randn(16, 32), pred_normals=random_pred_normals() if with_normals else None)
 jit = torch.rand(3, o.shape[0], device=dev)
 for _ in range(3):
     tr.train_step(o, d, target, jit, cams)
@@ -45,4 +54,4 @@ t0 = time.perf_counter(); a, b = ev(), ev(); a.record()
 for _ in range(20):
     tr.train_step(o, d, target, jit, cams)
 b.record(); torch.cuda.synchronize()
-print(f"20 steps: {a.elapsed_time(b) / 20:.3f} ms / step on the device, {(time.perf_counter() - t0) / 20 * 1e3:.3f} ms wall")
+print(f"predict_normals {with_normals}: 20 steps: {a.elapsed_time(b) / 20:.3f} ms / step on the device, {(time.perf_counter() - t0) / 20 * 1e3:.3f} ms wall")

@@ -86,7 +86,12 @@ SIGNATURES = {
     "sgn_field_refresh": (_i, [_vp, _vp]),
     "sgn_train_forward": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sgn_train_ws_bytes": (_i64, [_i64, _i]),
-    "sgn_train_backward": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "sgn_train_backward": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "sgn_pred_normals_param_count": (_i64, []),
+    "sgn_train_normals_forward": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _i, _vp, _vp, _vp]),
+    "sgn_normal_losses": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _f, _f, _vp, _vp, _vp, _vp]),
+    "sgn_train_normals_ws_bytes": (_i64, [_i64, _i]),
+    "sgn_train_normals_backward": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _i, _vp, _vp, _vp, _vp, _i64, _vp]),
     "sgn_appearance_bias": (_i, [_vp, _vp, _vp, _i, _vp, _i64, _vp, _vp]),
     "sgn_appearance_bias_backward": (_i, [_vp, _vp, _i, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "sgn_prop_param_count": (_i64, []),

@@ -509,4 +509,18 @@ struct Composite {
   }
 };
 
+// ---------------------------------------------------------------- weight gradients of the training kernels
+// dW[n][k] += sum_s D[doff + n][s] * A[aoff + k][s], db[n] += sum_s D[doff + n][s] over [component][sample] slabs
+// (k_outer_reduce, sgn_train.cu): up to five layers per launch.
+struct OuterLayer {
+  int doff, N, aoff, K, ldw;
+  float* dW;
+  float* db;
+};
+struct OuterParams {
+  OuterLayer layer[5];
+};
+void launch_outer_reduce(const float* D, const float* A, const OuterParams& op, int layers, int64_t count, int64_t cap,
+                         cudaStream_t st);
+
 }  // namespace sgn

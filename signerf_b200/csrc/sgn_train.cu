@@ -188,6 +188,7 @@ struct FieldBwd {
   TrainRays rays;
   const float* gsigma;
   const float* gcolor;
+  const float* ggeo;   // [samples, 15] d loss / d geo features from the normal-prediction branch, or null
   float* grad_table;   // [L * T, 2], accumulated
   float* deltas;       // [kDeltaDim, cap]: one row per delta component, samples of the chunk along the row, so that the
   float* acts;         // [kActDim, cap]    per-thread "arrays" below are coalesced across the warp
@@ -307,6 +308,10 @@ __global__ void __launch_bounds__(128, 3) k_train_field_bwd(const __grid_constan
       axpy_row<16>(w->w_head0 + m * 32 + 112, v3, d16);
     }
     d16[0] = sel ? p.gsigma[s] * w->avg_density * expf(fminf(logit, 15.f)) : 0.f;
+    if (p.ggeo) {
+#pragma unroll
+      for (int n = 1; n < 16; ++n) d16[n] += p.ggeo[15 * s + n - 1];
+    }
 #pragma unroll
     for (int n = 0; n < 16; ++n) SGN_AT(dout1, n) = d16[n];
 #pragma unroll
@@ -407,14 +412,6 @@ __global__ void __launch_bounds__(256) k_appearance_bwd(const float* __restrict_
 
 // dW[n][k] += sum_s D[s][doff + n] * A[s][aoff + k]  (n < N <= 64, k < K <= 64);  db[n] += sum_s D[s][doff + n]
 // 256 threads own a 64 x 64 register tile (4 x 4 each); samples are staged 32 at a time through shared memory.
-struct OuterLayer {
-  int doff, N, aoff, K, ldw;
-  float* dW;
-  float* db;
-};
-struct OuterParams {
-  OuterLayer layer[5];   // blockIdx.y
-};
 __global__ void __launch_bounds__(256) k_outer_reduce(const float* __restrict__ D, const float* __restrict__ A,
                                                       const __grid_constant__ OuterParams op, int64_t count, int64_t cap,
                                                       int per_cta) {
@@ -455,6 +452,15 @@ __global__ void __launch_bounds__(256) k_outer_reduce(const float* __restrict__ 
     for (int y = 0; y < 4; ++y)
       if (tn + x < N && tk + y < K) atomicAdd(dW + (tn + x) * ldw + tk + y, acc[x][y]);
   if (db && threadIdx.x < N) atomicAdd(db + threadIdx.x, bacc);
+}
+
+void launch_outer_reduce(const float* D, const float* A, const OuterParams& op, int layers, int64_t count, int64_t cap,
+                         cudaStream_t st) {
+  // 512-sample slabs keep ~1 000 CTAs in flight, which is what hides the latency of the slab loads (one 32-sample stage
+  // at a time per CTA); blockIdx.y = layer
+  const int per_cta = 512;
+  const int ctas = (int)((count + per_cta - 1) / per_cta);
+  k_outer_reduce<<<dim3(ctas, layers), 256, 0, st>>>(D, A, op, count, cap, per_cta);
 }
 
 // ---------------------------------------------------------------- loss + optimizer
@@ -554,8 +560,8 @@ extern "C" int64_t sgn_train_ws_bytes(int64_t N, int S) {
 extern "C" int sgn_train_backward(const SgnField* f, const float* d_origins, const float* d_directions, int64_t N,
                                   const float* d_bins, const float* d_ray_bins, int S, const float* d_head_bias,
                                   const float* d_sigma, const float* d_color, const float* d_grad_rgb,
-                                  const float* d_grad_weights, float* d_grad_table, float* d_grad_mlp, float* d_grad_head_bias,
-                                  void* d_ws, int64_t ws_bytes, void* stream) {
+                                  const float* d_grad_weights, const float* d_grad_geo, float* d_grad_table, float* d_grad_mlp,
+                                  float* d_grad_head_bias, void* d_ws, int64_t ws_bytes, void* stream) {
   int rc = check_rays(f, d_origins, d_directions, N, d_bins, d_ray_bins, S);
   if (rc) return rc;
   if (N == 0) return SGN_OK;
@@ -581,24 +587,20 @@ extern "C" int sgn_train_backward(const SgnField* f, const float* d_origins, con
   MlpF32* G = reinterpret_cast<MlpF32*>(d_grad_mlp);   // gradients in the parameter block's own layout
   for (int64_t first = 0; first < samples; first += kBwdChunk) {
     FieldBwd p;
-    p.grid = f->grid; p.w32 = f->d_f32; p.rays = r; p.gsigma = gsigma; p.gcolor = gcolor;
+    p.grid = f->grid; p.w32 = f->d_f32; p.rays = r; p.gsigma = gsigma; p.gcolor = gcolor; p.ggeo = d_grad_geo;
     p.grad_table = d_grad_table; p.deltas = deltas; p.acts = acts;
     p.first = first; p.count = std::min(kBwdChunk, samples - first);
     p.cap = std::min(samples, kBwdChunk);
     k_train_field_bwd<<<blocks_for(p.count, 128, 8), 128, sizeof(MlpF32), st>>>(p);
     SGN_LAUNCH_CHECK();
-    // the five weight gradients in one launch (blockIdx.y = layer): 512-sample slabs keep ~1 000 CTAs in flight, which is
-    // what hides the latency of the slab loads (one 32-sample stage at a time per CTA)
-    const int per_cta = 512;
-    const int ctas = (int)((p.count + per_cta - 1) / per_cta);
-    OuterParams op;
+    OuterParams op;   // the five weight gradients in one launch
     //             deltas (offset, N)  activations (offset, K)  ld
     op.layer[0] = {0, 64, 0, 32, 32, G->w_base0, G->b_base0};
     op.layer[1] = {64, 16, 32, 64, 64, G->w_base1, G->b_base1};
     op.layer[2] = {80, 64, 96, 32, 32, G->w_head0, G->b_head0};
     op.layer[3] = {144, 64, 128, 64, 64, G->w_head1, G->b_head1};
     op.layer[4] = {208, 3, 192, 64, 64, G->w_head2, G->b_head2};
-    k_outer_reduce<<<dim3(ctas, 5), 256, 0, st>>>(deltas, acts, op, p.count, p.cap, per_cta);
+    launch_outer_reduce(deltas, acts, op, 5, p.count, p.cap, st);
     SGN_LAUNCH_CHECK();
     if (d_grad_head_bias) {
       k_ray_bias_reduce<<<blocks_for((p.count / S + 2) * 64, 128, 8), 128, 0, st>>>(deltas, first, p.count, p.cap, S, d_grad_head_bias);

@@ -141,6 +141,9 @@ class SIGNeRFPipeline(VanillaPipeline):
                     average_init_density=float(getattr(cfg, "average_init_density", 0.01)), use_l1=bool(getattr(cfg, "use_l1", True)),
                     interlevel_loss_mult=float(getattr(cfg, "interlevel_loss_mult", 1.0)),
                     distortion_loss_mult=float(getattr(cfg, "distortion_loss_mult", 0.002)),
+                    predict_normals=bool(getattr(cfg, "predict_normals", False)) or None,
+                    orientation_loss_mult=float(getattr(cfg, "orientation_loss_mult", 0.0001)),
+                    pred_normal_loss_mult=float(getattr(cfg, "pred_normal_loss_mult", 0.001)),
                     counts=tuple(getattr(cfg, "num_proposal_samples_per_ray", (256, 96))) + (int(getattr(cfg, "num_nerf_samples_per_ray", 48)),))
         opts.update(kw)
         self._fused_step = FusedTrainingStep(self.model, **opts)

@@ -95,3 +95,18 @@ def proxy_mesh(num_faces: int = 4968, bump: float = 0.15) -> Tuple[np.ndarray, n
             faces.append((a, c, d))
             faces.append((a, d, b))
     return np.asarray(verts, np.float32), np.asarray(faces, np.int32)
+
+
+def random_pred_normals(seed: int = 5) -> dict:
+    """nn.Linear-style random init of nerfacto's normal-prediction branch (`predict_normals=True`, signerf_config.py:33)
+    under nerfstudio's parameter names: MLP 27 -> 64 -> 64 -> 64 and PredNormalsFieldHead's Linear(64, 3)."""
+    g = torch.Generator().manual_seed(seed)
+
+    def lin(o: int, i: int):
+        return (torch.rand(o, i, generator=g) * 2 - 1) / i ** 0.5, (torch.rand(o, generator=g) * 2 - 1) / i ** 0.5
+
+    p = {}
+    for j, (o_, i_) in enumerate(((64, 27), (64, 64), (64, 64))):
+        p[f"field.mlp_pred_normals.layers.{j}.weight"], p[f"field.mlp_pred_normals.layers.{j}.bias"] = lin(o_, i_)
+    p["field.field_head_pred_normals.net.weight"], p["field.field_head_pred_normals.net.bias"] = lin(3, 64)
+    return p

@@ -13,8 +13,9 @@ Mirrors, on the reference side,
 `NerfactoTrainer` is the whole nerfacto training step as `SIGNeRFModel` inherits it (signerf.py:62-68): the proposal
 sampler in training mode (stratified bins, jittered PDF re-sampling; the draws are inputs), the two proposal networks
 trained by `interlevel_loss`, `distortion_loss` on the final level, per-image appearance embeddings, and Adam on the
-`fields` and `proposal_networks` groups.  NOT built: the normal regularisers of `predict_normals` (signerf.py:69-80; they
-need second derivatives of the hash grid), the camera optimizer and the lr schedulers (host-side scalars)."""
+`fields` and `proposal_networks` groups, and - with the prediction branch's tensors - the normal regularisers of
+`predict_normals=True` (signerf.py:69-80).  NOT built: the camera optimizer and the lr schedulers (host-side scalars); LPIPS's
+pretrained network stays a host-side torch term (`extra_loss`)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -141,7 +142,8 @@ def train_forward(fld: NerfactoFieldB200, origins: Tensor, directions: Tensor, b
 
 def train_backward(fld: NerfactoFieldB200, origins: Tensor, directions: Tensor, bins: Tensor, saved, grad_rgb: Tensor,
                    grad_table: Tensor, grad_mlp: Tensor, grad_weights: Optional[Tensor] = None,
-                   head_bias: Optional[Tensor] = None, grad_head_bias: Optional[Tensor] = None) -> None:
+                   head_bias: Optional[Tensor] = None, grad_head_bias: Optional[Tensor] = None,
+                   grad_geo: Optional[Tensor] = None) -> None:
     """Accumulates dL/d(hash table) into grad_table [L*T,2] and dL/d(MLP block) into grad_mlp [sgn_mlp_param_count()];
     grad_weights [N,S]: gradient of the terms reading the weights directly (distortion loss); head_bias / grad_head_bias
     [N,64]: the per-ray appearance bias of the forward and where its gradient accumulates."""
@@ -161,9 +163,10 @@ def train_backward(fld: NerfactoFieldB200, origins: Tensor, directions: Tensor, 
         gw = None if grad_weights is None else _req(grad_weights.reshape(n, S), torch.float32, "grad_weights")
         hb = None if head_bias is None else _req(head_bias.reshape(n, 64), torch.float32, "head_bias")
         ghb = None if grad_head_bias is None else _req(grad_head_bias.reshape(n, 64), torch.float32, "grad_head_bias")
+        gg = None if grad_geo is None else _req(grad_geo.reshape(n, S, 15), torch.float32, "grad_geo")
         _lib.check(lib.sgn_train_backward(fld.handle, _ptr(o), _ptr(d), n, _ptr(shared), _ptr(per_ray), S, _ptr(hb), _ptr(sigma),
-                                          _ptr(color), _ptr(g), _ptr(gw), _ptr(grad_table), _ptr(grad_mlp), _ptr(ghb), _ptr(ws),
-                                          need, _stream(dev)))
+                                          _ptr(color), _ptr(g), _ptr(gw), _ptr(gg), _ptr(grad_table), _ptr(grad_mlp), _ptr(ghb),
+                                          _ptr(ws), need, _stream(dev)))
 
 
 def rgb_loss(pred: Tensor, target: Tensor, use_l1: bool = True, want_grad: bool = True) -> Tuple[Tensor, Optional[Tensor]]:
@@ -266,7 +269,8 @@ class FieldTrainer:
 
     # the other parameter layout nerfstudio's torch-fallback modules have used (plugin/model.py from_state_dict)
     _ALT_NAMES = (("field.mlp_base.encoding.", "field.mlp_base_grid."), ("field.mlp_base.mlp.", "field.mlp_base_mlp."),
-                  (".mlp_base.encoding.", ".encoding."), (".mlp_base.mlp.", ".mlp_base."))
+                  (".mlp_base.encoding.", ".encoding."), (".mlp_base.mlp.", ".mlp_base."),
+                  ("field_head_pred_normals.net.", "field_head_pred_normals."))
 
     def load_into(self, model: torch.nn.Module) -> list:
         """Copy the trained parameters into the matching tensors of a nerfstudio model (`pipeline.model`), in place, so that
@@ -423,6 +427,85 @@ def appearance_bias_backward(w_app: Tensor, embedding: Tensor, camera_indices: T
             _ptr(_req(grad_embedding, torch.float32, "grad_embedding")), _stream(cam.device)))
 
 
+# ---------------------------------------------------------------------------------------------- normal regularisers
+PN_LAYOUT = (("w1", (64, 64)), ("w2", (64, 64)), ("wh", (3, 64)), ("w0", (64, 27)), ("b0", (64,)), ("b1", (64,)), ("b2", (64,)),
+             ("bh", (4,)))
+PN_NAMES = {"w0": "field.mlp_pred_normals.layers.0.weight", "b0": "field.mlp_pred_normals.layers.0.bias",
+            "w1": "field.mlp_pred_normals.layers.1.weight", "b1": "field.mlp_pred_normals.layers.1.bias",
+            "w2": "field.mlp_pred_normals.layers.2.weight", "b2": "field.mlp_pred_normals.layers.2.bias",
+            "wh": "field.field_head_pred_normals.net.weight", "bh": "field.field_head_pred_normals.net.bias"}
+
+
+def pn_block_views(block: Tensor) -> Dict[str, Tensor]:
+    """Named views into a parameter / gradient block of sgn_pred_normals_param_count() floats (include/signerf_b200.h)."""
+    out, off = {}, 0
+    for name, shape in PN_LAYOUT:
+        n = 1
+        for d in shape:
+            n *= d
+        out[name] = block[off:off + n].view(*shape)
+        off += n
+    assert off == block.numel()
+    return out
+
+
+def pack_pred_normals(params: Dict[str, Tensor], device) -> Tensor:
+    """nerfstudio's `field.mlp_pred_normals.layers.*` / `field.field_head_pred_normals.net.*` tensors -> the C block."""
+    block = torch.zeros(int(_lib.load().sgn_pred_normals_param_count()), dtype=torch.float32, device=device)
+    v = pn_block_views(block)
+    for key, name in PN_NAMES.items():
+        t = params[name] if name in params else params[name.replace(".net.", ".")]
+        (v[key][:3] if key == "bh" else v[key]).copy_(t.detach().to(device, torch.float32))
+    return block
+
+
+def normals_forward(fld: NerfactoFieldB200, pn_block: Tensor, origins: Tensor, directions: Tensor, ray_bins: Tensor):
+    """-> (analytic normals [N,S,3] (no graph: Field.get_normals), predicted normals [N,S,3]) on the final level's bins."""
+    o = _req(origins.reshape(-1, 3), torch.float32, "origins")
+    d = _req(directions.reshape(-1, 3), torch.float32, "directions")
+    b = _req(ray_bins, torch.float32, "ray_bins")
+    n, S = b.shape[0], b.shape[1] - 1
+    normals = torch.empty((n, S, 3), dtype=torch.float32, device=fld.device)
+    pred = torch.empty_like(normals)
+    with torch.cuda.device(fld.device):
+        _lib.check(_lib.load().sgn_train_normals_forward(fld.handle, _ptr(_req(pn_block, torch.float32, "pn_block")), _ptr(o), _ptr(d),
+                                                         n, _ptr(b), S, _ptr(normals), _ptr(pred), _stream(fld.device)))
+    return normals, pred
+
+
+def normal_losses(weights: Tensor, normals: Tensor, pred: Tensor, directions: Tensor, loss_orientation: Tensor,
+                  loss_pred_normal: Tensor, orientation_mult: float = 1e-4, pred_normal_mult: float = 1e-3) -> Tensor:
+    """losses.py orientation_loss / pred_normal_loss (means over rays x multipliers): loss_* [1] +=; returns d / d pred."""
+    w = _req(weights, torch.float32, "weights")
+    g = torch.empty_like(pred)
+    with torch.cuda.device(w.device):
+        _lib.check(_lib.load().sgn_normal_losses(_ptr(w), _ptr(_req(normals, torch.float32, "normals")),
+                                                 _ptr(_req(pred, torch.float32, "pred")),
+                                                 _ptr(_req(directions.reshape(-1, 3), torch.float32, "directions")), w.shape[0],
+                                                 w.shape[1], float(orientation_mult), float(pred_normal_mult),
+                                                 _ptr(loss_orientation), _ptr(loss_pred_normal), _ptr(g), _stream(w.device)))
+    return g
+
+
+def normals_backward(fld: NerfactoFieldB200, pn_block: Tensor, origins: Tensor, directions: Tensor, ray_bins: Tensor,
+                     grad_pred: Tensor, grad_pn_block: Tensor) -> Tensor:
+    """d loss / d pred -> grad_pn_block (+=); returns d loss / d geo features [N,S,15] for `train_backward(grad_geo=...)`."""
+    o = _req(origins.reshape(-1, 3), torch.float32, "origins")
+    d = _req(directions.reshape(-1, 3), torch.float32, "directions")
+    b = _req(ray_bins, torch.float32, "ray_bins")
+    n, S = b.shape[0], b.shape[1] - 1
+    lib = _lib.load()
+    need = int(lib.sgn_train_normals_ws_bytes(n, S))
+    ws = torch.empty(max(need, 16), dtype=torch.uint8, device=fld.device)
+    ggeo = torch.empty((n, S, 15), dtype=torch.float32, device=fld.device)
+    with torch.cuda.device(fld.device):
+        _lib.check(lib.sgn_train_normals_backward(fld.handle, _ptr(_req(pn_block, torch.float32, "pn_block")), _ptr(o), _ptr(d), n,
+                                                  _ptr(b), S, _ptr(_req(grad_pred, torch.float32, "grad_pred")),
+                                                  _ptr(_req(grad_pn_block, torch.float32, "grad_pn_block")), _ptr(ggeo), _ptr(ws),
+                                                  need, _stream(fld.device)))
+    return ggeo
+
+
 class NerfactoTrainer(FieldTrainer):
     """The whole training step of `SIGNeRFModel` short of LPIPS and the normal regularisers: `get_outputs` while training
     + `get_loss_dict` (signerf/signerf.py:41-68) + Adam on `fields` and `proposal_networks` (signerf_config.py:43-50).
@@ -431,7 +514,10 @@ class NerfactoTrainer(FieldTrainer):
 
     def __init__(self, fld: NerfactoFieldB200, embedding: Optional[Tensor] = None, counts: Tuple[int, int, int] = (256, 96, 48),
                  near: float = 0.05, far: float = 1000.0, interlevel_loss_mult: float = 1.0, distortion_loss_mult: float = 0.002,
-                 **kw):
+                 pred_normals: Optional[Dict[str, Tensor]] = None, orientation_loss_mult: float = 1e-4,
+                 pred_normal_loss_mult: float = 1e-3, **kw):
+        """pred_normals: the `field.mlp_pred_normals.*` / `field.field_head_pred_normals.*` tensors of a model trained with
+        `predict_normals=True` (signerf_config.py:33) - enables the orientation / pred-normal losses of signerf.py:69-80."""
         super().__init__(fld, **kw)
         if len(fld.prop_grids) != 2:
             raise ValueError("NerfactoTrainer needs a field with its two proposal networks")
@@ -455,10 +541,18 @@ class NerfactoTrainer(FieldTrainer):
         if self.embedding is not None:
             self.grad_embedding = torch.zeros_like(self.embedding)
             self.state["embedding"] = (torch.zeros_like(self.embedding), torch.zeros_like(self.embedding))
+        self.pn = None
+        if pred_normals is not None:
+            self.pn = pack_pred_normals(pred_normals, dev)
+            self.grad_pn = torch.zeros_like(self.pn)
+            self.state["pred_normals"] = (torch.zeros_like(self.pn), torch.zeros_like(self.pn))
+        self.orientation_mult, self.pred_normal_mult = orientation_loss_mult, pred_normal_loss_mult
         self.loss_dict: Dict[str, Tensor] = {}
 
     def zero_grad(self) -> None:
         super().zero_grad()
+        if self.pn is not None:
+            self.grad_pn.zero_()
         for g in self.grad_prop_tables + self.grad_prop_mlps:
             g.zero_()
         self.grad_w_app.zero_()
@@ -491,7 +585,16 @@ class NerfactoTrainer(FieldTrainer):
             grad_rgb = grad_rgb + g_extra
             out["lpips_loss"] = extra.detach().reshape(1)
         ghb = torch.zeros_like(hb) if per_image else None
-        train_backward(fld, origins, directions, smp.euclid[2], saved, grad_rgb, self.grad_table, self.grad_mlp, g_wf, hb, ghb)
+        g_geo = None
+        if self.pn is not None:      # predict_normals: signerf.py:69-80 on the detached final weights
+            normals, pred = normals_forward(fld, self.pn, origins, directions, smp.euclid[2])
+            l_or = torch.zeros(1, dtype=torch.float32, device=dev)
+            l_pn = torch.zeros(1, dtype=torch.float32, device=dev)
+            g_pred = normal_losses(w_final, normals, pred, directions, l_or, l_pn, self.orientation_mult, self.pred_normal_mult)
+            g_geo = normals_backward(fld, self.pn, origins, directions, smp.euclid[2], g_pred, self.grad_pn)
+            out["orientation_loss"], out["pred_normal_loss"] = l_or, l_pn
+        train_backward(fld, origins, directions, smp.euclid[2], saved, grad_rgb, self.grad_table, self.grad_mlp, g_wf, hb, ghb,
+                       g_geo)
         if per_image:
             appearance_bias_backward(self.w_app, self.embedding, camera_indices.to(dev, torch.int32), ghb, self.grad_w_app,
                                      self.grad_b_head0, self.grad_embedding)
@@ -506,6 +609,10 @@ class NerfactoTrainer(FieldTrainer):
         sd = super().state_dict()
         if self.embedding is not None:
             sd["field.embedding_appearance.embedding.weight"] = self.embedding.detach().clone()
+        if self.pn is not None:
+            v = pn_block_views(self.pn)
+            for key, name in PN_NAMES.items():
+                sd[name] = (v[key][:3] if key == "bh" else v[key]).detach().clone()
         for l in range(2):
             pre, m = f"proposal_networks.{l}.mlp_base", self.prop_mlps[l]
             sd[pre + ".encoding.hash_table"] = self.prop_tables[l].detach().clone()
@@ -516,6 +623,7 @@ class NerfactoTrainer(FieldTrainer):
     def all_gradients(self):
         """Every gradient buffer of the step (for a data-parallel all-reduce)."""
         g = [self.grad_table, self.grad_mlp, self.grad_w_app, self.grad_b_head0] + self.grad_prop_tables + self.grad_prop_mlps
+        g += [self.grad_pn] if self.pn is not None else []
         return g + ([self.grad_embedding] if self.embedding is not None else [])
 
     def optimizer_step(self) -> None:
@@ -539,6 +647,10 @@ class NerfactoTrainer(FieldTrainer):
         else:
             super().optimizer_step()
         with torch.cuda.device(dev):
+            if self.pn is not None:
+                m, v = self.state["pred_normals"]
+                _lib.check(lib.sgn_adam_step(_ptr(self.pn), _ptr(self.grad_pn), _ptr(m), _ptr(v), self.pn.numel() - 1, self.lr,
+                                             self.betas[0], self.betas[1], self.eps, self.steps, _stream(dev)))
             for l in range(2):
                 for key, param, grad in ((f"prop_table{l}", self.prop_tables[l], self.grad_prop_tables[l]),
                                          (f"prop_mlp{l}", self.prop_mlps[l], self.grad_prop_mlps[l])):
@@ -583,7 +695,8 @@ class FusedTrainingStep:
 
     def __init__(self, model: torch.nn.Module, counts: Tuple[int, int, int] = (256, 96, 48), near: float = 0.05, far: float = 1000.0,
                  average_init_density: float = 0.01, use_l1: bool = True, interlevel_loss_mult: float = 1.0,
-                 distortion_loss_mult: float = 0.002):
+                 distortion_loss_mult: float = 0.002, predict_normals: Optional[bool] = None,
+                 orientation_loss_mult: float = 1e-4, pred_normal_loss_mult: float = 1e-3):
         from .plugin.model import FusedNerfactoGraph
         self.model = model
         sd = dict(model.state_dict(keep_vars=True))
@@ -602,6 +715,14 @@ class FusedTrainingStep:
             names += [f"proposal_networks.{l}.mlp_base.encoding.hash_table"]
             names += [f"proposal_networks.{l}.mlp_base.mlp.layers.{i}.{p}" for i in range(2) for p in ("weight", "bias")]
         self.params: Dict[str, Tensor] = {n: find(n) for n in names}
+        # predict_normals=True (signerf_config.py:33): the prediction branch's tensors, when the model has them
+        self.pn_names = {}
+        if predict_normals is None:
+            predict_normals = any("mlp_pred_normals" in k for k in sd)
+        if predict_normals:
+            for key, n in PN_NAMES.items():
+                self.params[n] = find(n)
+                self.pn_names[key] = n
         for n, t in self.params.items():
             if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
                 raise ValueError(f"{n} must be a contiguous fp32 CUDA tensor (the kernels read the model's tensors in place)")
@@ -612,8 +733,11 @@ class FusedTrainingStep:
         self.field = graph.field
         if self.field.grid.table.data_ptr() != detached["field.mlp_base.encoding.hash_table"].data_ptr():
             raise RuntimeError("the hash table was copied: it must be usable in place")
+        pn = {n: detached[n] for n in self.pn_names.values()} if self.pn_names else None
         self.trainer = NerfactoTrainer(self.field, embedding=emb, counts=counts, near=near, far=far, use_l1=use_l1,
-                                       interlevel_loss_mult=interlevel_loss_mult, distortion_loss_mult=distortion_loss_mult)
+                                       interlevel_loss_mult=interlevel_loss_mult, distortion_loss_mult=distortion_loss_mult,
+                                       pred_normals=pn, orientation_loss_mult=orientation_loss_mult,
+                                       pred_normal_loss_mult=pred_normal_loss_mult)
         self.trainer.embedding = emb                                   # the model's table itself, not a copy
 
     def _sync_from_model(self) -> None:
@@ -634,6 +758,10 @@ class FusedTrainingStep:
             v["w_head2"].copy_(p["field.mlp_head.layers.2.weight"]), v["b_head2"][:3].copy_(p["field.mlp_head.layers.2.bias"])
             tr.app_mean = tr.embedding.mean(dim=0)
             v["b_head0"].copy_(tr.b_head0 + tr.w_app @ tr.app_mean)    # folded bias: what the eval renderer uses
+            if self.pn_names:
+                pv = pn_block_views(tr.pn)
+                for key, n in self.pn_names.items():
+                    (pv[key][:3] if key == "bh" else pv[key]).copy_(p[n])
             for l in range(2):
                 pre, m = f"proposal_networks.{l}.mlp_base.mlp.layers", tr.prop_mlps[l]
                 m[:160].copy_(p[pre + ".0.weight"].reshape(-1)), m[160:176].copy_(p[pre + ".0.bias"])
@@ -645,6 +773,10 @@ class FusedTrainingStep:
         g["field.mlp_head.layers.0.weight"] = torch.cat([g["field.mlp_head.layers.0.weight"][:, :31], tr.grad_w_app], dim=1)
         g["field.mlp_head.layers.0.bias"] = tr.grad_b_head0
         g["field.embedding_appearance.embedding.weight"] = tr.grad_embedding
+        if self.pn_names:
+            gv = pn_block_views(tr.grad_pn)
+            for key, n in self.pn_names.items():
+                g[n] = gv[key][:3] if key == "bh" else gv[key]
         for l in range(2):
             pre, m = f"proposal_networks.{l}.mlp_base", tr.grad_prop_mlps[l]
             g[pre + ".encoding.hash_table"] = tr.grad_prop_tables[l]
@@ -654,7 +786,7 @@ class FusedTrainingStep:
 
     def loss_dict(self, origins: Tensor, directions: Tensor, target_rgb: Tensor, camera_indices: Tensor,
                   jitter: Optional[Tensor] = None, extra_loss: Optional[Callable[[Tensor], Tensor]] = None) -> Dict[str, Tensor]:
-        """One batch -> {"rgb_loss", "interlevel_loss", "distortion_loss" (, "lpips_loss")}.  `sum(values).backward()` leaves
+        """One batch -> {"rgb_loss", "interlevel_loss", "distortion_loss" (, "orientation_loss", "pred_normal_loss", "lpips_loss")}.  `sum(values).backward()` leaves
         the step's gradients in the model's parameters; the individual entries carry the reference's values (only
         "rgb_loss" holds the autograd node, for the sum of all terms)."""
         self._sync_from_model()

@@ -418,3 +418,91 @@ def test_pipeline_get_train_loss_dict_routes_through_the_fused_step():
     sum(loss_dict.values()).backward()
     assert all(p.grad is not None and bool(torch.isfinite(p.grad).all()) for n, p in m_gpu.named_parameters() if "scalings" not in n)
     assert float(m_gpu.field.encoding.hash_table.grad.abs().max()) > 0 and float(m_gpu.proposal_networks[1].encoding.hash_table.grad.abs().max()) > 0
+
+
+@pytest.mark.gpu
+def test_predict_normals_losses_and_gradients_match_autograd():
+    """predict_normals=True (signerf_config.py:33): analytic normals (closed-form gradient of the density logit through the
+    hash grid and the base MLP, no graph), predicted normals, orientation / pred-normal losses (signerf.py:69-80) and the
+    gradients they add - into the prediction MLP + head and, through the geo features, the base MLP and the hash table."""
+    from tests.helpers import field_from_oracle, ring_cameras
+    m = R.make_model(3, dense=True, table_scale=0.5, density_gain=20.0, log2_hashmap_size=14, num_proposal_samples=(64, 32),
+                     num_nerf_samples=16, predict_normals=True)
+    m.train()
+    fld = field_from_oracle(m, with_proposals=True)
+    _, _, o, d, target, jitter, cams = _setup_full(n_rays=128)
+    pn = {k: v for k, v in m.state_dict().items() if "pred_normals" in k}
+    tr = T.NerfactoTrainer(fld, embedding=m.field.embedding_appearance.weight, counts=(64, 32, 16), near=m.near, far=m.far,
+                           pred_normals=pn, pred_normal_loss_mult=1.0, orientation_loss_mult=1.0)     # weighted up: visible in the sums
+    oc, dc = o.cuda(), d.cuda()
+    ours = tr.forward_backward(oc, dc, target.cuda(), jitter.cuda(), cams.cuda())
+    torch.cuda.synchronize()
+    smp = T.train_sample(fld, oc, dc, (64, 32, 16), m.near, m.far, jitter.cuda())
+    fixed = [R.samples_from_edges(smp.spacing[l].cpu(), smp.euclid[l].cpu()) for l in range(3)]
+    out = R.forward_train(m, o, d, jitter, cams, fixed_samples=fixed)
+    ld = R.signerf_loss_dict(out, target, orientation_loss_mult=1.0, pred_normal_loss_mult=1.0)
+    sum(ld.values()).backward()
+    normals, pred = T.normals_forward(fld, tr.pn, oc, dc, smp.euclid[2])
+    # analytic normals are a normalised gradient: compare where the gradient is not degenerate
+    cosn = (normals.cpu() * out["normals"]).sum(-1)
+    print(f"analytic normals: median cos {float(cosn.median()):.6f}, fraction with cos < 0.999: {float((cosn < 0.999).float().mean()):.4f}; "
+          f"pred normals rel-L2 {rel_l2(pred, out['pred_normals'].detach()):.1e}")
+    assert float((cosn < 0.999).float().mean()) < 0.01 and rel_l2(pred, out["pred_normals"].detach()) < 1e-4
+    for k in ("rgb_loss", "interlevel_loss", "distortion_loss", "orientation_loss", "pred_normal_loss"):
+        a, b = float(ours[k]), float(ld[k].detach())
+        assert abs(a - b) < 2e-3 * max(abs(b), 1e-3), (k, a, b)
+    g = T.pn_block_views(tr.grad_pn)
+    f = m.field
+    errs = {"pn.w0": rel_l2(g["w0"], f.mlp_pred_normals.layers[0].weight.grad), "pn.b0": rel_l2(g["b0"], f.mlp_pred_normals.layers[0].bias.grad),
+            "pn.w1": rel_l2(g["w1"], f.mlp_pred_normals.layers[1].weight.grad), "pn.w2": rel_l2(g["w2"], f.mlp_pred_normals.layers[2].weight.grad),
+            "pn.b2": rel_l2(g["b2"], f.mlp_pred_normals.layers[2].bias.grad), "pn.wh": rel_l2(g["wh"], f.field_head_pred_normals.weight.grad),
+            "pn.bh": rel_l2(g["bh"][:3], f.field_head_pred_normals.bias.grad),
+            "table": rel_l2(tr.grad_table, f.encoding.hash_table.grad),
+            "w_base1": rel_l2(T.mlp_block_views(tr.grad_mlp)["w_base1"], f.mlp_base.layers[1].weight.grad),
+            "w_base0": rel_l2(T.mlp_block_views(tr.grad_mlp)["w_base0"], f.mlp_base.layers[0].weight.grad)}
+    print("gradient rel-L2 with predict_normals:", {k: f"{v:.1e}" for k, v in errs.items()})
+    assert max(errs.values()) < 2e-3, errs
+    before = tr.pn.clone()
+    tr.optimizer_step()
+    assert not torch.equal(before, tr.pn) and "field.field_head_pred_normals.net.weight" in tr.state_dict()
+
+
+@pytest.mark.gpu
+def test_fused_training_step_with_predict_normals_on_the_models_parameters():
+    """The reference's default model (`predict_normals=True`): FusedTrainingStep picks up `field.mlp_pred_normals.*` /
+    `field.field_head_pred_normals.net.*`, returns the five loss terms of signerf.py:62-80 and leaves gradients in those
+    tensors as well."""
+    import copy
+    from tests.test_plugin_parity import _ContractOnlyModel
+    m_cpu = R.make_model(3, dense=True, table_scale=0.5, density_gain=20.0, log2_hashmap_size=14, num_proposal_samples=(64, 32),
+                         num_nerf_samples=16, predict_normals=True)
+    m_cpu.train()
+    m_gpu = copy.deepcopy(m_cpu).cuda()
+
+    class _Model(_ContractOnlyModel):
+        def state_dict(self, *a, **k):
+            sd = super().state_dict()
+            for i, l in enumerate(self.field.mlp_pred_normals.layers):
+                sd[f"field.mlp_pred_normals.layers.{i}.weight"], sd[f"field.mlp_pred_normals.layers.{i}.bias"] = l.weight, l.bias
+            sd["field.field_head_pred_normals.net.weight"] = self.field.field_head_pred_normals.weight
+            sd["field.field_head_pred_normals.net.bias"] = self.field.field_head_pred_normals.bias
+            return sd
+
+    step = T.FusedTrainingStep(_Model(m_gpu), counts=(64, 32, 16), near=m_cpu.near, far=m_cpu.far,
+                               average_init_density=m_cpu.field.average_init_density)
+    assert step.trainer.pn is not None
+    _, _, o, d, target, jitter, cams = _setup_full(n_rays=128)
+    oc, dc, jc = o.cuda(), d.cuda(), jitter.cuda()
+    ld = step.loss_dict(oc, dc, target.cuda(), cams.cuda(), jc)
+    assert set(ld) == {"rgb_loss", "interlevel_loss", "distortion_loss", "orientation_loss", "pred_normal_loss"}
+    sum(ld.values()).backward()
+    smp = T.train_sample(step.field, oc, dc, (64, 32, 16), m_cpu.near, m_cpu.far, jc)
+    fixed = [R.samples_from_edges(smp.spacing[l].cpu(), smp.euclid[l].cpu()) for l in range(3)]
+    ref = R.signerf_loss_dict(R.forward_train(m_cpu, o, d, jitter, cams, fixed_samples=fixed), target)
+    sum(ref.values()).backward()
+    for k in ref:
+        assert abs(float(ld[k]) - float(ref[k].detach())) < 2e-3 * max(abs(float(ref[k].detach())), 1e-4), (k, float(ld[k]), float(ref[k]))
+    errs = {n: rel_l2(pg.grad, pc.grad) for (n, pg), (_, pc) in zip(m_gpu.named_parameters(), m_cpu.named_parameters())
+            if pc.grad is not None}
+    assert "field.mlp_pred_normals.layers.1.weight" in errs and "field.field_head_pred_normals.weight" in errs
+    assert max(errs.values()) < 1e-3, errs
