@@ -14,7 +14,9 @@ c2w, intr = ring_cameras(2, 16, 12)
 o, d, _, _ = ops.generate_rays(c2w.cuda(), intr.cuda(), 12, 16)
 o, d = o.reshape(-1, 3)[:77].contiguous(), d.reshape(-1, 3)[:77].contiguous()      # ragged: not a multiple of the warp
 g = torch.Generator().manual_seed(0)
-tr = T.NerfactoTrainer(fld, embedding=torch.randn(5, 32, generator=g), counts=(24, 12, 8), near=m.near, far=m.far)
+from signerf_b200 import synthetic
+tr = T.NerfactoTrainer(fld, embedding=torch.randn(5, 32, generator=g), counts=(24, 12, 8), near=m.near, far=m.far,
+                       pred_normals=synthetic.random_pred_normals())
 cams = torch.randint(0, 5, (77,), generator=g).cuda()
 for _ in range(2):
     out = tr.train_step(o, d, torch.rand(77, 3, generator=g).cuda(), torch.rand(3, 77, generator=g).cuda(), cams)
