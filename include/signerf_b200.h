@@ -496,13 +496,16 @@ typedef struct SgnTrainSamples {
   float* d_sigma[2];
   float* d_weights[2];
 } SgnTrainSamples;
-/* ProposalNetworkSampler.generate_ray_samples while training, _anneal = 1: d_jitter [3,N] uniform draws in [0,1) (initial
- * sampler, PDF level 1, PDF level 2; one per ray = single_jitter) or NULL for the eval bins (bin centres).  The draws are
- * inputs so that the oracle and this path sample the same bins.  d_ws: sgn_train_sample_ws_bytes bytes, 16-byte aligned. */
+/* ProposalNetworkSampler.generate_ray_samples while training: d_jitter [3,N] uniform draws in [0,1) (initial sampler, PDF
+ * level 1, PDF level 2; one per ray = single_jitter) or NULL for the eval bins (bin centres).  The draws are inputs so that
+ * the oracle and this path sample the same bins.  anneal: the proposal weights are raised to this power before each
+ * re-sampling (`use_proposal_weight_anneal`: bias(step / 1000, slope 10), 1 past the warm-up and in eval - the reference's
+ * trainer resets the step count, signerf_trainer.py:321-325, so a fine-tune starts at 0 = uniform re-sampling).
+ * d_ws: sgn_train_sample_ws_bytes bytes, 16-byte aligned. */
 int64_t sgn_train_sample_ws_bytes(int64_t N, int S0, int S1);
 int sgn_train_sample(const SgnField* f, const float* d_origins, const float* d_directions, int64_t N, int S0, int S1, int S2,
-                     float near_plane, float far_plane, const float* d_jitter, const SgnTrainSamples* out, void* d_ws,
-                     int64_t ws_bytes, void* stream);
+                     float near_plane, float far_plane, const float* d_jitter, float anneal, const SgnTrainSamples* out,
+                     void* d_ws, int64_t ws_bytes, void* stream);
 /* RaySamples.get_weights: d_euclid [N,S+1], d_sigma [N,S] -> d_weights [N,S]. */
 int sgn_weights_from_density(const float* d_euclid, const float* d_sigma, int64_t N, int S, float* d_weights, void* stream);
 /* losses.py lossfun_outer of one proposal level against the final level's histogram (weights detached), mean over

@@ -613,13 +613,14 @@ def samples_from_edges(spacing: Tensor, euclid: Tensor) -> SamplesRef:
 
 def forward_train(model: NerfactoRef, rays_o: Tensor, rays_d: Tensor, jitter: Optional[Tensor] = None,
                   camera_indices: Optional[Tensor] = None, update_proposals: bool = True,
-                  fixed_samples: Optional[List[SamplesRef]] = None) -> Dict[str, object]:
+                  fixed_samples: Optional[List[SamplesRef]] = None, anneal: float = 1.0) -> Dict[str, object]:
     """NerfactoModel.get_outputs WHILE TRAINING (models/nerfacto.py get_outputs + ProposalNetworkSampler.generate_ray_samples
     with _anneal = 1, i.e. past proposal_weights_anneal_max_num_iters, as a fine-tune of a trained scene is): stratified
     initial bins, two proposal levels with PDF re-sampling, the main field on the last level, autograd on.
     jitter [3, N] = the three per-ray draws (initial sampler, PDF level 1, PDF level 2); None = bin centres (eval bins).
     camera_indices [N]: per-ray rows of the appearance embedding (training semantics); None = the mean (eval semantics).
     update_proposals False = a step between two proposal updates (`proposal_update_every`): densities under no_grad.
+    anneal: ProposalNetworkSampler._anneal, `annealed_weights = torch.pow(weights, self._anneal)` in front of each PDF sampler.
     fixed_samples: the three levels' bins handed in instead of sampled (gradient checks on identical sample positions:
     the samplers carry no gradient, but a 1e-6 shift of a bin edge moves a sample across cells of the finest hash levels)."""
     n = rays_o.shape[0]
@@ -646,7 +647,7 @@ def forward_train(model: NerfactoRef, rays_o: Tensor, rays_d: Tensor, jitter: Op
         if fixed_samples is not None:
             samples = fixed_samples[i + 1]
         else:
-            samples = pdf_resample(samples, w.detach(), counts[i + 1], to_euclid, jitter=jit(i + 1))
+            samples = pdf_resample(samples, torch.pow(w.detach(), anneal), counts[i + 1], to_euclid, jitter=jit(i + 1))
     positions = positions_of(rays_o, rays_d, samples)
     normals = pred_normals = None
     if getattr(model.field, "use_pred_normals", False):

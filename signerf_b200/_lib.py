@@ -97,7 +97,7 @@ SIGNATURES = {
     "sgn_prop_param_count": (_i64, []),
     "sgn_field_prop_params": (_i, [_vp, _i, C.POINTER(_vp)]),
     "sgn_train_sample_ws_bytes": (_i64, [_i64, _i, _i]),
-    "sgn_train_sample": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _f, _f, _vp, C.POINTER(SgnTrainSamples), _vp, _i64, _vp]),
+    "sgn_train_sample": (_i, [_vp, _vp, _vp, _i64, _i, _i, _i, _f, _f, _vp, _f, C.POINTER(SgnTrainSamples), _vp, _i64, _vp]),
     "sgn_weights_from_density": (_i, [_vp, _vp, _i64, _i, _vp, _vp]),
     "sgn_interlevel_loss": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i64, _f, _vp, _vp, _vp, _i64, _vp]),
     "sgn_distortion_loss": (_i, [_vp, _vp, _i64, _i, _f, _vp, _vp, _vp]),

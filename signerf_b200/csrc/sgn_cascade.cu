@@ -121,6 +121,7 @@ struct PdfParams {
   int spacing_per_ray;
   const float* u;             // [nb] sample positions in cdf space
   const float* jitter;        // training (PDFSampler.train_stratified, single_jitter): [rays] draws, u_j + draw / nb; else null
+  float anneal;               // ProposalNetworkSampler: weights ** anneal before the re-sampling (1 in eval and past the warm-up)
   float* cdf_scratch;         // [rays][S+1]
   float* spacing_out;         // [rays][nb]
   float* euclid_out;          // [rays][nb]
@@ -154,15 +155,17 @@ __global__ void k_pdf_resample(const __grid_constant__ PdfParams p) {
       tile_xy(p.src, tx, ty, lane, x, y);
       if (x < p.W && y < p.H) out_ray = ((int64_t)v * p.H + y) * p.W + x;
     }
+    const bool ann = p.anneal != 1.f;
+    auto wt = [&](int i) -> float { const float v = w[at(p.S, i)]; return ann ? powf(v, p.anneal) : v; };
     float sum = 0.f;
-    for (int i = 0; i < p.S; ++i) sum += __fadd_rn(w[at(p.S, i)], pad_hist);
+    for (int i = 0; i < p.S; ++i) sum += __fadd_rn(wt(i), pad_hist);
     const float padding = fmaxf(eps - sum, 0.f);
     const float padw = __fdiv_rn(padding, (float)p.S);
     sum += padding;
     float run = 0.f;
     cdf[at(p.S + 1, 0)] = 0.f;
     for (int i = 0; i < p.S; ++i) {
-      float pdf = __fdiv_rn(__fadd_rn(__fadd_rn(w[at(p.S, i)], pad_hist), padw), sum);
+      float pdf = __fdiv_rn(__fadd_rn(__fadd_rn(wt(i), pad_hist), padw), sum);
       run = __fadd_rn(run, pdf);
       cdf[at(p.S + 1, i + 1)] = fminf(1.f, run);
     }
@@ -211,11 +214,11 @@ void host_linspace01(int n, std::vector<float>& out) {
 }
 
 // One PDF re-sampling pass over per-ray spacing bins (the training sampler's entry, sgn_train_prop.cu).
-int launch_pdf_resample(const float* weights, const float* spacing_in, const float* u, const float* jitter, float* cdf_scratch,
-                        float* spacing_out, float* euclid_out, float s_near, float s_far, int64_t rays, int S, int nb,
-                        cudaStream_t st) {
+int launch_pdf_resample(const float* weights, const float* spacing_in, const float* u, const float* jitter, float anneal,
+                        float* cdf_scratch, float* spacing_out, float* euclid_out, float s_near, float s_far, int64_t rays, int S,
+                        int nb, cudaStream_t st) {
   PdfParams q;
-  q.weights = weights; q.spacing_in = spacing_in; q.spacing_per_ray = 1; q.u = u; q.jitter = jitter;
+  q.weights = weights; q.spacing_in = spacing_in; q.spacing_per_ray = 1; q.u = u; q.jitter = jitter; q.anneal = anneal;
   q.cdf_scratch = cdf_scratch; q.spacing_out = spacing_out; q.euclid_out = euclid_out;
   q.s_near = s_near; q.s_far = s_far; q.rays = rays; q.S = S; q.nb = nb; q.euclid_row_major = 0;
   k_pdf_resample<false><<<(int)std::max<int64_t>(1, std::min<int64_t>((rays + 127) / 128, (int64_t)sm_count() * 16)), 128, 0, st>>>(q);
@@ -307,7 +310,7 @@ int render_cascade(const SgnField* f, const RaySource& src, int V, int H, int W,
     k_prop_weights<false><<<pblocks, kPThreads, (S0 + 1) * 4, st>>>(pp);
     SGN_LAUNCH_CHECK();
     PdfParams q;
-    q.weights = wbuf.as<float>(); q.spacing_in = d_sp0; q.spacing_per_ray = 0; q.u = d_u1; q.jitter = nullptr;
+    q.weights = wbuf.as<float>(); q.spacing_in = d_sp0; q.spacing_per_ray = 0; q.u = d_u1; q.jitter = nullptr; q.anneal = 1.f;
     q.cdf_scratch = cdfbuf.as<float>(); q.spacing_out = sp1.as<float>(); q.euclid_out = eu1.as<float>();
     q.s_near = s_near; q.s_far = s_far; q.rays = slots; q.S = S0; q.nb = S1 + 1;
     q.euclid_row_major = 0; q.src = pp.src; q.H = H; q.W = W; q.tiles_x = pp.tiles_x; q.per_view = pp.tiles_x * pp.tiles_y;

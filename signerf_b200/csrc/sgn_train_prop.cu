@@ -16,9 +16,9 @@ namespace sgn {
 
 void host_pdf_u(int nb, std::vector<float>& u);
 void host_linspace01(int n, std::vector<float>& out);
-int launch_pdf_resample(const float* weights, const float* spacing_in, const float* u, const float* jitter, float* cdf_scratch,
-                        float* spacing_out, float* euclid_out, float s_near, float s_far, int64_t rays, int S, int nb,
-                        cudaStream_t st);
+int launch_pdf_resample(const float* weights, const float* spacing_in, const float* u, const float* jitter, float anneal,
+                        float* cdf_scratch, float* spacing_out, float* euclid_out, float s_near, float s_far, int64_t rays, int S,
+                        int nb, cudaStream_t st);
 
 constexpr int kPropParams = 16 * 10 + 16 + 16 + 1;   // w0 | b0 | w1 | b1, contiguous in PropDev
 
@@ -313,11 +313,12 @@ extern "C" int64_t sgn_train_sample_ws_bytes(int64_t N, int S0, int S1) {
 }
 
 extern "C" int sgn_train_sample(const SgnField* f, const float* d_origins, const float* d_directions, int64_t N, int S0, int S1,
-                                int S2, float near_plane, float far_plane, const float* d_jitter, const SgnTrainSamples* out,
-                                void* d_ws, int64_t ws_bytes, void* stream) {
+                                int S2, float near_plane, float far_plane, const float* d_jitter, float anneal,
+                                const SgnTrainSamples* out, void* d_ws, int64_t ws_bytes, void* stream) {
   SGN_CHECK_ARG(f != nullptr && out != nullptr, "null pointer");
   SGN_CHECK_ARG(f->num_proposals == 2, "the training sampler needs a field created with 2 proposal networks");
   SGN_CHECK_ARG(N >= 0 && S0 >= 1 && S0 <= 1024 && S1 >= 1 && S1 <= 1024 && S2 >= 1 && S2 <= 1024, "bad sample counts");
+  SGN_CHECK_ARG(anneal >= 0.f && anneal <= 1.f, "anneal must be in [0, 1]");
   if (N == 0) return SGN_OK;
   SGN_CHECK_ARG(d_origins && d_directions && d_ws, "null pointer");
   for (int l = 0; l < 3; ++l) SGN_CHECK_ARG(out->d_spacing[l] && out->d_euclid[l], "null output");
@@ -359,7 +360,7 @@ extern "C" int sgn_train_sample(const SgnField* f, const float* d_origins, const
     k_weights_fwd<<<blocks_of(N, 128, 8), 128, 0, st>>>(out->d_euclid[l], out->d_sigma[l], N, S[l], out->d_weights[l]);
     SGN_LAUNCH_CHECK();
     int rc = launch_pdf_resample(out->d_weights[l], out->d_spacing[l], l ? d_u2 : d_u1, d_jitter ? d_jitter + (l + 1) * N : nullptr,
-                                 cdf, out->d_spacing[l + 1], out->d_euclid[l + 1], s_near, s_far, N, S[l], S[l + 1] + 1, st);
+                                 anneal, cdf, out->d_spacing[l + 1], out->d_euclid[l + 1], s_near, s_far, N, S[l], S[l + 1] + 1, st);
     if (rc) return rc;
   }
   return SGN_OK;

@@ -167,5 +167,5 @@ class SIGNeRFPipeline(VanillaPipeline):
             gt = patches(image.reshape(-1, 3))
             extra = lambda rgb: mult * lpips(patches(rgb), gt)                     # noqa: E731
         loss_dict = fused.loss_dict(ray_bundle.origins.reshape(-1, 3), ray_bundle.directions.reshape(-1, 3), image, cams,
-                                    extra_loss=extra)
+                                    extra_loss=extra, step=step)
         return {}, loss_dict, {"distortion": loss_dict["distortion_loss"].detach() / max(fused.trainer.distortion_mult, 1e-30)}

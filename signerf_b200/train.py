@@ -329,8 +329,9 @@ class TrainSamples:
 
 
 def train_sample(fld: NerfactoFieldB200, origins: Tensor, directions: Tensor, counts: Tuple[int, int, int] = (256, 96, 48),
-                 near: float = 0.05, far: float = 1000.0, jitter: Optional[Tensor] = None) -> TrainSamples:
-    """ProposalNetworkSampler.generate_ray_samples while training; jitter [3,N] uniform draws, None = eval bins."""
+                 near: float = 0.05, far: float = 1000.0, jitter: Optional[Tensor] = None, anneal: float = 1.0) -> TrainSamples:
+    """ProposalNetworkSampler.generate_ray_samples while training; jitter [3,N] uniform draws, None = eval bins; anneal:
+    exponent on the proposal weights before each re-sampling (`proposal_anneal`)."""
     o = _req(origins.reshape(-1, 3), torch.float32, "origins")
     d = _req(directions.reshape(-1, 3), torch.float32, "directions")
     n, dev = o.shape[0], fld.device
@@ -351,8 +352,32 @@ def train_sample(fld: NerfactoFieldB200, origins: Tensor, directions: Tensor, co
     ws = torch.empty(max(need, 16), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         _lib.check(lib.sgn_train_sample(fld.handle, _ptr(o), _ptr(d), n, S[0], S[1], S[2], float(near), float(far), _ptr(j),
-                                        C.byref(out), _ptr(ws), need, _stream(dev)))
+                                        float(anneal), C.byref(out), _ptr(ws), need, _stream(dev)))
     return TrainSamples(sp, eu, sg, w)
+
+
+def proposal_anneal(step: int, max_num_iters: int = 1000, slope: float = 10.0) -> float:
+    """[EXT] ProposalNetworkSampler.set_anneal as NerfactoModel's training callback drives it: bias(train_frac, slope) with
+    train_frac = clip(step / proposal_weights_anneal_max_num_iters, 0, 1) - 0 at step 0, 1 from max_num_iters on."""
+    x = min(max(step / max_num_iters, 0.0), 1.0)
+    return slope * x / ((slope - 1.0) * x + 1.0)
+
+
+class ProposalUpdateSchedule:
+    """[EXT] ProposalNetworkSampler.step_cb / generate_ray_samples: the proposal networks only get gradients on "update"
+    steps - `steps_since_update > update_sched(step) or step < 10`, update_sched = clamp(lerp(step / proposal_warmup, 1,
+    proposal_update_every), 1, proposal_update_every) (nerfacto: warm-up 5000, every 5)."""
+
+    def __init__(self, update_every: int = 5, warmup: int = 5000):
+        self.update_every, self.warmup, self.since = update_every, warmup, 0
+
+    def __call__(self, step: int) -> bool:
+        self.since += 1                                              # step_cb, before the forward of this step
+        sched = min(max(1.0 + (self.update_every - 1.0) * step / max(self.warmup, 1), 1.0), float(self.update_every))
+        updated = self.since > sched or step < 10
+        if updated:
+            self.since = 0
+        return updated
 
 
 def weights_from_density(euclid: Tensor, sigma: Tensor) -> Tensor:
@@ -562,12 +587,15 @@ class NerfactoTrainer(FieldTrainer):
 
     def forward_backward(self, origins: Tensor, directions: Tensor, target_rgb: Tensor, jitter: Optional[Tensor] = None,
                          camera_indices: Optional[Tensor] = None,
-                         extra_loss: Optional[Callable[[Tensor], Tensor]] = None) -> Dict[str, Tensor]:
+                         extra_loss: Optional[Callable[[Tensor], Tensor]] = None, anneal: float = 1.0,
+                         update_proposals: bool = True) -> Dict[str, Tensor]:
         """Gradients of rgb_loss + interlevel_loss + distortion_loss (+ extra_loss(rgb), the LPIPS hook) into every grad_*
-        buffer; returns the loss dict (device scalars)."""
+        buffer; returns the loss dict (device scalars).  anneal: `proposal_anneal(step)`; update_proposals False = a step
+        between two proposal updates (`ProposalUpdateSchedule`): the proposal densities carry no graph, the interlevel
+        term is reported but moves nothing."""
         fld, dev = self.field, self.field.device
         self.zero_grad()
-        smp = train_sample(fld, origins, directions, self.counts, self.near, self.far, jitter)
+        smp = train_sample(fld, origins, directions, self.counts, self.near, self.far, jitter, anneal)
         per_image = self.embedding is not None and camera_indices is not None
         hb = appearance_bias(self.w_app, self.b_head0, self.embedding, camera_indices.to(dev, torch.int32)) if per_image else None
         rgb, _, saved = train_forward(fld, origins, directions, smp.euclid[2], hb)
@@ -598,7 +626,7 @@ class NerfactoTrainer(FieldTrainer):
         if per_image:
             appearance_bias_backward(self.w_app, self.embedding, camera_indices.to(dev, torch.int32), ghb, self.grad_w_app,
                                      self.grad_b_head0, self.grad_embedding)
-        for l in range(2):
+        for l in range(2 if update_proposals else 0):
             prop_backward(fld, l, origins, directions, smp.euclid[l], smp.sigma[l], g_prop[l], self.grad_prop_tables[l],
                           self.grad_prop_mlps[l])
         self._per_image = per_image
@@ -739,6 +767,7 @@ class FusedTrainingStep:
                                        pred_normals=pn, orientation_loss_mult=orientation_loss_mult,
                                        pred_normal_loss_mult=pred_normal_loss_mult)
         self.trainer.embedding = emb                                   # the model's table itself, not a copy
+        self.update_schedule = ProposalUpdateSchedule()
 
     def _sync_from_model(self) -> None:
         """The model's current MLP tensors -> the field's parameter blocks (tables / embedding are shared storage)."""
@@ -785,14 +814,18 @@ class FusedTrainingStep:
         return g
 
     def loss_dict(self, origins: Tensor, directions: Tensor, target_rgb: Tensor, camera_indices: Tensor,
-                  jitter: Optional[Tensor] = None, extra_loss: Optional[Callable[[Tensor], Tensor]] = None) -> Dict[str, Tensor]:
+                  jitter: Optional[Tensor] = None, extra_loss: Optional[Callable[[Tensor], Tensor]] = None,
+                  step: Optional[int] = None) -> Dict[str, Tensor]:
         """One batch -> {"rgb_loss", "interlevel_loss", "distortion_loss" (, "orientation_loss", "pred_normal_loss", "lpips_loss")}.  `sum(values).backward()` leaves
         the step's gradients in the model's parameters; the individual entries carry the reference's values (only
         "rgb_loss" holds the autograd node, for the sum of all terms)."""
         self._sync_from_model()
         if jitter is None:
             jitter = torch.rand((3, origins.reshape(-1, 3).shape[0]), device=self.field.device)
-        out = self.trainer.forward_backward(origins, directions, target_rgb, jitter, camera_indices, extra_loss)
+        # step given: nerfacto's training callbacks - proposal-weight annealing and the proposal update schedule
+        anneal = proposal_anneal(step) if step is not None else 1.0
+        update = self.update_schedule(step) if step is not None else True
+        out = self.trainer.forward_backward(origins, directions, target_rgb, jitter, camera_indices, extra_loss, anneal, update)
         grads = self._gradients()
         order = list(self.params)
         others = sum(v for k, v in out.items() if k != "rgb_loss")

@@ -506,3 +506,35 @@ def test_fused_training_step_with_predict_normals_on_the_models_parameters():
             if pc.grad is not None}
     assert "field.mlp_pred_normals.layers.1.weight" in errs and "field.field_head_pred_normals.weight" in errs
     assert max(errs.values()) < 1e-3, errs
+
+
+def test_proposal_anneal_and_update_schedule_follow_nerfacto():
+    """CPU: `proposal_anneal` = bias(step / 1000, 10) and the update schedule of ProposalNetworkSampler (steps < 10 always,
+    then whenever steps_since_update exceeds lerp(step / 5000, 1, 5))."""
+    assert T.proposal_anneal(0) == 0.0 and T.proposal_anneal(1000) == 1.0 and T.proposal_anneal(5000) == 1.0
+    assert abs(T.proposal_anneal(100) - 10 * 0.1 / (9 * 0.1 + 1)) < 1e-12
+    sched = T.ProposalUpdateSchedule()
+    early = [sched(s) for s in range(12)]
+    assert all(early[:10])                                   # step < 10
+    late = T.ProposalUpdateSchedule()
+    hits = [late(s) for s in range(6000, 6030)]
+    assert sum(hits) == 5 and hits[5] and not hits[0]        # past the warm-up: every sixth step (since > 5)
+
+
+@pytest.mark.gpu
+def test_annealed_sampler_and_frozen_proposals_match_oracle():
+    """anneal < 1 (the first 1 000 steps after the reference's step-count reset): weights ** anneal in front of both PDF
+    re-samplings; update_proposals False: no gradient into the proposal networks, the main field's unchanged."""
+    m, fld, o, d, target, jitter, cams = _setup_full()
+    anneal = T.proposal_anneal(137)
+    with torch.no_grad():
+        ref = R.forward_train(m, o, d, jitter, anneal=anneal)
+    smp = T.train_sample(fld, o.cuda(), d.cuda(), (64, 32, 16), m.near, m.far, jitter.cuda(), anneal)
+    for l in range(3):          # powf (a few ulp) against torch.pow in front of the cdf: a little looser than the plain sampler's 1e-5
+        assert rel_l2(smp.spacing[l], R.sdist_of(ref["samples_list"][l])) < 5e-5, l
+    plain = T.train_sample(fld, o.cuda(), d.cuda(), (64, 32, 16), m.near, m.far, jitter.cuda())
+    assert rel_l2(plain.spacing[2], smp.spacing[2]) > 1e-3                                   # the exponent really acts
+    tr = T.NerfactoTrainer(fld, counts=(64, 32, 16), near=m.near, far=m.far)
+    out = tr.forward_backward(o.cuda(), d.cuda(), target.cuda(), jitter.cuda(), anneal=anneal, update_proposals=False)
+    assert float(out["interlevel_loss"]) > 0
+    assert all(float(g.abs().max()) == 0.0 for g in tr.grad_prop_tables + tr.grad_prop_mlps) and float(tr.grad_table.abs().max()) > 0
