@@ -17,7 +17,8 @@ import torch
 from torch import Tensor
 
 from . import ops
-from .train import FieldTrainer, NerfactoTrainer, PatchPixelSampler, PatchPixelSamplerConfig
+from .train import (FieldTrainer, NerfactoTrainer, PatchPixelSampler, PatchPixelSamplerConfig, ProposalUpdateSchedule,
+                    proposal_anneal)
 
 
 def load_generated_images(dataset_dir) -> Tuple[Tensor, Tensor, Tensor]:
@@ -48,6 +49,9 @@ class FineTuner:
         self.sampler = PatchPixelSampler(PatchPixelSamplerConfig(patch_size=patch_size, num_rays_per_batch=rays_per_batch))
         self.bins = ops.piecewise_bin_edges(num_samples, near, far).to(dev)
         self.gen = torch.Generator(device=dev).manual_seed(seed)
+        # nerfacto's step-dependent callbacks; the reference's trainer resets the step count when it switches to the generated
+        # dataset (signerf_trainer.py:321-325), so every fit() call of a fresh FineTuner starts them at step 0
+        self.step, self.schedule = 0, ProposalUpdateSchedule()
 
     def fit(self, images: Tensor, c2w: Tensor, intr: Tensor, steps: int) -> List[float]:
         """images [N,H,W,3] / cameras on the field's device.  Returns the loss of every `max(1, steps // 10)`-th step."""
@@ -67,7 +71,9 @@ class FineTuner:
             if full:
                 jitter = torch.rand((3, o.shape[0]), device=dev, generator=self.gen)
                 cams = i.to(torch.int32) if tr.embedding is not None and tr.embedding.shape[0] >= n else None
-                out = tr.forward_backward(o, d, target, jitter, cams)
+                out = tr.forward_backward(o, d, target, jitter, cams, anneal=proposal_anneal(self.step),
+                                          update_proposals=self.schedule(self.step))
+                self.step += 1
                 if world > 1:
                     grads = tr.all_gradients()
                     flat = torch.cat([g.reshape(-1) for g in grads])
