@@ -481,6 +481,14 @@ int sgn_train_normals_backward(const SgnField* f, const float* d_pn_params, cons
                                int64_t N, const float* d_ray_bins, int S, const float* d_grad_pred, float* d_grad_pn_params,
                                float* d_grad_geo, void* d_ws, int64_t ws_bytes, void* stream);
 
+/* The three calls above in ONE pass over the samples (what the trainer uses): analytic normals, both loss terms
+ * (d_loss_* [1] +=) and the backward of the prediction branch from the detached weights d_weights [N,S] - the separate
+ * forward and loss kernels would gather and run the base MLP a second time. */
+int sgn_train_normals_step(const SgnField* f, const float* d_pn_params, const float* d_origins, const float* d_directions,
+                           int64_t N, const float* d_ray_bins, int S, const float* d_weights, float orientation_mult,
+                           float pred_normal_mult, float* d_loss_orientation, float* d_loss_pred_normal,
+                           float* d_grad_pn_params, float* d_grad_geo, void* d_ws, int64_t ws_bytes, void* stream);
+
 /* --- the proposal half of the training step ([EXT] nerfstudio ProposalNetworkSampler in training mode, losses.py
  * interlevel_loss / distortion_loss as signerf/signerf.py:62-68 adds them to the loss dict) ---
  * A proposal network's trainable parameters: its 5-level hash table (the caller's SgnHashGrid.d_table) and

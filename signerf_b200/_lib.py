@@ -92,6 +92,7 @@ SIGNATURES = {
     "sgn_normal_losses": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _f, _f, _vp, _vp, _vp, _vp]),
     "sgn_train_normals_ws_bytes": (_i64, [_i64, _i]),
     "sgn_train_normals_backward": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _i, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "sgn_train_normals_step": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _i, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "sgn_appearance_bias": (_i, [_vp, _vp, _vp, _i, _vp, _i64, _vp, _vp]),
     "sgn_appearance_bias_backward": (_i, [_vp, _vp, _i, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "sgn_prop_param_count": (_i64, []),

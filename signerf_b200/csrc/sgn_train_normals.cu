@@ -266,13 +266,20 @@ struct NormalsBwd {
   const MlpF32* w32;
   const PnParams* pn;
   NormalRays rays;
-  const float* gpred;   // [N,S,3]
+  const float* gpred;   // [N,S,3], or null in the fused step (then derived from the weights and the analytic normals)
+  // fused step (sgn_train_normals_step): the analytic normals, both loss terms and d loss / d pred are evaluated here, in
+  // the same pass as the backward - the separate forward + loss kernels gather and run the base MLP a second time
+  const float* weights; // [N,S] detached final weights, or null
+  float s_orient, s_pn; // multipliers / N
+  float* loss_orient;
+  float* loss_pn;
   float* ggeo;          // [N,S,15] out: d loss / d geo features
   float* acts;          // [kPnActs][cap]
   float* deltas;        // [kPnDeltas][cap]
   int64_t first, count, cap;
 };
 
+template <bool kFused>
 __global__ void __launch_bounds__(kNThreads) k_normals_bwd(const __grid_constant__ NormalsBwd p) {
   extern __shared__ __align__(16) unsigned char smem[];
   PnParams* w = reinterpret_cast<PnParams*>(smem);
@@ -281,6 +288,7 @@ __global__ void __launch_bounds__(kNThreads) k_normals_bwd(const __grid_constant
   load_base(p.w32, sb);
   __syncthreads();
   const NormalRays& r = p.rays;
+  float lo = 0.f, lp = 0.f;   // fused: this thread's share of the two loss terms
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < p.count; e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t s = p.first + e;
     const int64_t ray = s / r.S;
@@ -296,10 +304,19 @@ __global__ void __launch_bounds__(kNThreads) k_normals_bwd(const __grid_constant
     float raw[3], px, py, pz;
     raw_and_contracted(r, ray, (int)(s - ray * r.S), raw, px, py, pz);
     float inp[27];
+    float nrm[3] = {0.f, 0.f, 0.f};   // fused: analytic normal
     {
       float feat[32], out1[16];
       encode_all(p.grid, px, py, pz, feat);
-      base_mlp<false>(sb, feat, out1, nullptr);
+      if (kFused) {
+        float gfeat[32], gp[3];
+        base_mlp<true>(sb, feat, out1, gfeat);
+        position_gradient(p.grid, px, py, pz, gfeat, gp);
+        const float gn = fmaxf(sqrtf(gp[0] * gp[0] + gp[1] * gp[1] + gp[2] * gp[2]), 1e-12f);
+        nrm[0] = -gp[0] / gn, nrm[1] = -gp[1] / gn, nrm[2] = -gp[2] / gn;
+      } else {
+        base_mlp<false>(sb, feat, out1, nullptr);
+      }
       nerf_enc12(raw, inp);
 #pragma unroll
       for (int j = 0; j < 15; ++j) inp[12 + j] = out1[1 + j];
@@ -327,8 +344,17 @@ __global__ void __launch_bounds__(kNThreads) k_normals_bwd(const __grid_constant
     for (int c = 0; c < 3; ++c) t[c] = tanhf(w->bh[c] + pn_dot4<64>(w->wh + c * 64, x));
     // backward: pred = t / |t| -> tanh -> head -> x3 -> l1 -> l0 -> inp
     const float tn = fmaxf(sqrtf(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]), 1e-12f);
-    const float g[3] = {p.gpred[3 * s], p.gpred[3 * s + 1], p.gpred[3 * s + 2]};
     const float ph[3] = {t[0] / tn, t[1] / tn, t[2] / tn};
+    float g[3];
+    if (kFused) {   // losses.py orientation_loss / pred_normal_loss on the detached weights; d pn / d pred = -w n
+      const float wi = p.weights[s];
+      const float ndv = fminf(0.f, -(nrm[0] * __ldg(r.dirs + 3 * ray) + nrm[1] * __ldg(r.dirs + 3 * ray + 1) + nrm[2] * __ldg(r.dirs + 3 * ray + 2)));
+      lo += wi * ndv * ndv;
+      lp += wi * (1.f - (nrm[0] * ph[0] + nrm[1] * ph[1] + nrm[2] * ph[2]));
+      g[0] = -p.s_pn * wi * nrm[0], g[1] = -p.s_pn * wi * nrm[1], g[2] = -p.s_pn * wi * nrm[2];
+    } else {
+      g[0] = p.gpred[3 * s], g[1] = p.gpred[3 * s + 1], g[2] = p.gpred[3 * s + 2];
+    }
     const float pg = ph[0] * g[0] + ph[1] * g[1] + ph[2] * g[2];
     float gh[3];
 #pragma unroll
@@ -375,6 +401,21 @@ __global__ void __launch_bounds__(kNThreads) k_normals_bwd(const __grid_constant
     for (int j = 0; j < 15; ++j) p.ggeo[15 * s + j] = gi[j];
 #undef PN_AT
   }
+  if (kFused) {   // block sums of the two loss terms (reported scalars: the order of the atomics is not fixed)
+    __shared__ float red[2][kNThreads / 32];
+    for (int o = 16; o > 0; o >>= 1) {
+      lo += __shfl_xor_sync(0xffffffffu, lo, o);
+      lp += __shfl_xor_sync(0xffffffffu, lp, o);
+    }
+    if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = lo, red[1][threadIdx.x >> 5] = lp;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float a = 0.f, b = 0.f;
+      for (int i = 0; i < kNThreads / 32; ++i) a += red[0][i], b += red[1][i];
+      if (a != 0.f) atomicAdd(p.loss_orient, a * p.s_orient);
+      if (b != 0.f) atomicAdd(p.loss_pn, b * p.s_pn);
+    }
+  }
 }
 
 static int blocks_n(int64_t n, int threads, int per_sm) {
@@ -408,7 +449,6 @@ extern "C" int sgn_train_normals_forward(const SgnField* f, const float* d_pn_pa
   static bool attr = false;
   if (!attr) {
     SGN_CUDA(cudaFuncSetAttribute(k_normals_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNormSmemFwd));
-    SGN_CUDA(cudaFuncSetAttribute(k_normals_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNormSmemBwd));
     attr = true;
   }
   NormalsFwd p;
@@ -439,20 +479,24 @@ extern "C" int64_t sgn_train_normals_ws_bytes(int64_t N, int S) {
   return std::min(N * S, kNormChunk) * (kPnActs + kPnDeltas) * (int64_t)sizeof(float) + 256;
 }
 
-extern "C" int sgn_train_normals_backward(const SgnField* f, const float* d_pn_params, const float* d_origins,
-                                          const float* d_directions, int64_t N, const float* d_ray_bins, int S,
-                                          const float* d_grad_pred, float* d_grad_pn_params, float* d_grad_geo, void* d_ws,
-                                          int64_t ws_bytes, void* stream) {
+static int normals_backward_impl(const SgnField* f, const float* d_pn_params, const float* d_origins, const float* d_directions,
+                                 int64_t N, const float* d_ray_bins, int S, const float* d_grad_pred, const float* d_weights,
+                                 float orientation_mult, float pred_normal_mult, float* d_loss_orientation,
+                                 float* d_loss_pred_normal, float* d_grad_pn_params, float* d_grad_geo, void* d_ws,
+                                 int64_t ws_bytes, void* stream) {
   int rc = check_normals_args(f, d_pn_params, d_origins, d_directions, N, d_ray_bins, S);
   if (rc) return rc;
   if (N == 0) return SGN_OK;
-  SGN_CHECK_ARG(d_grad_pred && d_grad_pn_params && d_grad_geo && d_ws, "null pointer");
+  const bool fused = d_grad_pred == nullptr;
+  SGN_CHECK_ARG(d_grad_pn_params && d_grad_geo && d_ws, "null pointer");
+  SGN_CHECK_ARG(!fused || (d_weights && d_loss_orientation && d_loss_pred_normal), "null pointer");
   SGN_CHECK_ARG(ws_bytes >= sgn_train_normals_ws_bytes(N, S) && (reinterpret_cast<uintptr_t>(d_ws) & 15) == 0,
                 "workspace smaller than sgn_train_normals_ws_bytes or misaligned");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   static bool attr = false;
   if (!attr) {
-    SGN_CUDA(cudaFuncSetAttribute(k_normals_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNormSmemBwd));
+    SGN_CUDA(cudaFuncSetAttribute(k_normals_bwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNormSmemBwd));
+    SGN_CUDA(cudaFuncSetAttribute(k_normals_bwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNormSmemBwd));
     attr = true;
   }
   const int64_t samples = N * S, cap = std::min(samples, kNormChunk);
@@ -463,9 +507,12 @@ extern "C" int sgn_train_normals_backward(const SgnField* f, const float* d_pn_p
     NormalsBwd p;
     p.grid = f->grid, p.w32 = f->d_f32, p.pn = reinterpret_cast<const PnParams*>(d_pn_params);
     p.rays = NormalRays{d_origins, d_directions, d_ray_bins, N, S};
-    p.gpred = d_grad_pred, p.ggeo = d_grad_geo, p.acts = acts, p.deltas = deltas;
+    p.gpred = d_grad_pred, p.weights = d_weights, p.s_orient = orientation_mult / (float)N, p.s_pn = pred_normal_mult / (float)N;
+    p.loss_orient = d_loss_orientation, p.loss_pn = d_loss_pred_normal;
+    p.ggeo = d_grad_geo, p.acts = acts, p.deltas = deltas;
     p.first = first, p.count = std::min(kNormChunk, samples - first), p.cap = cap;
-    k_normals_bwd<<<blocks_n(p.count, kNThreads, 8), kNThreads, kNormSmemBwd, st>>>(p);
+    if (fused) k_normals_bwd<true><<<blocks_n(p.count, kNThreads, 8), kNThreads, kNormSmemBwd, st>>>(p);
+    else k_normals_bwd<false><<<blocks_n(p.count, kNThreads, 8), kNThreads, kNormSmemBwd, st>>>(p);
     SGN_LAUNCH_CHECK();
     OuterParams op;
     //             deltas (offset, N)  activations (offset, K)  ld
@@ -475,6 +522,26 @@ extern "C" int sgn_train_normals_backward(const SgnField* f, const float* d_pn_p
     op.layer[3] = {192, 3, 155, 64, 64, G->wh, G->bh};
     op.layer[4] = op.layer[3];
     launch_outer_reduce(deltas, acts, op, 4, p.count, cap, st);
+    SGN_LAUNCH_CHECK();
   }
   return SGN_OK;
+}
+
+extern "C" int sgn_train_normals_backward(const SgnField* f, const float* d_pn_params, const float* d_origins,
+                                          const float* d_directions, int64_t N, const float* d_ray_bins, int S,
+                                          const float* d_grad_pred, float* d_grad_pn_params, float* d_grad_geo, void* d_ws,
+                                          int64_t ws_bytes, void* stream) {
+  SGN_CHECK_ARG(N == 0 || d_grad_pred != nullptr, "null gradient");
+  return normals_backward_impl(f, d_pn_params, d_origins, d_directions, N, d_ray_bins, S, d_grad_pred, nullptr, 0.f, 0.f, nullptr,
+                               nullptr, d_grad_pn_params, d_grad_geo, d_ws, ws_bytes, stream);
+}
+
+extern "C" int sgn_train_normals_step(const SgnField* f, const float* d_pn_params, const float* d_origins, const float* d_directions,
+                                      int64_t N, const float* d_ray_bins, int S, const float* d_weights, float orientation_mult,
+                                      float pred_normal_mult, float* d_loss_orientation, float* d_loss_pred_normal,
+                                      float* d_grad_pn_params, float* d_grad_geo, void* d_ws, int64_t ws_bytes, void* stream) {
+  SGN_CHECK_ARG(N == 0 || d_weights != nullptr, "null weights");
+  return normals_backward_impl(f, d_pn_params, d_origins, d_directions, N, d_ray_bins, S, nullptr, d_weights, orientation_mult,
+                               pred_normal_mult, d_loss_orientation, d_loss_pred_normal, d_grad_pn_params, d_grad_geo, d_ws,
+                               ws_bytes, stream);
 }

@@ -531,6 +531,28 @@ def normals_backward(fld: NerfactoFieldB200, pn_block: Tensor, origins: Tensor, 
     return ggeo
 
 
+def normals_step(fld: NerfactoFieldB200, pn_block: Tensor, origins: Tensor, directions: Tensor, ray_bins: Tensor, weights: Tensor,
+                 loss_orientation: Tensor, loss_pred_normal: Tensor, grad_pn_block: Tensor, orientation_mult: float = 1e-4,
+                 pred_normal_mult: float = 1e-3) -> Tensor:
+    """normals_forward + normal_losses + normals_backward in one pass over the samples (sgn_train_normals_step): loss_* [1]
+    +=, grad_pn_block +=, returns d loss / d geo features [N,S,15]."""
+    o = _req(origins.reshape(-1, 3), torch.float32, "origins")
+    d = _req(directions.reshape(-1, 3), torch.float32, "directions")
+    b = _req(ray_bins, torch.float32, "ray_bins")
+    n, S = b.shape[0], b.shape[1] - 1
+    lib = _lib.load()
+    need = int(lib.sgn_train_normals_ws_bytes(n, S))
+    ws = torch.empty(max(need, 16), dtype=torch.uint8, device=fld.device)
+    ggeo = torch.empty((n, S, 15), dtype=torch.float32, device=fld.device)
+    with torch.cuda.device(fld.device):
+        _lib.check(lib.sgn_train_normals_step(fld.handle, _ptr(_req(pn_block, torch.float32, "pn_block")), _ptr(o), _ptr(d), n, _ptr(b), S,
+                                              _ptr(_req(weights, torch.float32, "weights")), float(orientation_mult),
+                                              float(pred_normal_mult), _ptr(loss_orientation), _ptr(loss_pred_normal),
+                                              _ptr(_req(grad_pn_block, torch.float32, "grad_pn_block")), _ptr(ggeo), _ptr(ws), need,
+                                              _stream(fld.device)))
+    return ggeo
+
+
 class NerfactoTrainer(FieldTrainer):
     """The whole training step of `SIGNeRFModel` short of LPIPS and the normal regularisers: `get_outputs` while training
     + `get_loss_dict` (signerf/signerf.py:41-68) + Adam on `fields` and `proposal_networks` (signerf_config.py:43-50).
@@ -615,11 +637,10 @@ class NerfactoTrainer(FieldTrainer):
         ghb = torch.zeros_like(hb) if per_image else None
         g_geo = None
         if self.pn is not None:      # predict_normals: signerf.py:69-80 on the detached final weights
-            normals, pred = normals_forward(fld, self.pn, origins, directions, smp.euclid[2])
             l_or = torch.zeros(1, dtype=torch.float32, device=dev)
             l_pn = torch.zeros(1, dtype=torch.float32, device=dev)
-            g_pred = normal_losses(w_final, normals, pred, directions, l_or, l_pn, self.orientation_mult, self.pred_normal_mult)
-            g_geo = normals_backward(fld, self.pn, origins, directions, smp.euclid[2], g_pred, self.grad_pn)
+            g_geo = normals_step(fld, self.pn, origins, directions, smp.euclid[2], w_final, l_or, l_pn, self.grad_pn,
+                                 self.orientation_mult, self.pred_normal_mult)
             out["orientation_loss"], out["pred_normal_loss"] = l_or, l_pn
         train_backward(fld, origins, directions, smp.euclid[2], saved, grad_rgb, self.grad_table, self.grad_mlp, g_wf, hb, ghb,
                        g_geo)

@@ -462,6 +462,15 @@ def test_predict_normals_losses_and_gradients_match_autograd():
             "w_base0": rel_l2(T.mlp_block_views(tr.grad_mlp)["w_base0"], f.mlp_base.layers[0].weight.grad)}
     print("gradient rel-L2 with predict_normals:", {k: f"{v:.1e}" for k, v in errs.items()})
     assert max(errs.values()) < 2e-3, errs
+    # the three separate entry points (forward / losses / backward) give what the fused pass gives
+    w_final = T.weights_from_density(smp.euclid[2], T.train_forward(fld, oc, dc, smp.euclid[2],
+                                     T.appearance_bias(tr.w_app, tr.b_head0, tr.embedding, cams.cuda().int()))[2][0])
+    l_or, l_pn = torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda")
+    g_pred = T.normal_losses(w_final, normals, pred, dc, l_or, l_pn, 1.0, 1.0)
+    gpn2 = torch.zeros_like(tr.grad_pn)
+    T.normals_backward(fld, tr.pn, oc, dc, smp.euclid[2], g_pred, gpn2)
+    assert rel_l2(gpn2, tr.grad_pn) < 1e-5 and abs(float(l_pn) - float(ours["pred_normal_loss"])) < 1e-5 * max(1.0, abs(float(l_pn)))
+    assert abs(float(l_or) - float(ours["orientation_loss"])) < 1e-5 * max(1.0, abs(float(l_or)))
     before = tr.pn.clone()
     tr.optimizer_step()
     assert not torch.equal(before, tr.pn) and "field.field_head_pred_normals.net.weight" in tr.state_dict()
